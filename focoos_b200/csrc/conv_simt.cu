@@ -1,0 +1,269 @@
+// SIMT (CUDA-core, fp32 accumulate) convolution kernels:
+//   * fb200_stem_conv3x3s2 — normalise + 3x3/s2 conv + BN + act straight from the NCHW fp32 image.
+//   * conv_igemm_simt      — generic implicit-GEMM conv / linear with fused scale/bias/residual/act
+//                            epilogue.  This is the fp32 parity path and the fall-back for shapes the
+//                            tcgen05 kernel (conv_tc.cu) does not take (Cin % 64 != 0, fp32 activations).
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace fb200 {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ------------------------------------------------------------------------------------------------
+// stem: one thread = one output pixel x CO_PER_THREAD channels. Input NCHW fp32 raw.
+// ------------------------------------------------------------------------------------------------
+template <typename TOut, int COUT>
+__global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict__ img, int B, int H, int W,
+                                                        const float* __restrict__ w, const float* __restrict__ scale,
+                                                        const float* __restrict__ bias, float m0, float m1, float m2,
+                                                        float s0, float s1, float s2, int act, TOut* __restrict__ out) {
+  __shared__ float ws[27 * COUT];  // [tap*3+ci][co]
+  __shared__ float sc[COUT], bi[COUT];
+  for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) {
+    int co = i % COUT, t = i / COUT;  // t = (kh*3+kw)*3+ci ; w layout [co][kh][kw][ci]
+    ws[i] = w[co * 27 + t];
+  }
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) {
+    sc[i] = scale ? scale[i] : 1.f;
+    bi[i] = bias ? bias[i] : 0.f;
+  }
+  __syncthreads();
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const int64_t total = (int64_t)B * Ho * Wo;
+  const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= total) return;
+  const int wo = pix % Wo, ho = (pix / Wo) % Ho, b = pix / ((int64_t)Wo * Ho);
+  const float mean[3] = {m0, m1, m2}, stdv[3] = {s0, s1, s2};
+  float acc[COUT];
+#pragma unroll
+  for (int i = 0; i < COUT; ++i) acc[i] = 0.f;
+  const float* ib = img + (int64_t)b * 3 * H * W;
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh) {
+    const int hi = ho * 2 - 1 + kh;
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const int wi = wo * 2 - 1 + kw;
+      const bool ok = hi >= 0 && hi < H && wi >= 0 && wi < W;
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        // same arithmetic as the reference: (x - mean) / std, then the conv sees 0 outside the image
+        const float v = ok ? (ib[((int64_t)ci * H + hi) * W + wi] - mean[ci]) / stdv[ci] : 0.f;
+        const float* wr = &ws[((kh * 3 + kw) * 3 + ci) * COUT];
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[co] = fmaf(v, wr[co], acc[co]);
+      }
+    }
+  }
+  TOut* o = out + pix * COUT;
+#pragma unroll
+  for (int co = 0; co < COUT; co += 4) {
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = apply_act(acc[co + j] * sc[co + j] + bi[co + j], act);
+    store4(o + co, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic implicit GEMM.  M = B*Ho*Wo, N = Cout, K = KH*KW*Cin (k = (kh*KW+kw)*Cin + c).
+// 64x64x16 tile, 256 threads, 4x4 micro-tile, register-prefetch double buffering.
+// Requirements: Cin % 4 == 0, pitches % 4 == 0 (vector loads along the channel axis).
+// ------------------------------------------------------------------------------------------------
+
+constexpr int BM = 64, BN = 64, BK = 16, PADS = 4;
+
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256) conv_igemm_simt(const ConvParams p) {
+  __shared__ __align__(16) float As[2][BK][BM + PADS];
+  __shared__ __align__(16) float Bs[2][BK][BN + PADS];
+  const TIn* __restrict__ x = reinterpret_cast<const TIn*>(p.x);
+  const TIn* __restrict__ w = reinterpret_cast<const TIn*>(p.w);
+  const int tid = threadIdx.x;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  // loader mapping: row = tid/4 (0..63), kq = (tid%4)*4
+  const int lrow = tid >> 2, lkq = (tid & 3) * 4;
+  const int64_t am = m0 + lrow;
+  const bool a_row_ok = am < p.M;
+  int ab = 0, aho = 0, awo = 0;
+  if (a_row_ok) {
+    awo = am % p.Wo;
+    aho = (am / p.Wo) % p.Ho;
+    ab = am / ((int64_t)p.Wo * p.Ho);
+  }
+  const int bn = n0 + lrow;
+  const bool b_row_ok = bn < p.Cout;
+  const TIn* wrow = w + (int64_t)bn * p.K;
+
+  float ra[4], rb[4];
+  auto fetch = [&](int kt) {
+    const int k = kt * BK + lkq;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { ra[j] = 0.f; rb[j] = 0.f; }
+    if (k < p.K) {
+      if (a_row_ok) {
+        const int tap = k / p.Cin, c = k - tap * p.Cin;
+        const int kh = tap / p.KW, kw = tap - kh * p.KW;
+        const int hi = aho * p.stride - p.pad + kh, wi = awo * p.stride - p.pad + kw;
+        if (hi >= 0 && hi < p.H && wi >= 0 && wi < p.W)
+          load4(x + (((int64_t)ab * p.H + hi) * p.W + wi) * p.x_pitch + c, ra);
+      }
+      if (b_row_ok) load4(wrow + k, rb);
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      As[buf][lkq + j][lrow] = ra[j];
+      Bs[buf][lkq + j][lrow] = rb[j];
+    }
+  };
+
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int KT = (p.K + BK - 1) / BK;
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  for (int kt = 0; kt < KT; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < KT) fetch(kt + 1);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < KT) stash(buf ^ 1);
+    __syncthreads();
+  }
+
+  // epilogue
+  const int n = n0 + tx * 4;
+  if (n >= p.Cout) return;
+  float sc[4], bi[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const bool ok = n + j < p.Cout;
+    sc[j] = (p.scale && ok) ? p.scale[n + j] : 1.f;
+    bi[j] = (p.bias && ok) ? p.bias[n + j] : 0.f;
+  }
+  TOut* out = reinterpret_cast<TOut*>(p.out);
+  const TOut* res = reinterpret_cast<const TOut*>(p.res);
+  const bool full = (n + 3 < p.Cout) && p.vec_ok;
+  const bool post = (p.act & FB200_ACT_RESIDUAL_AFTER) != 0;
+  const int64_t hw = (int64_t)p.Ho * p.Wo;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+    if (m >= p.M) continue;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = acc[i][j] * sc[j] + bi[j];
+    const int64_t img = m / hw, o_off = img * p.out_bs + (m - img * hw) * p.out_pitch + n;
+    if (full) {
+      float r[4] = {0.f, 0.f, 0.f, 0.f};
+      if (res) load4(res + m * p.res_pitch + n, r);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = post ? apply_act(v[j], p.act) + r[j] : apply_act(v[j] + r[j], p.act);
+      store4(out + o_off, v);
+    } else {
+      for (int j = 0; j < 4 && n + j < p.Cout; ++j) {
+        const float r = res ? to_f(res[m * p.res_pitch + n + j]) : 0.f;
+        out[o_off + j] = from_f<TOut>(post ? apply_act(v[j], p.act) + r : apply_act(v[j] + r, p.act));
+      }
+    }
+  }
+}
+
+int conv2d_simt(const ConvParams& p, int x_dtype, int out_dtype, cudaStream_t st) {
+  FB_CHECK_ARG(p.Cin % 4 == 0 && p.x_pitch % 4 == 0, "conv2d(simt): Cin (%d) and x_pitch (%d) must be multiples of 4", p.Cin, p.x_pitch);
+  dim3 grid((unsigned)cdiv(p.M, BM), (unsigned)cdiv(p.Cout, BN));
+  if (x_dtype == FB200_F32 && out_dtype == FB200_F32) conv_igemm_simt<float, float><<<grid, 256, 0, st>>>(p);
+  else if (x_dtype == FB200_F16 && out_dtype == FB200_F16) conv_igemm_simt<__half, __half><<<grid, 256, 0, st>>>(p);
+  else if (x_dtype == FB200_F16 && out_dtype == FB200_F32) conv_igemm_simt<__half, float><<<grid, 256, 0, st>>>(p);
+  else if (x_dtype == FB200_F32 && out_dtype == FB200_F16) conv_igemm_simt<float, __half><<<grid, 256, 0, st>>>(p);
+  else { set_error("conv2d: bad dtypes %d/%d", x_dtype, out_dtype); return FB200_ERR_INVALID; }
+  FB_CHECK_LAUNCH("conv_igemm_simt");
+  return FB200_OK;
+}
+
+int conv2d_tc(const ConvParams& p, cudaStream_t st);          // conv_tc.cu
+bool conv2d_tc_supported(const ConvParams& p, int x_dtype, int out_dtype);
+
+}  // namespace fb200
+
+using namespace fb200;
+
+extern "C" const char* fb200_last_error(void) { return fb200::g_err; }
+extern "C" int fb200_version(void) { return 100; }
+extern "C" int fb200_device_supports_tcgen05(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return FB200_ERR_CUDA;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return FB200_ERR_CUDA;
+  return major == 10 ? 1 : 0;
+}
+
+extern "C" int fb200_stem_conv3x3s2(const float* img, int B, int H, int W, const float* w, const float* scale,
+                                    const float* bias, const float* mean3, const float* std3, int act, void* out,
+                                    int out_dtype, int Cout, void* stream) {
+  FB_CHECK_ARG(img && w && out && mean3 && std3, "stem_conv: null pointer");
+  FB_CHECK_ARG(Cout == 32, "stem_conv: only Cout=32 is instantiated (got %d)", Cout);
+  FB_CHECK_ARG(B > 0 && H > 0 && W > 0, "stem_conv: bad shape");
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const int64_t total = (int64_t)B * Ho * Wo;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* m = mean3; const float* s = std3;  // HOST pointers (3 floats each)
+  if (out_dtype == FB200_F32)
+    stem_conv_kernel<float, 32><<<(unsigned)cdiv(total, 128), 128, 0, st>>>(img, B, H, W, w, scale, bias, m[0], m[1], m[2], s[0], s[1], s[2], act, (float*)out);
+  else if (out_dtype == FB200_F16)
+    stem_conv_kernel<__half, 32><<<(unsigned)cdiv(total, 128), 128, 0, st>>>(img, B, H, W, w, scale, bias, m[0], m[1], m[2], s[0], s[1], s[2], act, (__half*)out);
+  else { set_error("stem_conv: bad dtype"); return FB200_ERR_INVALID; }
+  FB_CHECK_LAUNCH("stem_conv_kernel");
+  return FB200_OK;
+}
+
+extern "C" int fb200_conv2d(const void* x, int x_dtype, int B, int H, int W, int Cin, int x_pitch, const void* w, int KH,
+                            int KW, int stride, int pad, const float* scale, const float* bias, const void* residual,
+                            int res_pitch, int act, void* out, int out_dtype, int out_pitch, int64_t out_batch_stride, int Cout,
+                            int algo, void* stream) {
+  FB_CHECK_ARG(x && w && out, "conv2d: null pointer");
+  FB_CHECK_ARG(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && stride > 0 && pad >= 0, "conv2d: bad shape");
+  FB_CHECK_ARG(x_pitch >= Cin && out_pitch >= Cout, "conv2d: pitch smaller than channel count");
+  ConvParams p;
+  p.x = x; p.w = w; p.scale = scale; p.bias = bias; p.res = residual; p.out = out;
+  p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.x_pitch = x_pitch; p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad;
+  p.Ho = (H + 2 * pad - KH) / stride + 1; p.Wo = (W + 2 * pad - KW) / stride + 1;
+  FB_CHECK_ARG(p.Ho > 0 && p.Wo > 0, "conv2d: empty output");
+  p.Cout = Cout; p.res_pitch = res_pitch; p.out_pitch = out_pitch; p.act = act;
+  p.M = (int64_t)B * p.Ho * p.Wo; p.K = KH * KW * Cin; p.x_dtype = x_dtype; p.out_dtype = out_dtype;
+  p.vec_ok = (out_pitch % 4 == 0) && (!residual || res_pitch % 4 == 0);
+  p.out_bs = out_batch_stride > 0 ? out_batch_stride : (int64_t)p.Ho * p.Wo * out_pitch;
+  p.vec_ok = p.vec_ok && (p.out_bs % 4 == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool tc_ok = conv2d_tc_supported(p, x_dtype, out_dtype);
+  if (algo == FB200_ALGO_TCGEN05 && !tc_ok) {
+    set_error("conv2d: tcgen05 path does not support this shape/dtype (Cin=%d Cout=%d k=%dx%d s=%d dtype=%d/%d)", Cin, Cout, KH, KW, stride, x_dtype, out_dtype);
+    return FB200_ERR_UNSUPPORTED;
+  }
+  if ((algo == FB200_ALGO_AUTO && tc_ok) || algo == FB200_ALGO_TCGEN05) return conv2d_tc(p, st);
+  return conv2d_simt(p, x_dtype, out_dtype, st);
+}

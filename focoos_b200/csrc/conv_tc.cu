@@ -1,0 +1,472 @@
+// tcgen05 implicit-GEMM convolution / linear for sm_100a  (fp16 operands, fp32 accumulate in TMEM).
+//
+//   D[m, n] = act( (sum_k A[m,k] * W[n,k]) * scale[n] + bias[n] + residual[m,n] )
+//   m = output pixel (b, ho, wo), n = output channel, k = (kh, kw, c).
+//
+// Design (one CTA = one 128 x BLOCK_N output tile, warp-specialised):
+//   warp 0   TMA producer.  A is never materialised as im2col: an M-tile is a BW x BH rectangle of output
+//            pixels of one image, and the A block for filter tap (kh,kw), channel chunk c0 is the SAME
+//            rectangle of the NHWC input shifted by (kh-pad, kw-pad) — one 4-D tiled TMA load whose
+//            out-of-bounds rows/columns (the conv zero padding, and ragged tile edges) are zero-filled by the
+//            TMA unit.  Stride-2 3x3 convs use a 5-D view (c', w/2, h&1, h/2, b) of the same tensor so that
+//            every tap is again a dense box.  1x1 convs and linears are the degenerate W = M, H = 1 case.
+//            Smem tiles land in the canonical K-major SWIZZLE_128B layout tcgen05 wants (128-byte rows).
+//   warp 1   MMA issuer: one elected lane issues 4 x tcgen05.mma (128 x BLOCK_N x 16) per 64-wide k-block,
+//            accumulating in TMEM; tcgen05.commit releases the smem stage / signals the epilogue.
+//   warp 2   TMEM allocator.   warp 3  stages scale/bias in smem.
+//   warps 4-7 epilogue: tcgen05.ld 32 columns at a time -> folded-BN scale/bias, residual, activation ->
+//            fp16/fp32 -> swizzled smem staging -> TMA store (clips ragged tile edges and Cout tails).
+//
+// Algorithmic bytes: A (M x K' where K' = Cin, each input pixel counted once), W, D (+ residual) once each.
+#include <cuda.h>
+
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace fb200 {
+
+
+namespace tc {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;                       // 64 halves = 128 B = one swizzle row
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
+constexpr int STAGING_BYTES = BLOCK_M * 128;      // 16 KiB: 128 rows x 128 B
+constexpr int NUM_THREADS = 256;
+
+struct KParams {
+  const float* scale; const float* bias; const void* res;
+  int res_pitch, act, Cout;
+  int KH, KW, pad, cchunks;        // cchunks = Cin / 64
+  int BW, BH, tiles_w, tiles_h;    // output tile rectangle and tile counts per image
+  int Ho, Wo;                      // output spatial size (for residual addressing / validity)
+  int x_pitch;                     // only used by the stride-2 view (c' = wp * pitch + c)
+  int stride2;                     // 0: 4-D stride-1 view, 1: 5-D stride-2 view
+  int num_k_blocks;
+};
+
+// ---------------------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > (1u << 26)) { printf("fb200 conv_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format: version 1 at bit 46, layout 2 at bits 61-63)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);   // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major) = 1
+  d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D=F32, A=B=F16, both K-major, M=128, N=BLOCK_N
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BLOCK_N> constexpr int stage_bytes() { return A_STAGE_BYTES + BLOCK_N * BLOCK_K * 2; }
+template <int BLOCK_N, int STAGES> constexpr int smem_bytes() {
+  return STAGES * stage_bytes<BLOCK_N>() + STAGING_BYTES + 2 * BLOCK_N * 4 + (2 * STAGES + 1) * 8 + 16 + 1024 /*align slack*/;
+}
+
+// ---------------------------------------------------------------------------------------------- kernel
+template <int BLOCK_N, int STAGES, typename TOut, int MIN_BLOCKS>
+__global__ void __launch_bounds__(NUM_THREADS, MIN_BLOCKS)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_d, const KParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;                                      // STAGES x 16 KiB
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;             // STAGES x BLOCK_N*128 B
+  uint8_t* staging = smem_b + STAGES * BLOCK_N * BLOCK_K * 2;  // 16 KiB
+  float* s_scale = reinterpret_cast<float*>(staging + STAGING_BYTES);
+  float* s_bias = s_scale + BLOCK_N;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_bias + BLOCK_N);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // 1-D grid, N tiles fastest so that CTAs sharing an A tile are co-scheduled (A is then read from L2)
+  const int n_tiles = (p.Cout + BLOCK_N - 1) / BLOCK_N;
+  const int n0 = (blockIdx.x % n_tiles) * BLOCK_N;
+  // M tile -> (image, tile row, tile col)
+  const int mt = blockIdx.x / n_tiles;
+  const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, img = mt / (p.tiles_w * p.tiles_h);
+  const int w0 = tw * p.BW, h0 = th * p.BH;
+  constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_d) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 3) {
+    for (int i = lane; i < BLOCK_N; i += 32) {
+      const int n = n0 + i;
+      s_scale[i] = (p.scale && n < p.Cout) ? p.scale[n] : 1.f;
+      s_bias[i] = (p.bias && n < p.Cout) ? p.bias[n] : 0.f;
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      const uint32_t a_bytes = (uint32_t)(p.BW * p.BH * BLOCK_K * 2);
+      const uint32_t tx_bytes = a_bytes + (uint32_t)(BLOCK_N * BLOCK_K * 2);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+        const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
+        const int kh = tap / p.KW, kw = tap - kh * p.KW;
+        void* dst_a = smem_a + stage * A_STAGE_BYTES;
+        if (!p.stride2) {
+          tma_load_4d(&tmap_a, &full_bar[stage], dst_a, cc * BLOCK_K, w0 + kw - p.pad, h0 + kh - p.pad, img);
+        } else {
+          // input h = 2*ho + kh - 1 -> (h>>1, h&1) = (ho + ((kh-1)>>1), (kh-1)&1): kh=0 -> (ho-1,1); 1 -> (ho,0); 2 -> (ho,1)
+          const int dh = (kh == 0) ? -1 : 0, hp = (kh == 1) ? 0 : 1;
+          const int dw = (kw == 0) ? -1 : 0, wp = (kw == 1) ? 0 : 1;
+          tma_load_5d(&tmap_a, &full_bar[stage], dst_a, wp * p.x_pitch + cc * BLOCK_K, w0 + dw, hp, h0 + dh, img);
+        }
+        tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * (BLOCK_N * BLOCK_K * 2), kb * BLOCK_K, n0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        const uint64_t da = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
+        const uint64_t db = make_smem_desc(smem_u32(smem_b + stage * (BLOCK_N * BLOCK_K * 2)));
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / 16; ++k) {
+          // advance 16 halves = 32 B inside the 128-B swizzle row: +2 in 16-byte units
+          umma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);  // smem stage may be refilled once these MMAs have read it
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else if (warp >= 4) {
+    // ===================================================================== epilogue (128 threads)
+    const int ew = warp - 4;               // TMEM lane quarter
+    const int row = ew * 32 + lane;        // tile row == TMEM lane
+    const int bh = row / p.BW, bw = row - bh * p.BW;
+    const int ho = h0 + bh, wo = w0 + bw;
+    const bool row_valid = (row < p.BW * p.BH) && ho < p.Ho && wo < p.Wo;
+    const int64_t pix = ((int64_t)img * p.Ho + ho) * p.Wo + wo;
+    const TOut* res_row = p.res ? reinterpret_cast<const TOut*>(p.res) + pix * p.res_pitch : nullptr;
+    constexpr int CHUNK_COLS = 128 / (int)sizeof(TOut);  // output columns per 128-byte staging row
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+    uint8_t* srow = staging + row * 128;
+    for (int c0 = 0; c0 < BLOCK_N; c0 += CHUNK_COLS) {
+      if (n0 + c0 >= p.Cout) break;  // uniform across the CTA
+      // the previous TMA store must have finished READING the staging tile before it is overwritten
+      if (threadIdx.x == 128) tma_store_wait_read0();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+      for (int sub = 0; sub < CHUNK_COLS / 32; ++sub) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(c0 + sub * 32), r);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * s_scale[c0 + sub * 32 + j] + s_bias[c0 + sub * 32 + j];
+        const bool post = (p.act & FB200_ACT_RESIDUAL_AFTER) != 0;
+        if (post) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+        }
+        if (res_row && row_valid) {
+          const int nb = n0 + c0 + sub * 32;
+          if (nb + 32 <= p.Cout) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float rr[4];
+              load4(res_row + nb + j, rr);
+              v[j] += rr[0]; v[j + 1] += rr[1]; v[j + 2] += rr[2]; v[j + 3] += rr[3];
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (nb + j < p.Cout) v[j] += to_f(res_row[nb + j]);
+          }
+        }
+        if (!post) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+        }
+        // 16-byte pieces into the 128B-swizzled staging row: physical chunk = logical chunk ^ (row & 7)
+        if constexpr (sizeof(TOut) == 2) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {  // 8 halves per 16 B
+            __half2 h0_ = __floats2half2_rn(v[q * 8 + 0], v[q * 8 + 1]), h1_ = __floats2half2_rn(v[q * 8 + 2], v[q * 8 + 3]);
+            __half2 h2_ = __floats2half2_rn(v[q * 8 + 4], v[q * 8 + 5]), h3_ = __floats2half2_rn(v[q * 8 + 6], v[q * 8 + 7]);
+            uint4 pk = make_uint4(*reinterpret_cast<uint32_t*>(&h0_), *reinterpret_cast<uint32_t*>(&h1_),
+                                  *reinterpret_cast<uint32_t*>(&h2_), *reinterpret_cast<uint32_t*>(&h3_));
+            const int chunk = sub * 4 + q;
+            *reinterpret_cast<uint4*>(srow + ((chunk ^ (row & 7)) << 4)) = pk;
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {  // 4 floats per 16 B
+            const uint4 pk = make_uint4(__float_as_uint(v[q * 4 + 0]), __float_as_uint(v[q * 4 + 1]),
+                                        __float_as_uint(v[q * 4 + 2]), __float_as_uint(v[q * 4 + 3]));
+            *reinterpret_cast<uint4*>(srow + ((q ^ (row & 7)) << 4)) = pk;
+          }
+        }
+      }
+      fence_proxy_async();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 128) {
+        tma_store_4d(&tmap_d, staging, n0 + c0, w0, h0, img);
+        tma_store_commit();
+      }
+    }
+    if (threadIdx.x == 128) tma_store_wait_all();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int encode(CUtensorMap* m, CUtensorMapDataType dt, int elt, int rank, void* base, const uint64_t* dims, const uint64_t* strides_elts,
+                  const uint32_t* box, const char* what) {
+  EncodeTiledFn fn = get_encode();
+  if (!fn) { set_error("conv_tc: cuTensorMapEncodeTiled unavailable"); return FB200_ERR_CUDA; }
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1; }
+  for (int i = 1; i < rank; ++i) gstr[i - 1] = strides_elts[i] * (uint64_t)elt;  // bytes; dim0 stride is implicit
+  CUresult r = fn(m, dt, (cuuint32_t)rank, base, gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("conv_tc: cuTensorMapEncodeTiled(%s) failed with %d (rank %d dims %llu,%llu,%llu,%llu box %u,%u,%u,%u)", what, (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
+              (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+    return FB200_ERR_CUDA;
+  }
+  return FB200_OK;
+}
+
+// best output rectangle (BW x BH <= 128 pixels) for an Ho x Wo map
+static void choose_tile(int Ho, int Wo, int* BW, int* BH) {
+  double best = -1.0;
+  for (int bw = 1; bw <= (Wo < 128 ? Wo : 128); ++bw) {
+    int bh = 128 / bw;
+    if (bh > Ho) bh = Ho;
+    if (bh < 1) continue;
+    const double tiles = (double)((Wo + bw - 1) / bw) * (double)((Ho + bh - 1) / bh);
+    const double eff = (double)Wo * Ho / (tiles * 128.0);
+    if (eff > best + 1e-9 || (eff > best - 1e-9 && bw > *BW)) { best = eff; *BW = bw; *BH = bh; }
+  }
+}
+
+template <int BLOCK_N, int STAGES, typename TOut, int MIN_BLOCKS>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const KParams& kp, dim3 grid, cudaStream_t st) {
+  auto kern = conv_tc_kernel<BLOCK_N, STAGES, TOut, MIN_BLOCKS>;
+  constexpr int smem = smem_bytes<BLOCK_N, STAGES>();
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute(%d B) failed: %s", smem, cudaGetErrorString(e)); return FB200_ERR_CUDA; }
+    configured = true;
+  }
+  kern<<<grid, NUM_THREADS, smem, st>>>(ta, tb, td, kp);
+  FB_CHECK_LAUNCH("conv_tc_kernel");
+  return FB200_OK;
+}
+
+}  // namespace tc
+
+bool conv2d_tc_supported(const ConvParams& p, int x_dtype, int out_dtype) {
+  if (x_dtype != FB200_F16) return false;
+  if (out_dtype != FB200_F16 && out_dtype != FB200_F32) return false;
+  if (p.Cin % 64 != 0 || p.x_pitch % 8 != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.w) | reinterpret_cast<uintptr_t>(p.out)) & 15) return false;
+  const int oelt = out_dtype == FB200_F16 ? 2 : 4;
+  if ((p.out_pitch * oelt) % 16 != 0) return false;
+  if (p.res && ((p.res_pitch * oelt) % 16 != 0 || (reinterpret_cast<uintptr_t>(p.res) & 15))) return false;
+  if (p.KH != p.KW) return false;
+  if ((p.out_bs * oelt) % 16 != 0) return false;
+  if (p.stride == 1) return (2 * p.pad == p.KH - 1) || (p.KH == 1 && p.pad == 0);
+  if (p.stride == 2) return p.KH == 3 && p.pad == 1 && p.H % 2 == 0 && p.W % 2 == 0;
+  return false;
+}
+
+int conv2d_tc(const ConvParams& p, cudaStream_t st) {
+  using namespace tc;
+  KParams kp;
+  kp.scale = p.scale; kp.bias = p.bias; kp.res = p.res; kp.res_pitch = p.res_pitch; kp.act = p.act; kp.Cout = p.Cout;
+  kp.KH = p.KH; kp.KW = p.KW; kp.pad = p.pad; kp.cchunks = p.Cin / BLOCK_K; kp.x_pitch = p.x_pitch;
+  kp.stride2 = (p.stride == 2) ? 1 : 0;
+  kp.num_k_blocks = p.KH * p.KW * kp.cchunks;
+  // geometry: 1x1 stride-1 convs and linears flatten to W = M, H = 1, B = 1
+  int B = p.B, H = p.H, W = p.W, Ho = p.Ho, Wo = p.Wo;
+  const bool flat = (p.KH == 1 && p.stride == 1 && p.out_bs == (int64_t)p.Ho * p.Wo * p.out_pitch);
+  if (flat) {
+    if (p.M > 0x7fffffffLL) { set_error("conv_tc: M too large"); return FB200_ERR_UNSUPPORTED; }
+    W = Wo = (int)p.M; H = Ho = 1; B = 1;
+  }
+  int BW = 1, BH = 1;
+  choose_tile(Ho, Wo, &BW, &BH);
+  kp.BW = BW; kp.BH = BH; kp.tiles_w = (Wo + BW - 1) / BW; kp.tiles_h = (Ho + BH - 1) / BH; kp.Ho = Ho; kp.Wo = Wo;
+  const int64_t m_tiles = (int64_t)B * kp.tiles_w * kp.tiles_h;
+
+  CUtensorMap ta, tb, td;
+  int rc;
+  const uint64_t P = (uint64_t)p.x_pitch;
+  if (!kp.stride2) {
+    const uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[4] = {1, P, P * W, P * W * H};
+    const uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)BW, (uint32_t)BH, 1};
+    rc = encode(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4, const_cast<void*>(p.x), dims, str, box, "A");
+  } else {
+    const uint64_t dims[5] = {2 * P, (uint64_t)W / 2, 2, (uint64_t)H / 2, (uint64_t)B};
+    const uint64_t str[5] = {1, 2 * P, P * W, 2 * P * W, P * W * H};
+    const uint32_t box[5] = {(uint32_t)BLOCK_K, (uint32_t)BW, 1, (uint32_t)BH, 1};
+    rc = encode(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 5, const_cast<void*>(p.x), dims, str, box, "A(s2)");
+  }
+  if (rc) return rc;
+
+  auto run = [&](auto blockn_tag, auto stages_tag, auto minb_tag) -> int {
+    constexpr int BN_ = decltype(blockn_tag)::value;
+    constexpr int ST_ = decltype(stages_tag)::value;
+    constexpr int MB_ = decltype(minb_tag)::value;
+    {
+      const uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.Cout};
+      const uint64_t str[2] = {1, (uint64_t)p.K};
+      const uint32_t box[2] = {(uint32_t)BLOCK_K, (uint32_t)BN_};
+      int r2 = encode(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 2, const_cast<void*>(p.w), dims, str, box, "W");
+      if (r2) return r2;
+    }
+    const bool out16 = p.out_dtype == FB200_F16;
+    {
+      const uint64_t OP = (uint64_t)p.out_pitch;
+      const uint64_t dims[4] = {(uint64_t)p.Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)B};
+      const uint64_t str[4] = {1, OP, OP * Wo, flat ? OP * Wo * Ho : (uint64_t)p.out_bs};
+      const uint32_t box[4] = {(uint32_t)(out16 ? 64 : 32), (uint32_t)BW, (uint32_t)BH, 1};
+      int r2 = encode(&td, out16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, out16 ? 2 : 4, 4, p.out, dims, str, box, "D");
+      if (r2) return r2;
+    }
+    const int64_t ctas = m_tiles * ((p.Cout + BN_ - 1) / BN_);
+    if (ctas > 0x7fffffffLL) { set_error("conv_tc: too many tiles (%lld)", (long long)ctas); return FB200_ERR_UNSUPPORTED; }
+    dim3 grid((unsigned)ctas);
+    if (out16) return launch<BN_, ST_, __half, MB_>(ta, tb, td, kp, grid, st);
+    return launch<BN_, ST_, float, MB_>(ta, tb, td, kp, grid, st);
+  };
+  const int64_t tiles256 = m_tiles * ((p.Cout + 255) / 256);
+  if (p.Cout > 128 && tiles256 >= 148)
+    return run(std::integral_constant<int, 256>{}, std::integral_constant<int, 4>{}, std::integral_constant<int, 1>{});
+  if (p.Cout > 64)
+    return run(std::integral_constant<int, 128>{}, std::integral_constant<int, 5>{}, std::integral_constant<int, 1>{});
+  return run(std::integral_constant<int, 64>{}, std::integral_constant<int, 3>{}, std::integral_constant<int, 2>{});
+}
+
+}  // namespace fb200

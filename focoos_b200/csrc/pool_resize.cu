@@ -1,0 +1,141 @@
+// HBM-bound NHWC helpers: max/avg pooling, bilinear resize (align_corners=False), add.
+// One thread handles 4 consecutive channels of one output pixel (8/16-byte vector accesses,
+// consecutive threads -> consecutive channels -> coalesced rows).
+#include "common.cuh"
+
+namespace fb200 {
+
+template <typename T>
+__global__ void maxpool3x3s2_kernel(const T* __restrict__ x, int B, int H, int W, int C, int Ho, int Wo, T* __restrict__ out) {
+  const int cv = C / 4;
+  const int64_t total = (int64_t)B * Ho * Wo * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (i % cv) * 4;
+    const int64_t pix = i / cv;
+    const int wo = pix % Wo, ho = (pix / Wo) % Ho, b = pix / ((int64_t)Wo * Ho);
+    float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int hi = ho * 2 - 1 + kh;
+      if (hi < 0 || hi >= H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int wi = wo * 2 - 1 + kw;
+        if (wi < 0 || wi >= W) continue;
+        float v[4];
+        load4(x + (((int64_t)b * H + hi) * W + wi) * C + c, v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) m[j] = fmaxf(m[j], v[j]);
+      }
+    }
+    store4(out + pix * C + c, m);
+  }
+}
+
+template <typename T>
+__global__ void avgpool2x2_kernel(const T* __restrict__ x, int B, int H, int W, int C, int Ho, int Wo, T* __restrict__ out) {
+  const int cv = C / 4;
+  const int64_t total = (int64_t)B * Ho * Wo * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (i % cv) * 4;
+    const int64_t pix = i / cv;
+    const int wo = pix % Wo, ho = (pix / Wo) % Ho, b = pix / ((int64_t)Wo * Ho);
+    const int h0 = ho * 2, w0 = wo * 2, h1 = min(h0 + 2, H), w1 = min(w0 + 2, W);
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int hi = h0; hi < h1; ++hi)
+      for (int wi = w0; wi < w1; ++wi) {
+        float v[4];
+        load4(x + (((int64_t)b * H + hi) * W + wi) * C + c, v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[j] += v[j];
+      }
+    const float inv = 1.f / (float)((h1 - h0) * (w1 - w0));  // ceil_mode, pad 0: divisor = clipped window
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s[j] *= inv;
+    store4(out + pix * C + c, s);
+  }
+}
+
+// src index per ATen upsample_bilinear2d (align_corners=False): src = max((dst+0.5)*scale-0.5, 0), scale = in/out
+template <typename T>
+__global__ void resize_bilinear_kernel(const T* __restrict__ x, int B, int H, int W, int C, int x_pitch, T* __restrict__ out,
+                                       int Ho, int Wo, int out_pitch, float sh, float sw) {
+  const int cv = C / 4;
+  const int64_t total = (int64_t)B * Ho * Wo * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (i % cv) * 4;
+    const int64_t pix = i / cv;
+    const int wo = pix % Wo, ho = (pix / Wo) % Ho, b = pix / ((int64_t)Wo * Ho);
+    const float fh = fmaxf(((float)ho + 0.5f) * sh - 0.5f, 0.f), fw = fmaxf(((float)wo + 0.5f) * sw - 0.5f, 0.f);
+    const int h0 = (int)fh, w0 = (int)fw;
+    const int h1 = h0 + (h0 < H - 1 ? 1 : 0), w1 = w0 + (w0 < W - 1 ? 1 : 0);
+    const float lh1 = fh - (float)h0, lh0 = 1.f - lh1, lw1 = fw - (float)w0, lw0 = 1.f - lw1;
+    const T* base = x + (int64_t)b * H * W * x_pitch + c;
+    float v00[4], v01[4], v10[4], v11[4], r[4];
+    load4(base + ((int64_t)h0 * W + w0) * x_pitch, v00);
+    load4(base + ((int64_t)h0 * W + w1) * x_pitch, v01);
+    load4(base + ((int64_t)h1 * W + w0) * x_pitch, v10);
+    load4(base + ((int64_t)h1 * W + w1) * x_pitch, v11);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r[j] = lh0 * (lw0 * v00[j] + lw1 * v01[j]) + lh1 * (lw0 * v10[j] + lw1 * v11[j]);
+    store4(out + pix * out_pitch + c, r);
+  }
+}
+
+template <typename T>
+__global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, int64_t n4, int64_t bn4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float va[4], vb[4];
+    load4(a + i * 4, va);
+    load4(b + (i % bn4) * 4, vb);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) va[j] += vb[j];
+    store4(out + i * 4, va);
+  }
+}
+
+static inline unsigned grid_for(int64_t total, int threads) {
+  int64_t g = cdiv(total, threads);
+  const int64_t cap = 148LL * 32;
+  return (unsigned)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace fb200
+using namespace fb200;
+
+extern "C" int fb200_maxpool3x3s2(const void* x, int dtype, int B, int H, int W, int C, void* out, void* stream) {
+  FB_CHECK_ARG(x && out && C % 4 == 0, "maxpool: null pointer or C %% 4 != 0");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const int64_t total = (int64_t)B * Ho * Wo * (C / 4);
+  FB_DISPATCH_DTYPE(dtype, T, (maxpool3x3s2_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, B, H, W, C, Ho, Wo, (T*)out)));
+  FB_CHECK_LAUNCH("maxpool3x3s2");
+  return FB200_OK;
+}
+
+extern "C" int fb200_avgpool2x2_ceil(const void* x, int dtype, int B, int H, int W, int C, void* out, void* stream) {
+  FB_CHECK_ARG(x && out && C % 4 == 0, "avgpool: null pointer or C %% 4 != 0");
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const int64_t total = (int64_t)B * Ho * Wo * (C / 4);
+  FB_DISPATCH_DTYPE(dtype, T, (avgpool2x2_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, B, H, W, C, Ho, Wo, (T*)out)));
+  FB_CHECK_LAUNCH("avgpool2x2");
+  return FB200_OK;
+}
+
+extern "C" int fb200_resize_bilinear(const void* x, int dtype, int B, int H, int W, int C, int x_pitch, void* out, int Ho,
+                                     int Wo, int out_pitch, void* stream) {
+  FB_CHECK_ARG(x && out && C % 4 == 0 && x_pitch % 4 == 0 && out_pitch % 4 == 0, "resize: null pointer or C/pitch %% 4 != 0");
+  FB_CHECK_ARG(x_pitch >= C && out_pitch >= C && Ho > 0 && Wo > 0, "resize: bad shape");
+  const int64_t total = (int64_t)B * Ho * Wo * (C / 4);
+  const float sh = (float)H / (float)Ho, sw = (float)W / (float)Wo;
+  FB_DISPATCH_DTYPE(dtype, T, (resize_bilinear_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, B, H, W, C, x_pitch, (T*)out, Ho, Wo, out_pitch, sh, sw)));
+  FB_CHECK_LAUNCH("resize_bilinear");
+  return FB200_OK;
+}
+
+extern "C" int fb200_add(const void* a, const void* b, void* out, int dtype, int64_t rows, int64_t brows, int C, void* stream) {
+  FB_CHECK_ARG(a && b && out && C % 4 == 0 && brows > 0 && rows % brows == 0, "add: bad arguments");
+  const int64_t n4 = rows * C / 4, bn4 = brows * C / 4;
+  FB_DISPATCH_DTYPE(dtype, T, (add_kernel<T><<<grid_for(n4, 256), 256, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)b, (T*)out, n4, bn4)));
+  FB_CHECK_LAUNCH("add");
+  return FB200_OK;
+}

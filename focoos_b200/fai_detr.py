@@ -1,0 +1,569 @@
+"""FAIDetr (RT-DETR-style detector) — host-side mirror of `focoos/models/fai_detr/modelling.py`.
+
+The module TREE below mirrors the reference's (same attribute names, same parameter shapes) so that a
+reference `state_dict` / `model_final.pth` loads unchanged, but the modules are only
+parameter containers: `FAIDetr.forward` runs `DetrEngine`, a fused NHWC graph of `focoos_b200.ops`
+calls (hand-written sm_100a kernels) built once from the weights:
+
+  * BatchNorm folded into per-channel scale/bias applied in the conv epilogue (nn/layers/conv.py:89),
+  * RepVggBlock re-parameterised to one 3x3 conv (the reference's own `get_equivalent_kernel_bias`,
+    modelling.py:57-61, which it never calls),
+  * CSPRepLayer conv1‖conv2 as ONE 1x1 GEMM (N=512) and its output add fused as a post-activation residual,
+  * concat-free FPN/PAN: producers write straight into channel slices of the concat buffer,
+  * the six decoder value_proj GEMMs batched into one (memory is layer-invariant, modelling.py:848),
+  * sampling_offsets ‖ attention_weights as one GEMM feeding the fused MSDA kernel,
+  * encoder bbox MLP evaluated only on the 300 selected rows (row-wise op; identical result),
+  * the dead `mask_features` conv (modelling.py:347 computed, :381 discarded) skipped.
+
+There is no CPU / eager fallback: `forward` raises unless the tensors are on a CUDA device and the
+compiled library is present.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .ports import DETRConfig, DETRModelOutput, ResnetConfig
+
+RESNET_BLOCKS = {50: [3, 4, 6, 3], 101: [3, 4, 23, 3]}
+
+
+# --------------------------------------------------------------------------------------------------
+# parameter containers (names = the reference's state_dict keys)
+# --------------------------------------------------------------------------------------------------
+class ConvNormLayer(nn.Module):  # nn/layers/conv.py:78
+    def __init__(self, ch_in, ch_out, k, stride, act=None):
+        super().__init__()
+        self.conv = nn.Conv2d(ch_in, ch_out, k, stride, padding=(k - 1) // 2, bias=False)
+        self.norm = nn.BatchNorm2d(ch_out)
+        self.act_name, self.stride = act, stride
+
+
+class BottleNeck(nn.Module):  # nn/backbone/resnet.py:72
+    def __init__(self, ch_in, ch_out, stride, shortcut):
+        super().__init__()
+        self.branch2a = ConvNormLayer(ch_in, ch_out, 1, 1, "relu")
+        self.branch2b = ConvNormLayer(ch_out, ch_out, 3, stride, "relu")
+        self.branch2c = ConvNormLayer(ch_out, ch_out * 4, 1, 1)
+        self.shortcut, self.stride = shortcut, stride
+        if not shortcut:
+            if stride == 2:
+                self.short = nn.Sequential(OrderedDict([("pool", nn.AvgPool2d(2, 2, 0, ceil_mode=True)), ("conv", ConvNormLayer(ch_in, ch_out * 4, 1, 1))]))
+            else:
+                self.short = ConvNormLayer(ch_in, ch_out * 4, 1, stride)
+
+
+class Blocks(nn.Module):  # nn/backbone/resnet.py:124
+    def __init__(self, ch_in, ch_out, count, stage_num):
+        super().__init__()
+        self.blocks = nn.ModuleList()
+        for i in range(count):
+            self.blocks.append(BottleNeck(ch_in, ch_out, stride=2 if i == 0 and stage_num != 2 else 1, shortcut=i != 0))
+            if i == 0:
+                ch_in = ch_out * 4
+
+
+class ResNet(nn.Module):  # nn/backbone/resnet.py:164 (variant d, depth >= 50)
+    def __init__(self, cfg: ResnetConfig):
+        super().__init__()
+        assert cfg.variant == "d" and cfg.depth in RESNET_BLOCKS, "focoos_b200 implements ResNet-50/101 vd"
+        self.depth = cfg.depth
+        self.conv1 = nn.Sequential(OrderedDict([
+            ("conv1_1", ConvNormLayer(cfg.in_chans, 32, 3, 2, "relu")),
+            ("conv1_2", ConvNormLayer(32, 32, 3, 1, "relu")),
+            ("conv1_3", ConvNormLayer(32, 64, 3, 1, "relu")),
+        ]))
+        self.res_layers = nn.ModuleList()
+        ch_in = 64
+        for i, (n, ch) in enumerate(zip(RESNET_BLOCKS[cfg.depth], [64, 128, 256, 512])):
+            self.res_layers.append(Blocks(ch_in, ch, n, i + 2))
+            ch_in = ch * 4
+        self.out_channels = [256, 512, 1024, 2048]
+
+
+class RepVggBlock(nn.Module):  # modelling.py:30
+    def __init__(self, ch):
+        super().__init__()
+        self.conv1 = ConvNormLayer(ch, ch, 3, 1)
+        self.conv2 = ConvNormLayer(ch, ch, 1, 1)
+
+
+class CSPRepLayer(nn.Module):  # modelling.py:84 (expansion 1.0 -> conv3 = Identity)
+    def __init__(self, ch_in, ch_out, num_blocks=3):
+        super().__init__()
+        self.conv1 = ConvNormLayer(ch_in, ch_out, 1, 1, "silu")
+        self.conv2 = ConvNormLayer(ch_in, ch_out, 1, 1, "silu")
+        self.bottlenecks = nn.Sequential(*[RepVggBlock(ch_out) for _ in range(num_blocks)])
+        self.conv3 = nn.Identity()
+
+
+class TransformerEncoderLayer(nn.Module):  # nn/layers/transformer.py:553
+    def __init__(self, d, nhead, dff):
+        super().__init__()
+        self.self_attn = nn.MultiheadAttention(d, nhead, 0.0, batch_first=True)
+        self.linear1, self.linear2 = nn.Linear(d, dff), nn.Linear(dff, d)
+        self.norm1, self.norm2 = nn.LayerNorm(d), nn.LayerNorm(d)
+
+
+class TransformerEncoder(nn.Module):  # nn/layers/transformer.py:471
+    def __init__(self, d, nhead, dff, n):
+        super().__init__()
+        self.layers = nn.ModuleList([TransformerEncoderLayer(d, nhead, dff) for _ in range(n)])
+
+
+class Encoder(nn.Module):  # modelling.py:195 ("pixel_decoder")
+    def __init__(self, backbone: ResNet, feat_dim, out_dim, nhead, dff, num_encoder_layers):
+        super().__init__()
+        self.backbone = backbone
+        in_ch = backbone.out_channels[1:]
+        self.input_proj = nn.ModuleList([nn.Sequential(nn.Conv2d(c, feat_dim, 1, bias=False), nn.BatchNorm2d(feat_dim)) for c in in_ch])
+        self.encoder = nn.ModuleList([TransformerEncoder(feat_dim, nhead, dff, num_encoder_layers)])
+        self.lateral_convs = nn.ModuleList([ConvNormLayer(feat_dim, feat_dim, 1, 1, "silu") for _ in range(2)])
+        self.fpn_blocks = nn.ModuleList([CSPRepLayer(feat_dim * 2, feat_dim) for _ in range(2)])
+        self.downsample_convs = nn.ModuleList([ConvNormLayer(feat_dim, feat_dim, 3, 1, "silu") for _ in range(2)])
+        self.pan_blocks = nn.ModuleList([CSPRepLayer(feat_dim * 2, feat_dim) for _ in range(2)])
+        self.mask_features = nn.Conv2d(feat_dim, out_dim, 3, 1, 1)  # dead for detection (modelling.py:381); kept for the weight file
+
+
+class MLP(nn.Module):  # nn/layers/base.py:31
+    def __init__(self, i, h, o, n):
+        super().__init__()
+        hs = [h] * (n - 1)
+        self.layers = nn.ModuleList(nn.Linear(a, b) for a, b in zip([i] + hs, hs + [o]))
+
+
+class MSDeformableAttention(nn.Module):  # modelling.py:777
+    def __init__(self, d, heads, levels, points):
+        super().__init__()
+        self.sampling_offsets = nn.Linear(d, heads * levels * points * 2)
+        self.attention_weights = nn.Linear(d, heads * levels * points)
+        self.value_proj, self.output_proj = nn.Linear(d, d), nn.Linear(d, d)
+
+
+class TransformerDecoderLayer(nn.Module):  # modelling.py:887
+    def __init__(self, d, heads, dff, levels, points):
+        super().__init__()
+        self.self_attn = nn.MultiheadAttention(d, heads, dropout=0.0, batch_first=True)
+        self.norm1 = nn.LayerNorm(d)
+        self.cross_attn = MSDeformableAttention(d, heads, levels, points)
+        self.norm2 = nn.LayerNorm(d)
+        self.linear1, self.linear2 = nn.Linear(d, dff), nn.Linear(dff, d)
+        self.norm3 = nn.LayerNorm(d)
+
+
+class TransformerDecoder(nn.Module):  # modelling.py:961
+    def __init__(self, d, heads, dff, levels, points, n):
+        super().__init__()
+        self.layers = nn.ModuleList([TransformerDecoderLayer(d, heads, dff, levels, points) for _ in range(n)])
+
+
+class TransformerPredictor(nn.Module):  # modelling.py:1023
+    def __init__(self, in_channels, num_classes, hidden, num_queries, nhead, dec_layers, dff, num_scales=3, points=4):
+        super().__init__()
+        self.num_queries, self.num_levels, self.num_points, self.nhead, self.dec_layers = num_queries, num_scales, points, nhead, dec_layers
+        self.input_proj = nn.ModuleList([
+            nn.Sequential(OrderedDict([("conv", nn.Conv2d(in_channels, hidden, 1, bias=False)), ("norm", nn.BatchNorm2d(hidden))]))
+            for _ in range(num_scales)])
+        self.decoder = TransformerDecoder(hidden, nhead, dff, num_scales, points, dec_layers)
+        self.query_pos_head = MLP(4, 2 * hidden, hidden, 2)
+        self.enc_output = nn.Sequential(nn.Linear(hidden, hidden), nn.LayerNorm(hidden))
+        self.enc_score_classifier = nn.Linear(hidden, num_classes)
+        self.enc_bbox_classifier = MLP(hidden, hidden, 4, 3)
+        self.dec_score_classifier = nn.ModuleList([nn.Linear(hidden, num_classes) for _ in range(dec_layers)])
+        self.dec_bbox_classifier = nn.ModuleList([MLP(hidden, hidden, 4, 3) for _ in range(dec_layers)])
+
+
+class _CriterionStub(nn.Module):
+    """Holds `head.criterion.empty_weight` (it IS in the weight file). Losses: later round."""
+
+    def __init__(self, num_classes):
+        super().__init__()
+        w = torch.ones(num_classes + 1)
+        w[-1] = 0.1
+        self.register_buffer("empty_weight", w)
+
+
+class DETRHead(nn.Module):  # modelling.py:350
+    def __init__(self, predictor, num_classes):
+        super().__init__()
+        self.criterion = _CriterionStub(num_classes)
+        self.predictor = predictor
+
+
+def generate_anchors(spatial_shapes, grid_size=0.05, eps=1e-2):
+    """modelling.py:1169-1189 — logit-space anchors [S,4] fp32 and validity [S] (host, once per resolution)."""
+    anchors = []
+    for lvl, (h, w) in enumerate(spatial_shapes):
+        gy, gx = torch.meshgrid(torch.arange(end=h, dtype=torch.float32), torch.arange(end=w, dtype=torch.float32), indexing="ij")
+        grid_xy = (torch.stack([gx, gy], -1).unsqueeze(0) + 0.5) / torch.tensor([w, h], dtype=torch.float32)
+        wh = torch.ones_like(grid_xy) * grid_size * (2.0 ** (2 - lvl))
+        anchors.append(torch.concat([grid_xy, wh], -1).reshape(-1, h * w, 4))
+    anchors = torch.concat(anchors, 1)
+    valid = ((anchors > eps) * (anchors < 1 - eps)).all(-1, keepdim=True)
+    anchors = torch.where(valid, torch.log(anchors / (1 - anchors)), torch.zeros(()))
+    return anchors[0].contiguous(), valid[0, :, 0].contiguous()
+
+
+def aifi_position_embedding(h, w, num_pos_feats=128, temperature=10000.0):
+    """modelling.py:110-179 with normalize=False: [h*w, 4*num_pos_feats/2] = cat(y_sin, y_cos, x_sin, x_cos)."""
+    y_embed = torch.arange(h, dtype=torch.float32).view(h, 1).expand(h, w)
+    x_embed = torch.arange(w, dtype=torch.float32).view(1, w).expand(h, w)
+    dim_t = torch.arange(num_pos_feats, dtype=torch.float32)
+    dim_t = temperature ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / num_pos_feats)
+    pos_x = x_embed[:, :, None] / dim_t
+    pos_y = y_embed[:, :, None] / dim_t
+    return torch.cat((pos_y[:, :, 0::2].sin().reshape(h * w, -1), pos_y[:, :, 1::2].cos().reshape(h * w, -1),
+                      pos_x[:, :, 0::2].sin().reshape(h * w, -1), pos_x[:, :, 1::2].cos().reshape(h * w, -1)), dim=1)
+
+
+# --------------------------------------------------------------------------------------------------
+# the fused graph
+# --------------------------------------------------------------------------------------------------
+class _Conv:
+    """Packed conv/linear: weight [Cout,KH,KW,Cin] in activation dtype, fp32 scale/bias (folded BN)."""
+
+    __slots__ = ("w", "scale", "bias", "stride", "pad", "act")
+
+    def __init__(self, w, scale, bias, stride=1, pad=0, act=ops.ACT_NONE):
+        self.w, self.scale, self.bias, self.stride, self.pad, self.act = w, scale, bias, stride, pad, act
+
+    def __call__(self, x, residual=None, out=None, out_dtype=None, act=None, algo=ops.ALGO_AUTO):
+        return ops.conv2d(x, self.w, self.scale, self.bias, stride=self.stride, pad=self.pad, act=self.act if act is None else act,
+                          residual=residual, out=out, out_dtype=out_dtype, algo=algo)
+
+
+class _Linear:
+    __slots__ = ("w", "bias")
+
+    def __init__(self, w, bias):
+        self.w, self.bias = w, bias
+
+    def __call__(self, x, act=ops.ACT_NONE, residual=None, out_dtype=None, out=None, algo=ops.ALGO_AUTO):
+        return ops.linear(x, self.w, self.bias, act=act, residual=residual, out_dtype=out_dtype, out=out, algo=algo)
+
+
+def _bn_fold(sd, p, eps=1e-5):
+    s = sd[p + ".weight"].float() / torch.sqrt(sd[p + ".running_var"].float() + eps)
+    return s, sd[p + ".bias"].float() - sd[p + ".running_mean"].float() * s
+
+
+class DetrEngine:
+    """Packs a FAIDetr state_dict for one (device, precision) and runs the fused forward."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], cfg: DETRConfig, device, precision: str = "fp16", algo: int = ops.ALGO_AUTO):
+        assert precision in ("fp32", "fp16")
+        self.cfg, self.device, self.precision, self.algo = cfg, torch.device(device), precision, algo
+        self.dt = torch.float32 if precision == "fp32" else torch.float16
+        self.depth = cfg.backbone_config.depth
+        self.nhead = cfg.transformer_predictor_nhead
+        self.d = cfg.transformer_predictor_hidden_dim
+        self._consts: Dict[Tuple[int, int], dict] = {}
+        sd = {k: v.detach() for k, v in sd.items()}
+        self._pack(sd)
+
+    # ---- packing -------------------------------------------------------------------------------
+    def _to(self, t, dtype=None):
+        return t.to(device=self.device, dtype=dtype or self.dt).contiguous()
+
+    def _f32(self, t):
+        return t.to(device=self.device, dtype=torch.float32).contiguous()
+
+    def _cnl(self, sd, p, act=None, stride=1):
+        """ConvNormLayer -> _Conv with BN in the epilogue."""
+        w = sd[p + ".conv.weight"].float()
+        s, b = _bn_fold(sd, p + ".norm")
+        k = w.shape[-1]
+        return _Conv(self._to(w.permute(0, 2, 3, 1)), self._f32(s), self._f32(b), stride, (k - 1) // 2, ops.ACT[act])
+
+    def _seq_conv_bn(self, sd, pc, pn):
+        s, b = _bn_fold(sd, pn)
+        return _Conv(self._to(sd[pc + ".weight"].float().permute(0, 2, 3, 1)), self._f32(s), self._f32(b), 1, 0, ops.ACT_NONE)
+
+    def _lin(self, sd, p, rows=None, dtype=None):
+        w, b = sd[p + ".weight"].float(), sd[p + ".bias"].float()
+        if rows is not None:
+            w, b = w[rows], b[rows]
+        return _Linear(self._to(w, dtype), self._f32(b))
+
+    def _csp(self, sd, p):
+        w1, w2 = sd[p + ".conv1.conv.weight"].float(), sd[p + ".conv2.conv.weight"].float()
+        s1, b1 = _bn_fold(sd, p + ".conv1.norm")
+        s2, b2 = _bn_fold(sd, p + ".conv2.norm")
+        both = _Conv(self._to(torch.cat([w1, w2], 0).permute(0, 2, 3, 1)), self._f32(torch.cat([s1, s2])), self._f32(torch.cat([b1, b2])), 1, 0, ops.ACT_SILU)
+        reps = []
+        i = 0
+        while f"{p}.bottlenecks.{i}.conv1.conv.weight" in sd:
+            q = f"{p}.bottlenecks.{i}"
+            s3, b3 = _bn_fold(sd, q + ".conv1.norm")
+            s1_, b1_ = _bn_fold(sd, q + ".conv2.norm")
+            k = sd[q + ".conv1.conv.weight"].float() * s3.view(-1, 1, 1, 1) + nn.functional.pad(sd[q + ".conv2.conv.weight"].float() * s1_.view(-1, 1, 1, 1), [1, 1, 1, 1])
+            reps.append(_Conv(self._to(k.permute(0, 2, 3, 1)), None, self._f32(b3 + b1_), 1, 1, ops.ACT_SILU))
+            i += 1
+        return both, reps
+
+    def _pack(self, sd):
+        bb = "pixel_decoder.backbone"
+        w = sd[bb + ".conv1.conv1_1.conv.weight"].float()
+        s, b = _bn_fold(sd, bb + ".conv1.conv1_1.norm")
+        self.stem_w, self.stem_s, self.stem_b = self._f32(w.permute(0, 2, 3, 1)), self._f32(s), self._f32(b)
+        self.stem2 = self._cnl(sd, bb + ".conv1.conv1_2", "relu")
+        self.stem3 = self._cnl(sd, bb + ".conv1.conv1_3", "relu")
+        self.stages = []
+        for si, count in enumerate(RESNET_BLOCKS[self.depth]):
+            blocks = []
+            for bi in range(count):
+                p = f"{bb}.res_layers.{si}.blocks.{bi}"
+                stride = 2 if (bi == 0 and si != 0) else 1
+                blk = {"a": self._cnl(sd, p + ".branch2a", "relu"), "b": self._cnl(sd, p + ".branch2b", "relu", stride),
+                       "c": self._cnl(sd, p + ".branch2c", "relu"), "stride": stride, "short": None}
+                if bi == 0:
+                    blk["short"] = self._cnl(sd, p + (".short.conv" if stride == 2 else ".short"), None)
+                blocks.append(blk)
+            self.stages.append(blocks)
+        pd = "pixel_decoder"
+        self.enc_in = [self._seq_conv_bn(sd, f"{pd}.input_proj.{i}.0", f"{pd}.input_proj.{i}.1") for i in range(3)]
+        e = f"{pd}.encoder.0.layers.0"
+        self.aifi = self._pack_attn_block(sd, e, ffn_norms=("norm1", "norm2"))
+        self.lateral = [self._cnl(sd, f"{pd}.lateral_convs.{i}", "silu") for i in range(2)]
+        self.fpn = [self._csp(sd, f"{pd}.fpn_blocks.{i}") for i in range(2)]
+        self.down = [self._cnl(sd, f"{pd}.downsample_convs.{i}", "silu") for i in range(2)]
+        self.pan = [self._csp(sd, f"{pd}.pan_blocks.{i}") for i in range(2)]
+        hp = "head.predictor"
+        self.dec_in = [self._seq_conv_bn(sd, f"{hp}.input_proj.{i}.conv", f"{hp}.input_proj.{i}.norm") for i in range(3)]
+        self.enc_output = self._lin(sd, hp + ".enc_output.0")
+        self.enc_output_ln = (self._f32(sd[hp + ".enc_output.1.weight"]), self._f32(sd[hp + ".enc_output.1.bias"]))
+        self.enc_score = self._lin(sd, hp + ".enc_score_classifier")
+        self.enc_bbox = [self._lin(sd, f"{hp}.enc_bbox_classifier.layers.{i}") for i in range(3)]
+        self.qpos = [self._lin(sd, hp + ".query_pos_head.layers.0", dtype=torch.float32), self._lin(sd, hp + ".query_pos_head.layers.1")]
+        L = self.cfg.transformer_predictor_dec_layers
+        vw = torch.cat([sd[f"{hp}.decoder.layers.{i}.cross_attn.value_proj.weight"].float() for i in range(L)], 0)
+        vb = torch.cat([sd[f"{hp}.decoder.layers.{i}.cross_attn.value_proj.bias"].float() for i in range(L)], 0)
+        self.value_all = _Linear(self._to(vw), self._f32(vb))
+        self.dec = []
+        for i in range(L):
+            p = f"{hp}.decoder.layers.{i}"
+            blk = self._pack_attn_block(sd, p, ffn_norms=("norm1", "norm3"))
+            oa_w = torch.cat([sd[p + ".cross_attn.sampling_offsets.weight"].float(), sd[p + ".cross_attn.attention_weights.weight"].float()], 0)
+            oa_b = torch.cat([sd[p + ".cross_attn.sampling_offsets.bias"].float(), sd[p + ".cross_attn.attention_weights.bias"].float()], 0)
+            blk["oa"] = _Linear(self._to(oa_w), self._f32(oa_b))
+            blk["cross_out"] = self._lin(sd, p + ".cross_attn.output_proj")
+            blk["n_cross"] = (self._f32(sd[p + ".norm2.weight"]), self._f32(sd[p + ".norm2.bias"]))
+            blk["bbox"] = [self._lin(sd, f"{hp}.dec_bbox_classifier.{i}.layers.{j}") for j in range(3)]
+            self.dec.append(blk)
+        self.dec_score = self._lin(sd, f"{hp}.dec_score_classifier.{L - 1}")
+
+    def _pack_attn_block(self, sd, p, ffn_norms):
+        """MultiheadAttention (packed in_proj: rows [0,d)=Q, [d,2d)=K, [2d,3d)=V) + FFN + the two LayerNorms around them."""
+        d = self.d
+        w, b = sd[p + ".self_attn.in_proj_weight"].float(), sd[p + ".self_attn.in_proj_bias"].float()
+        n_attn, n_ffn = ffn_norms
+        return {
+            "qk": _Linear(self._to(w[: 2 * d]), self._f32(b[: 2 * d])), "v": _Linear(self._to(w[2 * d:]), self._f32(b[2 * d:])),
+            "out": self._lin(sd, p + ".self_attn.out_proj"), "l1": self._lin(sd, p + ".linear1"), "l2": self._lin(sd, p + ".linear2"),
+            "n_attn": (self._f32(sd[f"{p}.{n_attn}.weight"]), self._f32(sd[f"{p}.{n_attn}.bias"])),
+            "n_ffn": (self._f32(sd[f"{p}.{n_ffn}.weight"]), self._f32(sd[f"{p}.{n_ffn}.bias"])),
+        }
+
+    def _constants(self, h32, w32):
+        key = (h32, w32)
+        if key not in self._consts:
+            shapes = [(h32, w32), (h32 * 2, w32 * 2), (h32 * 4, w32 * 4)]
+            anchors, valid = generate_anchors(shapes)
+            self._consts[key] = {
+                "shapes": shapes, "anchors": self._f32(anchors), "valid": valid.to(self.device, torch.uint8).contiguous(),
+                "pos": self._to(aifi_position_embedding(h32, w32, self.cfg.pixel_decoder_feat_dim // 2)),
+            }
+        return self._consts[key]
+
+    # ---- forward -------------------------------------------------------------------------------
+    def _csp_run(self, packed, cat, out=None):
+        both, reps = packed
+        C = both.w.shape[0] // 2
+        y12 = both(cat, algo=self.algo)
+        x = y12[..., :C]
+        for i, r in enumerate(reps):
+            last = i == len(reps) - 1
+            x = r(x, residual=y12[..., C:] if last else None, act=(ops.ACT_SILU | 16) if last else None, out=out if last else None, algo=self.algo)
+        return x
+
+    def _mha(self, blk, x, pos):
+        """post-norm self-attention block: LN(x + out_proj(attn(q=k=x+pos, v=x)))."""
+        B, L, d = x.shape
+        qk = blk["qk"](ops.add(x, pos), algo=self.algo)
+        v = blk["v"](x, algo=self.algo)
+        a = ops.attention(qk[..., :d], qk[..., d:], v, self.nhead, 1.0 / math.sqrt(d // self.nhead))
+        y = blk["out"](a, residual=x, algo=self.algo)
+        return ops.layernorm(y, *blk["n_attn"])
+
+    def _ffn(self, blk, x, act):
+        f = blk["l2"](blk["l1"](x, act=act, algo=self.algo), residual=x, algo=self.algo)
+        return ops.layernorm(f, *blk["n_ffn"])
+
+    @torch.no_grad()
+    def forward(self, images: torch.Tensor, taps: Optional[dict] = None):
+        """images [B,3,H,W] fp32 0..255 (H,W multiples of 32) -> (scores [B,Q,C] fp32, boxes xyxy [B,Q,4] fp32)."""
+        cfg, dt, A = self.cfg, self.dt, self.algo
+        assert images.dim() == 4 and images.shape[1] == 3 and images.dtype == torch.float32
+        B, _, H, W = images.shape
+        assert H % 32 == 0 and W % 32 == 0, "input size must be a multiple of 32"
+        x = ops.stem_conv(images.contiguous(), self.stem_w, self.stem_s, self.stem_b, cfg.pixel_mean, cfg.pixel_std, ops.ACT_RELU, dt)
+        x = self.stem3(self.stem2(x, algo=A), algo=A)
+        x = ops.maxpool3x3s2(x)
+        feats = []
+        for blocks in self.stages:
+            for blk in blocks:
+                y = blk["b"](blk["a"](x, algo=A), algo=A)
+                if blk["short"] is None:
+                    short = x
+                else:
+                    short = blk["short"](ops.avgpool2x2(x) if blk["stride"] == 2 else x, algo=A)
+                x = blk["c"](y, residual=short, algo=A)
+            feats.append(x)
+        res3, res4, res5 = feats[1], feats[2], feats[3]
+        h32, w32 = res5.shape[1], res5.shape[2]
+        K = self._constants(h32, w32)
+        C = cfg.pixel_decoder_feat_dim
+        dev = images.device
+        cat1 = torch.empty((B, h32 * 2, w32 * 2, 2 * C), dtype=dt, device=dev)  # [up(lat0) | proj(res4)]
+        cat2 = torch.empty((B, h32 * 4, w32 * 4, 2 * C), dtype=dt, device=dev)  # [up(lat1) | proj(res3)]
+        cat3 = torch.empty((B, h32 * 2, w32 * 2, 2 * C), dtype=dt, device=dev)  # [down(fpn1) | lat1]
+        cat4 = torch.empty((B, h32, w32, 2 * C), dtype=dt, device=dev)          # [down(pan0) | lat0]
+        self.enc_in[0](res3, out=cat2[..., C:], algo=A)
+        self.enc_in[1](res4, out=cat1[..., C:], algo=A)
+        p5 = self.enc_in[2](res5, algo=A)
+        # AIFI (modelling.py:315-324)
+        src = p5.reshape(B, h32 * w32, C)
+        src = self._mha(self.aifi, src, K["pos"])
+        src = self._ffn(self.aifi, src, ops.ACT_GELU)
+        p5 = src.reshape(B, h32, w32, C)
+        # top-down FPN (modelling.py:328-336)
+        lat0 = self.lateral[0](p5, out=cat4[..., C:], algo=A)
+        ops.resize_bilinear(lat0, (h32 * 2, w32 * 2), out=cat1[..., :C])
+        fpn0 = self._csp_run(self.fpn[0], cat1)
+        lat1 = self.lateral[1](fpn0, out=cat3[..., C:], algo=A)
+        ops.resize_bilinear(lat1, (h32 * 4, w32 * 4), out=cat2[..., :C])
+        fpn1 = self._csp_run(self.fpn[1], cat2)
+        # bottom-up PAN (modelling.py:338-345)
+        self.down[0](ops.resize_bilinear(fpn1, (h32 * 2, w32 * 2)), out=cat3[..., :C], algo=A)
+        pan0 = self._csp_run(self.pan[0], cat3)
+        self.down[1](ops.resize_bilinear(pan0, (h32, w32)), out=cat4[..., :C], algo=A)
+        pan1 = self._csp_run(self.pan[1], cat4)
+        enc_outs = [pan1, pan0, fpn1]  # outs[::-1] (modelling.py:347): 1/32, 1/16, 1/8
+        if taps is not None:
+            taps.update(res3=res3, res4=res4, res5=res5, aifi=p5, fpn0=fpn0, fpn1=fpn1, pan0=pan0, pan1=pan1)
+        # predictor: memory [B, S, d] (modelling.py:1145-1167), each level written in place
+        shapes = K["shapes"]
+        S = sum(h * w for h, w in shapes)
+        d = self.d
+        memory = torch.empty((B, S, d), dtype=dt, device=dev)
+        start = 0
+        for i, (f, (h, w)) in enumerate(zip(enc_outs, shapes)):
+            self.dec_in[i](f, out=memory[:, start:start + h * w].unflatten(1, (h, w)), algo=A)
+            start += h * w
+        value_all = self.value_all(memory, algo=A)  # [B,S,6*d], layer i uses columns [i*d,(i+1)*d)
+        # query selection (modelling.py:1191-1232)
+        t = self.enc_output(memory, algo=A)
+        t = ops.row_select(t, K["valid"], self.enc_output.bias)
+        output_memory = ops.layernorm(t, *self.enc_output_ln)
+        ncls = cfg.num_classes
+        cls_buf = torch.empty((B, S, (ncls + 7) // 8 * 8), dtype=torch.float32, device=dev)
+        self.enc_score(output_memory, out=cls_buf[..., :ncls], algo=A)
+        scores = ops.rowmax(cls_buf[..., :ncls])
+        _, topk_ind = ops.topk(scores, cfg.num_queries)
+        tgt = ops.gather_rows(output_memory, topk_ind)
+        bb = self.enc_bbox[2](self.enc_bbox[1](self.enc_bbox[0](tgt, act=ops.ACT_RELU, algo=A), act=ops.ACT_RELU, algo=A), out_dtype=torch.float32, algo=A)
+        ref_unact = ops.box_add_anchors(bb, K["anchors"], topk_ind)
+        ref = ops.box_sigmoid(ref_unact)
+        if taps is not None:
+            taps.update(memory=memory, enc_scores=scores, topk_ind=topk_ind, target=tgt, ref_unact=ref_unact)
+        # decoder (modelling.py:969-1020, eval: logits only from the last layer)
+        for i, blk in enumerate(self.dec):
+            pos = self.qpos[1](self.qpos[0](ref, act=ops.ACT_RELU, out_dtype=dt, algo=ops.ALGO_SIMT), algo=A)
+            tgt = self._mha(blk, tgt, pos)
+            oa = blk["oa"](ops.add(tgt, pos), out_dtype=torch.float32, algo=A)
+            c = ops.msda(value_all[..., i * d:(i + 1) * d], oa, ref, shapes, cfg_points(cfg), self.nhead, out_dtype=dt)
+            tgt = ops.layernorm(blk["cross_out"](c, residual=tgt, algo=A), *blk["n_cross"])
+            tgt = self._ffn(blk, tgt, ops.ACT_RELU)
+            delta = blk["bbox"][2](blk["bbox"][1](blk["bbox"][0](tgt, act=ops.ACT_RELU, algo=A), act=ops.ACT_RELU, algo=A), out_dtype=torch.float32, algo=A)
+            ref = ops.box_refine(delta, ref)
+            if taps is not None:
+                taps[f"dec{i}_out"] = tgt
+                taps[f"dec{i}_ref"] = ref
+        logits = self.dec_score(tgt, out_dtype=torch.float32, algo=ops.ALGO_SIMT)  # [B,Q,C] contiguous
+        if taps is not None:
+            taps.update(pred_logits=logits, pred_boxes_cxcywh=ref)
+        return ops.box_sigmoid(logits), ops.box_cxcywh_to_xyxy(ref)
+
+
+def cfg_points(cfg) -> int:
+    return 4  # num_decoder_points (modelling.py:1039)
+
+
+class FAIDetr(nn.Module):
+    """Drop-in for the reference `FAIDetr(BaseModelNN)` (modelling.py:1273): same constructor argument, same
+    state_dict, `forward(images[, targets]) -> DETRModelOutput`, `.device` / `.dtype` from `pixel_mean`."""
+
+    def __init__(self, config: DETRConfig, precision: str = "fp16"):
+        super().__init__()
+        self.config = config
+        c = config
+        self.pixel_decoder = Encoder(ResNet(c.backbone_config), c.pixel_decoder_feat_dim, c.pixel_decoder_out_dim, c.pixel_decoder_nhead,
+                                     c.pixel_decoder_dim_feedforward, c.pixel_decoder_num_encoder_layers)
+        self.head = DETRHead(TransformerPredictor(c.pixel_decoder_out_dim, c.num_classes, c.transformer_predictor_hidden_dim, c.num_queries,
+                                                  c.transformer_predictor_nhead, c.transformer_predictor_dec_layers,
+                                                  c.transformer_predictor_dim_feedforward), c.num_classes)
+        self.register_buffer("pixel_mean", torch.tensor(c.pixel_mean, dtype=torch.float32).view(-1, 1, 1), False)
+        self.register_buffer("pixel_std", torch.tensor(c.pixel_std, dtype=torch.float32).view(-1, 1, 1), False)
+        self.num_classes = c.num_classes
+        self.precision = precision
+        self.algo = ops.ALGO_AUTO
+        self._engine: Optional[DetrEngine] = None
+        self.eval()
+
+    @property
+    def device(self):
+        return self.pixel_mean.device
+
+    @property
+    def dtype(self):
+        return self.pixel_mean.dtype
+
+    def set_precision(self, precision: str, algo: int = ops.ALGO_AUTO):
+        assert precision in ("fp32", "fp16")
+        self.precision, self.algo, self._engine = precision, algo, None
+        return self
+
+    def load_state_dict(self, state_dict, strict: bool = False, assign: bool = False):
+        """Shape-tolerant non-strict load like BaseModelNN.load_state_dict (models/base_model.py:98-143); accepts
+        {"model": sd} checkpoints (focoos_model.py:684-685)."""
+        if "model" in state_dict and isinstance(state_dict["model"], dict):
+            state_dict = state_dict["model"]
+        own = self.state_dict()
+        filtered = {k: v for k, v in state_dict.items() if k in own and tuple(own[k].shape) == tuple(v.shape)}
+        res = super().load_state_dict(filtered, strict=False)
+        self._engine = None
+        if strict and (res.missing_keys or len(filtered) != len(state_dict)):
+            raise RuntimeError(f"load_state_dict(strict): missing {res.missing_keys[:5]} / dropped {len(state_dict) - len(filtered)}")
+        return res
+
+    def _apply(self, fn, *a, **k):
+        self._engine = None
+        return super()._apply(fn, *a, **k)
+
+    def engine(self) -> DetrEngine:
+        if self._engine is None or self._engine.device != self.device or self._engine.precision != self.precision or self._engine.algo != self.algo:
+            self._engine = DetrEngine(self.state_dict(), self.config, self.device, self.precision, self.algo)
+        return self._engine
+
+    def forward(self, images: torch.Tensor, targets: list = [], taps: Optional[dict] = None) -> DETRModelOutput:
+        if self.training or (targets is not None and len(targets) > 0):
+            raise NotImplementedError("focoos_b200: the fine-tune path (losses/backward, SURVEY §8 a20-a21) is a later round")
+        if ops._backend is None and not images.is_cuda:
+            raise RuntimeError("focoos_b200.FAIDetr runs on CUDA (sm_100a) only — no CPU fallback; move the model and inputs to the GPU")
+        scores, boxes = self.engine().forward(images.to(torch.float32), taps)
+        return DETRModelOutput(boxes=boxes, logits=scores, loss=None)

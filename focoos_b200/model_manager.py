@@ -1,0 +1,113 @@
+"""ModelManager / FocoosModel — the reference's L5 facade for the detection hot path
+(`focoos/model_manager.py:43-91`, `focoos/models/focoos_model.py:100,370,575`).
+
+`ModelManager.get(name)` builds the B200-native model from the same registry JSON the reference ships
+(`focoos/model_registry/<name>.json`, `config` section; a copy of the architecture section for the fai-detr
+family is embedded below since the reference tree is not present on the GPU box).  No network: weights come from
+`model_info["weights_path"]`, an explicit `state_dict=` argument, or stay at their initial values.
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .fai_detr import FAIDetr
+from .ports import DETRConfig, FocoosDetections
+from .processor import DETRProcessor
+
+# architecture sections of focoos/model_registry/fai-detr-*.json (config.*; class lists omitted)
+_REGISTRY: Dict[str, dict] = {
+    "fai-detr-l-obj365": {"im_size": 640, "config": {"num_classes": 365, "backbone_config": {"model_type": "resnet", "depth": 50, "variant": "d"}, "num_queries": 300,
+                                                     "resolution": 640, "threshold": 0.5}},
+    "fai-detr-l-coco": {"im_size": 640, "config": {"num_classes": 80, "backbone_config": {"model_type": "resnet", "depth": 50, "variant": "d"}, "num_queries": 300,
+                                                   "resolution": 640, "threshold": 0.5}},
+}
+
+
+@dataclass
+class ModelInfo:
+    name: str
+    model_family: str = "fai_detr"
+    classes: List[str] = field(default_factory=list)
+    im_size: int = 640
+    config: dict = field(default_factory=dict)
+    weights_uri: Optional[str] = None
+
+
+class FocoosModel:
+    """focoos_model.py:100: owns the nn.Module + processor; `infer` / `__call__` / `benchmark`."""
+
+    def __init__(self, model: FAIDetr, model_info: ModelInfo):
+        self.model, self.model_info = model, model_info
+        self.processor = DETRProcessor(model.config, image_size=model_info.im_size).eval()
+        self.model.eval()
+        if torch.cuda.is_available():
+            self.model.cuda()
+
+    @property
+    def device(self):
+        return self.model.device
+
+    def __call__(self, inputs, threshold: Optional[float] = None, batched: bool = False):
+        """focoos_model.py:575-621.  The reference returns only the first image's detections ("we don't support
+        batching yet", :615-621); `batched=True` returns all of them."""
+        t0 = time.perf_counter()
+        images, _ = self.processor.preprocess(inputs, device=self.device, dtype=torch.float32)
+        t1 = time.perf_counter()
+        with torch.no_grad():
+            out = self.model(images)
+        t2 = time.perf_counter()
+        dets = self.processor.postprocess(out, inputs, class_names=self.model_info.classes, threshold=threshold)
+        t3 = time.perf_counter()
+        lat = {"preprocess": round(t1 - t0, 3), "inference": round(t2 - t1, 3), "postprocess": round(t3 - t2, 3)}
+        for d in dets:
+            d.latency = lat
+        return dets if batched else dets[0]
+
+    def infer(self, image, threshold: Optional[float] = None) -> FocoosDetections:
+        """focoos_model.py:370: single image (ndarray HWC uint8 / PIL / tensor) -> FocoosDetections."""
+        return self(image, threshold=threshold)
+
+    def benchmark(self, iterations: int = 50, size=(640, 640), batch: int = 1) -> dict:
+        """BaseModelNN.benchmark (models/base_model.py:160-216): CUDA-event latency of model.forward on 128*randn input."""
+        x = 128 * torch.randn(batch, 3, size[0], size[1], device=self.device)
+        for _ in range(5):
+            self.model(x)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iterations):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            self.model(x)
+            e.record()
+            e.synchronize()
+            ts.append(s.elapsed_time(e))
+        a = np.array(ts)
+        return {"fps": int(1000 * batch / a.mean()), "mean": round(float(a.mean()), 3), "min": round(float(a.min()), 3), "max": round(float(a.max()), 3),
+                "std": round(float(a.std()), 3), "im_size": size[0], "device": str(self.device), "engine": "focoos_b200"}
+
+
+class ModelManager:
+    @classmethod
+    def get(cls, name: str, model_info: Optional[ModelInfo] = None, config: Optional[DETRConfig] = None, state_dict=None,
+            precision: str = "fp16", **kwargs) -> FocoosModel:
+        """model_manager.py:43-91.  `kwargs` override config fields (validated like ConfigManager.from_dict, :336-389)."""
+        if model_info is None:
+            if name not in _REGISTRY:
+                raise ValueError(f"Model {name} not found in the focoos_b200 registry ({sorted(_REGISTRY)})")
+            r = _REGISTRY[name]
+            model_info = ModelInfo(name=name, im_size=r["im_size"], config=dict(r["config"]))
+        if config is None:
+            cd = dict(model_info.config)
+            cd.update(kwargs)
+            config = DETRConfig.from_dict(cd)
+        model = FAIDetr(config, precision=precision)
+        if state_dict is not None:
+            model.load_state_dict(state_dict)
+        elif model_info.weights_uri:
+            model.load_state_dict(torch.load(model_info.weights_uri, map_location="cpu", weights_only=True))
+        return FocoosModel(model, model_info)

@@ -1,0 +1,441 @@
+"""Operator surface of focoos_b200: torch tensors in, hand-written sm_100a kernels underneath.
+
+Every function below validates/allocates on the host and then calls ONE entry point of the C ABI
+declared in `include/focoos_b200.h` (loaded with ctypes from `focoos_b200/lib/libfocoos_b200.so`,
+built in-tree by `focoos_b200/csrc/build.py`).  The same functions are registered as PyTorch custom
+ops in the `focoos_b200::` namespace (see `_register_torch_ops`).
+
+There is NO CPU or eager-PyTorch fallback: without the compiled library, or with non-CUDA tensors,
+every op raises.  (`_backend` exists so that `tests/` can exercise the host-side orchestration on a
+GPU-less machine by installing the reference backend from `oracle/ops_ref.py`; product code never
+sets it.)
+
+Layout: activations are NHWC; a tensor argument may be a channel-slice view of a wider NHWC buffer
+(`t[..., a:b]`): only the last-dim stride must be 1, the pixel pitch is taken from `stride(-2)`.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+F32, F16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_SILU, ACT_GELU = 0, 1, 2, 3
+ACT = {None: 0, "none": 0, "relu": 1, "silu": 2, "gelu": 3}
+ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05 = 0, 1, 2
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libfocoos_b200.so")
+_lib = None
+_backend = None  # tests only
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.float16:
+        return F16
+    raise TypeError(f"focoos_b200: unsupported dtype {t.dtype}")
+
+
+def torch_dtype(code: int) -> torch.dtype:
+    return torch.float32 if code == F32 else torch.float16
+
+
+def load_library():
+    """Load the C-ABI library; raises if it has not been built (no silent fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise RuntimeError(
+            f"focoos_b200: CUDA library not found at {_LIB_PATH}. Build it with "
+            "`python -m focoos_b200.csrc.build` (or `__graft_entry__.build()`); there is no CPU fallback."
+        )
+    lib = ctypes.CDLL(_LIB_PATH)
+    lib.fb200_last_error.restype = ctypes.c_char_p
+    for name in EXPORTED_SYMBOLS:
+        if name != "fb200_last_error":
+            getattr(lib, name).restype = ctypes.c_int
+    _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = (
+    "fb200_last_error", "fb200_version", "fb200_device_supports_tcgen05", "fb200_stem_conv3x3s2", "fb200_conv2d",
+    "fb200_maxpool3x3s2", "fb200_avgpool2x2_ceil", "fb200_resize_bilinear", "fb200_add", "fb200_layernorm",
+    "fb200_attention", "fb200_msda", "fb200_row_select", "fb200_rowmax", "fb200_topk", "fb200_gather_rows",
+    "fb200_box_op", "fb200_detr_postprocess",
+)
+
+_launch_count = 0
+
+
+def launch_count() -> int:
+    """Number of kernels launched through this module since import (for bench.py's `gpu_launches`)."""
+    return _launch_count
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = load_library().fb200_last_error()
+        raise RuntimeError(f"focoos_b200.{what} failed ({rc}): {msg.decode() if msg else '?'}")
+
+
+def _p(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _pitch(t: torch.Tensor, free_batch_stride: bool = False) -> int:
+    """pixel pitch (elements) of an NHWC / [.., L, C] tensor that may be a channel slice of a wider buffer."""
+    assert t.stride(-1) == 1, "last dim must be contiguous"
+    p = t.stride(-2) if t.dim() >= 2 else t.shape[-1]
+    # outer dims must be dense w.r.t. the pitch
+    exp = p
+    for d in range(t.dim() - 2, -1, -1):
+        if t.shape[d] != 1 and not (d == 0 and free_batch_stride and t.dim() == 4):
+            assert t.stride(d) == exp, f"unsupported view strides {t.stride()} for shape {tuple(t.shape)}"
+        exp *= t.shape[d]
+    return p
+
+
+def _batch_stride(t: torch.Tensor) -> int:
+    return t.stride(0) if (t.dim() == 4 and t.shape[0] > 1) else 0
+
+
+class CudaBackend:
+    """Thin marshalling layer: tensors -> raw pointers/sizes -> C ABI."""
+
+    def __init__(self):
+        self.lib = load_library()
+
+    @staticmethod
+    def _cuda(*ts):
+        for t in ts:
+            if t is not None and not t.is_cuda:
+                raise RuntimeError("focoos_b200: tensors must live on a CUDA device (no CPU fallback)")
+
+    def _call(self, name, *args):
+        global _launch_count
+        _launch_count += 1
+        _check(getattr(self.lib, name)(*args), name)
+
+    def stem_conv(self, img, w, scale, bias, mean, std, act, out):
+        self._cuda(img, w, out)
+        B, _, H, W = img.shape
+        m = (ctypes.c_float * 3)(*mean)
+        s = (ctypes.c_float * 3)(*std)
+        self._call("fb200_stem_conv3x3s2", _p(img), B, H, W, _p(w), _p(scale), _p(bias), m, s, act, _p(out), _dt(out), out.shape[-1], _stream())
+
+    def conv2d(self, x, w, scale, bias, stride, pad, act, residual, out, algo):
+        self._cuda(x, w, out)
+        B, H, W, Cin = x.shape
+        Cout, KH, KW, _ = w.shape
+        self._call("fb200_conv2d", _p(x), _dt(x), B, H, W, Cin, _pitch(x), _p(w), KH, KW, stride, pad, _p(scale), _p(bias), _p(residual),
+                   0 if residual is None else _pitch(residual), act, _p(out), _dt(out), _pitch(out, True), ctypes.c_int64(_batch_stride(out)), Cout, algo, _stream())
+
+    def maxpool3x3s2(self, x, out):
+        self._cuda(x, out)
+        B, H, W, C = x.shape
+        self._call("fb200_maxpool3x3s2", _p(x), _dt(x), B, H, W, C, _p(out), _stream())
+
+    def avgpool2x2(self, x, out):
+        self._cuda(x, out)
+        B, H, W, C = x.shape
+        self._call("fb200_avgpool2x2_ceil", _p(x), _dt(x), B, H, W, C, _p(out), _stream())
+
+    def resize_bilinear(self, x, out):
+        self._cuda(x, out)
+        B, H, W, C = x.shape
+        self._call("fb200_resize_bilinear", _p(x), _dt(x), B, H, W, C, _pitch(x), _p(out), out.shape[1], out.shape[2], _pitch(out), _stream())
+
+    def add(self, a, b, out):
+        self._cuda(a, b, out)
+        C = a.shape[-1]
+        self._call("fb200_add", _p(a), _p(b), _p(out), _dt(a), ctypes.c_int64(a.numel() // C), ctypes.c_int64(b.numel() // C), C, _stream())
+
+    def layernorm(self, x, res, gamma, beta, out, eps):
+        self._cuda(x, out)
+        C = x.shape[-1]
+        self._call("fb200_layernorm", _p(x), _p(res), _p(gamma), _p(beta), _p(out), _dt(x), ctypes.c_int64(x.numel() // C), C, ctypes.c_float(eps), _stream())
+
+    def attention(self, q, k, v, out, heads, scale):
+        self._cuda(q, k, v, out)
+        B, Lq, C = q.shape
+        self._call("fb200_attention", _p(q), _pitch(q), _p(k), _pitch(k), _p(v), _pitch(v), _p(out), _pitch(out), _dt(q), B, Lq, k.shape[1],
+                   heads, C // heads, ctypes.c_float(scale), _stream())
+
+    def msda(self, value, oa, ref, shapes, P, heads, out):
+        self._cuda(value, oa, ref, out)
+        B, S, _ = value.shape
+        Q = oa.shape[1]
+        flat = [int(v) for hw in shapes for v in hw]
+        sh = (ctypes.c_int * len(flat))(*flat)
+        self._call("fb200_msda", _p(value), _dt(value), _pitch(value), _p(oa), _dt(oa), _pitch(oa), _p(ref), sh, len(shapes), P, B, S, Q, heads,
+                   _p(out), _dt(out), _pitch(out), _stream())
+
+    def row_select(self, x, valid, fill, out):
+        self._cuda(x, valid, fill, out)
+        C = x.shape[-1]
+        self._call("fb200_row_select", _p(x), _p(valid), _p(fill), _p(out), _dt(x), ctypes.c_int64(x.numel() // C), valid.numel(), C, _stream())
+
+    def rowmax(self, x, out):
+        self._cuda(x, out)
+        N = x.shape[-1]
+        self._call("fb200_rowmax", _p(x), _dt(x), ctypes.c_int64(out.numel()), N, _pitch(x), _p(out), _stream())
+
+    def topk(self, x, K, out_idx, out_val):
+        self._cuda(x, out_idx)
+        B, N = x.shape
+        self._call("fb200_topk", _p(x), B, N, K, _p(out_idx), _p(out_val), _stream())
+
+    def gather_rows(self, src, idx, out):
+        self._cuda(src, idx, out)
+        B, S, C = src.shape
+        self._call("fb200_gather_rows", _p(src), _dt(src), B, S, C, _pitch(src), _p(idx), idx.shape[1], _p(out), _stream())
+
+    def box_op(self, mode, x, ref, idx, out):
+        self._cuda(x, out)
+        self._call("fb200_box_op", mode, _p(x), _p(ref), _p(idx), _p(out), ctypes.c_int64(x.numel()), _stream())
+
+    def detr_postprocess(self, scores, boxes, sizes, K, thr, out_scores, out_labels, out_boxes, out_query, out_count):
+        self._cuda(scores, boxes, sizes)
+        B, Q, C = scores.shape
+        self._call("fb200_detr_postprocess", _p(scores), _p(boxes), _p(sizes), B, Q, C, K, ctypes.c_float(thr), _p(out_scores), _p(out_labels),
+                   _p(out_boxes), _p(out_query), _p(out_count), _stream())
+
+
+_cuda_backend = None
+
+
+def _be():
+    global _cuda_backend
+    if _backend is not None:
+        return _backend
+    if _cuda_backend is None:
+        _cuda_backend = CudaBackend()
+    return _cuda_backend
+
+
+def supports_tcgen05() -> bool:
+    return load_library().fb200_device_supports_tcgen05() == 1
+
+
+# ------------------------------------------------------------------------------------------------
+# public tensor-level API
+# ------------------------------------------------------------------------------------------------
+def stem_conv(img: torch.Tensor, w, scale, bias, mean: Sequence[float], std: Sequence[float], act=ACT_RELU, out_dtype=torch.float32):
+    """[B,3,H,W] fp32 NCHW 0..255 -> normalise -> conv3x3/s2 + BN + act -> NHWC [B,H/2,W/2,32]."""
+    assert img.dtype == torch.float32 and img.dim() == 4 and img.shape[1] == 3 and img.is_contiguous()
+    B, _, H, W = img.shape
+    out = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, w.shape[0]), dtype=out_dtype, device=img.device)
+    _be().stem_conv(img, w, scale, bias, [float(v) for v in mean], [float(v) for v in std], act, out)
+    return out
+
+
+def conv2d(x, w, scale=None, bias=None, *, stride=1, pad=0, act=ACT_NONE, residual=None, out=None, out_dtype=None, algo=ALGO_AUTO):
+    """NHWC conv with fused per-channel scale/bias (folded BN), residual add and activation.
+    w: [Cout,KH,KW,Cin] (same dtype as x).  `out` may be a channel slice of a wider NHWC buffer."""
+    assert x.dim() == 4 and w.dim() == 4 and w.is_contiguous() and w.dtype == x.dtype and w.shape[3] == x.shape[3]
+    B, H, W, _ = x.shape
+    Cout, KH, KW, _ = w.shape
+    Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+    if out is None:
+        out = torch.empty((B, Ho, Wo, Cout), dtype=out_dtype or x.dtype, device=x.device)
+    assert tuple(out.shape) == (B, Ho, Wo, Cout), (tuple(out.shape), (B, Ho, Wo, Cout))
+    if residual is not None:
+        assert residual.shape == out.shape and residual.dtype == out.dtype
+    _be().conv2d(x, w, scale, bias, stride, pad, act, residual, out, algo)
+    return out
+
+
+def linear(x, w, bias=None, *, act=ACT_NONE, residual=None, out=None, out_dtype=None, algo=ALGO_AUTO):
+    """y = act(x @ w.T + bias (+ residual)); x [..., K] (rows may be pitched), w [N, K]."""
+    lead = x.shape[:-1]
+    K = x.shape[-1]
+    N = w.shape[0]
+    x4 = x.reshape(1, 1, -1, K) if x.is_contiguous() else _as4(x)
+    r4 = None if residual is None else (residual.reshape(1, 1, -1, N) if residual.is_contiguous() else _as4(residual))
+    o4 = None if out is None else (out.reshape(1, 1, -1, N) if out.is_contiguous() else _as4(out))
+    y = conv2d(x4, w.reshape(N, 1, 1, K), None, bias, act=act, residual=r4, out=o4, out_dtype=out_dtype, algo=algo)
+    return out if out is not None else y.reshape(*lead, N)
+
+
+def _as4(t):
+    """[..., L, C] pitched view -> [1,1,M,C] view (requires uniform pitch, checked by _pitch)."""
+    p = _pitch(t)
+    M = t.numel() // t.shape[-1]
+    return t.as_strided((1, 1, M, t.shape[-1]), (M * p, M * p, p, 1), t.storage_offset())
+
+
+def maxpool3x3s2(x):
+    B, H, W, C = x.shape
+    out = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C), dtype=x.dtype, device=x.device)
+    _be().maxpool3x3s2(x.contiguous(), out)
+    return out
+
+
+def avgpool2x2(x):
+    B, H, W, C = x.shape
+    out = torch.empty((B, (H + 1) // 2, (W + 1) // 2, C), dtype=x.dtype, device=x.device)
+    _be().avgpool2x2(x.contiguous(), out)
+    return out
+
+
+def resize_bilinear(x, size: Tuple[int, int], out=None):
+    B, H, W, C = x.shape
+    if out is None:
+        out = torch.empty((B, size[0], size[1], C), dtype=x.dtype, device=x.device)
+    assert tuple(out.shape) == (B, size[0], size[1], C)
+    _be().resize_bilinear(x, out)
+    return out
+
+
+def add(a, b):
+    """a + b with b broadcast over leading dims (a [B,L,C], b [L,C] or [1,L,C] or same shape)."""
+    a = a.contiguous()
+    b = b.contiguous()
+    out = torch.empty_like(a)
+    _be().add(a, b, out)
+    return out
+
+
+def layernorm(x, gamma, beta, residual=None, eps=1e-5):
+    x = x.contiguous()
+    if residual is not None:
+        residual = residual.contiguous()
+        assert residual.shape == x.shape
+    out = torch.empty_like(x)
+    _be().layernorm(x, residual, gamma, beta, out, eps)
+    return out
+
+
+def attention(q, k, v, heads: int, scale: float):
+    """softmax(q k^T * scale) v per head; q [B,Lq,C], k,v [B,Lk,C] (may be column slices of one buffer)."""
+    B, Lq, C = q.shape
+    out = torch.empty((B, Lq, C), dtype=q.dtype, device=q.device)
+    _be().attention(q, k, v, out, heads, scale)
+    return out
+
+
+def msda(value, oa, ref, shapes, num_points: int, heads: int, out_dtype=None):
+    """value [B,S,heads*32]; oa [B,Q,heads*L*P*3] (offsets then logits); ref [B,Q,4] fp32 -> [B,Q,heads*32]."""
+    B, Q = oa.shape[0], oa.shape[1]
+    out = torch.empty((B, Q, heads * 32), dtype=out_dtype or value.dtype, device=value.device)
+    _be().msda(value, oa, ref.contiguous(), [tuple(s) for s in shapes], num_points, heads, out)
+    return out
+
+
+def row_select(x, valid_u8, fill_f32):
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    _be().row_select(x, valid_u8, fill_f32, out)
+    return out
+
+
+def rowmax(x):
+    out = torch.empty(x.shape[:-1], dtype=torch.float32, device=x.device)
+    _be().rowmax(x, out)
+    return out
+
+
+def topk(x, k: int):
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous()
+    idx = torch.empty((x.shape[0], k), dtype=torch.int32, device=x.device)
+    val = torch.empty((x.shape[0], k), dtype=torch.float32, device=x.device)
+    _be().topk(x, k, idx, val)
+    return val, idx
+
+
+def gather_rows(src, idx):
+    B, S, C = src.shape
+    out = torch.empty((B, idx.shape[1], C), dtype=src.dtype, device=src.device)
+    _be().gather_rows(src, idx, out)
+    return out
+
+
+def box_sigmoid(x):
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    _be().box_op(0, x, None, None, out)
+    return out
+
+
+def box_refine(delta, ref):
+    delta, ref = delta.contiguous(), ref.contiguous()
+    out = torch.empty_like(delta)
+    _be().box_op(1, delta, ref, None, out)
+    return out
+
+
+def box_add_anchors(x, anchors, idx):
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    _be().box_op(2, x, anchors, idx.contiguous(), out)
+    return out
+
+
+def box_cxcywh_to_xyxy(x):
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    _be().box_op(3, x, None, None, out)
+    return out
+
+
+def detr_postprocess(scores, boxes, sizes_i32, top_k: int, threshold: float):
+    """-> (scores [B,K], labels [B,K] i32, boxes [B,K,4] i32, query [B,K] i32, count [B] i32), sorted by score."""
+    B = scores.shape[0]
+    dev = scores.device
+    o_s = torch.empty((B, top_k), dtype=torch.float32, device=dev)
+    o_l = torch.empty((B, top_k), dtype=torch.int32, device=dev)
+    o_b = torch.empty((B, top_k, 4), dtype=torch.int32, device=dev)
+    o_q = torch.empty((B, top_k), dtype=torch.int32, device=dev)
+    o_c = torch.empty((B,), dtype=torch.int32, device=dev)
+    _be().detr_postprocess(scores.contiguous(), boxes.contiguous(), sizes_i32, top_k, float(threshold), o_s, o_l, o_b, o_q, o_c)
+    return o_s, o_l, o_b, o_q, o_c
+
+
+# ------------------------------------------------------------------------------------------------
+# torch.library registration: focoos_b200::<op>  (out-variant schemas; the python API above allocates)
+# ------------------------------------------------------------------------------------------------
+_torch_lib = None
+
+
+def _register_torch_ops():
+    global _torch_lib
+    if _torch_lib is not None:
+        return
+    lib = torch.library.Library("focoos_b200", "DEF")
+    defs = {
+        "conv2d": ("(Tensor x, Tensor w, Tensor? scale, Tensor? bias, int stride, int pad, int act, Tensor? residual, Tensor(a!) out, int algo) -> ()",
+                   lambda x, w, scale, bias, stride, pad, act, residual, out, algo: _be().conv2d(x, w, scale, bias, stride, pad, act, residual, out, algo)),
+        "maxpool3x3s2": ("(Tensor x, Tensor(a!) out) -> ()", lambda x, out: _be().maxpool3x3s2(x, out)),
+        "avgpool2x2": ("(Tensor x, Tensor(a!) out) -> ()", lambda x, out: _be().avgpool2x2(x, out)),
+        "resize_bilinear": ("(Tensor x, Tensor(a!) out) -> ()", lambda x, out: _be().resize_bilinear(x, out)),
+        "add": ("(Tensor a, Tensor b, Tensor(a!) out) -> ()", lambda a, b, out: _be().add(a, b, out)),
+        "layernorm": ("(Tensor x, Tensor? res, Tensor gamma, Tensor beta, Tensor(a!) out, float eps) -> ()",
+                      lambda x, res, gamma, beta, out, eps: _be().layernorm(x, res, gamma, beta, out, eps)),
+        "attention": ("(Tensor q, Tensor k, Tensor v, Tensor(a!) out, int heads, float scale) -> ()",
+                      lambda q, k, v, out, heads, scale: _be().attention(q, k, v, out, heads, scale)),
+        "msda": ("(Tensor value, Tensor oa, Tensor ref, int[] shapes, int points, int heads, Tensor(a!) out) -> ()",
+                 lambda value, oa, ref, shapes, points, heads, out: _be().msda(value, oa, ref, [tuple(shapes[i:i + 2]) for i in range(0, len(shapes), 2)], points, heads, out)),
+        "rowmax": ("(Tensor x, Tensor(a!) out) -> ()", lambda x, out: _be().rowmax(x, out)),
+        "topk": ("(Tensor x, int k, Tensor(a!) out_idx, Tensor(b!) out_val) -> ()", lambda x, k, oi, ov: _be().topk(x, k, oi, ov)),
+        "gather_rows": ("(Tensor src, Tensor idx, Tensor(a!) out) -> ()", lambda src, idx, out: _be().gather_rows(src, idx, out)),
+        "box_op": ("(int mode, Tensor x, Tensor? ref, Tensor? idx, Tensor(a!) out) -> ()", lambda mode, x, ref, idx, out: _be().box_op(mode, x, ref, idx, out)),
+    }
+    for name, (schema, fn) in defs.items():
+        lib.define(name + schema)
+        lib.impl(name, fn, "CUDA")
+    _torch_lib = lib
+
+
+try:  # registration itself needs no GPU and no compiled library
+    _register_torch_ops()
+except Exception:  # pragma: no cover - e.g. double import under a different module name
+    pass

@@ -1,0 +1,124 @@
+"""DETRProcessor — host-side mirror of `focoos/models/fai_detr/processor.py` + `focoos/processor/base_processor.py`.
+
+preprocess: list of HWC uint8 / CHW tensors -> [B,3,S,S] fp32 on the device (H2D copy + per-image bilinear
+resize to `im_size`, align_corners=False — Processor.get_torch_batch, base_processor.py:223-296).
+postprocess: ONE fused kernel for the whole batch (top-k over Q*C, label/query decode, threshold, scale to the
+original image, round-half-even), ONE device->host copy of the compacted result, then FocoosDet objects —
+replacing the reference's per-image Python loop with 3 `.cpu().tolist()` syncs each (processor.py:183-217).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import ops
+from .ports import DETRConfig, DETRModelOutput, FocoosDet, FocoosDetections
+
+
+def get_image_sizes(inputs) -> List[Tuple[int, int]]:
+    """base_processor.py:176-221: (height, width) of every ORIGINAL input image."""
+    if isinstance(inputs, (torch.Tensor, np.ndarray)) or not isinstance(inputs, (list, tuple)):
+        inputs = [inputs]
+    sizes = []
+    for img in inputs:
+        if isinstance(img, torch.Tensor):
+            h, w = img.shape[-2:]
+        elif isinstance(img, np.ndarray):
+            h, w = img.shape[-3:-1] if img.ndim > 3 else img.shape[:2]
+        elif hasattr(img, "size") and not callable(img.size):  # PIL
+            w, h = img.size
+        else:
+            raise ValueError(f"Unsupported input type: {type(img)}")
+        sizes.append((int(h), int(w)))
+    return sizes
+
+
+class DETRProcessor:
+    def __init__(self, config: DETRConfig, image_size: Optional[Union[int, Tuple[int, int]]] = None):
+        self.config = config
+        self.image_size = image_size
+        self.top_k = config.top_k
+        self.threshold = config.threshold
+        self.training = False
+
+    def eval(self):
+        self.training = False
+        return self
+
+    # -- preprocess -------------------------------------------------------------------------------
+    def preprocess(self, inputs, device, dtype: torch.dtype = torch.float32):
+        if self.training:
+            raise ValueError("During training, inputs should be a list of DetectionDatasetDict")
+        target = None
+        if self.image_size is not None:
+            target = (self.image_size, self.image_size) if isinstance(self.image_size, int) else tuple(self.image_size)
+        return self.get_torch_batch(inputs, target, device, dtype), []
+
+    def get_torch_batch(self, inputs, target_size, device, dtype):
+        if not isinstance(inputs, (list, tuple)):
+            inputs = [inputs]
+        outs = []
+        for inp in inputs:
+            if hasattr(inp, "size") and not isinstance(inp, (np.ndarray, torch.Tensor)):
+                inp = np.array(inp)
+            if isinstance(inp, np.ndarray):
+                inp = torch.from_numpy(np.ascontiguousarray(inp))
+            if inp.dim() == 3:
+                inp = inp.unsqueeze(0)
+            if inp.shape[1] != 3 and inp.shape[-1] == 3:
+                inp = inp.permute(0, 3, 1, 2)
+            if device is not None:
+                inp = inp.to(device, non_blocking=True)
+            inp = inp.to(dtype)
+            if target_size is not None and tuple(inp.shape[-2:]) != tuple(target_size):
+                inp = self._resize(inp, target_size)
+            outs.append(inp.squeeze(0))
+        return torch.stack(outs, 0).contiguous()
+
+    @staticmethod
+    def _resize(img_nchw: torch.Tensor, size):
+        """bilinear, align_corners=False, via the NHWC resize kernel (channels padded 3 -> 4 for vector access)."""
+        _, C, H, W = img_nchw.shape
+        x = torch.zeros((1, H, W, 4), dtype=img_nchw.dtype, device=img_nchw.device)
+        x[..., :C] = img_nchw.permute(0, 2, 3, 1)
+        y = ops.resize_bilinear(x, size)
+        return y[..., :C].permute(0, 3, 1, 2).contiguous()
+
+    # -- postprocess ------------------------------------------------------------------------------
+    def postprocess_tensors(self, output: DETRModelOutput, image_sizes: Sequence[Tuple[int, int]], top_k=None, threshold=None):
+        top_k = top_k or self.top_k
+        threshold = threshold or self.threshold  # `x or default` idiom of the reference (a falsy 0.0 -> default)
+        sizes = torch.tensor(list(image_sizes), dtype=torch.int32).to(output.logits.device, non_blocking=True)
+        return ops.detr_postprocess(output.logits, output.boxes, sizes, top_k, threshold)
+
+    def postprocess(self, output: DETRModelOutput, inputs, class_names: Sequence[str] = (), top_k=None, threshold=None) -> List[FocoosDetections]:
+        image_sizes = get_image_sizes(inputs)
+        B = output.boxes.shape[0]
+        assert len(image_sizes) == B, f"Expected image sizes {len(image_sizes)} to match batch size {B}"
+        s, l, b, q, c = self.postprocess_tensors(output, image_sizes, top_k, threshold)
+        K = s.shape[1]
+        # one packed D2H copy: [B, K, 7] (score bits, label, 4 box coords, query) + counts
+        packed = torch.cat([s.view(torch.int32).unsqueeze(-1), l.unsqueeze(-1), b, q.unsqueeze(-1)], dim=-1)
+        packed_h = torch.cat([packed.reshape(B, -1), c.unsqueeze(-1)], dim=1).cpu().numpy()
+        res = []
+        for i in range(B):
+            n = int(packed_h[i, -1])
+            row = packed_h[i, :-1].reshape(K, 7)[:n]
+            confs = row[:, 0].copy().view(np.float32).tolist()
+            labels = row[:, 1].tolist()
+            boxes = row[:, 2:6].tolist()
+            res.append(FocoosDetections(detections=[
+                FocoosDet(bbox=bx, conf=cf, cls_id=lb, label=class_names[lb] if class_names else None)
+                for bx, cf, lb in zip(boxes, confs, labels)]))
+        return res
+
+    def export_postprocess(self, output, inputs, class_names=(), top_k=None, threshold: float = 0.5):
+        """processor.py:219-236: output = (boxes, logits) of an exported graph."""
+        boxes, logits = output[0], output[1]
+        if isinstance(boxes, np.ndarray):
+            boxes = torch.from_numpy(boxes)
+        if isinstance(logits, np.ndarray):
+            logits = torch.from_numpy(logits)
+        return self.postprocess(DETRModelOutput(boxes=boxes, logits=logits, loss=None), inputs, class_names, 300 if top_k is None else top_k, threshold)

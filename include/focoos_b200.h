@@ -1,0 +1,131 @@
+/*
+ * focoos_b200 — C ABI of the B200-native (sm_100a) kernels behind the Focoos detection hot path.
+ *
+ * The reference (FocoosAI/focoos v0.25.0) is pure Python: it has NO FFI boundary for this path; every
+ * operator below replaces a chain of torch library calls at the cited reference call site
+ * (paths relative to /root/reference/focoos).  The Python side of the boundary is
+ * `focoos_b200/ops.py` (ctypes + torch.library registration `focoos_b200::*`); the binding a
+ * reference maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer unless the name ends in `_host`.  The caller owns all
+ *     buffers (activations, weights, outputs); the library allocates nothing persistent.
+ *   - Activations are NHWC ("channels-last"): element (b,h,w,c) at ((b*H+h)*W+w)*pitch + c,
+ *     `pitch >= C` in ELEMENTS, which lets a kernel read/write a channel slice of a wider tensor
+ *     (concat-free CSP/FPN blocks).  Token tensors [B,L,C] are the same thing with H=1.
+ *   - `dtype`: FB200_F32 (fp32 SIMT kernels; the near-bit-exact parity mode) or FB200_F16
+ *     (fp16 storage, fp32 accumulate; tcgen05 tensor cores for conv / linear).
+ *   - Work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises.
+ *     Stateless and re-entrant; one process per GPU.
+ *   - Return value: 0 on success, negative fb200_status on error; message via fb200_last_error()
+ *     (thread-local).  Python wrappers raise RuntimeError.
+ */
+#ifndef FOCOOS_B200_H_
+#define FOCOOS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum { FB200_OK = 0, FB200_ERR_INVALID = -1, FB200_ERR_UNSUPPORTED = -2, FB200_ERR_CUDA = -3 } fb200_status;
+typedef enum { FB200_F32 = 0, FB200_F16 = 1 } fb200_dtype;
+typedef enum { FB200_ACT_NONE = 0, FB200_ACT_RELU = 1, FB200_ACT_SILU = 2, FB200_ACT_GELU = 3,
+               FB200_ACT_RESIDUAL_AFTER = 16 /* OR-ed flag: out = act(conv) + residual instead of act(conv + residual) */ } fb200_act;
+typedef enum { FB200_ALGO_AUTO = 0, FB200_ALGO_SIMT = 1, FB200_ALGO_TCGEN05 = 2 } fb200_algo;
+
+const char* fb200_last_error(void);
+int fb200_version(void);
+/* 1 if the current device is sm_100 (tcgen05 path usable), 0 otherwise, <0 on error. */
+int fb200_device_supports_tcgen05(void);
+
+/* ---- a2: ResNet-vd stem, first conv fused with the input normalisation ------------------------
+ * Replaces `(images - pixel_mean) / pixel_std` (models/fai_detr/modelling.py:1349) followed by
+ * ConvNormLayer conv1_1 (3x3, stride 2, pad 1, BN, ReLU; nn/backbone/resnet.py:181-186,
+ * nn/layers/conv.py:93-97).  Zero padding applies to the NORMALISED image.
+ * img: [B,3,H,W] fp32 NCHW, 0..255.  mean3_host/std3_host: 3 floats each in HOST memory.  w: [Cout][3][3][3] fp32 as (kh,kw,ci).  out: NHWC [B,H/2,W/2,Cout]. */
+int fb200_stem_conv3x3s2(const float* img, int B, int H, int W, const float* w, const float* scale, const float* bias,
+                         const float* mean3_host, const float* std3_host, int act, void* out, int out_dtype, int Cout, void* stream);
+
+/* ---- a2,a3,a5,a7: conv (+ folded BN scale/bias, + residual, + activation), implicit GEMM -------
+ * Replaces ConvNormLayer.forward (nn/layers/conv.py:78-98), BottleNeck residual add + ReLU
+ * (nn/backbone/resnet.py:106-121), RepVggBlock (models/fai_detr/modelling.py:39-45, re-parameterised
+ * on the host), CSPRepLayer add (:103-107), and every nn.Linear on the path (as a 1x1 conv over
+ * H=1,W=M tokens: modelling.py:848-882,1204-1207; nn/layers/base.py:51-62).
+ *   out[m, n] = act( (sum_k A[m,k] * w[n,k]) * scale[n] + bias[n] + residual[m,n] )
+ * x: [B,H,W,Cin] (pitch x_pitch), w: [Cout][KH][KW][Cin] same dtype as x.
+ * scale/bias: fp32 [Cout] or NULL (=1 / 0).  residual: NULL or same dtype as out, [B,Ho,Wo,Cout]
+ * (pitch res_pitch).  out dtype may differ from x dtype (fp32 heads on fp16 features).
+ * out_batch_stride: elements between consecutive images of `out` (0 = dense Ho*Wo*out_pitch); lets a level's
+ * projection be written straight into its rows of the concatenated [B, sum(HW), C] memory (modelling.py:1165).
+ * algo: FB200_ALGO_AUTO picks tcgen05 when dtype==F16 and the shape qualifies. */
+int fb200_conv2d(const void* x, int x_dtype, int B, int H, int W, int Cin, int x_pitch, const void* w, int KH, int KW,
+                 int stride, int pad, const float* scale, const float* bias, const void* residual, int res_pitch,
+                 int act, void* out, int out_dtype, int out_pitch, int64_t out_batch_stride, int Cout, int algo, void* stream);
+
+/* ---- a2: pools.  F.max_pool2d(3,2,1) (nn/backbone/resnet.py:254); AvgPool2d(2,2,0,ceil_mode=True)
+ * of the vd shortcut (nn/backbone/resnet.py:95). */
+int fb200_maxpool3x3s2(const void* x, int dtype, int B, int H, int W, int C, void* out, void* stream);
+int fb200_avgpool2x2_ceil(const void* x, int dtype, int B, int H, int W, int C, void* out, void* stream);
+
+/* ---- a5: F.interpolate(mode="bilinear", align_corners=False) (models/fai_detr/modelling.py:334,342),
+ * writing straight into a channel slice of the concat buffer. */
+int fb200_resize_bilinear(const void* x, int dtype, int B, int H, int W, int C, int x_pitch, void* out, int Ho, int Wo,
+                          int out_pitch, void* stream);
+
+/* ---- elementwise: out = a + b (b broadcast over the leading `rows/brows` blocks when brows < rows).
+ * with_pos_embed (nn/layers/transformer.py:579-581, modelling.py:918-919). */
+int fb200_add(const void* a, const void* b, void* out, int dtype, int64_t rows, int64_t brows, int C, void* stream);
+
+/* ---- a4,a9: out = LayerNorm(x (+ res)) * gamma + beta, eps 1e-5, biased variance (nn.LayerNorm;
+ * nn/layers/transformer.py:590-600, modelling.py:939-956).  x,res,out: [M,C] contiguous. */
+int fb200_layernorm(const void* x, const void* res, const float* gamma, const float* beta, void* out, int dtype,
+                    int64_t M, int C, float eps, void* stream);
+
+/* ---- a4,a9: softmax(Q K^T * scale) V per (batch, head); nn.MultiheadAttention core
+ * (SURVEY A.6).  q/k/v/out rows are tokens; head h uses columns [h*hd, (h+1)*hd). hd must be 32. */
+int fb200_attention(const void* q, int q_pitch, const void* k, int k_pitch, const void* v, int v_pitch, void* out,
+                    int out_pitch, int dtype, int B, int Lq, int Lk, int heads, int head_dim, float scale, void* stream);
+
+/* ---- a10: multi-scale deformable attention core, softmax over levels*points fused.
+ * Replaces MSDeformableAttention.forward lines 854-880 (models/fai_detr/modelling.py) +
+ * ms_deform_attn_core_pytorch (nn/layers/deformable.py:10-35).
+ * value: [B,S,heads*32] (pitch v_pitch).  oa: [B*Q, heads*L*P*3] fp32 or fp16 = sampling offsets
+ * [heads][L][P][2] followed by attention logits [heads][L*P] (one fused linear).  ref: [B*Q,4] fp32
+ * (cx,cy,w,h in sigmoid space).  shapes_host: L pairs (H_l, W_l) in HOST memory.  out: [B*Q, heads*32]. */
+int fb200_msda(const void* value, int v_dtype, int v_pitch, const void* oa, int oa_dtype, int oa_pitch, const float* ref,
+               const int* shapes_host, int L, int P, int B, int S, int Q, int heads, void* out, int out_dtype,
+               int out_pitch, void* stream);
+
+/* ---- a8: query selection helpers (models/fai_detr/modelling.py:1202-1229) ---------------------- */
+/* out[r,:] = valid[r % S] ? x[r,:] : fill[:]   (memory * valid_mask folded behind enc_output.0) */
+int fb200_row_select(const void* x, const uint8_t* valid, const float* fill, void* out, int dtype, int64_t rows, int S,
+                     int C, void* stream);
+/* out[r] = max_n x[r,n] (fp32 out).  enc_outputs_class.max(-1) (:1210) */
+int fb200_rowmax(const void* x, int dtype, int64_t rows, int N, int pitch, float* out, void* stream);
+/* per row: K largest, sorted descending, ties by ascending index.  torch.topk (:1214; processor.py:147) */
+int fb200_topk(const float* x, int B, int N, int K, int* out_idx, float* out_val, void* stream);
+/* out[b,k,:] = src[b, idx[b,k], :]   (gather :1216-1229) */
+int fb200_gather_rows(const void* src, int dtype, int B, int S, int C, int pitch, const int* idx, int K, void* out,
+                      void* stream);
+
+/* ---- a8,a9,a11: box arithmetic in fp32 ---------------------------------------------------------
+ * mode 0: out = sigmoid(x)                                    (modelling.py:985, :397)
+ * mode 1: out = sigmoid(x + inverse_sigmoid(ref)), eps 1e-5   (modelling.py:1003; nn/layers/functional.py:4-6)
+ * mode 2: out = x + anchors[idx]  (x,[n,4]; anchors [S,4]; idx [n] with per-batch rows)  (:1207 after gather)
+ * mode 3: out = cxcywh -> xyxy                                (utils/box.py:14-17) */
+int fb200_box_op(int mode, const float* x, const float* ref, const int* idx, float* out, int64_t n, void* stream);
+
+/* ---- a12: DETRProcessor.postprocess (models/fai_detr/processor.py:146-217), whole batch, one launch.
+ * scores [B,Q,C] fp32 probabilities, boxes [B,Q,4] xyxy in [0,1], sizes [B,2] int32 (H,W) of the ORIGINAL
+ * images.  Outputs are padded to K per image, sorted by descending score (ties: ascending flat index);
+ * count[b] = number with score > threshold (strict); boxes scaled, rintf (half-to-even) -> int32. */
+int fb200_detr_postprocess(const float* scores, const float* boxes, const int* sizes, int B, int Q, int C, int K,
+                           float threshold, float* out_scores, int* out_labels, int* out_boxes, int* out_query,
+                           int* out_count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FOCOOS_B200_H_ */

@@ -1,0 +1,144 @@
+"""Per-operator CPU references with the SAME signatures as `focoos_b200.ops.CudaBackend`.
+
+TEST INFRASTRUCTURE — NOT PRODUCT CODE (see oracle/detr_oracle.py header for the import rules).
+Two uses: (1) `-m gpu` tests compare each CUDA kernel against these on seeded inputs;
+(2) `-m "not gpu"` tests install `RefBackend()` as `focoos_b200.ops._backend` to run the HOST
+orchestration (weight packing, fused NHWC graph, level ordering, slices) on a GPU-less machine
+and compare it with the golden fixtures.  Everything computes in fp32 with plain torch ops
+(F.conv2d, F.grid_sample, ...) — i.e. the reference's own library calls — and rounds to the output
+dtype at the end.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+def _act(x, act):
+    return [lambda v: v, F.relu, F.silu, F.gelu][act](x)
+
+
+def _f(t):
+    return None if t is None else t.float()
+
+
+class RefBackend:
+    def stem_conv(self, img, w, scale, bias, mean, std, act, out):
+        x = (img - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)
+        y = F.conv2d(x, w.permute(0, 3, 1, 2).float(), None, 2, 1)
+        if scale is not None:
+            y = y * scale.view(1, -1, 1, 1)
+        if bias is not None:
+            y = y + bias.view(1, -1, 1, 1)
+        out.copy_(_act(y, act).permute(0, 2, 3, 1).to(out.dtype))
+
+    def conv2d(self, x, w, scale, bias, stride, pad, act, residual, out, algo):
+        y = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), None, stride, pad)
+        if scale is not None:
+            y = y * scale.view(1, -1, 1, 1)
+        if bias is not None:
+            y = y + bias.view(1, -1, 1, 1)
+        y = y.permute(0, 2, 3, 1)
+        post = bool(act & 16)  # FB200_ACT_RESIDUAL_AFTER
+        r = 0.0 if residual is None else residual.float()
+        y = _act(y, act & 15) + r if post else _act(y + r, act & 15)
+        out.copy_(y.to(out.dtype))
+
+    def maxpool3x3s2(self, x, out):
+        out.copy_(F.max_pool2d(x.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).to(out.dtype))
+
+    def avgpool2x2(self, x, out):
+        out.copy_(F.avg_pool2d(x.float().permute(0, 3, 1, 2), 2, 2, 0, ceil_mode=True).permute(0, 2, 3, 1).to(out.dtype))
+
+    def resize_bilinear(self, x, out):
+        y = F.interpolate(x.float().permute(0, 3, 1, 2), size=(out.shape[1], out.shape[2]), mode="bilinear", align_corners=False)
+        out.copy_(y.permute(0, 2, 3, 1).to(out.dtype))
+
+    def add(self, a, b, out):
+        C = a.shape[-1]
+        rows, brows = a.numel() // C, b.numel() // C
+        out.copy_((a.float().reshape(rows // brows, brows, C) + b.float().reshape(1, brows, C)).reshape(a.shape).to(out.dtype))
+
+    def layernorm(self, x, res, gamma, beta, out, eps):
+        v = x.float() if res is None else x.float() + res.float()
+        out.copy_(F.layer_norm(v, (v.shape[-1],), gamma, beta, eps).to(out.dtype))
+
+    def attention(self, q, k, v, out, heads, scale):
+        B, Lq, C = q.shape
+        Lk = k.shape[1]
+        hd = C // heads
+        qh = q.float().reshape(B, Lq, heads, hd).transpose(1, 2)
+        kh = k.float().reshape(B, Lk, heads, hd).transpose(1, 2)
+        vh = v.float().reshape(B, Lk, heads, hd).transpose(1, 2)
+        a = torch.softmax((qh @ kh.transpose(-1, -2)) * scale, dim=-1)
+        out.copy_((a @ vh).transpose(1, 2).reshape(B, Lq, C).to(out.dtype))
+
+    def msda(self, value, oa, ref, shapes, P, heads, out):
+        B, S, C = value.shape
+        Q = oa.shape[1]
+        L = len(shapes)
+        hd = C // heads
+        oa = oa.float()
+        off = oa[..., : heads * L * P * 2].reshape(B, Q, heads, L, P, 2)
+        aw = torch.softmax(oa[..., heads * L * P * 2 : heads * L * P * 3].reshape(B, Q, heads, L * P), -1).reshape(B, Q, heads, L, P)
+        r = ref.float().reshape(B, Q, 1, 1, 1, 4)
+        loc = r[..., :2] + off / P * r[..., 2:] * 0.5
+        val = value.float().reshape(B, S, heads, hd)
+        vals = val.split([h * w for h, w in shapes], dim=1)
+        grids = 2 * loc - 1
+        sampled = []
+        for lid, (H_, W_) in enumerate(shapes):
+            vl = vals[lid].flatten(2).transpose(1, 2).reshape(B * heads, hd, H_, W_)
+            g = grids[:, :, :, lid].transpose(1, 2).flatten(0, 1)
+            sampled.append(F.grid_sample(vl, g, mode="bilinear", padding_mode="zeros", align_corners=False))
+        awt = aw.transpose(1, 2).reshape(B * heads, 1, Q, L * P)
+        o = (torch.stack(sampled, dim=-2).flatten(-2) * awt).sum(-1).view(B, heads * hd, Q).transpose(1, 2)
+        out.copy_(o.to(out.dtype))
+
+    def row_select(self, x, valid, fill, out):
+        C = x.shape[-1]
+        S = valid.numel()
+        xv = x.float().reshape(-1, S, C)
+        m = valid.bool().view(1, S, 1)
+        out.copy_(torch.where(m, xv, fill.view(1, 1, C)).reshape(x.shape).to(out.dtype))
+
+    def rowmax(self, x, out):
+        out.copy_(x.float().max(-1).values)
+
+    def topk(self, x, K, out_idx, out_val):
+        v, i = torch.sort(x, dim=-1, descending=True, stable=True)
+        out_idx.copy_(i[:, :K].to(torch.int32))
+        if out_val is not None:
+            out_val.copy_(v[:, :K])
+
+    def gather_rows(self, src, idx, out):
+        out.copy_(src.gather(1, idx.long().unsqueeze(-1).expand(-1, -1, src.shape[-1])))
+
+    def box_op(self, mode, x, ref, idx, out):
+        if mode == 0:
+            out.copy_(torch.sigmoid(x))
+        elif mode == 1:
+            r = ref.clip(0.0, 1.0)
+            out.copy_(torch.sigmoid(x + torch.log(r.clip(min=1e-5) / (1 - r).clip(min=1e-5))))
+        elif mode == 2:
+            out.copy_(x + ref[idx.long().reshape(-1)].reshape(x.shape))
+        else:
+            xc, yc, w, h = x.unbind(-1)
+            out.copy_(torch.stack([xc - 0.5 * w, yc - 0.5 * h, xc + 0.5 * w, yc + 0.5 * h], -1))
+
+    def detr_postprocess(self, scores, boxes, sizes, K, thr, out_scores, out_labels, out_boxes, out_query, out_count):
+        B, Q, C = scores.shape
+        for b in range(B):
+            v, i = torch.sort(scores[b].flatten(), descending=True, stable=True)
+            v, i = v[:K], i[:K]
+            q = i // C
+            bx = boxes[b][q].clone()
+            bx[:, 0::2] *= float(sizes[b, 1])
+            bx[:, 1::2] *= float(sizes[b, 0])
+            out_scores[b] = v
+            out_labels[b] = (i % C).to(torch.int32)
+            out_query[b] = q.to(torch.int32)
+            out_boxes[b] = bx.round().to(torch.int32)
+            out_count[b] = int((v > thr).sum())
