@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark: images/sec of fai-detr-l-obj365 inference, bs=32/GPU, 640x640 (BASELINE.json).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+    python bench.py --impl reference ...        # the reference's CPU path (oracle port) on the host cores
+
+A "step" = one pass of the hot path over one batch of 32 synthetic images: FAIDetr.forward (normalise -> ResNet50-vd ->
+hybrid encoder -> 6-layer deformable decoder) + the fused DETR post-process kernel.
+  value : whole-job images/s with inputs resident in HBM (CUDA-graph replay of the forward + post-process launch)
+  e2e   : same metric through the public API (FocoosModel.__call__) from PINNED HOST uint8 images, H2D and D2H inside
+          the timed region
+Multi-GPU: independent replicas, one process per GPU, no data-path collective ("replicas only"; weak scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "images/sec fai-detr-l bs=32 640x640 inference"
+GFLOP_PER_IMG_USEFUL = 139.05  # excludes the dead mask_features conv
+IDEAL_US_PER_IMG_16BIT = 129.0  # SURVEY.md §8(d) sum-of-max roofline at 16-bit activations
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"], "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
+
+
+def seeded_weights():
+    from focoos_b200.utils.seeded_weights import seeded_state_dict
+
+    with open(os.path.join(ROOT, "tests", "golden", "fai_detr_l_obj365_state_dict_manifest.json")) as f:
+        man = json.load(f)
+    return seeded_state_dict({k: torch.empty(v[0], dtype=getattr(torch, v[1])) for k, v in man.items()}, 0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(batch: int, steps: int, warmup: int, sd, threads: int):
+    """The reference's CPU path (oracle port of focoos' torch fp32 eval forward + post-process) on the host cores."""
+    from oracle import detr_oracle as O
+    from oracle.gen_golden import synth_images
+
+    torch.set_num_threads(threads)
+    imgs = synth_images(1, [(640, 640)] * batch)
+    cfg = O.DetrOracleConfig()
+    times = []
+    with torch.no_grad():
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            x = O.detr_preprocess(imgs, (640, 640))
+            s, b = O.detr_forward(sd, x, cfg)
+            O.detr_postprocess(s, b, [(640, 640)] * batch, 0.5)
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+    return batch / float(np.mean(times)), float(np.mean(times)) * 1e3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    cores = os.cpu_count() or 1
+    config = {"workload": "fai-detr-l-obj365 bs=32/GPU 640x640 inference (BASELINE configs[1])", "per_gpu_batch": args.batch, "global_batch": args.batch * world,
+              "weights": "seeded random (focoos_b200.utils.seeded_weights, seed 0)", "parallelism": f"replicas x{world}", "l2_policy": "inputs_larger_than_L2 (157 MB fp32 batch + >2 GB activations per step)"}
+    sd = seeded_weights()
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb, csteps, cwarm = 2, max(1, min(args.steps, 3)), min(args.warmup, 1)
+        v, ms = cpu_reference_run(cb, csteps, cwarm, sd, cores)
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": csteps, "warmup": cwarm, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": f"{csteps} timed passes of batch {cb} (reference is slower per image at larger CPU batches, BASELINE.md §3)"},
+                "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    from focoos_b200 import DETRConfig, FocoosModel, ModelInfo, ops
+    from focoos_b200.fai_detr import FAIDetr
+    from oracle.gen_golden import synth_images  # input generator only (numpy); not a compute path
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    model = FAIDetr(DETRConfig(), precision=args.precision)
+    model.load_state_dict(sd, strict=True)
+    fm = FocoosModel(model, ModelInfo(name="fai-detr-l-obj365", im_size=640))
+    fm.model.to(dev)
+    proc = fm.processor
+    B = args.batch
+    imgs_np = np.stack(synth_images(1 + rank, [(640, 640)] * B))  # [B,640,640,3] uint8
+    host_u8 = torch.from_numpy(imgs_np).pin_memory()
+    x_dev = host_u8.to(dev).permute(0, 3, 1, 2).float().contiguous()
+    sizes = [(640, 640)] * B
+    sizes_dev = torch.tensor(sizes, dtype=torch.int32, device=dev)
+
+    def step_device():
+        out = fm.model(x_dev)
+        return ops.detr_postprocess(out.logits, out.boxes, sizes_dev, 300, 0.5)
+
+    # ---- warm-up (also builds the engine), then capture forward+post-process in a CUDA graph
+    l0 = ops.launch_count()
+    step_device()
+    torch.cuda.synchronize()
+    launches_per_step = ops.launch_count() - l0
+    graph = None
+    if not args.no_graph:
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                step_device()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            g_out = step_device()
+
+    def run_step():
+        if graph is not None:
+            graph.replay()
+        else:
+            step_device()
+
+    for _ in range(max(args.warmup, 3)):
+        run_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            run_step()
+        e1.record()
+        torch.cuda.synchronize()
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = B * world / (ms_step / 1e3)
+
+    # ---- e2e through the public API: pinned host uint8 -> H2D -> preprocess -> forward -> postprocess -> D2H -> FocoosDetections
+    def step_e2e():
+        return fm(host_u8, threshold=0.5, batched=True)
+
+    for _ in range(3):
+        step_e2e()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e2e_steps = max(3, args.steps // 2)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        dets = step_e2e()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    te = torch.tensor([e2e_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te.item())
+    e2e = {"value": B * world / (e2e_ms / 1e3), "unit": "images/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(host_u8.numel()) + B * 8,
+           "d2h_bytes_per_step": B * (300 * 7 + 1) * 4, "api": "FocoosModel.__call__(pinned uint8 [B,H,W,3], batched=True)"}
+
+    # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv), heaviest layer shape timed alone: FPN 3x3 256->256 @80x80
+    peaks = measured_peaks()
+    roof = None
+    if args.precision == "fp16":
+        xr = torch.randn((B, 80, 80, 256), device=dev).half()
+        wr = (torch.randn((256, 3, 3, 256), device=dev) * 0.02).half()
+        br = torch.zeros(256, device=dev)
+        yr = torch.empty((B, 80, 80, 256), device=dev, dtype=torch.float16)
+        for _ in range(3):
+            ops.conv2d(xr, wr, None, br, pad=1, act=ops.ACT_SILU, out=yr)
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nrep = 20
+        r0.record()
+        for _ in range(nrep):
+            ops.conv2d(xr, wr, None, br, pad=1, act=ops.ACT_SILU, out=yr)
+        r1.record()
+        torch.cuda.synchronize()
+        k_ms = r0.elapsed_time(r1) / nrep
+        flops = 2.0 * B * 80 * 80 * 256 * 256 * 9
+        ach = flops / (k_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "conv_tc_kernel<256,4,half> 3x3 256->256 @80x80 (RepVGG block of CSPRepLayer; 4 launches/step, 21.7% of model FLOPs)",
+                "achieved": ach, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": ach / peaks["tf_burst"], "peak_source": peaks["source"] + " burst (kernel timed alone)",
+                "launch_ms": k_ms, "flops_per_launch": flops, "traffic": None,
+                "model": {"useful_gflop_per_img": GFLOP_PER_IMG_USEFUL, "achieved_tflops_whole_step": GFLOP_PER_IMG_USEFUL * B / ms_step,
+                          "ideal_ms_per_step_16bit": IDEAL_US_PER_IMG_16BIT * B / 1e3, "frac_of_ideal": (IDEAL_US_PER_IMG_16BIT * B / 1e3) / ms_step}}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            cv, cms = cpu_reference_run(2, 2, 1, sd, cores)
+            cpu = {"value": cv, "unit": "images/s", "cores": cores, "kind": "port", "sample": "2 timed passes of batch 2 (oracle port of the reference's torch fp32 CPU forward + post-process)"}
+        line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16" if args.precision == "fp16" else "f32", "data": "synthetic",
+                "config": config, "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
+                "cuda_graph": graph is not None, "roofline": roof, "cpu_baseline": cpu, "detections_img0": len(dets[0])}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -133,11 +133,15 @@ extern "C" int fb200_attention(const void* q, int q_pitch, const void* k, int k_
   FB_CHECK_ARG(smem <= 227 * 1024, "attention: Lk=%d does not fit shared memory", Lk);
   dim3 grid(B * heads, (unsigned)cdiv(Lq, ATT_QT));
   cudaStream_t st = (cudaStream_t)stream;
+  static bool configured = false;
+  if (!configured) {  // raise the dynamic-smem ceiling once (not inside a stream capture)
+    cudaFuncSetAttribute(attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attention_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    configured = true;
+  }
   if (dtype == FB200_F32) {
-    cudaFuncSetAttribute(attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attention_kernel<float><<<grid, 256, smem, st>>>((const float*)q, q_pitch, (const float*)k, k_pitch, (const float*)v, v_pitch, (float*)out, out_pitch, Lq, Lk, heads, scale);
   } else if (dtype == FB200_F16) {
-    cudaFuncSetAttribute(attention_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attention_kernel<__half><<<grid, 256, smem, st>>>((const __half*)q, q_pitch, (const __half*)k, k_pitch, (const __half*)v, v_pitch, (__half*)out, out_pitch, Lq, Lk, heads, scale);
   } else { set_error("attention: bad dtype"); return FB200_ERR_INVALID; }
   FB_CHECK_LAUNCH("attention");

@@ -19,6 +19,8 @@ from .ports import DETRConfig, DETRModelOutput, FocoosDet, FocoosDetections
 
 def get_image_sizes(inputs) -> List[Tuple[int, int]]:
     """base_processor.py:176-221: (height, width) of every ORIGINAL input image."""
+    if _is_u8_nhwc_batch(inputs):
+        return [(int(inputs.shape[1]), int(inputs.shape[2]))] * int(inputs.shape[0])
     if isinstance(inputs, (torch.Tensor, np.ndarray)) or not isinstance(inputs, (list, tuple)):
         inputs = [inputs]
     sizes = []
@@ -33,6 +35,11 @@ def get_image_sizes(inputs) -> List[Tuple[int, int]]:
             raise ValueError(f"Unsupported input type: {type(img)}")
         sizes.append((int(h), int(w)))
     return sizes
+
+
+def _is_u8_nhwc_batch(x) -> bool:
+    """Extension over the reference (which mis-stacks 4-D tensors): a uint8 [B,H,W,3] tensor is a batch."""
+    return isinstance(x, torch.Tensor) and x.dim() == 4 and x.dtype == torch.uint8 and x.shape[-1] == 3
 
 
 class DETRProcessor:
@@ -57,6 +64,13 @@ class DETRProcessor:
         return self.get_torch_batch(inputs, target, device, dtype), []
 
     def get_torch_batch(self, inputs, target_size, device, dtype):
+        if _is_u8_nhwc_batch(inputs):  # one H2D copy for the whole batch
+            x = inputs.to(device, non_blocking=True)
+            if target_size is not None and tuple(x.shape[1:3]) != tuple(target_size):
+                x4 = torch.zeros((*x.shape[:3], 4), dtype=dtype, device=x.device)
+                x4[..., :3] = x
+                x = ops.resize_bilinear(x4, target_size)[..., :3]
+            return x.permute(0, 3, 1, 2).to(dtype).contiguous()
         if not isinstance(inputs, (list, tuple)):
             inputs = [inputs]
         outs = []

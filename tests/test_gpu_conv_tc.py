@@ -1,0 +1,89 @@
+"""-m gpu: the tcgen05 implicit-GEMM conv/linear kernel against the CPU reference (fp32 accumulation of the same
+fp16 operands).  Kept in its own file: a descriptor bug would hang or trap, and must not take the SIMT tests down."""
+import math
+
+import pytest
+import torch
+
+from focoos_b200 import ops
+from oracle.ops_ref import RefBackend
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180)]
+REF = RefBackend()
+DEV = "cuda"
+
+
+def rnd(shape, dtype, seed, s=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * s).to(dtype)
+
+
+def run_case(B, H, W, Cin, Cout, k, stride, act=0, use_res=False, use_scale=True, out_dtype=torch.float16, seed=0, tolerance=3e-3):
+    x = rnd((B, H, W, Cin), torch.float16, seed + 1)
+    w = rnd((Cout, k, k, Cin), torch.float16, seed + 2, 1.0 / math.sqrt(k * k * Cin))
+    sc = (torch.rand(Cout) + 0.5) if use_scale else None
+    bi = rnd((Cout,), torch.float32, seed + 3, 0.2)
+    pad = (k - 1) // 2
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    res = rnd((B, Ho, Wo, Cout), out_dtype, seed + 4) if use_res else None
+    ref = torch.empty((B, Ho, Wo, Cout), dtype=out_dtype)
+    REF.conv2d(x, w, sc, bi, stride, pad, act, res, ref, 0)
+    out = ops.conv2d(x.to(DEV), w.to(DEV), None if sc is None else sc.to(DEV), bi.to(DEV), stride=stride, pad=pad, act=act,
+                     residual=None if res is None else res.to(DEV), out_dtype=out_dtype, algo=ops.ALGO_TCGEN05)
+    torch.cuda.synchronize()
+    a, b = out.float().cpu(), ref.float()
+    err = float((a - b).abs().max())
+    scale = max(1.0, float(b.abs().max()))
+    assert err <= tolerance * scale, f"tcgen05 conv B{B} {H}x{W} {Cin}->{Cout} k{k} s{stride}: max|d|={err:.3e} (scale {scale:.2e}); frac bad={(float(((a-b).abs()>tolerance*scale).float().mean())):.4f}"
+
+
+def test_tc_supported_flag():
+    assert ops.supports_tcgen05()
+
+
+@pytest.mark.parametrize("M,K,N", [(128, 64, 64), (256, 128, 128), (1000, 256, 256), (300, 256, 288), (777, 1024, 256), (128, 256, 512), (9600, 256, 1536)])
+def test_linear_flat(M, K, N):
+    run_case(1, 1, M, K, N, 1, 1, seed=M + K + N)
+
+
+def test_linear_fp32_out_and_odd_n():
+    run_case(1, 1, 500, 256, 368, 1, 1, out_dtype=torch.float32, use_scale=False, tolerance=2e-3)
+    run_case(1, 1, 300, 256, 4, 1, 1, out_dtype=torch.float32, use_scale=False, tolerance=2e-3)
+    run_case(1, 1, 300, 256, 80, 1, 1, out_dtype=torch.float32, use_scale=False, tolerance=2e-3)
+
+
+@pytest.mark.parametrize("H,W,Cin,Cout", [(16, 16, 64, 64), (20, 20, 256, 256), (40, 40, 256, 256), (80, 80, 128, 128), (24, 40, 64, 128), (7, 9, 64, 64)])
+def test_conv3x3_s1(H, W, Cin, Cout):
+    run_case(2, H, W, Cin, Cout, 3, 1, act=1, seed=H + Cin)
+
+
+@pytest.mark.parametrize("H,W,Cin,Cout", [(40, 40, 128, 128), (16, 24, 64, 64), (80, 80, 256, 256)])
+def test_conv3x3_s2(H, W, Cin, Cout):
+    run_case(2, H, W, Cin, Cout, 3, 2, act=1, seed=H + Cout)
+
+
+def test_epilogue_variants():
+    run_case(2, 20, 20, 256, 1024, 1, 1, act=1, use_res=True, seed=5)           # bottleneck tail: residual then ReLU
+    run_case(2, 20, 20, 256, 256, 3, 1, act=2 | 16, use_res=True, use_scale=False, seed=6)  # CSP tail: SiLU then residual
+    run_case(3, 10, 10, 512, 256, 1, 1, act=2, seed=7)
+    run_case(1, 1, 400, 256, 1024, 1, 1, act=3, use_scale=False, seed=8)        # GELU FFN
+
+
+def test_slices_and_batch_stride():
+    xb = rnd((2, 20, 20, 512), torch.float16, 50)
+    w = rnd((256, 3, 3, 256), torch.float16, 51, 0.02)
+    bi = rnd((256,), torch.float32, 52)
+    ref = torch.empty((2, 20, 20, 256), dtype=torch.float16)
+    REF.conv2d(xb[..., :256], w, None, bi, 1, 1, 2, None, ref, 0)
+    xg = xb.to(DEV)
+    ob = torch.zeros((2, 20, 20, 512), dtype=torch.float16, device=DEV)
+    ops.conv2d(xg[..., :256], w.to(DEV), None, bi.to(DEV), pad=1, act=2, out=ob[..., 256:], algo=ops.ALGO_TCGEN05)
+    assert float((ob[..., 256:].float().cpu() - ref.float()).abs().max()) <= 3e-3 * max(1.0, float(ref.abs().max()))
+    assert float(ob[..., :256].abs().max()) == 0.0
+    w1 = rnd((256, 1, 1, 256), torch.float16, 53, 0.06)
+    ref1 = torch.empty((2, 20, 20, 256), dtype=torch.float16)
+    REF.conv2d(xb[..., 256:], w1, None, bi, 1, 0, 0, None, ref1, 0)
+    mem = torch.zeros((2, 500, 256), dtype=torch.float16, device=DEV)
+    ops.conv2d(xg[..., 256:], w1.to(DEV), None, bi.to(DEV), out=mem[:, 50:450].unflatten(1, (20, 20)), algo=ops.ALGO_TCGEN05)
+    assert float((mem[:, 50:450].reshape(2, 20, 20, 256).float().cpu() - ref1.float()).abs().max()) <= 3e-3 * max(1.0, float(ref1.abs().max()))
+    assert float(mem[:, :50].abs().max()) == 0.0 and float(mem[:, 450:].abs().max()) == 0.0

@@ -1,0 +1,21 @@
+#!/bin/bash
+# Runs on the B200 box under gpurun: tests -> logs under gpurun_out/.  Usage: tools/gpu_trip.sh [stage ...]
+mkdir -p gpurun_out
+cd "$(dirname "$0")/.."
+STAGES="${@:-ops tc e2e bench}"
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
+for s in $STAGES; do
+  case $s in
+    ops)   timeout 900 python -m pytest tests/test_gpu_ops.py -q -m gpu -x 2>&1 | tail -40 > gpurun_out/t_ops.log ;;
+    tc)    timeout 900 python -m pytest tests/test_gpu_conv_tc.py -q -m gpu 2>&1 | tail -80 > gpurun_out/t_tc.log ;;
+    e2e)   timeout 1200 python -m pytest tests/test_gpu_e2e.py -q -m gpu 2>&1 | tail -60 > gpurun_out/t_e2e.log ;;
+    smoke) timeout 600 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1 ;;
+    bench) timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err ;;
+    bench32) timeout 900 python bench.py --steps 3 --warmup 3 --precision fp32 --no-cpu-baseline > gpurun_out/bench_fp32.log 2> gpurun_out/bench_fp32.err ;;
+    ref)   timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2>&1 ;;
+    ncu_list) timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1 ;;
+    ncu_full) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 40 -c 3 -o gpurun_out/prof_conv_tc python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1 ;;
+  esac
+  echo "stage $s exit $?" >> gpurun_out/stages.txt
+done
+tail -5 gpurun_out/t_*.log gpurun_out/bench.log 2>/dev/null | tail -60
