@@ -3,21 +3,24 @@
 //   D[m, n] = act( (sum_k A[m,k] * W[n,k]) * scale[n] + bias[n] + residual[m,n] )
 //   m = output pixel (b, ho, wo), n = output channel, k = (kh, kw, c).
 //
-// Design (one CTA = one 128 x BLOCK_N output tile, warp-specialised):
+// Design: PERSISTENT, warp-specialised CTAs (grid = #SMs x CTAs/SM); each CTA walks 128 x BLOCK_N output tiles
+// (N tiles fastest so CTAs that share an A tile run together and A comes from L2).
 //   warp 0   TMA producer.  A is never materialised as im2col: an M-tile is a BW x BH rectangle of output
 //            pixels of one image, and the A block for filter tap (kh,kw), channel chunk c0 is the SAME
 //            rectangle of the NHWC input shifted by (kh-pad, kw-pad) — one 4-D tiled TMA load whose
 //            out-of-bounds rows/columns (the conv zero padding, and ragged tile edges) are zero-filled by the
 //            TMA unit.  Stride-2 3x3 convs use a 5-D view (c', w/2, h&1, h/2, b) of the same tensor so that
 //            every tap is again a dense box.  1x1 convs and linears are the degenerate W = M, H = 1 case.
-//            Smem tiles land in the canonical K-major SWIZZLE_128B layout tcgen05 wants (128-byte rows).
-//   warp 1   MMA issuer: one elected lane issues 4 x tcgen05.mma (128 x BLOCK_N x 16) per 64-wide k-block,
-//            accumulating in TMEM; tcgen05.commit releases the smem stage / signals the epilogue.
-//   warp 2   TMEM allocator.   warp 3  stages scale/bias in smem.
-//   warps 4-7 epilogue: tcgen05.ld 32 columns at a time -> folded-BN scale/bias, residual, activation ->
-//            fp16/fp32 -> swizzled smem staging -> TMA store (clips ragged tile edges and Cout tails).
+//            Smem tiles land in the canonical K-major SWIZZLE_128B (or _64B for Cin = 32) layout tcgen05 wants.
+//   warp 1   MMA issuer: one elected lane issues BLOCK_K/16 x tcgen05.mma (128 x BLOCK_N x 16) per k-block into
+//            one of TWO TMEM accumulator stages; tcgen05.commit releases the smem stage / signals the epilogue.
+//   warp 2   TMEM allocator (2 x BLOCK_N columns).
+//   warps 4-7 epilogue, overlapped with the next tile's main loop: tcgen05.ld 32 columns at a time -> folded-BN
+//            scale/bias, residual (before or after the activation), ReLU/SiLU/GELU (switch hoisted out of the
+//            element loops — a per-element switch made the first version I-cache bound, profiles/r01_trip3) ->
+//            fp16/fp32 -> swizzled smem staging (double buffered) -> TMA store (clips ragged tiles / Cout tails).
 //
-// Algorithmic bytes: A (M x K' where K' = Cin, each input pixel counted once), W, D (+ residual) once each.
+// Algorithmic bytes: A (M x Cin, each input pixel counted once), W, D (+ residual) once each.
 #include <cuda.h>
 
 #include <type_traits>
@@ -26,24 +29,22 @@
 
 namespace fb200 {
 
-
 namespace tc {
 
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;                       // 64 halves = 128 B = one swizzle row
-constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
-constexpr int STAGING_BYTES = BLOCK_M * 128;      // 16 KiB: 128 rows x 128 B
+constexpr int STAGING_BYTES = BLOCK_M * 128;  // one staging tile: 128 rows x 128 B
 constexpr int NUM_THREADS = 256;
 
 struct KParams {
   const float* scale; const float* bias; const void* res;
   int res_pitch, act, Cout;
-  int KH, KW, pad, cchunks;        // cchunks = Cin / 64
+  int KH, KW, pad, cchunks;        // cchunks = Cin / BLOCK_K
   int BW, BH, tiles_w, tiles_h;    // output tile rectangle and tile counts per image
-  int Ho, Wo;                      // output spatial size (for residual addressing / validity)
-  int x_pitch;                     // only used by the stride-2 view (c' = wp * pitch + c)
+  int Ho, Wo;                      // output spatial size (residual addressing / validity)
+  int x_pitch;                     // stride-2 view only (c' = wp * pitch + c)
   int stride2;                     // 0: 4-D stride-1 view, 1: 5-D stride-2 view
   int num_k_blocks;
+  int n_tiles, total_tiles;        // N tiles per M tile; total = m_tiles * n_tiles
 };
 
 // ---------------------------------------------------------------------------------------------- PTX
@@ -54,6 +55,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done = 0;
@@ -67,13 +71,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
     if (done) break;
-    if (++spins > (1u << 26)) { printf("fb200 conv_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    if (++spins > (1u << 26)) __trap();  // a descriptor / phase bug must not hang the GPU
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -92,17 +97,18 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
                ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format: version 1 at bit 46, layout 2 at bits 61-63)
+// K-major swizzled shared-memory matrix descriptor (sm_100 format: version 1 at bit 46, layout type at bits 61-63)
+template <int BLOCK_K>
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);   // start address, 16-byte units
   d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major) = 1
-  d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)((8 * BLOCK_K * 2) >> 4) << 32;  // stride byte offset: 8 rows x (BLOCK_K*2) B
   d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+  d |= (uint64_t)(BLOCK_K == 64 ? 2 : 4) << 61;   // SWIZZLE_128B (2) / SWIZZLE_64B (4)
   return d;
 }
 // instruction descriptor: D=F32, A=B=F16, both K-major, M=128, N=BLOCK_N
@@ -132,37 +138,52 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int BLOCK_N> constexpr int stage_bytes() { return A_STAGE_BYTES + BLOCK_N * BLOCK_K * 2; }
-template <int BLOCK_N, int STAGES> constexpr int smem_bytes() {
-  return STAGES * stage_bytes<BLOCK_N>() + STAGING_BYTES + 2 * BLOCK_N * 4 + (2 * STAGES + 1) * 8 + 16 + 1024 /*align slack*/;
+// activation on 32 values with the switch OUTSIDE the element loop (uniform branch, lean straight-line bodies)
+__device__ __forceinline__ void act32(float (&v)[32], int act) {
+  switch (act & 15) {
+    case FB200_ACT_RELU:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      break;
+    case FB200_ACT_SILU:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = v[j] * __frcp_rn(1.f + __expf(-v[j]));
+      break;
+    case FB200_ACT_GELU:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752440f));
+      break;
+    default: break;
+  }
+}
+
+template <int BLOCK_N, int BLOCK_K> constexpr int stage_bytes() { return (BLOCK_M + BLOCK_N) * BLOCK_K * 2; }
+template <int BLOCK_N, int STAGES, int BLOCK_K, int NSTG> constexpr int smem_bytes() {
+  return STAGES * stage_bytes<BLOCK_N, BLOCK_K>() + NSTG * STAGING_BYTES + 2 * BLOCK_N * 4 + (2 * STAGES + 4) * 8 + 16 + 1024 /*align slack*/;
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
-template <int BLOCK_N, int STAGES, typename TOut, int MIN_BLOCKS>
+template <int BLOCK_N, int STAGES, typename TOut, int MIN_BLOCKS, int BLOCK_K, int NSTG>
 __global__ void __launch_bounds__(NUM_THREADS, MIN_BLOCKS)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_d, const KParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_a = smem;                                      // STAGES x 16 KiB
-  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;             // STAGES x BLOCK_N*128 B
-  uint8_t* staging = smem_b + STAGES * BLOCK_N * BLOCK_K * 2;  // 16 KiB
-  float* s_scale = reinterpret_cast<float*>(staging + STAGING_BYTES);
+  constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+  constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint8_t* staging = smem_b + STAGES * B_STAGE_BYTES;  // NSTG x 16 KiB
+  float* s_scale = reinterpret_cast<float*>(staging + NSTG * STAGING_BYTES);
   float* s_bias = s_scale + BLOCK_N;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_bias + BLOCK_N);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // 1-D grid, N tiles fastest so that CTAs sharing an A tile are co-scheduled (A is then read from L2)
-  const int n_tiles = (p.Cout + BLOCK_N - 1) / BLOCK_N;
-  const int n0 = (blockIdx.x % n_tiles) * BLOCK_N;
-  // M tile -> (image, tile row, tile col)
-  const int mt = blockIdx.x / n_tiles;
-  const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, img = mt / (p.tiles_w * p.tiles_h);
-  const int w0 = tw * p.BW, h0 = th * p.BH;
-  constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  constexpr uint32_t TMEM_COLS = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);  // two accumulator stages
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
@@ -171,147 +192,185 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4); }
     fence_barrier_init();
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (warp == 3) {
-    for (int i = lane; i < BLOCK_N; i += 32) {
-      const int n = n0 + i;
-      s_scale[i] = (p.scale && n < p.Cout) ? p.scale[n] : 1.f;
-      s_bias[i] = (p.bias && n < p.Cout) ? p.bias[n] : 0.f;
-    }
-  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
 
   if (warp == 0) {
     // ===================================================================== TMA producer
     if (lane == 0) {
-      const uint32_t a_bytes = (uint32_t)(p.BW * p.BH * BLOCK_K * 2);
-      const uint32_t tx_bytes = a_bytes + (uint32_t)(BLOCK_N * BLOCK_K * 2);
+      const uint32_t tx_bytes = (uint32_t)(p.BW * p.BH * BLOCK_K * 2) + (uint32_t)B_STAGE_BYTES;
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-        const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
-        const int kh = tap / p.KW, kw = tap - kh * p.KW;
-        void* dst_a = smem_a + stage * A_STAGE_BYTES;
-        if (!p.stride2) {
-          tma_load_4d(&tmap_a, &full_bar[stage], dst_a, cc * BLOCK_K, w0 + kw - p.pad, h0 + kh - p.pad, img);
-        } else {
-          // input h = 2*ho + kh - 1 -> (h>>1, h&1) = (ho + ((kh-1)>>1), (kh-1)&1): kh=0 -> (ho-1,1); 1 -> (ho,0); 2 -> (ho,1)
-          const int dh = (kh == 0) ? -1 : 0, hp = (kh == 1) ? 0 : 1;
-          const int dw = (kw == 0) ? -1 : 0, wp = (kw == 1) ? 0 : 1;
-          tma_load_5d(&tmap_a, &full_bar[stage], dst_a, wp * p.x_pitch + cc * BLOCK_K, w0 + dw, hp, h0 + dh, img);
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const int n0 = (t % p.n_tiles) * BLOCK_N, mt = t / p.n_tiles;
+        const int img = mt / tiles_per_img, rem = mt - img * tiles_per_img;
+        const int h0 = (rem / p.tiles_w) * p.BH, w0 = (rem % p.tiles_w) * p.BW;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+          const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
+          const int kh = tap / p.KW, kw = tap - kh * p.KW;
+          void* dst_a = smem_a + stage * A_STAGE_BYTES;
+          if (!p.stride2) {
+            tma_load_4d(&tmap_a, &full_bar[stage], dst_a, cc * BLOCK_K, w0 + kw - p.pad, h0 + kh - p.pad, img);
+          } else {
+            // input h = 2*ho + kh - 1 -> (h>>1, h&1): kh=0 -> (ho-1,1); kh=1 -> (ho,0); kh=2 -> (ho,1)
+            const int dh = (kh == 0) ? -1 : 0, hp = (kh == 1) ? 0 : 1;
+            const int dw = (kw == 0) ? -1 : 0, wp = (kw == 1) ? 0 : 1;
+            tma_load_5d(&tmap_a, &full_bar[stage], dst_a, wp * p.x_pitch + cc * BLOCK_K, w0 + dw, hp, h0 + dh, img);
+          }
+          tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb * BLOCK_K, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * (BLOCK_N * BLOCK_K * 2), kb * BLOCK_K, n0);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BLOCK_N);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator stage
         tcgen05_fence_after();
-        const uint64_t da = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
-        const uint64_t db = make_smem_desc(smem_u32(smem_b + stage * (BLOCK_N * BLOCK_K * 2)));
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint64_t da = make_smem_desc<BLOCK_K>(smem_u32(smem_a + stage * A_STAGE_BYTES));
+          const uint64_t db = make_smem_desc<BLOCK_K>(smem_u32(smem_b + stage * B_STAGE_BYTES));
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / 16; ++k) {
-          // advance 16 halves = 32 B inside the 128-B swizzle row: +2 in 16-byte units
-          umma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            // advance 16 halves = 32 B inside the swizzle row: +2 in 16-byte units
+            umma_f16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem stage may be refilled once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&empty_bar[stage]);  // smem stage may be refilled once these MMAs have read it
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        umma_commit(&tmem_full_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      umma_commit(tmem_full_bar);
     }
   } else if (warp >= 4) {
     // ===================================================================== epilogue (128 threads)
-    const int ew = warp - 4;               // TMEM lane quarter
-    const int row = ew * 32 + lane;        // tile row == TMEM lane
+    const int ew = warp - 4;             // TMEM lane quarter
+    const int row = ew * 32 + lane;      // tile row == TMEM lane
     const int bh = row / p.BW, bw = row - bh * p.BW;
-    const int ho = h0 + bh, wo = w0 + bw;
-    const bool row_valid = (row < p.BW * p.BH) && ho < p.Ho && wo < p.Wo;
-    const int64_t pix = ((int64_t)img * p.Ho + ho) * p.Wo + wo;
-    const TOut* res_row = p.res ? reinterpret_cast<const TOut*>(p.res) + pix * p.res_pitch : nullptr;
+    const int et = threadIdx.x - 128;
     constexpr int CHUNK_COLS = 128 / (int)sizeof(TOut);  // output columns per 128-byte staging row
-    mbar_wait(tmem_full_bar, 0);
-    tcgen05_fence_after();
-    uint8_t* srow = staging + row * 128;
-    for (int c0 = 0; c0 < BLOCK_N; c0 += CHUNK_COLS) {
-      if (n0 + c0 >= p.Cout) break;  // uniform across the CTA
-      // the previous TMA store must have finished READING the staging tile before it is overwritten
-      if (threadIdx.x == 128) tma_store_wait_read0();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+    const bool post = (p.act & FB200_ACT_RESIDUAL_AFTER) != 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t chunk_ctr = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const int n0 = (t % p.n_tiles) * BLOCK_N, mt = t / p.n_tiles;
+      const int img = mt / tiles_per_img, rem = mt - img * tiles_per_img;
+      const int h0 = (rem / p.tiles_w) * p.BH, w0 = (rem % p.tiles_w) * p.BW;
+      const int ho = h0 + bh, wo = w0 + bw;
+      const bool row_valid = (row < p.BW * p.BH) && ho < p.Ho && wo < p.Wo;
+      const TOut* res_row = p.res ? reinterpret_cast<const TOut*>(p.res) + (((int64_t)img * p.Ho + ho) * p.Wo + wo) * p.res_pitch : nullptr;
+      // per-tile scale / bias (n0 changes with the N tile)
+      epi_bar();  // everyone is done with the previous tile's scale/bias
+      for (int i = et; i < BLOCK_N; i += 128) {
+        const int n = n0 + i;
+        s_scale[i] = (p.scale && n < p.Cout) ? p.scale[n] : 1.f;
+        s_bias[i] = (p.bias && n < p.Cout) ? p.bias[n] : 0.f;
+      }
+      epi_bar();
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t tmem_acc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      for (int c0 = 0; c0 < BLOCK_N; c0 += CHUNK_COLS) {
+        if (n0 + c0 >= p.Cout) break;  // uniform across the CTA
+        uint8_t* stg = staging + (chunk_ctr % NSTG) * STAGING_BYTES;
+        uint8_t* srow = stg + row * 128;
+        // the TMA store that last used this staging buffer must have finished READING it
+        if (et == 0) tma_store_wait_read<NSTG - 1>();
+        epi_bar();
 #pragma unroll
-      for (int sub = 0; sub < CHUNK_COLS / 32; ++sub) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(c0 + sub * 32), r);
-        float v[32];
+        for (int sub = 0; sub < CHUNK_COLS / 32; ++sub) {
+          if (c0 + sub * 32 >= BLOCK_N) break;  // BLOCK_N = 32 with fp16 output: half a staging row
+          uint32_t r[32];
+          tmem_ld32(tmem_acc + (uint32_t)(c0 + sub * 32), r);
+          float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * s_scale[c0 + sub * 32 + j] + s_bias[c0 + sub * 32 + j];
-        const bool post = (p.act & FB200_ACT_RESIDUAL_AFTER) != 0;
-        if (post) {
+          for (int j = 0; j < 32; j += 4) {
+            const float4 sc = *reinterpret_cast<const float4*>(&s_scale[c0 + sub * 32 + j]);
+            const float4 bi = *reinterpret_cast<const float4*>(&s_bias[c0 + sub * 32 + j]);
+            v[j + 0] = fmaf(__uint_as_float(r[j + 0]), sc.x, bi.x);
+            v[j + 1] = fmaf(__uint_as_float(r[j + 1]), sc.y, bi.y);
+            v[j + 2] = fmaf(__uint_as_float(r[j + 2]), sc.z, bi.z);
+            v[j + 3] = fmaf(__uint_as_float(r[j + 3]), sc.w, bi.w);
+          }
+          if (post) act32(v, p.act);
+          if (res_row && row_valid) {
+            const int nb = n0 + c0 + sub * 32;
+            if (nb + 32 <= p.Cout) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
-        }
-        if (res_row && row_valid) {
-          const int nb = n0 + c0 + sub * 32;
-          if (nb + 32 <= p.Cout) {
+              for (int j = 0; j < 32; j += 8) {
+                if constexpr (sizeof(TOut) == 2) {
+                  const uint4 t4 = *reinterpret_cast<const uint4*>(res_row + nb + j);
+                  const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&t4.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&t4.y));
+                  const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&t4.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&t4.w));
+                  v[j] += f0.x; v[j + 1] += f0.y; v[j + 2] += f1.x; v[j + 3] += f1.y;
+                  v[j + 4] += f2.x; v[j + 5] += f2.y; v[j + 6] += f3.x; v[j + 7] += f3.y;
+                } else {
+                  const float4 a4 = *reinterpret_cast<const float4*>(res_row + nb + j), b4 = *reinterpret_cast<const float4*>(res_row + nb + j + 4);
+                  v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
+                  v[j + 4] += b4.x; v[j + 5] += b4.y; v[j + 6] += b4.z; v[j + 7] += b4.w;
+                }
+              }
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float rr[4];
-              load4(res_row + nb + j, rr);
-              v[j] += rr[0]; v[j + 1] += rr[1]; v[j + 2] += rr[2]; v[j + 3] += rr[3];
+              for (int j = 0; j < 32; ++j)
+                if (nb + j < p.Cout) v[j] += to_f(res_row[nb + j]);
+            }
+          }
+          if (!post) act32(v, p.act);
+          // 16-byte pieces into the 128B-swizzled staging row: physical chunk = logical chunk ^ (row & 7)
+          if constexpr (sizeof(TOut) == 2) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {  // 8 halves per 16 B
+              __half2 h0_ = __floats2half2_rn(v[q * 8 + 0], v[q * 8 + 1]), h1_ = __floats2half2_rn(v[q * 8 + 2], v[q * 8 + 3]);
+              __half2 h2_ = __floats2half2_rn(v[q * 8 + 4], v[q * 8 + 5]), h3_ = __floats2half2_rn(v[q * 8 + 6], v[q * 8 + 7]);
+              const uint4 pk = make_uint4(*reinterpret_cast<uint32_t*>(&h0_), *reinterpret_cast<uint32_t*>(&h1_),
+                                          *reinterpret_cast<uint32_t*>(&h2_), *reinterpret_cast<uint32_t*>(&h3_));
+              *reinterpret_cast<uint4*>(srow + (((sub * 4 + q) ^ (row & 7)) << 4)) = pk;
             }
           } else {
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < p.Cout) v[j] += to_f(res_row[nb + j]);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {  // 4 floats per 16 B
+              const uint4 pk = make_uint4(__float_as_uint(v[q * 4 + 0]), __float_as_uint(v[q * 4 + 1]),
+                                          __float_as_uint(v[q * 4 + 2]), __float_as_uint(v[q * 4 + 3]));
+              *reinterpret_cast<uint4*>(srow + ((q ^ (row & 7)) << 4)) = pk;
+            }
           }
         }
-        if (!post) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+        fence_proxy_async();
+        epi_bar();
+        if (et == 0) {
+          tma_store_4d(&tmap_d, stg, n0 + c0, w0, h0, img);
+          tma_store_commit();
         }
-        // 16-byte pieces into the 128B-swizzled staging row: physical chunk = logical chunk ^ (row & 7)
-        if constexpr (sizeof(TOut) == 2) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {  // 8 halves per 16 B
-            __half2 h0_ = __floats2half2_rn(v[q * 8 + 0], v[q * 8 + 1]), h1_ = __floats2half2_rn(v[q * 8 + 2], v[q * 8 + 3]);
-            __half2 h2_ = __floats2half2_rn(v[q * 8 + 4], v[q * 8 + 5]), h3_ = __floats2half2_rn(v[q * 8 + 6], v[q * 8 + 7]);
-            uint4 pk = make_uint4(*reinterpret_cast<uint32_t*>(&h0_), *reinterpret_cast<uint32_t*>(&h1_),
-                                  *reinterpret_cast<uint32_t*>(&h2_), *reinterpret_cast<uint32_t*>(&h3_));
-            const int chunk = sub * 4 + q;
-            *reinterpret_cast<uint4*>(srow + ((chunk ^ (row & 7)) << 4)) = pk;
-          }
-        } else {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {  // 4 floats per 16 B
-            const uint4 pk = make_uint4(__float_as_uint(v[q * 4 + 0]), __float_as_uint(v[q * 4 + 1]),
-                                        __float_as_uint(v[q * 4 + 2]), __float_as_uint(v[q * 4 + 3]));
-            *reinterpret_cast<uint4*>(srow + ((q ^ (row & 7)) << 4)) = pk;
-          }
-        }
+        ++chunk_ctr;
       }
-      fence_proxy_async();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 128) {
-        tma_store_4d(&tmap_d, staging, n0 + c0, w0, h0, img);
-        tma_store_commit();
-      }
+      // all tcgen05.ld of this accumulator stage have completed (wait::ld): hand it back to the MMA warp
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (threadIdx.x == 128) tma_store_wait_all();
+    if (et == 0) tma_store_wait_all();
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -337,14 +396,14 @@ static EncodeTiledFn get_encode() {
 }
 
 static int encode(CUtensorMap* m, CUtensorMapDataType dt, int elt, int rank, void* base, const uint64_t* dims, const uint64_t* strides_elts,
-                  const uint32_t* box, const char* what) {
+                  const uint32_t* box, const char* what, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = get_encode();
   if (!fn) { set_error("conv_tc: cuTensorMapEncodeTiled unavailable"); return FB200_ERR_CUDA; }
   cuuint64_t gdim[5], gstr[4];
   cuuint32_t bdim[5], estr[5];
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1; }
   for (int i = 1; i < rank; ++i) gstr[i - 1] = strides_elts[i] * (uint64_t)elt;  // bytes; dim0 stride is implicit
-  CUresult r = fn(m, dt, (cuuint32_t)rank, base, gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  CUresult r = fn(m, dt, (cuuint32_t)rank, base, gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("conv_tc: cuTensorMapEncodeTiled(%s) failed with %d (rank %d dims %llu,%llu,%llu,%llu box %u,%u,%u,%u)", what, (int)r, rank,
@@ -368,16 +427,31 @@ static void choose_tile(int Ho, int Wo, int* BW, int* BH) {
   }
 }
 
-template <int BLOCK_N, int STAGES, typename TOut, int MIN_BLOCKS>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const KParams& kp, dim3 grid, cudaStream_t st) {
-  auto kern = conv_tc_kernel<BLOCK_N, STAGES, TOut, MIN_BLOCKS>;
-  constexpr int smem = smem_bytes<BLOCK_N, STAGES>();
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BLOCK_N, int STAGES, typename TOut, int MIN_BLOCKS, int BLOCK_K, int NSTG>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const KParams& kp, cudaStream_t st) {
+  auto kern = conv_tc_kernel<BLOCK_N, STAGES, TOut, MIN_BLOCKS, BLOCK_K, NSTG>;
+  constexpr int smem = smem_bytes<BLOCK_N, STAGES, BLOCK_K, NSTG>();
+  static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
+  static_assert(MIN_BLOCKS * 2 * BLOCK_N <= 512, "TMEM budget exceeded (a blocked tcgen05.alloc would deadlock)");
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute(%d B) failed: %s", smem, cudaGetErrorString(e)); return FB200_ERR_CUDA; }
     configured = true;
   }
+  const int64_t cap = (int64_t)num_sms() * MIN_BLOCKS;
+  const unsigned grid = (unsigned)(kp.total_tiles < cap ? kp.total_tiles : cap);
   kern<<<grid, NUM_THREADS, smem, st>>>(ta, tb, td, kp);
   FB_CHECK_LAUNCH("conv_tc_kernel");
   return FB200_OK;
@@ -388,7 +462,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
 bool conv2d_tc_supported(const ConvParams& p, int x_dtype, int out_dtype) {
   if (x_dtype != FB200_F16) return false;
   if (out_dtype != FB200_F16 && out_dtype != FB200_F32) return false;
-  if (p.Cin % 64 != 0 || p.x_pitch % 8 != 0) return false;
+  if (p.Cin % 32 != 0 || p.x_pitch % 8 != 0) return false;
   if ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.w) | reinterpret_cast<uintptr_t>(p.out)) & 15) return false;
   const int oelt = out_dtype == FB200_F16 ? 2 : 4;
   if ((p.out_pitch * oelt) % 16 != 0) return false;
@@ -404,7 +478,10 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
   using namespace tc;
   KParams kp;
   kp.scale = p.scale; kp.bias = p.bias; kp.res = p.res; kp.res_pitch = p.res_pitch; kp.act = p.act; kp.Cout = p.Cout;
-  kp.KH = p.KH; kp.KW = p.KW; kp.pad = p.pad; kp.cchunks = p.Cin / BLOCK_K; kp.x_pitch = p.x_pitch;
+  kp.KH = p.KH; kp.KW = p.KW; kp.pad = p.pad;
+  const int BK = (p.Cin % 64 == 0) ? 64 : 32;
+  const CUtensorMapSwizzle swz = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  kp.cchunks = p.Cin / BK; kp.x_pitch = p.x_pitch;
   kp.stride2 = (p.stride == 2) ? 1 : 0;
   kp.num_k_blocks = p.KH * p.KW * kp.cchunks;
   // geometry: 1x1 stride-1 convs and linears flatten to W = M, H = 1, B = 1
@@ -425,25 +502,27 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
   if (!kp.stride2) {
     const uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     const uint64_t str[4] = {1, P, P * W, P * W * H};
-    const uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)BW, (uint32_t)BH, 1};
-    rc = encode(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4, const_cast<void*>(p.x), dims, str, box, "A");
+    const uint32_t box[4] = {(uint32_t)BK, (uint32_t)BW, (uint32_t)BH, 1};
+    rc = encode(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4, const_cast<void*>(p.x), dims, str, box, "A", swz);
   } else {
     const uint64_t dims[5] = {2 * P, (uint64_t)W / 2, 2, (uint64_t)H / 2, (uint64_t)B};
     const uint64_t str[5] = {1, 2 * P, P * W, 2 * P * W, P * W * H};
-    const uint32_t box[5] = {(uint32_t)BLOCK_K, (uint32_t)BW, 1, (uint32_t)BH, 1};
-    rc = encode(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 5, const_cast<void*>(p.x), dims, str, box, "A(s2)");
+    const uint32_t box[5] = {(uint32_t)BK, (uint32_t)BW, 1, (uint32_t)BH, 1};
+    rc = encode(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 5, const_cast<void*>(p.x), dims, str, box, "A(s2)", swz);
   }
   if (rc) return rc;
 
-  auto run = [&](auto blockn_tag, auto stages_tag, auto minb_tag) -> int {
+  auto run = [&](auto blockn_tag, auto stages_tag, auto minb_tag, auto bk_tag, auto nstg_tag) -> int {
     constexpr int BN_ = decltype(blockn_tag)::value;
     constexpr int ST_ = decltype(stages_tag)::value;
     constexpr int MB_ = decltype(minb_tag)::value;
+    constexpr int BK_ = decltype(bk_tag)::value;
+    constexpr int NS_ = decltype(nstg_tag)::value;
     {
       const uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.Cout};
       const uint64_t str[2] = {1, (uint64_t)p.K};
-      const uint32_t box[2] = {(uint32_t)BLOCK_K, (uint32_t)BN_};
-      int r2 = encode(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 2, const_cast<void*>(p.w), dims, str, box, "W");
+      const uint32_t box[2] = {(uint32_t)BK_, (uint32_t)BN_};
+      int r2 = encode(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 2, const_cast<void*>(p.w), dims, str, box, "W", swz);
       if (r2) return r2;
     }
     const bool out16 = p.out_dtype == FB200_F16;
@@ -455,18 +534,29 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
       int r2 = encode(&td, out16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, out16 ? 2 : 4, 4, p.out, dims, str, box, "D");
       if (r2) return r2;
     }
-    const int64_t ctas = m_tiles * ((p.Cout + BN_ - 1) / BN_);
-    if (ctas > 0x7fffffffLL) { set_error("conv_tc: too many tiles (%lld)", (long long)ctas); return FB200_ERR_UNSUPPORTED; }
-    dim3 grid((unsigned)ctas);
-    if (out16) return launch<BN_, ST_, __half, MB_>(ta, tb, td, kp, grid, st);
-    return launch<BN_, ST_, float, MB_>(ta, tb, td, kp, grid, st);
+    KParams k2 = kp;
+    k2.n_tiles = (p.Cout + BN_ - 1) / BN_;
+    const int64_t total = m_tiles * k2.n_tiles;
+    if (total > 0x7fffffffLL) { set_error("conv_tc: too many tiles (%lld)", (long long)total); return FB200_ERR_UNSUPPORTED; }
+    k2.total_tiles = (int)total;
+    if (out16) return launch<BN_, ST_, __half, MB_, BK_, NS_>(ta, tb, td, k2, st);
+    return launch<BN_, ST_, float, MB_, BK_, NS_>(ta, tb, td, k2, st);
   };
+  using std::integral_constant;
+  typedef integral_constant<int, 64> K64;
+  typedef integral_constant<int, 32> K32;
+  typedef integral_constant<int, 1> I1;
+  typedef integral_constant<int, 2> I2;
+  if (BK == 32) {  // stem convs (Cin = 32): HBM-bound, two CTAs per SM
+    if (p.Cout > 32) return run(integral_constant<int, 64>{}, integral_constant<int, 4>{}, I2{}, K32{}, I2{});
+    return run(integral_constant<int, 32>{}, integral_constant<int, 4>{}, I2{}, K32{}, I2{});
+  }
   const int64_t tiles256 = m_tiles * ((p.Cout + 255) / 256);
   if (p.Cout > 128 && tiles256 >= 148)
-    return run(std::integral_constant<int, 256>{}, std::integral_constant<int, 4>{}, std::integral_constant<int, 1>{});
+    return run(integral_constant<int, 256>{}, integral_constant<int, 3>{}, I1{}, K64{}, I2{});   // 144 + 32 KiB
   if (p.Cout > 64)
-    return run(std::integral_constant<int, 128>{}, std::integral_constant<int, 5>{}, std::integral_constant<int, 1>{});
-  return run(std::integral_constant<int, 64>{}, std::integral_constant<int, 3>{}, std::integral_constant<int, 2>{});
+    return run(integral_constant<int, 128>{}, integral_constant<int, 5>{}, I1{}, K64{}, I2{});   // 160 + 32 KiB
+  return run(integral_constant<int, 64>{}, integral_constant<int, 3>{}, I2{}, K64{}, I2{});      // 72 + 32 KiB, 2 CTAs/SM
 }
 
 }  // namespace fb200

@@ -87,3 +87,9 @@ def test_slices_and_batch_stride():
     ops.conv2d(xg[..., 256:], w1.to(DEV), None, bi.to(DEV), out=mem[:, 50:450].unflatten(1, (20, 20)), algo=ops.ALGO_TCGEN05)
     assert float((mem[:, 50:450].reshape(2, 20, 20, 256).float().cpu() - ref1.float()).abs().max()) <= 3e-3 * max(1.0, float(ref1.abs().max()))
     assert float(mem[:, :50].abs().max()) == 0.0 and float(mem[:, 450:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("H,W,Cin,Cout,k", [(40, 40, 32, 32, 3), (64, 48, 32, 64, 3), (16, 16, 32, 64, 1), (320, 320, 32, 32, 3), (20, 20, 96, 64, 3)])
+def test_conv_cin32_swizzle64(H, W, Cin, Cout, k):
+    """Cin % 64 != 0 -> BLOCK_K = 32 variant (64-byte rows, SWIZZLE_64B): the ResNet-vd stem convs."""
+    run_case(2, H, W, Cin, Cout, k, 1, act=1, seed=H + Cin + Cout)

@@ -14,7 +14,7 @@ for s in $STAGES; do
     bench32) timeout 900 python bench.py --steps 3 --warmup 3 --precision fp32 --no-cpu-baseline > gpurun_out/bench_fp32.log 2> gpurun_out/bench_fp32.err ;;
     ref)   timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2>&1 ;;
     ncu_list) timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -s 940 -c 240 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1 ;;
-    ncu_full) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 40 -c 3 -o gpurun_out/prof_conv_tc python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1 ;;
+    ncu_full) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 2 -c 8 -o gpurun_out/prof_conv_tc python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1 ;;
   esac
   echo "stage $s exit $?" >> gpurun_out/stages.txt
 done
