@@ -33,7 +33,10 @@ namespace tc {
 
 constexpr int BLOCK_M = 128;
 constexpr int STAGING_BYTES = BLOCK_M * 128;  // one staging tile: 128 rows x 128 B
-constexpr int NUM_THREADS = 256;
+constexpr int PRODUCER_THREADS = 128;  // warps 0-3: TMA, MMA, TMEM alloc, spare
+// epilogue warp-groups (128 threads each): BLOCK_N >= 128 -> two groups, each owning half of the tile's columns
+template <int BLOCK_N> __host__ __device__ constexpr int epi_groups() { return BLOCK_N >= 128 ? 2 : 1; }
+template <int BLOCK_N> __host__ __device__ constexpr int num_threads() { return PRODUCER_THREADS + 128 * epi_groups<BLOCK_N>(); }
 
 struct KParams {
   const float* scale; const float* bias; const void* res;
@@ -78,7 +81,7 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
 
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -159,12 +162,12 @@ __device__ __forceinline__ void act32(float (&v)[32], int act) {
 
 template <int BLOCK_N, int BLOCK_K> constexpr int stage_bytes() { return (BLOCK_M + BLOCK_N) * BLOCK_K * 2; }
 template <int BLOCK_N, int STAGES, int BLOCK_K, int NSTG> constexpr int smem_bytes() {
-  return STAGES * stage_bytes<BLOCK_N, BLOCK_K>() + NSTG * STAGING_BYTES + 2 * BLOCK_N * 4 + (2 * STAGES + 4) * 8 + 16 + 1024 /*align slack*/;
+  return STAGES * stage_bytes<BLOCK_N, BLOCK_K>() + NSTG * epi_groups<BLOCK_N>() * STAGING_BYTES + 2 * BLOCK_N * 4 + (2 * STAGES + 4) * 8 + 16 + 1024 /*align slack*/;
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
 template <int BLOCK_N, int STAGES, typename TOut, int MIN_BLOCKS, int BLOCK_K, int NSTG>
-__global__ void __launch_bounds__(NUM_THREADS, MIN_BLOCKS)
+__global__ void __launch_bounds__(num_threads<BLOCK_N>(), MIN_BLOCKS)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_d, const KParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -173,8 +176,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint8_t* staging = smem_b + STAGES * B_STAGE_BYTES;  // NSTG x 16 KiB
-  float* s_scale = reinterpret_cast<float*>(staging + NSTG * STAGING_BYTES);
+  constexpr int EPI_GROUPS = epi_groups<BLOCK_N>();
+  uint8_t* staging = smem_b + STAGES * B_STAGE_BYTES;  // EPI_GROUPS x NSTG x 16 KiB
+  float* s_scale = reinterpret_cast<float*>(staging + EPI_GROUPS * NSTG * STAGING_BYTES);
   float* s_bias = s_scale + BLOCK_N;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_bias + BLOCK_N);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -192,7 +196,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4 * EPI_GROUPS); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -263,10 +267,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else if (warp >= 4) {
     // ===================================================================== epilogue (128 threads)
-    const int ew = warp - 4;             // TMEM lane quarter
+    const int grp = (warp - 4) >> 2;     // column group
+    const int ew = warp & 3;             // TMEM lane quarter (a warp may only touch lanes 32*(warp%4)..+31)
     const int row = ew * 32 + lane;      // tile row == TMEM lane
     const int bh = row / p.BW, bw = row - bh * p.BW;
-    const int et = threadIdx.x - 128;
+    const int et = threadIdx.x - PRODUCER_THREADS - grp * 128;
+    constexpr int GROUP_COLS = BLOCK_N / EPI_GROUPS;
+    const int c_begin = grp * GROUP_COLS, c_end = c_begin + GROUP_COLS;
+    uint8_t* const my_staging = staging + grp * NSTG * STAGING_BYTES;
     constexpr int CHUNK_COLS = 128 / (int)sizeof(TOut);  // output columns per 128-byte staging row
     const bool post = (p.act & FB200_ACT_RESIDUAL_AFTER) != 0;
     int acc = 0;
@@ -280,26 +288,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const bool row_valid = (row < p.BW * p.BH) && ho < p.Ho && wo < p.Wo;
       const TOut* res_row = p.res ? reinterpret_cast<const TOut*>(p.res) + (((int64_t)img * p.Ho + ho) * p.Wo + wo) * p.res_pitch : nullptr;
       // per-tile scale / bias (n0 changes with the N tile)
-      epi_bar();  // everyone is done with the previous tile's scale/bias
-      for (int i = et; i < BLOCK_N; i += 128) {
+      epi_bar(grp);  // the group is done with the previous tile's scale/bias
+      for (int i = c_begin + et; i < c_end; i += 128) {
         const int n = n0 + i;
         s_scale[i] = (p.scale && n < p.Cout) ? p.scale[n] : 1.f;
         s_bias[i] = (p.bias && n < p.Cout) ? p.bias[n] : 0.f;
       }
-      epi_bar();
+      epi_bar(grp);
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t tmem_acc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-      for (int c0 = 0; c0 < BLOCK_N; c0 += CHUNK_COLS) {
-        if (n0 + c0 >= p.Cout) break;  // uniform across the CTA
-        uint8_t* stg = staging + (chunk_ctr % NSTG) * STAGING_BYTES;
+      for (int c0 = c_begin; c0 < c_end; c0 += CHUNK_COLS) {
+        if (n0 + c0 >= p.Cout) break;  // uniform across the group
+        uint8_t* stg = my_staging + (chunk_ctr % NSTG) * STAGING_BYTES;
         uint8_t* srow = stg + row * 128;
+        // residual prefetch: independent of TMEM, issued first so its L2/HBM latency overlaps the rest
+        constexpr int RES_VECS = CHUNK_COLS * (int)sizeof(TOut) / 16;  // 16-byte vectors per row chunk (8)
+        uint4 rpre[RES_VECS];
+        const bool res_vec = res_row && row_valid && (n0 + c0 + CHUNK_COLS <= p.Cout) && (c0 + CHUNK_COLS <= c_end);
+        if (res_vec) {
+#pragma unroll
+          for (int q = 0; q < RES_VECS; ++q) rpre[q] = __ldg(reinterpret_cast<const uint4*>(res_row + n0 + c0) + q);
+        }
         // the TMA store that last used this staging buffer must have finished READING it
         if (et == 0) tma_store_wait_read<NSTG - 1>();
-        epi_bar();
+        epi_bar(grp);
 #pragma unroll
         for (int sub = 0; sub < CHUNK_COLS / 32; ++sub) {
-          if (c0 + sub * 32 >= BLOCK_N) break;  // BLOCK_N = 32 with fp16 output: half a staging row
+          if (c0 + sub * 32 >= c_end) break;  // BLOCK_N = 32 with fp16 output: half a staging row
           uint32_t r[32];
           tmem_ld32(tmem_acc + (uint32_t)(c0 + sub * 32), r);
           float v[32];
@@ -313,28 +329,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             v[j + 3] = fmaf(__uint_as_float(r[j + 3]), sc.w, bi.w);
           }
           if (post) act32(v, p.act);
-          if (res_row && row_valid) {
-            const int nb = n0 + c0 + sub * 32;
-            if (nb + 32 <= p.Cout) {
+          if (res_vec) {
+            if constexpr (sizeof(TOut) == 2) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                if constexpr (sizeof(TOut) == 2) {
-                  const uint4 t4 = *reinterpret_cast<const uint4*>(res_row + nb + j);
-                  const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&t4.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&t4.y));
-                  const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&t4.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&t4.w));
-                  v[j] += f0.x; v[j + 1] += f0.y; v[j + 2] += f1.x; v[j + 3] += f1.y;
-                  v[j + 4] += f2.x; v[j + 5] += f2.y; v[j + 6] += f3.x; v[j + 7] += f3.y;
-                } else {
-                  const float4 a4 = *reinterpret_cast<const float4*>(res_row + nb + j), b4 = *reinterpret_cast<const float4*>(res_row + nb + j + 4);
-                  v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
-                  v[j + 4] += b4.x; v[j + 5] += b4.y; v[j + 6] += b4.z; v[j + 7] += b4.w;
-                }
+              for (int q = 0; q < 4; ++q) {  // 4 x 16 B = 32 halves of this sub-chunk
+                const uint4 t4 = rpre[sub * 4 + q];
+                const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&t4.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&t4.y));
+                const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&t4.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&t4.w));
+                v[q * 8 + 0] += f0.x; v[q * 8 + 1] += f0.y; v[q * 8 + 2] += f1.x; v[q * 8 + 3] += f1.y;
+                v[q * 8 + 4] += f2.x; v[q * 8 + 5] += f2.y; v[q * 8 + 6] += f3.x; v[q * 8 + 7] += f3.y;
               }
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (nb + j < p.Cout) v[j] += to_f(res_row[nb + j]);
+              for (int q = 0; q < 8; ++q) {  // 8 x 16 B = 32 floats
+                const uint4 t4 = rpre[q];
+                v[q * 4 + 0] += __uint_as_float(t4.x); v[q * 4 + 1] += __uint_as_float(t4.y);
+                v[q * 4 + 2] += __uint_as_float(t4.z); v[q * 4 + 3] += __uint_as_float(t4.w);
+              }
             }
+          } else if (res_row && row_valid) {
+            const int nb = n0 + c0 + sub * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nb + j < p.Cout) v[j] += to_f(res_row[nb + j]);
           }
           if (!post) act32(v, p.act);
           // 16-byte pieces into the 128B-swizzled staging row: physical chunk = logical chunk ^ (row & 7)
@@ -357,7 +374,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
         fence_proxy_async();
-        epi_bar();
+        epi_bar(grp);
         if (et == 0) {
           tma_store_4d(&tmap_d, stg, n0 + c0, w0, h0, img);
           tma_store_commit();
@@ -442,6 +459,7 @@ template <int BLOCK_N, int STAGES, typename TOut, int MIN_BLOCKS, int BLOCK_K, i
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const KParams& kp, cudaStream_t st) {
   auto kern = conv_tc_kernel<BLOCK_N, STAGES, TOut, MIN_BLOCKS, BLOCK_K, NSTG>;
   constexpr int smem = smem_bytes<BLOCK_N, STAGES, BLOCK_K, NSTG>();
+  constexpr int NUM_THREADS = num_threads<BLOCK_N>();
   static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
   static_assert(MIN_BLOCKS * 2 * BLOCK_N <= 512, "TMEM budget exceeded (a blocked tcgen05.alloc would deadlock)");
   static bool configured = false;
@@ -553,9 +571,9 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
   }
   const int64_t tiles256 = m_tiles * ((p.Cout + 255) / 256);
   if (p.Cout > 128 && tiles256 >= 148)
-    return run(integral_constant<int, 256>{}, integral_constant<int, 3>{}, I1{}, K64{}, I2{});   // 144 + 32 KiB
+    return run(integral_constant<int, 256>{}, integral_constant<int, 3>{}, I1{}, K64{}, I2{});   // 144 + 64 KiB
   if (p.Cout > 64)
-    return run(integral_constant<int, 128>{}, integral_constant<int, 5>{}, I1{}, K64{}, I2{});   // 160 + 32 KiB
+    return run(integral_constant<int, 128>{}, integral_constant<int, 4>{}, I1{}, K64{}, I2{});   // 128 + 64 KiB
   return run(integral_constant<int, 64>{}, integral_constant<int, 3>{}, I2{}, K64{}, I2{});      // 72 + 32 KiB, 2 CTAs/SM
 }
 

@@ -108,6 +108,8 @@ __global__ void __launch_bounds__(256) attention_kernel(const T* __restrict__ q,
   }
 }
 
+int attention_mma(const __half* q, int q_pitch, const __half* k, int k_pitch, const __half* v, int v_pitch, __half* out, int out_pitch, int B,
+                  int Lq, int Lk, int heads, float scale, cudaStream_t st);
 }  // namespace fb200
 using namespace fb200;
 
@@ -129,6 +131,10 @@ extern "C" int fb200_attention(const void* q, int q_pitch, const void* k, int k_
   FB_CHECK_ARG(q && k && v && out, "attention: null pointer");
   FB_CHECK_ARG(head_dim == 32, "attention: head_dim must be 32 (got %d)", head_dim);
   FB_CHECK_ARG(q_pitch % 4 == 0 && k_pitch % 4 == 0 && v_pitch % 4 == 0, "attention: pitches must be multiples of 4");
+  if (dtype == FB200_F16 && q_pitch % 8 == 0 && k_pitch % 8 == 0 && v_pitch % 8 == 0 && out_pitch % 2 == 0 &&
+      (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) & 15) == 0 && ((uintptr_t)out & 3) == 0)
+    return attention_mma((const __half*)q, q_pitch, (const __half*)k, k_pitch, (const __half*)v, v_pitch, (__half*)out, out_pitch, B, Lq, Lk, heads, scale,
+                         (cudaStream_t)stream);
   const size_t smem = ((size_t)Lk * 33 + (size_t)Lk * 32 + (size_t)8 * Lk + 8 * 32) * sizeof(float);
   FB_CHECK_ARG(smem <= 227 * 1024, "attention: Lk=%d does not fit shared memory", Lk);
   dim3 grid(B * heads, (unsigned)cdiv(Lq, ATT_QT));
@@ -147,3 +153,152 @@ extern "C" int fb200_attention(const void* q, int q_pitch, const void* k, int k_
   FB_CHECK_LAUNCH("attention");
   return FB200_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// fp16 tensor-core attention (head_dim 32): legacy mma.sync.m16n8k16 is the right tool here — per (batch, head) the
+// problem is 300..400 x 32, far below one tcgen05 tile; the whole K and V of a head stay in shared memory and each
+// warp runs a flash-style online softmax over 64-key blocks for 16 queries.  4 warps = 64 queries per CTA.
+// ------------------------------------------------------------------------------------------------
+namespace fb200 {
+
+constexpr int AM_PITCH = 40;  // halves per smem row (32 + 8 pad): conflict-free ldmatrix
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const __half* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const __half* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(128) attention_mma_kernel(const __half* __restrict__ q, int q_pitch, const __half* __restrict__ k, int k_pitch,
+                                                            const __half* __restrict__ v, int v_pitch, __half* __restrict__ out, int out_pitch,
+                                                            int Lq, int Lk, int heads, float scale_log2) {
+  extern __shared__ __align__(16) __half smh[];
+  const int LkP = (Lk + 63) & ~63;            // keys padded to whole 64-key blocks (zero rows)
+  __half* Ks = smh;                           // [LkP][AM_PITCH]
+  __half* Vs = Ks + (size_t)LkP * AM_PITCH;   // [LkP][AM_PITCH]
+  __half* Qs = Vs + (size_t)LkP * AM_PITCH;   // [64][AM_PITCH]
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int q0 = blockIdx.y * 64;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // cooperative loads: 4 x 16-byte vectors per row
+  for (int i = tid; i < LkP * 4; i += 128) {
+    const int r = i >> 2, c = (i & 3) * 8;
+    uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+    if (r < Lk) {
+      kv = *reinterpret_cast<const uint4*>(k + ((int64_t)b * Lk + r) * k_pitch + h * 32 + c);
+      vv = *reinterpret_cast<const uint4*>(v + ((int64_t)b * Lk + r) * v_pitch + h * 32 + c);
+    }
+    *reinterpret_cast<uint4*>(Ks + r * AM_PITCH + c) = kv;
+    *reinterpret_cast<uint4*>(Vs + r * AM_PITCH + c) = vv;
+  }
+  for (int i = tid; i < 64 * 4; i += 128) {
+    const int r = i >> 2, c = (i & 3) * 8;
+    uint4 qv = make_uint4(0, 0, 0, 0);
+    if (q0 + r < Lq) qv = *reinterpret_cast<const uint4*>(q + ((int64_t)b * Lq + q0 + r) * q_pitch + h * 32 + c);
+    *reinterpret_cast<uint4*>(Qs + r * AM_PITCH + c) = qv;
+  }
+  __syncthreads();
+  // Q fragments of this warp's 16 queries: 2 k-steps (d 0-15, 16-31)
+  uint32_t qa[2][4];
+  {
+    const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+    const int c = (lane >> 4) * 8;
+    ldsm_x4(qa[0], Qs + r * AM_PITCH + c);
+    ldsm_x4(qa[1], Qs + r * AM_PITCH + 16 + c);
+  }
+  float o[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;  // rows lane/4 and lane/4+8
+  for (int kb = 0; kb < LkP; kb += 64) {
+    float s[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[nt][j] = 0.f;
+      uint32_t kf[4];  // B fragments: (d 0-7, 8-15) = k-step 0, (d 16-23, 24-31) = k-step 1, for keys kb+nt*8..+7
+      ldsm_x4(kf, Ks + (kb + nt * 8 + (lane & 7)) * AM_PITCH + (lane >> 3) * 8);
+      mma16816(s[nt], qa[0], kf[0], kf[1]);
+      mma16816(s[nt], qa[1], kf[2], kf[3]);
+    }
+    // mask padded keys, block row max
+    float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int key = kb + nt * 8 + (lane & 3) * 2;
+      if (key >= Lk) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+      if (key + 1 >= Lk) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+      bm0 = fmaxf(bm0, fmaxf(s[nt][0], s[nt][1]));
+      bm1 = fmaxf(bm1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+    const float nm0 = fmaxf(m0, bm0), nm1 = fmaxf(m1, bm1);  // finite: every block holds at least one real key
+    const float a0 = exp2f((m0 - nm0) * scale_log2), a1 = exp2f((m1 - nm1) * scale_log2);
+    m0 = nm0; m1 = nm1;
+    l0 *= a0; l1 *= a1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { o[i][0] *= a0; o[i][1] *= a0; o[i][2] *= a1; o[i][3] *= a1; }
+    uint32_t pa[4][4];  // P as A fragments: 4 k-steps of 16 keys
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float p0 = exp2f((s[nt][0] - m0) * scale_log2), p1 = exp2f((s[nt][1] - m0) * scale_log2);
+      const float p2 = exp2f((s[nt][2] - m1) * scale_log2), p3 = exp2f((s[nt][3] - m1) * scale_log2);
+      l0 += p0 + p1; l1 += p2 + p3;
+      pa[nt >> 1][(nt & 1) * 2 + 0] = pack_h2(p0, p1);
+      pa[nt >> 1][(nt & 1) * 2 + 1] = pack_h2(p2, p3);
+    }
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {  // 16 keys per step
+      const int r = kb + ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+      uint32_t vf[4];
+      ldsm_x4_trans(vf, Vs + r * AM_PITCH + (lane >> 4) * 8);        // d 0-7 (b0,b1), d 8-15 (b0,b1)
+      mma16816(o[0], pa[ks], vf[0], vf[1]);
+      mma16816(o[1], pa[ks], vf[2], vf[3]);
+      ldsm_x4_trans(vf, Vs + r * AM_PITCH + 16 + (lane >> 4) * 8);   // d 16-23, 24-31
+      mma16816(o[2], pa[ks], vf[0], vf[1]);
+      mma16816(o[3], pa[ks], vf[2], vf[3]);
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  const int r0 = q0 + warp * 16 + (lane >> 2), r1 = r0 + 8;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const int c = h * 32 + nt * 8 + (lane & 3) * 2;
+    if (r0 < Lq) *reinterpret_cast<uint32_t*>(out + ((int64_t)b * Lq + r0) * out_pitch + c) = pack_h2(o[nt][0] * i0, o[nt][1] * i0);
+    if (r1 < Lq) *reinterpret_cast<uint32_t*>(out + ((int64_t)b * Lq + r1) * out_pitch + c) = pack_h2(o[nt][2] * i1, o[nt][3] * i1);
+  }
+}
+
+int attention_mma(const __half* q, int q_pitch, const __half* k, int k_pitch, const __half* v, int v_pitch, __half* out, int out_pitch, int B,
+                  int Lq, int Lk, int heads, float scale, cudaStream_t st) {
+  const int LkP = (Lk + 63) & ~63;
+  const size_t smem = ((size_t)2 * LkP + 64) * AM_PITCH * sizeof(__half);
+  if (smem > 227 * 1024) { set_error("attention(mma): Lk=%d does not fit shared memory", Lk); return FB200_ERR_UNSUPPORTED; }
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    configured = true;
+  }
+  dim3 grid(B * heads, (unsigned)cdiv(Lq, 64));
+  attention_mma_kernel<<<grid, 128, smem, st>>>(q, q_pitch, k, k_pitch, v, v_pitch, out, out_pitch, Lq, Lk, heads, scale * 1.4426950408889634f);
+  FB_CHECK_LAUNCH("attention_mma");
+  return FB200_OK;
+}
+
+}  // namespace fb200

@@ -70,6 +70,14 @@ EXPORTED_SYMBOLS = (
 )
 
 _launch_count = 0
+_trace = None       # profiling aid (tools/layer_roofline.py): list of [symbol, note, start_event, end_event]
+_trace_note = []
+
+
+def enable_trace(on: bool = True):
+    global _trace
+    _trace = [] if on else None
+    return _trace
 
 
 def launch_count() -> int:
@@ -123,7 +131,14 @@ class CudaBackend:
     def _call(self, name, *args):
         global _launch_count
         _launch_count += 1
+        if _trace is None:
+            _check(getattr(self.lib, name)(*args), name)
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         _check(getattr(self.lib, name)(*args), name)
+        e1.record()
+        _trace.append([name, _trace_note.pop() if _trace_note else "", e0, e1])
 
     def stem_conv(self, img, w, scale, bias, mean, std, act, out):
         self._cuda(img, w, out)
@@ -136,6 +151,8 @@ class CudaBackend:
         self._cuda(x, w, out)
         B, H, W, Cin = x.shape
         Cout, KH, KW, _ = w.shape
+        if _trace is not None:
+            _trace_note.append(dict(op="conv", B=B, H=H, W=W, Cin=Cin, Cout=Cout, k=KH, stride=stride, res=residual is not None, xdt=str(x.dtype)[6:], odt=str(out.dtype)[6:], algo=algo))
         self._call("fb200_conv2d", _p(x), _dt(x), B, H, W, Cin, _pitch(x), _p(w), KH, KW, stride, pad, _p(scale), _p(bias), _p(residual),
                    0 if residual is None else _pitch(residual), act, _p(out), _dt(out), _pitch(out, True), ctypes.c_int64(_batch_stride(out)), Cout, algo, _stream())
 
