@@ -23,6 +23,7 @@
 // Algorithmic bytes: A (M x Cin, each input pixel counted once), W, D (+ residual) once each.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -48,6 +49,7 @@ struct KParams {
   int stride2;                     // 0: 4-D stride-1 view, 1: 5-D stride-2 view
   int num_k_blocks;
   int n_tiles, total_tiles;        // N tiles per M tile; total = m_tiles * n_tiles
+  int dbg;                         // tuning aid (env FB200_TC_DBG): 1 = skip TMA store, 2 = skip residual, 4 = skip TMEM load
 };
 
 // ---------------------------------------------------------------------------------------------- PTX
@@ -94,6 +96,13 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* ba
 __device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3, int c4) {
   asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
                ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+// L2 prefetch of a box (no smem, no barrier): keeps the DRAM latency of the NEXT tile off the critical path
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_5d(const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global [%0, {%1, %2, %3, %4, %5}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
@@ -142,7 +151,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 // activation on 32 values with the switch OUTSIDE the element loop (uniform branch, lean straight-line bodies)
+template <bool GELU>
 __device__ __forceinline__ void act32(float (&v)[32], int act) {
+  if constexpr (GELU) {  // exact-erf GELU (AIFI FFN only) lives in its own kernel instantiation: ~50 instructions / element
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752440f));
+    return;
+  }
   switch (act & 15) {
     case FB200_ACT_RELU:
 #pragma unroll
@@ -150,11 +165,7 @@ __device__ __forceinline__ void act32(float (&v)[32], int act) {
       break;
     case FB200_ACT_SILU:
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = v[j] * __frcp_rn(1.f + __expf(-v[j]));
-      break;
-    case FB200_ACT_GELU:
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752440f));
+      for (int j = 0; j < 32; ++j) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));
       break;
     default: break;
   }
@@ -166,10 +177,10 @@ template <int BLOCK_N, int STAGES, int BLOCK_K, int NSTG> constexpr int smem_byt
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
-template <int BLOCK_N, int STAGES, typename TOut, int MIN_BLOCKS, int BLOCK_K, int NSTG>
+template <int BLOCK_N, int STAGES, typename TOut, int MIN_BLOCKS, int BLOCK_K, int NSTG, bool GELU>
 __global__ void __launch_bounds__(num_threads<BLOCK_N>(), MIN_BLOCKS)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const __grid_constant__ CUtensorMap tmap_d, const KParams p) {
+               const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r, const KParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
@@ -219,6 +230,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int n0 = (t % p.n_tiles) * BLOCK_N, mt = t / p.n_tiles;
         const int img = mt / tiles_per_img, rem = mt - img * tiles_per_img;
         const int h0 = (rem / p.tiles_w) * p.BH, w0 = (rem % p.tiles_w) * p.BW;
+        {  // L2 prefetch for the tile this CTA will process next (one box per channel chunk; taps overlap)
+          const int tn = t + (int)gridDim.x;
+          if (tn < p.total_tiles && (tn / p.n_tiles) != mt) {
+            const int mtn = tn / p.n_tiles, imgn = mtn / tiles_per_img, remn = mtn - imgn * tiles_per_img;
+            const int h0n = (remn / p.tiles_w) * p.BH, w0n = (remn % p.tiles_w) * p.BW;
+            for (int cc = 0; cc < p.cchunks; ++cc) {
+              if (!p.stride2) tma_prefetch_4d(&tmap_a, cc * BLOCK_K, w0n, h0n, imgn);
+              else {
+                for (int par = 0; par < 4; ++par)  // the four (h, w) parities of the 2x2 input cell
+                  tma_prefetch_5d(&tmap_a, (par & 1) * p.x_pitch + cc * BLOCK_K, w0n, par >> 1, h0n, imgn);
+              }
+            }
+          }
+        }
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
@@ -280,13 +305,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t chunk_ctr = 0;
+    // Residual: this thread's 128-byte row chunk is fetched (8 x LDG.128, L2-prefetched a tile ahead by TMA) at the top of
+    // each chunk, before the staging-buffer wait / TMEM load, and consumed after them.  (A one-chunk-ahead register
+    // pipeline was measured slower — profiles/r01_trip11 vs trip12; deeper prefetch needs an smem ring: next round.)
+    constexpr int RES_VECS = 8;  // 16-byte vectors per 128-byte row chunk
+    const bool has_res = p.res != nullptr && !(p.dbg & 2);
+    uint4 rcur[RES_VECS];
+    auto res_fetch = [&](int tt, int cc0, uint4 (&dst)[RES_VECS]) -> bool {
+      if (!has_res || tt >= p.total_tiles) return false;
+      const int n0_ = (tt % p.n_tiles) * BLOCK_N, mt_ = tt / p.n_tiles;
+      if (n0_ + cc0 + CHUNK_COLS > p.Cout || cc0 + CHUNK_COLS > c_end) return false;
+      const int img_ = mt_ / tiles_per_img, rem_ = mt_ - img_ * tiles_per_img;
+      const int ho_ = (rem_ / p.tiles_w) * p.BH + bh, wo_ = (rem_ % p.tiles_w) * p.BW + bw;
+      if (!(row < p.BW * p.BH && ho_ < p.Ho && wo_ < p.Wo)) return false;
+      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const TOut*>(p.res) + (((int64_t)img_ * p.Ho + ho_) * p.Wo + wo_) * p.res_pitch + n0_ + cc0);
+#pragma unroll
+      for (int q = 0; q < RES_VECS; ++q) dst[q] = __ldg(src + q);
+      return true;
+    };
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const int n0 = (t % p.n_tiles) * BLOCK_N, mt = t / p.n_tiles;
       const int img = mt / tiles_per_img, rem = mt - img * tiles_per_img;
       const int h0 = (rem / p.tiles_w) * p.BH, w0 = (rem % p.tiles_w) * p.BW;
       const int ho = h0 + bh, wo = w0 + bw;
       const bool row_valid = (row < p.BW * p.BH) && ho < p.Ho && wo < p.Wo;
-      const TOut* res_row = p.res ? reinterpret_cast<const TOut*>(p.res) + (((int64_t)img * p.Ho + ho) * p.Wo + wo) * p.res_pitch : nullptr;
+      const TOut* res_row = has_res ? reinterpret_cast<const TOut*>(p.res) + (((int64_t)img * p.Ho + ho) * p.Wo + wo) * p.res_pitch : nullptr;
+      if (has_res && et == 0) {  // L2 prefetch of the NEXT tile's residual columns owned by this group
+        const int tn = t + (int)gridDim.x;
+        if (tn < p.total_tiles) {
+          const int n0n = (tn % p.n_tiles) * BLOCK_N, mtn = tn / p.n_tiles, imgn = mtn / tiles_per_img, remn = mtn - imgn * tiles_per_img;
+          const int h0n = (remn / p.tiles_w) * p.BH, w0n = (remn % p.tiles_w) * p.BW;
+          for (int c = c_begin; c < c_end; c += 128 / (int)sizeof(TOut))
+            if (n0n + c < p.Cout) tma_prefetch_4d(&tmap_r, n0n + c, w0n, h0n, imgn);
+        }
+      }
       // per-tile scale / bias (n0 changes with the N tile)
       epi_bar(grp);  // the group is done with the previous tile's scale/bias
       for (int i = c_begin + et; i < c_end; i += 128) {
@@ -298,18 +350,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t tmem_acc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+#pragma unroll 1
       for (int c0 = c_begin; c0 < c_end; c0 += CHUNK_COLS) {
         if (n0 + c0 >= p.Cout) break;  // uniform across the group
         uint8_t* stg = my_staging + (chunk_ctr % NSTG) * STAGING_BYTES;
         uint8_t* srow = stg + row * 128;
-        // residual prefetch: independent of TMEM, issued first so its L2/HBM latency overlaps the rest
-        constexpr int RES_VECS = CHUNK_COLS * (int)sizeof(TOut) / 16;  // 16-byte vectors per row chunk (8)
-        uint4 rpre[RES_VECS];
-        const bool res_vec = res_row && row_valid && (n0 + c0 + CHUNK_COLS <= p.Cout) && (c0 + CHUNK_COLS <= c_end);
-        if (res_vec) {
-#pragma unroll
-          for (int q = 0; q < RES_VECS; ++q) rpre[q] = __ldg(reinterpret_cast<const uint4*>(res_row + n0 + c0) + q);
-        }
+        const bool res_vec = res_fetch(t, c0, rcur);
         // the TMA store that last used this staging buffer must have finished READING it
         if (et == 0) tma_store_wait_read<NSTG - 1>();
         epi_bar(grp);
@@ -328,32 +374,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             v[j + 2] = fmaf(__uint_as_float(r[j + 2]), sc.z, bi.z);
             v[j + 3] = fmaf(__uint_as_float(r[j + 3]), sc.w, bi.w);
           }
-          if (post) act32(v, p.act);
-          if (res_vec) {
-            if constexpr (sizeof(TOut) == 2) {
+          auto add_residual = [&]() {
+            if (res_vec) {
+              if constexpr (sizeof(TOut) == 2) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {  // 4 x 16 B = 32 halves of this sub-chunk
-                const uint4 t4 = rpre[sub * 4 + q];
-                const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&t4.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&t4.y));
-                const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&t4.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&t4.w));
-                v[q * 8 + 0] += f0.x; v[q * 8 + 1] += f0.y; v[q * 8 + 2] += f1.x; v[q * 8 + 3] += f1.y;
-                v[q * 8 + 4] += f2.x; v[q * 8 + 5] += f2.y; v[q * 8 + 6] += f3.x; v[q * 8 + 7] += f3.y;
-              }
-            } else {
+                for (int q = 0; q < 4; ++q) {  // 4 x 16 B = 32 halves of this sub-chunk
+                  const uint4 t4 = rcur[sub * 4 + q];
+                  const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&t4.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&t4.y));
+                  const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&t4.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&t4.w));
+                  v[q * 8 + 0] += f0.x; v[q * 8 + 1] += f0.y; v[q * 8 + 2] += f1.x; v[q * 8 + 3] += f1.y;
+                  v[q * 8 + 4] += f2.x; v[q * 8 + 5] += f2.y; v[q * 8 + 6] += f3.x; v[q * 8 + 7] += f3.y;
+                }
+              } else {
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {  // 8 x 16 B = 32 floats
-                const uint4 t4 = rpre[q];
-                v[q * 4 + 0] += __uint_as_float(t4.x); v[q * 4 + 1] += __uint_as_float(t4.y);
-                v[q * 4 + 2] += __uint_as_float(t4.z); v[q * 4 + 3] += __uint_as_float(t4.w);
+                for (int q = 0; q < 8; ++q) {  // 8 x 16 B = 32 floats
+                  const uint4 t4 = rcur[q];
+                  v[q * 4 + 0] += __uint_as_float(t4.x); v[q * 4 + 1] += __uint_as_float(t4.y);
+                  v[q * 4 + 2] += __uint_as_float(t4.z); v[q * 4 + 3] += __uint_as_float(t4.w);
+                }
               }
             }
-          } else if (res_row && row_valid) {
-            const int nb = n0 + c0 + sub * 32;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < p.Cout) v[j] += to_f(res_row[nb + j]);
-          }
-          if (!post) act32(v, p.act);
+          };
+          if (!post) add_residual();
+          act32<GELU>(v, p.act);
+          if (post) add_residual();
           // 16-byte pieces into the 128B-swizzled staging row: physical chunk = logical chunk ^ (row & 7)
           if constexpr (sizeof(TOut) == 2) {
 #pragma unroll
@@ -376,7 +420,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         fence_proxy_async();
         epi_bar(grp);
         if (et == 0) {
-          tma_store_4d(&tmap_d, stg, n0 + c0, w0, h0, img);
+          if (!(p.dbg & 1)) tma_store_4d(&tmap_d, stg, n0 + c0, w0, h0, img);
           tma_store_commit();
         }
         ++chunk_ctr;
@@ -455,9 +499,9 @@ static int num_sms() {
   return n;
 }
 
-template <int BLOCK_N, int STAGES, typename TOut, int MIN_BLOCKS, int BLOCK_K, int NSTG>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const KParams& kp, cudaStream_t st) {
-  auto kern = conv_tc_kernel<BLOCK_N, STAGES, TOut, MIN_BLOCKS, BLOCK_K, NSTG>;
+template <int BLOCK_N, int STAGES, typename TOut, int MIN_BLOCKS, int BLOCK_K, int NSTG, bool GELU>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr, const KParams& kp, cudaStream_t st) {
+  auto kern = conv_tc_kernel<BLOCK_N, STAGES, TOut, MIN_BLOCKS, BLOCK_K, NSTG, GELU>;
   constexpr int smem = smem_bytes<BLOCK_N, STAGES, BLOCK_K, NSTG>();
   constexpr int NUM_THREADS = num_threads<BLOCK_N>();
   static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
@@ -470,7 +514,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
   }
   const int64_t cap = (int64_t)num_sms() * MIN_BLOCKS;
   const unsigned grid = (unsigned)(kp.total_tiles < cap ? kp.total_tiles : cap);
-  kern<<<grid, NUM_THREADS, smem, st>>>(ta, tb, td, kp);
+  kern<<<grid, NUM_THREADS, smem, st>>>(ta, tb, td, tr, kp);
   FB_CHECK_LAUNCH("conv_tc_kernel");
   return FB200_OK;
 }
@@ -485,7 +529,9 @@ bool conv2d_tc_supported(const ConvParams& p, int x_dtype, int out_dtype) {
   const int oelt = out_dtype == FB200_F16 ? 2 : 4;
   if ((p.out_pitch * oelt) % 16 != 0) return false;
   if (p.res && ((p.res_pitch * oelt) % 16 != 0 || (reinterpret_cast<uintptr_t>(p.res) & 15))) return false;
+  if (p.res && p.Cout % (128 / oelt) != 0) return false;  // residual is consumed in whole 128-byte row chunks
   if (p.KH != p.KW) return false;
+  if ((p.act & 15) == FB200_ACT_GELU && (out_dtype != FB200_F16 || p.Cin % 64 != 0)) return false;
   if ((p.out_bs * oelt) % 16 != 0) return false;
   if (p.stride == 1) return (2 * p.pad == p.KH - 1) || (p.KH == 1 && p.pad == 0);
   if (p.stride == 2) return p.KH == 3 && p.pad == 1 && p.H % 2 == 0 && p.W % 2 == 0;
@@ -530,7 +576,7 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
   }
   if (rc) return rc;
 
-  auto run = [&](auto blockn_tag, auto stages_tag, auto minb_tag, auto bk_tag, auto nstg_tag) -> int {
+  auto run = [&](auto blockn_tag, auto stages_tag, auto minb_tag, auto bk_tag, auto nstg_tag, auto gelu_tag) -> int {
     constexpr int BN_ = decltype(blockn_tag)::value;
     constexpr int ST_ = decltype(stages_tag)::value;
     constexpr int MB_ = decltype(minb_tag)::value;
@@ -552,29 +598,49 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
       int r2 = encode(&td, out16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, out16 ? 2 : 4, 4, p.out, dims, str, box, "D");
       if (r2) return r2;
     }
+    CUtensorMap tr = td;  // residual: same geometry as the output, its own pointer / pitch (used for L2 prefetch only)
+    if (p.res) {
+      const uint64_t RP = (uint64_t)p.res_pitch;
+      const uint64_t dims[4] = {(uint64_t)p.Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)B};
+      const uint64_t str[4] = {1, RP, RP * Wo, RP * Wo * Ho};
+      const uint32_t box[4] = {(uint32_t)(out16 ? 64 : 32), (uint32_t)BW, (uint32_t)BH, 1};
+      int r2 = encode(&tr, out16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, out16 ? 2 : 4, 4, const_cast<void*>(p.res), dims, str, box, "R");
+      if (r2) return r2;
+    }
     KParams k2 = kp;
     k2.n_tiles = (p.Cout + BN_ - 1) / BN_;
     const int64_t total = m_tiles * k2.n_tiles;
     if (total > 0x7fffffffLL) { set_error("conv_tc: too many tiles (%lld)", (long long)total); return FB200_ERR_UNSUPPORTED; }
     k2.total_tiles = (int)total;
-    if (out16) return launch<BN_, ST_, __half, MB_, BK_, NS_>(ta, tb, td, k2, st);
-    return launch<BN_, ST_, float, MB_, BK_, NS_>(ta, tb, td, k2, st);
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("FB200_TC_DBG"); dbg = e ? atoi(e) : 0; } k2.dbg = dbg; }
+    if constexpr (decltype(gelu_tag)::value) return launch<BN_, ST_, __half, MB_, BK_, NS_, true>(ta, tb, td, tr, k2, st);
+    else {
+      if (out16) return launch<BN_, ST_, __half, MB_, BK_, NS_, false>(ta, tb, td, tr, k2, st);
+      return launch<BN_, ST_, float, MB_, BK_, NS_, false>(ta, tb, td, tr, k2, st);
+    }
   };
   using std::integral_constant;
   typedef integral_constant<int, 64> K64;
   typedef integral_constant<int, 32> K32;
   typedef integral_constant<int, 1> I1;
   typedef integral_constant<int, 2> I2;
+  if ((p.act & 15) == FB200_ACT_GELU)  // exact-erf GELU: dedicated instantiation (fp16 out, Cin % 64 == 0; checked in conv2d_tc_supported)
+    return run(integral_constant<int, 128>{}, integral_constant<int, 4>{}, I1{}, K64{}, I2{}, std::true_type{});
   if (BK == 32) {  // stem convs (Cin = 32): HBM-bound, two CTAs per SM
-    if (p.Cout > 32) return run(integral_constant<int, 64>{}, integral_constant<int, 4>{}, I2{}, K32{}, I2{});
-    return run(integral_constant<int, 32>{}, integral_constant<int, 4>{}, I2{}, K32{}, I2{});
+    if (p.Cout > 32) return run(integral_constant<int, 64>{}, integral_constant<int, 4>{}, I2{}, K32{}, I2{}, std::false_type{});
+    return run(integral_constant<int, 32>{}, integral_constant<int, 4>{}, I2{}, K32{}, I2{}, std::false_type{});
   }
+  static int force_bn = -1;  // tuning aid: FB200_TC_BN=64|128|256
+  if (force_bn < 0) { const char* e = getenv("FB200_TC_BN"); force_bn = e ? atoi(e) : 0; }
+  if (force_bn == 64) return run(integral_constant<int, 64>{}, integral_constant<int, 3>{}, I2{}, K64{}, I2{}, std::false_type{});
+  if (force_bn == 128) return run(integral_constant<int, 128>{}, integral_constant<int, 4>{}, I1{}, K64{}, I2{}, std::false_type{});
+  if (force_bn == 256) return run(integral_constant<int, 256>{}, integral_constant<int, 3>{}, I1{}, K64{}, I2{}, std::false_type{});
   const int64_t tiles256 = m_tiles * ((p.Cout + 255) / 256);
   if (p.Cout > 128 && tiles256 >= 148)
-    return run(integral_constant<int, 256>{}, integral_constant<int, 3>{}, I1{}, K64{}, I2{});   // 144 + 64 KiB
+    return run(integral_constant<int, 256>{}, integral_constant<int, 3>{}, I1{}, K64{}, I2{}, std::false_type{});   // 144 + 64 KiB
   if (p.Cout > 64)
-    return run(integral_constant<int, 128>{}, integral_constant<int, 4>{}, I1{}, K64{}, I2{});   // 128 + 64 KiB
-  return run(integral_constant<int, 64>{}, integral_constant<int, 3>{}, I2{}, K64{}, I2{});      // 72 + 32 KiB, 2 CTAs/SM
+    return run(integral_constant<int, 128>{}, integral_constant<int, 4>{}, I1{}, K64{}, I2{}, std::false_type{});   // 128 + 64 KiB
+  return run(integral_constant<int, 64>{}, integral_constant<int, 3>{}, I2{}, K64{}, I2{}, std::false_type{});      // 72 + 32 KiB, 2 CTAs/SM
 }
 
 }  // namespace fb200
