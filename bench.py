@@ -31,6 +31,8 @@ import torch  # noqa: E402
 METRIC = "images/sec fai-detr-l bs=32 640x640 inference"
 GFLOP_PER_IMG_USEFUL = 139.05  # excludes the dead mask_features conv
 IDEAL_US_PER_IMG_16BIT = 129.0  # SURVEY.md §8(d) sum-of-max roofline at 16-bit activations
+# dram__bytes_read.sum + dram__bytes_write.sum of that launch from the committed ncu --set full capture (profiles/); None until captured
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 167.8e6  # profiles/r01_trip13_summary.md §2 (106.1 MB read + 61.7 MB written; 211 MB algorithmic)
 
 
 def measured_peaks():
@@ -128,18 +130,19 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     cores = os.cpu_count() or 1
+    cpu_threads = min(cores, 32)  # torch CPU conv kernels stop scaling (and regress) beyond ~32 threads on this path
     config = {"workload": "fai-detr-l-obj365 bs=32/GPU 640x640 inference (BASELINE configs[1])", "per_gpu_batch": args.batch, "global_batch": args.batch * world,
-              "weights": "seeded random (focoos_b200.utils.seeded_weights, seed 0)", "parallelism": f"replicas x{world}", "l2_policy": "inputs_larger_than_L2 (157 MB fp32 batch + >2 GB activations per step)"}
+              "weights": "seeded random (focoos_b200.utils.seeded_weights, seed 0)", "parallelism": f"replicas x{world}", "l2_policy": "inputs_larger_than_L2 (each step streams >2 GB of activations + 88 MB of weights through the 126 MB L2; 39 MB uint8 input batch)"}
     sd = seeded_weights()
 
     if args.impl == "reference":
         if rank != 0:
             return
         cb, csteps, cwarm = 2, max(1, min(args.steps, 3)), min(args.warmup, 1)
-        v, ms = cpu_reference_run(cb, csteps, cwarm, sd, cores)
+        v, ms = cpu_reference_run(cb, csteps, cwarm, sd, cpu_threads)
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": csteps, "warmup": cwarm, "ms_per_step": ms,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": f"{csteps} timed passes of batch {cb} (reference is slower per image at larger CPU batches, BASELINE.md §3)"},
+                "cpu_baseline": {"value": v, "unit": "images/s", "cores": cpu_threads, "host_cores": cores, "kind": "port", "sample": f"{csteps} timed passes of batch {cb} (reference is slower per image at larger CPU batches, BASELINE.md §3)"},
                 "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line))
         return
@@ -148,12 +151,12 @@ def main():
     from focoos_b200.fai_detr import FAIDetr
     from oracle.gen_golden import synth_images  # input generator only (numpy); not a compute path
 
+    from focoos_b200 import distributed as D
+
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=dev)
+    D.init_from_env("nccl", dev)  # replicas only: the group is used for the timing barrier / max-over-ranks, never for data
+    import torch.distributed as dist
     model = FAIDetr(DETRConfig(), precision=args.precision)
     model.load_state_dict(sd, strict=True)
     fm = FocoosModel(model, ModelInfo(name="fai-detr-l-obj365", im_size=640))
@@ -162,7 +165,7 @@ def main():
     B = args.batch
     imgs_np = np.stack(synth_images(1 + rank, [(640, 640)] * B))  # [B,640,640,3] uint8
     host_u8 = torch.from_numpy(imgs_np).pin_memory()
-    x_dev = host_u8.to(dev).permute(0, 3, 1, 2).float().contiguous()
+    x_dev = host_u8.to(dev)  # uint8 [B,640,640,3] resident in HBM: the stem kernel reads it directly
     sizes = [(640, 640)] * B
     sizes_dev = torch.tensor(sizes, dtype=torch.int32, device=dev)
 
@@ -207,12 +210,8 @@ def main():
             run_step()
         e1.record()
         torch.cuda.synchronize()
-    ms_total = e0.elapsed_time(e1)
-    t = torch.tensor([ms_total], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.barrier()
-    ms_total = float(t.item())
+    ms_total = D.max_over_ranks(e0.elapsed_time(e1), dev)  # device time, max over ranks
+    D.synchronize()
     ms_step = ms_total / args.steps
     value = B * world / (ms_step / 1e3)
 
@@ -231,10 +230,7 @@ def main():
         dets = step_e2e()
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-    te = torch.tensor([e2e_ms], device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_ms = float(te.item())
+    e2e_ms = D.max_over_ranks(e2e_ms, dev)
     e2e = {"value": B * world / (e2e_ms / 1e3), "unit": "images/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(host_u8.numel()) + B * 8,
            "d2h_bytes_per_step": B * (300 * 7 + 1) * 4, "api": "FocoosModel.__call__(pinned uint8 [B,H,W,3], batched=True)"}
 
@@ -259,17 +255,17 @@ def main():
         k_ms = r0.elapsed_time(r1) / nrep
         flops = 2.0 * B * 80 * 80 * 256 * 256 * 9
         ach = flops / (k_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "conv_tc_kernel<256,4,half> 3x3 256->256 @80x80 (RepVGG block of CSPRepLayer; 4 launches/step, 21.7% of model FLOPs)",
+        roof = {"bound": "tensor", "kernel": "conv_tc_kernel<256,3,half,1,64,2> on the 3x3 256->256 @80x80 conv (re-parameterised RepVGG block of the FPN CSPRepLayer; 3 launches/step at this shape, 16% of model FLOPs; conv_tc_kernel as a family = 97% of FLOPs)",
                 "achieved": ach, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": ach / peaks["tf_burst"], "peak_source": peaks["source"] + " burst (kernel timed alone)",
-                "launch_ms": k_ms, "flops_per_launch": flops, "traffic": None,
+                "launch_ms": k_ms, "flops_per_launch": flops, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
                 "model": {"useful_gflop_per_img": GFLOP_PER_IMG_USEFUL, "achieved_tflops_whole_step": GFLOP_PER_IMG_USEFUL * B / ms_step,
                           "ideal_ms_per_step_16bit": IDEAL_US_PER_IMG_16BIT * B / 1e3, "frac_of_ideal": (IDEAL_US_PER_IMG_16BIT * B / 1e3) / ms_step}}
 
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
-            cv, cms = cpu_reference_run(2, 2, 1, sd, cores)
-            cpu = {"value": cv, "unit": "images/s", "cores": cores, "kind": "port", "sample": "2 timed passes of batch 2 (oracle port of the reference's torch fp32 CPU forward + post-process)"}
+            cv, cms = cpu_reference_run(2, 2, 1, sd, cpu_threads)
+            cpu = {"value": cv, "unit": "images/s", "cores": cpu_threads, "host_cores": cores, "kind": "port", "sample": "2 timed passes of batch 2 (oracle port of the reference's torch fp32 CPU forward + post-process)"}
         line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16" if args.precision == "fp16" else "f32", "data": "synthetic",
                 "config": config, "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,

@@ -20,8 +20,8 @@ void set_error(const char* fmt, ...) {
 // ------------------------------------------------------------------------------------------------
 // stem: one thread = one output pixel x CO_PER_THREAD channels. Input NCHW fp32 raw.
 // ------------------------------------------------------------------------------------------------
-template <typename TOut, int COUT>
-__global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict__ img, int B, int H, int W,
+template <typename TOut, int COUT, bool U8_NHWC>
+__global__ void __launch_bounds__(128) stem_conv_kernel(const void* __restrict__ img_, int B, int H, int W,
                                                         const float* __restrict__ w, const float* __restrict__ scale,
                                                         const float* __restrict__ bias, float m0, float m1, float m2,
                                                         float s0, float s1, float s2, int act, TOut* __restrict__ out) {
@@ -45,7 +45,8 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict_
   float acc[COUT];
 #pragma unroll
   for (int i = 0; i < COUT; ++i) acc[i] = 0.f;
-  const float* ib = img + (int64_t)b * 3 * H * W;
+  const float* ib = reinterpret_cast<const float*>(img_) + (int64_t)b * 3 * H * W;           // NCHW fp32
+  const uint8_t* ub = reinterpret_cast<const uint8_t*>(img_) + (int64_t)b * H * W * 3;        // NHWC uint8
 #pragma unroll
   for (int kh = 0; kh < 3; ++kh) {
     const int hi = ho * 2 - 1 + kh;
@@ -56,7 +57,9 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict_
 #pragma unroll
       for (int ci = 0; ci < 3; ++ci) {
         // same arithmetic as the reference: (x - mean) / std, then the conv sees 0 outside the image
-        const float v = ok ? (ib[((int64_t)ci * H + hi) * W + wi] - mean[ci]) / stdv[ci] : 0.f;
+        float raw = 0.f;
+        if (ok) raw = U8_NHWC ? (float)ub[((int64_t)hi * W + wi) * 3 + ci] : ib[((int64_t)ci * H + hi) * W + wi];
+        const float v = ok ? (raw - mean[ci]) / stdv[ci] : 0.f;
         const float* wr = &ws[((kh * 3 + kw) * 3 + ci) * COUT];
 #pragma unroll
         for (int co = 0; co < COUT; ++co) acc[co] = fmaf(v, wr[co], acc[co]);
@@ -222,9 +225,8 @@ extern "C" int fb200_device_supports_tcgen05(void) {
   return major == 10 ? 1 : 0;
 }
 
-extern "C" int fb200_stem_conv3x3s2(const float* img, int B, int H, int W, const float* w, const float* scale,
-                                    const float* bias, const float* mean3, const float* std3, int act, void* out,
-                                    int out_dtype, int Cout, void* stream) {
+static int stem_launch(const void* img, bool u8, int B, int H, int W, const float* w, const float* scale, const float* bias, const float* mean3,
+                       const float* std3, int act, void* out, int out_dtype, int Cout, void* stream) {
   FB_CHECK_ARG(img && w && out && mean3 && std3, "stem_conv: null pointer");
   FB_CHECK_ARG(Cout == 32, "stem_conv: only Cout=32 is instantiated (got %d)", Cout);
   FB_CHECK_ARG(B > 0 && H > 0 && W > 0, "stem_conv: bad shape");
@@ -232,13 +234,25 @@ extern "C" int fb200_stem_conv3x3s2(const float* img, int B, int H, int W, const
   const int64_t total = (int64_t)B * Ho * Wo;
   cudaStream_t st = (cudaStream_t)stream;
   const float* m = mean3; const float* s = std3;  // HOST pointers (3 floats each)
-  if (out_dtype == FB200_F32)
-    stem_conv_kernel<float, 32><<<(unsigned)cdiv(total, 128), 128, 0, st>>>(img, B, H, W, w, scale, bias, m[0], m[1], m[2], s[0], s[1], s[2], act, (float*)out);
-  else if (out_dtype == FB200_F16)
-    stem_conv_kernel<__half, 32><<<(unsigned)cdiv(total, 128), 128, 0, st>>>(img, B, H, W, w, scale, bias, m[0], m[1], m[2], s[0], s[1], s[2], act, (__half*)out);
+  const unsigned grid = (unsigned)cdiv(total, 128);
+#define STEM_LAUNCH(T, U8) stem_conv_kernel<T, 32, U8><<<grid, 128, 0, st>>>(img, B, H, W, w, scale, bias, m[0], m[1], m[2], s[0], s[1], s[2], act, (T*)out)
+  if (out_dtype == FB200_F32) { if (u8) STEM_LAUNCH(float, true); else STEM_LAUNCH(float, false); }
+  else if (out_dtype == FB200_F16) { if (u8) STEM_LAUNCH(__half, true); else STEM_LAUNCH(__half, false); }
   else { set_error("stem_conv: bad dtype"); return FB200_ERR_INVALID; }
+#undef STEM_LAUNCH
   FB_CHECK_LAUNCH("stem_conv_kernel");
   return FB200_OK;
+}
+
+extern "C" int fb200_stem_conv3x3s2(const float* img, int B, int H, int W, const float* w, const float* scale,
+                                    const float* bias, const float* mean3, const float* std3, int act, void* out,
+                                    int out_dtype, int Cout, void* stream) {
+  return stem_launch(img, false, B, H, W, w, scale, bias, mean3, std3, act, out, out_dtype, Cout, stream);
+}
+extern "C" int fb200_stem_conv3x3s2_u8(const uint8_t* img_nhwc, int B, int H, int W, const float* w, const float* scale,
+                                       const float* bias, const float* mean3, const float* std3, int act, void* out,
+                                       int out_dtype, int Cout, void* stream) {
+  return stem_launch(img_nhwc, true, B, H, W, w, scale, bias, mean3, std3, act, out, out_dtype, Cout, stream);
 }
 
 extern "C" int fb200_conv2d(const void* x, int x_dtype, int B, int H, int W, int Cin, int x_pitch, const void* w, int KH,

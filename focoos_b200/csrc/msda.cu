@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(256) msda_kernel(const TV* __restrict__ value,
   const float locy = r.y + oy / (float)P * r.w * 0.5f;
   const TV* vb = value + (int64_t)b * S * v_pitch + h * 32 + lane;
   float acc = 0.f;
+#pragma unroll 4  // 16 independent gathers in flight per lane: the kernel is L2/HBM-latency bound
   for (int pt = 0; pt < LP; ++pt) {
     const int lvl = pt / P;
     const float lx = __shfl_sync(0xffffffffu, locx, pt), ly = __shfl_sync(0xffffffffu, locy, pt);

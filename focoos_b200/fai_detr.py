@@ -408,8 +408,12 @@ class DetrEngine:
     def forward(self, images: torch.Tensor, taps: Optional[dict] = None):
         """images [B,3,H,W] fp32 0..255 (H,W multiples of 32) -> (scores [B,Q,C] fp32, boxes xyxy [B,Q,4] fp32)."""
         cfg, dt, A = self.cfg, self.dt, self.algo
-        assert images.dim() == 4 and images.shape[1] == 3 and images.dtype == torch.float32
-        B, _, H, W = images.shape
+        if images.dtype == torch.uint8:  # [B,H,W,3] decoded images straight into the stem kernel
+            assert images.dim() == 4 and images.shape[3] == 3
+            B, H, W, _ = images.shape
+        else:
+            assert images.dim() == 4 and images.shape[1] == 3 and images.dtype == torch.float32
+            B, _, H, W = images.shape
         assert H % 32 == 0 and W % 32 == 0, "input size must be a multiple of 32"
         x = ops.stem_conv(images.contiguous(), self.stem_w, self.stem_s, self.stem_b, cfg.pixel_mean, cfg.pixel_std, ops.ACT_RELU, dt)
         x = self.stem3(self.stem2(x, algo=A), algo=A)
@@ -565,5 +569,5 @@ class FAIDetr(nn.Module):
             raise NotImplementedError("focoos_b200: the fine-tune path (losses/backward, SURVEY §8 a20-a21) is a later round")
         if ops._backend is None and not images.is_cuda:
             raise RuntimeError("focoos_b200.FAIDetr runs on CUDA (sm_100a) only — no CPU fallback; move the model and inputs to the GPU")
-        scores, boxes = self.engine().forward(images.to(torch.float32), taps)
+        scores, boxes = self.engine().forward(images if images.dtype == torch.uint8 else images.to(torch.float32), taps)
         return DETRModelOutput(boxes=boxes, logits=scores, loss=None)

@@ -63,7 +63,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = (
-    "fb200_last_error", "fb200_version", "fb200_device_supports_tcgen05", "fb200_stem_conv3x3s2", "fb200_conv2d",
+    "fb200_last_error", "fb200_version", "fb200_device_supports_tcgen05", "fb200_stem_conv3x3s2", "fb200_stem_conv3x3s2_u8", "fb200_conv2d",
     "fb200_maxpool3x3s2", "fb200_avgpool2x2_ceil", "fb200_resize_bilinear", "fb200_add", "fb200_layernorm",
     "fb200_attention", "fb200_msda", "fb200_row_select", "fb200_rowmax", "fb200_topk", "fb200_gather_rows",
     "fb200_box_op", "fb200_detr_postprocess",
@@ -142,10 +142,11 @@ class CudaBackend:
 
     def stem_conv(self, img, w, scale, bias, mean, std, act, out):
         self._cuda(img, w, out)
-        B, _, H, W = img.shape
+        u8 = img.dtype == torch.uint8
+        B, H, W = (img.shape[0], img.shape[1], img.shape[2]) if u8 else (img.shape[0], img.shape[2], img.shape[3])
         m = (ctypes.c_float * 3)(*mean)
         s = (ctypes.c_float * 3)(*std)
-        self._call("fb200_stem_conv3x3s2", _p(img), B, H, W, _p(w), _p(scale), _p(bias), m, s, act, _p(out), _dt(out), out.shape[-1], _stream())
+        self._call("fb200_stem_conv3x3s2_u8" if u8 else "fb200_stem_conv3x3s2", _p(img), B, H, W, _p(w), _p(scale), _p(bias), m, s, act, _p(out), _dt(out), out.shape[-1], _stream())
 
     def conv2d(self, x, w, scale, bias, stride, pad, act, residual, out, algo):
         self._cuda(x, w, out)
@@ -248,8 +249,13 @@ def supports_tcgen05() -> bool:
 # ------------------------------------------------------------------------------------------------
 def stem_conv(img: torch.Tensor, w, scale, bias, mean: Sequence[float], std: Sequence[float], act=ACT_RELU, out_dtype=torch.float32):
     """[B,3,H,W] fp32 NCHW 0..255 -> normalise -> conv3x3/s2 + BN + act -> NHWC [B,H/2,W/2,32]."""
-    assert img.dtype == torch.float32 and img.dim() == 4 and img.shape[1] == 3 and img.is_contiguous()
-    B, _, H, W = img.shape
+    assert img.dim() == 4 and img.is_contiguous()
+    if img.dtype == torch.uint8:  # decoded images as they come: [B,H,W,3] uint8
+        assert img.shape[3] == 3
+        B, H, W, _ = img.shape
+    else:
+        assert img.dtype == torch.float32 and img.shape[1] == 3
+        B, _, H, W = img.shape
     out = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, w.shape[0]), dtype=out_dtype, device=img.device)
     _be().stem_conv(img, w, scale, bias, [float(v) for v in mean], [float(v) for v in std], act, out)
     return out

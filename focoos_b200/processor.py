@@ -69,7 +69,9 @@ class DETRProcessor:
             if target_size is not None and tuple(x.shape[1:3]) != tuple(target_size):
                 x4 = torch.zeros((*x.shape[:3], 4), dtype=dtype, device=x.device)
                 x4[..., :3] = x
-                x = ops.resize_bilinear(x4, target_size)[..., :3]
+                x = ops.resize_bilinear(x4, target_size)[..., :3]  # float from here on
+            if x.dtype == torch.uint8:
+                return x.contiguous()  # FAIDetr's stem kernel reads uint8 NHWC directly (no float CHW copy)
             return x.permute(0, 3, 1, 2).to(dtype).contiguous()
         if not isinstance(inputs, (list, tuple)):
             inputs = [inputs]

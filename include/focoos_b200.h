@@ -48,6 +48,11 @@ int fb200_device_supports_tcgen05(void);
 int fb200_stem_conv3x3s2(const float* img, int B, int H, int W, const float* w, const float* scale, const float* bias,
                          const float* mean3_host, const float* std3_host, int act, void* out, int out_dtype, int Cout, void* stream);
 
+/* Same, reading the decoded image directly: img_nhwc [B,H,W,3] uint8 RGB (fuses the uint8->float, HWC->CHW conversion of
+ * Processor.get_torch_batch, processor/base_processor.py:262-287, into the first conv). */
+int fb200_stem_conv3x3s2_u8(const uint8_t* img_nhwc, int B, int H, int W, const float* w, const float* scale, const float* bias,
+                            const float* mean3_host, const float* std3_host, int act, void* out, int out_dtype, int Cout, void* stream);
+
 /* ---- a2,a3,a5,a7: conv (+ folded BN scale/bias, + residual, + activation), implicit GEMM -------
  * Replaces ConvNormLayer.forward (nn/layers/conv.py:78-98), BottleNeck residual add + ReLU
  * (nn/backbone/resnet.py:106-121), RepVggBlock (models/fai_detr/modelling.py:39-45, re-parameterised

@@ -26,6 +26,8 @@ def _f(t):
 
 class RefBackend:
     def stem_conv(self, img, w, scale, bias, mean, std, act, out):
+        if img.dtype == torch.uint8:
+            img = img.permute(0, 3, 1, 2).float()
         x = (img - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)
         y = F.conv2d(x, w.permute(0, 3, 1, 2).float(), None, 2, 1)
         if scale is not None:

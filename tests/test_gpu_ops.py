@@ -212,3 +212,14 @@ def test_detr_postprocess_vs_ref():
     outs = ops.detr_postprocess(scores.to(DEV), boxes.to(DEV), sizes.to(DEV), K, 0.4)
     for a, b, name in zip(outs, outs_ref, ("scores", "labels", "boxes", "query", "count")):
         assert torch.equal(a.cpu(), b), name
+
+
+def test_stem_conv_u8_nhwc_matches_float_path():
+    g = torch.Generator().manual_seed(77)
+    u8 = torch.randint(0, 256, (2, 64, 96, 3), generator=g, dtype=torch.uint8)
+    w = rnd((32, 3, 3, 3), torch.float32, 1, 0.3)
+    sc, bi = torch.rand(32) + 0.5, rnd((32,), torch.float32, 2, 0.1)
+    mean, std = [123.675, 116.28, 103.53], [58.395, 57.12, 57.375]
+    a = ops.stem_conv(u8.to(DEV), w.to(DEV), sc.to(DEV), bi.to(DEV), mean, std, 1, torch.float32)
+    b = ops.stem_conv(u8.permute(0, 3, 1, 2).float().contiguous().to(DEV), w.to(DEV), sc.to(DEV), bi.to(DEV), mean, std, 1, torch.float32)
+    assert torch.equal(a, b)
