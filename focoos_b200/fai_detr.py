@@ -306,8 +306,8 @@ class DetrEngine:
             i += 1
         return both, reps
 
-    def _pack(self, sd):
-        bb = "pixel_decoder.backbone"
+    def _pack_backbone(self, sd, bb="pixel_decoder.backbone"):
+        """ResNet-vd (nn/backbone/resnet.py:164): stem + bottleneck stages with folded BN (shared by every model family)."""
         w = sd[bb + ".conv1.conv1_1.conv.weight"].float()
         s, b = _bn_fold(sd, bb + ".conv1.conv1_1.norm")
         self.stem_w, self.stem_s, self.stem_b = self._f32(w.permute(0, 2, 3, 1)), self._f32(s), self._f32(b)
@@ -325,6 +325,27 @@ class DetrEngine:
                     blk["short"] = self._cnl(sd, p + (".short.conv" if stride == 2 else ".short"), None)
                 blocks.append(blk)
             self.stages.append(blocks)
+
+    def _run_backbone(self, images):
+        """-> [res2, res3, res4, res5] NHWC (nn/backbone/resnet.py:252-266)."""
+        cfg, dt, A = self.cfg, self.dt, self.algo
+        x = ops.stem_conv(images.contiguous(), self.stem_w, self.stem_s, self.stem_b, cfg.pixel_mean, cfg.pixel_std, ops.ACT_RELU, dt)
+        x = self.stem3(self.stem2(x, algo=A), algo=A)
+        x = ops.maxpool3x3s2(x)
+        feats = []
+        for blocks in self.stages:
+            for blk in blocks:
+                y = blk["b"](blk["a"](x, algo=A), algo=A)
+                if blk["short"] is None:
+                    short = x
+                else:
+                    short = blk["short"](ops.avgpool2x2(x) if blk["stride"] == 2 else x, algo=A)
+                x = blk["c"](y, residual=short, algo=A)
+            feats.append(x)
+        return feats
+
+    def _pack(self, sd):
+        self._pack_backbone(sd)
         pd = "pixel_decoder"
         self.enc_in = [self._seq_conv_bn(sd, f"{pd}.input_proj.{i}.0", f"{pd}.input_proj.{i}.1") for i in range(3)]
         e = f"{pd}.encoder.0.layers.0"
@@ -415,19 +436,7 @@ class DetrEngine:
             assert images.dim() == 4 and images.shape[1] == 3 and images.dtype == torch.float32
             B, _, H, W = images.shape
         assert H % 32 == 0 and W % 32 == 0, "input size must be a multiple of 32"
-        x = ops.stem_conv(images.contiguous(), self.stem_w, self.stem_s, self.stem_b, cfg.pixel_mean, cfg.pixel_std, ops.ACT_RELU, dt)
-        x = self.stem3(self.stem2(x, algo=A), algo=A)
-        x = ops.maxpool3x3s2(x)
-        feats = []
-        for blocks in self.stages:
-            for blk in blocks:
-                y = blk["b"](blk["a"](x, algo=A), algo=A)
-                if blk["short"] is None:
-                    short = x
-                else:
-                    short = blk["short"](ops.avgpool2x2(x) if blk["stride"] == 2 else x, algo=A)
-                x = blk["c"](y, residual=short, algo=A)
-            feats.append(x)
+        feats = self._run_backbone(images)
         res3, res4, res5 = feats[1], feats[2], feats[3]
         h32, w32 = res5.shape[1], res5.shape[2]
         K = self._constants(h32, w32)

@@ -462,3 +462,124 @@ try:  # registration itself needs no GPU and no compiled library
     _register_torch_ops()
 except Exception:  # pragma: no cover - e.g. double import under a different module name
     pass
+
+
+# ------------------------------------------------------------------------------------------------
+# MaskFormer-family operators
+# ------------------------------------------------------------------------------------------------
+EXPORTED_SYMBOLS = EXPORTED_SYMBOLS + (
+    "fb200_upsample_nearest_add", "fb200_attn_mask_build", "fb200_attention_masked", "fb200_softmax_drop_last",
+    "fb200_mask_sigmoid_upsample", "fb200_mask_stats", "fb200_mask_resize_bbox",
+)
+
+
+def _cb_upsample_nearest_add(self, y, cur, out):
+    self._cuda(y, cur, out)
+    B, h, w, C = y.shape
+    self._call("fb200_upsample_nearest_add", _p(y), _p(cur), _p(out), _dt(y), B, h, w, cur.shape[1], cur.shape[2], C, _stream())
+
+
+def _cb_attn_mask_build(self, x, Q, mask, allowed):
+    self._cuda(x, mask, allowed)
+    B, h, w, Qp = x.shape
+    self._call("fb200_attn_mask_build", _p(x), _dt(x), B, h * w, Qp, Q, _p(mask), mask.shape[2], _p(allowed), _stream())
+
+
+def _cb_attention_masked(self, q, k, v, mask, allowed, out, heads, scale):
+    self._cuda(q, k, v, mask, allowed, out)
+    B, Lq, C = q.shape
+    self._call("fb200_attention_masked", _p(q), _pitch(q), _p(k), _pitch(k), _p(v), _pitch(v), _p(mask), mask.shape[2], _p(allowed), _p(out), _pitch(out),
+               _dt(q), B, Lq, k.shape[1], heads, C // heads, ctypes.c_float(scale), _stream())
+
+
+def _cb_softmax_drop_last(self, x, out):
+    self._cuda(x, out)
+    N = x.shape[-1]
+    self._call("fb200_softmax_drop_last", _p(x), ctypes.c_int64(x.numel() // N), N, _pitch(x), _p(out), _stream())
+
+
+def _cb_mask_sigmoid_upsample(self, x, Q, out):
+    self._cuda(x, out)
+    B, h, w, Qp = x.shape
+    self._call("fb200_mask_sigmoid_upsample", _p(x), _dt(x), B, h, w, Qp, Q, _p(out), out.shape[2], out.shape[3], _stream())
+
+
+def _cb_mask_stats(self, masks, thr, count, psum):
+    self._cuda(masks, count, psum)
+    B, Q, H, W = masks.shape
+    self._call("fb200_mask_stats", _p(masks), ctypes.c_int64(B * Q), ctypes.c_int64(H * W), ctypes.c_float(thr), _p(count), _p(psum), _stream())
+
+
+def _cb_mask_resize_bbox(self, masks, bq, thr, out_masks, out_bbox):
+    self._cuda(masks, bq, out_masks, out_bbox)
+    B, Q, H, W = masks.shape
+    self._call("fb200_mask_resize_bbox", _p(masks), Q, H, W, _p(bq), bq.shape[0], ctypes.c_float(thr), _p(out_masks), out_masks.shape[1], out_masks.shape[2], _p(out_bbox), _stream())
+
+
+for _n, _f in (("upsample_nearest_add", _cb_upsample_nearest_add), ("attn_mask_build", _cb_attn_mask_build), ("attention_masked", _cb_attention_masked),
+               ("softmax_drop_last", _cb_softmax_drop_last), ("mask_sigmoid_upsample", _cb_mask_sigmoid_upsample), ("mask_stats", _cb_mask_stats),
+               ("mask_resize_bbox", _cb_mask_resize_bbox)):
+    setattr(CudaBackend, _n, _f)
+
+
+def upsample_nearest_add(y, cur):
+    """cur + F.interpolate(y, size=cur.shape, mode="nearest")  (fai_mf/modelling.py:364), NHWC."""
+    out = torch.empty_like(cur)
+    _be().upsample_nearest_add(y.contiguous(), cur.contiguous(), out)
+    return out
+
+
+def attn_mask_build(mask_logits_nhwc, num_queries: int):
+    """[B,h,w,Qp] mask logits at the target level size -> (uint8 mask [B,Q,LkP] with 1 = NOT allowed (logit < 0), int32 allowed-key
+    count [B,Q]).  A row whose count is 0 attends everywhere (fai_mf/modelling.py:96-105,510-513)."""
+    B, h, w, _ = mask_logits_nhwc.shape
+    LkP = (h * w + 3) // 4 * 4
+    mask = torch.empty((B, num_queries, LkP), dtype=torch.uint8, device=mask_logits_nhwc.device)
+    allowed = torch.zeros((B, num_queries), dtype=torch.int32, device=mask_logits_nhwc.device)
+    _be().attn_mask_build(mask_logits_nhwc.contiguous(), num_queries, mask, allowed)
+    return mask, allowed
+
+
+def attention_masked(q, k, v, mask, allowed, heads: int, scale: float):
+    """masked cross-attention: q [B,Lq,C], k/v [B,Lk,C]; mask/allowed from attn_mask_build (shared by all heads)."""
+    B, Lq, C = q.shape
+    out = torch.empty((B, Lq, C), dtype=q.dtype, device=q.device)
+    _be().attention_masked(q, k, v, mask, allowed, out, heads, scale)
+    return out
+
+
+def softmax_drop_last(x):
+    """F.softmax(x, -1)[..., :-1] on fp32 rows (fai_mf/modelling.py:618)."""
+    assert x.dtype == torch.float32
+    out = torch.empty((*x.shape[:-1], x.shape[-1] - 1), dtype=torch.float32, device=x.device)
+    _be().softmax_drop_last(x, out)
+    return out
+
+
+def mask_sigmoid_upsample(mask_logits_nhwc, num_queries: int, size):
+    """[B,h,w,Qp] logits -> sigmoid -> bilinear (align_corners=False) to `size` -> [B,Q,H,W] fp32 probabilities
+    (fai_mf/modelling.py:619,722-723: sigmoid at low resolution THEN upsample)."""
+    B = mask_logits_nhwc.shape[0]
+    out = torch.empty((B, num_queries, size[0], size[1]), dtype=torch.float32, device=mask_logits_nhwc.device)
+    _be().mask_sigmoid_upsample(mask_logits_nhwc.contiguous(), num_queries, out)
+    return out
+
+
+def mask_stats(masks, thr: float):
+    """per (b,q): number of pixels with prob >= thr and the sum of those probabilities (fai_mf/processor.py:222-257)."""
+    B, Q = masks.shape[:2]
+    count = torch.empty((B, Q), dtype=torch.int32, device=masks.device)
+    psum = torch.empty((B, Q), dtype=torch.float32, device=masks.device)
+    _be().mask_stats(masks.contiguous(), thr, count, psum)
+    return count, psum
+
+
+def mask_resize_bbox(masks, bq_i32, thr: float, size):
+    """kept (b,q) pairs -> binary masks (prob >= thr) bilinearly resized to `size` and re-binarised (> 0), plus their xyxy boxes
+    (fai_mf/processor.py:275-283, utils/vision.py:344-370)."""
+    n = bq_i32.shape[0]
+    om = torch.empty((n, size[0], size[1]), dtype=torch.uint8, device=masks.device)
+    ob = torch.empty((n, 4), dtype=torch.int32, device=masks.device)
+    if n:
+        _be().mask_resize_bbox(masks.contiguous(), bq_i32.contiguous(), thr, om, ob)
+    return om, ob

@@ -138,3 +138,77 @@ class DETRProcessor:
         if isinstance(logits, np.ndarray):
             logits = torch.from_numpy(logits)
         return self.postprocess(DETRModelOutput(boxes=boxes, logits=logits, loss=None), inputs, class_names, 300 if top_k is None else top_k, threshold)
+
+
+# ==================================================================================================
+# MaskFormerProcessor — mirror of `focoos/models/fai_mf/processor.py`, instance mode
+# ==================================================================================================
+def binary_mask_to_base64(mask: np.ndarray) -> str:
+    """utils/vision.py:270-293: PNG (0/255, single channel) -> base64.  The reference encodes with OpenCV; PIL yields the same image."""
+    import base64
+    import io
+
+    from PIL import Image
+
+    buf = io.BytesIO()
+    Image.fromarray((mask.astype(np.uint8) * 255), mode="L").save(buf, format="PNG")
+    return base64.b64encode(buf.getvalue()).decode("utf-8")
+
+
+class MaskFormerProcessor(DETRProcessor):
+    """preprocess as the base Processor; postprocess = the reference's tensor pipeline as GPU reductions + one compaction:
+    per (image, query): pixel count and probability mass of `prob >= mask_threshold` (ONE pass over the [B,Q,H,W] tensor),
+    class score x mask score, threshold, then only the KEPT masks are binarised / resized to the original image size and
+    boxed on the device and copied to the host for PNG encoding.  Works for any batch size (the reference raises IndexError
+    for B >= 2): the batched result equals the concatenation of the reference's per-image results."""
+
+    def __init__(self, config, image_size=None):
+        self.config = config
+        self.image_size = image_size
+        self.top_k, self.threshold = config.top_k, config.threshold
+        self.mask_threshold, self.use_mask_score, self.predict_all_pixels = config.mask_threshold, config.use_mask_score, config.predict_all_pixels
+        self.training = False
+
+    def postprocess_tensors(self, output, threshold=None, use_mask_score=None):
+        """-> list over images of (query idx [n], scores [n], labels [n]) on the host, plus the device masks tensor."""
+        threshold = threshold or self.threshold
+        use_mask_score = use_mask_score or self.use_mask_score
+        if self.predict_all_pixels:
+            raise NotImplementedError("semantic (predict_all_pixels) post-processing lands with the BiSeNetFormer family")
+        count, psum = ops.mask_stats(output.masks, float(self.mask_threshold))
+        host = torch.cat([output.logits.reshape(output.logits.shape[0], -1), count.float(), psum], dim=1).cpu().numpy()  # one D2H
+        B, Q, K = output.logits.shape
+        res = []
+        for b in range(B):
+            logits = host[b, : Q * K].reshape(Q, K)
+            cnt, ps = host[b, Q * K: Q * K + Q], host[b, Q * K + Q:]
+            scores, labels = logits.max(-1), logits.argmax(-1)
+            nz = np.nonzero(cnt > 1)[0]
+            s = scores[nz]
+            if use_mask_score:  # (sum 1e-3*m*p) / (sum 1e-3*m + 1e-5), fai_mf/processor.py:249-257
+                s = s * ((np.float32(1e-3) * ps[nz]) / (np.float32(1e-3) * cnt[nz] + np.float32(1e-5)))
+            keep = np.nonzero(s > threshold)[0] if threshold > 0 else np.arange(len(s))
+            res.append((nz[keep].astype(np.int32), s[keep].astype(np.float32), labels[nz][keep].astype(np.int32)))
+        return res
+
+    def postprocess(self, output, inputs, class_names=(), top_k=None, threshold=None, use_mask_score=None, predict_all_pixels=None):
+        image_sizes = get_image_sizes(inputs)
+        B = output.logits.shape[0]
+        assert len(image_sizes) == B, f"Expected image sizes {len(image_sizes)} to match batch size {B}"
+        kept = self.postprocess_tensors(output, threshold, use_mask_score)
+        results = []
+        for b, (q, s, l) in enumerate(kept):
+            if len(q) == 0:
+                results.append(FocoosDetections(detections=[]))
+                continue
+            bq = torch.tensor(np.stack([np.full_like(q, b), q], 1), dtype=torch.int32).to(output.masks.device)
+            m, box = ops.mask_resize_bbox(output.masks, bq, float(self.mask_threshold), image_sizes[b])
+            m, box = m.cpu().numpy().astype(bool), box.cpu().numpy()
+            dets = []
+            for i in range(len(q)):
+                x1, y1, x2, y2 = (int(v) for v in box[i])
+                crop = m[i][y1:min(y2, m[i].shape[0]), x1:min(x2, m[i].shape[1])]  # trim_mask (utils/vision.py:264-267)
+                dets.append(FocoosDet(bbox=[x1, y1, x2, y2], conf=float(s[i]), cls_id=int(l[i]), mask=binary_mask_to_base64(crop),
+                                      label=class_names[int(l[i])] if class_names else None))
+            results.append(FocoosDetections(detections=dets))
+        return results

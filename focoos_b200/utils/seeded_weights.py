@@ -69,6 +69,10 @@ def seeded_tensor(name: str, shape: Sequence[int], dtype: torch.dtype, keys: Map
             std *= 0.5
         if "score_classifier" in name:
             std *= 2.5  # wide logit spread: the top-300 scores straddle the 0.5 threshold
+        if name.endswith("forward_prediction_heads.classifier.weight"):
+            std *= 3.0  # peaky class softmax so that some queries clear the 0.5 score threshold (MaskFormer family)
+        if name.endswith("mask_classifier.layers.2.weight"):
+            std *= 0.03  # keep mask logits O(10): mask_embed . mask_features sums 256 products of O(1..30) features
         if "bbox_classifier" in name and name.endswith("layers.2.weight"):
             std *= 0.5
         if name.endswith("query_feat.weight") or name.endswith("query_embed.weight"):

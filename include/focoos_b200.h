@@ -130,6 +130,41 @@ int fb200_detr_postprocess(const float* scores, const float* boxes, const int* s
                            float threshold, float* out_scores, int* out_labels, int* out_boxes, int* out_query,
                            int* out_count, void* stream);
 
+/* ======== MaskFormer family (focoos/models/fai_mf/{modelling,processor}.py) ======================== */
+
+/* out = cur + F.interpolate(y, size=(H,W), mode="nearest")   TransformerFPN top-down path (fai_mf/modelling.py:364).
+ * y [B,h,w,C], cur/out [B,H,W,C], NHWC contiguous. */
+int fb200_upsample_nearest_add(const void* y, const void* cur, void* out, int dtype, int B, int h, int w, int H, int W, int C, void* stream);
+
+/* Attention mask of the masked decoder (fai_mf/modelling.py:96-105,510-513): x [B,Lk,Qp] mask logits already resized to the
+ * level, mask[b,q,k] (uint8, row pitch LkP) = x[b,k,q] < 0 ("not allowed"); allowed[b,q] (int32, ZERO-INITIALISED by the caller)
+ * += number of allowed keys — a row with 0 allowed keys attends everywhere. */
+int fb200_attn_mask_build(const void* x, int dtype, int B, int Lk, int Qp, int Q, uint8_t* mask, int LkP, int* allowed, void* stream);
+
+/* softmax(q k^T * scale + mask) v per (batch, head), keys streamed (Lk up to H/8*W/8), head_dim 32; mask/allowed as above and shared
+ * by all heads (the reference replicates a [B*heads,Q,Lk] bool tensor, :513); mask == NULL -> unmasked.
+ * nn.MultiheadAttention inside CrossAttentionLayer (nn/layers/transformer.py:206-238). */
+int fb200_attention_masked(const void* q, int q_pitch, const void* k, int k_pitch, const void* v, int v_pitch, const uint8_t* mask, int LkP,
+                           const int* allowed, void* out, int out_pitch, int dtype, int B, int Lq, int Lk, int heads, int head_dim, float scale,
+                           void* stream);
+
+/* out[r, 0..N-2] = softmax(x[r, 0..N-1])[..., :-1]  (drop the no-object class; fai_mf/modelling.py:618). fp32. */
+int fb200_softmax_drop_last(const float* x, int64_t rows, int N, int pitch, float* out, void* stream);
+
+/* MaskFormerHead sigmoid (fai_mf/modelling.py:619) + final F.interpolate(bilinear) to the input size (:722-723), fused:
+ * x [B,h,w,Qp] mask logits NHWC -> out [B,Q,H,W] fp32 probabilities. */
+int fb200_mask_sigmoid_upsample(const void* x, int dtype, int B, int h, int w, int Qp, int Q, float* out, int H, int W, void* stream);
+
+/* MaskFormerProcessor.postprocess reductions (fai_mf/processor.py:222-257): per plane of masks [planes, hw] fp32:
+ * count = #(p >= thr), psum = sum of those p. */
+int fb200_mask_stats(const float* masks, int64_t planes, int64_t hw, float thr, int* count, float* psum, void* stream);
+
+/* Kept masks -> original image size (fai_mf/processor.py:275-283): for pair i = (b,q) in bq [n,2]: (masks[b,q] >= thr) as float,
+ * bilinear resize to (Ho,Wo), != 0 -> out [n,Ho,Wo] uint8; bbox [n,4] = (xmin,ymin,xmax,ymax) of the set pixels, zeros if empty
+ * (masks_to_xyxy, utils/vision.py:344-370). */
+int fb200_mask_resize_bbox(const float* masks, int Q, int H, int W, const int* bq, int n, float thr, uint8_t* out, int Ho, int Wo, int* bbox,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

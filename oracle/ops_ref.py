@@ -144,3 +144,61 @@ class RefBackend:
             out_query[b] = q.to(torch.int32)
             out_boxes[b] = bx.round().to(torch.int32)
             out_count[b] = int((v > thr).sum())
+
+
+# ---- MaskFormer-family operators (same signatures as the CudaBackend extensions in focoos_b200/ops.py) -------------------
+def _ref_upsample_nearest_add(self, y, cur, out):
+    up = F.interpolate(y.float().permute(0, 3, 1, 2), size=(cur.shape[1], cur.shape[2]), mode="nearest").permute(0, 2, 3, 1)
+    out.copy_((cur.float() + up).to(out.dtype))
+
+
+def _ref_attn_mask_build(self, x, Q, mask, allowed):
+    B, h, w, Qp = x.shape
+    m = (x.float().reshape(B, h * w, Qp)[:, :, :Q] < 0).permute(0, 2, 1)  # [B,Q,hw], True = not allowed
+    mask.zero_()
+    mask[:, :, : h * w] = m.to(torch.uint8)
+    allowed.copy_((~m).sum(-1).to(torch.int32))
+
+
+def _ref_attention_masked(self, q, k, v, mask, allowed, out, heads, scale):
+    B, Lq, C = q.shape
+    Lk = k.shape[1]
+    hd = C // heads
+    qh = q.float().reshape(B, Lq, heads, hd).transpose(1, 2)
+    kh = k.float().reshape(B, Lk, heads, hd).transpose(1, 2)
+    vh = v.float().reshape(B, Lk, heads, hd).transpose(1, 2)
+    m = mask[:, :, :Lk].bool() & (allowed > 0).unsqueeze(-1)
+    s = (qh @ kh.transpose(-1, -2)) * scale
+    s = s.masked_fill(m.unsqueeze(1), float("-inf"))
+    out.copy_((torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(B, Lq, C).to(out.dtype))
+
+
+def _ref_softmax_drop_last(self, x, out):
+    out.copy_(F.softmax(x.float(), dim=-1)[..., :-1])
+
+
+def _ref_mask_sigmoid_upsample(self, x, Q, out):
+    p = torch.sigmoid(x.float()[..., :Q]).permute(0, 3, 1, 2)
+    out.copy_(F.interpolate(p, size=(out.shape[2], out.shape[3]), mode="bilinear", align_corners=False))
+
+
+def _ref_mask_stats(self, masks, thr, count, psum):
+    b = masks >= thr
+    count.copy_(b.sum(dim=(-2, -1)).to(torch.int32))
+    psum.copy_((masks * b).sum(dim=(-2, -1)))
+
+
+def _ref_mask_resize_bbox(self, masks, bq, thr, out_masks, out_bbox):
+    for i in range(bq.shape[0]):
+        b, q = int(bq[i, 0]), int(bq[i, 1])
+        m = (masks[b, q] >= thr).float()[None, None]
+        r = F.interpolate(m, size=(out_masks.shape[1], out_masks.shape[2]), mode="bilinear", align_corners=False)[0, 0].bool()
+        out_masks[i] = r.to(torch.uint8)
+        rows, cols = r.any(1).nonzero(), r.any(0).nonzero()
+        out_bbox[i] = torch.tensor([int(cols[0]), int(rows[0]), int(cols[-1]), int(rows[-1])] if len(rows) else [0, 0, 0, 0], dtype=torch.int32)
+
+
+for _n, _f in (("upsample_nearest_add", _ref_upsample_nearest_add), ("attn_mask_build", _ref_attn_mask_build), ("attention_masked", _ref_attention_masked),
+               ("softmax_drop_last", _ref_softmax_drop_last), ("mask_sigmoid_upsample", _ref_mask_sigmoid_upsample), ("mask_stats", _ref_mask_stats),
+               ("mask_resize_bbox", _ref_mask_resize_bbox)):
+    setattr(RefBackend, _n, _f)

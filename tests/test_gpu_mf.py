@@ -1,0 +1,146 @@
+"""-m gpu: MaskFormer-family kernels vs their CPU references, and FAIMaskFormer end-to-end vs the golden fixtures produced by
+the unmodified reference (fp32 mode held to the parity bars; fp16 measured and reported)."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from focoos_b200 import ops
+from focoos_b200.fai_mf import FAIMaskFormer, MaskFormerConfig
+from focoos_b200.processor import MaskFormerProcessor
+from focoos_b200.utils.seeded_weights import seeded_state_dict
+from oracle.gen_golden import synth_images
+from oracle.ops_ref import RefBackend
+from tests.parity_utils import load_golden, manifest_template
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+REF = RefBackend()
+DEV = "cuda"
+
+
+def rnd(shape, dtype, seed, s=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * s).to(dtype)
+
+
+def close(a, b, tol, what):
+    a, b = a.detach().float().cpu(), b.detach().float()
+    err, scale = float((a - b).abs().max()), max(1.0, float(b.abs().max()))
+    assert err <= tol * scale, f"{what}: max|d|={err:.3e} scale={scale:.2e}"
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_upsample_nearest_add(dtype):
+    for (h, w, H, W) in ((10, 13, 20, 26), (5, 7, 13, 15)):
+        y, cur = rnd((2, h, w, 64), dtype, 1), rnd((2, H, W, 64), dtype, 2)
+        ref = torch.empty_like(cur)
+        REF.upsample_nearest_add(y, cur, ref)
+        close(ops.upsample_nearest_add(y.to(DEV), cur.to(DEV)), ref, 2e-3 if dtype == torch.float16 else 1e-6, "nearest_add")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("hw", [(10, 13), (25, 25), (20, 26)])
+def test_mask_build_and_masked_attention(dtype, hw):
+    B, Q, Qp, heads = 2, 100, 104, 8
+    h, w = hw
+    Lk = h * w
+    x = rnd((B, h, w, Qp), dtype, 3)
+    x[0, :, :, 5] = 1.0    # query 5 of image 0: everything allowed
+    x[1, :, :, 7] = -1.0   # query 7 of image 1: everything masked -> must attend everywhere
+    LkP = (Lk + 3) // 4 * 4
+    rm, ra = torch.empty((B, Q, LkP), dtype=torch.uint8), torch.zeros((B, Q), dtype=torch.int32)
+    REF.attn_mask_build(x, Q, rm, ra)
+    m, a = ops.attn_mask_build(x.to(DEV), Q)
+    assert torch.equal(m.cpu()[:, :, :Lk], rm[:, :, :Lk]) and torch.equal(a.cpu(), ra)
+    assert int(ra[1, 7]) == 0 and int(ra[0, 5]) == Lk
+    q, k, v = rnd((B, Q, 256), dtype, 4), rnd((B, Lk, 256), dtype, 5), rnd((B, Lk, 256), dtype, 6)
+    ref = torch.empty((B, Q, 256), dtype=dtype)
+    REF.attention_masked(q, k, v, rm, ra, ref, heads, 1 / math.sqrt(32))
+    out = ops.attention_masked(q.to(DEV), k.to(DEV), v.to(DEV), m, a, heads, 1 / math.sqrt(32))
+    close(out, ref, 3e-3 if dtype == torch.float16 else 1e-4, f"masked attention {hw}")
+
+
+def test_softmax_drop_last():
+    x = rnd((3, 100, 81), torch.float32, 7, 3.0)
+    ref = torch.empty((3, 100, 80))
+    REF.softmax_drop_last(x, ref)
+    close(ops.softmax_drop_last(x.to(DEV)), ref, 1e-6, "softmax_drop_last")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_mask_sigmoid_upsample(dtype):
+    for (h, w, H, W) in ((80, 104, 320, 416), (20, 26, 160, 208), (25, 25, 100, 100)):
+        x = rnd((2, h, w, 104), dtype, 8, 4.0)
+        ref = torch.empty((2, 100, H, W))
+        REF.mask_sigmoid_upsample(x, 100, ref)
+        close(ops.mask_sigmoid_upsample(x.to(DEV), 100, (H, W)), ref, 2e-6, f"mask_sigmoid_upsample {h}x{w}->{H}x{W}")
+
+
+def test_mask_stats_and_resize_bbox():
+    g = torch.Generator().manual_seed(9)
+    masks = torch.rand((2, 10, 64, 96), generator=g)
+    masks[0, 3] = 0.0  # empty mask
+    rc, rs = torch.empty((2, 10), dtype=torch.int32), torch.empty((2, 10))
+    REF.mask_stats(masks, 0.5, rc, rs)
+    c, s = ops.mask_stats(masks.to(DEV), 0.5)
+    assert torch.equal(c.cpu(), rc)
+    close(s, rs, 1e-5, "mask_stats sum")
+    blob = torch.zeros((2, 10, 64, 96))
+    blob[1, 2, 10:20, 30:50] = 0.9
+    blob[0, 1, 5, 7] = 0.7
+    bq = torch.tensor([[1, 2], [0, 1], [0, 3]], dtype=torch.int32)
+    for size in ((64, 96), (100, 150), (37, 41)):
+        rm, rb = torch.empty((3, *size), dtype=torch.uint8), torch.empty((3, 4), dtype=torch.int32)
+        REF.mask_resize_bbox(blob, bq, 0.5, rm, rb)
+        m, b = ops.mask_resize_bbox(blob.to(DEV), bq.to(DEV), 0.5, size)
+        assert torch.equal(m.cpu(), rm), size
+        assert torch.equal(b.cpu(), rb), (size, b.cpu(), rb)
+
+
+def _report(key, val):
+    path = "gpurun_out/parity_report_mf.json"
+    os.makedirs("gpurun_out", exist_ok=True)
+    d = json.load(open(path)) if os.path.exists(path) else {}
+    d[key] = val
+    json.dump(d, open(path, "w"), indent=1)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_mf_end_to_end_vs_reference_golden(precision):
+    g = load_golden("mf_l_coco_ins_b2_320x416")
+    sd = seeded_state_dict(manifest_template("fai_mf_l_coco_ins"), 0)
+    m = FAIMaskFormer(MaskFormerConfig(), precision=precision)
+    m.load_state_dict(sd, strict=True)
+    m.cuda()
+    imgs = synth_images(3, [tuple(s) for s in g["sizes"].tolist()])
+    x = torch.stack([torch.from_numpy(im).permute(2, 0, 1).float() for im in imgs]).cuda()
+    taps = {}
+    out = m(x, taps=taps)
+    torch.cuda.synchronize()
+    scale = float(g["pred_masks_stat"][2])
+    pm = taps["pred_masks"][..., :100].permute(0, 3, 1, 2).float().cpu().numpy()
+    e_logit = float(np.abs(pm[:, ::4] - g["pred_masks_q4"]).max())
+    e_cls = float(np.abs(out.logits.cpu().numpy() - g["logits"]).max())
+    e_mask = float(np.abs(out.masks[:, ::10, ::4, ::4].cpu().numpy() - g["masks_q10_s4"]).max())
+    proc = MaskFormerProcessor(m.config)
+    dets = proc.postprocess(out, imgs, threshold=float(g["threshold"]))
+    match = []
+    for i, d in enumerate(dets):
+        n = int(g["det_count"][i])
+        ref_set = set(zip(g["det_labels"][i, :n].tolist(), map(tuple, g["det_boxes"][i, :n].tolist())))
+        got = set((x.cls_id, tuple(x.bbox)) for x in d.detections)
+        match.append({"ref": n, "got": len(d), "exact_common": len(ref_set & got)})
+    _report(precision, {"mask_logits_max_abs": e_logit, "mask_logit_scale": scale, "class_prob_max_abs": e_cls, "mask_prob_max_abs": e_mask, "detections": match})
+    if precision == "fp32":
+        assert e_logit <= 1e-4 * scale and e_cls <= 1e-3 and e_mask <= 1e-3, (e_logit, e_cls, e_mask)
+        for i, d in enumerate(dets):
+            n = int(g["det_count"][i])
+            assert len(d) == n
+            assert [x.cls_id for x in d.detections] == g["det_labels"][i, :n].tolist()
+            assert [x.bbox for x in d.detections] == g["det_boxes"][i, :n].tolist()
+            assert np.abs(np.array([x.conf for x in d.detections]) - g["det_scores"][i, :n]).max() < 1e-4
+    else:
+        assert np.isfinite(e_logit) and e_cls < 0.1
