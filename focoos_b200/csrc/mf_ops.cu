@@ -275,6 +275,8 @@ __global__ void __launch_bounds__(256) mask_resize_bbox_kernel(const float* __re
   }
 }
 
+int attention_mma_stream(const __half* q, int q_pitch, const __half* k, int k_pitch, const __half* v, int v_pitch, const uint8_t* mask, int LkP,
+                         const int* allowed, __half* out, int out_pitch, int B, int Lq, int Lk, int heads, float scale, cudaStream_t st);
 }  // namespace fb200
 using namespace fb200;
 
@@ -300,6 +302,10 @@ extern "C" int fb200_attention_masked(const void* q, int q_pitch, const void* k,
   FB_CHECK_ARG(q && k && v && out && head_dim == 32, "attention_masked: null pointer or head_dim != 32");
   FB_CHECK_ARG((mask == nullptr) == (allowed == nullptr), "attention_masked: mask and allowed go together");
   FB_CHECK_ARG(k_pitch % 4 == 0 && v_pitch % 4 == 0, "attention_masked: k/v pitches must be multiples of 4");
+  if (dtype == FB200_F16 && q_pitch % 8 == 0 && k_pitch % 8 == 0 && v_pitch % 8 == 0 && out_pitch % 2 == 0 && (mask == nullptr || LkP % 4 == 0) &&
+      (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) & 15) == 0 && ((uintptr_t)out & 3) == 0)  // tensor-core path (norm_attn.cu)
+    return attention_mma_stream((const __half*)q, q_pitch, (const __half*)k, k_pitch, (const __half*)v, v_pitch, mask, LkP, allowed, (__half*)out, out_pitch,
+                                B, Lq, Lk, heads, scale, (cudaStream_t)stream);
   dim3 grid((unsigned)(B * heads), (unsigned)cdiv(Lq, MA_QPB));
   FB_DISPATCH_DTYPE(dtype, T, (attention_masked_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)q, q_pitch, (const T*)k, k_pitch, (const T*)v, v_pitch, mask, LkP, allowed, (T*)out, out_pitch, Lq, Lk, heads, scale)));
   FB_CHECK_LAUNCH("attention_masked");

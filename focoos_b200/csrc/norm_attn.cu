@@ -302,3 +302,152 @@ int attention_mma(const __half* q, int q_pitch, const __half* k, int k_pitch, co
 }
 
 }  // namespace fb200
+
+// ------------------------------------------------------------------------------------------------
+// Streaming variant for long key sequences (MaskFormer masked cross-attention: 100 queries x up to (H/8 * W/8) keys):
+// 64-key K/V blocks are double-buffered through shared memory; an optional per-(batch, query, key) uint8 mask (shared by all
+// heads) is applied to the score fragments.  Same mma.sync m16n8k16 fragment algebra as attention_mma_kernel above.
+// ------------------------------------------------------------------------------------------------
+namespace fb200 {
+
+__global__ void __launch_bounds__(128) attention_mma_stream_kernel(const __half* __restrict__ q, int q_pitch, const __half* __restrict__ k, int k_pitch,
+                                                                   const __half* __restrict__ v, int v_pitch, const uint8_t* __restrict__ mask, int LkP,
+                                                                   const int* __restrict__ allowed, __half* __restrict__ out, int out_pitch, int Lq,
+                                                                   int Lk, int heads, float scale_log2) {
+  __shared__ __align__(16) __half Ks[2][64 * AM_PITCH];
+  __shared__ __align__(16) __half Vs[2][64 * AM_PITCH];
+  __shared__ __align__(16) __half Qs[64 * AM_PITCH];
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int q0 = blockIdx.y * 64;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nblk = (Lk + 63) / 64;
+  // this thread's slice of a 64x32 block: rows r_ld, r_ld + 32 ; 8 halves at column c_ld
+  const int r_ld = tid >> 2, c_ld = (tid & 3) * 8;
+  uint4 kreg[2], vreg[2];
+  auto fetch = [&](int blk) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int key = blk * 64 + r_ld + i * 32;
+      kreg[i] = make_uint4(0, 0, 0, 0); vreg[i] = make_uint4(0, 0, 0, 0);
+      if (key < Lk) {
+        kreg[i] = *reinterpret_cast<const uint4*>(k + ((int64_t)b * Lk + key) * k_pitch + h * 32 + c_ld);
+        vreg[i] = *reinterpret_cast<const uint4*>(v + ((int64_t)b * Lk + key) * v_pitch + h * 32 + c_ld);
+      }
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      *reinterpret_cast<uint4*>(&Ks[buf][(r_ld + i * 32) * AM_PITCH + c_ld]) = kreg[i];
+      *reinterpret_cast<uint4*>(&Vs[buf][(r_ld + i * 32) * AM_PITCH + c_ld]) = vreg[i];
+    }
+  };
+  for (int i = tid; i < 64 * 4; i += 128) {
+    const int r = i >> 2, c = (i & 3) * 8;
+    uint4 qv = make_uint4(0, 0, 0, 0);
+    if (q0 + r < Lq) qv = *reinterpret_cast<const uint4*>(q + ((int64_t)b * Lq + q0 + r) * q_pitch + h * 32 + c);
+    *reinterpret_cast<uint4*>(Qs + r * AM_PITCH + c) = qv;
+  }
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  uint32_t qa[2][4];
+  {
+    const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+    const int c = (lane >> 4) * 8;
+    ldsm_x4(qa[0], Qs + r * AM_PITCH + c);
+    ldsm_x4(qa[1], Qs + r * AM_PITCH + 16 + c);
+  }
+  // the two query rows this thread holds score columns for
+  const int qr0 = q0 + warp * 16 + (lane >> 2), qr1 = qr0 + 8;
+  const bool use0 = mask && qr0 < Lq && allowed[b * Lq + qr0] > 0, use1 = mask && qr1 < Lq && allowed[b * Lq + qr1] > 0;
+  const uint8_t* mr0 = mask ? mask + ((int64_t)b * Lq + min(qr0, Lq - 1)) * LkP : nullptr;
+  const uint8_t* mr1 = mask ? mask + ((int64_t)b * Lq + min(qr1, Lq - 1)) * LkP : nullptr;
+  float o[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  for (int blk = 0; blk < nblk; ++blk) {
+    const int buf = blk & 1, kb = blk * 64;
+    if (blk + 1 < nblk) fetch(blk + 1);
+    const __half* Kb = Ks[buf];
+    const __half* Vb = Vs[buf];
+    float s[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[nt][j] = 0.f;
+      uint32_t kf[4];
+      ldsm_x4(kf, Kb + (nt * 8 + (lane & 7)) * AM_PITCH + (lane >> 3) * 8);
+      mma16816(s[nt], qa[0], kf[0], kf[1]);
+      mma16816(s[nt], qa[1], kf[2], kf[3]);
+    }
+    float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int key = kb + nt * 8 + (lane & 3) * 2;  // even; LkP % 4 == 0 keeps the 2-byte mask loads aligned
+      bool d00 = key >= Lk, d01 = key + 1 >= Lk, d10 = d00, d11 = d01;
+      if (use0 && key < LkP) { const uchar2 mm = *reinterpret_cast<const uchar2*>(mr0 + key); d00 |= mm.x != 0; d01 |= mm.y != 0; }
+      if (use1 && key < LkP) { const uchar2 mm = *reinterpret_cast<const uchar2*>(mr1 + key); d10 |= mm.x != 0; d11 |= mm.y != 0; }
+      if (d00) s[nt][0] = -INFINITY;
+      if (d01) s[nt][1] = -INFINITY;
+      if (d10) s[nt][2] = -INFINITY;
+      if (d11) s[nt][3] = -INFINITY;
+      bm0 = fmaxf(bm0, fmaxf(s[nt][0], s[nt][1]));
+      bm1 = fmaxf(bm1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+    const float nm0 = fmaxf(m0, bm0), nm1 = fmaxf(m1, bm1);
+    const float z0 = (nm0 == -INFINITY) ? 0.f : nm0, z1 = (nm1 == -INFINITY) ? 0.f : nm1;  // fully-masked-so-far rows stay at zero mass
+    const float a0 = exp2f((m0 - z0) * scale_log2), a1 = exp2f((m1 - z1) * scale_log2);
+    m0 = nm0; m1 = nm1;
+    l0 *= a0; l1 *= a1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { o[i][0] *= a0; o[i][1] *= a0; o[i][2] *= a1; o[i][3] *= a1; }
+    uint32_t pa[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float p0 = exp2f((s[nt][0] - z0) * scale_log2), p1 = exp2f((s[nt][1] - z0) * scale_log2);
+      const float p2 = exp2f((s[nt][2] - z1) * scale_log2), p3 = exp2f((s[nt][3] - z1) * scale_log2);
+      l0 += p0 + p1; l1 += p2 + p3;
+      pa[nt >> 1][(nt & 1) * 2 + 0] = pack_h2(p0, p1);
+      pa[nt >> 1][(nt & 1) * 2 + 1] = pack_h2(p2, p3);
+    }
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int r = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+      uint32_t vf[4];
+      ldsm_x4_trans(vf, Vb + r * AM_PITCH + (lane >> 4) * 8);
+      mma16816(o[0], pa[ks], vf[0], vf[1]);
+      mma16816(o[1], pa[ks], vf[2], vf[3]);
+      ldsm_x4_trans(vf, Vb + r * AM_PITCH + 16 + (lane >> 4) * 8);
+      mma16816(o[2], pa[ks], vf[0], vf[1]);
+      mma16816(o[3], pa[ks], vf[2], vf[3]);
+    }
+    if (blk + 1 < nblk) stash(buf ^ 1);  // the other buffer was last read in iteration blk-1, separated by the barrier below
+    __syncthreads();
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const int c = h * 32 + nt * 8 + (lane & 3) * 2;
+    if (qr0 < Lq) *reinterpret_cast<uint32_t*>(out + ((int64_t)b * Lq + qr0) * out_pitch + c) = pack_h2(o[nt][0] * i0, o[nt][1] * i0);
+    if (qr1 < Lq) *reinterpret_cast<uint32_t*>(out + ((int64_t)b * Lq + qr1) * out_pitch + c) = pack_h2(o[nt][2] * i1, o[nt][3] * i1);
+  }
+}
+
+int attention_mma_stream(const __half* q, int q_pitch, const __half* k, int k_pitch, const __half* v, int v_pitch, const uint8_t* mask, int LkP,
+                         const int* allowed, __half* out, int out_pitch, int B, int Lq, int Lk, int heads, float scale, cudaStream_t st) {
+  dim3 grid(B * heads, (unsigned)cdiv(Lq, 64));
+  attention_mma_stream_kernel<<<grid, 128, 0, st>>>(q, q_pitch, k, k_pitch, v, v_pitch, mask, LkP, allowed, out, out_pitch, Lq, Lk, heads,
+                                                    scale * 1.4426950408889634f);
+  FB_CHECK_LAUNCH("attention_mma_stream");
+  return FB200_OK;
+}
+
+}  // namespace fb200
