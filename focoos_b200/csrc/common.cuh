@@ -65,6 +65,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     case FB200_ACT_RELU: return fmaxf(v, 0.f);
     case FB200_ACT_SILU: return v / (1.f + expf(-v));
     case FB200_ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+    case FB200_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
     default: return v;
   }
 }

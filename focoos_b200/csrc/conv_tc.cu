@@ -532,6 +532,7 @@ bool conv2d_tc_supported(const ConvParams& p, int x_dtype, int out_dtype) {
   if (p.res && p.Cout % (128 / oelt) != 0) return false;  // residual is consumed in whole 128-byte row chunks
   if (p.KH != p.KW) return false;
   if ((p.act & 15) == FB200_ACT_GELU && (out_dtype != FB200_F16 || p.Cin % 64 != 0)) return false;
+  if ((p.act & 15) == FB200_ACT_SIGMOID) return false;  // gates are [B, C] vectors: SIMT path
   if ((p.out_bs * oelt) % 16 != 0) return false;
   if (p.stride == 1) return (2 * p.pad == p.KH - 1) || (p.KH == 1 && p.pad == 0);
   if (p.stride == 2) return p.KH == 3 && p.pad == 1 && p.H % 2 == 0 && p.W % 2 == 0;

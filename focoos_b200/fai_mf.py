@@ -206,8 +206,13 @@ class MFEngine(DetrEngine):
         self.layer = {i: self._conv_bn(sd, f"{pd}.layer_{i}", 1, ops.ACT_RELU) for i in (1, 2, 3, 4)}
         self.adapter = {i: self._conv_bn(sd, f"{pd}.adapter_{i}", 0, ops.ACT_NONE) for i in (1, 2, 3)}
         self.mask_features = self._conv_bias(sd, pd + ".mask_features", 1)
+        self._pack_decoder(sd, 3)
+
+    def _pack_decoder(self, sd, num_levels):
+        """head.predictor.* of the masked transformer decoder (same key names in fai_mf and bisenetformer)."""
+        cfg = self.cfg
         hp = "head.predictor"
-        self.dec_in = [self._conv_bias(sd, f"{hp}.input_proj.{i}", 0) for i in range(3)]
+        self.dec_in = [self._conv_bias(sd, f"{hp}.input_proj.{i}", 0) for i in range(num_levels)]
         self.query_feat, self.query_embed = self._to(sd[hp + ".query_feat.weight"].float()), self._to(sd[hp + ".query_embed.weight"].float())
         d = self.d
         self.dec = []
@@ -293,9 +298,17 @@ class MFEngine(DetrEngine):
         mask_features = self.mask_features(y, algo=A)
         if taps is not None:
             taps.update(res5=res5, enc_memory=src.reshape(B, h, w, d), mask_features=mask_features, multi_scale=ms)
-        # ---- masked transformer decoder
+        return self._run_decoder(ms, mask_features, B, H, W, taps)
+
+    def _run_decoder(self, ms, mask_features, B, H, W, taps=None):
+        """MultiScaleMaskedTransformerDecoder.forward (fai_mf/modelling.py:467-550) + head + final upsample; `ms` = the decoder's
+        feature levels (3 for fai_mf, 2 for bisenetformer)."""
+        cfg, A = self.cfg, self.algo
+        d, nh = self.d, self.nhead
+        scale = 1.0 / math.sqrt(d // nh)
+        nl = len(ms)
         srcs, kpos, sizes = [], [], []
-        for i in range(3):
+        for i in range(nl):
             hh, ww = ms[i].shape[1], ms[i].shape[2]
             s = self.dec_in[i](ms[i], algo=A).reshape(B, hh * ww, d)
             srcs.append(s)
@@ -308,7 +321,7 @@ class MFEngine(DetrEngine):
         L = len(self.dec)
         cls = None
         for i, blk in enumerate(self.dec):
-            lvl = i % 3
+            lvl = i % nl
             t2 = ops.layernorm(out, *blk["cn"])
             q = blk["cq"](ops.add(t2, qpos), algo=A)
             a = ops.attention_masked(q, blk["ck"](kpos[lvl], algo=A), blk["cv"](srcs[lvl], algo=A), attn[0], attn[1], nh, scale)
@@ -320,7 +333,7 @@ class MFEngine(DetrEngine):
             t2 = ops.layernorm(out, *blk["fn"])
             out = blk["l2"](blk["l1"](t2, act=ops.ACT_RELU, algo=A), residual=out, algo=A)
             last = i == L - 1
-            cls, masks, attn = self._heads(out, mask_features, None if last else sizes[(i + 1) % 3], last)
+            cls, masks, attn = self._heads(out, mask_features, None if last else sizes[(i + 1) % nl], last)
             if taps is not None:
                 taps[f"dec{i}_out"] = out
         if taps is not None:

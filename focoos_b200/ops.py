@@ -583,3 +583,100 @@ def mask_resize_bbox(masks, bq_i32, thr: float, size):
     if n:
         _be().mask_resize_bbox(masks.contiguous(), bq_i32.contiguous(), thr, om, ob)
     return om, ob
+
+
+# ------------------------------------------------------------------------------------------------
+# BiSeNetFormer-family operators
+# ------------------------------------------------------------------------------------------------
+ACT_SIGMOID = 4
+EXPORTED_SYMBOLS = EXPORTED_SYMBOLS + ("fb200_dwconv3x3s2_bn", "fb200_avgpool3x3s2", "fb200_global_avgpool", "fb200_channel_scale", "fb200_mask_argmax",
+                                       "fb200_label_resize_bbox")
+
+
+def _cb_dwconv3x3s2(self, x, w9c, scale, bias, out):
+    self._cuda(x, w9c, out)
+    B, H, W, C = x.shape
+    self._call("fb200_dwconv3x3s2_bn", _p(x), _dt(x), B, H, W, C, _p(w9c), _p(scale), _p(bias), _p(out), _stream())
+
+
+def _cb_avgpool3x3s2(self, x, out):
+    self._cuda(x, out)
+    B, H, W, C = x.shape
+    self._call("fb200_avgpool3x3s2", _p(x), _dt(x), B, H, W, C, _p(out), _pitch(out), _stream())
+
+
+def _cb_global_avgpool(self, x, out):
+    self._cuda(x, out)
+    B, C = x.shape[0], x.shape[-1]
+    self._call("fb200_global_avgpool", _p(x), _dt(x), B, x.numel() // (B * C), C, _p(out), _stream())
+
+
+def _cb_channel_scale(self, x, gate, addvec, addt, self_add, out):
+    self._cuda(x, gate, out)
+    B, C = x.shape[0], x.shape[-1]
+    self._call("fb200_channel_scale", _p(x), _p(gate), _p(addvec), _p(addt), int(self_add), _p(out), _dt(x), B, ctypes.c_int64(x.numel() // (B * C)), C, _stream())
+
+
+def _cb_mask_argmax(self, masks, scores, labels, counts):
+    self._cuda(masks, scores, labels, counts)
+    B, Q, H, W = masks.shape
+    self._call("fb200_mask_argmax", _p(masks), _p(scores), B, Q, ctypes.c_int64(H * W), _p(labels), _p(counts), _stream())
+
+
+def _cb_label_resize_bbox(self, labels, bq, out_masks, out_bbox):
+    self._cuda(labels, bq, out_masks, out_bbox)
+    self._call("fb200_label_resize_bbox", _p(labels), labels.shape[1], labels.shape[2], _p(bq), bq.shape[0], _p(out_masks), out_masks.shape[1], out_masks.shape[2],
+               _p(out_bbox), _stream())
+
+
+for _n, _f in (("dwconv3x3s2", _cb_dwconv3x3s2), ("avgpool3x3s2", _cb_avgpool3x3s2), ("global_avgpool", _cb_global_avgpool), ("channel_scale", _cb_channel_scale),
+               ("mask_argmax", _cb_mask_argmax), ("label_resize_bbox", _cb_label_resize_bbox)):
+    setattr(CudaBackend, _n, _f)
+
+
+def dwconv3x3s2(x, w9c, scale, bias):
+    """depthwise 3x3/s2/p1 conv + folded BN (CatBottleneck.avd_layer); w9c fp32 [9, C]."""
+    B, H, W, C = x.shape
+    out = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C), dtype=x.dtype, device=x.device)
+    _be().dwconv3x3s2(x.contiguous(), w9c, scale, bias, out)
+    return out
+
+
+def avgpool3x3s2(x, out=None):
+    B, H, W, C = x.shape
+    if out is None:
+        out = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C), dtype=x.dtype, device=x.device)
+    _be().avgpool3x3s2(x.contiguous(), out)
+    return out
+
+
+def global_avgpool(x):
+    """[B,H,W,C] (or [B,L,C]) -> [B,C] mean over the middle dims."""
+    out = torch.empty((x.shape[0], x.shape[-1]), dtype=x.dtype, device=x.device)
+    _be().global_avgpool(x.contiguous(), out)
+    return out
+
+
+def channel_scale(x, gate, addvec=None, addt=None, self_add=False):
+    """x * gate[b,c] (+ addvec[b,c]) (+ addt) (+ x)."""
+    out = torch.empty_like(x)
+    _be().channel_scale(x.contiguous(), gate.contiguous(), None if addvec is None else addvec.contiguous(), None if addt is None else addt.contiguous(), self_add, out)
+    return out
+
+
+def mask_argmax(masks, scores):
+    """-> (labels uint8 [B,H,W] = argmax_q(score_q * mask_q), counts int32 [B,Q])."""
+    B, Q, H, W = masks.shape
+    labels = torch.empty((B, H, W), dtype=torch.uint8, device=masks.device)
+    counts = torch.zeros((B, Q), dtype=torch.int32, device=masks.device)
+    _be().mask_argmax(masks.contiguous(), scores.contiguous(), labels, counts)
+    return labels, counts
+
+
+def label_resize_bbox(labels, bq_i32, size):
+    n = bq_i32.shape[0]
+    om = torch.empty((n, size[0], size[1]), dtype=torch.uint8, device=labels.device)
+    ob = torch.empty((n, 4), dtype=torch.int32, device=labels.device)
+    if n:
+        _be().label_resize_bbox(labels.contiguous(), bq_i32.contiguous(), om, ob)
+    return om, ob

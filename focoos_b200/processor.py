@@ -173,9 +173,13 @@ class MaskFormerProcessor(DETRProcessor):
         """-> list over images of (query idx [n], scores [n], labels [n]) on the host, plus the device masks tensor."""
         threshold = threshold or self.threshold
         use_mask_score = use_mask_score or self.use_mask_score
-        if self.predict_all_pixels:
-            raise NotImplementedError("semantic (predict_all_pixels) post-processing lands with the BiSeNetFormer family")
-        count, psum = ops.mask_stats(output.masks, float(self.mask_threshold))
+        self._labels = None
+        if self.predict_all_pixels:  # semantic: every pixel goes to argmax_q(score_q * prob_q) (processor.py:208-220)
+            scores_dev = output.logits.max(-1).values  # [B,Q]; tiny reduction, stays on the device for the argmax kernel
+            self._labels, count = ops.mask_argmax(output.masks, scores_dev)
+            psum = count.float()
+        else:
+            count, psum = ops.mask_stats(output.masks, float(self.mask_threshold))
         host = torch.cat([output.logits.reshape(output.logits.shape[0], -1), count.float(), psum], dim=1).cpu().numpy()  # one D2H
         B, Q, K = output.logits.shape
         res = []
@@ -202,7 +206,10 @@ class MaskFormerProcessor(DETRProcessor):
                 results.append(FocoosDetections(detections=[]))
                 continue
             bq = torch.tensor(np.stack([np.full_like(q, b), q], 1), dtype=torch.int32).to(output.masks.device)
-            m, box = ops.mask_resize_bbox(output.masks, bq, float(self.mask_threshold), image_sizes[b])
+            if self._labels is not None:
+                m, box = ops.label_resize_bbox(self._labels, bq, image_sizes[b])
+            else:
+                m, box = ops.mask_resize_bbox(output.masks, bq, float(self.mask_threshold), image_sizes[b])
             m, box = m.cpu().numpy().astype(bool), box.cpu().numpy()
             dets = []
             for i in range(len(q)):

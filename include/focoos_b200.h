@@ -31,7 +31,7 @@ extern "C" {
 
 typedef enum { FB200_OK = 0, FB200_ERR_INVALID = -1, FB200_ERR_UNSUPPORTED = -2, FB200_ERR_CUDA = -3 } fb200_status;
 typedef enum { FB200_F32 = 0, FB200_F16 = 1 } fb200_dtype;
-typedef enum { FB200_ACT_NONE = 0, FB200_ACT_RELU = 1, FB200_ACT_SILU = 2, FB200_ACT_GELU = 3,
+typedef enum { FB200_ACT_NONE = 0, FB200_ACT_RELU = 1, FB200_ACT_SILU = 2, FB200_ACT_GELU = 3, FB200_ACT_SIGMOID = 4 /* SIMT path only */,
                FB200_ACT_RESIDUAL_AFTER = 16 /* OR-ed flag: out = act(conv) + residual instead of act(conv + residual) */ } fb200_act;
 typedef enum { FB200_ALGO_AUTO = 0, FB200_ALGO_SIMT = 1, FB200_ALGO_TCGEN05 = 2 } fb200_algo;
 
@@ -164,6 +164,24 @@ int fb200_mask_stats(const float* masks, int64_t planes, int64_t hw, float thr, 
  * (masks_to_xyxy, utils/vision.py:344-370). */
 int fb200_mask_resize_bbox(const float* masks, int Q, int H, int W, const int* bq, int n, float thr, uint8_t* out, int Ho, int Wo, int* bbox,
                            void* stream);
+
+/* ======== BiSeNetFormer family (focoos/nn/backbone/stdc.py, focoos/models/bisenetformer/modelling.py) ===== */
+
+/* CatBottleneck.avd_layer: depthwise 3x3 stride-2 pad-1 conv + BatchNorm (nn/backbone/stdc.py:117-130). x [B,H,W,C] NHWC,
+ * w9c fp32 [9][C] (tap-major), scale/bias = folded BN. out [B,ceil(H/2),ceil(W/2),C]. */
+int fb200_dwconv3x3s2_bn(const void* x, int dtype, int B, int H, int W, int C, const float* w9c, const float* scale, const float* bias, void* out, void* stream);
+/* CatBottleneck.skip: AvgPool2d(3, 2, 1), count_include_pad=True (nn/backbone/stdc.py:131); out may be a channel slice. */
+int fb200_avgpool3x3s2(const void* x, int dtype, int B, int H, int W, int C, void* out, int out_pitch, void* stream);
+/* feat.mean(dim=(2,3)) / adaptive_avg_pool2d(1) (bisenetformer/modelling.py:162,187,228): [B,HW,C] -> [B,C]. */
+int fb200_global_avgpool(const void* x, int dtype, int B, int HW, int C, void* out, void* stream);
+/* ARM / FFM gating: out = x * gate[b,c] (+ addvec[b,c]) (+ addt[b,hw,c]) (+ x if self_add) (bisenetformer/modelling.py:166,190,196,232-234). */
+int fb200_channel_scale(const void* x, const void* gate, const void* addvec, const void* addt, int self_add, void* out, int dtype, int B, int64_t HW, int C,
+                        void* stream);
+/* Semantic post-process (processor.py:208-220, predict_all_pixels): labels[b,p] = argmax_q(scores[b,q] * masks[b,q,p]) (first maximum),
+ * counts[b,q] (ZERO-INITIALISED by the caller) += pixels labelled q. masks [B,Q,HW] fp32, Q <= 255. */
+int fb200_mask_argmax(const float* masks, const float* scores, int B, int Q, int64_t HW, uint8_t* labels, int* counts, void* stream);
+/* kept one-hot masks -> original image size + boxes: pair i = (b,q): (labels[b] == q) -> bilinear resize -> != 0 (processor.py:275-283). */
+int fb200_label_resize_bbox(const uint8_t* labels, int H, int W, const int* bq, int n, uint8_t* out, int Ho, int Wo, int* bbox, void* stream);
 
 #ifdef __cplusplus
 }

@@ -124,8 +124,9 @@ def masked_decoder(ms: List[Tensor], mask_features: Tensor, sd: SD, cfg: MFOracl
     (nn/layers/transformer.py:83-106,206-238,365-378)."""
     p = "head.predictor"
     B = ms[0].shape[0]
+    nl = len(ms)  # 3 levels for fai_mf, 2 for bisenetformer (x[:-1], bisenetformer/modelling.py:378)
     src, pos, sizes = [], [], []
-    for i in range(3):
+    for i in range(nl):
         h, w = ms[i].shape[-2:]
         sizes.append((h, w))
         pos.append(position_embedding_sine_normalized(h, w, cfg.hidden_dim // 2).flatten(2).permute(0, 2, 1))
@@ -136,7 +137,7 @@ def masked_decoder(ms: List[Tensor], mask_features: Tensor, sd: SD, cfg: MFOracl
     hp = p + ".forward_prediction_heads"
     cls, masks, attn = prediction_heads(out, mask_features, sd, hp, sizes[0])
     for i in range(cfg.dec_layers):
-        lvl = i % 3
+        lvl = i % nl
         # rows that mask everything are un-masked (:510-512)
         keep = (attn.sum(-1) != attn.shape[-1]).unsqueeze(-1)
         attn = attn & keep
@@ -150,7 +151,7 @@ def masked_decoder(ms: List[Tensor], mask_features: Tensor, sd: SD, cfg: MFOracl
         f = f"{p}.transformer_ffn_layers.{i}"
         t2 = layer_norm(out, sd, f + ".norm")
         out = out + linear(F.relu(linear(t2, sd, f + ".linear1")), sd, f + ".linear2")
-        cls, masks, attn = prediction_heads(out, mask_features, sd, hp, sizes[(i + 1) % 3])
+        cls, masks, attn = prediction_heads(out, mask_features, sd, hp, sizes[(i + 1) % nl])
         if taps is not None:
             taps[f"dec{i}_out"] = out
     return cls, masks

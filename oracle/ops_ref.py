@@ -17,7 +17,7 @@ import torch.nn.functional as F
 
 
 def _act(x, act):
-    return [lambda v: v, F.relu, F.silu, F.gelu][act](x)
+    return [lambda v: v, F.relu, F.silu, F.gelu, torch.sigmoid][act](x)
 
 
 def _f(t):
@@ -201,4 +201,57 @@ def _ref_mask_resize_bbox(self, masks, bq, thr, out_masks, out_bbox):
 for _n, _f in (("upsample_nearest_add", _ref_upsample_nearest_add), ("attn_mask_build", _ref_attn_mask_build), ("attention_masked", _ref_attention_masked),
                ("softmax_drop_last", _ref_softmax_drop_last), ("mask_sigmoid_upsample", _ref_mask_sigmoid_upsample), ("mask_stats", _ref_mask_stats),
                ("mask_resize_bbox", _ref_mask_resize_bbox)):
+    setattr(RefBackend, _n, _f)
+
+
+# ---- BiSeNetFormer-family operators -----------------------------------------------------------------------------------
+def _ref_dwconv3x3s2(self, x, w9c, scale, bias, out):
+    C = x.shape[-1]
+    w = w9c.t().reshape(C, 1, 3, 3)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), w, None, 2, 1, 1, C) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
+    out.copy_(y.permute(0, 2, 3, 1).to(out.dtype))
+
+
+def _ref_avgpool3x3s2(self, x, out):
+    out.copy_(F.avg_pool2d(x.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).to(out.dtype))
+
+
+def _ref_global_avgpool(self, x, out):
+    B, C = x.shape[0], x.shape[-1]
+    out.copy_(x.float().reshape(B, -1, C).mean(1).to(out.dtype))
+
+
+def _ref_channel_scale(self, x, gate, addvec, addt, self_add, out):
+    B, C = x.shape[0], x.shape[-1]
+    xs = x.float().reshape(B, -1, C)
+    y = xs * gate.float().view(B, 1, C)
+    if addvec is not None:
+        y = y + addvec.float().view(B, 1, C)
+    if addt is not None:
+        y = y + addt.float().reshape(B, -1, C)
+    if self_add:
+        y = y + xs
+    out.copy_(y.reshape(x.shape).to(out.dtype))
+
+
+def _ref_mask_argmax(self, masks, scores, labels, counts):
+    B, Q = scores.shape
+    lab = (scores.view(B, Q, 1, 1) * masks).argmax(dim=1)
+    labels.copy_(lab.to(torch.uint8))
+    for b in range(B):
+        counts[b] = torch.bincount(lab[b].flatten(), minlength=Q).to(torch.int32)
+
+
+def _ref_label_resize_bbox(self, labels, bq, out_masks, out_bbox):
+    for i in range(bq.shape[0]):
+        b, q = int(bq[i, 0]), int(bq[i, 1])
+        m = (labels[b] == q).float()[None, None]
+        r = F.interpolate(m, size=(out_masks.shape[1], out_masks.shape[2]), mode="bilinear", align_corners=False)[0, 0].bool()
+        out_masks[i] = r.to(torch.uint8)
+        rows, cols = r.any(1).nonzero(), r.any(0).nonzero()
+        out_bbox[i] = torch.tensor([int(cols[0]), int(rows[0]), int(cols[-1]), int(rows[-1])] if len(rows) else [0, 0, 0, 0], dtype=torch.int32)
+
+
+for _n, _f in (("dwconv3x3s2", _ref_dwconv3x3s2), ("avgpool3x3s2", _ref_avgpool3x3s2), ("global_avgpool", _ref_global_avgpool), ("channel_scale", _ref_channel_scale),
+               ("mask_argmax", _ref_mask_argmax), ("label_resize_bbox", _ref_label_resize_bbox)):
     setattr(RefBackend, _n, _f)

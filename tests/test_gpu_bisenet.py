@@ -1,0 +1,124 @@
+"""-m gpu: BiSeNetFormer-family kernels vs CPU references and BisenetFormer end-to-end vs reference goldens."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from focoos_b200 import ops
+from focoos_b200.bisenetformer import BisenetFormer, BisenetFormerConfig
+from focoos_b200.processor import MaskFormerProcessor
+from focoos_b200.utils.seeded_weights import seeded_state_dict
+from oracle.gen_golden import synth_images
+from oracle.ops_ref import RefBackend
+from tests.parity_utils import load_golden, manifest_template
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+REF = RefBackend()
+DEV = "cuda"
+
+
+def rnd(shape, dtype, seed, s=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * s).to(dtype)
+
+
+def close(a, b, tol, what):
+    a, b = a.detach().float().cpu(), b.detach().float()
+    err, scale = float((a - b).abs().max()), max(1.0, float(b.abs().max()))
+    assert err <= tol * scale, f"{what}: max|d|={err:.3e} scale={scale:.2e}"
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_stdc_ops(dtype):
+    tol = 3e-3 if dtype == torch.float16 else 1e-5
+    x = rnd((2, 17, 22, 64), dtype, 1)
+    w9c, sc, bi = rnd((9, 64), torch.float32, 2, 0.3), torch.rand(64) + 0.5, rnd((64,), torch.float32, 3, 0.1)
+    ref = torch.empty((2, 9, 11, 64), dtype=dtype)
+    REF.dwconv3x3s2(x, w9c, sc, bi, ref)
+    close(ops.dwconv3x3s2(x.to(DEV), w9c.to(DEV), sc.to(DEV), bi.to(DEV)), ref, tol, "dwconv")
+    REF.avgpool3x3s2(x, ref)
+    close(ops.avgpool3x3s2(x.to(DEV)), ref, tol, "avgpool3x3s2")
+    buf = torch.zeros((2, 9, 11, 128), dtype=dtype, device=DEV)
+    ops.avgpool3x3s2(x.to(DEV), out=buf[..., 64:])
+    close(buf[..., 64:], ref, tol, "avgpool into slice")
+    assert float(buf[..., :64].abs().max()) == 0
+    g = torch.empty((2, 64), dtype=dtype)
+    REF.global_avgpool(x, g)
+    close(ops.global_avgpool(x.to(DEV)), g, tol, "global_avgpool")
+    gate, av, at = rnd((2, 64), dtype, 4), rnd((2, 64), dtype, 5), rnd((2, 17, 22, 64), dtype, 6)
+    for kw in ({"addvec": av}, {"addt": at}, {"self_add": True}):
+        r = torch.empty_like(x)
+        REF.channel_scale(x, gate, kw.get("addvec"), kw.get("addt"), kw.get("self_add", False), r)
+        close(ops.channel_scale(x.to(DEV), gate.to(DEV), **{k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in kw.items()}), r, tol, f"channel_scale {list(kw)}")
+    # sigmoid epilogue of the gate GEMM (SIMT path)
+    w = rnd((64, 1, 1, 64), dtype, 7, 0.2)
+    r = torch.empty((2, 1, 1, 64), dtype=dtype)
+    REF.conv2d(g.reshape(2, 1, 1, 64), w, sc, bi, 1, 0, ops.ACT_SIGMOID, None, r, 0)
+    close(ops.conv2d(g.reshape(2, 1, 1, 64).to(DEV), w.to(DEV), sc.to(DEV), bi.to(DEV), act=ops.ACT_SIGMOID, algo=ops.ALGO_SIMT), r, tol, "sigmoid gate")
+
+
+def test_conv_s2_cin32_tc():
+    # STDC features.1: 3x3 stride-2 conv with Cin = 32 (5-D parity view + SWIZZLE_64B)
+    x, w = rnd((2, 32, 48, 32), torch.float16, 8), rnd((64, 3, 3, 32), torch.float16, 9, 0.06)
+    bi = rnd((64,), torch.float32, 10)
+    ref = torch.empty((2, 16, 24, 64), dtype=torch.float16)
+    REF.conv2d(x, w, None, bi, 2, 1, 1, None, ref, 0)
+    close(ops.conv2d(x.to(DEV), w.to(DEV), None, bi.to(DEV), stride=2, pad=1, act=1, algo=ops.ALGO_TCGEN05), ref, 3e-3, "s2 cin32")
+
+
+def test_semantic_postprocess_ops():
+    g = torch.Generator().manual_seed(11)
+    masks = torch.rand((2, 100, 40, 56), generator=g)
+    scores = torch.rand((2, 100), generator=g)
+    rl, rc = torch.empty((2, 40, 56), dtype=torch.uint8), torch.zeros((2, 100), dtype=torch.int32)
+    REF.mask_argmax(masks, scores, rl, rc)
+    l, c = ops.mask_argmax(masks.to(DEV), scores.to(DEV))
+    assert torch.equal(l.cpu(), rl) and torch.equal(c.cpu(), rc)
+    bq = torch.tensor([[0, int(rl[0, 0, 0])], [1, int(rl[1, 5, 5])], [1, 200 % 100]], dtype=torch.int32)
+    for size in ((40, 56), (77, 91)):
+        rm, rb = torch.empty((3, *size), dtype=torch.uint8), torch.empty((3, 4), dtype=torch.int32)
+        REF.label_resize_bbox(rl, bq, rm, rb)
+        m, b = ops.label_resize_bbox(l, bq.to(DEV), size)
+        assert torch.equal(m.cpu(), rm) and torch.equal(b.cpu(), rb), size
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_bisenet_end_to_end_vs_reference_golden(precision):
+    g = load_golden("bisenetformer_l_ade_b2_256x384")
+    sd = seeded_state_dict(manifest_template("bisenetformer_l_ade"), 0)
+    m = BisenetFormer(BisenetFormerConfig(), precision=precision)
+    m.load_state_dict(sd, strict=True)
+    m.cuda()
+    imgs = synth_images(4, [tuple(s) for s in g["sizes"].tolist()])
+    x = torch.stack([torch.from_numpy(im).permute(2, 0, 1).float() for im in imgs]).cuda()
+    taps = {}
+    out = m(x, taps=taps)
+    torch.cuda.synchronize()
+    scale = float(g["pred_masks_stat"][2])
+    pm = taps["pred_masks"][..., :100].permute(0, 3, 1, 2).float().cpu().numpy()
+    e = {"cp32_rel": float(np.abs(taps["cp32"].permute(0, 3, 1, 2)[:, ::16].float().cpu().numpy() - g["cp32_tap"]).max() / np.abs(g["cp32_tap"]).max()),
+         "mask_features_rel": float(np.abs(taps["mask_features"].permute(0, 3, 1, 2)[:, ::16, ::2, ::2].float().cpu().numpy() - g["mask_features_tap"]).max() / np.abs(g["mask_features_tap"]).max()),
+         "mask_logits_max_abs": float(np.abs(pm[:, ::4] - g["pred_masks_q4"]).max()), "mask_logit_scale": scale,
+         "class_prob_max_abs": float(np.abs(out.logits.cpu().numpy() - g["logits"]).max()),
+         "mask_prob_max_abs": float(np.abs(out.masks[:, ::10, ::4, ::4].cpu().numpy() - g["masks_q10_s4"]).max())}
+    proc = MaskFormerProcessor(m.config)
+    dets = proc.postprocess(out, imgs, threshold=float(g["threshold"]))
+    e["det_counts"] = [len(d) for d in dets]
+    e["ref_counts"] = g["det_count"].tolist()
+    path = "gpurun_out/parity_report_bisenet.json"
+    os.makedirs("gpurun_out", exist_ok=True)
+    d0 = json.load(open(path)) if os.path.exists(path) else {}
+    d0[precision] = e
+    json.dump(d0, open(path, "w"), indent=1)
+    if precision == "fp32":
+        assert e["mask_logits_max_abs"] <= 1e-4 * scale and e["class_prob_max_abs"] <= 1e-3 and e["mask_prob_max_abs"] <= 1e-3, e
+        for i, d in enumerate(dets):
+            n = int(g["det_count"][i])
+            assert len(d) == n
+            assert [x.cls_id for x in d.detections] == g["det_labels"][i, :n].tolist()
+            assert np.abs(np.array([x.conf for x in d.detections]) - g["det_scores"][i, :n]).max() < 1e-3
+            assert np.abs(np.array([x.bbox for x in d.detections]) - g["det_boxes"][i, :n]).max() <= 3
+    else:
+        assert np.isfinite(e["mask_logits_max_abs"])

@@ -1,0 +1,37 @@
+"""Config 4 of BASELINE.json: bisenetformer-l-ade, bs=64, 1024x512 on one B200 (forward + GPU part of the semantic post-process).
+    python tools/bench_bisenet.py [batch] [H] [W]"""
+import json, os, sys, collections
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from focoos_b200 import ops
+from focoos_b200.bisenetformer import BisenetFormer, BisenetFormerConfig
+from focoos_b200.utils.seeded_weights import seeded_state_dict
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+H = int(sys.argv[2]) if len(sys.argv) > 2 else 512
+W = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
+with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "bisenetformer_l_ade_state_dict_manifest.json")) as f:
+    man = json.load(f)
+sd = seeded_state_dict({k: torch.empty(v[0], dtype=getattr(torch, v[1])) for k, v in man.items()}, 0)
+m = BisenetFormer(BisenetFormerConfig(), precision="fp16"); m.load_state_dict(sd, strict=True); m.cuda()
+x = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device="cuda")
+def step():
+    out = m(x)
+    return ops.mask_argmax(out.masks, out.logits.max(-1).values)
+for _ in range(3): step()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+n = 5
+e0.record()
+for _ in range(n): step()
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / n
+tr = ops.enable_trace(True); step(); torch.cuda.synchronize(); ops.enable_trace(False)
+agg = collections.defaultdict(lambda: [0, 0.0])
+for name, note, a, b in tr:
+    agg[name][0] += 1; agg[name][1] += a.elapsed_time(b)
+tot = sum(v[1] for v in agg.values())
+print(json.dumps({"workload": f"bisenetformer-l-ade bs={B} {W}x{H} (BASELINE configs[3])", "images_per_s": B / ms * 1e3, "ms_per_step": ms, "dtype": "f16", "launches": len(tr),
+                  "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}))
+for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+    print(f"{t:9.2f} ms {100*t/tot:5.1f}%  n={c:4d}  {k}")

@@ -17,6 +17,8 @@ for s in $STAGES; do
     micro_ncu) timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 4 -c 2 -o gpurun_out/prof_micro python tools/conv_micro.py rep_3x3_80 s0_2c_res > gpurun_out/micro_ncu.log 2>&1 ;;
     mf)    timeout 900 python -m pytest tests/test_gpu_mf.py -q -m gpu 2>&1 | tail -40 > gpurun_out/t_mf.log ;;
     mfbench) timeout 900 python tools/bench_mf.py > gpurun_out/bench_mf.txt 2>&1 ;;
+    bise)  timeout 900 python -m pytest tests/test_gpu_bisenet.py -q -m gpu 2>&1 | tail -40 > gpurun_out/t_bise.log ;;
+    bisebench) timeout 900 python tools/bench_bisenet.py > gpurun_out/bench_bisenet.txt 2>&1 ;;
     ref)   timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2>&1 ;;
     ncu_list) timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -s 940 -c 240 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1 ;;
     ncu_full) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 2 -c 8 -o gpurun_out/prof_conv_tc python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1 ;;
