@@ -15,9 +15,11 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 import torch
 
+from .bisenetformer import BisenetFormer, BisenetFormerConfig
 from .fai_detr import FAIDetr
+from .fai_mf import FAIMaskFormer, MaskFormerConfig
 from .ports import DETRConfig, FocoosDetections
-from .processor import DETRProcessor
+from .processor import DETRProcessor, MaskFormerProcessor
 
 # architecture sections of focoos/model_registry/fai-detr-*.json (config.*; class lists omitted)
 _REGISTRY: Dict[str, dict] = {
@@ -25,6 +27,20 @@ _REGISTRY: Dict[str, dict] = {
                                                      "resolution": 640, "threshold": 0.5}},
     "fai-detr-l-coco": {"im_size": 640, "config": {"num_classes": 80, "backbone_config": {"model_type": "resnet", "depth": 50, "variant": "d"}, "num_queries": 300,
                                                    "resolution": 640, "threshold": 0.5}},
+    "fai-mf-l-coco-ins": {"family": "fai_mf", "im_size": 1024, "config": {"num_classes": 80, "backbone_config": {"model_type": "resnet", "depth": 101, "variant": "d"},
+                                                                           "num_queries": 100, "postprocessing_type": "instance", "predict_all_pixels": False,
+                                                                           "use_mask_score": True, "threshold": 0.5}},
+    "bisenetformer-l-ade": {"family": "bisenetformer", "im_size": 640, "config": {"num_classes": 150, "backbone_config": {"model_type": "stdc", "base": 64, "layers": [4, 5, 3]},
+                                                                                   "num_queries": 100, "postprocessing_type": "semantic", "predict_all_pixels": True,
+                                                                                   "use_mask_score": False, "threshold": 0.5}},
+}
+
+# model family -> (config class, nn.Module class, processor class, resize inputs to im_size?) — ModelManager.register_model / ProcessorManager
+# (focoos/model_manager.py:94-105, focoos/processor/processor_manager.py:14-18)
+_FAMILIES = {
+    "fai_detr": (DETRConfig, FAIDetr, DETRProcessor, True),
+    "fai_mf": (MaskFormerConfig, FAIMaskFormer, MaskFormerProcessor, False),
+    "bisenetformer": (BisenetFormerConfig, BisenetFormer, MaskFormerProcessor, False),
 }
 
 
@@ -41,9 +57,10 @@ class ModelInfo:
 class FocoosModel:
     """focoos_model.py:100: owns the nn.Module + processor; `infer` / `__call__` / `benchmark`."""
 
-    def __init__(self, model: FAIDetr, model_info: ModelInfo):
+    def __init__(self, model, model_info: ModelInfo):
         self.model, self.model_info = model, model_info
-        self.processor = DETRProcessor(model.config, image_size=model_info.im_size).eval()
+        _, _, proc_cls, resize = _FAMILIES[model_info.model_family]
+        self.processor = proc_cls(model.config, image_size=model_info.im_size if resize else None).eval()
         self.model.eval()
         if torch.cuda.is_available():
             self.model.cuda()
@@ -100,12 +117,15 @@ class ModelManager:
             if name not in _REGISTRY:
                 raise ValueError(f"Model {name} not found in the focoos_b200 registry ({sorted(_REGISTRY)})")
             r = _REGISTRY[name]
-            model_info = ModelInfo(name=name, im_size=r["im_size"], config=dict(r["config"]))
+            model_info = ModelInfo(name=name, model_family=r.get("family", "fai_detr"), im_size=r["im_size"], config=dict(r["config"]))
+        if model_info.model_family not in _FAMILIES:
+            raise ValueError(f"Model family {model_info.model_family} is not on the B200 hot path ({sorted(_FAMILIES)})")
+        cfg_cls, model_cls, _, _ = _FAMILIES[model_info.model_family]
         if config is None:
             cd = dict(model_info.config)
             cd.update(kwargs)
-            config = DETRConfig.from_dict(cd)
-        model = FAIDetr(config, precision=precision)
+            config = cfg_cls.from_dict(cd)
+        model = model_cls(config, precision=precision)
         if state_dict is not None:
             model.load_state_dict(state_dict)
         elif model_info.weights_uri:
