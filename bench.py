@@ -118,11 +118,11 @@ def cpu_reference_run(batch: int, steps: int, warmup: int, sd, threads: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32)
-    ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32", "fp32_tc"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -267,7 +267,7 @@ def main():
             cv, cms = cpu_reference_run(2, 2, 1, sd, cpu_threads)
             cpu = {"value": cv, "unit": "images/s", "cores": cpu_threads, "host_cores": cores, "kind": "port", "sample": "2 timed passes of batch 2 (oracle port of the reference's torch fp32 CPU forward + post-process)"}
         line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16" if args.precision == "fp16" else "f32", "data": "synthetic",
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"fp16": "f16", "fp32": "f32", "fp32_tc": "f32 (3x f16 tensor-core products)"}[args.precision], "data": "synthetic",
                 "config": config, "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
                 "cuda_graph": graph is not None, "roofline": roof, "cpu_baseline": cpu, "detections_img0": len(dets[0])}
         print(json.dumps(line))

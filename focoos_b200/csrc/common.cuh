@@ -85,7 +85,7 @@ __device__ __forceinline__ float warp_max(float v) {
 struct ConvParams {
   const void* x; const void* w; const float* scale; const float* bias; const void* res; void* out;
   int B, H, W, Cin, x_pitch, KH, KW, stride, pad, Ho, Wo, Cout, res_pitch, out_pitch, act;
-  int64_t M; int K; int x_dtype, out_dtype, vec_ok; int64_t out_bs;  // out_bs: elements between images of `out`
+  int64_t M; int K; int x_dtype, out_dtype, vec_ok; int split3; int64_t out_bs;  // out_bs: elements between images of `out`
 };
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }

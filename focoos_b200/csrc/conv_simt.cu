@@ -263,6 +263,13 @@ extern "C" int fb200_conv2d(const void* x, int x_dtype, int B, int H, int W, int
   FB_CHECK_ARG(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && stride > 0 && pad >= 0, "conv2d: bad shape");
   FB_CHECK_ARG(x_pitch >= Cin && out_pitch >= Cout, "conv2d: pitch smaller than channel count");
   ConvParams p;
+  p.split3 = 0;
+  if (algo == FB200_ALGO_TCGEN05_SPLIT3) {  // x = [hi | lo] fp16 pair tensor with Cin = 2C stored channels; w = [Cout][KH][KW][3C]
+    FB_CHECK_ARG(x_dtype == FB200_F16 && Cin % 2 == 0, "conv2d(split3): x must be the fp16 [hi|lo] pair tensor");
+    p.split3 = 1;
+    Cin = (Cin / 2) * 3;  // K runs over hi*W_hi, hi*W_lo, lo*W_hi
+    algo = FB200_ALGO_TCGEN05;
+  }
   p.x = x; p.w = w; p.scale = scale; p.bias = bias; p.res = residual; p.out = out;
   p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.x_pitch = x_pitch; p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad;
   p.Ho = (H + 2 * pad - KH) / stride + 1; p.Wo = (W + 2 * pad - KW) / stride + 1;

@@ -42,7 +42,8 @@ template <int BLOCK_N> __host__ __device__ constexpr int num_threads() { return 
 struct KParams {
   const float* scale; const float* bias; const void* res;
   int res_pitch, act, Cout;
-  int KH, KW, pad, cchunks;        // cchunks = Cin / BLOCK_K
+  int KH, KW, pad, cchunks;        // cchunks = Cin / BLOCK_K (3C/BLOCK_K in split-precision mode)
+  int seg_chunks, lo_off;          // split-precision: chunks per K segment (C/BLOCK_K) and channel offset of the lo half (C); 0 = off
   int BW, BH, tiles_w, tiles_h;    // output tile rectangle and tile counts per image
   int Ho, Wo;                      // output spatial size (residual addressing / validity)
   int x_pitch;                     // stride-2 view only (c' = wp * pitch + c)
@@ -224,6 +225,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ===================================================================== TMA producer
     if (lane == 0) {
       const uint32_t tx_bytes = (uint32_t)(p.BW * p.BH * BLOCK_K * 2) + (uint32_t)B_STAGE_BYTES;
+      // channel coordinate of K-chunk cc.  Split-precision mode (fp32-accurate products from fp16 tensor cores): the stored tensor is
+      // [hi(C) | lo(C)] and K runs over three segments  hi x W_hi,  hi x W_lo,  lo x W_hi  (weights packed [W_hi | W_lo | W_hi]).
+      auto a_chan = [&](int cc) -> int {
+        if (p.seg_chunks == 0) return cc * BLOCK_K;
+        const int seg = cc / p.seg_chunks, within = cc - seg * p.seg_chunks;
+        return (seg == 2 ? p.lo_off : 0) + within * BLOCK_K;
+      };
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -236,10 +244,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const int mtn = tn / p.n_tiles, imgn = mtn / tiles_per_img, remn = mtn - imgn * tiles_per_img;
             const int h0n = (remn / p.tiles_w) * p.BH, w0n = (remn % p.tiles_w) * p.BW;
             for (int cc = 0; cc < p.cchunks; ++cc) {
-              if (!p.stride2) tma_prefetch_4d(&tmap_a, cc * BLOCK_K, w0n, h0n, imgn);
+              const int a_c0 = a_chan(cc);
+              if (!p.stride2) tma_prefetch_4d(&tmap_a, a_c0, w0n, h0n, imgn);
               else {
                 for (int par = 0; par < 4; ++par)  // the four (h, w) parities of the 2x2 input cell
-                  tma_prefetch_5d(&tmap_a, (par & 1) * p.x_pitch + cc * BLOCK_K, w0n, par >> 1, h0n, imgn);
+                  tma_prefetch_5d(&tmap_a, (par & 1) * p.x_pitch + a_c0, w0n, par >> 1, h0n, imgn);
               }
             }
           }
@@ -248,15 +257,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
           const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
+          const int a_c0 = a_chan(cc);
           const int kh = tap / p.KW, kw = tap - kh * p.KW;
           void* dst_a = smem_a + stage * A_STAGE_BYTES;
           if (!p.stride2) {
-            tma_load_4d(&tmap_a, &full_bar[stage], dst_a, cc * BLOCK_K, w0 + kw - p.pad, h0 + kh - p.pad, img);
+            tma_load_4d(&tmap_a, &full_bar[stage], dst_a, a_c0, w0 + kw - p.pad, h0 + kh - p.pad, img);
           } else {
             // input h = 2*ho + kh - 1 -> (h>>1, h&1): kh=0 -> (ho-1,1); kh=1 -> (ho,0); kh=2 -> (ho,1)
             const int dh = (kh == 0) ? -1 : 0, hp = (kh == 1) ? 0 : 1;
             const int dw = (kw == 0) ? -1 : 0, wp = (kw == 1) ? 0 : 1;
-            tma_load_5d(&tmap_a, &full_bar[stage], dst_a, wp * p.x_pitch + cc * BLOCK_K, w0 + dw, hp, h0 + dh, img);
+            tma_load_5d(&tmap_a, &full_bar[stage], dst_a, wp * p.x_pitch + a_c0, w0 + dw, hp, h0 + dh, img);
           }
           tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb * BLOCK_K, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -524,14 +534,16 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
 bool conv2d_tc_supported(const ConvParams& p, int x_dtype, int out_dtype) {
   if (x_dtype != FB200_F16) return false;
   if (out_dtype != FB200_F16 && out_dtype != FB200_F32) return false;
-  if (p.Cin % 32 != 0 || p.x_pitch % 8 != 0) return false;
+  const int Clog = p.split3 ? p.Cin / 3 : p.Cin;  // channels of one K segment
+  if (Clog % 32 != 0 || p.x_pitch % 8 != 0) return false;
+  if (p.split3 && p.Cin % 3 != 0) return false;
   if ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.w) | reinterpret_cast<uintptr_t>(p.out)) & 15) return false;
   const int oelt = out_dtype == FB200_F16 ? 2 : 4;
   if ((p.out_pitch * oelt) % 16 != 0) return false;
   if (p.res && ((p.res_pitch * oelt) % 16 != 0 || (reinterpret_cast<uintptr_t>(p.res) & 15))) return false;
   if (p.res && p.Cout % (128 / oelt) != 0) return false;  // residual is consumed in whole 128-byte row chunks
   if (p.KH != p.KW) return false;
-  if ((p.act & 15) == FB200_ACT_GELU && (out_dtype != FB200_F16 || p.Cin % 64 != 0)) return false;
+  if ((p.act & 15) == FB200_ACT_GELU && (out_dtype != FB200_F16 || Clog % 64 != 0)) return false;
   if ((p.act & 15) == FB200_ACT_SIGMOID) return false;  // gates are [B, C] vectors: SIMT path
   if ((p.out_bs * oelt) % 16 != 0) return false;
   if (p.stride == 1) return (2 * p.pad == p.KH - 1) || (p.KH == 1 && p.pad == 0);
@@ -544,7 +556,10 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
   KParams kp;
   kp.scale = p.scale; kp.bias = p.bias; kp.res = p.res; kp.res_pitch = p.res_pitch; kp.act = p.act; kp.Cout = p.Cout;
   kp.KH = p.KH; kp.KW = p.KW; kp.pad = p.pad;
-  const int BK = (p.Cin % 64 == 0) ? 64 : 32;
+  const int Clog = p.split3 ? p.Cin / 3 : p.Cin;
+  const int BK = (Clog % 64 == 0) ? 64 : 32;
+  kp.seg_chunks = p.split3 ? Clog / BK : 0;
+  kp.lo_off = Clog;
   const CUtensorMapSwizzle swz = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   kp.cchunks = p.Cin / BK; kp.x_pitch = p.x_pitch;
   kp.stride2 = (p.stride == 2) ? 1 : 0;
@@ -565,7 +580,7 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
   int rc;
   const uint64_t P = (uint64_t)p.x_pitch;
   if (!kp.stride2) {
-    const uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t dims[4] = {(uint64_t)(p.split3 ? 2 * Clog : p.Cin), (uint64_t)W, (uint64_t)H, (uint64_t)B};
     const uint64_t str[4] = {1, P, P * W, P * W * H};
     const uint32_t box[4] = {(uint32_t)BK, (uint32_t)BW, (uint32_t)BH, 1};
     rc = encode(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4, const_cast<void*>(p.x), dims, str, box, "A", swz);

@@ -94,6 +94,26 @@ __global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* 
   }
 }
 
+// fp32 -> [hi | lo] fp16 pair (split-precision operands): hi = fp16(x), lo = fp16(x - hi)
+__global__ void split_f32_pair_kernel(const float* __restrict__ x, int64_t rows, int C, int x_pitch, __half* __restrict__ out) {
+  const int cv = C / 4;
+  const int64_t total = rows * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cv;
+    const int c = (i % cv) * 4;
+    float v[4], hi[4], lo[4];
+    load4(x + r * x_pitch + c, v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __half h = __float2half_rn(v[j]);
+      hi[j] = __half2float(h);
+      lo[j] = v[j] - hi[j];
+    }
+    store4(out + r * 2 * C + c, hi);
+    store4(out + r * 2 * C + C + c, lo);
+  }
+}
+
 static inline unsigned grid_for(int64_t total, int threads) {
   int64_t g = cdiv(total, threads);
   const int64_t cap = 148LL * 32;
@@ -137,5 +157,12 @@ extern "C" int fb200_add(const void* a, const void* b, void* out, int dtype, int
   const int64_t n4 = rows * C / 4, bn4 = brows * C / 4;
   FB_DISPATCH_DTYPE(dtype, T, (add_kernel<T><<<grid_for(n4, 256), 256, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)b, (T*)out, n4, bn4)));
   FB_CHECK_LAUNCH("add");
+  return FB200_OK;
+}
+
+extern "C" int fb200_split_f32_pair(const float* x, int64_t rows, int C, int x_pitch, void* out, void* stream) {
+  FB_CHECK_ARG(x && out && C % 4 == 0 && x_pitch % 4 == 0 && x_pitch >= C, "split_f32_pair: bad arguments");
+  split_f32_pair_kernel<<<grid_for(rows * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(x, rows, C, x_pitch, (__half*)out);
+  FB_CHECK_LAUNCH("split_f32_pair");
   return FB200_OK;
 }

@@ -224,27 +224,70 @@ def aifi_position_embedding(h, w, num_pos_feats=128, temperature=10000.0):
 # --------------------------------------------------------------------------------------------------
 # the fused graph
 # --------------------------------------------------------------------------------------------------
-class _Conv:
-    """Packed conv/linear: weight [Cout,KH,KW,Cin] in activation dtype, fp32 scale/bias (folded BN)."""
+def _split3_weights(w):
+    """fp32 [..., C] -> fp16 [..., 3C] = [W_hi | W_lo | W_hi] (operands of FB200_ALGO_TCGEN05_SPLIT3)."""
+    hi = w.half()
+    lo = (w - hi.float()).half()
+    return torch.cat([hi, lo, hi], dim=-1).contiguous()
 
-    __slots__ = ("w", "scale", "bias", "stride", "pad", "act")
+
+def _split3_ok(x, w3, act, algo):
+    a = (act & 15)
+    return (w3 is not None and algo != ops.ALGO_SIMT and x.dtype == torch.float32 and (x.is_cuda or ops._backend is not None) and a not in (ops.ACT_GELU, 4)
+            and (x.numel() // x.shape[-1]) >= 64)
+
+
+class _Conv:
+    """Packed conv/linear: weight [Cout,KH,KW,Cin] in activation dtype, fp32 scale/bias (folded BN).
+    `w3` (precision="fp32_tc"): the [W_hi|W_lo|W_hi] fp16 triple for the split-precision tensor-core path on fp32 activations."""
+
+    __slots__ = ("w", "scale", "bias", "stride", "pad", "act", "w3")
 
     def __init__(self, w, scale, bias, stride=1, pad=0, act=ops.ACT_NONE):
-        self.w, self.scale, self.bias, self.stride, self.pad, self.act = w, scale, bias, stride, pad, act
+        self.w, self.scale, self.bias, self.stride, self.pad, self.act, self.w3 = w, scale, bias, stride, pad, act, None
+
+    def enable_split3(self):
+        if self.w.dtype == torch.float32 and self.w.shape[-1] % 32 == 0:
+            self.w3 = _split3_weights(self.w)
 
     def __call__(self, x, residual=None, out=None, out_dtype=None, act=None, algo=ops.ALGO_AUTO):
-        return ops.conv2d(x, self.w, self.scale, self.bias, stride=self.stride, pad=self.pad, act=self.act if act is None else act,
-                          residual=residual, out=out, out_dtype=out_dtype, algo=algo)
+        act = self.act if act is None else act
+        if _split3_ok(x, self.w3, act, algo) and (out_dtype in (None, torch.float32)):
+            return ops.conv2d(ops.split_pair(x), self.w3, self.scale, self.bias, stride=self.stride, pad=self.pad, act=act, residual=residual, out=out,
+                              out_dtype=torch.float32, algo=ops.ALGO_TCGEN05_SPLIT3)
+        return ops.conv2d(x, self.w, self.scale, self.bias, stride=self.stride, pad=self.pad, act=act, residual=residual, out=out, out_dtype=out_dtype, algo=algo)
 
 
 class _Linear:
-    __slots__ = ("w", "bias")
+    __slots__ = ("w", "bias", "w3")
 
     def __init__(self, w, bias):
-        self.w, self.bias = w, bias
+        self.w, self.bias, self.w3 = w, bias, None
+
+    def enable_split3(self):
+        if self.w.dtype == torch.float32 and self.w.shape[-1] % 32 == 0:
+            self.w3 = _split3_weights(self.w)
 
     def __call__(self, x, act=ops.ACT_NONE, residual=None, out_dtype=None, out=None, algo=ops.ALGO_AUTO):
+        if _split3_ok(x, self.w3, act, algo) and (out_dtype in (None, torch.float32)) and (out is None or out.shape[-1] % 4 == 0 or True):
+            return ops.linear(ops.split_pair(x), self.w3, self.bias, act=act, residual=residual, out_dtype=torch.float32, out=out, algo=ops.ALGO_TCGEN05_SPLIT3)
         return ops.linear(x, self.w, self.bias, act=act, residual=residual, out_dtype=out_dtype, out=out, algo=algo)
+
+
+def _enable_split3(obj, seen=None):
+    """walk an engine's packed layers (attributes / lists / dicts / tuples) and attach the split-precision weight triples"""
+    seen = set() if seen is None else seen
+    if id(obj) in seen:
+        return
+    seen.add(id(obj))
+    if isinstance(obj, (_Conv, _Linear)):
+        obj.enable_split3()
+    elif isinstance(obj, dict):
+        for v in obj.values():
+            _enable_split3(v, seen)
+    elif isinstance(obj, (list, tuple)):
+        for v in obj:
+            _enable_split3(v, seen)
 
 
 def _bn_fold(sd, p, eps=1e-5):
@@ -256,15 +299,17 @@ class DetrEngine:
     """Packs a FAIDetr state_dict for one (device, precision) and runs the fused forward."""
 
     def __init__(self, sd: Dict[str, torch.Tensor], cfg: DETRConfig, device, precision: str = "fp16", algo: int = ops.ALGO_AUTO):
-        assert precision in ("fp32", "fp16")
+        assert precision in ("fp32", "fp16", "fp32_tc")
         self.cfg, self.device, self.precision, self.algo = cfg, torch.device(device), precision, algo
-        self.dt = torch.float32 if precision == "fp32" else torch.float16
+        self.dt = torch.float16 if precision == "fp16" else torch.float32
         self.depth = cfg.backbone_config.depth
         self.nhead = cfg.transformer_predictor_nhead
         self.d = cfg.transformer_predictor_hidden_dim
         self._consts: Dict[Tuple[int, int], dict] = {}
         sd = {k: v.detach() for k, v in sd.items()}
         self._pack(sd)
+        if precision == "fp32_tc":  # fp32 storage everywhere; convs/linears = three fp16 tensor-core products (fp32-accurate)
+            _enable_split3(vars(self))
 
     # ---- packing -------------------------------------------------------------------------------
     def _to(self, t, dtype=None):
@@ -547,7 +592,7 @@ class FAIDetr(nn.Module):
         return self.pixel_mean.dtype
 
     def set_precision(self, precision: str, algo: int = ops.ALGO_AUTO):
-        assert precision in ("fp32", "fp16")
+        assert precision in ("fp32", "fp16", "fp32_tc")
         self.precision, self.algo, self._engine = precision, algo, None
         return self
 

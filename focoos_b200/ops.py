@@ -24,7 +24,7 @@ import torch
 F32, F16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_SILU, ACT_GELU = 0, 1, 2, 3
 ACT = {None: 0, "none": 0, "relu": 1, "silu": 2, "gelu": 3}
-ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05 = 0, 1, 2
+ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05, ALGO_TCGEN05_SPLIT3 = 0, 1, 2, 3
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libfocoos_b200.so")
 _lib = None
@@ -63,7 +63,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = (
-    "fb200_last_error", "fb200_version", "fb200_device_supports_tcgen05", "fb200_stem_conv3x3s2", "fb200_stem_conv3x3s2_u8", "fb200_conv2d",
+    "fb200_last_error", "fb200_version", "fb200_device_supports_tcgen05", "fb200_stem_conv3x3s2", "fb200_stem_conv3x3s2_u8", "fb200_conv2d", "fb200_split_f32_pair",
     "fb200_maxpool3x3s2", "fb200_avgpool2x2_ceil", "fb200_resize_bilinear", "fb200_add", "fb200_layernorm",
     "fb200_attention", "fb200_msda", "fb200_row_select", "fb200_rowmax", "fb200_topk", "fb200_gather_rows",
     "fb200_box_op", "fb200_detr_postprocess",
@@ -156,6 +156,11 @@ class CudaBackend:
             _trace_note.append(dict(op="conv", B=B, H=H, W=W, Cin=Cin, Cout=Cout, k=KH, stride=stride, res=residual is not None, xdt=str(x.dtype)[6:], odt=str(out.dtype)[6:], algo=algo))
         self._call("fb200_conv2d", _p(x), _dt(x), B, H, W, Cin, _pitch(x), _p(w), KH, KW, stride, pad, _p(scale), _p(bias), _p(residual),
                    0 if residual is None else _pitch(residual), act, _p(out), _dt(out), _pitch(out, True), ctypes.c_int64(_batch_stride(out)), Cout, algo, _stream())
+
+    def split_pair(self, x, out):
+        self._cuda(x, out)
+        C = x.shape[-1]
+        self._call("fb200_split_f32_pair", _p(x), ctypes.c_int64(x.numel() // C), C, _pitch(x), _p(out), _stream())
 
     def maxpool3x3s2(self, x, out):
         self._cuda(x, out)
@@ -264,7 +269,11 @@ def stem_conv(img: torch.Tensor, w, scale, bias, mean: Sequence[float], std: Seq
 def conv2d(x, w, scale=None, bias=None, *, stride=1, pad=0, act=ACT_NONE, residual=None, out=None, out_dtype=None, algo=ALGO_AUTO):
     """NHWC conv with fused per-channel scale/bias (folded BN), residual add and activation.
     w: [Cout,KH,KW,Cin] (same dtype as x).  `out` may be a channel slice of a wider NHWC buffer."""
-    assert x.dim() == 4 and w.dim() == 4 and w.is_contiguous() and w.dtype == x.dtype and w.shape[3] == x.shape[3]
+    assert x.dim() == 4 and w.dim() == 4 and w.is_contiguous() and w.dtype == x.dtype
+    if algo == ALGO_TCGEN05_SPLIT3:  # x = [hi|lo] pair (2C channels), w = [W_hi|W_lo|W_hi] (3C)
+        assert x.dtype == torch.float16 and w.shape[3] * 2 == x.shape[3] * 3
+    else:
+        assert w.shape[3] == x.shape[3]
     B, H, W, _ = x.shape
     Cout, KH, KW, _ = w.shape
     Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
@@ -277,6 +286,15 @@ def conv2d(x, w, scale=None, bias=None, *, stride=1, pad=0, act=ACT_NONE, residu
     return out
 
 
+def split_pair(x):
+    """fp32 [..., C] (rows may be pitched) -> fp16 [..., 2C] = [hi | lo] with hi = fp16(x), lo = fp16(x - hi): operands of the
+    split-precision tensor-core mode (three fp16 products reproduce the fp32 product to ~2^-21)."""
+    assert x.dtype == torch.float32
+    out = torch.empty((*x.shape[:-1], 2 * x.shape[-1]), dtype=torch.float16, device=x.device)
+    _be().split_pair(x, out)
+    return out
+
+
 def linear(x, w, bias=None, *, act=ACT_NONE, residual=None, out=None, out_dtype=None, algo=ALGO_AUTO):
     """y = act(x @ w.T + bias (+ residual)); x [..., K] (rows may be pitched), w [N, K]."""
     lead = x.shape[:-1]
@@ -285,7 +303,7 @@ def linear(x, w, bias=None, *, act=ACT_NONE, residual=None, out=None, out_dtype=
     x4 = x.reshape(1, 1, -1, K) if x.is_contiguous() else _as4(x)
     r4 = None if residual is None else (residual.reshape(1, 1, -1, N) if residual.is_contiguous() else _as4(residual))
     o4 = None if out is None else (out.reshape(1, 1, -1, N) if out.is_contiguous() else _as4(out))
-    y = conv2d(x4, w.reshape(N, 1, 1, K), None, bias, act=act, residual=r4, out=o4, out_dtype=out_dtype, algo=algo)
+    y = conv2d(x4, w.reshape(N, 1, 1, w.shape[-1]), None, bias, act=act, residual=r4, out=o4, out_dtype=out_dtype, algo=algo)
     return out if out is not None else y.reshape(*lead, N)
 
 

@@ -33,7 +33,10 @@ typedef enum { FB200_OK = 0, FB200_ERR_INVALID = -1, FB200_ERR_UNSUPPORTED = -2,
 typedef enum { FB200_F32 = 0, FB200_F16 = 1 } fb200_dtype;
 typedef enum { FB200_ACT_NONE = 0, FB200_ACT_RELU = 1, FB200_ACT_SILU = 2, FB200_ACT_GELU = 3, FB200_ACT_SIGMOID = 4 /* SIMT path only */,
                FB200_ACT_RESIDUAL_AFTER = 16 /* OR-ed flag: out = act(conv) + residual instead of act(conv + residual) */ } fb200_act;
-typedef enum { FB200_ALGO_AUTO = 0, FB200_ALGO_SIMT = 1, FB200_ALGO_TCGEN05 = 2 } fb200_algo;
+typedef enum { FB200_ALGO_AUTO = 0, FB200_ALGO_SIMT = 1, FB200_ALGO_TCGEN05 = 2,
+               /* fp32-accurate products on the fp16 tensor cores: x is the [hi|lo] fp16 pair of an fp32 tensor (fb200_split_f32_pair),
+                * w = [Cout][KH][KW][W_hi|W_lo|W_hi]; computes hi*W_hi + hi*W_lo + lo*W_hi with fp32 accumulation (error ~2^-21). */
+               FB200_ALGO_TCGEN05_SPLIT3 = 3 } fb200_algo;
 
 const char* fb200_last_error(void);
 int fb200_version(void);
@@ -68,6 +71,10 @@ int fb200_stem_conv3x3s2_u8(const uint8_t* img_nhwc, int B, int H, int W, const 
 int fb200_conv2d(const void* x, int x_dtype, int B, int H, int W, int Cin, int x_pitch, const void* w, int KH, int KW,
                  int stride, int pad, const float* scale, const float* bias, const void* residual, int res_pitch,
                  int act, void* out, int out_dtype, int out_pitch, int64_t out_batch_stride, int Cout, int algo, void* stream);
+
+/* x fp32 [rows, C] (row pitch x_pitch) -> out fp16 [rows, 2C]: out[:, :C] = hi = fp16(x), out[:, C:] = lo = fp16(x - hi).
+ * Operand preparation of the split-precision conv/linear mode (precision="fp32_tc"). */
+int fb200_split_f32_pair(const float* x, int64_t rows, int C, int x_pitch, void* out, void* stream);
 
 /* ---- a2: pools.  F.max_pool2d(3,2,1) (nn/backbone/resnet.py:254); AvgPool2d(2,2,0,ceil_mode=True)
  * of the vd shortcut (nn/backbone/resnet.py:95). */

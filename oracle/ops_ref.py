@@ -37,6 +37,10 @@ class RefBackend:
         out.copy_(_act(y, act).permute(0, 2, 3, 1).to(out.dtype))
 
     def conv2d(self, x, w, scale, bias, stride, pad, act, residual, out, algo):
+        if algo == 3:  # split-precision operands: x = [hi|lo], w = [W_hi|W_lo|W_hi] -> the fp32 values they encode
+            C = x.shape[-1] // 2
+            x = x[..., :C].float() + x[..., C:].float()
+            w = w[..., :C].float() + w[..., C:2 * C].float()
         y = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), None, stride, pad)
         if scale is not None:
             y = y * scale.view(1, -1, 1, 1)
@@ -47,6 +51,12 @@ class RefBackend:
         r = 0.0 if residual is None else residual.float()
         y = _act(y, act & 15) + r if post else _act(y + r, act & 15)
         out.copy_(y.to(out.dtype))
+
+    def split_pair(self, x, out):
+        C = x.shape[-1]
+        hi = x.half()
+        out[..., :C] = hi
+        out[..., C:] = (x - hi.float()).half()
 
     def maxpool3x3s2(self, x, out):
         out.copy_(F.max_pool2d(x.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).to(out.dtype))

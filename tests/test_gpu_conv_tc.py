@@ -93,3 +93,27 @@ def test_slices_and_batch_stride():
 def test_conv_cin32_swizzle64(H, W, Cin, Cout, k):
     """Cin % 64 != 0 -> BLOCK_K = 32 variant (64-byte rows, SWIZZLE_64B): the ResNet-vd stem convs."""
     run_case(2, H, W, Cin, Cout, k, 1, act=1, seed=H + Cin + Cout)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,stride,res", [(2, 20, 20, 256, 256, 3, 1, False), (1, 1, 1000, 256, 512, 1, 1, True), (2, 40, 40, 128, 128, 3, 2, False),
+                                                          (2, 32, 32, 32, 64, 3, 1, False), (1, 1, 300, 1024, 256, 1, 1, True)])
+def test_split_precision_conv_matches_fp32(B, H, W, Cin, Cout, k, stride, res):
+    """precision="fp32_tc": fp32 tensors, three fp16 tensor-core products (hi*hi + hi*lo + lo*hi) -> fp32-level agreement."""
+    from focoos_b200.fai_detr import _split3_weights
+
+    x = rnd((B, H, W, Cin), torch.float32, 1, 3.0)
+    w = rnd((Cout, k, k, Cin), torch.float32, 2, 1.0 / math.sqrt(k * k * Cin))
+    bi, sc = rnd((Cout,), torch.float32, 3, 0.2), torch.rand(Cout) + 0.5
+    pad = (k - 1) // 2
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    r = rnd((B, Ho, Wo, Cout), torch.float32, 4) if res else None
+    ref = torch.empty((B, Ho, Wo, Cout), dtype=torch.float32)
+    REF.conv2d(x, w, sc, bi, stride, pad, 1, r, ref, 0)
+    xp = ops.split_pair(x.to(DEV))
+    hi = x.half()
+    assert torch.equal(xp.cpu()[..., :Cin], hi) and torch.equal(xp.cpu()[..., Cin:], (x - hi.float()).half())
+    out = ops.conv2d(xp, _split3_weights(w).to(DEV), sc.to(DEV), bi.to(DEV), stride=stride, pad=pad, act=1, residual=None if r is None else r.to(DEV),
+                     out_dtype=torch.float32, algo=ops.ALGO_TCGEN05_SPLIT3)
+    err = float((out.cpu() - ref).abs().max())
+    scale = max(1.0, float(ref.abs().max()))
+    assert err <= 2e-5 * scale, f"split-precision conv: max|d|={err:.3e} scale={scale:.2e}"

@@ -171,3 +171,26 @@ def test_batch_invariance_and_full_size(sd):
     # the flat index (query*C + label) must point back at the same score
     flat = out32.logits.reshape(32, -1).gather(1, (q.long() * out32.logits.shape[-1] + l.long()))
     assert torch.equal(flat, s)
+
+
+def test_fp32_tc_meets_the_parity_bars(sd):
+    """precision="fp32_tc" (fp32 storage, split-precision tensor-core convs/linears): same bars as the fp32 SIMT mode."""
+    g = load_golden("detr_l_obj365_b2_640")
+    m = _model(sd, "fp32_tc")
+    proc = DETRProcessor(m.config, image_size=640)
+    imgs = synth_images(1, [(640, 640)] * 2)
+    x, _ = proc.preprocess(imgs, device=m.device)
+    taps = {}
+    out = m(x, taps=taps)
+    torch.cuda.synchronize()
+    keys = taps["topk_ind"].cpu().numpy()
+    assert _set_stats(g["enc_topk_ind"], keys) == [300, 300], "encoder query SETS must be identical"
+    ds, db = compare_queries(g["scores"], g["boxes"], g["enc_topk_ind"], out.logits.cpu().numpy(), out.boxes.cpu().numpy(), keys)
+    _report("fp32_tc_vs_reference_golden", {"scores_max_abs": ds, "boxes_max_abs": db})
+    assert ds < 1e-3 and db < 1e-3, (ds, db)
+    dets = proc.postprocess(out, imgs, threshold=0.5)
+    for i, d in enumerate(dets):
+        n = int(g["det_count"][i])
+        assert len(d) == n
+        assert sorted(x.cls_id for x in d.detections) == sorted(g["det_labels"][i, :n].tolist())
+        assert sorted(tuple(x.bbox) for x in d.detections) == sorted(map(tuple, g["det_boxes"][i, :n].tolist()))
