@@ -115,6 +115,55 @@ def cpu_reference_run(batch: int, steps: int, warmup: int, sd, threads: int):
     return batch / float(np.mean(times)), float(np.mean(times)) * 1e3
 
 
+def _graphed(step, use_graph):
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    if not use_graph:
+        return step
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        step()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        step()
+    return g.replay
+
+
+def _throughput_ms(step, use_graph, steps):
+    run = _graphed(step, use_graph)
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def _latency(step, use_graph, warm=20, iters=100):
+    run = _graphed(step, use_graph)
+    for _ in range(warm):
+        run()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run()
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return {"batch": 1, "p50_ms": ts[len(ts) // 2], "p90_ms": ts[int(len(ts) * 0.9)], "iters": iters, "warmup": warm, "what": "forward + on-device post-process of one 640x640 image, device-timed per iteration"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -125,6 +174,7 @@ def main():
     ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32", "fp32_tc"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="skip the bs=1 latency and parity-mode legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -234,6 +284,32 @@ def main():
     e2e = {"value": B * world / (e2e_ms / 1e3), "unit": "images/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(host_u8.numel()) + B * 8,
            "d2h_bytes_per_step": B * (300 * 7 + 1) * 4, "api": "FocoosModel.__call__(pinned uint8 [B,H,W,3], batched=True)"}
 
+    # ---- bs=1 latency (BASELINE.json metric, second half): p50/p90 of single-image forward+post-process, CUDA graph replay, device-timed
+    lat = None
+    par = None
+    if rank == 0 and not args.quick:
+        x1, s1 = x_dev[:1].contiguous(), sizes_dev[:1].contiguous()
+
+        def step1():
+            o = fm.model(x1)
+            return ops.detr_postprocess(o.logits, o.boxes, s1, 300, 0.5)
+
+        lat = _latency(step1, not args.no_graph)
+        # ---- the parity-exact tensor-core mode (fp32 storage, 3 fp16 tcgen05 products per conv/linear) on the same workload
+        if args.precision == "fp16":
+            m2 = FAIDetr(DETRConfig(), precision="fp32_tc")
+            m2.load_state_dict(sd, strict=True)
+            m2.to(dev)
+
+            def step2():
+                o = m2(x_dev)
+                return ops.detr_postprocess(o.logits, o.boxes, sizes_dev, 300, 0.5)
+
+            ms2 = _throughput_ms(step2, not args.no_graph, max(5, args.steps // 5))
+            par = {"precision": "fp32_tc", "value": B / (ms2 / 1e3), "unit": "images/s", "ms_per_step": ms2, "n_gpus": 1,
+                   "note": "meets the 1e-3 / identical keep-set bars against the reference golden (tests/test_gpu_e2e.py::test_fp32_tc_meets_the_parity_bars); the fp16 headline mode is within 3e-3 on boxes"}
+            del m2
+
     # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv), heaviest layer shape timed alone: FPN 3x3 256->256 @80x80
     peaks = measured_peaks()
     roof = None
@@ -269,7 +345,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"fp16": "f16", "fp32": "f32", "fp32_tc": "f32 (3x f16 tensor-core products)"}[args.precision], "data": "synthetic",
                 "config": config, "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
-                "cuda_graph": graph is not None, "roofline": roof, "cpu_baseline": cpu, "detections_img0": len(dets[0])}
+                "cuda_graph": graph is not None, "latency_bs1": lat, "parity_mode": par, "roofline": roof, "cpu_baseline": cpu, "detections_img0": len(dets[0])}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

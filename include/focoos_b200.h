@@ -190,6 +190,28 @@ int fb200_mask_argmax(const float* masks, const float* scores, int B, int Q, int
 /* kept one-hot masks -> original image size + boxes: pair i = (b,q): (labels[b] == q) -> bilinear resize -> != 0 (processor.py:275-283). */
 int fb200_label_resize_bbox(const uint8_t* labels, int H, int W, const int* bq, int n, uint8_t* out, int Ho, int Wo, int* bbox, void* stream);
 
+/* ---- training criterion ---------------------------------------------------------------------
+ * Replaces BoxHungarianMatcher.forward (focoos/models/fai_detr/modelling.py:693-758) and SetCriterion.forward with
+ * loss_labels_vfl / loss_boxes (:464-531, :553-612) for all L supervised layers at once.
+ * logits [L,B,Q,C] f32 raw, boxes [L,B,Q,4] f32 cxcywh; targets concatenated over the batch: tgt_labels [T] i32,
+ * tgt_boxes [T,4] f32 cxcywh, tgt_offsets [B+1] i32 (prefix sums of per-image target counts). */
+
+/* cost[l][t][q] = w_bbox*L1 + w_class*(focal pos - neg) + w_giou*(-GIoU) for every target t against the Q queries of
+ * its own image (the diagonal blocks the reference keeps after C.split, :744-747).  cost: [L,T,Q] f32. */
+int fb200_detr_match_cost(const float* logits, const float* boxes, const int* tgt_labels, const float* tgt_boxes, const int* tgt_offsets,
+                          int L, int B, int Q, int C, int T, float w_class, float w_bbox, float w_giou, float alpha, float gamma,
+                          float* cost, void* stream);
+/* Linear-sum assignment per (layer, image) on the device (replaces scipy.optimize.linear_sum_assignment, :747).
+ * match_q [L,T] i32: the query assigned to each target (-1 only if the costs were not finite).  Needs n_b <= Q. */
+int fb200_hungarian(const float* cost, const int* tgt_offsets, int L, int B, int Q, int T, int max_targets, int* match_q, void* stream);
+int64_t fb200_detr_loss_workspace_bytes(int L, int B, int Q);
+/* losses [L,3] = {w_vfl*loss_vfl, w_bbox*loss_bbox, w_giou*loss_giou}; gradients of those weighted losses:
+ * grad_logits [L,B,Q,C] (d loss_vfl), grad_boxes_l1 / grad_boxes_giou [L,B,Q,4] (d loss_bbox, d loss_giou w.r.t. cxcywh). */
+int fb200_detr_loss(const float* logits, const float* boxes, const int* tgt_labels, const float* tgt_boxes, const int* tgt_offsets,
+                    const int* match_q, int L, int B, int Q, int C, int T, float num_boxes, float w_vfl, float w_bbox, float w_giou,
+                    float alpha, float gamma, float* losses, float* grad_logits, float* grad_boxes_l1, float* grad_boxes_giou,
+                    void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

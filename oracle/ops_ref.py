@@ -265,3 +265,45 @@ def _ref_label_resize_bbox(self, labels, bq, out_masks, out_bbox):
 for _n, _f in (("dwconv3x3s2", _ref_dwconv3x3s2), ("avgpool3x3s2", _ref_avgpool3x3s2), ("global_avgpool", _ref_global_avgpool), ("channel_scale", _ref_channel_scale),
                ("mask_argmax", _ref_mask_argmax), ("label_resize_bbox", _ref_label_resize_bbox)):
     setattr(RefBackend, _n, _f)
+
+
+# ---- training criterion (tests of focoos_b200/criterion.py's host logic on the CPU) ------------------------------
+def _rb_detr_match_cost(self, logits, boxes, tl, tb, toff, wts, alpha, gamma, cost):
+    from oracle import criterion_oracle as CO
+    L, B, Q, C = logits.shape
+    for l in range(L):
+        for b in range(B):
+            t0, t1 = int(toff[b]), int(toff[b + 1])
+            if t1 > t0:
+                cost[l, t0:t1] = CO.match_cost(logits[l, b], boxes[l, b], tl[t0:t1].long(), tb[t0:t1], wts[0], wts[1], wts[2], alpha, gamma).T
+
+
+def _rb_hungarian(self, cost, toff, B, max_targets, match_q):
+    from scipy.optimize import linear_sum_assignment
+    for l in range(cost.shape[0]):
+        for b in range(B):
+            t0, t1 = int(toff[b]), int(toff[b + 1])
+            if t1 > t0:
+                r, c = linear_sum_assignment(cost[l, t0:t1].numpy())
+                match_q[l, t0 + torch.as_tensor(r)] = torch.as_tensor(c, dtype=torch.int32)
+
+
+def _rb_detr_loss(self, logits, boxes, tl, tb, toff, match_q, num_boxes, wts, alpha, gamma, losses, g_logits, g_l1, g_giou):
+    from oracle import criterion_oracle as CO
+    L, B, Q, C = logits.shape
+    has = tl is not None
+    targets = [(tl[int(toff[b]):int(toff[b + 1])].long(), tb[int(toff[b]):int(toff[b + 1])]) if has else (torch.zeros(0, dtype=torch.long), torch.zeros((0, 4))) for b in range(B)]
+    with torch.enable_grad():
+        for l in range(L):
+            lg = logits[l].detach().clone().requires_grad_(True)
+            bx = boxes[l].detach().clone().requires_grad_(True)
+            idx = [(match_q[l, int(toff[b]):int(toff[b + 1])].long() if has else torch.zeros(0, dtype=torch.long), torch.arange(len(targets[b][0]))) for b in range(B)]
+            v, b1, gi = CO.layer_losses(lg, bx, targets, idx, num_boxes, alpha, gamma, wts)
+            losses[l] = torch.stack([v, b1, gi]).detach()
+            g_logits[l] = torch.autograd.grad(v, lg, retain_graph=True)[0]
+            g_l1[l] = torch.autograd.grad(b1, bx, retain_graph=True)[0] if has else 0
+            g_giou[l] = torch.autograd.grad(gi, bx)[0] if has else 0
+
+
+for _n, _f in (("detr_match_cost", _rb_detr_match_cost), ("hungarian", _rb_hungarian), ("detr_loss", _rb_detr_loss)):
+    setattr(RefBackend, _n, _f)

@@ -7,6 +7,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gp
 for s in $STAGES; do
   case $s in
     ops)   timeout 900 python -m pytest tests/test_gpu_ops.py -q -m gpu -x 2>&1 | tail -40 > gpurun_out/t_ops.log ;;
+    crit)  timeout 900 python -m pytest tests/test_gpu_criterion.py -q -m gpu 2>&1 | tail -60 > gpurun_out/t_crit.log ;;
     tc)    timeout 900 python -m pytest tests/test_gpu_conv_tc.py -q -m gpu 2>&1 | tail -80 > gpurun_out/t_tc.log ;;
     e2e)   timeout 1200 python -m pytest tests/test_gpu_e2e.py -q -m gpu 2>&1 | tail -60 > gpurun_out/t_e2e.log ;;
     smoke) timeout 600 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1 ;;
@@ -21,6 +22,7 @@ for s in $STAGES; do
     bisebench) timeout 900 python tools/bench_bisenet.py > gpurun_out/bench_bisenet.txt 2>&1 ;;
     ref)   timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2>&1 ;;
     ncu_list) timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -s 940 -c 240 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1 ;;
+    list_*) P=${s#list_}; timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_$P.csv python tools/profile_step.py $P > gpurun_out/ncu_list_$P.log 2>&1 ;;
     ncu_full) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 2 -c 8 -o gpurun_out/prof_conv_tc python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1 ;;
   esac
   echo "stage $s exit $?" >> gpurun_out/stages.txt
