@@ -581,6 +581,9 @@ class FAIDetr(nn.Module):
         self.precision = precision
         self.algo = ops.ALGO_AUTO
         self._engine: Optional[DetrEngine] = None
+        from .train_step import freeze_backbone_norm
+        if getattr(c.backbone_config, "freeze_norm", False):  # resnet.py:226 (the registry configs ship freeze_norm=false)
+            freeze_backbone_norm(self)
         self.eval()
 
     @property
@@ -590,6 +593,10 @@ class FAIDetr(nn.Module):
     @property
     def dtype(self):
         return self.pixel_mean.dtype
+
+    def train(self, mode: bool = True):
+        self._engine = None  # packed (BN-folded, re-parameterised) weights are rebuilt from the parameters at the next eval forward
+        return super().train(mode)
 
     def set_precision(self, precision: str, algo: int = ops.ALGO_AUTO):
         assert precision in ("fp32", "fp16", "fp32_tc")

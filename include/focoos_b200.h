@@ -212,6 +212,31 @@ int fb200_detr_loss(const float* logits, const float* boxes, const int* tgt_labe
                     float alpha, float gamma, float* losses, float* grad_logits, float* grad_boxes_l1, float* grad_boxes_giou,
                     void* workspace, void* stream);
 
+/* ---- optimiser step of the fine-tune loop -------------------------------------------------------
+ * Replaces, on one flat fp32 buffer of all trainable parameters (each tensor padded to a multiple of 4 elements):
+ * GradScaler.unscale_/step/update + clip_grad_norm_ x2 + AdamW.step with per-tensor lr / weight decay
+ * (focoos/trainer/trainer.py:757-773,782-794; focoos/trainer/solver/build.py:29-37,40-138).
+ * Control block `ctrl`: 16 x 4-byte words in device memory, never read by the host on the step path: */
+#define FB200_CTRL_SCALE 0          /* f32 loss scale (GradScaler init 2^10, trainer.py:645) */
+#define FB200_CTRL_GROWTH_TRACKER 1 /* i32 consecutive finite steps */
+#define FB200_CTRL_FOUND_INF 2      /* i32 1 = this step's gradients were not finite -> adamw_step is a no-op */
+#define FB200_CTRL_GRAD_NORM 3      /* f32 global L2 norm of the unscaled, world-averaged gradient (before clipping) */
+#define FB200_CTRL_GMUL 4           /* f32 multiplier adamw_step applies to the raw gradient buffer: clip / (scale * world) */
+#define FB200_CTRL_STEP 5           /* i32 number of optimiser steps taken (skipped steps do not count) */
+#define FB200_CTRL_BC1 6            /* f32 1 - beta1^step */
+#define FB200_CTRL_BC2_SQRT 7       /* f32 sqrt(1 - beta2^step) */
+#define FB200_CTRL_CLIP_COEF 8      /* f32 product of the clip coefficients */
+int64_t fb200_optim_workspace_bytes(void);
+/* sum of squares + non-finite flag of the flat gradient buffer (per-block partials, reduced in a fixed order) */
+int fb200_grad_stats(const float* grads, int64_t n, void* workspace, void* stream);
+/* one thread: norm, `clip_passes` successive clip_grad_norm_(max_norm) coefficients, loss-scale update, bias corrections */
+int fb200_optim_finalize(const void* workspace, float* ctrl, float max_norm, int clip_passes, float inv_world, int use_scaler, float growth,
+                         float backoff, int growth_interval, float beta1, float beta2, void* stream);
+/* AdamW over chunks (chunk c covers [chunk_start[c], +chunk_len[c]) of tensor chunk_seg[c]; lr = seg_lr[seg]*lr_factor) */
+int fb200_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const int64_t* chunk_start, const int* chunk_len,
+                     const int* chunk_seg, int nchunks, const float* seg_lr, const float* seg_wd, float lr_factor, float beta1, float beta2,
+                     float eps, const float* ctrl, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

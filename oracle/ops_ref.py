@@ -307,3 +307,59 @@ def _rb_detr_loss(self, logits, boxes, tl, tb, toff, match_q, num_boxes, wts, al
 
 for _n, _f in (("detr_match_cost", _rb_detr_match_cost), ("hungarian", _rb_hungarian), ("detr_loss", _rb_detr_loss)):
     setattr(RefBackend, _n, _f)
+
+
+# ---- optimiser step (tests of focoos_b200/train_step.py's host logic on the CPU; same control-block layout) ---------
+def _rb_optim_workspace(self, device):
+    return torch.zeros(4, dtype=torch.float64)
+
+
+def _rb_grad_stats(self, grads, ws):
+    ws[0] = float((grads.double() ** 2).sum())
+    ws[1] = 0.0 if bool(torch.isfinite(grads).all()) else 1.0
+
+
+def _rb_optim_finalize(self, ws, ctrl, max_norm, clip_passes, inv_world, use_scaler, growth, backoff, growth_interval, beta1, beta2):
+    ic = ctrl.view(torch.int32)
+    scale = float(ctrl[0]) if use_scaler else 1.0
+    pre = inv_world / scale
+    norm = math.sqrt(float(ws[0])) * pre if math.isfinite(float(ws[0])) else float("inf")
+    bad = int(ws[1] != 0 or not math.isfinite(norm))
+    coef, nrm = 1.0, norm
+    for _ in range(clip_passes if max_norm > 0 else 0):
+        c = min(max_norm / (nrm + 1e-6), 1.0) if math.isfinite(nrm) else 0.0
+        coef *= c
+        nrm *= c
+    ic[2] = bad
+    ctrl[3], ctrl[4], ctrl[8] = norm, pre * coef, coef
+    if not bad:
+        ic[5] += 1
+        ctrl[6] = 1.0 - beta1 ** int(ic[5])
+        ctrl[7] = math.sqrt(1.0 - beta2 ** int(ic[5]))
+    if use_scaler:
+        if bad:
+            ctrl[0] = scale * backoff
+            ic[1] = 0
+        elif int(ic[1]) + 1 == growth_interval:
+            ctrl[0] = scale * growth
+            ic[1] = 0
+        else:
+            ic[1] += 1
+
+
+def _rb_adamw_step(self, params, grads, m, v, chunk_start, chunk_len, chunk_seg, seg_lr, seg_wd, lr_factor, beta1, beta2, eps, ctrl):
+    if int(ctrl.view(torch.int32)[2]):
+        return
+    gmul, bc1, bc2s = float(ctrl[4]), float(ctrl[6]), float(ctrl[7])
+    for s0, ln, sg in zip(chunk_start.tolist(), chunk_len.tolist(), chunk_seg.tolist()):
+        sl = slice(s0, s0 + ln)
+        lr, wd = float(seg_lr[sg]) * lr_factor, float(seg_wd[sg])
+        g = grads[sl] * gmul
+        params[sl] *= 1.0 - lr * wd
+        m[sl] = m[sl] + (g - m[sl]) * (1.0 - beta1)
+        v[sl] = v[sl] * beta2 + (1.0 - beta2) * (g * g)
+        params[sl] -= (lr / bc1) * (m[sl] / (v[sl].sqrt() / bc2s + eps))
+
+
+for _n, _f in (("optim_workspace", _rb_optim_workspace), ("grad_stats", _rb_grad_stats), ("optim_finalize", _rb_optim_finalize), ("adamw_step", _rb_adamw_step)):
+    setattr(RefBackend, _n, _f)
