@@ -1,0 +1,516 @@
+// Backward / training-mode kernels of the convolutional part of the path (what autograd runs for
+// ConvNormLayer, BottleNeck, RepVggBlock, the pools and F.interpolate when the reference fine-tunes, trainer.py:757).
+// fp32 throughout (the reference's CPU training path is fp32; its CUDA path is fp16 autocast with fp32 master weights).
+//
+//   conv weight gradient   dW[co,kh,kw,ci] = sum_p dY[p,co] * X[pix(p,kh,kw),ci]      (aten conv backward, weight)
+//   conv data gradient     = forward conv of dY (zero-dilated for stride 2) with flipped/transposed weights - host side
+//   BatchNorm2d, training  batch statistics (biased var for normalisation, unbiased for running_var), fused +residual, ReLU/SiLU
+//   column sums            bias gradients, LayerNorm parameter gradients
+//   pools / resize         adjoint of max_pool2d(3,2,1), AvgPool2d(2,2,ceil), F.interpolate(bilinear, align_corners=False)
+//
+// All reductions are two-phase with a fixed summation order (per-block partials, then one pass in double) => reproducible.
+#include "common.cuh"
+
+namespace fb200 {
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------------
+// conv weight gradient: C[M=Cout, N=Cin] per filter tap, K = output pixels; both operands are "K-outer" in NHWC, so
+// 16-pixel x 64-channel tiles of dY and X load coalesced; 256 threads, 4x4 micro-tiles; split-K over gridDim.z.
+constexpr int WG_TM = 64, WG_TN = 64, WG_TK = 16;
+
+__global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict__ x, int x_pitch, const float* __restrict__ dy, int dy_pitch, int B, int H,
+                                                         int W, int Cin, int Ho, int Wo, int Cout, int KH, int KW, int stride, int pad, int64_t pix_per_split,
+                                                         float* __restrict__ part) {
+  __shared__ float sA[WG_TK][WG_TM + 4];  // dY tile  [k][co]
+  __shared__ float sB[WG_TK][WG_TN + 4];  // X tile   [k][ci]
+  const int tiles_n = (Cin + WG_TN - 1) / WG_TN;
+  const int m0 = (blockIdx.x / tiles_n) * WG_TM, n0 = (blockIdx.x % tiles_n) * WG_TN;
+  const int kh = blockIdx.y / KW, kw = blockIdx.y % KW;
+  const int64_t P = (int64_t)B * Ho * Wo;
+  const int64_t p_begin = (int64_t)blockIdx.z * pix_per_split, p_end = min(P, p_begin + pix_per_split);
+  const int tid = threadIdx.x, tr = tid >> 4, tc = (tid & 15) * 4;  // loader: row tr (0..15), 4 channels at tc
+  const int ty = tid >> 4, tx = tid & 15;                             // compute: rows ty*4.., cols tx*4..
+  float acc[4][4] = {};
+  for (int64_t p0 = p_begin; p0 < p_end; p0 += WG_TK) {
+    const int64_t p = p0 + tr;
+    float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p < p_end) {
+      const int wo = p % Wo, ho = (p / Wo) % Ho, bi = p / ((int64_t)Wo * Ho);
+      const float* dyp = dy + p * dy_pitch + m0 + tc;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (m0 + tc + j < Cout) a[j] = dyp[j];
+      const int hi = ho * stride + kh - pad, wi = wo * stride + kw - pad;
+      if (hi >= 0 && hi < H && wi >= 0 && wi < W) {
+        const float* xp = x + (((int64_t)bi * H + hi) * W + wi) * x_pitch + n0 + tc;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (n0 + tc + j < Cin) b[j] = xp[j];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { sA[tr][tc + j] = a[j]; sB[tr][tc + j] = b[j]; }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < WG_TK; ++k) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { av[i] = sA[k][ty * 4 + i]; bv[i] = sB[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+  }
+  float* out = part + (int64_t)blockIdx.z * Cout * KH * KW * Cin;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int co = m0 + ty * 4 + i;
+    if (co >= Cout) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ci = n0 + tx * 4 + j;
+      if (ci < Cin) out[(((int64_t)co * KH + kh) * KW + kw) * Cin + ci] = acc[i][j];
+    }
+  }
+}
+
+__global__ void split_reduce_kernel(const float* __restrict__ part, int splits, int64_t n, float* __restrict__ out, int accumulate) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int k = 0; k < splits; ++k) s += (double)part[(int64_t)k * n + i];
+  out[i] = accumulate ? out[i] + (float)s : (float)s;
+}
+
+// out[b,h,w,:] = (h,w both even and inside) ? dy[b,h/2,w/2,:] : 0     (zero-dilation for the stride-2 data gradient)
+__global__ void dilate2_kernel(const float* __restrict__ dy, int B, int Ho, int Wo, int C, int Hd, int Wd, float* __restrict__ out) {
+  const int cv = C / 4;
+  const int64_t total = (int64_t)B * Hd * Wd * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (i % cv) * 4;
+    const int64_t pix = i / cv;
+    const int w = pix % Wd, h = (pix / Wd) % Hd, b = pix / ((int64_t)Wd * Hd);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!(h & 1) && !(w & 1) && (h >> 1) < Ho && (w >> 1) < Wo) v = *reinterpret_cast<const float4*>(dy + (((int64_t)b * Ho + (h >> 1)) * Wo + (w >> 1)) * C + c);
+    *reinterpret_cast<float4*>(out + pix * C + c) = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// column reductions over [R, C] (row pitch).  MODE 0: sum x   1: sum (x-mean)^2   2: BN backward (sum g, sum g*xhat)
+// partial[blockIdx.y][c] per row-slice; 32 channels x 8 row lanes per block.
+constexpr int CR_ROWS = 296;  // row slices (2 x 148 SMs)
+
+__device__ __forceinline__ float act_grad(int act, float z, float y) {
+  if (act == FB200_ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  if (act == FB200_ACT_SILU) { const float s = 1.f / (1.f + expf(-z)); return s * (1.f + z * (1.f - s)); }
+  if (act == FB200_ACT_GELU) { return 0.5f * (1.f + erff(z * 0.70710678118654752f)) + z * 0.3989422804014327f * expf(-0.5f * z * z); }
+  return 1.f;
+}
+__device__ __forceinline__ float act_fwd(int act, float z) {
+  if (act == FB200_ACT_RELU) return fmaxf(z, 0.f);
+  if (act == FB200_ACT_SILU) return z / (1.f + expf(-z));
+  if (act == FB200_ACT_GELU) return 0.5f * z * (1.f + erff(z * 0.70710678118654752f));
+  return z;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) col_partial_kernel(const float* __restrict__ x, int x_pitch, int64_t R, int C, const float* __restrict__ mean,
+                                                          const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          const float* __restrict__ dy, int dy_pitch, const float* __restrict__ y, int y_pitch, int act,
+                                                          float* __restrict__ p0, float* __restrict__ p1) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int lane_r = threadIdx.x >> 5;  // 0..7
+  float s0 = 0.f, s1 = 0.f;
+  if (c < C) {
+    const float mu = (MODE >= 1) ? mean[c] : 0.f;
+    const float rs = (MODE == 2) ? rstd[c] : 0.f;
+    const float ga = (MODE == 2) ? gamma[c] : 0.f, be = (MODE == 2) ? beta[c] : 0.f;
+    for (int64_t r = (int64_t)blockIdx.y * 8 + lane_r; r < R; r += (int64_t)gridDim.y * 8) {
+      const float v = x[r * x_pitch + c];
+      if (MODE == 0) s0 += v;
+      else if (MODE == 1) { const float d = v - mu; s0 += d * d; }
+      else {
+        const float xh = (v - mu) * rs;
+        float g = dy[r * dy_pitch + c];
+        if (act != FB200_ACT_NONE) g *= act_grad(act, xh * ga + be, y[r * y_pitch + c]);
+        s0 += g;
+        s1 += g * xh;
+      }
+    }
+  }
+  __shared__ float r0[8][33], r1[8][33];
+  r0[lane_r][threadIdx.x & 31] = s0;
+  r1[lane_r][threadIdx.x & 31] = s1;
+  __syncthreads();
+  if (lane_r == 0 && c < C) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a += r0[k][threadIdx.x]; b += r1[k][threadIdx.x]; }
+    p0[(int64_t)blockIdx.y * C + c] = a;
+    if (MODE == 2) p1[(int64_t)blockIdx.y * C + c] = b;
+  }
+}
+
+// FIN 0: out0 = sum                       (colsum)
+// FIN 1: out0 = mean = sum / R            (BN pass 1)
+// FIN 2: out0 = rstd from sum of squared deviations; running stats update (BN pass 2)
+// FIN 3: out0 = dbeta = sum p0, out1 = dgamma = sum p1 (BN backward)
+template <int FIN>
+__global__ void col_finalize_kernel(const float* __restrict__ p0, const float* __restrict__ p1, int nparts, int C, double R, float eps, float momentum,
+                                    const float* __restrict__ mean, float* __restrict__ run_mean, float* __restrict__ run_var, float* __restrict__ out0,
+                                    float* __restrict__ out1, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double a = 0.0, b = 0.0;
+  for (int k = 0; k < nparts; ++k) {
+    a += (double)p0[(int64_t)k * C + c];
+    if (FIN == 3) b += (double)p1[(int64_t)k * C + c];
+  }
+  if (FIN == 0) out0[c] = accumulate ? out0[c] + (float)a : (float)a;
+  if (FIN == 1) out0[c] = (float)(a / R);
+  if (FIN == 2) {
+    const double var = a / R;
+    out0[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (run_mean) {
+      run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * mean[c];
+      run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)(R > 1.0 ? a / (R - 1.0) : var);
+    }
+  }
+  if (FIN == 3) {
+    out0[c] = accumulate ? out0[c] + (float)a : (float)a;
+    out1[c] = accumulate ? out1[c] + (float)b : (float)b;
+  }
+}
+
+// y = act((x - mean) * rstd * gamma + beta + res)
+__global__ void bn_apply_kernel(const float* __restrict__ x, int x_pitch, const float* __restrict__ res, int res_pitch, int64_t R, int C,
+                                const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                int act, float* __restrict__ y, int y_pitch) {
+  const int cv = C / 4;
+  const int64_t total = R * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cv;
+    const int c = (i % cv) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(x + r * x_pitch + c);
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c), rs = *reinterpret_cast<const float4*>(rstd + c);
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+    float4 z = make_float4((v.x - mu.x) * rs.x * ga.x + be.x, (v.y - mu.y) * rs.y * ga.y + be.y, (v.z - mu.z) * rs.z * ga.z + be.z, (v.w - mu.w) * rs.w * ga.w + be.w);
+    if (res) {
+      const float4 q = *reinterpret_cast<const float4*>(res + r * res_pitch + c);
+      z.x += q.x; z.y += q.y; z.z += q.z; z.w += q.w;
+    }
+    *reinterpret_cast<float4*>(y + r * y_pitch + c) = make_float4(act_fwd(act, z.x), act_fwd(act, z.y), act_fwd(act, z.z), act_fwd(act, z.w));
+  }
+}
+
+// dx = gamma * rstd * (g - dbeta/R - xhat * dgamma/R),  g = dy * act'(.);  dres = g
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ x, int x_pitch, const float* __restrict__ dy, int dy_pitch, const float* __restrict__ y, int y_pitch,
+                                    int64_t R, int C, const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, const float* __restrict__ dgamma, const float* __restrict__ dbeta, int act, float inv_R,
+                                    float* __restrict__ dx, int dx_pitch, float* __restrict__ dres, int dres_pitch) {
+  const int64_t total = R * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / C;
+    const int c = i % C;
+    const float xh = (x[r * x_pitch + c] - mean[c]) * rstd[c];
+    float g = dy[r * dy_pitch + c];
+    if (act != FB200_ACT_NONE) g *= act_grad(act, xh * gamma[c] + beta[c], y[r * y_pitch + c]);
+    dx[r * dx_pitch + c] = gamma[c] * rstd[c] * (g - dbeta[c] * inv_R - xh * dgamma[c] * inv_R);
+    if (dres) dres[r * dres_pitch + c] = g;
+  }
+}
+
+// out = act(a + b) ; backward: da = db = dy * act'(a + b)
+__global__ void add_act_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ dy, int act, int64_t n, float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float z = a[i] + (b ? b[i] : 0.f);
+    out[i] = dy ? dy[i] * act_grad(act, z, act_fwd(act, z)) : act_fwd(act, z);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// max_pool2d(3, 2, 1) backward: each input pixel collects from the <=4 windows that contain it where it is the FIRST maximum
+// (row-major scan order, the tie rule of aten's max_pool2d_with_indices).
+__global__ void maxpool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, int B, int H, int W, int C, int Ho, int Wo, float* __restrict__ dx) {
+  const int64_t total = (int64_t)B * H * W * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = i % C;
+    const int64_t pix = i / C;
+    const int w = pix % W, h = (pix / W) % H, b = pix / ((int64_t)W * H);
+    const float* xb = x + (int64_t)b * H * W * C + c;
+    float acc = 0.f;
+    for (int ho = (h + 1 - 2 + 1) / 2; ho <= (h + 1) / 2 && ho < Ho; ++ho) {   // windows rows: 2*ho-1 <= h <= 2*ho+1
+      if (ho < 0) continue;
+      for (int wo = (w + 1 - 2 + 1) / 2; wo <= (w + 1) / 2 && wo < Wo; ++wo) {
+        if (wo < 0) continue;
+        float best = -INFINITY;
+        int bh = -1, bw = -1;
+        for (int dh = 0; dh < 3; ++dh) {
+          const int hh = 2 * ho - 1 + dh;
+          if (hh < 0 || hh >= H) continue;
+          for (int dw = 0; dw < 3; ++dw) {
+            const int ww = 2 * wo - 1 + dw;
+            if (ww < 0 || ww >= W) continue;
+            const float v = xb[((int64_t)hh * W + ww) * C];
+            if (v > best || isnan(v)) { if (!(best != best)) { best = v; bh = hh; bw = ww; } }
+          }
+        }
+        if (bh == h && bw == w) acc += dy[(((int64_t)b * Ho + ho) * Wo + wo) * C + c];
+      }
+    }
+    dx[i] = acc;
+  }
+}
+
+// AvgPool2d(2, 2, 0, ceil_mode=True) backward (divisor = number of in-bounds elements, as count_include_pad only affects padding)
+__global__ void avgpool_bwd_kernel(const float* __restrict__ dy, int B, int H, int W, int C, int Ho, int Wo, float* __restrict__ dx) {
+  const int64_t total = (int64_t)B * H * W * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = i % C;
+    const int64_t pix = i / C;
+    const int w = pix % W, h = (pix / W) % H, b = pix / ((int64_t)W * H);
+    const int ho = h >> 1, wo = w >> 1;
+    const int nh = min(2, H - 2 * ho), nw = min(2, W - 2 * wo);
+    dx[i] = dy[(((int64_t)b * Ho + ho) * Wo + wo) * C + c] / (float)(nh * nw);
+  }
+}
+
+// bilinear (align_corners=False) backward as a GATHER over the input grid: dx[h,w] = sum over output pixels whose 2x2 footprint
+// touches (h,w) of weight * dy.  For every output row only two source rows have non-zero weight, so we invert the map by scanning the
+// output rows/cols that can reference h / w (bounded by ceil(scale)+1 each side).
+__global__ void resize_bwd_kernel(const float* __restrict__ dy, int dy_pitch, int B, int H, int W, int C, int Ho, int Wo, float* __restrict__ dx) {
+  const float sh = (float)H / Ho, sw = (float)W / Wo;
+  const int64_t total = (int64_t)B * H * W * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = i % C;
+    const int64_t pix = i / C;
+    const int w = pix % W, h = (pix / W) % H, b = pix / ((int64_t)W * H);
+    // candidate output rows: source coordinate (ho+0.5)*sh-0.5 in (h-1, h+1) (plus clamping at the borders)
+    int ho_lo = (int)floorf((h - 1 + 0.5f) / sh - 0.5f), ho_hi = (int)ceilf((h + 1 + 0.5f) / sh - 0.5f);
+    int wo_lo = (int)floorf((w - 1 + 0.5f) / sw - 0.5f), wo_hi = (int)ceilf((w + 1 + 0.5f) / sw - 0.5f);
+    if (h == 0) ho_lo = 0;
+    if (w == 0) wo_lo = 0;
+    if (h == H - 1) ho_hi = Ho - 1;
+    if (w == W - 1) wo_hi = Wo - 1;
+    ho_lo = max(ho_lo, 0); wo_lo = max(wo_lo, 0); ho_hi = min(ho_hi, Ho - 1); wo_hi = min(wo_hi, Wo - 1);
+    float acc = 0.f;
+    for (int ho = ho_lo; ho <= ho_hi; ++ho) {
+      float fy = ((float)ho + 0.5f) * sh - 0.5f;
+      fy = fy < 0.f ? 0.f : fy;
+      const int y0 = min((int)fy, H - 1), y1 = min(y0 + 1, H - 1);
+      const float ly = fy - (float)y0;
+      const float wy = (y0 == h ? 1.f - ly : 0.f) + (y1 == h ? ly : 0.f);
+      if (wy == 0.f) continue;
+      for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+        float fx = ((float)wo + 0.5f) * sw - 0.5f;
+        fx = fx < 0.f ? 0.f : fx;
+        const int x0 = min((int)fx, W - 1), x1 = min(x0 + 1, W - 1);
+        const float lx = fx - (float)x0;
+        const float wx = (x0 == w ? 1.f - lx : 0.f) + (x1 == w ? lx : 0.f);
+        if (wx != 0.f) acc += wy * wx * dy[(((int64_t)b * Ho + ho) * Wo + wo) * dy_pitch + c];
+      }
+    }
+    dx[i] = acc;
+  }
+}
+
+// LayerNorm backward over s = x (+ res): one warp per row (C <= 1024, C % 32 == 0), row statistics recomputed;
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma.  Per-block partial sums of dy*xhat / dy for dgamma / dbeta.
+constexpr int LN_MAXV = 32;
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ res, const float* __restrict__ gamma,
+                                                            const float* __restrict__ dy, int64_t M, int C, float eps, float* __restrict__ dx,
+                                                            float* __restrict__ pg, float* __restrict__ pb) {
+  extern __shared__ float ln_sm[];  // [2][C] block accumulators
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nv = C / 32;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) ln_sm[i] = 0.f;
+  __syncthreads();
+  float ag[LN_MAXV], ab[LN_MAXV];
+#pragma unroll
+  for (int k = 0; k < LN_MAXV; ++k) { ag[k] = 0.f; ab[k] = 0.f; }
+  for (int64_t row = (int64_t)blockIdx.x * 8 + wid; row < M; row += (int64_t)gridDim.x * 8) {
+    float v[LN_MAXV], g[LN_MAXV];
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_MAXV; ++k)
+      if (k < nv) {
+        const int c = k * 32 + lane;
+        v[k] = x[row * C + c] + (res ? res[row * C + c] : 0.f);
+        sum += v[k];
+      }
+    const float mean = warp_sum(sum) / (float)C;
+    float sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_MAXV; ++k)
+      if (k < nv) { const float d = v[k] - mean; sq += d * d; }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_MAXV; ++k)
+      if (k < nv) {
+        const int c = k * 32 + lane;
+        const float d = dy[row * C + c];
+        v[k] = (v[k] - mean) * rstd;
+        g[k] = d * gamma[c];
+        sg += g[k];
+        sgx += g[k] * v[k];
+        ag[k] += d * v[k];
+        ab[k] += d;
+      }
+    sg = warp_sum(sg) / (float)C;
+    sgx = warp_sum(sgx) / (float)C;
+#pragma unroll
+    for (int k = 0; k < LN_MAXV; ++k)
+      if (k < nv) dx[row * C + k * 32 + lane] = rstd * (g[k] - sg - v[k] * sgx);
+  }
+  // deterministic in-block combine: warps add their accumulators one after the other
+  for (int w = 0; w < 8; ++w) {
+    if (wid == w) {
+#pragma unroll
+      for (int k = 0; k < LN_MAXV; ++k)
+        if (k < nv) { ln_sm[k * 32 + lane] += ag[k]; ln_sm[C + k * 32 + lane] += ab[k]; }
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { pg[(int64_t)blockIdx.x * C + i] = ln_sm[i]; pb[(int64_t)blockIdx.x * C + i] = ln_sm[C + i]; }
+}
+
+inline unsigned grid_for(int64_t n, int threads = 256) { return (unsigned)std::min<int64_t>(cdiv(n, threads), 148 * 16); }
+
+}  // namespace
+}  // namespace fb200
+
+using namespace fb200;
+
+extern "C" int64_t fb200_conv_wgrad_workspace_bytes(int B, int Ho, int Wo, int Cin, int Cout, int KH, int KW) {
+  const int64_t tiles = (int64_t)cdiv(Cout, WG_TM) * cdiv(Cin, WG_TN) * KH * KW;
+  const int64_t P = (int64_t)B * Ho * Wo;
+  int64_t splits = std::max<int64_t>(1, std::min<int64_t>(cdiv(148 * 4, tiles), cdiv(P, 512)));
+  return splits * Cout * KH * KW * Cin * 4 + 16;
+}
+
+extern "C" int fb200_conv_wgrad(const float* x, int B, int H, int W, int Cin, int x_pitch, const float* dy, int Ho, int Wo, int Cout, int dy_pitch, int KH,
+                                int KW, int stride, int pad, float* dw, int accumulate, void* workspace, void* stream) {
+  FB_CHECK_ARG(x && dy && dw && workspace, "conv_wgrad: null pointer");
+  FB_CHECK_ARG(B > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && stride >= 1, "conv_wgrad: bad sizes");
+  FB_CHECK_ARG(Ho == (H + 2 * pad - KH) / stride + 1 && Wo == (W + 2 * pad - KW) / stride + 1, "conv_wgrad: output size does not match");
+  const int64_t tiles = (int64_t)cdiv(Cout, WG_TM) * cdiv(Cin, WG_TN);
+  const int64_t P = (int64_t)B * Ho * Wo;
+  const int64_t splits = std::max<int64_t>(1, std::min<int64_t>(cdiv(148 * 4, tiles * KH * KW), cdiv(P, 512)));
+  const int64_t per = cdiv(cdiv(P, splits), WG_TK) * WG_TK;
+  float* part = reinterpret_cast<float*>(workspace);
+  cudaStream_t st = (cudaStream_t)stream;
+  conv_wgrad_kernel<<<dim3((unsigned)tiles, KH * KW, (unsigned)splits), 256, 0, st>>>(x, x_pitch, dy, dy_pitch, B, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad, per, part);
+  FB_CHECK_LAUNCH("conv_wgrad");
+  const int64_t n = (int64_t)Cout * KH * KW * Cin;
+  split_reduce_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(part, (int)splits, n, dw, accumulate);
+  FB_CHECK_LAUNCH("conv_wgrad(reduce)");
+  return FB200_OK;
+}
+
+extern "C" int fb200_dilate2(const float* dy, int B, int Ho, int Wo, int C, int Hd, int Wd, float* out, void* stream) {
+  FB_CHECK_ARG(dy && out && C % 4 == 0 && Hd >= 2 * Ho - 1 && Wd >= 2 * Wo - 1, "dilate2: bad arguments");
+  dilate2_kernel<<<grid_for((int64_t)B * Hd * Wd * (C / 4)), 256, 0, (cudaStream_t)stream>>>(dy, B, Ho, Wo, C, Hd, Wd, out);
+  FB_CHECK_LAUNCH("dilate2");
+  return FB200_OK;
+}
+
+extern "C" int64_t fb200_col_workspace_bytes(int C) { return (int64_t)(2 * CR_ROWS + 2) * C * 4 + 16; }
+
+static inline dim3 col_grid(int C, int64_t R) { return dim3((unsigned)cdiv(C, 32), (unsigned)std::min<int64_t>(CR_ROWS, cdiv(R, 8))); }
+
+extern "C" int fb200_colsum(const float* x, int64_t R, int C, int pitch, float* out, int accumulate, void* workspace, void* stream) {
+  FB_CHECK_ARG(x && out && workspace && R > 0 && C > 0, "colsum: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* p0 = reinterpret_cast<float*>(workspace);
+  const dim3 g = col_grid(C, R);
+  col_partial_kernel<0><<<g, 256, 0, st>>>(x, pitch, R, C, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, 0, p0, nullptr);
+  FB_CHECK_LAUNCH("colsum");
+  col_finalize_kernel<0><<<cdiv(C, 128), 128, 0, st>>>(p0, nullptr, g.y, C, (double)R, 0.f, 0.f, nullptr, nullptr, nullptr, out, nullptr, accumulate);
+  FB_CHECK_LAUNCH("colsum(finalize)");
+  return FB200_OK;
+}
+
+extern "C" int fb200_bn_train_fwd(const float* x, int x_pitch, int64_t R, int C, const float* gamma, const float* beta, const float* res, int res_pitch, int act,
+                                  float eps, float momentum, float* running_mean, float* running_var, float* save_mean, float* save_rstd, float* y, int y_pitch,
+                                  void* workspace, void* stream) {
+  FB_CHECK_ARG(x && gamma && beta && save_mean && save_rstd && y && workspace && R > 0 && C % 4 == 0, "bn_train_fwd: bad arguments");
+  FB_CHECK_ARG(act == FB200_ACT_NONE || act == FB200_ACT_RELU || (act == FB200_ACT_SILU && !res), "bn_train_fwd: act must be none/relu (or silu without residual)");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* p0 = reinterpret_cast<float*>(workspace);
+  const dim3 g = col_grid(C, R);
+  col_partial_kernel<0><<<g, 256, 0, st>>>(x, x_pitch, R, C, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, 0, p0, nullptr);
+  col_finalize_kernel<1><<<cdiv(C, 128), 128, 0, st>>>(p0, nullptr, g.y, C, (double)R, eps, momentum, nullptr, nullptr, nullptr, save_mean, nullptr, 0);
+  col_partial_kernel<1><<<g, 256, 0, st>>>(x, x_pitch, R, C, save_mean, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, 0, p0, nullptr);
+  col_finalize_kernel<2><<<cdiv(C, 128), 128, 0, st>>>(p0, nullptr, g.y, C, (double)R, eps, momentum, save_mean, running_mean, running_var, save_rstd, nullptr, 0);
+  bn_apply_kernel<<<grid_for(R * (C / 4)), 256, 0, st>>>(x, x_pitch, res, res_pitch, R, C, save_mean, save_rstd, gamma, beta, act, y, y_pitch);
+  FB_CHECK_LAUNCH("bn_train_fwd");
+  return FB200_OK;
+}
+
+extern "C" int fb200_bn_train_bwd(const float* x, int x_pitch, const float* dy, int dy_pitch, const float* y, int y_pitch, int64_t R, int C, const float* gamma,
+                                  const float* beta, const float* save_mean, const float* save_rstd, int act, float* dx, int dx_pitch, float* dres, int dres_pitch,
+                                  float* dgamma, float* dbeta, int accumulate, void* workspace, void* stream) {
+  FB_CHECK_ARG(x && dy && gamma && beta && save_mean && save_rstd && dx && dgamma && dbeta && workspace && R > 0, "bn_train_bwd: bad arguments");
+  FB_CHECK_ARG(act == FB200_ACT_NONE || y, "bn_train_bwd: the activation gradient needs the forward output");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* p0 = reinterpret_cast<float*>(workspace);
+  float* p1 = p0 + (int64_t)CR_ROWS * C;
+  const dim3 g = col_grid(C, R);
+  float* f0 = p1 + (int64_t)CR_ROWS * C;  // this step's dbeta / dgamma: needed by dx before they may be accumulated into the caller's buffers
+  float* f1 = f0 + C;
+  col_partial_kernel<2><<<g, 256, 0, st>>>(x, x_pitch, R, C, save_mean, save_rstd, gamma, beta, dy, dy_pitch, y, y_pitch, act, p0, p1);
+  col_finalize_kernel<3><<<cdiv(C, 128), 128, 0, st>>>(p0, p1, g.y, C, (double)R, 0.f, 0.f, nullptr, nullptr, nullptr, f0, f1, 0);
+  bn_bwd_apply_kernel<<<grid_for(R * C), 256, 0, st>>>(x, x_pitch, dy, dy_pitch, y, y_pitch, R, C, save_mean, save_rstd, gamma, beta, f1, f0, act, (float)(1.0 / (double)R),
+                                                       dx, dx_pitch, dres, dres_pitch);
+  col_finalize_kernel<3><<<cdiv(C, 128), 128, 0, st>>>(f0, f1, 1, C, (double)R, 0.f, 0.f, nullptr, nullptr, nullptr, dbeta, dgamma, accumulate);
+  FB_CHECK_LAUNCH("bn_train_bwd");
+  return FB200_OK;
+}
+
+extern "C" int fb200_add_act(const float* a, const float* b, const float* dy, int act, int64_t n, float* out, void* stream) {
+  FB_CHECK_ARG(a && out && n > 0 && act >= 0 && act <= FB200_ACT_GELU, "add_act: bad arguments");
+  add_act_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(a, b, dy, act, n, out);
+  FB_CHECK_LAUNCH("add_act");
+  return FB200_OK;
+}
+
+extern "C" int fb200_maxpool3x3s2_bwd(const float* x, const float* dy, int B, int H, int W, int C, float* dx, void* stream) {
+  FB_CHECK_ARG(x && dy && dx, "maxpool3x3s2_bwd: null pointer");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  maxpool_bwd_kernel<<<grid_for((int64_t)B * H * W * C), 256, 0, (cudaStream_t)stream>>>(x, dy, B, H, W, C, Ho, Wo, dx);
+  FB_CHECK_LAUNCH("maxpool3x3s2_bwd");
+  return FB200_OK;
+}
+
+extern "C" int fb200_avgpool2x2_ceil_bwd(const float* dy, int B, int H, int W, int C, float* dx, void* stream) {
+  FB_CHECK_ARG(dy && dx, "avgpool2x2_ceil_bwd: null pointer");
+  avgpool_bwd_kernel<<<grid_for((int64_t)B * H * W * C), 256, 0, (cudaStream_t)stream>>>(dy, B, H, W, C, (H + 1) / 2, (W + 1) / 2, dx);
+  FB_CHECK_LAUNCH("avgpool2x2_ceil_bwd");
+  return FB200_OK;
+}
+
+extern "C" int fb200_resize_bilinear_bwd(const float* dy, int dy_pitch, int B, int H, int W, int C, int Ho, int Wo, float* dx, void* stream) {
+  FB_CHECK_ARG(dy && dx && H > 0 && W > 0 && Ho > 0 && Wo > 0, "resize_bilinear_bwd: bad arguments");
+  resize_bwd_kernel<<<grid_for((int64_t)B * H * W * C), 256, 0, (cudaStream_t)stream>>>(dy, dy_pitch, B, H, W, C, Ho, Wo, dx);
+  FB_CHECK_LAUNCH("resize_bilinear_bwd");
+  return FB200_OK;
+}
+
+extern "C" int fb200_layernorm_bwd(const float* x, const float* res, const float* gamma, const float* dy, int64_t M, int C, float eps, float* dx, float* dgamma,
+                                   float* dbeta, int accumulate, void* workspace, void* stream) {
+  FB_CHECK_ARG(x && gamma && dy && dx && dgamma && dbeta && workspace && M > 0, "layernorm_bwd: bad arguments");
+  FB_CHECK_ARG(C % 32 == 0 && C <= 32 * LN_MAXV, "layernorm_bwd: C must be a multiple of 32 and <= %d", 32 * LN_MAXV);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nblk = (int)std::min<int64_t>(CR_ROWS, cdiv(M, 8));
+  float* pg = reinterpret_cast<float*>(workspace);
+  float* pb = pg + (int64_t)CR_ROWS * C;
+  layernorm_bwd_kernel<<<nblk, 256, 2 * C * sizeof(float), st>>>(x, res, gamma, dy, M, C, eps, dx, pg, pb);
+  FB_CHECK_LAUNCH("layernorm_bwd");
+  col_finalize_kernel<3><<<cdiv(C, 128), 128, 0, st>>>(pb, pg, nblk, C, 1.0, 0.f, 0.f, nullptr, nullptr, nullptr, dbeta, dgamma, accumulate);
+  FB_CHECK_LAUNCH("layernorm_bwd(finalize)");
+  return FB200_OK;
+}

@@ -83,13 +83,14 @@ __global__ void optim_finalize_kernel(const double* __restrict__ partial, const 
 // p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps).   One CTA per chunk; a chunk never straddles two tensors.
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                                      const int64_t* __restrict__ chunk_start, const int* __restrict__ chunk_len, const int* __restrict__ chunk_seg,
-                                                     const float* __restrict__ seg_lr, const float* __restrict__ seg_wd, float lr_factor, float beta1, float beta2,
-                                                     float eps, const float* __restrict__ ctrl) {
+                                                     const float* __restrict__ seg_lr, const float* __restrict__ seg_wd, const int* __restrict__ seg_active, float lr_factor,
+                                                     float beta1, float beta2, float eps, const float* __restrict__ ctrl) {
   if (reinterpret_cast<const int*>(ctrl)[2]) return;      // non-finite gradients: the step is skipped (GradScaler.step)
   const float gmul = ctrl[4], bc1 = ctrl[6], bc2s = ctrl[7];
   const int c = blockIdx.x;
   const int64_t s0 = chunk_start[c];
   const int len = chunk_len[c], seg = chunk_seg[c];
+  if (seg_active && !seg_active[seg]) return;  // tensor received no gradient this step: torch.optim skips it entirely (p.grad is None), decay included
   const float lr = seg_lr[seg] * lr_factor, wd = seg_wd[seg];
   const float decay = 1.f - lr * wd, step_size = lr / bc1;
   float4* p4 = reinterpret_cast<float4*>(p + s0);
@@ -140,12 +141,12 @@ extern "C" int fb200_optim_finalize(const void* workspace, float* ctrl, float ma
 }
 
 extern "C" int fb200_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const int64_t* chunk_start, const int* chunk_len,
-                                const int* chunk_seg, int nchunks, const float* seg_lr, const float* seg_wd, float lr_factor, float beta1, float beta2,
-                                float eps, const float* ctrl, void* stream) {
+                                const int* chunk_seg, int nchunks, const float* seg_lr, const float* seg_wd, const int* seg_active, float lr_factor, float beta1,
+                                float beta2, float eps, const float* ctrl, void* stream) {
   FB_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && chunk_start && chunk_len && chunk_seg && seg_lr && seg_wd && ctrl && nchunks > 0,
                "adamw_step: bad arguments");
-  adamw_kernel<<<nchunks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, chunk_start, chunk_len, chunk_seg, seg_lr, seg_wd, lr_factor, beta1,
-                                                          beta2, eps, ctrl);
+  adamw_kernel<<<nchunks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, chunk_start, chunk_len, chunk_seg, seg_lr, seg_wd, seg_active, lr_factor,
+                                                          beta1, beta2, eps, ctrl);
   FB_CHECK_LAUNCH("adamw_step");
   return FB200_OK;
 }

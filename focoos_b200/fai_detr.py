@@ -620,15 +620,42 @@ class FAIDetr(nn.Module):
         self._engine = None
         return super()._apply(fn, *a, **k)
 
+    def train_graph(self):
+        """training-mode forward built from the autograd ops (fai_detr_train.py); fp32 storage, tensor-core split products by default"""
+        from .fai_detr_train import DetrTrainGraph
+        prec = "fp32" if self.precision == "fp32" else "fp32_tc"
+        if getattr(self, "_train_graph", None) is None or self._train_graph.prec != prec:
+            self._train_graph = DetrTrainGraph(self, prec)
+        return self._train_graph
+
+    def criterion(self):
+        """SetCriterion with the config's matcher / loss weights (modelling.py:1295-1316)"""
+        if getattr(self, "_criterion", None) is None:
+            from .criterion import BoxHungarianMatcher, SetCriterion
+            c = self.config
+            self._criterion = SetCriterion(
+                num_classes=c.num_classes,
+                matcher=BoxHungarianMatcher(cost_class=c.matcher_cost_class, cost_bbox=c.matcher_cost_bbox, cost_giou=c.matcher_cost_giou,
+                                            use_focal_loss=c.matcher_use_focal_loss, alpha=c.matcher_alpha, gamma=c.matcher_gamma),
+                weight_dict={"loss_vfl": c.weight_dict_loss_vfl, "loss_bbox": c.weight_dict_loss_bbox, "loss_giou": c.weight_dict_loss_giou},
+                losses=c.criterion_losses, eos_coef=c.criterion_eos_coef, focal_alpha=c.criterion_focal_alpha, focal_gamma=c.criterion_focal_gamma,
+                deep_supervision=c.criterion_deep_supervision)
+        return self._criterion
+
     def engine(self) -> DetrEngine:
         if self._engine is None or self._engine.device != self.device or self._engine.precision != self.precision or self._engine.algo != self.algo:
             self._engine = DetrEngine(self.state_dict(), self.config, self.device, self.precision, self.algo)
         return self._engine
 
     def forward(self, images: torch.Tensor, targets: list = [], taps: Optional[dict] = None) -> DETRModelOutput:
-        if self.training or (targets is not None and len(targets) > 0):
-            raise NotImplementedError("focoos_b200: the fine-tune path (losses/backward, SURVEY §8 a20-a21) is a later round")
         if ops._backend is None and not images.is_cuda:
             raise RuntimeError("focoos_b200.FAIDetr runs on CUDA (sm_100a) only — no CPU fallback; move the model and inputs to the GPU")
+        if self.training:  # modelling.py:1354-1356: losses only, empty logits/boxes
+            assert targets is not None and len(targets) > 0, "targets should not be None or empty - training mode"
+            outputs = self.train_graph().forward(images)
+            losses = self.criterion()({k: v for k, v in outputs.items() if not k.startswith("_")}, targets)
+            if taps is not None:
+                taps.update(outputs)
+            return DETRModelOutput(logits=torch.zeros(0, 0, 0), boxes=torch.zeros(0, 0, 4), loss=losses)
         scores, boxes = self.engine().forward(images if images.dtype == torch.uint8 else images.to(torch.float32), taps)
         return DETRModelOutput(boxes=boxes, logits=scores, loss=None)

@@ -45,9 +45,9 @@ def _cb_optim_finalize(self, ws, ctrl, max_norm, clip_passes, inv_world, use_sca
                ctypes.c_float(growth), ctypes.c_float(backoff), int(growth_interval), ctypes.c_float(beta1), ctypes.c_float(beta2), _stream())
 
 
-def _cb_adamw_step(self, params, grads, m, v, chunk_start, chunk_len, chunk_seg, seg_lr, seg_wd, lr_factor, beta1, beta2, eps, ctrl):
+def _cb_adamw_step(self, params, grads, m, v, chunk_start, chunk_len, chunk_seg, seg_lr, seg_wd, seg_active, lr_factor, beta1, beta2, eps, ctrl):
     self._cuda(params, grads, m, v, chunk_start, chunk_len, chunk_seg, seg_lr, seg_wd, ctrl)
-    self._call("fb200_adamw_step", _p(params), _p(grads), _p(m), _p(v), _p(chunk_start), _p(chunk_len), _p(chunk_seg), chunk_len.shape[0], _p(seg_lr), _p(seg_wd),
+    self._call("fb200_adamw_step", _p(params), _p(grads), _p(m), _p(v), _p(chunk_start), _p(chunk_len), _p(chunk_seg), chunk_len.shape[0], _p(seg_lr), _p(seg_wd), _p(seg_active),
                ctypes.c_float(lr_factor), ctypes.c_float(beta1), ctypes.c_float(beta2), ctypes.c_float(eps), _p(ctrl), _stream())
 
 
@@ -146,6 +146,8 @@ class FlatAdamW:
         self.ctrl = torch.zeros(CTRL_WORDS, dtype=torch.float32, device=dev)
         self.ctrl[CTRL_SCALE] = init_scale if amp else 1.0
         self.ws = ops._be().optim_workspace(dev)
+        self._fired: Optional[List[bool]] = None  # set by track_unused_parameters()
+        self._hooks = []
 
     # -- GradScaler-shaped helpers (device scalars: no host sync on the step path)
     @property
@@ -155,8 +157,19 @@ class FlatAdamW:
     def scale_loss(self, loss: torch.Tensor) -> torch.Tensor:
         return loss * self.ctrl[CTRL_SCALE].to(loss.dtype) if self.amp else loss
 
+    def track_unused_parameters(self) -> None:
+        """torch.optim skips a tensor whose .grad is None (no update, no weight decay) and clip_grad_norm_ ignores it - e.g. the dead
+        `mask_features` conv of fai-detr.  Here gradients are views of a zeroed flat buffer and never None, so backward marks
+        the tensors it reached through post-accumulate hooks and step() skips the others."""
+        if self._fired is None:
+            self._fired = [False] * len(self.params)
+            for i, p in enumerate(self.params):
+                self._hooks.append(p.register_post_accumulate_grad_hook(lambda _p, i=i: self._fired.__setitem__(i, True)))
+
     def zero_grad(self) -> None:
         self.flat_grads.zero_()
+        if self._fired is not None:
+            self._fired = [False] * len(self.params)
         for p, o in zip(self.params, self.offsets):  # autograd may have replaced .grad (set_to_none callers)
             if p.grad is None or p.grad.data_ptr() != self.flat_grads.data_ptr() + 4 * o:
                 p.grad = self.flat_grads[o:o + p.numel()].view_as(p)
@@ -167,8 +180,9 @@ class FlatAdamW:
         be.grad_stats(self.flat_grads, self.ws)
         be.optim_finalize(self.ws, self.ctrl, self.clip, self.clip_passes, 1.0 / self.world_size, self.amp, self.growth, self.backoff, self.growth_interval,
                           self.betas[0], self.betas[1])
+        active = None if self._fired is None else torch.tensor(self._fired, dtype=torch.int32).to(self.flat_params.device, non_blocking=True)
         be.adamw_step(self.flat_params, self.flat_grads, self.exp_avg, self.exp_avg_sq, self.chunk_start, self.chunk_len, self.chunk_seg, self.seg_lr, self.seg_wd,
-                      float(lr_factor), self.betas[0], self.betas[1], self.eps, self.ctrl)
+                      active, float(lr_factor), self.betas[0], self.betas[1], self.eps, self.ctrl)
 
     def stats(self) -> Dict[str, float]:
         """host read-back (syncs): for logging / tests only."""

@@ -232,10 +232,48 @@ int fb200_grad_stats(const float* grads, int64_t n, void* workspace, void* strea
 /* one thread: norm, `clip_passes` successive clip_grad_norm_(max_norm) coefficients, loss-scale update, bias corrections */
 int fb200_optim_finalize(const void* workspace, float* ctrl, float max_norm, int clip_passes, float inv_world, int use_scaler, float growth,
                          float backoff, int growth_interval, float beta1, float beta2, void* stream);
-/* AdamW over chunks (chunk c covers [chunk_start[c], +chunk_len[c]) of tensor chunk_seg[c]; lr = seg_lr[seg]*lr_factor) */
+/* AdamW over chunks (chunk c covers [chunk_start[c], +chunk_len[c]) of tensor chunk_seg[c]; lr = seg_lr[seg]*lr_factor).
+ * seg_active: NULL, or one int per tensor, 0 = the tensor received no gradient this step and is skipped (torch: p.grad is None). */
 int fb200_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const int64_t* chunk_start, const int* chunk_len,
-                     const int* chunk_seg, int nchunks, const float* seg_lr, const float* seg_wd, float lr_factor, float beta1, float beta2,
-                     float eps, const float* ctrl, void* stream);
+                     const int* chunk_seg, int nchunks, const float* seg_lr, const float* seg_wd, const int* seg_active, float lr_factor, float beta1,
+                     float beta2, float eps, const float* ctrl, void* stream);
+
+/* ---- backward / training-mode kernels (what autograd executes under TrainerLoop.run_step, trainer/trainer.py:757) ----
+ * fp32, NHWC, caller-owned workspaces.  Each replaces the aten backward of the torch call the reference makes at the cited site. */
+
+/* weight gradient of nn.Conv2d (nn/layers/conv.py:84-92): dw[Cout][KH][KW][Cin] (+)= sum_p dy[p,co] * x[pix(p,kh,kw),ci] */
+int64_t fb200_conv_wgrad_workspace_bytes(int B, int Ho, int Wo, int Cin, int Cout, int KH, int KW);
+int fb200_conv_wgrad(const float* x, int B, int H, int W, int Cin, int x_pitch, const float* dy, int Ho, int Wo, int Cout, int dy_pitch, int KH,
+                     int KW, int stride, int pad, float* dw, int accumulate, void* workspace, void* stream);
+/* zero-dilation of dy for the stride-2 data gradient (dx = conv(dilate(dy), flipped transposed weights) through fb200_conv2d) */
+int fb200_dilate2(const float* dy, int B, int Ho, int Wo, int C, int Hd, int Wd, float* out, void* stream);
+/* column sums of [R,C] (bias gradients); workspace of fb200_col_workspace_bytes(C) also serves the BN / LayerNorm calls below */
+int64_t fb200_col_workspace_bytes(int C);
+int fb200_colsum(const float* x, int64_t R, int C, int pitch, float* out, int accumulate, void* workspace, void* stream);
+/* nn.BatchNorm2d in training mode (+ residual add + ReLU/SiLU): batch mean / biased variance over R = B*H*W rows, running stats
+ * updated with `momentum` (unbiased variance), y = act((x-mean)*rstd*gamma + beta + res)   (conv.py:93-97, resnet.py:106-121) */
+int fb200_bn_train_fwd(const float* x, int x_pitch, int64_t R, int C, const float* gamma, const float* beta, const float* res, int res_pitch, int act,
+                       float eps, float momentum, float* running_mean, float* running_var, float* save_mean, float* save_rstd, float* y, int y_pitch,
+                       void* workspace, void* stream);
+int fb200_bn_train_bwd(const float* x, int x_pitch, const float* dy, int dy_pitch, const float* y, int y_pitch, int64_t R, int C, const float* gamma,
+                       const float* beta, const float* save_mean, const float* save_rstd, int act, float* dx, int dx_pitch, float* dres, int dres_pitch,
+                       float* dgamma, float* dbeta, int accumulate, void* workspace, void* stream);
+/* out = act(a + b) when dy == NULL, else out = dy * act'(a + b)   (RepVggBlock :45, GELU of the AIFI FFN) */
+int fb200_add_act(const float* a, const float* b, const float* dy, int act, int64_t n, float* out, void* stream);
+int fb200_maxpool3x3s2_bwd(const float* x, const float* dy, int B, int H, int W, int C, float* dx, void* stream);
+int fb200_avgpool2x2_ceil_bwd(const float* dy, int B, int H, int W, int C, float* dx, void* stream);
+int fb200_resize_bilinear_bwd(const float* dy, int dy_pitch, int B, int H, int W, int C, int Ho, int Wo, float* dx, void* stream);
+/* nn.LayerNorm backward over s = x (+ res): dx is the gradient w.r.t. s */
+int fb200_layernorm_bwd(const float* x, const float* res, const float* gamma, const float* dy, int64_t M, int C, float eps, float* dx, float* dgamma,
+                        float* dbeta, int accumulate, void* workspace, void* stream);
+/* nn.MultiheadAttention core backward (o = forward output) */
+int fb200_attention_bwd(const float* q, int q_pitch, const float* k, int k_pitch, const float* v, int v_pitch, const float* o, int o_pitch,
+                        const float* dout, int do_pitch, int B, int Lq, int Lk, int heads, int head_dim, float scale, float* dq, int dq_pitch,
+                        float* dk, int dk_pitch, float* dv, int dv_pitch, void* stream);
+/* adjoint of fb200_msda: dvalue [B,S,heads*32] must be zero-initialised (accumulated with atomics); doa like oa */
+int fb200_msda_bwd(const float* value, int v_pitch, const float* oa, int oa_pitch, const float* ref, const float* dout, int do_pitch,
+                   const int* shapes_host, int L, int P, int B, int S, int Q, int heads, float* dvalue, int dv_pitch, float* doa, int doa_pitch,
+                   void* stream);
 
 #ifdef __cplusplus
 }

@@ -347,11 +347,13 @@ def _rb_optim_finalize(self, ws, ctrl, max_norm, clip_passes, inv_world, use_sca
             ic[1] += 1
 
 
-def _rb_adamw_step(self, params, grads, m, v, chunk_start, chunk_len, chunk_seg, seg_lr, seg_wd, lr_factor, beta1, beta2, eps, ctrl):
+def _rb_adamw_step(self, params, grads, m, v, chunk_start, chunk_len, chunk_seg, seg_lr, seg_wd, seg_active, lr_factor, beta1, beta2, eps, ctrl):
     if int(ctrl.view(torch.int32)[2]):
         return
     gmul, bc1, bc2s = float(ctrl[4]), float(ctrl[6]), float(ctrl[7])
     for s0, ln, sg in zip(chunk_start.tolist(), chunk_len.tolist(), chunk_seg.tolist()):
+        if seg_active is not None and not int(seg_active[sg]):
+            continue
         sl = slice(s0, s0 + ln)
         lr, wd = float(seg_lr[sg]) * lr_factor, float(seg_wd[sg])
         g = grads[sl] * gmul
@@ -362,4 +364,155 @@ def _rb_adamw_step(self, params, grads, m, v, chunk_start, chunk_len, chunk_seg,
 
 
 for _n, _f in (("optim_workspace", _rb_optim_workspace), ("grad_stats", _rb_grad_stats), ("optim_finalize", _rb_optim_finalize), ("adamw_step", _rb_adamw_step)):
+    setattr(RefBackend, _n, _f)
+
+
+# ---- backward / training-mode operators (tests of focoos_b200/autograd_ops.py + train graph host logic on the CPU) -------------
+def _nchw(t):
+    return t.permute(0, 3, 1, 2)
+
+
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1)
+
+
+def _act_bw(act, z):
+    return {0: lambda t: t, 1: F.relu, 2: F.silu, 3: F.gelu}[act](z)
+
+
+def _rb_conv_wgrad(self, x, dy, KH, KW, stride, pad, dw):
+    Cout, Cin = dy.shape[-1], x.shape[-1]
+    g = torch.nn.grad.conv2d_weight(_nchw(x).contiguous(), (Cout, Cin, KH, KW), _nchw(dy).contiguous(), stride=stride, padding=pad)
+    dw.copy_(g.permute(0, 2, 3, 1))
+
+
+def _rb_dilate2(self, dy, out):
+    out.zero_()
+    out[:, : 2 * dy.shape[1] : 2, : 2 * dy.shape[2] : 2] = dy
+
+
+def _rb_colsum(self, x2d, out):
+    out.copy_(x2d.double().sum(0).float())
+
+
+def _rb_bn_train_fwd(self, x2d, gamma, beta, res2d, act, eps, momentum, rmean, rvar, save_mean, save_rstd, y2d):
+    R = x2d.shape[0]
+    mean = x2d.double().mean(0)
+    var = ((x2d.double() - mean) ** 2).mean(0)
+    save_mean.copy_(mean.float())
+    save_rstd.copy_((1.0 / torch.sqrt(var + eps)).float())
+    if rmean is not None:
+        rmean.mul_(1 - momentum).add_(momentum * save_mean)
+        rvar.mul_(1 - momentum).add_(momentum * (var * R / max(R - 1, 1)).float())
+    z = (x2d - save_mean) * save_rstd * gamma + beta
+    if res2d is not None:
+        z = z + res2d
+    y2d.copy_(_act_bw(act, z))
+
+
+def _rb_bn_train_bwd(self, x2d, dy2d, y2d, gamma, beta, save_mean, save_rstd, act, dx2d, dres2d, dgamma, dbeta):
+    R = x2d.shape[0]
+    xh = (x2d - save_mean) * save_rstd
+    g = dy2d
+    if act == 1:
+        g = dy2d * (y2d > 0)
+    elif act == 2:
+        z = (xh * gamma + beta).detach().requires_grad_(True)
+        with torch.enable_grad():
+            (gz,) = torch.autograd.grad(F.silu(z), z, dy2d)
+        g = gz
+    db = g.double().sum(0).float()
+    dg = (g.double() * xh.double()).sum(0).float()
+    dx2d.copy_(gamma * save_rstd * (g - db / R - xh * dg / R))
+    if dres2d is not None:
+        dres2d.copy_(g)
+    dgamma.copy_(dg)
+    dbeta.copy_(db)
+
+
+def _rb_add_act(self, a, b, dy, act, out):
+    z = (a if b is None else a + b).detach().requires_grad_(dy is not None)
+    if dy is None:
+        out.copy_(_act_bw(act, z))
+    else:
+        with torch.enable_grad():
+            (g,) = torch.autograd.grad(_act_bw(act, z), z, dy)
+        out.copy_(g)
+
+
+def _via_autograd(fn, x, dy):
+    xx = x.detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        (g,) = torch.autograd.grad(fn(xx), xx, dy)
+    return g
+
+
+def _rb_maxpool_bwd(self, x, dy, dx):
+    dx.copy_(_nhwc(_via_autograd(lambda t: F.max_pool2d(t, 3, 2, 1), _nchw(x), _nchw(dy))))
+
+
+def _rb_avgpool_bwd(self, dy, dx):
+    dx.copy_(_nhwc(_via_autograd(lambda t: F.avg_pool2d(t, 2, 2, 0, ceil_mode=True), _nchw(torch.zeros_like(dx)), _nchw(dy))))
+
+
+def _rb_resize_bwd(self, dy, dx):
+    size = dy.shape[1:3]
+    dx.copy_(_nhwc(_via_autograd(lambda t: F.interpolate(t, size=tuple(size), mode="bilinear", align_corners=False), _nchw(torch.zeros_like(dx)), _nchw(dy))))
+
+
+def _rb_layernorm_bwd(self, x2d, res2d, gamma, dy2d, eps, dx2d, dgamma, dbeta):
+    s = (x2d if res2d is None else x2d + res2d).detach().clone().requires_grad_(True)
+    g = gamma.detach().clone().requires_grad_(True)
+    b = torch.zeros_like(gamma).requires_grad_(True)
+    with torch.enable_grad():
+        ds, dg, db = torch.autograd.grad(F.layer_norm(s, (s.shape[-1],), g, b, eps), (s, g, b), dy2d)
+    dx2d.copy_(ds)
+    dgamma.copy_(dg)
+    dbeta.copy_(db)
+
+
+def _mha_core(q, k, v, heads, scale):
+    B, Lq, C = q.shape
+    hd = C // heads
+    qh, kh, vh = (t.reshape(B, -1, heads, hd).transpose(1, 2) for t in (q, k, v))
+    p = torch.softmax(qh @ kh.transpose(-1, -2) * scale, -1)
+    return (p @ vh).transpose(1, 2).reshape(B, Lq, C)
+
+
+def _rb_attention_bwd(self, q, k, v, o, do, heads, scale, dq, dk, dv):
+    qq, kk, vv = (t.detach().clone().requires_grad_(True) for t in (q, k, v))
+    with torch.enable_grad():
+        gq, gk, gv = torch.autograd.grad(_mha_core(qq, kk, vv, heads, scale), (qq, kk, vv), do)
+    dq.copy_(gq)
+    dk.copy_(gk)
+    dv.copy_(gv)
+
+
+def _rb_msda_bwd(self, value, oa, ref, do, shapes, P, heads, dvalue, doa):
+    vv, oo = value.detach().clone().requires_grad_(True), oa.detach().clone().requires_grad_(True)
+    out = torch.empty((value.shape[0], oa.shape[1], value.shape[2]))
+    with torch.enable_grad():
+        B, S, C = vv.shape
+        Q, L, hd = oo.shape[1], len(shapes), C // heads
+        off = oo[..., : heads * L * P * 2].reshape(B, Q, heads, L, P, 2)
+        aw = torch.softmax(oo[..., heads * L * P * 2 : heads * L * P * 3].reshape(B, Q, heads, L * P), -1).reshape(B, Q, heads, L, P)
+        r = ref.reshape(B, Q, 1, 1, 1, 4)
+        loc = r[..., :2] + off / P * r[..., 2:] * 0.5
+        vals = vv.reshape(B, S, heads, hd).split([h * w for h, w in shapes], dim=1)
+        grids = 2 * loc - 1
+        sampled = []
+        for lid, (H_, W_) in enumerate(shapes):
+            vl = vals[lid].flatten(2).transpose(1, 2).reshape(B * heads, hd, H_, W_)
+            g = grids[:, :, :, lid].transpose(1, 2).flatten(0, 1)
+            sampled.append(F.grid_sample(vl, g, mode="bilinear", padding_mode="zeros", align_corners=False))
+        awt = aw.transpose(1, 2).reshape(B * heads, 1, Q, L * P)
+        o = (torch.stack(sampled, dim=-2).flatten(-2) * awt).sum(-1).view(B, heads * hd, Q).transpose(1, 2)
+        gv, go = torch.autograd.grad(o, (vv, oo), do)
+    dvalue.add_(gv)
+    doa.copy_(go)
+
+
+for _n, _f in (("conv_wgrad", _rb_conv_wgrad), ("dilate2", _rb_dilate2), ("colsum", _rb_colsum), ("bn_train_fwd", _rb_bn_train_fwd), ("bn_train_bwd", _rb_bn_train_bwd),
+               ("add_act", _rb_add_act), ("maxpool_bwd", _rb_maxpool_bwd), ("avgpool_bwd", _rb_avgpool_bwd), ("resize_bwd", _rb_resize_bwd),
+               ("layernorm_bwd", _rb_layernorm_bwd), ("attention_bwd", _rb_attention_bwd), ("msda_bwd", _rb_msda_bwd)):
     setattr(RefBackend, _n, _f)
