@@ -99,6 +99,7 @@ def _free_port():
 
 def _ddp_worker(rank, world, port, q):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(2)  # two workers on a shared host: do not oversubscribe the cores
     dist.init_process_group("gloo", rank=rank, world_size=world)
     ops._backend = RefBackend()
     torch.manual_seed(0)
@@ -114,7 +115,7 @@ def _ddp_worker(rank, world, port, q):
         opt.scale_loss(((m(x) - y) ** 2).mean()).backward()
         red.finish()
         opt.step()
-    q.put((rank, [p.detach().clone() for p in m.parameters()]))
+    q.put((rank, [p.detach().numpy().copy() for p in m.parameters()]))  # numpy: pickled by value (tensors go through fd passing and race with worker exit)
     dist.destroy_process_group()
 
 
@@ -125,7 +126,7 @@ def test_two_rank_gradient_exchange_equals_full_batch_reference():
     procs = [ctx.Process(target=_ddp_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = dict(q.get(timeout=180) for _ in range(world))
+    res = {r: [torch.from_numpy(a) for a in ps] for r, ps in (q.get(timeout=600) for _ in range(world))}
     for p in procs:
         p.join(30)
         assert p.exitcode == 0
