@@ -144,6 +144,8 @@ class SetCriterion(torch.nn.Module):
             raise NotImplementedError(f"focoos_b200: criterion losses {list(losses)} not built (only ['vfl', 'boxes'])")
         self.num_classes, self.matcher, self.weight_dict, self.losses = num_classes, matcher, dict(weight_dict), list(losses)
         self.deep_supervision, self.focal_alpha, self.focal_gamma, self.eos_coef = deep_supervision, float(focal_alpha), float(focal_gamma), eos_coef
+        self.forced_match = None  # optional [L,T] int tensor: use these assignments instead of running the matcher (teacher forcing in parity tests)
+        self.last_match = None    # the assignments used by the most recent forward, [L,T] int32 on the device
 
     def forward(self, outputs: dict, targets: List[DETRTargets]) -> Dict[str, torch.Tensor]:
         layers = [outputs] + (list(outputs.get("aux_outputs", [])) if self.deep_supervision else [])
@@ -161,7 +163,12 @@ class SetCriterion(torch.nn.Module):
         num_boxes = max(float(nb.item()) / world, 1.0)
         tl, tb, toff, counts = _pack_targets(targets, dev)
         with torch.no_grad():
-            mq = self.matcher.match_layers(logits.detach(), boxes.detach(), targets) if tl is not None else None
+            if self.forced_match is not None:
+                mq = self.forced_match.to(device=dev, dtype=torch.int32).contiguous()
+                assert tuple(mq.shape) == (logits.shape[0], 0 if tl is None else tl.shape[0])
+            else:
+                mq = self.matcher.match_layers(logits.detach(), boxes.detach(), targets) if tl is not None else None
+            self.last_match = mq
         w = (float(self.weight_dict.get("loss_vfl", 1.0)), float(self.weight_dict.get("loss_bbox", 1.0)), float(self.weight_dict.get("loss_giou", 1.0)))
         table = _DetrLossFn.apply(logits, boxes, tl, tb, toff, mq, num_boxes, w, self.focal_alpha, self.focal_gamma)
         out = {}

@@ -35,6 +35,12 @@ class DetrTrainGraph:
         assert precision in ("fp32", "fp32_tc")
         self.m, self.prec = model, precision
         self._const = {}
+        self.taps = None  # optional dict: named intermediate tensors (detached) for parity debugging
+        self.forced_topk = None  # optional [B, num_queries] int tensor: use this query selection instead of the top-k (teacher forcing in parity tests)
+
+    def _tap(self, name, t):
+        if self.taps is not None:
+            self.taps[name] = t.detach()
 
     # ---- building blocks ---------------------------------------------------------------------------------------------
     def cnl(self, x, layer, res=None, act="default"):
@@ -136,6 +142,7 @@ class DetrTrainGraph:
             toks.append(y.reshape(B, h * w, C))
             shapes.append((h, w))
         memory = torch.cat(toks, 1)
+        self._tap("memory", memory)
         dev = memory.device
         key = ("anchors", tuple(shapes), str(dev))
         if key not in self._const:
@@ -149,12 +156,15 @@ class DetrTrainGraph:
         with torch.no_grad():
             scores = ops.rowmax(enc_cls.detach())
             _, topk_ind = ops.topk(scores.reshape(B, -1).contiguous(), tp.num_queries)
+            if self.forced_topk is not None:
+                topk_ind = self.forced_topk.to(device=dev, dtype=torch.int32)
             idx = topk_ind.to(torch.int64)
         ref_unact = enc_box_unact.gather(1, idx.unsqueeze(-1).expand(-1, -1, 4))
         enc_topk_bboxes = torch.sigmoid(ref_unact)
         enc_topk_logits = enc_cls.gather(1, idx.unsqueeze(-1).expand(-1, -1, enc_cls.shape[-1]))
         target = om.gather(1, idx.unsqueeze(-1).expand(-1, -1, om.shape[-1])).detach()
         ref_unact = ref_unact.detach()
+        self._tap("om", om); self._tap("target", target); self._tap("ref_unact", ref_unact); self._tap("enc_cls", enc_cls)
 
         # decoder (:969-1020)
         out = target
@@ -163,17 +173,21 @@ class DetrTrainGraph:
         dec_boxes, dec_logits = [], []
         for i, layer in enumerate(tp.decoder.layers):
             pos = self.mlp(ref_detach, tp.query_pos_head)
+            self._tap(f"dec{i}.pos", pos)
             qk = A.AddActFn.apply(out, pos, ops.ACT_NONE)
             out = A.layer_norm(out, layer.norm1, res=self.mha(qk, qk, out, layer.self_attn))
+            self._tap(f"dec{i}.after_sa", out)
             ca = layer.cross_attn
             value = A.linear(memory, ca.value_proj.weight, ca.value_proj.bias, precision=self.prec)
             q = A.AddActFn.apply(out, pos, ops.ACT_NONE)
             oa = torch.cat([A.linear(q, ca.sampling_offsets.weight, ca.sampling_offsets.bias, precision=self.prec),
                             A.linear(q, ca.attention_weights.weight, ca.attention_weights.bias, precision=self.prec)], -1)
             sampled = A.MSDAFn.apply(value, oa, ref_detach, shapes, tp.num_points, tp.nhead)
+            self._tap(f"dec{i}.value", value); self._tap(f"dec{i}.oa", oa); self._tap(f"dec{i}.sampled", sampled)
             out = A.layer_norm(out, layer.norm2, res=A.linear(sampled, ca.output_proj.weight, ca.output_proj.bias, precision=self.prec))
             ff = A.linear(A.linear(out, layer.linear1.weight, layer.linear1.bias, ops.ACT_RELU, self.prec), layer.linear2.weight, layer.linear2.bias, precision=self.prec)
             out = A.layer_norm(out, layer.norm3, res=ff)
+            self._tap(f"dec{i}.out", out)
             delta = self.mlp(out, tp.dec_bbox_classifier[i])
             inter = torch.sigmoid(delta + _inverse_sigmoid(ref_detach))
             dec_logits.append(A.linear(out, tp.dec_score_classifier[i].weight, tp.dec_score_classifier[i].bias, precision=self.prec))
@@ -184,6 +198,7 @@ class DetrTrainGraph:
                "aux_outputs": [{"pred_logits": a, "pred_boxes": b} for a, b in zip(dec_logits[:-1], dec_boxes[:-1])]}
         res["aux_outputs"].append({"pred_logits": enc_topk_logits, "pred_boxes": enc_topk_bboxes})
         res["_topk_ind"] = topk_ind
+        self.last_topk = topk_ind.detach().cpu()
         return res
 
     def forward(self, images) -> Dict:

@@ -89,3 +89,16 @@ def seeded_state_dict(template: Mapping[str, torch.Tensor], seed: int = 0) -> Di
     for k, v in template.items():
         out[k] = seeded_tensor(k, v.shape, v.dtype, template, seed)
     return out
+
+
+def desaturate_classifiers(sd, factor: float = 0.25):
+    """Training-parity fixtures only: scale every score classifier (weights and biases) so that logits stay within a few units.
+    The reference's matching cost contains -log(1 - sigmoid(x) + 1e-8) (fai_detr/modelling.py:733-735); for x in ~[15, 17] the fp32
+    value of sigmoid(x) is either 1 or 1 - 2^-24 depending on the last ulp of exp(-x), which moves that term by ~2.5 - so with the
+    saturated logits of the inference fixtures (up to 18) the Hungarian assignment is not reproducible between ANY two fp32
+    implementations (torch CPU vs torch CUDA included).  Trained checkpoints do not reach that range."""
+    out = dict(sd)
+    for k, v in sd.items():
+        if "score_classifier" in k:
+            out[k] = v * factor
+    return out

@@ -10,7 +10,7 @@ import os
 import numpy as np
 import torch
 
-from focoos_b200.utils.seeded_weights import seeded_state_dict
+from focoos_b200.utils.seeded_weights import desaturate_classifiers, seeded_state_dict
 from oracle import ref_import
 from oracle.gen_golden import synth_images
 
@@ -37,13 +37,42 @@ def main(size=192, B=2):
     from focoos.models.fai_detr.ports import DETRTargets
 
     model = fm.model
-    sd = seeded_state_dict(model.state_dict(), seed=0)
+    sd = desaturate_classifiers(seeded_state_dict(model.state_dict(), seed=0))
     model.load_state_dict(sd, strict=True)
     model.train()
     imgs = np.stack(synth_images(5, [(size, size)] * B))
     x = torch.from_numpy(imgs).permute(0, 3, 1, 2).float()
     targets = synth_targets(6, B, model.config.num_classes)
-    out = model(x, [DETRTargets(labels=t[0], boxes=t[1]) for t in targets])
+    recorded = []  # the matcher's assignments in call order: final layer, aux_0..aux_4 (decoder layers), aux_5 (encoder proposals)
+    matcher = model.head.criterion.matcher
+    orig_forward = matcher.forward
+
+    def recording_forward(outputs, tg):
+        idx = orig_forward(outputs, tg)
+        row = []
+        for (qi, tj), t in zip(idx, tg):
+            mq = torch.empty(len(t.labels), dtype=torch.int64)
+            mq[tj] = qi
+            row.append(mq)
+        recorded.append(torch.cat(row))
+        return idx
+
+    matcher.forward = recording_forward
+    topk_calls = []  # the query selection (modelling.py:1214) is the only torch.topk of the training forward
+    orig_topk = torch.topk
+
+    def recording_topk(*a, **k):
+        r = orig_topk(*a, **k)
+        topk_calls.append(r[1].clone())
+        return r
+
+    torch.topk = recording_topk
+    try:
+        out = model(x, [DETRTargets(labels=t[0], boxes=t[1]) for t in targets])
+    finally:
+        torch.topk = orig_topk
+        matcher.forward = orig_forward
+    assert len(topk_calls) == 1 and len(recorded) == 7
     losses = out.loss
     sum(losses.values()).backward()
     names = [n for n, p in model.named_parameters() if p.requires_grad]
@@ -66,7 +95,7 @@ def main(size=192, B=2):
     keys = sorted(losses.keys())
     bufs = dict(model.named_buffers())
     blob = {"loss_keys": np.array(keys), "loss_values": np.array([float(losses[k]) for k in keys], dtype=np.float64), "param_names": np.array(names), "grad_has": has,
-            "grad_norm": gnorm, "grad_sum": gsum, "size": np.array([size, B]), "total_grad_norm": np.array(total_norm), "step_delta_norm": dnorm, "step_delta_sum": dsum}
+            "grad_norm": gnorm, "grad_sum": gsum, "size": np.array([size, B]), "total_grad_norm": np.array(total_norm), "match_q": torch.stack(recorded).numpy().astype(np.int32), "topk_ind": topk_calls[0].numpy().astype(np.int32), "step_delta_norm": dnorm, "step_delta_sum": dsum}
     for n in FULL:
         blob["grad::" + n] = full[n]
     for n in BN_BUFFERS:

@@ -12,6 +12,7 @@ from focoos_b200.criterion import DETRTargets
 from oracle.gen_golden import synth_images
 from oracle.gen_golden_train import BN_BUFFERS, FULL, synth_targets
 from oracle.ops_ref import RefBackend
+from focoos_b200.utils.seeded_weights import desaturate_classifiers
 from tests.parity_utils import load_golden, seeded_sd
 
 
@@ -69,7 +70,7 @@ def check_against_golden(model, losses, g, loss_rtol, grad_rtol):
 def test_train_step_matches_reference_golden(ref_backend):
     g = load_golden("detr_l_train_b2_192")
     m = FAIDetr(DETRConfig(), precision="fp32")
-    m.load_state_dict(seeded_sd(0), strict=True)
+    m.load_state_dict(desaturate_classifiers(seeded_sd(0)), strict=True)
     losses = run_step(m, g)
     worst = check_against_golden(m, losses, g, loss_rtol=1e-4, grad_rtol=2e-3)
     print("worst relative gradient-norm error:", worst)
@@ -82,7 +83,7 @@ def test_full_iteration_matches_reference_optimizer_step(ref_backend):
 
     g = load_golden("detr_l_train_b2_192")
     m = FAIDetr(DETRConfig(), precision="fp32")
-    m.load_state_dict(seeded_sd(0), strict=True)
+    m.load_state_dict(desaturate_classifiers(seeded_sd(0)), strict=True)
     m.train()
     opt = FlatAdamW(get_optimizer_params(m, base_lr=5e-4, weight_decay=0.02, weight_decay_norm=0.0, backbone_multiplier=0.1), clip_gradients=0.1, amp=False)
     opt.track_unused_parameters()
