@@ -12,6 +12,7 @@ for s in $STAGES; do
     optbench*) N=${s#optbench}; N=${N:-1}; timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tools/bench_train_step.py > gpurun_out/bench_train_step_$N.log 2>&1 ;;
     bwd)  timeout 1200 python -m pytest tests/test_gpu_backward.py -q -m gpu 2>&1 | tail -120 > gpurun_out/t_bwd.log ;;
     train)  timeout 1500 python -m pytest tests/test_gpu_train.py -q -m gpu -s 2>&1 | tail -80 > gpurun_out/t_train.log ;;
+    trainbench*) N=${s#trainbench}; N=${N:-1}; timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 tools/bench_train.py > gpurun_out/bench_train_$N.log 2>&1 ;;
     tc)    timeout 900 python -m pytest tests/test_gpu_conv_tc.py -q -m gpu 2>&1 | tail -80 > gpurun_out/t_tc.log ;;
     e2e)   timeout 1200 python -m pytest tests/test_gpu_e2e.py -q -m gpu 2>&1 | tail -60 > gpurun_out/t_e2e.log ;;
     smoke) timeout 600 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1 ;;
