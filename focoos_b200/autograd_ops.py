@@ -27,7 +27,7 @@ from . import ops
 from .ops import CudaBackend, _p, _stream
 
 ops.EXPORTED_SYMBOLS = ops.EXPORTED_SYMBOLS + (
-    "fb200_conv_wgrad_workspace_bytes", "fb200_conv_wgrad", "fb200_dilate2", "fb200_col_workspace_bytes", "fb200_colsum", "fb200_bn_train_fwd", "fb200_bn_train_bwd",
+    "fb200_conv_wgrad_workspace_bytes", "fb200_conv_wgrad", "fb200_conv_wgrad_tc_supported", "fb200_conv_wgrad_tc_workspace_bytes", "fb200_conv_wgrad_tc", "fb200_dilate2", "fb200_col_workspace_bytes", "fb200_colsum", "fb200_bn_train_fwd", "fb200_bn_train_bwd",
     "fb200_add_act", "fb200_maxpool3x3s2_bwd", "fb200_avgpool2x2_ceil_bwd", "fb200_resize_bilinear_bwd", "fb200_layernorm_bwd", "fb200_attention_bwd", "fb200_msda_bwd")
 
 _f = ctypes.c_float
@@ -45,6 +45,21 @@ def _cb_conv_wgrad(self, x, dy, KH, KW, stride, pad, dw):
     self.lib.fb200_conv_wgrad_workspace_bytes.restype = ctypes.c_int64
     ws = _ws(self.lib.fb200_conv_wgrad_workspace_bytes(B, Ho, Wo, Cin, Cout, KH, KW), x.device)
     self._call("fb200_conv_wgrad", _p(x), B, H, W, Cin, x.stride(2), _p(dy), Ho, Wo, Cout, dy.stride(2), KH, KW, stride, pad, _p(dw), 0, _p(ws), _stream())
+
+
+def _cb_conv_wgrad_tc_supported(self, x_shape, dy_shape, KH, KW, stride, pad):
+    B, H, W, Cin = x_shape
+    _, Ho, Wo, Cout = dy_shape
+    return bool(self.lib.fb200_conv_wgrad_tc_supported(B, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad))
+
+
+def _cb_conv_wgrad_tc(self, x_pair, dy_pair, KH, KW, pad, dw):
+    self._cuda(x_pair, dy_pair, dw)
+    B, H, W, C2 = x_pair.shape
+    Cin, Cout = C2 // 2, dy_pair.shape[-1] // 2
+    self.lib.fb200_conv_wgrad_tc_workspace_bytes.restype = ctypes.c_int64
+    ws = _ws(self.lib.fb200_conv_wgrad_tc_workspace_bytes(B, H, W, Cin, Cout, KH, KW), x_pair.device)
+    self._call("fb200_conv_wgrad_tc", _p(x_pair), B, H, W, Cin, _p(dy_pair), Cout, KH, KW, pad, _p(dw), 0, _p(ws), _stream())
 
 
 def _cb_dilate2(self, dy, out):
@@ -125,7 +140,7 @@ def _cb_msda_bwd(self, value, oa, ref, do, shapes, P, heads, dvalue, doa):
                dvalue.stride(1), _p(doa), doa.stride(1), _stream())
 
 
-for _n, _fn in (("conv_wgrad", _cb_conv_wgrad), ("dilate2", _cb_dilate2), ("colsum", _cb_colsum), ("bn_train_fwd", _cb_bn_train_fwd), ("bn_train_bwd", _cb_bn_train_bwd),
+for _n, _fn in (("conv_wgrad", _cb_conv_wgrad), ("conv_wgrad_tc_supported", _cb_conv_wgrad_tc_supported), ("conv_wgrad_tc", _cb_conv_wgrad_tc), ("dilate2", _cb_dilate2), ("colsum", _cb_colsum), ("bn_train_fwd", _cb_bn_train_fwd), ("bn_train_bwd", _cb_bn_train_bwd),
                 ("add_act", _cb_add_act), ("maxpool_bwd", _cb_maxpool_bwd), ("avgpool_bwd", _cb_avgpool_bwd), ("resize_bwd", _cb_resize_bwd),
                 ("layernorm_bwd", _cb_layernorm_bwd), ("attention_bwd", _cb_attention_bwd), ("msda_bwd", _cb_msda_bwd)):
     setattr(CudaBackend, _n, _fn)
@@ -155,6 +170,18 @@ def conv_any(x, w_khwc, bias, stride: int, pad: int, precision: str, act=ops.ACT
     if ok:
         return ops.conv2d(ops.split_pair(x), _split3_weights(w_khwc), None, bias, stride=stride, pad=pad, act=act, out_dtype=torch.float32, algo=ops.ALGO_TCGEN05_SPLIT3)
     return ops.conv2d(x, w_khwc, None, bias, stride=stride, pad=pad, act=act, algo=ops.ALGO_SIMT)
+
+
+def weight_grad(x, dy, KH, KW, stride, pad, precision):
+    """dW [Cout,KH,KW,Cin] fp32 of a conv (or a linear as 1x1 over [1,1,M,K]): tensor cores (split precision) when the shape allows, else SIMT fp32."""
+    be = ops._be()
+    Cout, Cin = dy.shape[-1], x.shape[-1]
+    dwk = torch.empty((Cout, KH, KW, Cin), dtype=torch.float32, device=dy.device)
+    if precision == "fp32_tc" and x.is_contiguous() and dy.is_contiguous() and be.conv_wgrad_tc_supported(tuple(x.shape), tuple(dy.shape), KH, KW, stride, pad):
+        be.conv_wgrad_tc(ops.split_pair(x), ops.split_pair(dy), KH, KW, pad, dwk)
+    else:
+        be.conv_wgrad(x, dy, KH, KW, stride, pad, dwk)
+    return dwk
 
 
 class Conv2dFn(torch.autograd.Function):
@@ -189,9 +216,7 @@ class Conv2dFn(torch.autograd.Function):
             dx = conv_any(g, wt, None, 1, KH - 1 - pad, precision)
             assert dx.shape == x.shape, (dx.shape, x.shape)
         if ctx.needs_input_grad[1]:
-            dwk = torch.empty((Cout, KH, KW, Cin), dtype=torch.float32, device=dy.device)
-            be.conv_wgrad(x, dy, KH, KW, stride, pad, dwk)
-            dw = dwk.permute(0, 3, 1, 2)
+            dw = weight_grad(x, dy, KH, KW, stride, pad, precision).permute(0, 3, 1, 2)
         if has_bias and ctx.needs_input_grad[2]:
             db = torch.empty(Cout, dtype=torch.float32, device=dy.device)
             be.colsum(dy.reshape(-1, Cout), db)
@@ -281,9 +306,7 @@ class LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = conv_any(g2, w.t().contiguous().reshape(K, 1, 1, N), None, 1, 0, precision).reshape(x.shape)
         if ctx.needs_input_grad[1]:
-            dwk = torch.empty((N, 1, 1, K), dtype=torch.float32, device=x.device)
-            be.conv_wgrad(x.reshape(1, 1, -1, K), g2, 1, 1, 1, 0, dwk)
-            dw = dwk.reshape(N, K)
+            dw = weight_grad(x.reshape(1, 1, -1, K), g2, 1, 1, 1, 0, precision).reshape(N, K)
         if has_bias and ctx.needs_input_grad[2]:
             db = torch.empty(N, dtype=torch.float32, device=x.device)
             be.colsum(g2.reshape(-1, N), db)

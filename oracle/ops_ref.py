@@ -386,6 +386,20 @@ def _rb_conv_wgrad(self, x, dy, KH, KW, stride, pad, dw):
     dw.copy_(g.permute(0, 2, 3, 1))
 
 
+def _rb_conv_wgrad_tc_supported(self, x_shape, dy_shape, KH, KW, stride, pad):
+    B, H, W, Cin = x_shape
+    Cout = dy_shape[-1]
+    return stride == 1 and KH == KW and KH in (1, 3) and 2 * pad == KH - 1 and Cin % 8 == 0 and Cout % 8 == 0 and B * H * W >= 512
+
+
+def _rb_conv_wgrad_tc(self, x_pair, dy_pair, KH, KW, pad, dw):
+    Cin, Cout = x_pair.shape[-1] // 2, dy_pair.shape[-1] // 2
+    xh, xl = x_pair[..., :Cin].float(), x_pair[..., Cin:].float()
+    dh, dl = dy_pair[..., :Cout].float(), dy_pair[..., Cout:].float()
+    g = lambda a, b: torch.nn.grad.conv2d_weight(_nchw(a).contiguous(), (Cout, Cin, KH, KW), _nchw(b).contiguous(), stride=1, padding=pad)
+    dw.copy_((g(xh, dh) + g(xl, dh) + g(xh, dl)).permute(0, 2, 3, 1))
+
+
 def _rb_dilate2(self, dy, out):
     out.zero_()
     out[:, : 2 * dy.shape[1] : 2, : 2 * dy.shape[2] : 2] = dy
@@ -512,7 +526,7 @@ def _rb_msda_bwd(self, value, oa, ref, do, shapes, P, heads, dvalue, doa):
     doa.copy_(go)
 
 
-for _n, _f in (("conv_wgrad", _rb_conv_wgrad), ("dilate2", _rb_dilate2), ("colsum", _rb_colsum), ("bn_train_fwd", _rb_bn_train_fwd), ("bn_train_bwd", _rb_bn_train_bwd),
+for _n, _f in (("conv_wgrad", _rb_conv_wgrad), ("conv_wgrad_tc_supported", _rb_conv_wgrad_tc_supported), ("conv_wgrad_tc", _rb_conv_wgrad_tc), ("dilate2", _rb_dilate2), ("colsum", _rb_colsum), ("bn_train_fwd", _rb_bn_train_fwd), ("bn_train_bwd", _rb_bn_train_bwd),
                ("add_act", _rb_add_act), ("maxpool_bwd", _rb_maxpool_bwd), ("avgpool_bwd", _rb_avgpool_bwd), ("resize_bwd", _rb_resize_bwd),
                ("layernorm_bwd", _rb_layernorm_bwd), ("attention_bwd", _rb_attention_bwd), ("msda_bwd", _rb_msda_bwd)):
     setattr(RefBackend, _n, _f)
