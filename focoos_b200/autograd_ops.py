@@ -154,69 +154,93 @@ def _split3_weights(w):
     return torch.cat([hi, lo, hi], dim=-1).contiguous()
 
 
-def conv_any(x, w_khwc, bias, stride: int, pad: int, precision: str, act=ops.ACT_NONE):
-    """x NHWC fp32, w [Cout,KH,KW,Cin] fp32 -> NHWC fp32 through the SIMT fp32 or the split-precision tcgen05 kernel."""
+def conv_any(x, w_khwc, bias, stride: int, pad: int, precision: str, act=ops.ACT_NONE, x_pair=None, return_pair=False):
+    """x NHWC fp32, w [Cout,KH,KW,Cin] fp32 -> NHWC fp32 through the SIMT fp32 or the split-precision tcgen05 kernel.
+    x_pair: the [hi|lo] fp16 pair of x if the caller already has it; return_pair: also return the pair used (None on the SIMT path)."""
     B, H, W, C = x.shape
     Cout, KH, KW, _ = w_khwc.shape
     Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
-    if C % 4:  # the 3-channel image: zero-pad the channel dimension (the SIMT kernel reads 16-byte vectors)
-        padc = 4 - C % 4
-        x = torch.nn.functional.pad(x, (0, padc))
-        w_khwc = torch.nn.functional.pad(w_khwc, (0, padc))
-        C += padc
     geom = (stride == 1 and (2 * pad == KH - 1)) or (stride == 2 and KH == 3 and pad == 1 and H % 2 == 0 and W % 2 == 0)  # conv_tc.cu: conv2d_tc_supported
     ok = (precision == "fp32_tc" and (x.is_cuda or ops._backend is not None) and C % 32 == 0 and Cout % 4 == 0 and B * Ho * Wo >= 64 and x.is_contiguous()
           and KH == KW and geom and act in (ops.ACT_NONE, ops.ACT_RELU, ops.ACT_SILU))
     if ok:
-        return ops.conv2d(ops.split_pair(x), _split3_weights(w_khwc), None, bias, stride=stride, pad=pad, act=act, out_dtype=torch.float32, algo=ops.ALGO_TCGEN05_SPLIT3)
-    return ops.conv2d(x, w_khwc, None, bias, stride=stride, pad=pad, act=act, algo=ops.ALGO_SIMT)
+        xp = x_pair if x_pair is not None else ops.split_pair(x)
+        y = ops.conv2d(xp, _split3_weights(w_khwc), None, bias, stride=stride, pad=pad, act=act, out_dtype=torch.float32, algo=ops.ALGO_TCGEN05_SPLIT3)
+        return (y, xp) if return_pair else y
+    if C % 4:  # the 3-channel image: zero-pad the channel dimension (the SIMT kernel reads 16-byte vectors)
+        padc = 4 - C % 4
+        x = torch.nn.functional.pad(x, (0, padc))
+        w_khwc = torch.nn.functional.pad(w_khwc, (0, padc))
+    y = ops.conv2d(x, w_khwc, None, bias, stride=stride, pad=pad, act=act, algo=ops.ALGO_SIMT)
+    return (y, None) if return_pair else y
 
 
-def weight_grad(x, dy, KH, KW, stride, pad, precision):
-    """dW [Cout,KH,KW,Cin] fp32 of a conv (or a linear as 1x1 over [1,1,M,K]): tensor cores (split precision) when the shape allows, else SIMT fp32."""
+def wgrad_on_tensor_cores(x_shape, dy_shape, KH, KW, stride, pad, precision) -> bool:
+    return precision == "fp32_tc" and ops._be().conv_wgrad_tc_supported(tuple(x_shape), tuple(dy_shape), KH, KW, stride, pad)
+
+
+def weight_grad(x, dy, KH, KW, stride, pad, precision, x_pair=None, dy_pair=None):
+    """dW [Cout,KH,KW,Cin] fp32 of a conv (or a linear as 1x1 over [1,1,M,K]): tensor cores (split precision) when the shape allows, else SIMT fp32.
+    x / dy may be None when the corresponding pair is given and the shape takes the tensor-core path."""
     be = ops._be()
-    Cout, Cin = dy.shape[-1], x.shape[-1]
-    dwk = torch.empty((Cout, KH, KW, Cin), dtype=torch.float32, device=dy.device)
-    if precision == "fp32_tc" and x.is_contiguous() and dy.is_contiguous() and be.conv_wgrad_tc_supported(tuple(x.shape), tuple(dy.shape), KH, KW, stride, pad):
-        be.conv_wgrad_tc(ops.split_pair(x), ops.split_pair(dy), KH, KW, pad, dwk)
+    Cout = dy.shape[-1] if dy is not None else dy_pair.shape[-1] // 2
+    xs = tuple(x.shape) if x is not None else (*x_pair.shape[:-1], x_pair.shape[-1] // 2)
+    ds = (*xs[:1], (xs[1] + 2 * pad - KH) // stride + 1, (xs[2] + 2 * pad - KW) // stride + 1, Cout)
+    dev = (dy if dy is not None else dy_pair).device
+    dwk = torch.empty((Cout, KH, KW, xs[-1]), dtype=torch.float32, device=dev)
+    if wgrad_on_tensor_cores(xs, ds, KH, KW, stride, pad, precision):
+        xp = x_pair if x_pair is not None else ops.split_pair(x.contiguous())
+        dp = dy_pair if dy_pair is not None else ops.split_pair(dy.contiguous())
+        be.conv_wgrad_tc(xp, dp, KH, KW, pad, dwk)
     else:
         be.conv_wgrad(x, dy, KH, KW, stride, pad, dwk)
     return dwk
 
 
 class Conv2dFn(torch.autograd.Function):
-    """x [B,H,W,Cin] NHWC, w [Cout,Cin,KH,KW] (state_dict layout), bias [Cout] or None."""
+    """x [B,H,W,Cin] NHWC, w [Cout,Cin,KH,KW] (state_dict layout), bias [Cout] or None.
+    In the tensor-core mode the activation is saved for backward as its [hi|lo] fp16 pair (same bytes as fp32) - the operand format of both
+    the forward conv and the weight-gradient kernel - so it is split once, not three times."""
 
     @staticmethod
     def forward(ctx, x, w, bias, stride, pad, precision):
         x = x.contiguous()
-        ctx.save_for_backward(x, w)
-        ctx.cfg = (stride, pad, precision, bias is not None)
-        return conv_any(x, w.permute(0, 2, 3, 1).contiguous(), bias, stride, pad, precision)
+        Cout, _, KH, KW = w.shape
+        y, xp = conv_any(x, w.permute(0, 2, 3, 1).contiguous(), bias, stride, pad, precision, return_pair=True)
+        keep_pair = xp is not None and wgrad_on_tensor_cores(x.shape, y.shape, KH, KW, stride, pad, precision)
+        ctx.save_for_backward(xp if keep_pair else x, w)
+        ctx.cfg = (stride, pad, precision, bias is not None, keep_pair, tuple(x.shape))
+        return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, w = ctx.saved_tensors
-        stride, pad, precision, has_bias = ctx.cfg
+        saved, w = ctx.saved_tensors
+        stride, pad, precision, has_bias, keep_pair, xshape = ctx.cfg
         dy = dy.contiguous()
-        B, H, W, Cin = x.shape
+        B, H, W, Cin = xshape
         Cout, _, KH, KW = w.shape
         be = ops._be()
         dx = dw = db = None
+        dyp = None
+        if keep_pair or (precision == "fp32_tc" and stride == 1 and ctx.needs_input_grad[0] and Cout % 32 == 0):
+            dyp = ops.split_pair(dy)  # shared by the data-gradient conv and the weight-gradient GEMM
         if ctx.needs_input_grad[0]:
             # data gradient: correlation of (dilated) dy with the spatially flipped, in/out-transposed filter
             wt = w.flip(2, 3).permute(1, 2, 3, 0).contiguous()  # [Cin,KH,KW,Cout]
-            g = dy
+            g, gp = dy, dyp
             if stride == 2:
                 Hd, Wd = H + 2 * pad - KH + 1, W + 2 * pad - KW + 1
-                g = torch.empty((B, Hd, Wd, Cout), dtype=torch.float32, device=dy.device)
+                g, gp = torch.empty((B, Hd, Wd, Cout), dtype=torch.float32, device=dy.device), None
                 be.dilate2(dy, g)
             elif stride != 1:
                 raise NotImplementedError("focoos_b200: conv data gradient for stride > 2")
-            dx = conv_any(g, wt, None, 1, KH - 1 - pad, precision)
-            assert dx.shape == x.shape, (dx.shape, x.shape)
+            dx = conv_any(g, wt, None, 1, KH - 1 - pad, precision, x_pair=gp)
+            assert tuple(dx.shape) == tuple(xshape), (dx.shape, xshape)
         if ctx.needs_input_grad[1]:
-            dw = weight_grad(x, dy, KH, KW, stride, pad, precision).permute(0, 3, 1, 2)
+            if keep_pair:
+                dw = weight_grad(None, dy, KH, KW, stride, pad, precision, x_pair=saved, dy_pair=dyp).permute(0, 3, 1, 2)
+            else:
+                dw = weight_grad(saved, dy, KH, KW, stride, pad, precision).permute(0, 3, 1, 2)
         if has_bias and ctx.needs_input_grad[2]:
             db = torch.empty(Cout, dtype=torch.float32, device=dy.device)
             be.colsum(dy.reshape(-1, Cout), db)
@@ -285,16 +309,19 @@ class LinearFn(torch.autograd.Function):
         assert act in (ops.ACT_NONE, ops.ACT_RELU)
         x = x.contiguous()
         K, N = x.shape[-1], w.shape[0]
-        y = conv_any(x.reshape(1, 1, -1, K), w.reshape(N, 1, 1, K).contiguous(), bias, 1, 0, precision, act=act).reshape(*x.shape[:-1], N)
-        ctx.save_for_backward(x, w, y if act == ops.ACT_RELU else None)
-        ctx.cfg = (act, precision, bias is not None)
+        x4 = x.reshape(1, 1, -1, K)
+        y4, xp = conv_any(x4, w.reshape(N, 1, 1, K).contiguous(), bias, 1, 0, precision, act=act, return_pair=True)
+        y = y4.reshape(*x.shape[:-1], N)
+        keep_pair = xp is not None and wgrad_on_tensor_cores(x4.shape, y4.shape, 1, 1, 1, 0, precision)
+        ctx.save_for_backward(xp if keep_pair else x, w, y if act == ops.ACT_RELU else None)
+        ctx.cfg = (act, precision, bias is not None, keep_pair, tuple(x.shape))
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, w, y = ctx.saved_tensors
-        act, precision, has_bias = ctx.cfg
-        K, N = x.shape[-1], w.shape[0]
+        saved, w, y = ctx.saved_tensors
+        act, precision, has_bias, keep_pair, xshape = ctx.cfg
+        K, N = xshape[-1], w.shape[0]
         be = ops._be()
         g = dy.contiguous()
         if act == ops.ACT_RELU:  # dy * relu'(y): y > 0 <=> pre-activation > 0
@@ -302,13 +329,17 @@ class LinearFn(torch.autograd.Function):
             be.add_act(y, None, g, ops.ACT_RELU, gm)
             g = gm
         g2 = g.reshape(1, 1, -1, N)
+        gp = ops.split_pair(g2) if (keep_pair or (precision == "fp32_tc" and N % 32 == 0 and g2.shape[2] >= 64 and ctx.needs_input_grad[0])) else None
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = conv_any(g2, w.t().contiguous().reshape(K, 1, 1, N), None, 1, 0, precision).reshape(x.shape)
+            dx = conv_any(g2, w.t().contiguous().reshape(K, 1, 1, N), None, 1, 0, precision, x_pair=gp).reshape(xshape)
         if ctx.needs_input_grad[1]:
-            dw = weight_grad(x.reshape(1, 1, -1, K), g2, 1, 1, 1, 0, precision).reshape(N, K)
+            if keep_pair:
+                dw = weight_grad(None, g2, 1, 1, 1, 0, precision, x_pair=saved, dy_pair=gp).reshape(N, K)
+            else:
+                dw = weight_grad(saved.reshape(1, 1, -1, K), g2, 1, 1, 1, 0, precision).reshape(N, K)
         if has_bias and ctx.needs_input_grad[2]:
-            db = torch.empty(N, dtype=torch.float32, device=x.device)
+            db = torch.empty(N, dtype=torch.float32, device=g.device)
             be.colsum(g2.reshape(-1, N), db)
         return dx, dw, db, None, None
 

@@ -60,7 +60,8 @@ def check_against_golden(model, losses, g, loss_rtol, grad_rtol):
     for n in FULL:
         ref = g["grad::" + n]
         d = float(np.abs(params[n].grad.detach().cpu().numpy() - ref).max())
-        assert d <= 5 * grad_rtol * max(float(np.abs(ref).max()), 1e-8), f"{n}: full gradient differs by {d:.3e}"  # element-wise: 5x the norm tolerance
+        tol = 5e-2 if "sampling_offsets" in n else 5 * grad_rtol  # element-wise: 5x the norm tolerance; bilinear kinks as above
+        assert d <= tol * max(float(np.abs(ref).max()), 1e-8), f"{n}: full gradient differs by {d:.3e}"
     bufs = dict(model.named_buffers())
     for n in BN_BUFFERS:
         np.testing.assert_allclose(bufs[n].detach().cpu().numpy(), g["buf::" + n], rtol=1e-4, atol=1e-6, err_msg=n)
@@ -109,3 +110,15 @@ def test_full_iteration_matches_reference_optimizer_step(ref_backend):
         else:
             # first Adam step: |delta| = lr * |g| / (|g| + eps) per element, i.e. ~lr for every element whose gradient is well above eps
             assert abs(mine - dn) <= 2e-2 * dn + 1e-9, f"{n}: |delta| {mine:.4e} vs reference {dn:.4e}"
+
+
+def test_tensor_core_mode_host_logic(ref_backend):
+    """precision="fp32_tc": activations saved as [hi|lo] pairs, pairs shared between the data- and weight-gradient kernels, split-precision
+    weight gradients - the host-side bookkeeping, with the CPU references standing in for the tensor-core kernels (assignments teacher-forced)."""
+    g = load_golden("detr_l_train_b2_192")
+    m = FAIDetr(DETRConfig(), precision="fp32_tc")
+    m.load_state_dict(desaturate_classifiers(seeded_sd(0)), strict=True)
+    m.criterion().forced_match = torch.from_numpy(g["match_q"])
+    m.train_graph().forced_topk = torch.from_numpy(g["topk_ind"])
+    losses = run_step(m, g)
+    check_against_golden(m, losses, g, loss_rtol=5e-4, grad_rtol=4e-3)
