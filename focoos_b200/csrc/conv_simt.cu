@@ -255,10 +255,31 @@ extern "C" int fb200_stem_conv3x3s2_u8(const uint8_t* img_nhwc, int B, int H, in
   return stem_launch(img_nhwc, true, B, H, W, w, scale, bias, mean3, std3, act, out, out_dtype, Cout, stream);
 }
 
+static int conv2d_impl(const void* x, int x_dtype, int B, int H, int W, int Cin, int x_pitch, const void* w, int64_t w_bs, int KH,
+                       int KW, int stride, int pad, const float* scale, const float* bias, const void* residual,
+                       int res_pitch, int act, void* out, int out_dtype, int out_pitch, int64_t out_batch_stride, int Cout,
+                       int algo, void* stream);
+
 extern "C" int fb200_conv2d(const void* x, int x_dtype, int B, int H, int W, int Cin, int x_pitch, const void* w, int KH,
                             int KW, int stride, int pad, const float* scale, const float* bias, const void* residual,
                             int res_pitch, int act, void* out, int out_dtype, int out_pitch, int64_t out_batch_stride, int Cout,
                             int algo, void* stream) {
+  return conv2d_impl(x, x_dtype, B, H, W, Cin, x_pitch, w, 0, KH, KW, stride, pad, scale, bias, residual, res_pitch, act, out, out_dtype, out_pitch, out_batch_stride,
+                     Cout, algo, stream);
+}
+
+extern "C" int fb200_conv2d_per_image_weights(const void* x, int x_dtype, int B, int H, int W, int Cin, int x_pitch, const void* w, int64_t w_batch_stride,
+                                              int KH, int KW, int stride, int pad, const float* scale, const float* bias, int act, void* out, int out_dtype,
+                                              int out_pitch, int Cout, int algo, void* stream) {
+  FB_CHECK_ARG(w_batch_stride >= (int64_t)Cout * KH * KW * Cin, "conv2d_per_image_weights: weight batch stride smaller than one weight set");
+  return conv2d_impl(x, x_dtype, B, H, W, Cin, x_pitch, w, w_batch_stride, KH, KW, stride, pad, scale, bias, nullptr, 0, act, out, out_dtype, out_pitch, 0, Cout, algo,
+                     stream);
+}
+
+static int conv2d_impl(const void* x, int x_dtype, int B, int H, int W, int Cin, int x_pitch, const void* w, int64_t w_bs, int KH,
+                       int KW, int stride, int pad, const float* scale, const float* bias, const void* residual,
+                       int res_pitch, int act, void* out, int out_dtype, int out_pitch, int64_t out_batch_stride, int Cout,
+                       int algo, void* stream) {
   FB_CHECK_ARG(x && w && out, "conv2d: null pointer");
   FB_CHECK_ARG(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && stride > 0 && pad >= 0, "conv2d: bad shape");
   FB_CHECK_ARG(x_pitch >= Cin && out_pitch >= Cout, "conv2d: pitch smaller than channel count");
@@ -280,11 +301,25 @@ extern "C" int fb200_conv2d(const void* x, int x_dtype, int B, int H, int W, int
   p.out_bs = out_batch_stride > 0 ? out_batch_stride : (int64_t)p.Ho * p.Wo * out_pitch;
   p.vec_ok = p.vec_ok && (p.out_bs % 4 == 0);
   cudaStream_t st = (cudaStream_t)stream;
+  p.w_bs = w_bs;
   const bool tc_ok = conv2d_tc_supported(p, x_dtype, out_dtype);
   if (algo == FB200_ALGO_TCGEN05 && !tc_ok) {
     set_error("conv2d: tcgen05 path does not support this shape/dtype (Cin=%d Cout=%d k=%dx%d s=%d dtype=%d/%d)", Cin, Cout, KH, KW, stride, x_dtype, out_dtype);
     return FB200_ERR_UNSUPPORTED;
   }
   if ((algo == FB200_ALGO_AUTO && tc_ok) || algo == FB200_ALGO_TCGEN05) return conv2d_tc(p, st);
+  if (w_bs != 0) {  // CUDA-core path: one launch per image (the parity mode; the tensor-core path batches them)
+    const size_t xe = x_dtype == FB200_F16 ? 2 : 4, oe = out_dtype == FB200_F16 ? 2 : 4;
+    ConvParams q = p;
+    q.B = 1; q.M = (int64_t)p.Ho * p.Wo; q.w_bs = 0;
+    for (int b = 0; b < B; ++b) {
+      q.x = static_cast<const char*>(x) + (size_t)b * H * W * x_pitch * xe;
+      q.w = static_cast<const char*>(w) + (size_t)b * w_bs * xe;
+      q.out = static_cast<char*>(out) + (size_t)b * p.out_bs * oe;
+      const int rc = conv2d_simt(q, x_dtype, out_dtype, st);
+      if (rc) return rc;
+    }
+    return FB200_OK;
+  }
   return conv2d_simt(p, x_dtype, out_dtype, st);
 }

@@ -50,6 +50,7 @@ struct KParams {
   int stride2;                     // 0: 4-D stride-1 view, 1: 5-D stride-2 view
   int num_k_blocks;
   int n_tiles, total_tiles;        // N tiles per M tile; total = m_tiles * n_tiles
+  int w_batched;                   // 1: weights differ per image (3-D weight map, third coordinate = image)
   int dbg;                         // tuning aid (env FB200_TC_DBG): 1 = skip TMA store, 2 = skip residual, 4 = skip TMEM load
 };
 
@@ -89,6 +90,10 @@ __device__ __forceinline__ void epi_bar(int grp) { asm volatile("bar.sync %0, 12
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -268,7 +273,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const int dw = (kw == 0) ? -1 : 0, wp = (kw == 1) ? 0 : 1;
             tma_load_5d(&tmap_a, &full_bar[stage], dst_a, wp * p.x_pitch + a_c0, w0 + dw, hp, h0 + dh, img);
           }
-          tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb * BLOCK_K, n0);
+          if (p.w_batched) tma_load_3d(&tmap_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb * BLOCK_K, n0, img);
+          else tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb * BLOCK_K, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -543,6 +549,7 @@ bool conv2d_tc_supported(const ConvParams& p, int x_dtype, int out_dtype) {
   if (p.res && ((p.res_pitch * oelt) % 16 != 0 || (reinterpret_cast<uintptr_t>(p.res) & 15))) return false;
   if (p.res && p.Cout % (128 / oelt) != 0) return false;  // residual is consumed in whole 128-byte row chunks
   if (p.KH != p.KW) return false;
+  if (p.w_bs != 0 && (p.w_bs * 2) % 16 != 0) return false;
   if ((p.act & 15) == FB200_ACT_GELU && (out_dtype != FB200_F16 || Clog % 64 != 0)) return false;
   if ((p.act & 15) == FB200_ACT_SIGMOID) return false;  // gates are [B, C] vectors: SIMT path
   if ((p.out_bs * oelt) % 16 != 0) return false;
@@ -566,7 +573,8 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
   kp.num_k_blocks = p.KH * p.KW * kp.cchunks;
   // geometry: 1x1 stride-1 convs and linears flatten to W = M, H = 1, B = 1
   int B = p.B, H = p.H, W = p.W, Ho = p.Ho, Wo = p.Wo;
-  const bool flat = (p.KH == 1 && p.stride == 1 && p.out_bs == (int64_t)p.Ho * p.Wo * p.out_pitch);
+  const bool flat = (p.KH == 1 && p.stride == 1 && p.out_bs == (int64_t)p.Ho * p.Wo * p.out_pitch) && p.w_bs == 0;
+  kp.w_batched = p.w_bs != 0 ? 1 : 0;
   if (flat) {
     if (p.M > 0x7fffffffLL) { set_error("conv_tc: M too large"); return FB200_ERR_UNSUPPORTED; }
     W = Wo = (int)p.M; H = Ho = 1; B = 1;
@@ -599,10 +607,10 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
     constexpr int BK_ = decltype(bk_tag)::value;
     constexpr int NS_ = decltype(nstg_tag)::value;
     {
-      const uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.Cout};
-      const uint64_t str[2] = {1, (uint64_t)p.K};
-      const uint32_t box[2] = {(uint32_t)BK_, (uint32_t)BN_};
-      int r2 = encode(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 2, const_cast<void*>(p.w), dims, str, box, "W", swz);
+      const uint64_t dims[3] = {(uint64_t)p.K, (uint64_t)p.Cout, (uint64_t)p.B};
+      const uint64_t str[3] = {1, (uint64_t)p.K, (uint64_t)p.w_bs};
+      const uint32_t box[3] = {(uint32_t)BK_, (uint32_t)BN_, 1};
+      int r2 = encode(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, p.w_bs ? 3 : 2, const_cast<void*>(p.w), dims, str, box, "W", swz);
       if (r2) return r2;
     }
     const bool out16 = p.out_dtype == FB200_F16;

@@ -256,8 +256,8 @@ class MFEngine(DetrEngine):
         _, h4, w4, C = mask_features.shape
         Qp = (Q + 7) // 8 * 8
         masks = torch.zeros((B, h4, w4, Qp), dtype=dt, device=out.device)
-        for b in range(B):  # einsum("bqc,bchw->bqhw"): one [h4*w4, C] x [C, Q] GEMM per image (the "weights" differ per image)
-            ops.conv2d(mask_features[b:b + 1], me[b].reshape(Q, 1, 1, C), None, None, out=masks[b:b + 1, :, :, :Q], algo=A)
+        # einsum("bqc,bchw->bqhw"): a [h4*w4, C] x [C, Q] GEMM per image whose "weights" (the mask embeddings) differ per image - ONE launch
+        ops.conv2d_per_image(mask_features, me.reshape(B, Q, 1, 1, C), out=masks[..., :Q], algo=A)
         attn = None
         if size is not None:
             low = masks if (h4, w4) == tuple(size) else ops.resize_bilinear(masks, size)

@@ -63,7 +63,8 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = (
-    "fb200_last_error", "fb200_version", "fb200_device_supports_tcgen05", "fb200_stem_conv3x3s2", "fb200_stem_conv3x3s2_u8", "fb200_conv2d", "fb200_split_f32_pair",
+    "fb200_last_error", "fb200_version", "fb200_device_supports_tcgen05", "fb200_stem_conv3x3s2", "fb200_stem_conv3x3s2_u8", "fb200_conv2d", "fb200_conv2d_per_image_weights",
+    "fb200_split_f32_pair",
     "fb200_maxpool3x3s2", "fb200_avgpool2x2_ceil", "fb200_resize_bilinear", "fb200_add", "fb200_layernorm",
     "fb200_attention", "fb200_msda", "fb200_row_select", "fb200_rowmax", "fb200_topk", "fb200_gather_rows",
     "fb200_box_op", "fb200_detr_postprocess",
@@ -156,6 +157,13 @@ class CudaBackend:
             _trace_note.append(dict(op="conv", B=B, H=H, W=W, Cin=Cin, Cout=Cout, k=KH, stride=stride, res=residual is not None, xdt=str(x.dtype)[6:], odt=str(out.dtype)[6:], algo=algo))
         self._call("fb200_conv2d", _p(x), _dt(x), B, H, W, Cin, _pitch(x), _p(w), KH, KW, stride, pad, _p(scale), _p(bias), _p(residual),
                    0 if residual is None else _pitch(residual), act, _p(out), _dt(out), _pitch(out, True), ctypes.c_int64(_batch_stride(out)), Cout, algo, _stream())
+
+    def conv2d_per_image(self, x, w, act, out, algo):
+        self._cuda(x, w, out)
+        B, H, W, Cin = x.shape
+        _, Cout, KH, KW, _ = w.shape
+        self._call("fb200_conv2d_per_image_weights", _p(x), _dt(x), B, H, W, Cin, _pitch(x), _p(w), ctypes.c_int64(w.stride(0)), KH, KW, 1, (KH - 1) // 2, None, None, act,
+                   _p(out), _dt(out), _pitch(out, True), Cout, algo, _stream())
 
     def split_pair(self, x, out):
         self._cuda(x, out)
@@ -283,6 +291,18 @@ def conv2d(x, w, scale=None, bias=None, *, stride=1, pad=0, act=ACT_NONE, residu
     if residual is not None:
         assert residual.shape == out.shape and residual.dtype == out.dtype
     _be().conv2d(x, w, scale, bias, stride, pad, act, residual, out, algo)
+    return out
+
+
+def conv2d_per_image(x, w, *, act=ACT_NONE, out=None, out_dtype=None, algo=ALGO_AUTO):
+    """conv with one weight set per image: x [B,H,W,Cin], w [B,Cout,KH,KW,Cin] -> [B,H,W,Cout]  (the per-query mask product, one launch per batch)."""
+    assert x.dim() == 4 and w.dim() == 5 and w.shape[0] == x.shape[0] and w.shape[-1] == x.shape[-1] and w.dtype == x.dtype and w.stride(-1) == 1
+    B, H, W, _ = x.shape
+    Cout = w.shape[1]
+    if out is None:
+        out = torch.empty((B, H, W, Cout), dtype=out_dtype or x.dtype, device=x.device)
+    assert tuple(out.shape) == (B, H, W, Cout)
+    _be().conv2d_per_image(x, w.contiguous(), act, out, algo)
     return out
 
 

@@ -72,6 +72,13 @@ int fb200_conv2d(const void* x, int x_dtype, int B, int H, int W, int Cin, int x
                  int stride, int pad, const float* scale, const float* bias, const void* residual, int res_pitch,
                  int act, void* out, int out_dtype, int out_pitch, int64_t out_batch_stride, int Cout, int algo, void* stream);
 
+/* Same conv with one weight set PER IMAGE: w [B][Cout][KH][KW][Cin] (w_batch_stride elements apart).  This is the per-query mask product
+ * einsum("bqc,bchw->bqhw") of PredictionHeads.forward (models/fai_mf/modelling.py:86, bisenetformer/modelling.py:364): x = mask features
+ * [B,h,w,C], "weights" = the B x Q mask embeddings; one launch for the batch (3-D weight tensor map, third coordinate = image). */
+int fb200_conv2d_per_image_weights(const void* x, int x_dtype, int B, int H, int W, int Cin, int x_pitch, const void* w, int64_t w_batch_stride,
+                                   int KH, int KW, int stride, int pad, const float* scale, const float* bias, int act, void* out, int out_dtype,
+                                   int out_pitch, int Cout, int algo, void* stream);
+
 /* x fp32 [rows, C] (row pitch x_pitch) -> out fp16 [rows, 2C]: out[:, :C] = hi = fp16(x), out[:, C:] = lo = fp16(x - hi).
  * Operand preparation of the split-precision conv/linear mode (precision="fp32_tc"). */
 int fb200_split_f32_pair(const float* x, int64_t rows, int C, int x_pitch, void* out, void* stream);

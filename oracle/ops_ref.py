@@ -530,3 +530,11 @@ for _n, _f in (("conv_wgrad", _rb_conv_wgrad), ("conv_wgrad_tc_supported", _rb_c
                ("add_act", _rb_add_act), ("maxpool_bwd", _rb_maxpool_bwd), ("avgpool_bwd", _rb_avgpool_bwd), ("resize_bwd", _rb_resize_bwd),
                ("layernorm_bwd", _rb_layernorm_bwd), ("attention_bwd", _rb_attention_bwd), ("msda_bwd", _rb_msda_bwd)):
     setattr(RefBackend, _n, _f)
+
+
+def _rb_conv2d_per_image(self, x, w, act, out, algo):
+    for b in range(x.shape[0]):
+        self.conv2d(x[b:b + 1], w[b], None, None, 1, (w.shape[2] - 1) // 2, act, None, out[b:b + 1], algo)
+
+
+RefBackend.conv2d_per_image = _rb_conv2d_per_image

@@ -117,3 +117,20 @@ def test_split_precision_conv_matches_fp32(B, H, W, Cin, Cout, k, stride, res):
     err = float((out.cpu() - ref).abs().max())
     scale = max(1.0, float(ref.abs().max()))
     assert err <= 2e-5 * scale, f"split-precision conv: max|d|={err:.3e} scale={scale:.2e}"
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+@pytest.mark.parametrize("B,H,W,C,Q", [(3, 40, 52, 256, 100), (2, 64, 128, 128, 100), (5, 8, 8, 64, 7)])
+def test_per_image_weights_product(B, H, W, C, Q, dtype):
+    """einsum('bqc,bchw->bqhw') as ONE launch with a per-image weight set (3-D weight tensor map on the tcgen05 path)."""
+    x = rnd((B, H, W, C), dtype, 1)
+    w = rnd((B, Q, 1, 1, C), dtype, 2, 1.0 / math.sqrt(C))
+    ref = torch.einsum("bhwc,bqc->bhwq", x.float(), w.float().reshape(B, Q, C))
+    Qp = (Q + 7) // 8 * 8
+    out = torch.zeros((B, H, W, Qp), dtype=dtype, device=DEV)
+    ops.conv2d_per_image(x.to(DEV), w.to(DEV), out=out[..., :Q])
+    got = out.cpu().float()
+    tol = 3e-3 if dtype == torch.float16 else 1e-4
+    scale = max(1.0, float(ref.abs().max()))
+    assert float((got[..., :Q] - ref).abs().max()) <= tol * scale
+    assert float(got[..., Q:].abs().max()) == 0.0, "padding channels must stay untouched"
