@@ -303,6 +303,8 @@ class BisenetEngine(MFEngine):
 class BisenetFormer(nn.Module):
     """Drop-in for the reference `BisenetFormer(BaseModelNN)` (bisenetformer/modelling.py:534)."""
 
+    lazy_masks = False  # True: forward() returns fai_mf.LazyMasks (low-resolution logits) instead of the upsampled [B,Q,H,W] probabilities
+
     def __init__(self, config: BisenetFormerConfig, precision: str = "fp16"):
         super().__init__()
         self.config = c = config
@@ -343,5 +345,7 @@ class BisenetFormer(nn.Module):
             raise NotImplementedError("focoos_b200: losses / fine-tuning are not part of the inference hot path")
         if ops._backend is None and not images.is_cuda:
             raise RuntimeError("focoos_b200.BisenetFormer runs on CUDA (sm_100a) only — no CPU fallback")
-        probs, masks = self.engine().forward(images if images.dtype == torch.uint8 else images.to(torch.float32), taps)
+        eng = self.engine()
+        eng.lazy_masks = bool(getattr(self, "lazy_masks", False))
+        probs, masks = eng.forward(images if images.dtype == torch.uint8 else images.to(torch.float32), taps)
         return MaskFormerModelOutput(masks=masks, logits=probs, loss=None)

@@ -139,15 +139,50 @@ __global__ void __launch_bounds__(256) mask_argmax_kernel(const float* __restric
   for (int i = threadIdx.x; i < Q; i += 256) { hist[i] = 0; sc[i] = scores[b * Q + i]; }
   __syncthreads();
   const float* mb = masks + (int64_t)b * Q * HW;
-  for (int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x; p < HW; p += (int64_t)gridDim.x * 256) {
-    float best = -INFINITY;
-    int bi = 0;
-    for (int q = 0; q < Q; ++q) {
-      const float v = sc[q] * mb[(int64_t)q * HW + p];
-      if (v > best) { best = v; bi = q; }
+  if ((HW & 3) == 0) {  // 4 pixels per thread: 16-byte loads, 8 independent loads in flight per thread (HBM-bound: the masks are read exactly once)
+    const int64_t HW4 = HW >> 2;
+    for (int64_t p4 = (int64_t)blockIdx.x * 256 + threadIdx.x; p4 < HW4; p4 += (int64_t)gridDim.x * 256) {
+      float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      int bi[4] = {0, 0, 0, 0};
+      const float4* col = reinterpret_cast<const float4*>(mb) + p4;
+      int q = 0;
+      for (; q + 8 <= Q; q += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcs(col + (int64_t)(q + u) * HW4);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float s = sc[q + u];
+          const float a0 = s * v[u].x, a1 = s * v[u].y, a2 = s * v[u].z, a3 = s * v[u].w;
+          if (a0 > best[0]) { best[0] = a0; bi[0] = q + u; }
+          if (a1 > best[1]) { best[1] = a1; bi[1] = q + u; }
+          if (a2 > best[2]) { best[2] = a2; bi[2] = q + u; }
+          if (a3 > best[3]) { best[3] = a3; bi[3] = q + u; }
+        }
+      }
+      for (; q < Q; ++q) {
+        const float4 v = __ldcs(col + (int64_t)q * HW4);
+        const float s = sc[q];
+        if (s * v.x > best[0]) { best[0] = s * v.x; bi[0] = q; }
+        if (s * v.y > best[1]) { best[1] = s * v.y; bi[1] = q; }
+        if (s * v.z > best[2]) { best[2] = s * v.z; bi[2] = q; }
+        if (s * v.w > best[3]) { best[3] = s * v.w; bi[3] = q; }
+      }
+      *reinterpret_cast<uchar4*>(labels + (int64_t)b * HW + (p4 << 2)) = make_uchar4((unsigned char)bi[0], (unsigned char)bi[1], (unsigned char)bi[2], (unsigned char)bi[3]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) atomicAdd(&hist[bi[j]], 1);
     }
-    labels[(int64_t)b * HW + p] = (uint8_t)bi;
-    atomicAdd(&hist[bi], 1);
+  } else {
+    for (int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x; p < HW; p += (int64_t)gridDim.x * 256) {
+      float best = -INFINITY;
+      int bi = 0;
+      for (int q = 0; q < Q; ++q) {
+        const float v = sc[q] * mb[(int64_t)q * HW + p];
+        if (v > best) { best = v; bi = q; }
+      }
+      labels[(int64_t)b * HW + p] = (uint8_t)bi;
+      atomicAdd(&hist[bi], 1);
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < Q; i += 256)
@@ -228,7 +263,7 @@ extern "C" int fb200_channel_scale(const void* x, const void* gate, const void* 
 
 extern "C" int fb200_mask_argmax(const float* masks, const float* scores, int B, int Q, int64_t HW, uint8_t* labels, int* counts, void* stream) {
   FB_CHECK_ARG(masks && scores && labels && counts && Q >= 1 && Q <= 255, "mask_argmax: bad arguments (Q <= 255)");
-  dim3 grid((unsigned)std::min<int64_t>(cdiv(HW, 256), 148 * 4), (unsigned)B);
+  dim3 grid((unsigned)std::min<int64_t>(cdiv((HW & 3) ? HW : HW / 4, 256), 148 * 4), (unsigned)B);
   mask_argmax_kernel<<<grid, 256, Q * 8, (cudaStream_t)stream>>>(masks, scores, Q, HW, labels, counts);
   FB_CHECK_LAUNCH("mask_argmax");
   return FB200_OK;

@@ -157,10 +157,18 @@ __global__ void softmax_drop_last_kernel(const float* __restrict__ x, int64_t ro
 // element, kept in smem, and every query plane of the tile is then written with coalesced 256-byte rows.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int MU_TH = 16, MU_TW = 64;
-template <typename T>
+// ARGMAX = true: the semantic post-process fused in (fai_mf/processor.py:208-220): instead of writing the [B,Q,H,W] probabilities (13.4 GB at
+// 64 x 100 x 512 x 1024) and reading them back, each output pixel keeps argmax_q(score[b,q] * prob) -> uint8 label + per-(b,q) pixel counts.
+// The probability is computed by the very same expression, so labels equal mask_argmax(mask_sigmoid_upsample(x)) bit for bit.
+template <typename T, bool ARGMAX>
 __global__ void __launch_bounds__(256) mask_sigmoid_upsample_kernel(const T* __restrict__ x, int h, int w, int Qp, int Q, float* __restrict__ out,
-                                                                    int H, int W, float sh, float sw, int ph_max, int pw_max) {
-  extern __shared__ float patch[];  // [ph][pw][Q]
+                                                                    int H, int W, float sh, float sw, int ph_max, int pw_max,
+                                                                    const float* __restrict__ scores, uint8_t* __restrict__ labels, int* __restrict__ counts) {
+  extern __shared__ float patch[];  // [ph][pw][Q] (+ ARGMAX: [Q] scores, [Q] int histogram behind the largest possible patch)
+  float* s_sc = patch + (size_t)ph_max * pw_max * Q;
+  int* s_hist = reinterpret_cast<int*>(s_sc + Q);
+  if (ARGMAX)
+    for (int i = threadIdx.x; i < Q; i += 256) { s_sc[i] = scores[blockIdx.z * Q + i]; s_hist[i] = 0; }
   const int b = blockIdx.z, oy0 = blockIdx.y * MU_TH, ox0 = blockIdx.x * MU_TW;
   const int oy1 = min(oy0 + MU_TH, H) - 1, ox1 = min(ox0 + MU_TW, W) - 1;
   const int ys0 = (int)fmaxf(((float)oy0 + 0.5f) * sh - 0.5f, 0.f), xs0 = (int)fmaxf(((float)ox0 + 0.5f) * sw - 0.5f, 0.f);
@@ -192,17 +200,64 @@ __global__ void __launch_bounds__(256) mask_sigmoid_upsample_kernel(const T* __r
       o10[i] = ((y1 - ys0) * pw + (x0 - xs0)) * Q; o11[i] = ((y1 - ys0) * pw + (x1 - xs0)) * Q;
     }
   }
-  if (!x_ok) return;
-  for (int qq = 0; qq < Q; ++qq) {
-    float* op = out + (((int64_t)b * Q + qq) * H) * W;
+  if (!ARGMAX && !x_ok) return;
+  float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  int bi[4] = {0, 0, 0, 0};
+  if (x_ok && ARGMAX && (Q & 3) == 0) {
+    // four queries per shared-memory load (the patch is query-contiguous and every tap offset is a multiple of Q): the fused kernel is
+    // bound by shared-memory bandwidth, not HBM
+    for (int qq = 0; qq < Q; qq += 4) {
+      const float4 sq = *reinterpret_cast<const float4*>(s_sc + qq);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int Y = oy0 + r0 + 4 * i;
-      if (Y >= H) continue;
-      const float v00 = patch[o00[i] + qq], v01 = patch[o01[i] + qq], v10 = patch[o10[i] + qq], v11 = patch[o11[i] + qq];
-      const float lw1 = wx, lw0 = 1.f - wx, lh1 = wy[i], lh0 = 1.f - wy[i];
-      op[(int64_t)Y * W + X] = lh0 * (lw0 * v00 + lw1 * v01) + lh1 * (lw0 * v10 + lw1 * v11);
+      for (int i = 0; i < 4; ++i) {
+        const int Y = oy0 + r0 + 4 * i;
+        if (Y >= H) continue;
+        const float4 v00 = *reinterpret_cast<const float4*>(patch + o00[i] + qq), v01 = *reinterpret_cast<const float4*>(patch + o01[i] + qq);
+        const float4 v10 = *reinterpret_cast<const float4*>(patch + o10[i] + qq), v11 = *reinterpret_cast<const float4*>(patch + o11[i] + qq);
+        const float lw1 = wx, lw0 = 1.f - wx, lh1 = wy[i], lh0 = 1.f - wy[i];
+        const float p0 = lh0 * (lw0 * v00.x + lw1 * v01.x) + lh1 * (lw0 * v10.x + lw1 * v11.x);
+        const float p1 = lh0 * (lw0 * v00.y + lw1 * v01.y) + lh1 * (lw0 * v10.y + lw1 * v11.y);
+        const float p2 = lh0 * (lw0 * v00.z + lw1 * v01.z) + lh1 * (lw0 * v10.z + lw1 * v11.z);
+        const float p3 = lh0 * (lw0 * v00.w + lw1 * v01.w) + lh1 * (lw0 * v10.w + lw1 * v11.w);
+        float v = sq.x * p0; if (v > best[i]) { best[i] = v; bi[i] = qq; }
+        v = sq.y * p1; if (v > best[i]) { best[i] = v; bi[i] = qq + 1; }
+        v = sq.z * p2; if (v > best[i]) { best[i] = v; bi[i] = qq + 2; }
+        v = sq.w * p3; if (v > best[i]) { best[i] = v; bi[i] = qq + 3; }
+      }
     }
+  } else if (x_ok) {
+    for (int qq = 0; qq < Q; ++qq) {
+      float* op = ARGMAX ? nullptr : out + (((int64_t)b * Q + qq) * H) * W;
+      const float sq = ARGMAX ? s_sc[qq] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int Y = oy0 + r0 + 4 * i;
+        if (Y >= H) continue;
+        const float v00 = patch[o00[i] + qq], v01 = patch[o01[i] + qq], v10 = patch[o10[i] + qq], v11 = patch[o11[i] + qq];
+        const float lw1 = wx, lw0 = 1.f - wx, lh1 = wy[i], lh0 = 1.f - wy[i];
+        const float pr = lh0 * (lw0 * v00 + lw1 * v01) + lh1 * (lw0 * v10 + lw1 * v11);
+        if (ARGMAX) {
+          const float v = sq * pr;
+          if (v > best[i]) { best[i] = v; bi[i] = qq; }
+        } else {
+          op[(int64_t)Y * W + X] = pr;
+        }
+      }
+    }
+  }
+  if (ARGMAX) {
+    if (x_ok) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int Y = oy0 + r0 + 4 * i;
+        if (Y >= H) continue;
+        labels[((int64_t)b * H + Y) * W + X] = (uint8_t)bi[i];
+        atomicAdd(&s_hist[bi[i]], 1);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < Q; i += 256)
+      if (s_hist[i]) atomicAdd(&counts[b * Q + i], s_hist[i]);
   }
 }
 
@@ -319,23 +374,42 @@ extern "C" int fb200_softmax_drop_last(const float* x, int64_t rows, int N, int 
   return FB200_OK;
 }
 
-extern "C" int fb200_mask_sigmoid_upsample(const void* x, int dtype, int B, int h, int w, int Qp, int Q, float* out, int H, int W, void* stream) {
-  FB_CHECK_ARG(x && out && Q <= Qp && H >= h && W >= w, "mask_sigmoid_upsample: bad arguments (upsampling only)");
+static int mask_upsample_launch(const void* x, int dtype, int B, int h, int w, int Qp, int Q, float* out, int H, int W, const float* scores, uint8_t* labels,
+                                int* counts, void* stream) {
+  const bool argmax = labels != nullptr;
   const float sh = (float)h / (float)H, sw = (float)w / (float)W;
   const int ph = (int)(MU_TH * sh) + 3, pw = (int)(MU_TW * sw) + 3;
-  const size_t smem = (size_t)ph * pw * Q * sizeof(float);
+  const size_t smem = (size_t)ph * pw * Q * sizeof(float) + (argmax ? (size_t)Q * 8 : 0);
   FB_CHECK_ARG(smem <= 200 * 1024, "mask_sigmoid_upsample: low-resolution patch does not fit shared memory (%zu B)", smem);
   dim3 grid((unsigned)cdiv(W, MU_TW), (unsigned)cdiv(H, MU_TH), (unsigned)B);
   cudaStream_t st = (cudaStream_t)stream;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(mask_sigmoid_upsample_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(mask_sigmoid_upsample_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(mask_sigmoid_upsample_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(mask_sigmoid_upsample_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(mask_sigmoid_upsample_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(mask_sigmoid_upsample_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     configured = true;
   }
-  FB_DISPATCH_DTYPE(dtype, T, (mask_sigmoid_upsample_kernel<T><<<grid, 256, smem, st>>>((const T*)x, h, w, Qp, Q, out, H, W, sh, sw, ph, pw)));
+  if (argmax) {
+    cudaMemsetAsync(counts, 0, (size_t)B * Q * sizeof(int), st);
+    FB_DISPATCH_DTYPE(dtype, T, (mask_sigmoid_upsample_kernel<T, true><<<grid, 256, smem, st>>>((const T*)x, h, w, Qp, Q, nullptr, H, W, sh, sw, ph, pw, scores, labels, counts)));
+  } else {
+    FB_DISPATCH_DTYPE(dtype, T, (mask_sigmoid_upsample_kernel<T, false><<<grid, 256, smem, st>>>((const T*)x, h, w, Qp, Q, out, H, W, sh, sw, ph, pw, nullptr, nullptr, nullptr)));
+  }
   FB_CHECK_LAUNCH("mask_sigmoid_upsample");
   return FB200_OK;
+}
+
+extern "C" int fb200_mask_sigmoid_upsample(const void* x, int dtype, int B, int h, int w, int Qp, int Q, float* out, int H, int W, void* stream) {
+  FB_CHECK_ARG(x && out && Q <= Qp && H >= h && W >= w, "mask_sigmoid_upsample: bad arguments (upsampling only)");
+  return mask_upsample_launch(x, dtype, B, h, w, Qp, Q, out, H, W, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int fb200_mask_sigmoid_upsample_argmax(const void* x, int dtype, int B, int h, int w, int Qp, int Q, const float* scores, int H, int W, uint8_t* labels,
+                                                  int* counts, void* stream) {
+  FB_CHECK_ARG(x && scores && labels && counts && Q <= Qp && Q <= 255 && H >= h && W >= w, "mask_sigmoid_upsample_argmax: bad arguments (upsampling only, Q <= 255)");
+  return mask_upsample_launch(x, dtype, B, h, w, Qp, Q, nullptr, H, W, scores, labels, counts, stream);
 }
 
 extern "C" int fb200_mask_stats(const float* masks, int64_t planes, int64_t hw, float thr, int* count, float* psum, void* stream) {

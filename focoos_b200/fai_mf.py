@@ -90,6 +90,27 @@ class MaskFormerModelOutput(ModelOutput):
     loss: Optional[dict] = None
 
 
+class LazyMasks:
+    """The model output `masks` before the final sigmoid + bilinear upsampling (fai_mf/modelling.py:619,722-723): low-resolution logits
+    NHWC [B,h,w,Qp] plus the target size.  `materialize()` gives the reference's [B,Q,H,W] fp32 probabilities; a processor that understands
+    this object fuses the upsampling into its own reduction instead (semantic argmax: 13.4 GB of HBM traffic avoided at config 4).
+    Enabled by `model.lazy_masks = True` (FocoosModel sets it: it owns model + processor); plain `model(images)` returns tensors."""
+
+    def __init__(self, logits_nhwc: torch.Tensor, num_queries: int, size):
+        self.logits, self.num_queries, self.size = logits_nhwc, num_queries, (int(size[0]), int(size[1]))
+
+    @property
+    def shape(self):
+        return (self.logits.shape[0], self.num_queries, *self.size)
+
+    @property
+    def device(self):
+        return self.logits.device
+
+    def materialize(self) -> torch.Tensor:
+        return ops.mask_sigmoid_upsample(self.logits, self.num_queries, self.size)
+
+
 # ---- parameter containers -------------------------------------------------------------------------
 class _ConvBN(nn.Conv2d):
     """nn/layers/conv.py:22 `Conv2d` wrapper whose norm is a CHILD module (`<name>.weight`, `<name>.norm.*`)."""
@@ -190,6 +211,8 @@ def position_embedding_sine_normalized(h, w, num_pos_feats=128, temperature=1000
 
 class MFEngine(DetrEngine):
     """Packs a FAIMaskFormer state_dict and runs the fused forward (reuses DetrEngine's packing helpers and backbone)."""
+
+    lazy_masks = False  # True: return LazyMasks instead of the materialised [B,Q,H,W] probabilities
 
     def __init__(self, sd: Dict[str, torch.Tensor], cfg: MaskFormerConfig, device, precision: str = "fp16", algo: int = ops.ALGO_AUTO):
         self.cfg, self.device, self.precision, self.algo = cfg, torch.device(device), precision, algo
@@ -339,11 +362,14 @@ class MFEngine(DetrEngine):
         if taps is not None:
             taps.update(pred_logits=cls, pred_masks=masks)  # masks: NHWC [B,h4,w4,Qp] pre-sigmoid logits
         probs = ops.softmax_drop_last(cls)
-        return probs, ops.mask_sigmoid_upsample(masks, Q, (H, W))
+        lazy = LazyMasks(masks, Q, (H, W))
+        return probs, (lazy if self.lazy_masks else lazy.materialize())
 
 
 class FAIMaskFormer(nn.Module):
     """Drop-in for the reference `FAIMaskFormer(BaseModelNN)` (fai_mf/modelling.py:633)."""
+
+    lazy_masks = False  # True: forward() returns fai_mf.LazyMasks (low-resolution logits) instead of the upsampled [B,Q,H,W] probabilities
 
     def __init__(self, config: MaskFormerConfig, precision: str = "fp16"):
         super().__init__()
@@ -389,5 +415,7 @@ class FAIMaskFormer(nn.Module):
             raise NotImplementedError("focoos_b200: losses / fine-tuning are not part of the inference hot path")
         if ops._backend is None and not images.is_cuda:
             raise RuntimeError("focoos_b200.FAIMaskFormer runs on CUDA (sm_100a) only — no CPU fallback")
-        probs, masks = self.engine().forward(images if images.dtype == torch.uint8 else images.to(torch.float32), taps)
+        eng = self.engine()
+        eng.lazy_masks = bool(getattr(self, "lazy_masks", False))
+        probs, masks = eng.forward(images if images.dtype == torch.uint8 else images.to(torch.float32), taps)
         return MaskFormerModelOutput(masks=masks, logits=probs, loss=None)

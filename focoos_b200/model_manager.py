@@ -76,7 +76,15 @@ class FocoosModel:
         images, _ = self.processor.preprocess(inputs, device=self.device, dtype=torch.float32)
         t1 = time.perf_counter()
         with torch.no_grad():
-            out = self.model(images)
+            # segmentation families: let the processor fuse the final mask upsampling into its own reduction (fai_mf.LazyMasks)
+            fused = hasattr(self.model, "lazy_masks")
+            if fused:
+                self.model.lazy_masks = True
+            try:
+                out = self.model(images)
+            finally:
+                if fused:
+                    self.model.lazy_masks = False
         t2 = time.perf_counter()
         dets = self.processor.postprocess(out, inputs, class_names=self.model_info.classes, threshold=threshold)
         t3 = time.perf_counter()

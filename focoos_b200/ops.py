@@ -507,7 +507,7 @@ except Exception:  # pragma: no cover - e.g. double import under a different mod
 # ------------------------------------------------------------------------------------------------
 EXPORTED_SYMBOLS = EXPORTED_SYMBOLS + (
     "fb200_upsample_nearest_add", "fb200_attn_mask_build", "fb200_attention_masked", "fb200_softmax_drop_last",
-    "fb200_mask_sigmoid_upsample", "fb200_mask_stats", "fb200_mask_resize_bbox",
+    "fb200_mask_sigmoid_upsample", "fb200_mask_sigmoid_upsample_argmax", "fb200_mask_stats", "fb200_mask_resize_bbox",
 )
 
 
@@ -542,6 +542,12 @@ def _cb_mask_sigmoid_upsample(self, x, Q, out):
     self._call("fb200_mask_sigmoid_upsample", _p(x), _dt(x), B, h, w, Qp, Q, _p(out), out.shape[2], out.shape[3], _stream())
 
 
+def _cb_mask_sigmoid_upsample_argmax(self, x, Q, scores, labels, counts):
+    self._cuda(x, scores, labels, counts)
+    B, h, w, Qp = x.shape
+    self._call("fb200_mask_sigmoid_upsample_argmax", _p(x), _dt(x), B, h, w, Qp, Q, _p(scores), labels.shape[1], labels.shape[2], _p(labels), _p(counts), _stream())
+
+
 def _cb_mask_stats(self, masks, thr, count, psum):
     self._cuda(masks, count, psum)
     B, Q, H, W = masks.shape
@@ -554,7 +560,7 @@ def _cb_mask_resize_bbox(self, masks, bq, thr, out_masks, out_bbox):
     self._call("fb200_mask_resize_bbox", _p(masks), Q, H, W, _p(bq), bq.shape[0], ctypes.c_float(thr), _p(out_masks), out_masks.shape[1], out_masks.shape[2], _p(out_bbox), _stream())
 
 
-for _n, _f in (("upsample_nearest_add", _cb_upsample_nearest_add), ("attn_mask_build", _cb_attn_mask_build), ("attention_masked", _cb_attention_masked),
+for _n, _f in (("mask_sigmoid_upsample_argmax", _cb_mask_sigmoid_upsample_argmax), ("upsample_nearest_add", _cb_upsample_nearest_add), ("attn_mask_build", _cb_attn_mask_build), ("attention_masked", _cb_attention_masked),
                ("softmax_drop_last", _cb_softmax_drop_last), ("mask_sigmoid_upsample", _cb_mask_sigmoid_upsample), ("mask_stats", _cb_mask_stats),
                ("mask_resize_bbox", _cb_mask_resize_bbox)):
     setattr(CudaBackend, _n, _f)
@@ -601,6 +607,16 @@ def mask_sigmoid_upsample(mask_logits_nhwc, num_queries: int, size):
     out = torch.empty((B, num_queries, size[0], size[1]), dtype=torch.float32, device=mask_logits_nhwc.device)
     _be().mask_sigmoid_upsample(mask_logits_nhwc.contiguous(), num_queries, out)
     return out
+
+
+def mask_sigmoid_upsample_argmax(mask_logits_nhwc, num_queries: int, size, scores):
+    """semantic labels straight from the low-resolution mask logits: argmax_q(scores[b,q] * bilinear(sigmoid(x))[b,q]) -> (labels uint8 [B,H,W],
+    counts int32 [B,Q]) without materialising the [B,Q,H,W] probabilities."""
+    B = mask_logits_nhwc.shape[0]
+    labels = torch.empty((B, size[0], size[1]), dtype=torch.uint8, device=mask_logits_nhwc.device)
+    counts = torch.empty((B, num_queries), dtype=torch.int32, device=mask_logits_nhwc.device)
+    _be().mask_sigmoid_upsample_argmax(mask_logits_nhwc.contiguous(), num_queries, scores.contiguous().float(), labels, counts)
+    return labels, counts
 
 
 def mask_stats(masks, thr: float):

@@ -174,11 +174,17 @@ class MaskFormerProcessor(DETRProcessor):
         threshold = threshold or self.threshold
         use_mask_score = use_mask_score or self.use_mask_score
         self._labels = None
+        lazy = hasattr(output.masks, "materialize")  # fai_mf.LazyMasks: low-resolution logits, upsampling not done yet
         if self.predict_all_pixels:  # semantic: every pixel goes to argmax_q(score_q * prob_q) (processor.py:208-220)
             scores_dev = output.logits.max(-1).values  # [B,Q]; tiny reduction, stays on the device for the argmax kernel
-            self._labels, count = ops.mask_argmax(output.masks, scores_dev)
+            if lazy:  # sigmoid + bilinear upsampling + argmax in one kernel: the [B,Q,H,W] tensor is never written
+                self._labels, count = ops.mask_sigmoid_upsample_argmax(output.masks.logits, output.masks.num_queries, output.masks.size, scores_dev)
+            else:
+                self._labels, count = ops.mask_argmax(output.masks, scores_dev)
             psum = count.float()
         else:
+            if lazy:
+                output.masks = output.masks.materialize()
             count, psum = ops.mask_stats(output.masks, float(self.mask_threshold))
         host = torch.cat([output.logits.reshape(output.logits.shape[0], -1), count.float(), psum], dim=1).cpu().numpy()  # one D2H
         B, Q, K = output.logits.shape
@@ -205,7 +211,7 @@ class MaskFormerProcessor(DETRProcessor):
             if len(q) == 0:
                 results.append(FocoosDetections(detections=[]))
                 continue
-            bq = torch.tensor(np.stack([np.full_like(q, b), q], 1), dtype=torch.int32).to(output.masks.device)
+            bq = torch.tensor(np.stack([np.full_like(q, b), q], 1), dtype=torch.int32).to(output.logits.device)
             if self._labels is not None:
                 m, box = ops.label_resize_bbox(self._labels, bq, image_sizes[b])
             else:

@@ -168,6 +168,11 @@ int fb200_softmax_drop_last(const float* x, int64_t rows, int N, int pitch, floa
 /* MaskFormerHead sigmoid (fai_mf/modelling.py:619) + final F.interpolate(bilinear) to the input size (:722-723), fused:
  * x [B,h,w,Qp] mask logits NHWC -> out [B,Q,H,W] fp32 probabilities. */
 int fb200_mask_sigmoid_upsample(const void* x, int dtype, int B, int h, int w, int Qp, int Q, float* out, int H, int W, void* stream);
+/* The same upsampling with the SEMANTIC post-process fused in (models/fai_mf/processor.py:208-220 on top of :722-723): per output pixel
+ * argmax_q(scores[b,q] * prob[b,q,y,x]) -> labels [B,H,W] uint8 and counts [B,Q] (pixels per query); the [B,Q,H,W] probabilities are never
+ * written.  Bit-identical to fb200_mask_argmax(fb200_mask_sigmoid_upsample(x)). */
+int fb200_mask_sigmoid_upsample_argmax(const void* x, int dtype, int B, int h, int w, int Qp, int Q, const float* scores, int H, int W, uint8_t* labels,
+                                       int* counts, void* stream);
 
 /* MaskFormerProcessor.postprocess reductions (fai_mf/processor.py:222-257): per plane of masks [planes, hw] fp32:
  * count = #(p >= thr), psum = sum of those p. */

@@ -538,3 +538,13 @@ def _rb_conv2d_per_image(self, x, w, act, out, algo):
 
 
 RefBackend.conv2d_per_image = _rb_conv2d_per_image
+
+
+def _rb_mask_sigmoid_upsample_argmax(self, x, Q, scores, labels, counts):
+    B, h, w, _ = x.shape
+    probs = torch.empty((B, Q, labels.shape[1], labels.shape[2]), dtype=torch.float32)
+    self.mask_sigmoid_upsample(x, Q, probs)
+    self.mask_argmax(probs, scores, labels, counts)
+
+
+RefBackend.mask_sigmoid_upsample_argmax = _rb_mask_sigmoid_upsample_argmax

@@ -122,3 +122,40 @@ def test_bisenet_end_to_end_vs_reference_golden(precision):
             assert np.abs(np.array([x.bbox for x in d.detections]) - g["det_boxes"][i, :n]).max() <= 3
     else:
         assert np.isfinite(e["mask_logits_max_abs"])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_fused_upsample_argmax_is_bit_identical(dtype):
+    """sigmoid + bilinear upsampling + semantic argmax in one kernel == mask_argmax(mask_sigmoid_upsample(x)) exactly (labels AND counts)."""
+    g = torch.Generator().manual_seed(5)
+    B, h, w, Q = 3, 32, 48, 100
+    x = (torch.randn((B, h, w, 104), generator=g) * 3).to(dtype).to(DEV)
+    scores = torch.rand((B, Q), generator=g).to(DEV)
+    for size in ((256, 384), (250, 380)):
+        probs = ops.mask_sigmoid_upsample(x, Q, size)
+        l0, c0 = ops.mask_argmax(probs, scores)
+        l1, c1 = ops.mask_sigmoid_upsample_argmax(x, Q, size, scores)
+        assert torch.equal(l0, l1) and torch.equal(c0, c1), size
+
+
+def test_focoos_model_fused_semantic_path_equals_unfused():
+    """FocoosModel.__call__ lets the processor fuse the final upsampling (LazyMasks); detections must equal model(...) + postprocess(...)."""
+    from focoos_b200 import FocoosModel, ModelInfo
+
+    g = load_golden("bisenetformer_l_ade_b2_256x384")
+    sd = seeded_state_dict(manifest_template("bisenetformer_l_ade"), 0)
+    m = BisenetFormer(BisenetFormerConfig(), precision="fp32")
+    m.load_state_dict(sd, strict=True)
+    m.cuda()
+    imgs = synth_images(4, [tuple(s) for s in g["sizes"].tolist()])
+    x = torch.stack([torch.from_numpy(im).permute(2, 0, 1).float() for im in imgs]).cuda()
+    proc = MaskFormerProcessor(m.config)
+    ref = proc.postprocess(m(x), imgs, threshold=float(g["threshold"]))
+    m.lazy_masks = True
+    out = m(x)
+    m.lazy_masks = False
+    assert hasattr(out.masks, "materialize") and tuple(out.masks.shape) == (2, 100, 256, 384)
+    got = proc.postprocess(out, imgs, threshold=float(g["threshold"]))
+    for a, b in zip(ref, got):
+        assert [(d.cls_id, d.bbox, d.mask) for d in a.detections] == [(d.cls_id, d.bbox, d.mask) for d in b.detections]
+        assert np.allclose([d.conf for d in a.detections], [d.conf for d in b.detections], atol=0)
