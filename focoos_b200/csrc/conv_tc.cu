@@ -268,9 +268,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (!p.stride2) {
             tma_load_4d(&tmap_a, &full_bar[stage], dst_a, a_c0, w0 + kw - p.pad, h0 + kh - p.pad, img);
           } else {
-            // input h = 2*ho + kh - 1 -> (h>>1, h&1): kh=0 -> (ho-1,1); kh=1 -> (ho,0); kh=2 -> (ho,1)
-            const int dh = (kh == 0) ? -1 : 0, hp = (kh == 1) ? 0 : 1;
-            const int dw = (kw == 0) ? -1 : 0, wp = (kw == 1) ? 0 : 1;
+            // input h = 2*ho + kh - pad -> (h>>1, h&1).  3x3/pad 1: kh=0 -> (ho-1,1); 1 -> (ho,0); 2 -> (ho,1).  2x2/pad 0: kh -> (ho,kh)
+            const int th = kh - p.pad, tw = kw - p.pad;
+            const int dh = th >> 1, hp = th & 1;   // arithmetic shift: -1 -> (-1, 1)
+            const int dw = tw >> 1, wp = tw & 1;
             tma_load_5d(&tmap_a, &full_bar[stage], dst_a, wp * p.x_pitch + a_c0, w0 + dw, hp, h0 + dh, img);
           }
           if (p.w_batched) tma_load_3d(&tmap_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb * BLOCK_K, n0, img);
@@ -554,7 +555,7 @@ bool conv2d_tc_supported(const ConvParams& p, int x_dtype, int out_dtype) {
   if ((p.act & 15) == FB200_ACT_SIGMOID) return false;  // gates are [B, C] vectors: SIMT path
   if ((p.out_bs * oelt) % 16 != 0) return false;
   if (p.stride == 1) return (2 * p.pad == p.KH - 1) || (p.KH == 1 && p.pad == 0);
-  if (p.stride == 2) return p.KH == 3 && p.pad == 1 && p.H % 2 == 0 && p.W % 2 == 0;
+  if (p.stride == 2) return ((p.KH == 3 && p.pad == 1) || (p.KH == 2 && p.pad == 0)) && p.H % 2 == 0 && p.W % 2 == 0;
   return false;
 }
 

@@ -298,6 +298,8 @@ def _bn_fold(sd, p, eps=1e-5):
 class DetrEngine:
     """Packs a FAIDetr state_dict for one (device, precision) and runs the fused forward."""
 
+    fuse_shortcut_pool = False  # fold the vd shortcut's AvgPool2d into a 2x2/s2 conv (slower on B200, see _pack_backbone)
+
     def __init__(self, sd: Dict[str, torch.Tensor], cfg: DETRConfig, device, precision: str = "fp16", algo: int = ops.ALGO_AUTO):
         assert precision in ("fp32", "fp16", "fp32_tc")
         self.cfg, self.device, self.precision, self.algo = cfg, torch.device(device), precision, algo
@@ -368,6 +370,12 @@ class DetrEngine:
                        "c": self._cnl(sd, p + ".branch2c", "relu"), "stride": stride, "short": None}
                 if bi == 0:
                     blk["short"] = self._cnl(sd, p + (".short.conv" if stride == 2 else ".short"), None)
+                    if stride == 2 and self.precision != "fp32" and self.fuse_shortcut_pool:
+                        # AvgPool2d(2,2) followed by a 1x1 conv (resnet.py:91-102) IS a 2x2 stride-2 conv whose four taps are W/4 (an exact
+                        # power-of-two scaling).  Measured (trip 43): 11.39 vs 11.22 ms/step - the four 5-D TMA boxes per K chunk cost more than the
+                        # pooling launch saves - so it is OFF by default (DetrEngine.fuse_shortcut_pool); kept as a tested kernel capability.
+                        c = blk["short"]
+                        blk["short_fused"] = _Conv((c.w * 0.25).expand(-1, 2, 2, -1).contiguous(), c.scale, c.bias, 2, 0, c.act)
                 blocks.append(blk)
             self.stages.append(blocks)
 
@@ -384,7 +392,10 @@ class DetrEngine:
                 if blk["short"] is None:
                     short = x
                 else:
-                    short = blk["short"](ops.avgpool2x2(x) if blk["stride"] == 2 else x, algo=A)
+                    if "short_fused" in blk and x.shape[1] % 2 == 0 and x.shape[2] % 2 == 0 and (x.is_cuda or ops._backend is not None):
+                        short = blk["short_fused"](x, algo=A)
+                    else:
+                        short = blk["short"](ops.avgpool2x2(x) if blk["stride"] == 2 else x, algo=A)
                 x = blk["c"](y, residual=short, algo=A)
             feats.append(x)
         return feats

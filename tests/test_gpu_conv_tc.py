@@ -134,3 +134,19 @@ def test_per_image_weights_product(B, H, W, C, Q, dtype):
     scale = max(1.0, float(ref.abs().max()))
     assert float((got[..., :Q] - ref).abs().max()) <= tol * scale
     assert float(got[..., Q:].abs().max()) == 0.0, "padding channels must stay untouched"
+
+
+@pytest.mark.parametrize("dtype", [torch.float16])
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 40, 40, 256, 512), (3, 16, 24, 512, 1024), (1, 80, 80, 64, 128)])
+def test_avgpool_folded_into_2x2_stride2_conv(B, H, W, Cin, Cout, dtype):
+    """AvgPool2d(2,2) + 1x1 conv == 2x2 stride-2 conv with W/4 on every tap (the vd shortcut, resnet.py:91-102) on the tcgen05 stride-2 view."""
+    x = rnd((B, H, W, Cin), dtype, 1)
+    w1 = rnd((Cout, 1, 1, Cin), dtype, 2, 1.0 / math.sqrt(Cin))
+    sc, bi = torch.rand(Cout) + 0.5, rnd((Cout,), torch.float32, 3, 0.2)
+    pooled = torch.nn.functional.avg_pool2d(x.float().permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).contiguous()
+    ref = torch.empty((B, H // 2, W // 2, Cout), dtype=torch.float32)
+    REF.conv2d(pooled, w1.float(), sc, bi, 1, 0, 0, None, ref, 0)
+    wf = (w1 * 0.25).expand(-1, 2, 2, -1).contiguous()
+    out = ops.conv2d(x.to(DEV), wf.to(DEV), sc.to(DEV), bi.to(DEV), stride=2, pad=0, algo=ops.ALGO_TCGEN05)
+    scale = max(1.0, float(ref.abs().max()))
+    assert float((out.float().cpu() - ref).abs().max()) <= 3e-3 * scale
