@@ -50,6 +50,7 @@ struct KParams {
   int stride2;                     // 0: 4-D stride-1 view, 1: 5-D stride-2 view
   int num_k_blocks;
   int n_tiles, total_tiles;        // N tiles per M tile; total = m_tiles * n_tiles
+  int res_tma;                     // 1: the residual tile is TMA-loaded into the staging buffer (coalesced, one chunk ahead) instead of per-thread LDG
   int w_batched;                   // 1: weights differ per image (3-D weight map, third coordinate = image)
   int dbg;                         // tuning aid (env FB200_TC_DBG): 1 = skip TMA store, 2 = skip residual, 4 = skip TMEM load
 };
@@ -179,7 +180,7 @@ __device__ __forceinline__ void act32(float (&v)[32], int act) {
 
 template <int BLOCK_N, int BLOCK_K> constexpr int stage_bytes() { return (BLOCK_M + BLOCK_N) * BLOCK_K * 2; }
 template <int BLOCK_N, int STAGES, int BLOCK_K, int NSTG> constexpr int smem_bytes() {
-  return STAGES * stage_bytes<BLOCK_N, BLOCK_K>() + NSTG * epi_groups<BLOCK_N>() * STAGING_BYTES + 2 * BLOCK_N * 4 + (2 * STAGES + 4) * 8 + 16 + 1024 /*align slack*/;
+  return STAGES * stage_bytes<BLOCK_N, BLOCK_K>() + NSTG * epi_groups<BLOCK_N>() * STAGING_BYTES + 2 * BLOCK_N * 4 + (2 * STAGES + 4 + NSTG * epi_groups<BLOCK_N>()) * 8 + 16 + 1024 /*align slack*/;
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
@@ -201,7 +202,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* res_bar = tmem_empty_bar + 2;         // [EPI_GROUPS * NSTG] residual tile landed in staging buffer
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + EPI_GROUPS * NSTG);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t TMEM_COLS = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);  // two accumulator stages
@@ -214,6 +216,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4 * EPI_GROUPS); }
+    for (int i = 0; i < EPI_GROUPS * NSTG; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -340,6 +343,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int q = 0; q < RES_VECS; ++q) dst[q] = __ldg(src + q);
       return true;
     };
+    // ---- residual through TMA (res_tma): the [BW x BH x CHUNK_COLS] residual box of chunk k+1 is loaded into the staging buffer that chunk will
+    // use, one chunk ahead of its consumption; each thread then reads ITS row from shared memory (same swizzle as the output staging), adds the
+    // accumulator and writes the result back in place before the TMA store.  Coalescing is the TMA unit's job (the per-thread LDG.128 pattern touches
+    // 32 different 128-byte lines per instruction), nothing is held in registers across the wait, and no extra shared memory is needed.
+    const bool res_tma = has_res && p.res_tma && NSTG >= 2;
+    uint64_t* const my_res_bar = res_bar + grp * NSTG;
+    const uint32_t res_box_bytes = (uint32_t)(p.BW * p.BH * 128);
+    auto chunk_valid = [&](int tt, int cc0) { return tt < p.total_tiles && cc0 < c_end && (tt % p.n_tiles) * BLOCK_N + cc0 < p.Cout; };
+    auto issue_res = [&](int tt, int cc0, uint32_t k) {  // elected thread only
+      const int n0_ = (tt % p.n_tiles) * BLOCK_N, mt_ = tt / p.n_tiles;
+      const int img_ = mt_ / tiles_per_img, rem_ = mt_ - img_ * tiles_per_img;
+      const int h0_ = (rem_ / p.tiles_w) * p.BH, w0_ = (rem_ % p.tiles_w) * p.BW;
+      uint64_t* bar = &my_res_bar[k % NSTG];
+      mbar_arrive_expect_tx(bar, res_box_bytes);
+      tma_load_4d(&tmap_r, bar, my_staging + (k % NSTG) * STAGING_BYTES, n0_ + cc0, w0_, h0_, img_);
+    };
+    if (res_tma && et == 0 && chunk_valid((int)blockIdx.x, c_begin)) issue_res((int)blockIdx.x, c_begin, 0);
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const int n0 = (t % p.n_tiles) * BLOCK_N, mt = t / p.n_tiles;
       const int img = mt / tiles_per_img, rem = mt - img * tiles_per_img;
@@ -347,7 +367,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int ho = h0 + bh, wo = w0 + bw;
       const bool row_valid = (row < p.BW * p.BH) && ho < p.Ho && wo < p.Wo;
       const TOut* res_row = has_res ? reinterpret_cast<const TOut*>(p.res) + (((int64_t)img * p.Ho + ho) * p.Wo + wo) * p.res_pitch : nullptr;
-      if (has_res && et == 0) {  // L2 prefetch of the NEXT tile's residual columns owned by this group
+      if (has_res && !res_tma && et == 0) {  // L2 prefetch of the NEXT tile's residual columns owned by this group
         const int tn = t + (int)gridDim.x;
         if (tn < p.total_tiles) {
           const int n0n = (tn % p.n_tiles) * BLOCK_N, mtn = tn / p.n_tiles, imgn = mtn / tiles_per_img, remn = mtn - imgn * tiles_per_img;
@@ -372,10 +392,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (n0 + c0 >= p.Cout) break;  // uniform across the group
         uint8_t* stg = my_staging + (chunk_ctr % NSTG) * STAGING_BYTES;
         uint8_t* srow = stg + row * 128;
-        const bool res_vec = res_fetch(t, c0, rcur);
-        // the TMA store that last used this staging buffer must have finished READING it
-        if (et == 0) tma_store_wait_read<NSTG - 1>();
-        epi_bar(grp);
+        bool res_vec = false;
+        if (res_tma) {
+          if (et == 0) {  // prefetch the NEXT chunk's residual into the buffer it will use: that buffer's last store must have finished reading it
+            int tn = t, cn = c0 + CHUNK_COLS;
+            if (!chunk_valid(tn, cn)) { tn = t + (int)gridDim.x; cn = c_begin; }
+            if (chunk_valid(tn, cn)) {
+              tma_store_wait_read<(NSTG >= 2 ? NSTG - 2 : 0)>();
+              issue_res(tn, cn, chunk_ctr + 1);
+            }
+          }
+          mbar_wait(&my_res_bar[chunk_ctr % NSTG], (chunk_ctr / NSTG) & 1);  // this chunk's residual has landed in `stg`
+        } else {
+          res_vec = res_fetch(t, c0, rcur);
+          // the TMA store that last used this staging buffer must have finished READING it
+          if (et == 0) tma_store_wait_read<NSTG - 1>();
+          epi_bar(grp);
+        }
 #pragma unroll
         for (int sub = 0; sub < CHUNK_COLS / 32; ++sub) {
           if (c0 + sub * 32 >= c_end) break;  // BLOCK_N = 32 with fp16 output: half a staging row
@@ -392,7 +425,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             v[j + 3] = fmaf(__uint_as_float(r[j + 3]), sc.w, bi.w);
           }
           auto add_residual = [&]() {
-            if (res_vec) {
+            if (res_tma) {  // this thread's row of the TMA-loaded residual box, 16-byte pieces at the swizzled positions it will overwrite below
+              if constexpr (sizeof(TOut) == 2) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const uint4 t4 = *reinterpret_cast<const uint4*>(srow + (((sub * 4 + q) ^ (row & 7)) << 4));
+                  const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&t4.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&t4.y));
+                  const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&t4.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&t4.w));
+                  v[q * 8 + 0] += f0.x; v[q * 8 + 1] += f0.y; v[q * 8 + 2] += f1.x; v[q * 8 + 3] += f1.y;
+                  v[q * 8 + 4] += f2.x; v[q * 8 + 5] += f2.y; v[q * 8 + 6] += f3.x; v[q * 8 + 7] += f3.y;
+                }
+              } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const uint4 t4 = *reinterpret_cast<const uint4*>(srow + ((q ^ (row & 7)) << 4));
+                  v[q * 4 + 0] += __uint_as_float(t4.x); v[q * 4 + 1] += __uint_as_float(t4.y);
+                  v[q * 4 + 2] += __uint_as_float(t4.z); v[q * 4 + 3] += __uint_as_float(t4.w);
+                }
+              }
+            } else if (res_vec) {
               if constexpr (sizeof(TOut) == 2) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {  // 4 x 16 B = 32 halves of this sub-chunk
@@ -638,6 +689,7 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
     if (total > 0x7fffffffLL) { set_error("conv_tc: too many tiles (%lld)", (long long)total); return FB200_ERR_UNSUPPORTED; }
     k2.total_tiles = (int)total;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("FB200_TC_DBG"); dbg = e ? atoi(e) : 0; } k2.dbg = dbg; }
+    { static int rt = -1; if (rt < 0) { const char* e = getenv("FB200_TC_RES_TMA"); rt = e ? atoi(e) : 1; } k2.res_tma = (p.res && rt) ? 1 : 0; }
     if constexpr (decltype(gelu_tag)::value) return launch<BN_, ST_, __half, MB_, BK_, NS_, true>(ta, tb, td, tr, k2, st);
     else {
       if (out16) return launch<BN_, ST_, __half, MB_, BK_, NS_, false>(ta, tb, td, tr, k2, st);

@@ -15,6 +15,7 @@ for s in $STAGES; do
     trainbench*) N=${s#trainbench}; N=${N:-1}; timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 tools/bench_train.py > gpurun_out/bench_train_$N.log 2>&1 ;;
     wgmicro) python tools/wgrad_micro.py > gpurun_out/wgrad_micro.txt 2>&1 ;;
     wgncu) timeout 900 ncu --set full --clock-control none --import-source on -k regex:wgrad_tc_kernel -s 3 -c 1 -o gpurun_out/prof_wgrad python tools/wgrad_micro.py fpn_rep_3x3_80 > gpurun_out/wgrad_ncu.log 2>&1 ;;
+    microres) (python tools/conv_micro.py s0_2c_res s1_2c_res s2_2c_res; FB200_TC_RES_TMA=0 python tools/conv_micro.py s0_2c_res s1_2c_res s2_2c_res; true) > gpurun_out/conv_micro_res.txt 2>&1 ;;
     tc)    timeout 900 python -m pytest tests/test_gpu_conv_tc.py -q -m gpu 2>&1 | tail -80 > gpurun_out/t_tc.log ;;
     e2e)   timeout 1200 python -m pytest tests/test_gpu_e2e.py -q -m gpu 2>&1 | tail -60 > gpurun_out/t_e2e.log ;;
     smoke) timeout 600 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1 ;;
