@@ -5,6 +5,84 @@
 
 namespace fb200 {
 
+// 16-byte vectors: 4 floats or 8 halves per thread (these kernels are pure HBM streams; 8-byte fp16 accesses left half the bandwidth unused)
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) { const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[8]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct Vec16<__half> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __half* p, float (&v)[8]) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
+    const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&t.z)), d = __half22float2(*reinterpret_cast<const __half2*>(&t.w));
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+  }
+  static __device__ __forceinline__ void store(__half* p, const float (&v)[8]) {
+    __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]), c = __floats2half2_rn(v[4], v[5]), d = __floats2half2_rn(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = make_uint4(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b), *reinterpret_cast<uint32_t*>(&c), *reinterpret_cast<uint32_t*>(&d));
+  }
+};
+
+template <typename T>
+__global__ void maxpool3x3s2_v16_kernel(const T* __restrict__ x, int B, int H, int W, int C, int Ho, int Wo, T* __restrict__ out) {
+  constexpr int N = Vec16<T>::N;
+  const int cv = C / N;
+  const int64_t total = (int64_t)B * Ho * Wo * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (i % cv) * N;
+    const int64_t pix = i / cv;
+    const int wo = pix % Wo, ho = (pix / Wo) % Ho, b = pix / ((int64_t)Wo * Ho);
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int hi = ho * 2 - 1 + kh;
+      if (hi < 0 || hi >= H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int wi = wo * 2 - 1 + kw;
+        if (wi < 0 || wi >= W) continue;
+        float v[8];
+        Vec16<T>::load(x + (((int64_t)b * H + hi) * W + wi) * C + c, v);
+#pragma unroll
+        for (int j = 0; j < N; ++j) m[j] = fmaxf(m[j], v[j]);
+      }
+    }
+    Vec16<T>::store(out + pix * C + c, m);
+  }
+}
+
+template <typename T>
+__global__ void avgpool2x2_v16_kernel(const T* __restrict__ x, int B, int H, int W, int C, int Ho, int Wo, T* __restrict__ out) {
+  constexpr int N = Vec16<T>::N;
+  const int cv = C / N;
+  const int64_t total = (int64_t)B * Ho * Wo * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (i % cv) * N;
+    const int64_t pix = i / cv;
+    const int wo = pix % Wo, ho = (pix / Wo) % Ho, b = pix / ((int64_t)Wo * Ho);
+    const int h0 = ho * 2, w0 = wo * 2, h1 = min(h0 + 2, H), w1 = min(w0 + 2, W);
+    float s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = 0.f;
+    for (int hi = h0; hi < h1; ++hi)
+      for (int wi = w0; wi < w1; ++wi) {
+        float v[8];
+        Vec16<T>::load(x + (((int64_t)b * H + hi) * W + wi) * C + c, v);
+#pragma unroll
+        for (int j = 0; j < N; ++j) s[j] += v[j];
+      }
+    const float inv = 1.f / (float)((h1 - h0) * (w1 - w0));
+#pragma unroll
+    for (int j = 0; j < N; ++j) s[j] *= inv;
+    Vec16<T>::store(out + pix * C + c, s);
+  }
+}
+
 template <typename T>
 __global__ void maxpool3x3s2_kernel(const T* __restrict__ x, int B, int H, int W, int C, int Ho, int Wo, T* __restrict__ out) {
   const int cv = C / 4;
@@ -82,6 +160,30 @@ __global__ void resize_bilinear_kernel(const T* __restrict__ x, int B, int H, in
   }
 }
 
+__global__ void resize_bilinear_h8_kernel(const __half* __restrict__ x, int B, int H, int W, int C, int x_pitch, __half* __restrict__ out,
+                                          int Ho, int Wo, int out_pitch, float sh, float sw) {
+  const int cv = C / 8;
+  const int64_t total = (int64_t)B * Ho * Wo * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (i % cv) * 8;
+    const int64_t pix = i / cv;
+    const int wo = pix % Wo, ho = (pix / Wo) % Ho, b = pix / ((int64_t)Wo * Ho);
+    const float fh = fmaxf(((float)ho + 0.5f) * sh - 0.5f, 0.f), fw = fmaxf(((float)wo + 0.5f) * sw - 0.5f, 0.f);
+    const int h0 = (int)fh, w0 = (int)fw;
+    const int h1 = h0 + (h0 < H - 1 ? 1 : 0), w1 = w0 + (w0 < W - 1 ? 1 : 0);
+    const float lh1 = fh - (float)h0, lh0 = 1.f - lh1, lw1 = fw - (float)w0, lw0 = 1.f - lw1;
+    const __half* base = x + (int64_t)b * H * W * x_pitch + c;
+    float v00[8], v01[8], v10[8], v11[8], r[8];
+    Vec16<__half>::load(base + ((int64_t)h0 * W + w0) * x_pitch, v00);
+    Vec16<__half>::load(base + ((int64_t)h0 * W + w1) * x_pitch, v01);
+    Vec16<__half>::load(base + ((int64_t)h1 * W + w0) * x_pitch, v10);
+    Vec16<__half>::load(base + ((int64_t)h1 * W + w1) * x_pitch, v11);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = lh0 * (lw0 * v00[j] + lw1 * v01[j]) + lh1 * (lw0 * v10[j] + lw1 * v11[j]);
+    Vec16<__half>::store(out + pix * out_pitch + c, r);
+  }
+}
+
 template <typename T>
 __global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, int64_t n4, int64_t bn4) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -127,6 +229,12 @@ extern "C" int fb200_maxpool3x3s2(const void* x, int dtype, int B, int H, int W,
   FB_CHECK_ARG(x && out && C % 4 == 0, "maxpool: null pointer or C %% 4 != 0");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const int64_t total = (int64_t)B * Ho * Wo * (C / 4);
+  const bool al16 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  if (dtype == FB200_F16 && C % 8 == 0 && al16) {
+    maxpool3x3s2_v16_kernel<__half><<<grid_for(total / 2, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, B, H, W, C, Ho, Wo, (__half*)out);
+    FB_CHECK_LAUNCH("maxpool3x3s2");
+    return FB200_OK;
+  }
   FB_DISPATCH_DTYPE(dtype, T, (maxpool3x3s2_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, B, H, W, C, Ho, Wo, (T*)out)));
   FB_CHECK_LAUNCH("maxpool3x3s2");
   return FB200_OK;
@@ -136,6 +244,12 @@ extern "C" int fb200_avgpool2x2_ceil(const void* x, int dtype, int B, int H, int
   FB_CHECK_ARG(x && out && C % 4 == 0, "avgpool: null pointer or C %% 4 != 0");
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
   const int64_t total = (int64_t)B * Ho * Wo * (C / 4);
+  const bool al16 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  if (dtype == FB200_F16 && C % 8 == 0 && al16) {
+    avgpool2x2_v16_kernel<__half><<<grid_for(total / 2, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, B, H, W, C, Ho, Wo, (__half*)out);
+    FB_CHECK_LAUNCH("avgpool2x2");
+    return FB200_OK;
+  }
   FB_DISPATCH_DTYPE(dtype, T, (avgpool2x2_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, B, H, W, C, Ho, Wo, (T*)out)));
   FB_CHECK_LAUNCH("avgpool2x2");
   return FB200_OK;
@@ -147,6 +261,11 @@ extern "C" int fb200_resize_bilinear(const void* x, int dtype, int B, int H, int
   FB_CHECK_ARG(x_pitch >= C && out_pitch >= C && Ho > 0 && Wo > 0, "resize: bad shape");
   const int64_t total = (int64_t)B * Ho * Wo * (C / 4);
   const float sh = (float)H / (float)Ho, sw = (float)W / (float)Wo;
+  if (dtype == FB200_F16 && C % 8 == 0 && x_pitch % 8 == 0 && out_pitch % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    resize_bilinear_h8_kernel<<<grid_for(total / 2, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, B, H, W, C, x_pitch, (__half*)out, Ho, Wo, out_pitch, sh, sw);
+    FB_CHECK_LAUNCH("resize_bilinear");
+    return FB200_OK;
+  }
   FB_DISPATCH_DTYPE(dtype, T, (resize_bilinear_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, B, H, W, C, x_pitch, (T*)out, Ho, Wo, out_pitch, sh, sw)));
   FB_CHECK_LAUNCH("resize_bilinear");
   return FB200_OK;
