@@ -8,6 +8,7 @@ family is embedded below since the reference tree is not present on the GPU box)
 """
 from __future__ import annotations
 
+import os
 import time
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence
@@ -15,6 +16,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 import torch
 
+from . import ops
 from .bisenetformer import BisenetFormer, BisenetFormerConfig
 from .fai_detr import FAIDetr
 from .fai_mf import FAIMaskFormer, MaskFormerConfig
@@ -64,6 +66,41 @@ class FocoosModel:
         self.model.eval()
         if torch.cuda.is_available():
             self.model.cuda()
+        # CUDA-graph cache of model.forward per (input shape, dtype): the eager forward is ~240 launches of partly very short kernels (the
+        # decoder runs ahead of a Python host), so replaying a captured graph removes the host from the critical path of `infer` / `__call__`
+        self.cuda_graphs = os.environ.get("FB200_NO_GRAPH", "0") != "1"
+        self._graphs = {}  # key -> (graph, static_input, static_output)
+        self._graph_seen = {}
+
+    def _forward(self, images):
+        """model.forward, through a cached CUDA graph when the same input shape has been seen before (first sighting runs eagerly)."""
+        if not (self.cuda_graphs and images.is_cuda and ops._backend is None):
+            return self.model(images)
+        key = (tuple(images.shape), images.dtype, getattr(self.model, "precision", None), bool(getattr(self.model, "lazy_masks", False)))
+        ent = self._graphs.get(key)
+        if ent is None:
+            self._graph_seen[key] = self._graph_seen.get(key, 0) + 1
+            if self._graph_seen[key] < 2:  # capture only shapes that come back (a one-off image size is not worth 2+ GB of pooled activations)
+                return self.model(images)
+            if len(self._graphs) >= 2:  # bounded: each entry owns a private activation pool
+                self._graphs.pop(next(iter(self._graphs)))
+            static_in = images.clone()
+            self.model(static_in)  # make sure every lazily-initialised piece (engine, constants) exists before capture
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self.model(static_in)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                static_out = self.model(static_in)
+            ent = self._graphs[key] = (g, static_in, static_out)
+        g, static_in, static_out = ent
+        static_in.copy_(images, non_blocking=True)
+        g.replay()
+        return static_out
 
     @property
     def device(self):
@@ -81,7 +118,7 @@ class FocoosModel:
             if fused:
                 self.model.lazy_masks = True
             try:
-                out = self.model(images)
+                out = self._forward(images)
             finally:
                 if fused:
                     self.model.lazy_masks = False

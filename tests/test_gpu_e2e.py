@@ -194,3 +194,21 @@ def test_fp32_tc_meets_the_parity_bars(sd):
         assert len(d) == n
         assert sorted(x.cls_id for x in d.detections) == sorted(g["det_labels"][i, :n].tolist())
         assert sorted(tuple(x.bbox) for x in d.detections) == sorted(map(tuple, g["det_boxes"][i, :n].tolist()))
+
+
+def test_focoos_model_cuda_graph_path_equals_eager(sd):
+    """FocoosModel replays a captured CUDA graph of model.forward from the second sighting of an input shape: identical detections, call after call,
+    also with different images flowing through the same static buffers."""
+    from focoos_b200 import FocoosModel, ModelInfo
+
+    fm = FocoosModel(_model(sd, "fp32"), ModelInfo(name="fai-detr-l-obj365", im_size=640))
+    batches = [np.stack(synth_images(s, [(640, 640)] * 2)) for s in (1, 2)]
+    fm.cuda_graphs = False
+    ref = [fm(torch.from_numpy(b), threshold=0.5, batched=True) for b in batches]
+    fm.cuda_graphs = True
+    for rep in range(3):  # call 1 eager, call 2 captures, call 3+ replay
+        for b, r in zip(batches, ref):
+            got = fm(torch.from_numpy(b), threshold=0.5, batched=True)
+            for g, e in zip(got, r):
+                assert [(d.cls_id, d.bbox, d.conf) for d in g.detections] == [(d.cls_id, d.bbox, d.conf) for d in e.detections], rep
+    assert len(fm._graphs) == 1
