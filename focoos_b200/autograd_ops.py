@@ -408,9 +408,9 @@ class AttentionFn(torch.autograd.Function):
     """q [B,Lq,C], k/v [B,Lk,C] (already projected), heads of 32 channels."""
 
     @staticmethod
-    def forward(ctx, q, k, v, heads, scale):
+    def forward(ctx, q, k, v, heads, scale, split=False):
         q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
-        o = ops.attention(q, k, v, heads, scale)
+        o = ops.attention(q, k, v, heads, scale, split=split)
         ctx.save_for_backward(q, k, v, o)
         ctx.cfg = (heads, scale)
         return o
@@ -421,7 +421,7 @@ class AttentionFn(torch.autograd.Function):
         heads, scale = ctx.cfg
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
         ops._be().attention_bwd(q, k, v, o, do.contiguous(), heads, scale, dq, dk, dv)
-        return dq, dk, dv, None, None
+        return dq, dk, dv, None, None, None
 
 
 class MSDAFn(torch.autograd.Function):

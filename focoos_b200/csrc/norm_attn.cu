@@ -108,6 +108,8 @@ __global__ void __launch_bounds__(256) attention_kernel(const T* __restrict__ q,
   }
 }
 
+int attention_mma_split(const float* q, int q_pitch, const float* k, int k_pitch, const float* v, int v_pitch, float* out, int out_pitch, int B, int Lq, int Lk,
+                        int heads, float scale, cudaStream_t st);
 int attention_mma(const __half* q, int q_pitch, const __half* k, int k_pitch, const __half* v, int v_pitch, __half* out, int out_pitch, int B,
                   int Lq, int Lk, int heads, float scale, cudaStream_t st);
 }  // namespace fb200
@@ -152,6 +154,15 @@ extern "C" int fb200_attention(const void* q, int q_pitch, const void* k, int k_
   } else { set_error("attention: bad dtype"); return FB200_ERR_INVALID; }
   FB_CHECK_LAUNCH("attention");
   return FB200_OK;
+}
+
+extern "C" int fb200_attention_split(const float* q, int q_pitch, const float* k, int k_pitch, const float* v, int v_pitch, float* out, int out_pitch, int B,
+                                     int Lq, int Lk, int heads, int head_dim, float scale, void* stream) {
+  FB_CHECK_ARG(q && k && v && out, "attention_split: null pointer");
+  FB_CHECK_ARG(head_dim == 32, "attention_split: head_dim must be 32 (got %d)", head_dim);
+  FB_CHECK_ARG(q_pitch % 4 == 0 && k_pitch % 4 == 0 && v_pitch % 4 == 0 && out_pitch % 2 == 0 && (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) & 15) == 0 &&
+                   ((uintptr_t)out & 7) == 0, "attention_split: pitches / alignment");
+  return attention_mma_split(q, q_pitch, k, k_pitch, v, v_pitch, out, out_pitch, B, Lq, Lk, heads, scale, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -283,6 +294,145 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const __half* __rest
     if (r0 < Lq) *reinterpret_cast<uint32_t*>(out + ((int64_t)b * Lq + r0) * out_pitch + c) = pack_h2(o[nt][0] * i0, o[nt][1] * i0);
     if (r1 < Lq) *reinterpret_cast<uint32_t*>(out + ((int64_t)b * Lq + r1) * out_pitch + c) = pack_h2(o[nt][2] * i1, o[nt][3] * i1);
   }
+}
+
+// Split-precision variant for fp32 tensors (precision="fp32_tc"): Q, K, V are split into [hi | lo] fp16 halves while being staged in shared memory;
+// S = Qh Kh^T + Qh Kl^T + Ql Kh^T and O += Ph Vh + Ph Vl + Pl Vh (P = softmax numerators, split in registers) reproduce the fp32 products to ~2^-21,
+// with the same fragment algebra and online softmax as attention_mma_kernel.  fp32 in, fp32 out.
+__device__ __forceinline__ void split_store4(__half* hi, __half* lo, const float4 v) {
+  const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+  const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+  const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+  *reinterpret_cast<__half2*>(hi) = h0; *reinterpret_cast<__half2*>(hi + 2) = h1;
+  *reinterpret_cast<__half2*>(lo) = l0; *reinterpret_cast<__half2*>(lo + 2) = l1;
+}
+
+__global__ void __launch_bounds__(128) attention_mma_split_kernel(const float* __restrict__ q, int q_pitch, const float* __restrict__ k, int k_pitch,
+                                                                  const float* __restrict__ v, int v_pitch, float* __restrict__ out, int out_pitch,
+                                                                  int Lq, int Lk, int heads, float scale_log2) {
+  extern __shared__ __align__(16) __half smh[];
+  const int LkP = (Lk + 63) & ~63;
+  const size_t kv = (size_t)LkP * AM_PITCH;
+  __half* Kh = smh; __half* Kl = Kh + kv; __half* Vh = Kl + kv; __half* Vl = Vh + kv;
+  __half* Qh = Vl + kv; __half* Ql = Qh + 64 * AM_PITCH;
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int q0 = blockIdx.y * 64;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < LkP * 8; i += 128) {  // 8 x float4 per 32-wide row
+    const int r = i >> 3, c = (i & 7) * 4;
+    float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+    if (r < Lk) {
+      kk = *reinterpret_cast<const float4*>(k + ((int64_t)b * Lk + r) * k_pitch + h * 32 + c);
+      vv = *reinterpret_cast<const float4*>(v + ((int64_t)b * Lk + r) * v_pitch + h * 32 + c);
+    }
+    split_store4(Kh + r * AM_PITCH + c, Kl + r * AM_PITCH + c, kk);
+    split_store4(Vh + r * AM_PITCH + c, Vl + r * AM_PITCH + c, vv);
+  }
+  for (int i = tid; i < 64 * 8; i += 128) {
+    const int r = i >> 3, c = (i & 7) * 4;
+    float4 qq = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q0 + r < Lq) qq = *reinterpret_cast<const float4*>(q + ((int64_t)b * Lq + q0 + r) * q_pitch + h * 32 + c);
+    split_store4(Qh + r * AM_PITCH + c, Ql + r * AM_PITCH + c, qq);
+  }
+  __syncthreads();
+  uint32_t qah[2][4], qal[2][4];
+  {
+    const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+    const int c = (lane >> 4) * 8;
+    ldsm_x4(qah[0], Qh + r * AM_PITCH + c); ldsm_x4(qah[1], Qh + r * AM_PITCH + 16 + c);
+    ldsm_x4(qal[0], Ql + r * AM_PITCH + c); ldsm_x4(qal[1], Ql + r * AM_PITCH + 16 + c);
+  }
+  float o[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  for (int kb = 0; kb < LkP; kb += 64) {
+    float s[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[nt][j] = 0.f;
+      uint32_t kh[4], kl[4];
+      const int off = (kb + nt * 8 + (lane & 7)) * AM_PITCH + (lane >> 3) * 8;
+      ldsm_x4(kh, Kh + off);
+      ldsm_x4(kl, Kl + off);
+      mma16816(s[nt], qal[0], kh[0], kh[1]); mma16816(s[nt], qal[1], kh[2], kh[3]);   // small terms first
+      mma16816(s[nt], qah[0], kl[0], kl[1]); mma16816(s[nt], qah[1], kl[2], kl[3]);
+      mma16816(s[nt], qah[0], kh[0], kh[1]); mma16816(s[nt], qah[1], kh[2], kh[3]);
+    }
+    float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int key = kb + nt * 8 + (lane & 3) * 2;
+      if (key >= Lk) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+      if (key + 1 >= Lk) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+      bm0 = fmaxf(bm0, fmaxf(s[nt][0], s[nt][1]));
+      bm1 = fmaxf(bm1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+    const float nm0 = fmaxf(m0, bm0), nm1 = fmaxf(m1, bm1);
+    const float a0 = exp2f((m0 - nm0) * scale_log2), a1 = exp2f((m1 - nm1) * scale_log2);
+    m0 = nm0; m1 = nm1;
+    l0 *= a0; l1 *= a1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { o[i][0] *= a0; o[i][1] *= a0; o[i][2] *= a1; o[i][3] *= a1; }
+    uint32_t pah[4][4], pal[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float p0 = exp2f((s[nt][0] - m0) * scale_log2), p1 = exp2f((s[nt][1] - m0) * scale_log2);
+      const float p2 = exp2f((s[nt][2] - m1) * scale_log2), p3 = exp2f((s[nt][3] - m1) * scale_log2);
+      l0 += p0 + p1; l1 += p2 + p3;
+      const __half2 h01 = __floats2half2_rn(p0, p1), h23 = __floats2half2_rn(p2, p3);
+      const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+      pah[nt >> 1][(nt & 1) * 2 + 0] = *reinterpret_cast<const uint32_t*>(&h01);
+      pah[nt >> 1][(nt & 1) * 2 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+      pal[nt >> 1][(nt & 1) * 2 + 0] = pack_h2(p0 - f01.x, p1 - f01.y);
+      pal[nt >> 1][(nt & 1) * 2 + 1] = pack_h2(p2 - f23.x, p3 - f23.y);
+    }
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int r = kb + ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {  // d 0-15, d 16-31
+        uint32_t vh[4], vl[4];
+        const int off = r * AM_PITCH + half * 16 + (lane >> 4) * 8;
+        ldsm_x4_trans(vh, Vh + off);
+        ldsm_x4_trans(vl, Vl + off);
+        mma16816(o[half * 2 + 0], pal[ks], vh[0], vh[1]); mma16816(o[half * 2 + 1], pal[ks], vh[2], vh[3]);
+        mma16816(o[half * 2 + 0], pah[ks], vl[0], vl[1]); mma16816(o[half * 2 + 1], pah[ks], vl[2], vl[3]);
+        mma16816(o[half * 2 + 0], pah[ks], vh[0], vh[1]); mma16816(o[half * 2 + 1], pah[ks], vh[2], vh[3]);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  const int r0 = q0 + warp * 16 + (lane >> 2), r1 = r0 + 8;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const int c = h * 32 + nt * 8 + (lane & 3) * 2;
+    if (r0 < Lq) *reinterpret_cast<float2*>(out + ((int64_t)b * Lq + r0) * out_pitch + c) = make_float2(o[nt][0] * i0, o[nt][1] * i0);
+    if (r1 < Lq) *reinterpret_cast<float2*>(out + ((int64_t)b * Lq + r1) * out_pitch + c) = make_float2(o[nt][2] * i1, o[nt][3] * i1);
+  }
+}
+
+int attention_mma_split(const float* q, int q_pitch, const float* k, int k_pitch, const float* v, int v_pitch, float* out, int out_pitch, int B, int Lq, int Lk,
+                        int heads, float scale, cudaStream_t st) {
+  const int LkP = (Lk + 63) & ~63;
+  const size_t smem = ((size_t)4 * LkP + 128) * AM_PITCH * sizeof(__half);
+  if (smem > 227 * 1024) { set_error("attention(split): Lk=%d does not fit shared memory", Lk); return FB200_ERR_UNSUPPORTED; }
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(attention_mma_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    configured = true;
+  }
+  dim3 grid(B * heads, (unsigned)cdiv(Lq, 64));
+  attention_mma_split_kernel<<<grid, 128, smem, st>>>(q, q_pitch, k, k_pitch, v, v_pitch, out, out_pitch, Lq, Lk, heads, scale * 1.4426950408889634f);
+  FB_CHECK_LAUNCH("attention_mma_split");
+  return FB200_OK;
 }
 
 int attention_mma(const __half* q, int q_pitch, const __half* k, int k_pitch, const __half* v, int v_pitch, __half* out, int out_pitch, int B,

@@ -473,7 +473,7 @@ class DetrEngine:
         B, L, d = x.shape
         qk = blk["qk"](ops.add(x, pos), algo=self.algo)
         v = blk["v"](x, algo=self.algo)
-        a = ops.attention(qk[..., :d], qk[..., d:], v, self.nhead, 1.0 / math.sqrt(d // self.nhead))
+        a = ops.attention(qk[..., :d], qk[..., d:], v, self.nhead, 1.0 / math.sqrt(d // self.nhead), split=self.precision == "fp32_tc")
         y = blk["out"](a, residual=x, algo=self.algo)
         return ops.layernorm(y, *blk["n_attn"])
 

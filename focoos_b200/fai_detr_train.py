@@ -86,7 +86,7 @@ class DetrTrainGraph:
         q = A.linear(q_in, w[:d], b[:d], precision=self.prec)
         k = A.linear(k_in, w[d:2 * d], b[d:2 * d], precision=self.prec)
         v = A.linear(v_in, w[2 * d:], b[2 * d:], precision=self.prec)
-        o = A.AttentionFn.apply(q, k, v, h, 1.0 / math.sqrt(d // h))
+        o = A.AttentionFn.apply(q, k, v, h, 1.0 / math.sqrt(d // h), self.prec == "fp32_tc")
         return A.linear(o, attn.out_proj.weight, attn.out_proj.bias, precision=self.prec)
 
     def mlp(self, x, mlp):

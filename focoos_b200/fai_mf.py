@@ -307,7 +307,7 @@ class MFEngine(DetrEngine):
         for blk in self.enc:  # pre-norm encoder layer (nn/layers/transformer.py:583-601 with normalize_before)
             s2 = ops.layernorm(src, *blk["n_attn"])
             qk = blk["qk"](ops.add(s2, pos), algo=A)
-            a = ops.attention(qk[..., :d], qk[..., d:], blk["v"](s2, algo=A), nh, scale)
+            a = ops.attention(qk[..., :d], qk[..., d:], blk["v"](s2, algo=A), nh, scale, split=self.precision == "fp32_tc")
             src = blk["out"](a, residual=src, algo=A)
             s2 = ops.layernorm(src, *blk["n_ffn"])
             src = blk["l2"](blk["l1"](s2, act=ops.ACT_RELU, algo=A), residual=src, algo=A)
@@ -351,7 +351,7 @@ class MFEngine(DetrEngine):
             out = blk["cout"](a, residual=out, algo=A)
             t2 = ops.layernorm(out, *blk["sn"])
             qk = blk["sqk"](ops.add(t2, qpos), algo=A)
-            a = ops.attention(qk[..., :d], qk[..., d:], blk["sv"](t2, algo=A), nh, scale)
+            a = ops.attention(qk[..., :d], qk[..., d:], blk["sv"](t2, algo=A), nh, scale, split=self.precision == "fp32_tc")
             out = blk["sout"](a, residual=out, algo=A)
             t2 = ops.layernorm(out, *blk["fn"])
             out = blk["l2"](blk["l1"](t2, act=ops.ACT_RELU, algo=A), residual=out, algo=A)

@@ -66,7 +66,7 @@ EXPORTED_SYMBOLS = (
     "fb200_last_error", "fb200_version", "fb200_device_supports_tcgen05", "fb200_stem_conv3x3s2", "fb200_stem_conv3x3s2_u8", "fb200_conv2d", "fb200_conv2d_per_image_weights",
     "fb200_split_f32_pair",
     "fb200_maxpool3x3s2", "fb200_avgpool2x2_ceil", "fb200_resize_bilinear", "fb200_add", "fb200_layernorm",
-    "fb200_attention", "fb200_msda", "fb200_row_select", "fb200_rowmax", "fb200_topk", "fb200_gather_rows",
+    "fb200_attention", "fb200_attention_split", "fb200_msda", "fb200_row_select", "fb200_rowmax", "fb200_topk", "fb200_gather_rows",
     "fb200_box_op", "fb200_detr_postprocess",
 )
 
@@ -195,9 +195,13 @@ class CudaBackend:
         C = x.shape[-1]
         self._call("fb200_layernorm", _p(x), _p(res), _p(gamma), _p(beta), _p(out), _dt(x), ctypes.c_int64(x.numel() // C), C, ctypes.c_float(eps), _stream())
 
-    def attention(self, q, k, v, out, heads, scale):
+    def attention(self, q, k, v, out, heads, scale, split=False):
         self._cuda(q, k, v, out)
         B, Lq, C = q.shape
+        if split and q.dtype == torch.float32:
+            self._call("fb200_attention_split", _p(q), _pitch(q), _p(k), _pitch(k), _p(v), _pitch(v), _p(out), _pitch(out), B, Lq, k.shape[1], heads, C // heads,
+                       ctypes.c_float(scale), _stream())
+            return
         self._call("fb200_attention", _p(q), _pitch(q), _p(k), _pitch(k), _p(v), _pitch(v), _p(out), _pitch(out), _dt(q), B, Lq, k.shape[1],
                    heads, C // heads, ctypes.c_float(scale), _stream())
 
@@ -376,11 +380,15 @@ def layernorm(x, gamma, beta, residual=None, eps=1e-5):
     return out
 
 
-def attention(q, k, v, heads: int, scale: float):
-    """softmax(q k^T * scale) v per head; q [B,Lq,C], k,v [B,Lk,C] (may be column slices of one buffer)."""
+def attention(q, k, v, heads: int, scale: float, split: bool = False):
+    """softmax(q k^T * scale) v per head; q [B,Lq,C], k,v [B,Lk,C] (may be column slices of one buffer).
+    split=True (fp32 tensors only): tensor-core kernel with split-precision products instead of the CUDA-core fp32 kernel."""
     B, Lq, C = q.shape
     out = torch.empty((B, Lq, C), dtype=q.dtype, device=q.device)
-    _be().attention(q, k, v, out, heads, scale)
+    if split and q.dtype == torch.float32:
+        _be().attention(q, k, v, out, heads, scale, True)
+    else:
+        _be().attention(q, k, v, out, heads, scale)
     return out
 
 

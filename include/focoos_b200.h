@@ -106,6 +106,10 @@ int fb200_layernorm(const void* x, const void* res, const float* gamma, const fl
  * (SURVEY A.6).  q/k/v/out rows are tokens; head h uses columns [h*hd, (h+1)*hd). hd must be 32. */
 int fb200_attention(const void* q, int q_pitch, const void* k, int k_pitch, const void* v, int v_pitch, void* out,
                     int out_pitch, int dtype, int B, int Lq, int Lk, int heads, int head_dim, float scale, void* stream);
+/* fp32 tensors on the fp16 tensor cores (precision="fp32_tc"): Q, K, V are split into [hi|lo] halves on the way into shared memory and every product
+ * is formed as hi*hi + hi*lo + lo*hi with fp32 accumulation (mma.sync m16n8k16), softmax in fp32.  Same semantics as fb200_attention(FB200_F32). */
+int fb200_attention_split(const float* q, int q_pitch, const float* k, int k_pitch, const float* v, int v_pitch, float* out, int out_pitch, int B,
+                          int Lq, int Lk, int heads, int head_dim, float scale, void* stream);
 
 /* ---- a10: multi-scale deformable attention core, softmax over levels*points fused.
  * Replaces MSDeformableAttention.forward lines 854-880 (models/fai_detr/modelling.py) +

@@ -77,7 +77,7 @@ class RefBackend:
         v = x.float() if res is None else x.float() + res.float()
         out.copy_(F.layer_norm(v, (v.shape[-1],), gamma, beta, eps).to(out.dtype))
 
-    def attention(self, q, k, v, out, heads, scale):
+    def attention(self, q, k, v, out, heads, scale, split=False):
         B, Lq, C = q.shape
         Lk = k.shape[1]
         hd = C // heads

@@ -223,3 +223,26 @@ def test_stem_conv_u8_nhwc_matches_float_path():
     a = ops.stem_conv(u8.to(DEV), w.to(DEV), sc.to(DEV), bi.to(DEV), mean, std, 1, torch.float32)
     b = ops.stem_conv(u8.permute(0, 3, 1, 2).float().contiguous().to(DEV), w.to(DEV), sc.to(DEV), bi.to(DEV), mean, std, 1, torch.float32)
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("B,Lq,Lk,heads", [(2, 400, 400, 8), (3, 300, 300, 8), (2, 100, 37, 4), (1, 65, 129, 2)])
+def test_attention_split_precision(B, Lq, Lk, heads):
+    """fp32 attention on the tensor cores (hi/lo fp16 splits of Q, K, V and of the softmax numerators) vs the fp32 reference, column-sliced inputs."""
+    C = heads * 32
+    if Lq == Lk:  # q and k as column slices of one fused projection buffer (how the engines call it; batch stride = L * pitch)
+        qk = rnd((B, Lq, 2 * C), torch.float32, 1, 1.5)
+        q, k = qk[..., :C], qk[..., C:]
+    else:
+        q, k = rnd((B, Lq, C), torch.float32, 1, 1.5), rnd((B, Lk, C), torch.float32, 3, 1.5)
+    v = rnd((B, Lk, C), torch.float32, 2)
+    scale = 1.0 / math.sqrt(32)
+    ref = torch.empty((B, Lq, C))
+    REF.attention(q, k, v, ref, heads, scale)
+    if Lq == Lk:
+        qd = qk.to(DEV)
+        qg, kg = qd[..., :C], qd[..., C:]
+    else:
+        qg, kg = q.to(DEV), k.to(DEV)
+    out = ops.attention(qg, kg, v.to(DEV), heads, scale, split=True)
+    err = float((out.cpu() - ref).abs().max())
+    assert err <= 2e-5 * max(1.0, float(ref.abs().max())), err
