@@ -53,13 +53,13 @@ def _cb_conv_wgrad_tc_supported(self, x_shape, dy_shape, KH, KW, stride, pad):
     return bool(self.lib.fb200_conv_wgrad_tc_supported(B, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad))
 
 
-def _cb_conv_wgrad_tc(self, x_pair, dy_pair, KH, KW, pad, dw):
+def _cb_conv_wgrad_tc(self, x_pair, dy_pair, KH, KW, stride, pad, dw):
     self._cuda(x_pair, dy_pair, dw)
     B, H, W, C2 = x_pair.shape
     Cin, Cout = C2 // 2, dy_pair.shape[-1] // 2
     self.lib.fb200_conv_wgrad_tc_workspace_bytes.restype = ctypes.c_int64
-    ws = _ws(self.lib.fb200_conv_wgrad_tc_workspace_bytes(B, H, W, Cin, Cout, KH, KW), x_pair.device)
-    self._call("fb200_conv_wgrad_tc", _p(x_pair), B, H, W, Cin, _p(dy_pair), Cout, KH, KW, pad, _p(dw), 0, _p(ws), _stream())
+    ws = _ws(self.lib.fb200_conv_wgrad_tc_workspace_bytes(B, dy_pair.shape[1], dy_pair.shape[2], Cin, Cout, KH, KW), x_pair.device)
+    self._call("fb200_conv_wgrad_tc", _p(x_pair), B, H, W, Cin, _p(dy_pair), Cout, KH, KW, stride, pad, _p(dw), 0, _p(ws), _stream())
 
 
 def _cb_dilate2(self, dy, out):
@@ -191,7 +191,7 @@ def weight_grad(x, dy, KH, KW, stride, pad, precision, x_pair=None, dy_pair=None
     if wgrad_on_tensor_cores(xs, ds, KH, KW, stride, pad, precision):
         xp = x_pair if x_pair is not None else ops.split_pair(x.contiguous())
         dp = dy_pair if dy_pair is not None else ops.split_pair(dy.contiguous())
-        be.conv_wgrad_tc(xp, dp, KH, KW, pad, dwk)
+        be.conv_wgrad_tc(xp, dp, KH, KW, stride, pad, dwk)
     else:
         be.conv_wgrad(x, dy, KH, KW, stride, pad, dwk)
     return dwk
@@ -260,7 +260,9 @@ class BatchNormTrainFn(torch.autograd.Function):
         rstd = torch.empty(C, dtype=torch.float32, device=x.device)
         r2 = None if res is None else res.contiguous().reshape(-1, C)
         ops._be().bn_train_fwd(x2, gamma, beta, r2, act, eps, momentum, running_mean, running_var, mean, rstd, y.reshape(-1, C))
-        ctx.save_for_backward(x, gamma, beta, mean, rstd, y if act != ops.ACT_NONE else None)
+        # the ReLU mask is recomputed from x (sign of the normalised value) unless a residual was added before the activation: saves the output from
+        # being kept alive and two passes over it in backward
+        ctx.save_for_backward(x, gamma, beta, mean, rstd, y if (act != ops.ACT_NONE and res is not None) else None)
         ctx.cfg = (act, res is not None)
         return y
 

@@ -104,7 +104,7 @@ __global__ void dilate2_kernel(const float* __restrict__ dy, int B, int Ho, int 
 // partial[blockIdx.y][c] per row-slice; 32 channels x 8 row lanes per block.
 constexpr int CR_ROWS = 296;  // row slices (2 x 148 SMs)
 
-__device__ __forceinline__ float act_grad(int act, float z, float y) {
+__device__ __forceinline__ float act_grad(int act, float z, float y) {  // y = forward output where one exists, else pass z twice
   if (act == FB200_ACT_RELU) return y > 0.f ? 1.f : 0.f;
   if (act == FB200_ACT_SILU) { const float s = 1.f / (1.f + expf(-z)); return s * (1.f + z * (1.f - s)); }
   if (act == FB200_ACT_GELU) { return 0.5f * (1.f + erff(z * 0.70710678118654752f)) + z * 0.3989422804014327f * expf(-0.5f * z * z); }
@@ -129,14 +129,51 @@ __global__ void __launch_bounds__(256) col_partial_kernel(const float* __restric
     const float mu = (MODE >= 1) ? mean[c] : 0.f;
     const float rs = (MODE == 2) ? rstd[c] : 0.f;
     const float ga = (MODE == 2) ? gamma[c] : 0.f, be = (MODE == 2) ? beta[c] : 0.f;
-    for (int64_t r = (int64_t)blockIdx.y * 8 + lane_r; r < R; r += (int64_t)gridDim.y * 8) {
+    const float pivot = (MODE == 3) ? x[c] : 0.f;  // single-pass mean/variance: sums of (x - x[0,c]) and its square (shift kills the cancellation)
+    const int64_t rstep = (int64_t)gridDim.y * 8;
+    int64_t r = (int64_t)blockIdx.y * 8 + lane_r;
+    if (MODE == 2) {  // four independent rows per iteration: 8-12 loads in flight per thread instead of 2-3 (the kernel is latency-, not bandwidth-bound otherwise)
+      for (; r + 3 * rstep < R; r += 4 * rstep) {
+        float xv[4], gv[4], yv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          xv[u] = x[(r + u * rstep) * x_pitch + c];
+          gv[u] = dy[(r + u * rstep) * dy_pitch + c];
+          yv[u] = (act != FB200_ACT_NONE && y) ? y[(r + u * rstep) * y_pitch + c] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float xh = (xv[u] - mu) * rs;
+          float g = gv[u];
+          if (act != FB200_ACT_NONE) {
+            const float z = xh * ga + be;
+            g *= act_grad(act, z, y ? yv[u] : z);
+          }
+          s0 += g;
+          s1 += g * xh;
+        }
+      }
+    } else if (MODE == 3) {
+      for (; r + 3 * rstep < R; r += 4 * rstep) {
+        float xv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xv[u] = x[(r + u * rstep) * x_pitch + c];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const float d = xv[u] - pivot; s0 += d; s1 += d * d; }
+      }
+    }
+    for (; r < R; r += rstep) {
       const float v = x[r * x_pitch + c];
       if (MODE == 0) s0 += v;
       else if (MODE == 1) { const float d = v - mu; s0 += d * d; }
+      else if (MODE == 3) { const float d = v - pivot; s0 += d; s1 += d * d; }
       else {
         const float xh = (v - mu) * rs;
         float g = dy[r * dy_pitch + c];
-        if (act != FB200_ACT_NONE) g *= act_grad(act, xh * ga + be, y[r * y_pitch + c]);
+        if (act != FB200_ACT_NONE) {
+          const float z = xh * ga + be;
+          g *= act_grad(act, z, y ? y[r * y_pitch + c] : z);
+        }
         s0 += g;
         s1 += g * xh;
       }
@@ -151,7 +188,7 @@ __global__ void __launch_bounds__(256) col_partial_kernel(const float* __restric
 #pragma unroll
     for (int k = 0; k < 8; ++k) { a += r0[k][threadIdx.x]; b += r1[k][threadIdx.x]; }
     p0[(int64_t)blockIdx.y * C + c] = a;
-    if (MODE == 2) p1[(int64_t)blockIdx.y * C + c] = b;
+    if (MODE >= 2) p1[(int64_t)blockIdx.y * C + c] = b;
   }
 }
 
@@ -168,7 +205,7 @@ __global__ void col_finalize_kernel(const float* __restrict__ p0, const float* _
   double a = 0.0, b = 0.0;
   for (int k = 0; k < nparts; ++k) {
     a += (double)p0[(int64_t)k * C + c];
-    if (FIN == 3) b += (double)p1[(int64_t)k * C + c];
+    if (FIN >= 3) b += (double)p1[(int64_t)k * C + c];
   }
   if (FIN == 0) out0[c] = accumulate ? out0[c] + (float)a : (float)a;
   if (FIN == 1) out0[c] = (float)(a / R);
@@ -183,6 +220,18 @@ __global__ void col_finalize_kernel(const float* __restrict__ p0, const float* _
   if (FIN == 3) {
     out0[c] = accumulate ? out0[c] + (float)a : (float)a;
     out1[c] = accumulate ? out1[c] + (float)b : (float)b;
+  }
+  if (FIN == 4) {  // single-pass BN statistics from shifted sums: a = sum(x - pivot), b = sum((x - pivot)^2); `mean` carries the pivot row
+    const double m1 = a / R;
+    double var = b / R - m1 * m1;
+    if (var < 0.0) var = 0.0;
+    const float mu = (float)((double)mean[c] + m1);
+    out0[c] = mu;
+    out1[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (run_mean) {
+      run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * mu;
+      run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)(R > 1.0 ? var * R / (R - 1.0) : var);
+    }
   }
 }
 
@@ -207,6 +256,42 @@ __global__ void bn_apply_kernel(const float* __restrict__ x, int x_pitch, const 
   }
 }
 
+// float4 version of bn_bwd_apply_kernel (C % 4 == 0, 16-byte aligned rows): no per-element 64-bit division, per-channel parameters loaded as vectors
+__global__ void bn_bwd_apply4_kernel(const float* __restrict__ x, int x_pitch, const float* __restrict__ dy, int dy_pitch, const float* __restrict__ y, int y_pitch,
+                                     int64_t R, int C, const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, const float* __restrict__ dgamma, const float* __restrict__ dbeta, int act, float inv_R,
+                                     float* __restrict__ dx, int dx_pitch, float* __restrict__ dres, int dres_pitch) {
+  const int cv = C / 4;
+  const int64_t total = R * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cv;
+    const int c = (int)(i - r * cv) * 4;
+    const float4 xv = *reinterpret_cast<const float4*>(x + r * x_pitch + c), gv = *reinterpret_cast<const float4*>(dy + r * dy_pitch + c);
+    float4 yv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (act != FB200_ACT_NONE && y) yv = *reinterpret_cast<const float4*>(y + r * y_pitch + c);
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c), rs = *reinterpret_cast<const float4*>(rstd + c);
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+    const float4 dg = *reinterpret_cast<const float4*>(dgamma + c), db = *reinterpret_cast<const float4*>(dbeta + c);
+    const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, ga4[4] = {gv.x, gv.y, gv.z, gv.w}, ya[4] = {yv.x, yv.y, yv.z, yv.w};
+    const float m4[4] = {mu.x, mu.y, mu.z, mu.w}, r4[4] = {rs.x, rs.y, rs.z, rs.w}, g4[4] = {ga.x, ga.y, ga.z, ga.w}, b4[4] = {be.x, be.y, be.z, be.w};
+    const float dg4[4] = {dg.x, dg.y, dg.z, dg.w}, db4[4] = {db.x, db.y, db.z, db.w};
+    float o[4], gr[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float xh = (xa[j] - m4[j]) * r4[j];
+      float g = ga4[j];
+      if (act != FB200_ACT_NONE) {
+        const float z = xh * g4[j] + b4[j];
+        g *= act_grad(act, z, y ? ya[j] : z);
+      }
+      gr[j] = g;
+      o[j] = g4[j] * r4[j] * (g - db4[j] * inv_R - xh * dg4[j] * inv_R);
+    }
+    *reinterpret_cast<float4*>(dx + r * dx_pitch + c) = make_float4(o[0], o[1], o[2], o[3]);
+    if (dres) *reinterpret_cast<float4*>(dres + r * dres_pitch + c) = make_float4(gr[0], gr[1], gr[2], gr[3]);
+  }
+}
+
 // dx = gamma * rstd * (g - dbeta/R - xhat * dgamma/R),  g = dy * act'(.);  dres = g
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ x, int x_pitch, const float* __restrict__ dy, int dy_pitch, const float* __restrict__ y, int y_pitch,
                                     int64_t R, int C, const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
@@ -218,7 +303,10 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ x, int x_pitch, co
     const int c = i % C;
     const float xh = (x[r * x_pitch + c] - mean[c]) * rstd[c];
     float g = dy[r * dy_pitch + c];
-    if (act != FB200_ACT_NONE) g *= act_grad(act, xh * gamma[c] + beta[c], y[r * y_pitch + c]);
+    if (act != FB200_ACT_NONE) {
+      const float z = xh * gamma[c] + beta[c];
+      g *= act_grad(act, z, y ? y[r * y_pitch + c] : z);
+    }
     dx[r * dx_pitch + c] = gamma[c] * rstd[c] * (g - dbeta[c] * inv_R - xh * dgamma[c] * inv_R);
     if (dres) dres[r * dres_pitch + c] = g;
   }
@@ -263,6 +351,46 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ x, const float* __r
       }
     }
     dx[i] = acc;
+  }
+}
+
+// four channels per thread (16-byte loads): same first-maximum rule per channel
+__global__ void maxpool_bwd4_kernel(const float* __restrict__ x, const float* __restrict__ dy, int B, int H, int W, int C, int Ho, int Wo, float* __restrict__ dx) {
+  const int cv = C / 4;
+  const int64_t total = (int64_t)B * H * W * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * 4;
+    const int64_t pix = i / cv;
+    const int w = pix % W, h = (pix / W) % H, b = pix / ((int64_t)W * H);
+    const float* xb = x + (int64_t)b * H * W * C + c;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int ho = h / 2; ho <= (h + 1) / 2 && ho < Ho; ++ho) {
+      for (int wo = w / 2; wo <= (w + 1) / 2 && wo < Wo; ++wo) {
+        float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        int bidx[4] = {-1, -1, -1, -1};
+#pragma unroll
+        for (int dh = 0; dh < 3; ++dh) {
+          const int hh = 2 * ho - 1 + dh;
+          if (hh < 0 || hh >= H) continue;
+#pragma unroll
+          for (int dw = 0; dw < 3; ++dw) {
+            const int ww = 2 * wo - 1 + dw;
+            if (ww < 0 || ww >= W) continue;
+            const float4 v4 = *reinterpret_cast<const float4*>(xb + ((int64_t)hh * W + ww) * C);
+            const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (v[j] > best[j]) { best[j] = v[j]; bidx[j] = hh * W + ww; }
+          }
+        }
+        const float4 g4 = *reinterpret_cast<const float4*>(dy + (((int64_t)b * Ho + ho) * Wo + wo) * C + c);
+        const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (bidx[j] == h * W + w) acc[j] += g[j];
+      }
+    }
+    *reinterpret_cast<float4*>(dx + pix * C + c) = make_float4(acc[0], acc[1], acc[2], acc[3]);
   }
 }
 
@@ -442,10 +570,10 @@ extern "C" int fb200_bn_train_fwd(const float* x, int x_pitch, int64_t R, int C,
   cudaStream_t st = (cudaStream_t)stream;
   float* p0 = reinterpret_cast<float*>(workspace);
   const dim3 g = col_grid(C, R);
-  col_partial_kernel<0><<<g, 256, 0, st>>>(x, x_pitch, R, C, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, 0, p0, nullptr);
-  col_finalize_kernel<1><<<cdiv(C, 128), 128, 0, st>>>(p0, nullptr, g.y, C, (double)R, eps, momentum, nullptr, nullptr, nullptr, save_mean, nullptr, 0);
-  col_partial_kernel<1><<<g, 256, 0, st>>>(x, x_pitch, R, C, save_mean, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, 0, p0, nullptr);
-  col_finalize_kernel<2><<<cdiv(C, 128), 128, 0, st>>>(p0, nullptr, g.y, C, (double)R, eps, momentum, save_mean, running_mean, running_var, save_rstd, nullptr, 0);
+  float* p1 = p0 + (int64_t)CR_ROWS * C;
+  // ONE pass over x for both moments (sums shifted by the first row, finalised in double); `x` itself serves as the pivot row for the finaliser
+  col_partial_kernel<3><<<g, 256, 0, st>>>(x, x_pitch, R, C, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, 0, p0, p1);
+  col_finalize_kernel<4><<<cdiv(C, 128), 128, 0, st>>>(p0, p1, g.y, C, (double)R, eps, momentum, x, running_mean, running_var, save_mean, save_rstd, 0);
   bn_apply_kernel<<<grid_for(R * (C / 4)), 256, 0, st>>>(x, x_pitch, res, res_pitch, R, C, save_mean, save_rstd, gamma, beta, act, y, y_pitch);
   FB_CHECK_LAUNCH("bn_train_fwd");
   return FB200_OK;
@@ -455,7 +583,7 @@ extern "C" int fb200_bn_train_bwd(const float* x, int x_pitch, const float* dy, 
                                   const float* beta, const float* save_mean, const float* save_rstd, int act, float* dx, int dx_pitch, float* dres, int dres_pitch,
                                   float* dgamma, float* dbeta, int accumulate, void* workspace, void* stream) {
   FB_CHECK_ARG(x && dy && gamma && beta && save_mean && save_rstd && dx && dgamma && dbeta && workspace && R > 0, "bn_train_bwd: bad arguments");
-  FB_CHECK_ARG(act == FB200_ACT_NONE || y, "bn_train_bwd: the activation gradient needs the forward output");
+  FB_CHECK_ARG(act == FB200_ACT_NONE || y || !dres, "bn_train_bwd: with a fused residual the activation gradient needs the forward output");
   cudaStream_t st = (cudaStream_t)stream;
   float* p0 = reinterpret_cast<float*>(workspace);
   float* p1 = p0 + (int64_t)CR_ROWS * C;
@@ -464,8 +592,15 @@ extern "C" int fb200_bn_train_bwd(const float* x, int x_pitch, const float* dy, 
   float* f1 = f0 + C;
   col_partial_kernel<2><<<g, 256, 0, st>>>(x, x_pitch, R, C, save_mean, save_rstd, gamma, beta, dy, dy_pitch, y, y_pitch, act, p0, p1);
   col_finalize_kernel<3><<<cdiv(C, 128), 128, 0, st>>>(p0, p1, g.y, C, (double)R, 0.f, 0.f, nullptr, nullptr, nullptr, f0, f1, 0);
-  bn_bwd_apply_kernel<<<grid_for(R * C), 256, 0, st>>>(x, x_pitch, dy, dy_pitch, y, y_pitch, R, C, save_mean, save_rstd, gamma, beta, f1, f0, act, (float)(1.0 / (double)R),
-                                                       dx, dx_pitch, dres, dres_pitch);
+  const bool v4 = C % 4 == 0 && x_pitch % 4 == 0 && dy_pitch % 4 == 0 && dx_pitch % 4 == 0 && (!y || y_pitch % 4 == 0) && (!dres || dres_pitch % 4 == 0) &&
+                  ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(y) |
+                    reinterpret_cast<uintptr_t>(dres)) & 15) == 0;
+  if (v4)
+    bn_bwd_apply4_kernel<<<grid_for(R * (C / 4)), 256, 0, st>>>(x, x_pitch, dy, dy_pitch, y, y_pitch, R, C, save_mean, save_rstd, gamma, beta, f1, f0, act,
+                                                               (float)(1.0 / (double)R), dx, dx_pitch, dres, dres_pitch);
+  else
+    bn_bwd_apply_kernel<<<grid_for(R * C), 256, 0, st>>>(x, x_pitch, dy, dy_pitch, y, y_pitch, R, C, save_mean, save_rstd, gamma, beta, f1, f0, act, (float)(1.0 / (double)R),
+                                                         dx, dx_pitch, dres, dres_pitch);
   col_finalize_kernel<3><<<cdiv(C, 128), 128, 0, st>>>(f0, f1, 1, C, (double)R, 0.f, 0.f, nullptr, nullptr, nullptr, dbeta, dgamma, accumulate);
   FB_CHECK_LAUNCH("bn_train_bwd");
   return FB200_OK;
@@ -481,7 +616,10 @@ extern "C" int fb200_add_act(const float* a, const float* b, const float* dy, in
 extern "C" int fb200_maxpool3x3s2_bwd(const float* x, const float* dy, int B, int H, int W, int C, float* dx, void* stream) {
   FB_CHECK_ARG(x && dy && dx, "maxpool3x3s2_bwd: null pointer");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  maxpool_bwd_kernel<<<grid_for((int64_t)B * H * W * C), 256, 0, (cudaStream_t)stream>>>(x, dy, B, H, W, C, Ho, Wo, dx);
+  if (C % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0)
+    maxpool_bwd4_kernel<<<grid_for((int64_t)B * H * W * (C / 4)), 256, 0, (cudaStream_t)stream>>>(x, dy, B, H, W, C, Ho, Wo, dx);
+  else
+    maxpool_bwd_kernel<<<grid_for((int64_t)B * H * W * C), 256, 0, (cudaStream_t)stream>>>(x, dy, B, H, W, C, Ho, Wo, dx);
   FB_CHECK_LAUNCH("maxpool3x3s2_bwd");
   return FB200_OK;
 }

@@ -216,6 +216,26 @@ __global__ void split_f32_pair_kernel(const float* __restrict__ x, int64_t rows,
   }
 }
 
+// 8 values per thread: two 16-byte loads, two 16-byte stores (C % 8 == 0, 16-byte aligned rows)
+__global__ void split_f32_pair8_kernel(const float* __restrict__ x, int64_t rows, int C, int x_pitch, __half* __restrict__ out) {
+  const int cv = C / 8;
+  const int64_t total = rows * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cv;
+    const int c = (i % cv) * 8;
+    const float4 a = *reinterpret_cast<const float4*>(x + r * x_pitch + c), b = *reinterpret_cast<const float4*>(x + r * x_pitch + c + 4);
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    float hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      hi[j] = __half2float(__float2half_rn(v[j]));
+      lo[j] = v[j] - hi[j];
+    }
+    Vec16<__half>::store(out + r * 2 * C + c, hi);
+    Vec16<__half>::store(out + r * 2 * C + C + c, lo);
+  }
+}
+
 static inline unsigned grid_for(int64_t total, int threads) {
   int64_t g = cdiv(total, threads);
   const int64_t cap = 148LL * 32;
@@ -281,7 +301,10 @@ extern "C" int fb200_add(const void* a, const void* b, void* out, int dtype, int
 
 extern "C" int fb200_split_f32_pair(const float* x, int64_t rows, int C, int x_pitch, void* out, void* stream) {
   FB_CHECK_ARG(x && out && C % 4 == 0 && x_pitch % 4 == 0 && x_pitch >= C, "split_f32_pair: bad arguments");
-  split_f32_pair_kernel<<<grid_for(rows * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(x, rows, C, x_pitch, (__half*)out);
+  if (C % 8 == 0 && x_pitch % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0)
+    split_f32_pair8_kernel<<<grid_for(rows * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(x, rows, C, x_pitch, (__half*)out);
+  else
+    split_f32_pair_kernel<<<grid_for(rows * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(x, rows, C, x_pitch, (__half*)out);
   FB_CHECK_LAUNCH("split_f32_pair");
   return FB200_OK;
 }

@@ -29,7 +29,7 @@ constexpr int STAGES = 3;
 constexpr int BOX_BYTES = BLOCK_K * 64 * 2;  // one TMA box: 64 pixels x 64 channels fp16 = 8 KiB
 
 struct WParams {
-  int Cout, Cin, KH, KW, pad;
+  int Cout, Cin, KH, KW, pad, stride;
   int BW, BH, tiles_w, tiles_h, B;     // pixel tile rectangle (BW*BH == 64) and counts
   int m_tiles, n_tiles, taps, splits;  // work decomposition
   int pt_total, pt_per_split;          // pixel tiles
@@ -164,7 +164,8 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const __grid_constant_
               tma_load_4d(&tmap_dy, &full_bar[stage], sa + half * A_HALF + j * BOX_BYTES, half * p.Cout + m0 + j * 64, w0, h0, img);
 #pragma unroll
             for (int j = 0; j < BLOCK_N / 64; ++j)
-              tma_load_4d(&tmap_x, &full_bar[stage], sb + half * B_HALF + j * BOX_BYTES, half * p.Cin + n0 + j * 64, w0 + kw - p.pad, h0 + kh - p.pad, img);
+              tma_load_4d(&tmap_x, &full_bar[stage], sb + half * B_HALF + j * BOX_BYTES, half * p.Cin + n0 + j * 64, w0 * p.stride + kw - p.pad,
+                          h0 * p.stride + kh - p.pad, img);  // stride 2: the X map traverses every second pixel (TMA element strides)
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -265,12 +266,13 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 // pair tensor [B,H,W,2C] fp16 -> 4-D map (channel, w, h, b) with a 64-channel x BW x BH box, SWIZZLE_128B, OOB = zero
-static int encode_pair(CUtensorMap* m, const void* base, int C2, int W, int H, int B, int BW, int BH, const char* what) {
+static int encode_pair(CUtensorMap* m, const void* base, int C2, int W, int H, int B, int BW, int BH, const char* what, int stride = 1) {
   EncodeTiledFn fn = get_encode();
   if (!fn) { set_error("wgrad_tc: cuTensorMapEncodeTiled unavailable"); return FB200_ERR_CUDA; }
   const cuuint64_t gdim[4] = {(cuuint64_t)C2, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   const cuuint64_t gstr[3] = {(cuuint64_t)C2 * 2, (cuuint64_t)C2 * 2 * W, (cuuint64_t)C2 * 2 * W * H};
-  const cuuint32_t box[4] = {64, (cuuint32_t)BW, (cuuint32_t)BH, 1}, estr[4] = {1, 1, 1, 1};
+  // with a traversal stride s the box spans s*BW x s*BH input pixels and delivers ceil(s*BW / s) x ceil(s*BH / s) = BW x BH of them
+  const cuuint32_t box[4] = {64, (cuuint32_t)(BW * stride), (cuuint32_t)(BH * stride), 1}, estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("wgrad_tc: cuTensorMapEncodeTiled(%s) failed with %d (C2=%d W=%d H=%d B=%d box %dx%d)", what, (int)r, C2, W, H, B, BW, BH); return FB200_ERR_CUDA; }
@@ -321,8 +323,9 @@ using namespace fb200;
 
 /* 1 if fb200_conv_wgrad_tc supports the shape (else the caller uses fb200_conv_wgrad) */
 extern "C" int fb200_conv_wgrad_tc_supported(int B, int H, int W, int Cin, int Ho, int Wo, int Cout, int KH, int KW, int stride, int pad) {
-  if (stride != 1 || KH != KW || (KH != 1 && KH != 3) || 2 * pad != KH - 1) return 0;
-  if (Ho != H || Wo != W) return 0;
+  if ((stride != 1 && stride != 2) || KH != KW || (KH != 1 && KH != 3) || 2 * pad != KH - 1) return 0;
+  if (Ho != (H + 2 * pad - KH) / stride + 1 || Wo != (W + 2 * pad - KW) / stride + 1) return 0;
+  if (stride == 2 && KH != 3) return 0;
   if (Cin % 8 != 0 || Cout % 8 != 0) return 0;            // 16-byte global strides of the fp16 pair tensors
   if ((int64_t)B * Ho * Wo < 512) return 0;
   return 1;
@@ -334,22 +337,24 @@ extern "C" int64_t fb200_conv_wgrad_tc_workspace_bytes(int B, int Ho, int Wo, in
 }
 
 /* x_pair [B,H,W,2*Cin] fp16, dy_pair [B,Ho,Wo,2*Cout] fp16 (both from fb200_split_f32_pair, dense) -> dw [Cout][KH][KW][Cin] fp32 */
-extern "C" int fb200_conv_wgrad_tc(const void* x_pair, int B, int H, int W, int Cin, const void* dy_pair, int Cout, int KH, int KW, int pad, float* dw, int accumulate,
-                                   void* workspace, void* stream) {
+extern "C" int fb200_conv_wgrad_tc(const void* x_pair, int B, int H, int W, int Cin, const void* dy_pair, int Cout, int KH, int KW, int stride, int pad, float* dw,
+                                   int accumulate, void* workspace, void* stream) {
   FB_CHECK_ARG(x_pair && dy_pair && dw && workspace, "conv_wgrad_tc: null pointer");
-  FB_CHECK_ARG(fb200_conv_wgrad_tc_supported(B, H, W, Cin, H, W, Cout, KH, KW, 1, pad), "conv_wgrad_tc: unsupported shape (B=%d H=%d W=%d Cin=%d Cout=%d k=%d)", B, H, W, Cin, Cout, KH);
+  const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+  FB_CHECK_ARG(fb200_conv_wgrad_tc_supported(B, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad), "conv_wgrad_tc: unsupported shape (B=%d H=%d W=%d Cin=%d Cout=%d k=%d s=%d)", B, H, W,
+               Cin, Cout, KH, stride);
   FB_CHECK_ARG(((reinterpret_cast<uintptr_t>(x_pair) | reinterpret_cast<uintptr_t>(dy_pair) | reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(dw)) & 15) == 0,
                "conv_wgrad_tc: pointers must be 16-byte aligned");
   using namespace wg;
   const int taps = KH * KW;
-  const Plan pl = make_plan(B, H, W, Cin, Cout, taps);
+  const Plan pl = make_plan(B, Ho, Wo, Cin, Cout, taps);
   CUtensorMap tdy, tx;
-  int rc = encode_pair(&tdy, dy_pair, 2 * Cout, W, H, B, pl.BW, pl.BH, "dY");
+  int rc = encode_pair(&tdy, dy_pair, 2 * Cout, Wo, Ho, B, pl.BW, pl.BH, "dY");
   if (rc) return rc;
-  rc = encode_pair(&tx, x_pair, 2 * Cin, W, H, B, pl.BW, pl.BH, "X");
+  rc = encode_pair(&tx, x_pair, 2 * Cin, W, H, B, pl.BW, pl.BH, "X", stride);
   if (rc) return rc;
   WParams p;
-  p.Cout = Cout; p.Cin = Cin; p.KH = KH; p.KW = KW; p.pad = pad;
+  p.Cout = Cout; p.Cin = Cin; p.KH = KH; p.KW = KW; p.pad = pad; p.stride = stride;
   p.BW = pl.BW; p.BH = pl.BH; p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h; p.B = B;
   p.m_tiles = pl.m_tiles; p.n_tiles = pl.n_tiles; p.taps = taps; p.splits = pl.splits;
   p.pt_total = pl.pt_total; p.pt_per_split = pl.pt_per_split;

@@ -261,13 +261,13 @@ int fb200_adamw_step(float* params, const float* grads, float* exp_avg, float* e
 int64_t fb200_conv_wgrad_workspace_bytes(int B, int Ho, int Wo, int Cin, int Cout, int KH, int KW);
 int fb200_conv_wgrad(const float* x, int B, int H, int W, int Cin, int x_pitch, const float* dy, int Ho, int Wo, int Cout, int dy_pitch, int KH,
                      int KW, int stride, int pad, float* dw, int accumulate, void* workspace, void* stream);
-/* Same weight gradient on the tensor cores (stride-1 k=1/3 convs and linears; fb200_conv_wgrad_tc_supported says when): x_pair / dy_pair are
+/* Same weight gradient on the tensor cores (k=1/3 stride-1 convs and linears, 3x3 stride-2 convs through TMA element strides; fb200_conv_wgrad_tc_supported says when): x_pair / dy_pair are
  * the dense [hi|lo] fp16 pairs (fb200_split_f32_pair) of x [B,H,W,Cin] and dy [B,H,W,Cout]; three tcgen05 products per 64-pixel chunk
  * (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM) reproduce the fp32 result to ~2^-21. */
 int fb200_conv_wgrad_tc_supported(int B, int H, int W, int Cin, int Ho, int Wo, int Cout, int KH, int KW, int stride, int pad);
 int64_t fb200_conv_wgrad_tc_workspace_bytes(int B, int Ho, int Wo, int Cin, int Cout, int KH, int KW);
-int fb200_conv_wgrad_tc(const void* x_pair, int B, int H, int W, int Cin, const void* dy_pair, int Cout, int KH, int KW, int pad, float* dw, int accumulate,
-                        void* workspace, void* stream);
+int fb200_conv_wgrad_tc(const void* x_pair, int B, int H, int W, int Cin, const void* dy_pair, int Cout, int KH, int KW, int stride, int pad, float* dw,
+                        int accumulate, void* workspace, void* stream);
 /* zero-dilation of dy for the stride-2 data gradient (dx = conv(dilate(dy), flipped transposed weights) through fb200_conv2d) */
 int fb200_dilate2(const float* dy, int B, int Ho, int Wo, int C, int Hd, int Wd, float* out, void* stream);
 /* column sums of [R,C] (bias gradients); workspace of fb200_col_workspace_bytes(C) also serves the BN / LayerNorm calls below */

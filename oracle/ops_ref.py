@@ -389,14 +389,14 @@ def _rb_conv_wgrad(self, x, dy, KH, KW, stride, pad, dw):
 def _rb_conv_wgrad_tc_supported(self, x_shape, dy_shape, KH, KW, stride, pad):
     B, H, W, Cin = x_shape
     Cout = dy_shape[-1]
-    return stride == 1 and KH == KW and KH in (1, 3) and 2 * pad == KH - 1 and Cin % 8 == 0 and Cout % 8 == 0 and B * H * W >= 512
+    return stride in (1, 2) and KH == KW and KH in (1, 3) and 2 * pad == KH - 1 and not (stride == 2 and KH != 3) and Cin % 8 == 0 and Cout % 8 == 0 and B * dy_shape[1] * dy_shape[2] >= 512
 
 
-def _rb_conv_wgrad_tc(self, x_pair, dy_pair, KH, KW, pad, dw):
+def _rb_conv_wgrad_tc(self, x_pair, dy_pair, KH, KW, stride, pad, dw):
     Cin, Cout = x_pair.shape[-1] // 2, dy_pair.shape[-1] // 2
     xh, xl = x_pair[..., :Cin].float(), x_pair[..., Cin:].float()
     dh, dl = dy_pair[..., :Cout].float(), dy_pair[..., Cout:].float()
-    g = lambda a, b: torch.nn.grad.conv2d_weight(_nchw(a).contiguous(), (Cout, Cin, KH, KW), _nchw(b).contiguous(), stride=1, padding=pad)
+    g = lambda a, b: torch.nn.grad.conv2d_weight(_nchw(a).contiguous(), (Cout, Cin, KH, KW), _nchw(b).contiguous(), stride=stride, padding=pad)
     dw.copy_((g(xh, dh) + g(xl, dh) + g(xh, dl)).permute(0, 2, 3, 1))
 
 
@@ -429,7 +429,7 @@ def _rb_bn_train_bwd(self, x2d, dy2d, y2d, gamma, beta, save_mean, save_rstd, ac
     xh = (x2d - save_mean) * save_rstd
     g = dy2d
     if act == 1:
-        g = dy2d * (y2d > 0)
+        g = dy2d * ((y2d if y2d is not None else xh * gamma + beta) > 0)
     elif act == 2:
         z = (xh * gamma + beta).detach().requires_grad_(True)
         with torch.enable_grad():

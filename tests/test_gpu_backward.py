@@ -209,3 +209,15 @@ def test_weight_gradient_on_tensor_cores(B, H, W, Cin, Cout, k):
     close(got, ref.float(), "wgrad tc", 2e-5)
     simt = A.weight_grad(x.to(DEV), dy.to(DEV), k, k, 1, pad, "fp32")
     close(simt, ref.float(), "wgrad simt", 2e-5)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 40, 40, 128, 128), (2, 31, 45, 64, 256), (4, 80, 80, 256, 256)])
+def test_stride2_weight_gradient_on_tensor_cores(B, H, W, Cin, Cout):
+    """3x3 stride-2 convs: the X operand is gathered by a TMA map that traverses every second pixel (element strides 2)."""
+    k, pad = 3, 1
+    Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    x, dy = rnd((B, H, W, Cin), 1), rnd((B, Ho, Wo, Cout), 2)
+    ref = torch.nn.grad.conv2d_weight(nchw(x).double().contiguous(), (Cout, Cin, k, k), nchw(dy).double().contiguous(), stride=2, padding=pad).permute(0, 2, 3, 1)
+    assert ops._be().conv_wgrad_tc_supported(tuple(x.shape), tuple(dy.shape), k, k, 2, pad)
+    got = A.weight_grad(x.to(DEV), dy.to(DEV), k, k, 2, pad, "fp32_tc")
+    close(got, ref.float(), "wgrad tc stride 2", 2e-5)

@@ -15,12 +15,12 @@ for n in names:
     xp, dp = ops.split_pair(x), ops.split_pair(dy)
     dw = torch.empty((Cout, k, k, Cin), device="cuda")
     for _ in range(3):
-        be.conv_wgrad_tc(xp, dp, k, k, (k - 1) // 2, dw)
+        be.conv_wgrad_tc(xp, dp, k, k, 1, (k - 1) // 2, dw)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(10):
-        be.conv_wgrad_tc(xp, dp, k, k, (k - 1) // 2, dw)
+        be.conv_wgrad_tc(xp, dp, k, k, 1, (k - 1) // 2, dw)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
