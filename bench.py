@@ -174,7 +174,8 @@ def main():
     ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32", "fp32_tc"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--quick", action="store_true", help="skip the bs=1 latency and parity-mode legs")
+    ap.add_argument("--quick", action="store_true", help="skip the bs=1 latency, parity-mode and other-config legs")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the MaskFormer / BisenetFormer / fine-tune legs (separate processes)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -337,6 +338,23 @@ def main():
                 "model": {"useful_gflop_per_img": GFLOP_PER_IMG_USEFUL, "achieved_tflops_whole_step": GFLOP_PER_IMG_USEFUL * B / ms_step,
                           "ideal_ms_per_step_16bit": IDEAL_US_PER_IMG_16BIT * B / 1e3, "frac_of_ideal": (IDEAL_US_PER_IMG_16BIT * B / 1e3) / ms_step}}
 
+    # ---- the other BASELINE.json configs (secondary numbers, each in its own process so that a failure there cannot touch the headline line):
+    # configs[2] MaskFormer bs=16 800^2, configs[3] BisenetFormer bs=64 1024x512, configs[4] fai-detr fine-tune step bs=16 (1 GPU here)
+    other = None
+    if rank == 0 and world == 1 and not args.quick and not args.no_other_configs:
+        other = {}
+        root = os.path.dirname(os.path.abspath(__file__))
+        for key, cmd in (("fai-mf-l-coco-ins bs=16 800x800 inference", ["tools/bench_mf.py"]), ("bisenetformer-l-ade bs=64 1024x512 inference", ["tools/bench_bisenet.py"]),
+                         ("fai-detr-l fine-tune step bs=16 640x640", ["tools/bench_train.py", "--steps", "3", "--warmup", "2"])):
+            try:
+                env = dict(os.environ, FB200_TRACE="0")
+                r = subprocess.run([sys.executable] + cmd, cwd=root, env=env, capture_output=True, text=True, timeout=240)
+                line = next(l for l in r.stdout.splitlines() if l.startswith("{"))
+                d = json.loads(line)
+                other[key] = {k: d[k] for k in ("images_per_s", "value", "ms_per_step", "unfused_images_per_s", "dtype", "phases_ms", "peak_mem_GB") if k in d}
+            except Exception as e:  # noqa: BLE001
+                other[key] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
@@ -345,7 +363,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"fp16": "f16", "fp32": "f32", "fp32_tc": "f32 (3x f16 tensor-core products)"}[args.precision], "data": "synthetic",
                 "config": config, "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
-                "cuda_graph": graph is not None, "latency_bs1": lat, "parity_mode": par, "roofline": roof, "cpu_baseline": cpu, "detections_img0": len(dets[0])}
+                "cuda_graph": graph is not None, "latency_bs1": lat, "parity_mode": par, "other_configs": other, "roofline": roof, "cpu_baseline": cpu, "detections_img0": len(dets[0])}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -99,7 +99,7 @@ def main():
     total = float(sum(v.detach() for v in losses.values()))
     if rank == 0:
         print(json.dumps({"metric": "images/sec fai-detr-l fine-tune step (fwd + criterion + bwd + all-reduce + AdamW)", "value": args.batch * world / (ms / 1e3), "unit": "images/s",
-                          "n_gpus": world, "ms_per_step": ms, "steps": args.steps, "warmup": args.warmup, "scaling": "weak", "dtype": "f32 storage; " + ("3x f16 tcgen05 products for conv/linear fwd+dgrad, SIMT f32 wgrad" if args.precision == "fp32_tc" else "SIMT f32"),
+                          "n_gpus": world, "ms_per_step": ms, "steps": args.steps, "warmup": args.warmup, "scaling": "weak", "dtype": "f32 storage; " + ("3x f16 tcgen05 products for conv/linear forward, data and weight gradients" if args.precision == "fp32_tc" else "SIMT f32"),
                           "config": {"workload": f"fai-detr-l (80 classes) bs={args.batch}/GPU {args.size}x{args.size} synthetic COCO-shape targets (BASELINE configs[4])", "global_batch": args.batch * world},
                           "kernel_launches_per_step": launches, "phases_ms": phases, "peak_mem_GB": torch.cuda.max_memory_allocated() / 1e9, "loss_total": total, "optimizer": opt.stats(), "by_symbol": by_sym}))
     if world > 1:

@@ -19,7 +19,8 @@ for s in $STAGES; do
     tc)    timeout 900 python -m pytest tests/test_gpu_conv_tc.py -q -m gpu 2>&1 | tail -80 > gpurun_out/t_tc.log ;;
     e2e)   timeout 1200 python -m pytest tests/test_gpu_e2e.py -q -m gpu 2>&1 | tail -60 > gpurun_out/t_e2e.log ;;
     smoke) timeout 600 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1 ;;
-    bench) timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err ;;
+    bench) timeout 900 python bench.py --steps 10 --warmup 3 --no-other-configs > gpurun_out/bench.log 2> gpurun_out/bench.err ;;
+    benchfull) (time timeout 900 python bench.py) > gpurun_out/bench_default.log 2> gpurun_out/bench_default.err ;;
     bench32) timeout 900 python bench.py --steps 3 --warmup 3 --precision fp32 --no-cpu-baseline > gpurun_out/bench_fp32.log 2> gpurun_out/bench_fp32.err; timeout 900 python bench.py --steps 10 --warmup 3 --precision fp32_tc --no-cpu-baseline > gpurun_out/bench_fp32tc.log 2> gpurun_out/bench_fp32tc.err ;;
     layers) timeout 600 python tools/layer_roofline.py > gpurun_out/layer_roofline.txt 2>&1 ;;
     micro) (python tools/conv_micro.py; true) > gpurun_out/conv_micro.txt 2>&1 ;;
