@@ -107,7 +107,9 @@ def install():
 
     importlib.metadata.version = _version
     if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+        # appended, not prepended: the reference tree has its own top-level `tests` package, and multiprocessing's spawn hands this
+        # process's sys.path to its children - prepending made `tests.<worker module>` resolve to the reference's package there
+        sys.path.append(REFERENCE_ROOT)
     _installed = True
 
 

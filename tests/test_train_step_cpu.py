@@ -126,7 +126,7 @@ def test_two_rank_gradient_exchange_equals_full_batch_reference():
     procs = [ctx.Process(target=_ddp_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = {r: [torch.from_numpy(a) for a in ps] for r, ps in (q.get(timeout=600) for _ in range(world))}
+    res = {r: [torch.from_numpy(a) for a in ps] for r, ps in (q.get(timeout=150) for _ in range(world))}
     for p in procs:
         p.join(30)
         assert p.exitcode == 0
