@@ -270,20 +270,29 @@ def main():
     def step_e2e():
         return fm(host_u8, threshold=0.5, batched=True)
 
-    for _ in range(3):
+    for _ in range(5):  # call 1 runs eagerly, call 2 captures the CUDA graph of model.forward, calls 3+ replay it
         step_e2e()
     torch.cuda.synchronize()
+    # serving-style GC hygiene: everything allocated so far (model, packed weights, graph pools) moves to the permanent generation, so the cyclic
+    # collector only ever walks the per-step detection objects (a full collection over the torch heap showed up as one ~50 ms step in 25)
+    import gc
+    gc.collect()
+    gc.freeze()
     if world > 1:
         dist.barrier()
     e2e_steps = max(3, args.steps // 2)
+    per_step = []
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
+        ts = time.perf_counter()
         dets = step_e2e()
+        per_step.append((time.perf_counter() - ts) * 1e3)
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
     e2e_ms = D.max_over_ranks(e2e_ms, dev)
+    per_step.sort()
     e2e = {"value": B * world / (e2e_ms / 1e3), "unit": "images/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(host_u8.numel()) + B * 8,
-           "d2h_bytes_per_step": B * (300 * 7 + 1) * 4, "api": "FocoosModel.__call__(pinned uint8 [B,H,W,3], batched=True)"}
+           "d2h_bytes_per_step": B * (300 * 7 + 1) * 4, "p50_ms": per_step[len(per_step) // 2], "max_ms": per_step[-1], "steps": e2e_steps, "api": "FocoosModel.__call__(pinned uint8 [B,H,W,3], batched=True)"}
 
     # ---- bs=1 latency (BASELINE.json metric, second half): p50/p90 of single-image forward+post-process, CUDA graph replay, device-timed
     lat = None
