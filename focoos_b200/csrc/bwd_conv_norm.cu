@@ -77,6 +77,52 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict
   }
 }
 
+// Weight gradient of the stem conv (3x3, stride 2, pad 1, Cin <= 4, Cout = 32): 864 outputs reduced over B*Ho*Wo pixels.  The generic 64x64 tile would waste
+// 31/32 of its FMAs on the 3-channel operand; here a block stages an 8 x 16 tile of dY and the (17 x 33) x Cin input halo in shared memory and thread
+// (co = t % 32, g = t / 32) accumulates the (tap, ci) pairs j = g, g + 8, ... < 9*Cin for its output channel.  Per-block partials, fixed-order reduce.
+constexpr int SW_TH = 8, SW_TW = 16;
+__global__ void __launch_bounds__(256) conv_wgrad_stem_kernel(const float* __restrict__ x, int x_pitch, const float* __restrict__ dy, int dy_pitch, int B, int H, int W,
+                                                              int Cin, int Ho, int Wo, int tiles_w, int tiles_h, float* __restrict__ part) {
+  __shared__ float sdy[SW_TH * SW_TW][33];
+  __shared__ float sx[(2 * SW_TH + 1) * (2 * SW_TW + 1) * 4];
+  const int co = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int K = 9 * Cin;  // <= 36
+  float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  const int PW = 2 * SW_TW + 1, PH = 2 * SW_TH + 1;
+  const int64_t ntiles = (int64_t)B * tiles_h * tiles_w;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int b = t / (tiles_h * tiles_w), rem = t % (tiles_h * tiles_w);
+    const int ho0 = (rem / tiles_w) * SW_TH, wo0 = (rem % tiles_w) * SW_TW;
+    __syncthreads();
+    for (int i = threadIdx.x; i < SW_TH * SW_TW * 32; i += 256) {
+      const int c = i & 31, p = i >> 5, ho = ho0 + p / SW_TW, wo = wo0 + p % SW_TW;
+      sdy[p][c] = (ho < Ho && wo < Wo) ? dy[(((int64_t)b * Ho + ho) * Wo + wo) * dy_pitch + c] : 0.f;
+    }
+    for (int i = threadIdx.x; i < PH * PW * Cin; i += 256) {
+      const int ci = i % Cin, pp = i / Cin, hi = 2 * ho0 - 1 + pp / PW, wi = 2 * wo0 - 1 + pp % PW;
+      sx[pp * 4 + ci] = (hi >= 0 && hi < H && wi >= 0 && wi < W) ? x[(((int64_t)b * H + hi) * W + wi) * x_pitch + ci] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 5; ++u) {
+      const int j = g + 8 * u;
+      if (j >= K) break;
+      const int tap = j / Cin, ci = j - tap * Cin, kh = tap / 3, kw = tap - kh * 3;
+      float a = 0.f;
+      for (int py = 0; py < SW_TH; ++py)
+#pragma unroll 8
+        for (int px = 0; px < SW_TW; ++px) a = fmaf(sdy[py * SW_TW + px][co], sx[((2 * py + kh) * PW + 2 * px + kw) * 4 + ci], a);
+      acc[u] += a;
+    }
+  }
+  float* out = part + (int64_t)blockIdx.x * 32 * K;
+#pragma unroll
+  for (int u = 0; u < 5; ++u) {
+    const int j = g + 8 * u;
+    if (j < K) out[co * K + j] = acc[u];  // j = tap * Cin + ci: the [Cout][KH][KW][Cin] order
+  }
+}
+
 __global__ void split_reduce_kernel(const float* __restrict__ part, int splits, int64_t n, float* __restrict__ out, int accumulate) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -517,6 +563,7 @@ extern "C" int64_t fb200_conv_wgrad_workspace_bytes(int B, int Ho, int Wo, int C
   const int64_t tiles = (int64_t)cdiv(Cout, WG_TM) * cdiv(Cin, WG_TN) * KH * KW;
   const int64_t P = (int64_t)B * Ho * Wo;
   int64_t splits = std::max<int64_t>(1, std::min<int64_t>(cdiv(148 * 4, tiles), cdiv(P, 512)));
+  splits = std::max<int64_t>(splits, 296);  // the stem kernel writes one partial per block (<= 296 blocks)
   return splits * Cout * KH * KW * Cin * 4 + 16;
 }
 
@@ -525,6 +572,17 @@ extern "C" int fb200_conv_wgrad(const float* x, int B, int H, int W, int Cin, in
   FB_CHECK_ARG(x && dy && dw && workspace, "conv_wgrad: null pointer");
   FB_CHECK_ARG(B > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && stride >= 1, "conv_wgrad: bad sizes");
   FB_CHECK_ARG(Ho == (H + 2 * pad - KH) / stride + 1 && Wo == (W + 2 * pad - KW) / stride + 1, "conv_wgrad: output size does not match");
+  if (KH == 3 && KW == 3 && stride == 2 && pad == 1 && Cin <= 4 && Cout == 32 && 296LL * 32 * 9 * Cin * 4 + 16 <= fb200_conv_wgrad_workspace_bytes(B, Ho, Wo, Cin, Cout, KH, KW)) {
+    const int tiles_w = (int)cdiv(Wo, SW_TW), tiles_h = (int)cdiv(Ho, SW_TH);
+    const int nblk = (int)std::min<int64_t>(296, (int64_t)B * tiles_w * tiles_h);
+    cudaStream_t st0 = (cudaStream_t)stream;
+    conv_wgrad_stem_kernel<<<nblk, 256, 0, st0>>>(x, x_pitch, dy, dy_pitch, B, H, W, Cin, Ho, Wo, tiles_w, tiles_h, reinterpret_cast<float*>(workspace));
+    FB_CHECK_LAUNCH("conv_wgrad(stem)");
+    const int64_t n0 = (int64_t)Cout * 9 * Cin;
+    split_reduce_kernel<<<(unsigned)cdiv(n0, 256), 256, 0, st0>>>(reinterpret_cast<float*>(workspace), nblk, n0, dw, accumulate);
+    FB_CHECK_LAUNCH("conv_wgrad(stem reduce)");
+    return FB200_OK;
+  }
   const int64_t tiles = (int64_t)cdiv(Cout, WG_TM) * cdiv(Cin, WG_TN);
   const int64_t P = (int64_t)B * Ho * Wo;
   const int64_t splits = std::max<int64_t>(1, std::min<int64_t>(cdiv(148 * 4, tiles * KH * KW), cdiv(P, 512)));

@@ -221,3 +221,19 @@ def test_stride2_weight_gradient_on_tensor_cores(B, H, W, Cin, Cout):
     assert ops._be().conv_wgrad_tc_supported(tuple(x.shape), tuple(dy.shape), k, k, 2, pad)
     got = A.weight_grad(x.to(DEV), dy.to(DEV), k, k, 2, pad, "fp32_tc")
     close(got, ref.float(), "wgrad tc stride 2", 2e-5)
+
+
+def test_stem_weight_gradient_kernel():
+    """3x3 stride-2 conv on the 3-channel image (conv1_1): dedicated CUDA-core kernel (8x16 dY tile + input halo in shared memory)."""
+    B, H, W, Cin, Cout = 2, 70, 100, 3, 32
+    x, w = rnd((B, H, W, Cin), 1), rnd((Cout, Cin, 3, 3), 2, 0.2)
+    xr, wr = leaf(x), leaf(w)
+    yr = nhwc(F.conv2d(nchw(xr), wr, None, 2, 1))
+    dy = rnd(tuple(yr.shape), 4)
+    yr.backward(dy)
+    xg, wg = leaf(x, DEV), leaf(w, DEV)
+    yg = A.conv2d(xg, wg, None, 2, 1, "fp32_tc")
+    yg.backward(dy.to(DEV))
+    close(yg, yr, "stem fwd")
+    close(wg.grad, wr.grad, "stem dw")
+    close(xg.grad, xr.grad, "stem dx")
