@@ -262,6 +262,136 @@ __global__ void __launch_bounds__(256) mask_sigmoid_upsample_kernel(const T* __r
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Instance post-process fused into the upsampling (fai_mf/processor.py:222-257 on top of modelling.py:619,722-723): per (b,q) the number of pixels with
+// prob >= thr and their probability mass, straight from the low-resolution logits - the [B,Q,H,W] tensor (4.1 GB at 16 x 100 x 800 x 800) is never written
+// or re-read.  Same tiling and the same probability expression as mask_sigmoid_upsample_kernel; counts are exact, the mass is summed with float atomics
+// (order not fixed: ~1e-7 relative).
+template <typename T>
+__global__ void __launch_bounds__(256) mask_upsample_stats_kernel(const T* __restrict__ x, int h, int w, int Qp, int Q, int H, int W, float sh, float sw, int ph_max,
+                                                                  int pw_max, float thr, int* __restrict__ count, float* __restrict__ psum) {
+  extern __shared__ float patch[];  // [ph][pw][Q], then [Q] float mass, [Q] int count
+  float* s_sum = patch + (size_t)ph_max * pw_max * Q;
+  int* s_cnt = reinterpret_cast<int*>(s_sum + Q);
+  const int b = blockIdx.z, oy0 = blockIdx.y * MU_TH, ox0 = blockIdx.x * MU_TW;
+  const int oy1 = min(oy0 + MU_TH, H) - 1, ox1 = min(ox0 + MU_TW, W) - 1;
+  const int ys0 = (int)fmaxf(((float)oy0 + 0.5f) * sh - 0.5f, 0.f), xs0 = (int)fmaxf(((float)ox0 + 0.5f) * sw - 0.5f, 0.f);
+  const int ys1 = min((int)fmaxf(((float)oy1 + 0.5f) * sh - 0.5f, 0.f) + 1, h - 1), xs1 = min((int)fmaxf(((float)ox1 + 0.5f) * sw - 0.5f, 0.f) + 1, w - 1);
+  const int ph = ys1 - ys0 + 1, pw = xs1 - xs0 + 1;
+  for (int i = threadIdx.x; i < Q; i += 256) { s_sum[i] = 0.f; s_cnt[i] = 0; }
+  for (int i = threadIdx.x; i < ph * pw * Q; i += 256) {
+    const int qq = i % Q, pp = i / Q, px = pp % pw, py = pp / pw;
+    const float v = to_f(x[(((int64_t)b * h + ys0 + py) * w + xs0 + px) * Qp + qq]);
+    patch[i] = 1.f / (1.f + expf(-v));
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  if ((Q & 3) == 0 && Q <= 128) {
+    // thread = (query quad qg, pixel group pgp): four queries per 16-byte shared-memory load, counts / mass for its quad kept in registers over the
+    // tile's pixels - no per-query warp reductions, 4x fewer shared-memory instructions than the pixel-per-thread mapping
+    const int nq4 = Q >> 2, ngroups = 256 / nq4;
+    const int qg = threadIdx.x % nq4, pgp = threadIdx.x / nq4;
+    if (pgp < ngroups) {
+      int c[4] = {0, 0, 0, 0};
+      float m[4] = {0.f, 0.f, 0.f, 0.f};
+      const int tw = min(MU_TW, W - ox0), th = min(MU_TH, H - oy0);
+      for (int p = pgp; p < tw * th; p += ngroups) {
+        const int py = p / tw, px = p - py * tw;
+        const float fx = fmaxf(((float)(ox0 + px) + 0.5f) * sw - 0.5f, 0.f), fy = fmaxf(((float)(oy0 + py) + 0.5f) * sh - 0.5f, 0.f);
+        const int x0 = min((int)fx, w - 1), x1 = min(x0 + 1, w - 1), y0 = min((int)fy, h - 1), y1 = min(y0 + 1, h - 1);
+        const float lw1 = fx - (float)x0, lw0 = 1.f - lw1, lh1 = fy - (float)y0, lh0 = 1.f - lh1;
+        const float4 v00 = *reinterpret_cast<const float4*>(patch + ((y0 - ys0) * pw + (x0 - xs0)) * Q + qg * 4);
+        const float4 v01 = *reinterpret_cast<const float4*>(patch + ((y0 - ys0) * pw + (x1 - xs0)) * Q + qg * 4);
+        const float4 v10 = *reinterpret_cast<const float4*>(patch + ((y1 - ys0) * pw + (x0 - xs0)) * Q + qg * 4);
+        const float4 v11 = *reinterpret_cast<const float4*>(patch + ((y1 - ys0) * pw + (x1 - xs0)) * Q + qg * 4);
+        const float pr[4] = {lh0 * (lw0 * v00.x + lw1 * v01.x) + lh1 * (lw0 * v10.x + lw1 * v11.x), lh0 * (lw0 * v00.y + lw1 * v01.y) + lh1 * (lw0 * v10.y + lw1 * v11.y),
+                             lh0 * (lw0 * v00.z + lw1 * v01.z) + lh1 * (lw0 * v10.z + lw1 * v11.z), lh0 * (lw0 * v00.w + lw1 * v01.w) + lh1 * (lw0 * v10.w + lw1 * v11.w)};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (pr[k] >= thr) { ++c[k]; m[k] += pr[k]; }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (c[k]) { atomicAdd(&s_cnt[qg * 4 + k], c[k]); atomicAdd(&s_sum[qg * 4 + k], m[k]); }
+    }
+  } else {
+  const int tx = threadIdx.x & 63, r0 = threadIdx.x >> 6;
+  int o00[4], o01[4], o10[4], o11[4];
+  float wy[4], wx;
+  bool ok[4];
+  const int X = ox0 + tx;
+  {
+    const float fx = fmaxf(((float)min(X, W - 1) + 0.5f) * sw - 0.5f, 0.f);
+    const int x0 = min((int)fx, w - 1), x1 = min(x0 + 1, w - 1);
+    wx = fx - (float)x0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int Y = oy0 + r0 + 4 * i;
+      ok[i] = X < W && Y < H;
+      const float fy = fmaxf(((float)min(Y, H - 1) + 0.5f) * sh - 0.5f, 0.f);
+      const int y0 = min((int)fy, h - 1), y1 = min(y0 + 1, h - 1);
+      wy[i] = fy - (float)y0;
+      o00[i] = ((y0 - ys0) * pw + (x0 - xs0)) * Q; o01[i] = ((y0 - ys0) * pw + (x1 - xs0)) * Q;
+      o10[i] = ((y1 - ys0) * pw + (x0 - xs0)) * Q; o11[i] = ((y1 - ys0) * pw + (x1 - xs0)) * Q;
+    }
+  }
+  for (int qq = 0; qq < Q; ++qq) {
+    int c = 0;
+    float m = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float v00 = patch[o00[i] + qq], v01 = patch[o01[i] + qq], v10 = patch[o10[i] + qq], v11 = patch[o11[i] + qq];
+      const float lw1 = wx, lw0 = 1.f - wx, lh1 = wy[i], lh0 = 1.f - wy[i];
+      const float pr = lh0 * (lw0 * v00 + lw1 * v01) + lh1 * (lw0 * v10 + lw1 * v11);
+      if (ok[i] && pr >= thr) { ++c; m += pr; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { c += __shfl_xor_sync(0xffffffffu, c, o); m += __shfl_xor_sync(0xffffffffu, m, o); }
+    if (lane == 0 && c) { atomicAdd(&s_cnt[qq], c); atomicAdd(&s_sum[qq], m); }
+  }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Q; i += 256)
+    if (s_cnt[i]) { atomicAdd(&count[b * Q + i], s_cnt[i]); atomicAdd(&psum[b * Q + i], s_sum[i]); }
+}
+
+// out[i] = bilinear(sigmoid(x[b_i, :, :, q_i])) for the n kept (b,q) pairs only: [n,H,W] fp32, same expression as the full upsampling
+template <typename T>
+__global__ void __launch_bounds__(256) mask_upsample_select_kernel(const T* __restrict__ x, int h, int w, int Qp, const int* __restrict__ bq, float* __restrict__ out,
+                                                                   int H, int W, float sh, float sw) {
+  extern __shared__ float patch[];  // [ph][pw]
+  const int i_ = blockIdx.z, b = bq[i_ * 2], q = bq[i_ * 2 + 1];
+  const int oy0 = blockIdx.y * MU_TH, ox0 = blockIdx.x * MU_TW;
+  const int oy1 = min(oy0 + MU_TH, H) - 1, ox1 = min(ox0 + MU_TW, W) - 1;
+  const int ys0 = (int)fmaxf(((float)oy0 + 0.5f) * sh - 0.5f, 0.f), xs0 = (int)fmaxf(((float)ox0 + 0.5f) * sw - 0.5f, 0.f);
+  const int ys1 = min((int)fmaxf(((float)oy1 + 0.5f) * sh - 0.5f, 0.f) + 1, h - 1), xs1 = min((int)fmaxf(((float)ox1 + 0.5f) * sw - 0.5f, 0.f) + 1, w - 1);
+  const int ph = ys1 - ys0 + 1, pw = xs1 - xs0 + 1;
+  for (int i = threadIdx.x; i < ph * pw; i += 256) {
+    const int px = i % pw, py = i / pw;
+    const float v = to_f(x[(((int64_t)b * h + ys0 + py) * w + xs0 + px) * Qp + q]);
+    patch[i] = 1.f / (1.f + expf(-v));
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 63, r0 = threadIdx.x >> 6;
+  const int X = ox0 + tx;
+  if (X >= W) return;
+  const float fx = fmaxf(((float)X + 0.5f) * sw - 0.5f, 0.f);
+  const int x0 = min((int)fx, w - 1), x1 = min(x0 + 1, w - 1);
+  const float wx = fx - (float)x0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int Y = oy0 + r0 + 4 * i;
+    if (Y >= H) continue;
+    const float fy = fmaxf(((float)Y + 0.5f) * sh - 0.5f, 0.f);
+    const int y0 = min((int)fy, h - 1), y1 = min(y0 + 1, h - 1);
+    const float wyv = fy - (float)y0;
+    const float v00 = patch[(y0 - ys0) * pw + (x0 - xs0)], v01 = patch[(y0 - ys0) * pw + (x1 - xs0)];
+    const float v10 = patch[(y1 - ys0) * pw + (x0 - xs0)], v11 = patch[(y1 - ys0) * pw + (x1 - xs0)];
+    const float lw1 = wx, lw0 = 1.f - wx, lh1 = wyv, lh0 = 1.f - wyv;
+    out[((int64_t)i_ * H + Y) * W + X] = lh0 * (lw0 * v00 + lw1 * v01) + lh1 * (lw0 * v10 + lw1 * v11);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // per plane: count(p >= thr), sum(p * [p >= thr])
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) mask_stats_kernel(const float* __restrict__ masks, int64_t hw, float thr, int* __restrict__ count,
@@ -410,6 +540,38 @@ extern "C" int fb200_mask_sigmoid_upsample_argmax(const void* x, int dtype, int 
                                                   int* counts, void* stream) {
   FB_CHECK_ARG(x && scores && labels && counts && Q <= Qp && Q <= 255 && H >= h && W >= w, "mask_sigmoid_upsample_argmax: bad arguments (upsampling only, Q <= 255)");
   return mask_upsample_launch(x, dtype, B, h, w, Qp, Q, nullptr, H, W, scores, labels, counts, stream);
+}
+
+extern "C" int fb200_mask_sigmoid_upsample_stats(const void* x, int dtype, int B, int h, int w, int Qp, int Q, int H, int W, float thr, int* count, float* psum,
+                                                 void* stream) {
+  FB_CHECK_ARG(x && count && psum && Q <= Qp && H >= h && W >= w, "mask_sigmoid_upsample_stats: bad arguments (upsampling only)");
+  const float sh = (float)h / (float)H, sw = (float)w / (float)W;
+  const int ph = (int)(MU_TH * sh) + 3, pw = (int)(MU_TW * sw) + 3;
+  const size_t smem = (size_t)ph * pw * Q * sizeof(float) + (size_t)Q * 8;
+  FB_CHECK_ARG(smem <= 200 * 1024, "mask_sigmoid_upsample_stats: low-resolution patch does not fit shared memory (%zu B)", smem);
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(mask_upsample_stats_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(mask_upsample_stats_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    configured = true;
+  }
+  cudaMemsetAsync(count, 0, (size_t)B * Q * sizeof(int), st);
+  cudaMemsetAsync(psum, 0, (size_t)B * Q * sizeof(float), st);
+  dim3 grid((unsigned)cdiv(W, MU_TW), (unsigned)cdiv(H, MU_TH), (unsigned)B);
+  FB_DISPATCH_DTYPE(dtype, T, (mask_upsample_stats_kernel<T><<<grid, 256, smem, st>>>((const T*)x, h, w, Qp, Q, H, W, sh, sw, ph, pw, thr, count, psum)));
+  FB_CHECK_LAUNCH("mask_sigmoid_upsample_stats");
+  return FB200_OK;
+}
+
+extern "C" int fb200_mask_sigmoid_upsample_select(const void* x, int dtype, int h, int w, int Qp, const int* bq, int n, float* out, int H, int W, void* stream) {
+  FB_CHECK_ARG(x && bq && out && n > 0 && H >= h && W >= w, "mask_sigmoid_upsample_select: bad arguments (upsampling only)");
+  const float sh = (float)h / (float)H, sw = (float)w / (float)W;
+  const int ph = (int)(MU_TH * sh) + 3, pw = (int)(MU_TW * sw) + 3;
+  dim3 grid((unsigned)cdiv(W, MU_TW), (unsigned)cdiv(H, MU_TH), (unsigned)n);
+  FB_DISPATCH_DTYPE(dtype, T, (mask_upsample_select_kernel<T><<<grid, 256, (size_t)ph * pw * sizeof(float), (cudaStream_t)stream>>>((const T*)x, h, w, Qp, bq, out, H, W, sh, sw)));
+  FB_CHECK_LAUNCH("mask_sigmoid_upsample_select");
+  return FB200_OK;
 }
 
 extern "C" int fb200_mask_stats(const float* masks, int64_t planes, int64_t hw, float thr, int* count, float* psum, void* stream) {

@@ -515,7 +515,7 @@ except Exception:  # pragma: no cover - e.g. double import under a different mod
 # ------------------------------------------------------------------------------------------------
 EXPORTED_SYMBOLS = EXPORTED_SYMBOLS + (
     "fb200_upsample_nearest_add", "fb200_attn_mask_build", "fb200_attention_masked", "fb200_softmax_drop_last",
-    "fb200_mask_sigmoid_upsample", "fb200_mask_sigmoid_upsample_argmax", "fb200_mask_stats", "fb200_mask_resize_bbox",
+    "fb200_mask_sigmoid_upsample", "fb200_mask_sigmoid_upsample_argmax", "fb200_mask_sigmoid_upsample_stats", "fb200_mask_sigmoid_upsample_select", "fb200_mask_stats", "fb200_mask_resize_bbox",
 )
 
 
@@ -556,6 +556,18 @@ def _cb_mask_sigmoid_upsample_argmax(self, x, Q, scores, labels, counts):
     self._call("fb200_mask_sigmoid_upsample_argmax", _p(x), _dt(x), B, h, w, Qp, Q, _p(scores), labels.shape[1], labels.shape[2], _p(labels), _p(counts), _stream())
 
 
+def _cb_mask_sigmoid_upsample_stats(self, x, Q, size, thr, count, psum):
+    self._cuda(x, count, psum)
+    B, h, w, Qp = x.shape
+    self._call("fb200_mask_sigmoid_upsample_stats", _p(x), _dt(x), B, h, w, Qp, Q, size[0], size[1], ctypes.c_float(thr), _p(count), _p(psum), _stream())
+
+
+def _cb_mask_sigmoid_upsample_select(self, x, bq, out):
+    self._cuda(x, bq, out)
+    _, h, w, Qp = x.shape
+    self._call("fb200_mask_sigmoid_upsample_select", _p(x), _dt(x), h, w, Qp, _p(bq), bq.shape[0], _p(out), out.shape[1], out.shape[2], _stream())
+
+
 def _cb_mask_stats(self, masks, thr, count, psum):
     self._cuda(masks, count, psum)
     B, Q, H, W = masks.shape
@@ -568,7 +580,8 @@ def _cb_mask_resize_bbox(self, masks, bq, thr, out_masks, out_bbox):
     self._call("fb200_mask_resize_bbox", _p(masks), Q, H, W, _p(bq), bq.shape[0], ctypes.c_float(thr), _p(out_masks), out_masks.shape[1], out_masks.shape[2], _p(out_bbox), _stream())
 
 
-for _n, _f in (("mask_sigmoid_upsample_argmax", _cb_mask_sigmoid_upsample_argmax), ("upsample_nearest_add", _cb_upsample_nearest_add), ("attn_mask_build", _cb_attn_mask_build), ("attention_masked", _cb_attention_masked),
+for _n, _f in (("mask_sigmoid_upsample_stats", _cb_mask_sigmoid_upsample_stats), ("mask_sigmoid_upsample_select", _cb_mask_sigmoid_upsample_select),
+               ("mask_sigmoid_upsample_argmax", _cb_mask_sigmoid_upsample_argmax), ("upsample_nearest_add", _cb_upsample_nearest_add), ("attn_mask_build", _cb_attn_mask_build), ("attention_masked", _cb_attention_masked),
                ("softmax_drop_last", _cb_softmax_drop_last), ("mask_sigmoid_upsample", _cb_mask_sigmoid_upsample), ("mask_stats", _cb_mask_stats),
                ("mask_resize_bbox", _cb_mask_resize_bbox)):
     setattr(CudaBackend, _n, _f)
@@ -625,6 +638,24 @@ def mask_sigmoid_upsample_argmax(mask_logits_nhwc, num_queries: int, size, score
     counts = torch.empty((B, num_queries), dtype=torch.int32, device=mask_logits_nhwc.device)
     _be().mask_sigmoid_upsample_argmax(mask_logits_nhwc.contiguous(), num_queries, scores.contiguous().float(), labels, counts)
     return labels, counts
+
+
+def mask_sigmoid_upsample_stats(mask_logits_nhwc, num_queries: int, size, thr: float):
+    """(count [B,Q] int32, psum [B,Q] fp32) of mask_stats(mask_sigmoid_upsample(x)) without materialising the [B,Q,H,W] probabilities."""
+    B = mask_logits_nhwc.shape[0]
+    count = torch.empty((B, num_queries), dtype=torch.int32, device=mask_logits_nhwc.device)
+    psum = torch.empty((B, num_queries), dtype=torch.float32, device=mask_logits_nhwc.device)
+    _be().mask_sigmoid_upsample_stats(mask_logits_nhwc.contiguous(), num_queries, (int(size[0]), int(size[1])), float(thr), count, psum)
+    return count, psum
+
+
+def mask_sigmoid_upsample_select(mask_logits_nhwc, bq_i32, size):
+    """upsampled probabilities [n,H,W] of the kept (b,q) pairs only (same values as mask_sigmoid_upsample(x)[b,q])."""
+    n = bq_i32.shape[0]
+    out = torch.empty((n, int(size[0]), int(size[1])), dtype=torch.float32, device=mask_logits_nhwc.device)
+    if n:
+        _be().mask_sigmoid_upsample_select(mask_logits_nhwc.contiguous(), bq_i32.contiguous(), out)
+    return out
 
 
 def mask_stats(masks, thr: float):

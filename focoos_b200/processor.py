@@ -173,7 +173,7 @@ class MaskFormerProcessor(DETRProcessor):
         """-> list over images of (query idx [n], scores [n], labels [n]) on the host, plus the device masks tensor."""
         threshold = threshold or self.threshold
         use_mask_score = use_mask_score or self.use_mask_score
-        self._labels = self._masks = None
+        self._labels = self._masks = self._lazy = None
         lazy = hasattr(output.masks, "materialize")  # fai_mf.LazyMasks: low-resolution logits, upsampling not done yet
         if self.predict_all_pixels:  # semantic: every pixel goes to argmax_q(score_q * prob_q) (processor.py:208-220)
             scores_dev = output.logits.max(-1).values  # [B,Q]; tiny reduction, stays on the device for the argmax kernel
@@ -183,8 +183,12 @@ class MaskFormerProcessor(DETRProcessor):
                 self._labels, count = ops.mask_argmax(output.masks, scores_dev)
             psum = count.float()
         else:
-            self._masks = output.masks.materialize() if lazy else output.masks  # never written back into `output` (it may be a CUDA-graph static)
-            count, psum = ops.mask_stats(self._masks, float(self.mask_threshold))
+            if lazy:  # counts / probability mass straight from the low-resolution logits; only the kept masks are upsampled later
+                self._lazy = output.masks
+                count, psum = ops.mask_sigmoid_upsample_stats(output.masks.logits, output.masks.num_queries, output.masks.size, float(self.mask_threshold))
+            else:
+                self._masks = output.masks  # never written back into `output` (it may be a CUDA-graph static)
+                count, psum = ops.mask_stats(self._masks, float(self.mask_threshold))
         host = torch.cat([output.logits.reshape(output.logits.shape[0], -1), count.float(), psum], dim=1).cpu().numpy()  # one D2H
         B, Q, K = output.logits.shape
         res = []
@@ -214,7 +218,12 @@ class MaskFormerProcessor(DETRProcessor):
             if self._labels is not None:
                 m, box = ops.label_resize_bbox(self._labels, bq, image_sizes[b])
             else:
-                m, box = ops.mask_resize_bbox(self._masks, bq, float(self.mask_threshold), image_sizes[b])
+                if self._lazy is not None:  # upsample just this image's kept planes, then index them as a [n,1,H,W] batch
+                    planes = ops.mask_sigmoid_upsample_select(self._lazy.logits, bq, self._lazy.size).unsqueeze(1)
+                    idx = torch.stack([torch.arange(len(q), dtype=torch.int32), torch.zeros(len(q), dtype=torch.int32)], 1).to(planes.device)
+                    m, box = ops.mask_resize_bbox(planes, idx, float(self.mask_threshold), image_sizes[b])
+                else:
+                    m, box = ops.mask_resize_bbox(self._masks, bq, float(self.mask_threshold), image_sizes[b])
             m, box = m.cpu().numpy().astype(bool), box.cpu().numpy()
             dets = []
             for i in range(len(q)):

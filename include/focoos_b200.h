@@ -177,6 +177,10 @@ int fb200_mask_sigmoid_upsample(const void* x, int dtype, int B, int h, int w, i
  * written.  Bit-identical to fb200_mask_argmax(fb200_mask_sigmoid_upsample(x)). */
 int fb200_mask_sigmoid_upsample_argmax(const void* x, int dtype, int B, int h, int w, int Qp, int Q, const float* scores, int H, int W, uint8_t* labels,
                                        int* counts, void* stream);
+/* The INSTANCE post-process fused in the same way (processor.py:222-257): count[b,q] = #pixels with prob >= thr, psum[b,q] = their probability mass,
+ * straight from the low-resolution logits; and the upsampled probabilities of only the n kept (b,q) pairs (bq [n,2] i32 -> out [n,H,W] f32). */
+int fb200_mask_sigmoid_upsample_stats(const void* x, int dtype, int B, int h, int w, int Qp, int Q, int H, int W, float thr, int* count, float* psum, void* stream);
+int fb200_mask_sigmoid_upsample_select(const void* x, int dtype, int h, int w, int Qp, const int* bq, int n, float* out, int H, int W, void* stream);
 
 /* MaskFormerProcessor.postprocess reductions (fai_mf/processor.py:222-257): per plane of masks [planes, hw] fp32:
  * count = #(p >= thr), psum = sum of those p. */

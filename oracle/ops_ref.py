@@ -548,3 +548,21 @@ def _rb_mask_sigmoid_upsample_argmax(self, x, Q, scores, labels, counts):
 
 
 RefBackend.mask_sigmoid_upsample_argmax = _rb_mask_sigmoid_upsample_argmax
+
+
+def _rb_mask_sigmoid_upsample_stats(self, x, Q, size, thr, count, psum):
+    probs = torch.empty((x.shape[0], Q, size[0], size[1]), dtype=torch.float32)
+    self.mask_sigmoid_upsample(x, Q, probs)
+    self.mask_stats(probs, thr, count, psum)
+
+
+def _rb_mask_sigmoid_upsample_select(self, x, bq, out):
+    Q = int(bq[:, 1].max()) + 1
+    probs = torch.empty((x.shape[0], Q, out.shape[1], out.shape[2]), dtype=torch.float32)
+    self.mask_sigmoid_upsample(x, Q, probs)
+    for i in range(bq.shape[0]):
+        out[i] = probs[int(bq[i, 0]), int(bq[i, 1])]
+
+
+RefBackend.mask_sigmoid_upsample_stats = _rb_mask_sigmoid_upsample_stats
+RefBackend.mask_sigmoid_upsample_select = _rb_mask_sigmoid_upsample_select

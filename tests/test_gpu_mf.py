@@ -155,3 +155,40 @@ def test_mf_end_to_end_vs_reference_golden(precision):
         assert box_dev <= 3, box_dev
     else:
         assert np.isfinite(e_logit)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_fused_upsample_stats_and_select(dtype):
+    """instance post-process fused into the upsampling: counts exact, probability mass to fp32 reassociation, selected planes bit-identical."""
+    g = torch.Generator().manual_seed(7)
+    B, h, w, Q = 2, 40, 52, 100
+    x = (torch.randn((B, h, w, 104), generator=g) * 3).to(dtype).to(DEV)
+    for size in ((160, 208), (150, 200)):
+        probs = ops.mask_sigmoid_upsample(x, Q, size)
+        c0, s0 = ops.mask_stats(probs, 0.5)
+        c1, s1 = ops.mask_sigmoid_upsample_stats(x, Q, size, 0.5)
+        assert torch.equal(c0, c1), size
+        assert float((s0 - s1).abs().max()) <= 1e-5 * float(s0.abs().max()), size
+        bq = torch.tensor([[0, 3], [1, 99], [1, 0], [0, 57]], dtype=torch.int32, device=DEV)
+        sel = ops.mask_sigmoid_upsample_select(x, bq, size)
+        for i, (b, q) in enumerate(bq.tolist()):
+            assert torch.equal(sel[i], probs[b, q]), (size, b, q)
+
+
+def test_mf_lazy_instance_path_equals_materialised():
+    g = load_golden("mf_l_coco_ins_b2_320x416")
+    sd = seeded_state_dict(manifest_template("fai_mf_l_coco_ins"), 0)
+    m = FAIMaskFormer(MaskFormerConfig(), precision="fp32")
+    m.load_state_dict(sd, strict=True)
+    m.cuda()
+    imgs = synth_images(3, [tuple(s) for s in g["sizes"].tolist()])
+    x = torch.stack([torch.from_numpy(im).permute(2, 0, 1).float() for im in imgs]).cuda()
+    proc = MaskFormerProcessor(m.config)
+    ref = proc.postprocess(m(x), imgs, threshold=float(g["threshold"]))
+    m.lazy_masks = True
+    out = m(x)
+    m.lazy_masks = False
+    got = proc.postprocess(out, imgs, threshold=float(g["threshold"]))
+    for a, b in zip(ref, got):
+        assert [(d.cls_id, d.bbox, d.mask) for d in a.detections] == [(d.cls_id, d.bbox, d.mask) for d in b.detections]
+        assert np.allclose([d.conf for d in a.detections], [d.conf for d in b.detections], rtol=1e-5)
