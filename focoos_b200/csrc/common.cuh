@@ -87,6 +87,7 @@ struct ConvParams {
   int B, H, W, Cin, x_pitch, KH, KW, stride, pad, Ho, Wo, Cout, res_pitch, out_pitch, act;
   int64_t M; int K; int x_dtype, out_dtype, vec_ok; int split3; int64_t out_bs;  // out_bs: elements between images of `out`
   int64_t w_bs = 0;  // elements between the per-image weight sets (0 = one shared weight tensor)
+  float* rowmax = nullptr;  // not null: no output tensor, only max over the Cout columns of every row (atomic max into a buffer pre-filled with -inf)
 };
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }

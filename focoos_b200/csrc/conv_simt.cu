@@ -276,6 +276,24 @@ extern "C" int fb200_conv2d_per_image_weights(const void* x, int x_dtype, int B,
                      stream);
 }
 
+extern "C" int fb200_linear_rowmax(const void* x, int64_t M, int K, int x_pitch, const void* w, const float* bias, int Cout, float* rowmax, void* stream) {
+  FB_CHECK_ARG(x && w && rowmax && M > 0 && M <= 0x7fffffffLL && K > 0 && Cout > 0, "linear_rowmax: bad arguments");
+  ConvParams p;
+  p.split3 = 0;
+  p.x = x; p.w = w; p.scale = nullptr; p.bias = bias; p.res = nullptr;
+  p.out = const_cast<void*>(x);  // never written: the tensor map of the (absent) output only needs a valid aligned address
+  p.B = 1; p.H = 1; p.W = (int)M; p.Cin = K; p.x_pitch = x_pitch; p.KH = 1; p.KW = 1; p.stride = 1; p.pad = 0; p.Ho = 1; p.Wo = (int)M;
+  p.Cout = Cout; p.res_pitch = 0; p.out_pitch = (Cout + 3) / 4 * 4; p.act = FB200_ACT_NONE;
+  p.M = M; p.K = K; p.x_dtype = FB200_F16; p.out_dtype = FB200_F32; p.vec_ok = 1;
+  p.out_bs = (int64_t)M * p.out_pitch;
+  p.rowmax = rowmax;
+  if (!conv2d_tc_supported(p, FB200_F16, FB200_F32)) {
+    set_error("linear_rowmax: shape not supported by the tcgen05 path (K=%d must be a multiple of 32, fp16 operands, 16-byte aligned)", K);
+    return FB200_ERR_UNSUPPORTED;
+  }
+  return conv2d_tc(p, (cudaStream_t)stream);
+}
+
 static int conv2d_impl(const void* x, int x_dtype, int B, int H, int W, int Cin, int x_pitch, const void* w, int64_t w_bs, int KH,
                        int KW, int stride, int pad, const float* scale, const float* bias, const void* residual,
                        int res_pitch, int act, void* out, int out_dtype, int out_pitch, int64_t out_batch_stride, int Cout,

@@ -51,6 +51,7 @@ struct KParams {
   int num_k_blocks;
   int n_tiles, total_tiles;        // N tiles per M tile; total = m_tiles * n_tiles
   int res_tma;                     // 1: the residual tile is TMA-loaded into the staging buffer (coalesced, one chunk ahead) instead of per-thread LDG
+  float* rowmax;                   // not null: row-max-only epilogue (query selection scores), nothing is stored
   int w_batched;                   // 1: weights differ per image (3-D weight map, third coordinate = image)
   int dbg;                         // tuning aid (env FB200_TC_DBG): 1 = skip TMA store, 2 = skip residual, 4 = skip TMEM load
 };
@@ -176,6 +177,12 @@ __device__ __forceinline__ void act32(float (&v)[32], int act) {
       break;
     default: break;
   }
+}
+
+// max of floats through integer atomics (buffer initialised to -inf): non-negative values order like ints, negative ones like reversed uints
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 
 template <int BLOCK_N, int BLOCK_K> constexpr int stage_bytes() { return (BLOCK_M + BLOCK_N) * BLOCK_K * 2; }
@@ -387,8 +394,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t tmem_acc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      float row_max = -INFINITY;
+      if (p.rowmax) {  // row-max-only epilogue: enc_outputs_class.max(-1) (modelling.py:1210) without materialising the [B*S, num_classes] logits
 #pragma unroll 1
-      for (int c0 = c_begin; c0 < c_end; c0 += CHUNK_COLS) {
+        for (int c0 = c_begin; c0 < c_end && n0 + c0 < p.Cout; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_acc + (uint32_t)c0, r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c0 + j < p.Cout) row_max = fmaxf(row_max, fmaf(__uint_as_float(r[j]), s_scale[c0 + j], s_bias[c0 + j]));
+        }
+        if (row_valid) atomic_max_float(p.rowmax + ((int64_t)img * p.Ho + ho) * p.Wo + wo, row_max);
+      }
+#pragma unroll 1
+      for (int c0 = c_begin; c0 < c_end && !p.rowmax; c0 += CHUNK_COLS) {
         if (n0 + c0 >= p.Cout) break;  // uniform across the group
         uint8_t* stg = my_staging + (chunk_ctr % NSTG) * STAGING_BYTES;
         uint8_t* srow = stg + row * 128;
@@ -627,6 +646,7 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
   int B = p.B, H = p.H, W = p.W, Ho = p.Ho, Wo = p.Wo;
   const bool flat = (p.KH == 1 && p.stride == 1 && p.out_bs == (int64_t)p.Ho * p.Wo * p.out_pitch) && p.w_bs == 0;
   kp.w_batched = p.w_bs != 0 ? 1 : 0;
+  kp.rowmax = p.rowmax;
   if (flat) {
     if (p.M > 0x7fffffffLL) { set_error("conv_tc: M too large"); return FB200_ERR_UNSUPPORTED; }
     W = Wo = (int)p.M; H = Ho = 1; B = 1;

@@ -540,9 +540,13 @@ class DetrEngine:
         t = ops.row_select(t, K["valid"], self.enc_output.bias)
         output_memory = ops.layernorm(t, *self.enc_output_ln)
         ncls = cfg.num_classes
-        cls_buf = torch.empty((B, S, (ncls + 7) // 8 * 8), dtype=torch.float32, device=dev)
-        self.enc_score(output_memory, out=cls_buf[..., :ncls], algo=A)
-        scores = ops.rowmax(cls_buf[..., :ncls])
+        if self.precision == "fp16" and A == ops.ALGO_AUTO and ops.supports_tcgen05_cached():
+            # only the per-anchor maximum is ever used in eval (modelling.py:1210-1214): the [B,S,365] fp32 logits (395 MB at bs=32) are never materialised
+            scores = ops.linear_rowmax(output_memory, self.enc_score.w, self.enc_score.bias)
+        else:
+            cls_buf = torch.empty((B, S, (ncls + 7) // 8 * 8), dtype=torch.float32, device=dev)
+            self.enc_score(output_memory, out=cls_buf[..., :ncls], algo=A)
+            scores = ops.rowmax(cls_buf[..., :ncls])
         _, topk_ind = ops.topk(scores, cfg.num_queries)
         tgt = ops.gather_rows(output_memory, topk_ind)
         bb = self.enc_bbox[2](self.enc_bbox[1](self.enc_bbox[0](tgt, act=ops.ACT_RELU, algo=A), act=ops.ACT_RELU, algo=A), out_dtype=torch.float32, algo=A)

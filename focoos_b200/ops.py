@@ -63,7 +63,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = (
-    "fb200_last_error", "fb200_version", "fb200_device_supports_tcgen05", "fb200_stem_conv3x3s2", "fb200_stem_conv3x3s2_u8", "fb200_conv2d", "fb200_conv2d_per_image_weights",
+    "fb200_last_error", "fb200_version", "fb200_device_supports_tcgen05", "fb200_stem_conv3x3s2", "fb200_stem_conv3x3s2_u8", "fb200_conv2d", "fb200_conv2d_per_image_weights", "fb200_linear_rowmax",
     "fb200_split_f32_pair",
     "fb200_maxpool3x3s2", "fb200_avgpool2x2_ceil", "fb200_resize_bilinear", "fb200_add", "fb200_layernorm",
     "fb200_attention", "fb200_attention_split", "fb200_msda", "fb200_row_select", "fb200_rowmax", "fb200_topk", "fb200_gather_rows",
@@ -165,6 +165,10 @@ class CudaBackend:
         self._call("fb200_conv2d_per_image_weights", _p(x), _dt(x), B, H, W, Cin, _pitch(x), _p(w), ctypes.c_int64(w.stride(0)), KH, KW, 1, (KH - 1) // 2, None, None, act,
                    _p(out), _dt(out), _pitch(out, True), Cout, algo, _stream())
 
+    def linear_rowmax(self, x2d, w, bias, out):
+        self._cuda(x2d, w, out)
+        self._call("fb200_linear_rowmax", _p(x2d), ctypes.c_int64(x2d.shape[0]), x2d.shape[1], x2d.stride(0), _p(w), _p(bias), w.shape[0], _p(out), _stream())
+
     def split_pair(self, x, out):
         self._cuda(x, out)
         C = x.shape[-1]
@@ -261,6 +265,19 @@ def supports_tcgen05() -> bool:
     return load_library().fb200_device_supports_tcgen05() == 1
 
 
+_tc_ok = None
+
+
+def supports_tcgen05_cached() -> bool:
+    """tcgen05 path usable (real sm_100 device; False under the tests' CPU backend hook)"""
+    global _tc_ok
+    if _backend is not None:
+        return False
+    if _tc_ok is None:
+        _tc_ok = supports_tcgen05()
+    return _tc_ok
+
+
 # ------------------------------------------------------------------------------------------------
 # public tensor-level API
 # ------------------------------------------------------------------------------------------------
@@ -308,6 +325,16 @@ def conv2d_per_image(x, w, *, act=ACT_NONE, out=None, out_dtype=None, algo=ALGO_
     assert tuple(out.shape) == (B, H, W, Cout)
     _be().conv2d_per_image(x, w.contiguous(), act, out, algo)
     return out
+
+
+def linear_rowmax(x, w, bias=None):
+    """max over the output features of x @ w.T + bias, per row, without materialising the product (fp16 x [..., K], w [N, K]) -> fp32 [...]."""
+    assert x.dtype == torch.float16 and w.dtype == torch.float16 and x.stride(-1) == 1
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, x.shape[-1])
+    out = torch.full((x2.shape[0],), float("-inf"), dtype=torch.float32, device=x.device)
+    _be().linear_rowmax(x2, w.reshape(w.shape[0], -1).contiguous(), bias, out)
+    return out.reshape(lead)
 
 
 def split_pair(x):

@@ -79,6 +79,11 @@ int fb200_conv2d_per_image_weights(const void* x, int x_dtype, int B, int H, int
                                    int KH, int KW, int stride, int pad, const float* scale, const float* bias, int act, void* out, int out_dtype,
                                    int out_pitch, int Cout, int algo, void* stream);
 
+/* rowmax[m] = max_n (x[m,:] . w[n,:] + bias[n]) for fp16 x [M,K] / w [Cout,K] on the tensor cores, WITHOUT writing the [M,Cout] product:
+ * the query-selection score enc_outputs_class.max(-1) of _get_decoder_input (models/fai_detr/modelling.py:1204-1214; 268 800 x 365 fp32 logits = 395 MB at
+ * bs=32 that are otherwise written and read back).  rowmax must be pre-filled with -inf (combined with integer atomics across N tiles). */
+int fb200_linear_rowmax(const void* x, int64_t M, int K, int x_pitch, const void* w, const float* bias, int Cout, float* rowmax, void* stream);
+
 /* x fp32 [rows, C] (row pitch x_pitch) -> out fp16 [rows, 2C]: out[:, :C] = hi = fp16(x), out[:, C:] = lo = fp16(x - hi).
  * Operand preparation of the split-precision conv/linear mode (precision="fp32_tc"). */
 int fb200_split_f32_pair(const float* x, int64_t rows, int C, int x_pitch, void* out, void* stream);

@@ -566,3 +566,13 @@ def _rb_mask_sigmoid_upsample_select(self, x, bq, out):
 
 RefBackend.mask_sigmoid_upsample_stats = _rb_mask_sigmoid_upsample_stats
 RefBackend.mask_sigmoid_upsample_select = _rb_mask_sigmoid_upsample_select
+
+
+def _rb_linear_rowmax(self, x2d, w, bias, out):
+    y = x2d.float() @ w.float().t()
+    if bias is not None:
+        y = y + bias
+    out.copy_(y.max(-1).values)
+
+
+RefBackend.linear_rowmax = _rb_linear_rowmax

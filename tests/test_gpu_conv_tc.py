@@ -150,3 +150,14 @@ def test_avgpool_folded_into_2x2_stride2_conv(B, H, W, Cin, Cout, dtype):
     out = ops.conv2d(x.to(DEV), wf.to(DEV), sc.to(DEV), bi.to(DEV), stride=2, pad=0, algo=ops.ALGO_TCGEN05)
     scale = max(1.0, float(ref.abs().max()))
     assert float((out.float().cpu() - ref).abs().max()) <= 3e-3 * scale
+
+
+@pytest.mark.parametrize("M,K,N", [(2 * 8400, 256, 365), (4800, 256, 80), (300, 512, 1000), (129, 64, 7)])
+def test_linear_rowmax_without_materialising_the_product(M, K, N):
+    """enc_outputs_class.max(-1): row maximum of x @ w.T + b computed in the tcgen05 epilogue (atomic max across column groups / N tiles)."""
+    x = rnd((M, K), torch.float16, 1)
+    w = rnd((N, K), torch.float16, 2, 1.0 / math.sqrt(K))
+    b = rnd((N,), torch.float32, 3, 2.0) - 3.0  # mostly negative rows: exercises the signed atomic max
+    ref = (x.float() @ w.float().t() + b).max(-1).values
+    got = ops.linear_rowmax(x.to(DEV), w.to(DEV), b.to(DEV)).cpu()
+    assert float((got - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max()))
