@@ -51,6 +51,7 @@ struct KParams {
   int num_k_blocks;
   int n_tiles, total_tiles;        // N tiles per M tile; total = m_tiles * n_tiles
   int res_tma;                     // 1: the residual tile is TMA-loaded into the staging buffer (coalesced, one chunk ahead) instead of per-thread LDG
+  int halo_boff;                   // halo mode: also set the descriptor base-offset field (A/B experiment knob FB200_TC_HALO=2)
   float* rowmax;                   // not null: row-max-only epilogue (query selection scores), nothing is stored
   int w_batched;                   // 1: weights differ per image (3-D weight map, third coordinate = image)
   int dbg;                         // tuning aid (env FB200_TC_DBG): 1 = skip TMA store, 2 = skip residual, 4 = skip TMEM load
@@ -185,9 +186,20 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
   else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 
-template <int BLOCK_N, int BLOCK_K> constexpr int stage_bytes() { return (BLOCK_M + BLOCK_N) * BLOCK_K * 2; }
+// BLOCK_K == 96 selects the HALO mode for 32-channel 3x3 stride-1 convs (the ResNet-vd stem): an M tile is 128 consecutive pixels of ONE image row, a
+// k-block is one filter ROW (kh): the (128 + 2) x 32-channel input strip is loaded ONCE and the three kw taps are three UMMA descriptors whose start
+// address is shifted by one 64-byte pixel row each - the tap boxes are no longer re-read from L2 three times (these layers run at the L2 bandwidth).
+template <int BLOCK_K> __host__ __device__ constexpr bool is_halo() { return BLOCK_K == 96; }
+template <int BLOCK_K> __host__ __device__ constexpr int phys_k() { return BLOCK_K == 96 ? 32 : BLOCK_K; }  // channels per shared-memory row
+template <int BLOCK_N, int BLOCK_K> __host__ __device__ constexpr int a_stage_bytes() { return BLOCK_K == 96 ? 9216 : BLOCK_M * BLOCK_K * 2; }  // 130 rows x 64 B, 1 KiB aligned
+template <int BLOCK_N, int BLOCK_K> __host__ __device__ constexpr int b_stage_bytes() { return BLOCK_K == 96 ? 0 : BLOCK_N * BLOCK_K * 2; }
+// halo mode keeps ALL NINE weight taps resident in shared memory for the life of the persistent CTA (9 x BLOCK_N x 64 B <= 36 KiB): per tile only the
+// three input strips travel from L2
+template <int BLOCK_N, int BLOCK_K> __host__ __device__ constexpr int b_resident_bytes() { return BLOCK_K == 96 ? 9 * BLOCK_N * 64 : 0; }
+template <int BLOCK_N, int BLOCK_K> constexpr int stage_bytes() { return a_stage_bytes<BLOCK_N, BLOCK_K>() + b_stage_bytes<BLOCK_N, BLOCK_K>(); }
 template <int BLOCK_N, int STAGES, int BLOCK_K, int NSTG> constexpr int smem_bytes() {
-  return STAGES * stage_bytes<BLOCK_N, BLOCK_K>() + NSTG * epi_groups<BLOCK_N>() * STAGING_BYTES + 2 * BLOCK_N * 4 + (2 * STAGES + 4 + NSTG * epi_groups<BLOCK_N>()) * 8 + 16 + 1024 /*align slack*/;
+  return STAGES * stage_bytes<BLOCK_N, BLOCK_K>() + b_resident_bytes<BLOCK_N, BLOCK_K>() + NSTG * epi_groups<BLOCK_N>() * STAGING_BYTES + 2 * BLOCK_N * 4 +
+         (2 * STAGES + 5 + NSTG * epi_groups<BLOCK_N>()) * 8 + 16 + 1024 /*align slack*/;
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
@@ -197,12 +209,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r, const KParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
-  constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+  constexpr bool HALO = is_halo<BLOCK_K>();
+  constexpr int BKP = phys_k<BLOCK_K>();
+  constexpr int A_STAGE_BYTES = a_stage_bytes<BLOCK_N, BLOCK_K>();
+  constexpr int B_STAGE_BYTES = b_stage_bytes<BLOCK_N, BLOCK_K>();
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
   constexpr int EPI_GROUPS = epi_groups<BLOCK_N>();
-  uint8_t* staging = smem_b + STAGES * B_STAGE_BYTES;  // EPI_GROUPS x NSTG x 16 KiB
+  uint8_t* smem_w = smem_b + STAGES * B_STAGE_BYTES;   // halo mode: the nine resident weight taps
+  uint8_t* staging = smem_w + b_resident_bytes<BLOCK_N, BLOCK_K>();  // EPI_GROUPS x NSTG x 16 KiB
   float* s_scale = reinterpret_cast<float*>(staging + EPI_GROUPS * NSTG * STAGING_BYTES);
   float* s_bias = s_scale + BLOCK_N;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_bias + BLOCK_N);
@@ -210,7 +225,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
   uint64_t* res_bar = tmem_empty_bar + 2;         // [EPI_GROUPS * NSTG] residual tile landed in staging buffer
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + EPI_GROUPS * NSTG);
+  uint64_t* w_bar = res_bar + EPI_GROUPS * NSTG;  // halo mode: resident weights landed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t TMEM_COLS = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);  // two accumulator stages
@@ -224,6 +240,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4 * EPI_GROUPS); }
     for (int i = 0; i < EPI_GROUPS * NSTG; ++i) mbar_init(&res_bar[i], 1);
+    mbar_init(w_bar, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -239,7 +256,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 0) {
     // ===================================================================== TMA producer
     if (lane == 0) {
-      const uint32_t tx_bytes = (uint32_t)(p.BW * p.BH * BLOCK_K * 2) + (uint32_t)B_STAGE_BYTES;
+      const uint32_t tx_bytes = HALO ? (uint32_t)((p.BW + 2) * 64) : (uint32_t)(p.BW * p.BH * BKP * 2) + (uint32_t)B_STAGE_BYTES;
+      if constexpr (HALO) {  // the nine weight taps, once
+        mbar_arrive_expect_tx(w_bar, (uint32_t)b_resident_bytes<BLOCK_N, BLOCK_K>());
+        for (int tap = 0; tap < 9; ++tap) tma_load_2d(&tmap_b, w_bar, smem_w + tap * (BLOCK_N * 64), tap * 32, 0);
+      }
       // channel coordinate of K-chunk cc.  Split-precision mode (fp32-accurate products from fp16 tensor cores): the stored tensor is
       // [hi(C) | lo(C)] and K runs over three segments  hi x W_hi,  hi x W_lo,  lo x W_hi  (weights packed [W_hi | W_lo | W_hi]).
       auto a_chan = [&](int cc) -> int {
@@ -253,6 +274,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int n0 = (t % p.n_tiles) * BLOCK_N, mt = t / p.n_tiles;
         const int img = mt / tiles_per_img, rem = mt - img * tiles_per_img;
         const int h0 = (rem / p.tiles_w) * p.BH, w0 = (rem % p.tiles_w) * p.BW;
+        if constexpr (HALO) {
+          for (int kh = 0; kh < 3; ++kh) {  // one k-block per filter row: the input strip once, the three kw weight slices
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+            tma_load_4d(&tmap_a, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, 0, w0 - 1, h0 + kh - 1, img);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          continue;
+        }
         {  // L2 prefetch for the tile this CTA will process next (one box per channel chunk; taps overlap)
           const int tn = t + (int)gridDim.x;
           if (tn < p.total_tiles && (tn / p.n_tiles) != mt) {
@@ -284,8 +314,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const int dw = tw >> 1, wp = tw & 1;
             tma_load_5d(&tmap_a, &full_bar[stage], dst_a, wp * p.x_pitch + a_c0, w0 + dw, hp, h0 + dh, img);
           }
-          if (p.w_batched) tma_load_3d(&tmap_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb * BLOCK_K, n0, img);
-          else tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb * BLOCK_K, n0);
+          if (p.w_batched) tma_load_3d(&tmap_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb * BKP, n0, img);
+          else tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb * BKP, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -296,6 +326,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       constexpr uint32_t idesc = make_idesc(BLOCK_N);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
+      if constexpr (HALO) mbar_wait(w_bar, 0);
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator stage
         tcgen05_fence_after();
@@ -303,12 +334,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
-          const uint64_t da = make_smem_desc<BLOCK_K>(smem_u32(smem_a + stage * A_STAGE_BYTES));
-          const uint64_t db = make_smem_desc<BLOCK_K>(smem_u32(smem_b + stage * B_STAGE_BYTES));
+          const uint64_t da = make_smem_desc<BKP>(smem_u32(smem_a + stage * A_STAGE_BYTES));
+          const uint64_t db = make_smem_desc<BKP>(smem_u32(smem_b + stage * B_STAGE_BYTES));
+          if constexpr (HALO) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            // advance 16 halves = 32 B inside the swizzle row: +2 in 16-byte units
-            umma_f16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int kw = 0; kw < 3; ++kw) {
+              // tap kw reads the strip shifted by kw pixels = kw * 64 B (+4 per pixel in 16-byte units); p.halo_boff: also patch the descriptor's
+              // base-offset field (bits 49-51) with the 128-byte phase of the shifted start
+              uint64_t dak = da + (uint64_t)(kw * 4);
+              if (p.halo_boff) dak |= (uint64_t)(((smem_u32(smem_a + stage * A_STAGE_BYTES) + kw * 64) >> 7) & 7) << 49;
+              const uint64_t dbk = make_smem_desc<BKP>(smem_u32(smem_w + (kb * 3 + kw) * (BLOCK_N * 64)));
+#pragma unroll
+              for (int k = 0; k < 2; ++k) umma_f16(tmem_d, dak + (uint64_t)(k * 2), dbk + (uint64_t)(k * 2), idesc, (kb > 0 || kw > 0 || k > 0) ? 1u : 0u);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / 16; ++k) {
+              // advance 16 halves = 32 B inside the swizzle row: +2 in 16-byte units
+              umma_f16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);  // smem stage may be refilled once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -651,8 +695,15 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
     if (p.M > 0x7fffffffLL) { set_error("conv_tc: M too large"); return FB200_ERR_UNSUPPORTED; }
     W = Wo = (int)p.M; H = Ho = 1; B = 1;
   }
+  // halo mode (see is_halo): 32-channel 3x3 stride-1 convs, fp16 in, no residual.  FB200_TC_HALO=0 disables, =2 also sets the descriptor base offset
+  static int halo_env = -1;
+  if (halo_env < 0) { const char* e = getenv("FB200_TC_HALO"); halo_env = e ? atoi(e) : 1; }
+  const bool halo = halo_env != 0 && BK == 32 && p.Cin == 32 && !p.split3 && p.KH == 3 && p.KW == 3 && p.stride == 1 && p.pad == 1 && !p.res && p.w_bs == 0 &&
+                    !p.rowmax && (p.act & 15) != FB200_ACT_GELU && Wo >= 64 && p.Cout <= 64;
+  kp.halo_boff = halo_env == 2 ? 1 : 0;
   int BW = 1, BH = 1;
-  choose_tile(Ho, Wo, &BW, &BH);
+  if (halo) { BW = 128; BH = 1; kp.num_k_blocks = 3; }
+  else choose_tile(Ho, Wo, &BW, &BH);
   kp.BW = BW; kp.BH = BH; kp.tiles_w = (Wo + BW - 1) / BW; kp.tiles_h = (Ho + BH - 1) / BH; kp.Ho = Ho; kp.Wo = Wo;
   const int64_t m_tiles = (int64_t)B * kp.tiles_w * kp.tiles_h;
 
@@ -662,7 +713,7 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
   if (!kp.stride2) {
     const uint64_t dims[4] = {(uint64_t)(p.split3 ? 2 * Clog : p.Cin), (uint64_t)W, (uint64_t)H, (uint64_t)B};
     const uint64_t str[4] = {1, P, P * W, P * W * H};
-    const uint32_t box[4] = {(uint32_t)BK, (uint32_t)BW, (uint32_t)BH, 1};
+    const uint32_t box[4] = {(uint32_t)BK, (uint32_t)(halo ? BW + 2 : BW), (uint32_t)BH, 1};
     rc = encode(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4, const_cast<void*>(p.x), dims, str, box, "A", swz);
   } else {
     const uint64_t dims[5] = {2 * P, (uint64_t)W / 2, 2, (uint64_t)H / 2, (uint64_t)B};
@@ -681,7 +732,7 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
     {
       const uint64_t dims[3] = {(uint64_t)p.K, (uint64_t)p.Cout, (uint64_t)p.B};
       const uint64_t str[3] = {1, (uint64_t)p.K, (uint64_t)p.w_bs};
-      const uint32_t box[3] = {(uint32_t)BK_, (uint32_t)BN_, 1};
+      const uint32_t box[3] = {(uint32_t)phys_k<BK_>(), (uint32_t)BN_, 1};
       int r2 = encode(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, p.w_bs ? 3 : 2, const_cast<void*>(p.w), dims, str, box, "W", swz);
       if (r2) return r2;
     }
@@ -723,6 +774,11 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
   typedef integral_constant<int, 2> I2;
   if ((p.act & 15) == FB200_ACT_GELU)  // exact-erf GELU: dedicated instantiation (fp16 out, Cin % 64 == 0; checked in conv2d_tc_supported)
     return run(integral_constant<int, 128>{}, integral_constant<int, 4>{}, I1{}, K64{}, I2{}, std::true_type{});
+  typedef integral_constant<int, 96> K96;  // halo mode tag
+  if (halo) {
+    if (p.Cout > 32) return run(integral_constant<int, 64>{}, integral_constant<int, 4>{}, I2{}, K96{}, I2{}, std::false_type{});
+    return run(integral_constant<int, 32>{}, integral_constant<int, 4>{}, I2{}, K96{}, I2{}, std::false_type{});
+  }
   if (BK == 32) {  // stem convs (Cin = 32): HBM-bound, two CTAs per SM
     if (p.Cout > 32) return run(integral_constant<int, 64>{}, integral_constant<int, 4>{}, I2{}, K32{}, I2{}, std::false_type{});
     return run(integral_constant<int, 32>{}, integral_constant<int, 4>{}, I2{}, K32{}, I2{}, std::false_type{});

@@ -161,3 +161,16 @@ def test_linear_rowmax_without_materialising_the_product(M, K, N):
     ref = (x.float() @ w.float().t() + b).max(-1).values
     got = ops.linear_rowmax(x.to(DEV), w.to(DEV), b.to(DEV)).cpu()
     assert float((got - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("B,H,W,Cout", [(2, 40, 200, 32), (1, 33, 320, 64), (2, 16, 64, 64), (3, 9, 131, 32)])
+def test_stem_halo_mode(B, H, W, Cout):
+    """32-channel 3x3 stride-1 convs (ResNet-vd conv1_2 / conv1_3): one (128+2)-pixel strip per filter row, the three kw taps as row-shifted UMMA descriptors."""
+    x = rnd((B, H, W, 32), torch.float16, 1)
+    w = rnd((Cout, 3, 3, 32), torch.float16, 2, 1.0 / math.sqrt(288))
+    sc, bi = torch.rand(Cout) + 0.5, rnd((Cout,), torch.float32, 3, 0.2)
+    ref = torch.empty((B, H, W, Cout), dtype=torch.float32)
+    REF.conv2d(x.float(), w.float(), sc, bi, 1, 1, 1, None, ref, 0)
+    out = ops.conv2d(x.to(DEV), w.to(DEV), sc.to(DEV), bi.to(DEV), stride=1, pad=1, act=1, algo=ops.ALGO_TCGEN05)
+    err = float((out.float().cpu() - ref).abs().max())
+    assert err <= 3e-3 * max(1.0, float(ref.abs().max())), err
