@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(256) mask_stats_kernel(const float* __restrict
   const float* p = masks + (int64_t)blockIdx.x * hw;
   int c = 0;
   float s = 0.f;
-  const int64_t n4 = hw / 4;
+  const int64_t n4 = (hw & 3) ? 0 : hw / 4;  // planes are only 16-byte aligned when hw % 4 == 0; otherwise the scalar loop below covers everything
   for (int64_t i = threadIdx.x; i < n4; i += 256) {
     const float4 v = reinterpret_cast<const float4*>(p)[i];
     if (v.x >= thr) { ++c; s += v.x; }
@@ -576,7 +576,6 @@ extern "C" int fb200_mask_sigmoid_upsample_select(const void* x, int dtype, int 
 
 extern "C" int fb200_mask_stats(const float* masks, int64_t planes, int64_t hw, float thr, int* count, float* psum, void* stream) {
   FB_CHECK_ARG(masks && count && psum && planes > 0 && hw > 0, "mask_stats: bad arguments");
-  FB_CHECK_ARG((hw % 4 == 0) || true, "mask_stats");
   mask_stats_kernel<<<(unsigned)planes, 256, 0, (cudaStream_t)stream>>>(masks, hw, thr, count, psum);
   FB_CHECK_LAUNCH("mask_stats");
   return FB200_OK;

@@ -269,7 +269,7 @@ class _Linear:
             self.w3 = _split3_weights(self.w)
 
     def __call__(self, x, act=ops.ACT_NONE, residual=None, out_dtype=None, out=None, algo=ops.ALGO_AUTO):
-        if _split3_ok(x, self.w3, act, algo) and (out_dtype in (None, torch.float32)) and (out is None or out.shape[-1] % 4 == 0 or True):
+        if _split3_ok(x, self.w3, act, algo) and (out_dtype in (None, torch.float32)):
             return ops.linear(ops.split_pair(x), self.w3, self.bias, act=act, residual=residual, out_dtype=torch.float32, out=out, algo=ops.ALGO_TCGEN05_SPLIT3)
         return ops.linear(x, self.w, self.bias, act=act, residual=residual, out_dtype=out_dtype, out=out, algo=algo)
 

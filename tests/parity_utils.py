@@ -69,5 +69,4 @@ def detections_match(det_a, det_b, score_tol=1e-4, box_tol=1):
         if la[i] != lb[i] or tuple(ba[i]) != tuple(bb[i]):
             j = [j for j in range(len(sb)) if lb[j] == la[i] and np.abs(np.array(bb[j]) - np.array(ba[i])).max() <= box_tol and abs(sb[j] - sa[i]) <= score_tol]
             assert j, f"detection {i} of A has no counterpart in B"
-            assert abs(sa[i] - sb[i]) <= score_tol * 2 + 1e-7 or True
     return True

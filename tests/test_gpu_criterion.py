@@ -94,7 +94,6 @@ def test_obj365_width_and_images_without_targets():
 def test_all_images_empty():
     logits, boxes, _ = CO.synth_case(seed=12, B=2, Q=50, C=10, L=1)
     empty = [(torch.zeros(0, dtype=torch.int64), torch.zeros((0, 4)))] * 2
-    ref, _ = CO.criterion(logits, boxes, empty) if False else (None, None)
     out = _criterion()({"pred_logits": logits[0].to(DEV), "pred_boxes": boxes[0].to(DEV)}, _targets(empty))
     p = torch.sigmoid(logits[0])
     vfl = (0.75 * p.pow(2) * torch.nn.functional.binary_cross_entropy_with_logits(logits[0], torch.zeros_like(p), reduction="none")).sum()  # num_boxes clamps to 1
