@@ -57,3 +57,12 @@ def test_bisenet_fused_graph_matches_golden(ref_backend):
         assert [x.cls_id for x in d.detections] == g["det_labels"][i, :n].tolist()
         assert np.abs(np.array([x.conf for x in d.detections]) - g["det_scores"][i, :n]).max() < 1e-4
         assert [x.bbox for x in d.detections] == g["det_boxes"][i, :n].tolist()
+    # the lazy path (what FocoosModel.__call__ uses): semantic argmax straight from the low-resolution logits - same detections
+    m.lazy_masks = True
+    lazy_out = m(x)
+    m.lazy_masks = False
+    assert hasattr(lazy_out.masks, "materialize") and tuple(lazy_out.masks.shape) == tuple(out.masks.shape)
+    dets2 = proc.postprocess(lazy_out, imgs, threshold=float(g["threshold"]))
+    for a_, b_ in zip(dets, dets2):
+        assert [(d.cls_id, d.bbox, d.mask, d.conf) for d in a_.detections] == [(d.cls_id, d.bbox, d.mask, d.conf) for d in b_.detections]
+    assert torch.equal(lazy_out.masks.materialize(), out.masks)

@@ -144,3 +144,40 @@ def test_two_rank_gradient_exchange_equals_full_batch_reference():
             assert torch.allclose(p, r, rtol=2e-6, atol=1e-7), float((p - r).abs().max())
     for a, b in zip(res[0], res[1]):
         assert torch.equal(a, b), "replicas must stay bit-identical"
+
+
+def test_bucket_layout_and_unused_parameter_tracking(ref_backend):
+    """GradBucketReducer: buckets tile the flat gradient buffer exactly once, in reverse parameter order, never splitting a tensor; hooks launch a bucket
+    when its last tensor is ready.  FlatAdamW: tensors the loss never reaches are skipped entirely (torch.optim semantics for p.grad is None); state round-trips."""
+    torch.manual_seed(0)
+    m = _Tiny()
+    dead = nn.Linear(3, 3)  # never used in forward
+    m.add_module("dead", dead)
+    opt = FlatAdamW(_groups(m), amp=False, chunk_elems=16)
+    opt.track_unused_parameters()
+    red = GradBucketReducer(opt, bucket_bytes=200)
+    spans = sorted((s, e) for s, e, _, _ in red.buckets)
+    assert spans[0][0] == 0 and spans[-1][1] == opt.total and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    assert [b[3] for b in red.buckets] == sorted([b[3] for b in red.buckets], reverse=True), "reverse parameter order"
+    for s, e, lo, hi in red.buckets:
+        assert s == opt.offsets[lo] and e == (opt.offsets[hi + 1] if hi + 1 < len(opt.offsets) else opt.total)
+    launched = []
+    red._launch = lambda b, _orig=red._launch: (launched.append(b), _orig(b))[1]
+    red.attach_hooks()
+    before = opt.flat_params.clone()
+    x, y = torch.randn(4, 7), torch.randn(4, 3)
+    opt.zero_grad()
+    ((m(x) - y) ** 2).mean().backward()
+    full = {b for b, (_, _, lo, hi) in enumerate(red.buckets) if not any(opt.names[i].startswith("dead") for i in range(lo, hi + 1))}
+    assert full and full.issubset(set(launched)), "every bucket whose tensors ALL received gradients is launched from the hooks, before finish()"
+    assert not (set(range(len(red.buckets))) - full) & set(launched), "a bucket holding an unused tensor waits for finish()"
+    red.finish()
+    opt.step()
+    for i, n in enumerate(opt.names):
+        o, cnt = opt.offsets[i], opt.params[i].numel()
+        moved = not torch.equal(before[o:o + cnt], opt.flat_params[o:o + cnt])
+        assert moved == (not n.startswith("dead")), n
+    sd = opt.state_dict()
+    opt2 = FlatAdamW(_groups(m), amp=False, chunk_elems=16)
+    opt2.load_state_dict(sd)
+    assert torch.equal(opt2.exp_avg, opt.exp_avg) and opt2.stats()["step"] == 1
