@@ -69,7 +69,7 @@ class FocoosModel:
         # CUDA-graph cache of model.forward per (input shape, dtype): the eager forward is ~240 launches of partly very short kernels (the
         # decoder runs ahead of a Python host), so replaying a captured graph removes the host from the critical path of `infer` / `__call__`
         self.cuda_graphs = os.environ.get("FB200_NO_GRAPH", "0") != "1"
-        self._graphs = {}  # key -> (graph, static_input, static_output)
+        self._graphs = {}  # key -> (graph, static_input, static_output, the engine whose packed weights the graph reads)
         self._graph_seen = {}
 
     def _forward(self, images):
@@ -78,6 +78,12 @@ class FocoosModel:
             return self.model(images)
         key = (tuple(images.shape), images.dtype, getattr(self.model, "precision", None), bool(getattr(self.model, "lazy_masks", False)))
         ent = self._graphs.get(key)
+        if ent is not None and ent[3] is not getattr(self.model, "_engine", None):
+            # the model re-packed its weights (load_state_dict / train() -> eval() / .to()): the captured graph points at the OLD packed tensors
+            # (kept alive by the entry, so the replay would be valid but stale) - drop it and capture again
+            del self._graphs[key]
+            ent = None
+            self._graph_seen[key] = 1
         if ent is None:
             self._graph_seen[key] = self._graph_seen.get(key, 0) + 1
             if self._graph_seen[key] < 2:  # capture only shapes that come back (a one-off image size is not worth 2+ GB of pooled activations)
@@ -96,8 +102,8 @@ class FocoosModel:
             torch.cuda.synchronize()
             with torch.cuda.graph(g):
                 static_out = self.model(static_in)
-            ent = self._graphs[key] = (g, static_in, static_out)
-        g, static_in, static_out = ent
+            ent = self._graphs[key] = (g, static_in, static_out, getattr(self.model, "_engine", None))
+        g, static_in, static_out, _ = ent
         static_in.copy_(images, non_blocking=True)
         g.replay()
         return static_out
