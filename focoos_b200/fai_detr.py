@@ -231,6 +231,12 @@ def _split3_weights(w):
     return torch.cat([hi, lo, hi], dim=-1).contiguous()
 
 
+# number of fp16 tensor-core products per conv/linear in precision="fp32_tc" (DetrEngine.mix sets it per stage; tools/error_budget.py measures what each
+# choice costs in parity):  3 = x_hi*W_hi + x_hi*W_lo + x_lo*W_hi (fp32-accurate),  2 = x_hi*W_hi + x_lo*W_hi (weights rounded to fp16),
+# 1 = x_hi*W_hi only (fp16 operands, fp32 storage: the "fp32 residual stream" variant)
+_products = 3
+
+
 def _split3_ok(x, w3, act, algo):
     a = (act & 15)
     return (w3 is not None and algo != ops.ALGO_SIMT and x.dtype == torch.float32 and (x.is_cuda or ops._backend is not None) and a not in (ops.ACT_GELU, 4)
@@ -253,6 +259,8 @@ class _Conv:
     def __call__(self, x, residual=None, out=None, out_dtype=None, act=None, algo=ops.ALGO_AUTO):
         act = self.act if act is None else act
         if _split3_ok(x, self.w3, act, algo) and (out_dtype in (None, torch.float32)):
+            if _products != 3:
+                return _reduced_products(self, x, ops.conv2d, dict(stride=self.stride, pad=self.pad), self.scale, act, residual, out)
             return ops.conv2d(ops.split_pair(x), self.w3, self.scale, self.bias, stride=self.stride, pad=self.pad, act=act, residual=residual, out=out,
                               out_dtype=torch.float32, algo=ops.ALGO_TCGEN05_SPLIT3)
         return ops.conv2d(x, self.w, self.scale, self.bias, stride=self.stride, pad=self.pad, act=act, residual=residual, out=out, out_dtype=out_dtype, algo=algo)
@@ -270,8 +278,32 @@ class _Linear:
 
     def __call__(self, x, act=ops.ACT_NONE, residual=None, out_dtype=None, out=None, algo=ops.ALGO_AUTO):
         if _split3_ok(x, self.w3, act, algo) and (out_dtype in (None, torch.float32)):
+            if _products != 3:
+                return _reduced_products(self, x, ops.linear, {}, None, act, residual, out)
             return ops.linear(ops.split_pair(x), self.w3, self.bias, act=act, residual=residual, out_dtype=torch.float32, out=out, algo=ops.ALGO_TCGEN05_SPLIT3)
         return ops.linear(x, self.w, self.bias, act=act, residual=residual, out_dtype=out_dtype, out=out, algo=algo)
+
+
+_reduced_cache = {}
+
+
+def _reduced_products(layer, x, fn, kw, scale, act, residual, out):
+    """fp32_tc layer with fewer than three products (see `_products`); weights derived lazily from the split triple."""
+    C = layer.w3.shape[-1] // 3
+    key = (id(layer), _products)
+    w = _reduced_cache.get(key)
+    if w is None:
+        if _products == 2:
+            w = layer.w3.clone()
+            w[..., C:2 * C] = 0
+        else:
+            w = layer.w3[..., :C].contiguous()
+        _reduced_cache[key] = w
+    xp = ops.split_pair(x)
+    pos = (scale, layer.bias) if fn is ops.conv2d else (layer.bias,)
+    if _products == 2:
+        return fn(xp, w, *pos, act=act, residual=residual, out=out, out_dtype=torch.float32, algo=ops.ALGO_TCGEN05_SPLIT3, **kw)
+    return fn(xp[..., :C], w, *pos, act=act, residual=residual, out=out, out_dtype=torch.float32, algo=ops.ALGO_TCGEN05, **kw)
 
 
 def _enable_split3(obj, seen=None):
@@ -308,6 +340,7 @@ class DetrEngine:
         self.nhead = cfg.transformer_predictor_nhead
         self.d = cfg.transformer_predictor_hidden_dim
         self._consts: Dict[Tuple[int, int], dict] = {}
+        self.mix = {"backbone": 3, "encoder": 3, "select": 3, "decoder": 3}  # fp32_tc only: tensor-core products per stage (see `_products`)
         sd = {k: v.detach() for k, v in sd.items()}
         self._pack(sd)
         if precision == "fp32_tc":  # fp32 storage everywhere; convs/linears = three fp16 tensor-core products (fp32-accurate)
@@ -492,7 +525,10 @@ class DetrEngine:
             assert images.dim() == 4 and images.shape[1] == 3 and images.dtype == torch.float32
             B, _, H, W = images.shape
         assert H % 32 == 0 and W % 32 == 0, "input size must be a multiple of 32"
+        global _products
+        _products = self.mix["backbone"]
         feats = self._run_backbone(images)
+        _products = self.mix["encoder"]
         res3, res4, res5 = feats[1], feats[2], feats[3]
         h32, w32 = res5.shape[1], res5.shape[2]
         K = self._constants(h32, w32)
@@ -529,6 +565,7 @@ class DetrEngine:
         shapes = K["shapes"]
         S = sum(h * w for h, w in shapes)
         d = self.d
+        _products = self.mix["select"]
         memory = torch.empty((B, S, d), dtype=dt, device=dev)
         start = 0
         for i, (f, (h, w)) in enumerate(zip(enc_outs, shapes)):
@@ -555,6 +592,7 @@ class DetrEngine:
         if taps is not None:
             taps.update(memory=memory, enc_scores=scores, topk_ind=topk_ind, target=tgt, ref_unact=ref_unact)
         # decoder (modelling.py:969-1020, eval: logits only from the last layer)
+        _products = self.mix["decoder"]
         for i, blk in enumerate(self.dec):
             pos = self.qpos[1](self.qpos[0](ref, act=ops.ACT_RELU, out_dtype=dt, algo=ops.ALGO_SIMT), algo=A)
             tgt = self._mha(blk, tgt, pos)
@@ -570,6 +608,7 @@ class DetrEngine:
         logits = self.dec_score(tgt, out_dtype=torch.float32, algo=ops.ALGO_SIMT)  # [B,Q,C] contiguous
         if taps is not None:
             taps.update(pred_logits=logits, pred_boxes_cxcywh=ref)
+        _products = 3
         return ops.box_sigmoid(logits), ops.box_cxcywh_to_xyxy(ref)
 
 
