@@ -218,6 +218,12 @@ using namespace fb200;
 
 extern "C" const char* fb200_last_error(void) { return fb200::g_err; }
 extern "C" int fb200_version(void) { return 100; }
+namespace fb200 { int conv_tc_set_pair_mode(int v); }  // conv_tc.cu
+extern "C" int fb200_set_option(int option, int value) {
+  if (option == FB200_OPT_CONV_CTA_PAIR && value >= 0 && value <= 2) return conv_tc_set_pair_mode(value);
+  set_error("set_option: unknown option %d / value %d", option, value);
+  return FB200_ERR_INVALID;
+}
 extern "C" int fb200_device_supports_tcgen05(void) {
   int dev = 0, major = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return FB200_ERR_CUDA;

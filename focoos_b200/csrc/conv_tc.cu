@@ -55,6 +55,7 @@ struct KParams {
   float* rowmax;                   // not null: row-max-only epilogue (query selection scores), nothing is stored
   int w_batched;                   // 1: weights differ per image (3-D weight map, third coordinate = image)
   int dbg;                         // tuning aid (env FB200_TC_DBG): 1 = skip TMA store, 2 = skip residual, 4 = skip TMEM load
+  int nimg;                        // images in the (possibly flattened) view: M tiles beyond it are phantoms of an odd CTA-pair count
 };
 
 // ---------------------------------------------------------------------------------------------- PTX
@@ -121,6 +122,39 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// ---- CTA-pair (cta_group::2) variants: the two CTAs of a cluster compute ONE 256 x BLOCK_N tile; each loads its own 128 A rows and HALF of the B tile,
+// the leader (cluster rank 0) issues the MMAs for both, commits are multicast to both CTAs' barriers
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_rank0(uint32_t addr) {  // the same shared-memory offset in the leader CTA (shared::cluster window)
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(0));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads of a CTA pair: data lands in the EXECUTING CTA's shared memory, the transaction bytes are counted on the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint32_t bar_cluster, void* dst, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(const CUtensorMap* map, uint32_t bar_cluster, void* dst, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(const CUtensorMap* map, uint32_t bar_cluster, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_2sm(const CUtensorMap* map, uint32_t bar_cluster, void* dst, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+
 // K-major swizzled shared-memory matrix descriptor (sm_100 format: version 1 at bit 46, layout type at bits 61-63)
 template <int BLOCK_K>
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
@@ -133,8 +167,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   return d;
 }
 // instruction descriptor: D=F32, A=B=F16, both K-major, M=128, N=BLOCK_N
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-  return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int n, int m = 128) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -145,6 +179,16 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {  // arrives on the barrier at this offset in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -192,18 +236,18 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
 template <int BLOCK_K> __host__ __device__ constexpr bool is_halo() { return BLOCK_K == 96; }
 template <int BLOCK_K> __host__ __device__ constexpr int phys_k() { return BLOCK_K == 96 ? 32 : BLOCK_K; }  // channels per shared-memory row
 template <int BLOCK_N, int BLOCK_K> __host__ __device__ constexpr int a_stage_bytes() { return BLOCK_K == 96 ? 9216 : BLOCK_M * BLOCK_K * 2; }  // 130 rows x 64 B, 1 KiB aligned
-template <int BLOCK_N, int BLOCK_K> __host__ __device__ constexpr int b_stage_bytes() { return BLOCK_K == 96 ? 0 : BLOCK_N * BLOCK_K * 2; }
+template <int BLOCK_N, int BLOCK_K, bool CTA2 = false> __host__ __device__ constexpr int b_stage_bytes() { return BLOCK_K == 96 ? 0 : (CTA2 ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2; }
 // halo mode keeps ALL NINE weight taps resident in shared memory for the life of the persistent CTA (9 x BLOCK_N x 64 B <= 36 KiB): per tile only the
 // three input strips travel from L2
 template <int BLOCK_N, int BLOCK_K> __host__ __device__ constexpr int b_resident_bytes() { return BLOCK_K == 96 ? 9 * BLOCK_N * 64 : 0; }
-template <int BLOCK_N, int BLOCK_K> constexpr int stage_bytes() { return a_stage_bytes<BLOCK_N, BLOCK_K>() + b_stage_bytes<BLOCK_N, BLOCK_K>(); }
-template <int BLOCK_N, int STAGES, int BLOCK_K, int NSTG> constexpr int smem_bytes() {
-  return STAGES * stage_bytes<BLOCK_N, BLOCK_K>() + b_resident_bytes<BLOCK_N, BLOCK_K>() + NSTG * epi_groups<BLOCK_N>() * STAGING_BYTES + 2 * BLOCK_N * 4 +
+template <int BLOCK_N, int BLOCK_K, bool CTA2 = false> constexpr int stage_bytes() { return a_stage_bytes<BLOCK_N, BLOCK_K>() + b_stage_bytes<BLOCK_N, BLOCK_K, CTA2>(); }
+template <int BLOCK_N, int STAGES, int BLOCK_K, int NSTG, bool CTA2 = false> constexpr int smem_bytes() {
+  return STAGES * stage_bytes<BLOCK_N, BLOCK_K, CTA2>() + b_resident_bytes<BLOCK_N, BLOCK_K>() + NSTG * epi_groups<BLOCK_N>() * STAGING_BYTES + 2 * BLOCK_N * 4 +
          (2 * STAGES + 5 + NSTG * epi_groups<BLOCK_N>()) * 8 + 16 + 1024 /*align slack*/;
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
-template <int BLOCK_N, int STAGES, typename TOut, int MIN_BLOCKS, int BLOCK_K, int NSTG, bool GELU>
+template <int BLOCK_N, int STAGES, typename TOut, int MIN_BLOCKS, int BLOCK_K, int NSTG, bool GELU, bool CTA2>
 __global__ void __launch_bounds__(num_threads<BLOCK_N>(), MIN_BLOCKS)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r, const KParams p) {
@@ -212,7 +256,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   constexpr bool HALO = is_halo<BLOCK_K>();
   constexpr int BKP = phys_k<BLOCK_K>();
   constexpr int A_STAGE_BYTES = a_stage_bytes<BLOCK_N, BLOCK_K>();
-  constexpr int B_STAGE_BYTES = b_stage_bytes<BLOCK_N, BLOCK_K>();
+  constexpr int B_STAGE_BYTES = b_stage_bytes<BLOCK_N, BLOCK_K, CTA2>();
+  static_assert(!(CTA2 && HALO), "the halo mode is single-CTA");
+  uint32_t cta_rank = 0;  // CTA pair: 0 = leader (issues the MMAs), 1 = peer
+  if constexpr (CTA2) cta_rank = cluster_ctarank();
+  // persistent tile walk: a CTA pair shares one tile index (two adjacent M tiles x one N tile)
+  const int t_first = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int t_stride = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
   constexpr int EPI_GROUPS = epi_groups<BLOCK_N>();
@@ -238,20 +288,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4 * EPI_GROUPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], (CTA2 ? 8 : 4) * EPI_GROUPS); }  // pair: both CTAs' epilogue warps release the leader's accumulator stage
     for (int i = 0; i < EPI_GROUPS * NSTG; ++i) mbar_init(&res_bar[i], 1);
     mbar_init(w_bar, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CTA2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();  // the peer's barriers are initialised before any remote arrive / complete_tx can reach them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const int tiles_per_img = p.tiles_w * p.tiles_h;
+  struct TileXY { int n0, mt, img, h0, w0; };
+  auto tile_of = [&](int t) {
+    TileXY r;
+    r.n0 = (t % p.n_tiles) * BLOCK_N;
+    r.mt = t / p.n_tiles;
+    if constexpr (CTA2) r.mt = r.mt * 2 + (int)cta_rank;
+    r.img = r.mt / tiles_per_img;
+    const int rem = r.mt - r.img * tiles_per_img;
+    r.h0 = (rem / p.tiles_w) * p.BH;
+    r.w0 = (rem % p.tiles_w) * p.BW;
+    return r;
+  };
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -270,10 +338,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       };
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const int n0 = (t % p.n_tiles) * BLOCK_N, mt = t / p.n_tiles;
-        const int img = mt / tiles_per_img, rem = mt - img * tiles_per_img;
-        const int h0 = (rem / p.tiles_w) * p.BH, w0 = (rem % p.tiles_w) * p.BW;
+      for (int t = t_first; t < p.total_tiles; t += t_stride) {
+        const TileXY tc = tile_of(t);
+        const int n0 = tc.n0, mt = tc.mt, img = tc.img, h0 = tc.h0, w0 = tc.w0;
         if constexpr (HALO) {
           for (int kh = 0; kh < 3; ++kh) {  // one k-block per filter row: the input strip once, the three kw weight slices
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -284,10 +351,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           continue;
         }
         {  // L2 prefetch for the tile this CTA will process next (one box per channel chunk; taps overlap)
-          const int tn = t + (int)gridDim.x;
-          if (tn < p.total_tiles && (tn / p.n_tiles) != mt) {
-            const int mtn = tn / p.n_tiles, imgn = mtn / tiles_per_img, remn = mtn - imgn * tiles_per_img;
-            const int h0n = (remn / p.tiles_w) * p.BH, w0n = (remn % p.tiles_w) * p.BW;
+          const int tn = t + t_stride;
+          if (tn < p.total_tiles && (tn / p.n_tiles) != (t / p.n_tiles)) {
+            const TileXY tnx = tile_of(tn);
+            const int imgn = tnx.img, h0n = tnx.h0, w0n = tnx.w0;
             for (int cc = 0; cc < p.cchunks; ++cc) {
               const int a_c0 = a_chan(cc);
               if (!p.stride2) tma_prefetch_4d(&tmap_a, a_c0, w0n, h0n, imgn);
@@ -300,11 +367,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
           const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
           const int a_c0 = a_chan(cc);
           const int kh = tap / p.KW, kw = tap - kh * p.KW;
           void* dst_a = smem_a + stage * A_STAGE_BYTES;
+          if constexpr (CTA2) {  // both CTAs load their A rows and their half of B; all bytes are counted on the leader's barrier
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * tx_bytes);
+            const uint32_t lbar = mapa_rank0(smem_u32(&full_bar[stage]));
+            if (!p.stride2) {
+              tma_load_4d_2sm(&tmap_a, lbar, dst_a, a_c0, w0 + kw - p.pad, h0 + kh - p.pad, img);
+            } else {
+              const int th = kh - p.pad, tw = kw - p.pad;
+              tma_load_5d_2sm(&tmap_a, lbar, dst_a, (tw & 1) * p.x_pitch + a_c0, w0 + (tw >> 1), th & 1, h0 + (th >> 1), img);
+            }
+            const int nb = n0 + (int)cta_rank * (BLOCK_N / 2);
+            if (p.w_batched) tma_load_3d_2sm(&tmap_b, lbar, smem_b + stage * B_STAGE_BYTES, kb * BKP, nb, img);
+            else tma_load_2d_2sm(&tmap_b, lbar, smem_b + stage * B_STAGE_BYTES, kb * BKP, nb);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
           if (!p.stride2) {
             tma_load_4d(&tmap_a, &full_bar[stage], dst_a, a_c0, w0 + kw - p.pad, h0 + kh - p.pad, img);
           } else {
@@ -321,13 +403,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BLOCK_N);
+    // ===================================================================== MMA issuer (CTA pair: the leader only)
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc(BLOCK_N, CTA2 ? 256 : 128);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       if constexpr (HALO) mbar_wait(w_bar, 0);
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int t = t_first; t < p.total_tiles; t += t_stride) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator stage
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
@@ -351,13 +433,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
             for (int k = 0; k < BLOCK_K / 16; ++k) {
               // advance 16 halves = 32 B inside the swizzle row: +2 in 16-byte units
-              umma_f16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              if constexpr (CTA2) umma_f16_2sm(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              else umma_f16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
             }
           }
-          umma_commit(&empty_bar[stage]);  // smem stage may be refilled once these MMAs have read it
+          if constexpr (CTA2) umma_commit_2sm(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);  // smem stage may be refilled once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full_bar[acc]);
+        if constexpr (CTA2) umma_commit_2sm(&tmem_full_bar[acc]);
+        else umma_commit(&tmem_full_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -384,11 +469,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint4 rcur[RES_VECS];
     auto res_fetch = [&](int tt, int cc0, uint4 (&dst)[RES_VECS]) -> bool {
       if (!has_res || tt >= p.total_tiles) return false;
-      const int n0_ = (tt % p.n_tiles) * BLOCK_N, mt_ = tt / p.n_tiles;
+      const TileXY tx = tile_of(tt);
+      const int n0_ = tx.n0, img_ = tx.img;
       if (n0_ + cc0 + CHUNK_COLS > p.Cout || cc0 + CHUNK_COLS > c_end) return false;
-      const int img_ = mt_ / tiles_per_img, rem_ = mt_ - img_ * tiles_per_img;
-      const int ho_ = (rem_ / p.tiles_w) * p.BH + bh, wo_ = (rem_ % p.tiles_w) * p.BW + bw;
-      if (!(row < p.BW * p.BH && ho_ < p.Ho && wo_ < p.Wo)) return false;
+      const int ho_ = tx.h0 + bh, wo_ = tx.w0 + bw;
+      if (!(row < p.BW * p.BH && ho_ < p.Ho && wo_ < p.Wo && img_ < p.nimg)) return false;
       const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const TOut*>(p.res) + (((int64_t)img_ * p.Ho + ho_) * p.Wo + wo_) * p.res_pitch + n0_ + cc0);
 #pragma unroll
       for (int q = 0; q < RES_VECS; ++q) dst[q] = __ldg(src + q);
@@ -403,26 +488,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const uint32_t res_box_bytes = (uint32_t)(p.BW * p.BH * 128);
     auto chunk_valid = [&](int tt, int cc0) { return tt < p.total_tiles && cc0 < c_end && (tt % p.n_tiles) * BLOCK_N + cc0 < p.Cout; };
     auto issue_res = [&](int tt, int cc0, uint32_t k) {  // elected thread only
-      const int n0_ = (tt % p.n_tiles) * BLOCK_N, mt_ = tt / p.n_tiles;
-      const int img_ = mt_ / tiles_per_img, rem_ = mt_ - img_ * tiles_per_img;
-      const int h0_ = (rem_ / p.tiles_w) * p.BH, w0_ = (rem_ % p.tiles_w) * p.BW;
+      const TileXY tx = tile_of(tt);
+      const int n0_ = tx.n0, img_ = tx.img, h0_ = tx.h0, w0_ = tx.w0;
       uint64_t* bar = &my_res_bar[k % NSTG];
       mbar_arrive_expect_tx(bar, res_box_bytes);
       tma_load_4d(&tmap_r, bar, my_staging + (k % NSTG) * STAGING_BYTES, n0_ + cc0, w0_, h0_, img_);
     };
-    if (res_tma && et == 0 && chunk_valid((int)blockIdx.x, c_begin)) issue_res((int)blockIdx.x, c_begin, 0);
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      const int n0 = (t % p.n_tiles) * BLOCK_N, mt = t / p.n_tiles;
-      const int img = mt / tiles_per_img, rem = mt - img * tiles_per_img;
-      const int h0 = (rem / p.tiles_w) * p.BH, w0 = (rem % p.tiles_w) * p.BW;
+    if (res_tma && et == 0 && chunk_valid(t_first, c_begin)) issue_res(t_first, c_begin, 0);
+    for (int t = t_first; t < p.total_tiles; t += t_stride) {
+      const TileXY tc = tile_of(t);
+      const int n0 = tc.n0, img = tc.img, h0 = tc.h0, w0 = tc.w0;
       const int ho = h0 + bh, wo = w0 + bw;
-      const bool row_valid = (row < p.BW * p.BH) && ho < p.Ho && wo < p.Wo;
+      const bool row_valid = (row < p.BW * p.BH) && ho < p.Ho && wo < p.Wo && img < p.nimg;
       const TOut* res_row = has_res ? reinterpret_cast<const TOut*>(p.res) + (((int64_t)img * p.Ho + ho) * p.Wo + wo) * p.res_pitch : nullptr;
       if (has_res && !res_tma && et == 0) {  // L2 prefetch of the NEXT tile's residual columns owned by this group
-        const int tn = t + (int)gridDim.x;
+        const int tn = t + t_stride;
         if (tn < p.total_tiles) {
-          const int n0n = (tn % p.n_tiles) * BLOCK_N, mtn = tn / p.n_tiles, imgn = mtn / tiles_per_img, remn = mtn - imgn * tiles_per_img;
-          const int h0n = (remn / p.tiles_w) * p.BH, w0n = (remn % p.tiles_w) * p.BW;
+          const TileXY tnx = tile_of(tn);
+          const int n0n = tnx.n0, imgn = tnx.img, h0n = tnx.h0, w0n = tnx.w0;
           for (int c = c_begin; c < c_end; c += 128 / (int)sizeof(TOut))
             if (n0n + c < p.Cout) tma_prefetch_4d(&tmap_r, n0n + c, w0n, h0n, imgn);
         }
@@ -459,7 +542,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (res_tma) {
           if (et == 0) {  // prefetch the NEXT chunk's residual into the buffer it will use: that buffer's last store must have finished reading it
             int tn = t, cn = c0 + CHUNK_COLS;
-            if (!chunk_valid(tn, cn)) { tn = t + (int)gridDim.x; cn = c_begin; }
+            if (!chunk_valid(tn, cn)) { tn = t + t_stride; cn = c_begin; }
             if (chunk_valid(tn, cn)) {
               tma_store_wait_read<(NSTG >= 2 ? NSTG - 2 : 0)>();
               issue_res(tn, cn, chunk_ctr + 1);
@@ -559,16 +642,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // all tcgen05.ld of this accumulator stage have completed (wait::ld): hand it back to the MMA warp
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (lane == 0) {
+        if constexpr (CTA2) mbar_arrive_cluster(mapa_rank0(smem_u32(&tmem_empty_bar[acc])));
+        else mbar_arrive(&tmem_empty_bar[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (et == 0) tma_store_wait_all();
   }
   tcgen05_fence_before();
   __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();  // neither CTA may retire (or free TMEM) while its partner can still touch its barriers / shared memory
   if (warp == 2) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    if constexpr (CTA2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
 }
 
@@ -630,10 +718,10 @@ static int num_sms() {
   return n;
 }
 
-template <int BLOCK_N, int STAGES, typename TOut, int MIN_BLOCKS, int BLOCK_K, int NSTG, bool GELU>
+template <int BLOCK_N, int STAGES, typename TOut, int MIN_BLOCKS, int BLOCK_K, int NSTG, bool GELU, bool CTA2 = false>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr, const KParams& kp, cudaStream_t st) {
-  auto kern = conv_tc_kernel<BLOCK_N, STAGES, TOut, MIN_BLOCKS, BLOCK_K, NSTG, GELU>;
-  constexpr int smem = smem_bytes<BLOCK_N, STAGES, BLOCK_K, NSTG>();
+  auto kern = conv_tc_kernel<BLOCK_N, STAGES, TOut, MIN_BLOCKS, BLOCK_K, NSTG, GELU, CTA2>;
+  constexpr int smem = smem_bytes<BLOCK_N, STAGES, BLOCK_K, NSTG, CTA2>();
   constexpr int NUM_THREADS = num_threads<BLOCK_N>();
   static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
   static_assert(MIN_BLOCKS * 2 * BLOCK_N <= 512, "TMEM budget exceeded (a blocked tcgen05.alloc would deadlock)");
@@ -643,6 +731,24 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
     if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute(%d B) failed: %s", smem, cudaGetErrorString(e)); return FB200_ERR_CUDA; }
     configured = true;
   }
+  if constexpr (CTA2) {  // one cluster of two CTAs per tile (SM pair of a TPC), persistent over the pair tiles
+    static_assert(MIN_BLOCKS == 1, "CTA pairs own the whole TMEM of both SMs");
+    const int64_t pairs = num_sms() / 2;
+    const unsigned grid = 2u * (unsigned)(kp.total_tiles < pairs ? kp.total_tiles : pairs);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, td, tr, kp);
+    if (e != cudaSuccess) { set_error("conv_tc(cta pair): launch failed: %s", cudaGetErrorString(e)); return FB200_ERR_CUDA; }
+    return FB200_OK;
+  }
   const int64_t cap = (int64_t)num_sms() * MIN_BLOCKS;
   const unsigned grid = (unsigned)(kp.total_tiles < cap ? kp.total_tiles : cap);
   kern<<<grid, NUM_THREADS, smem, st>>>(ta, tb, td, tr, kp);
@@ -651,6 +757,14 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
 }
 
 }  // namespace tc
+
+static int g_cta_pair_mode = -1;  // FB200_OPT_CONV_CTA_PAIR
+
+int conv_tc_set_pair_mode(int v) {
+  const int old = g_cta_pair_mode < 0 ? 1 : g_cta_pair_mode;
+  g_cta_pair_mode = v;
+  return old;
+}
 
 bool conv2d_tc_supported(const ConvParams& p, int x_dtype, int out_dtype) {
   if (x_dtype != FB200_F16) return false;
@@ -723,7 +837,8 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
   }
   if (rc) return rc;
 
-  auto run = [&](auto blockn_tag, auto stages_tag, auto minb_tag, auto bk_tag, auto nstg_tag, auto gelu_tag) -> int {
+  auto run = [&](auto blockn_tag, auto stages_tag, auto minb_tag, auto bk_tag, auto nstg_tag, auto gelu_tag, auto cta2_tag) -> int {
+    constexpr bool C2_ = decltype(cta2_tag)::value;
     constexpr int BN_ = decltype(blockn_tag)::value;
     constexpr int ST_ = decltype(stages_tag)::value;
     constexpr int MB_ = decltype(minb_tag)::value;
@@ -732,7 +847,7 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
     {
       const uint64_t dims[3] = {(uint64_t)p.K, (uint64_t)p.Cout, (uint64_t)p.B};
       const uint64_t str[3] = {1, (uint64_t)p.K, (uint64_t)p.w_bs};
-      const uint32_t box[3] = {(uint32_t)phys_k<BK_>(), (uint32_t)BN_, 1};
+      const uint32_t box[3] = {(uint32_t)phys_k<BK_>(), (uint32_t)(C2_ ? BN_ / 2 : BN_), 1};  // CTA pair: each CTA loads half of the N tile
       int r2 = encode(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, p.w_bs ? 3 : 2, const_cast<void*>(p.w), dims, str, box, "W", swz);
       if (r2) return r2;
     }
@@ -756,44 +871,56 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
     }
     KParams k2 = kp;
     k2.n_tiles = (p.Cout + BN_ - 1) / BN_;
-    const int64_t total = m_tiles * k2.n_tiles;
+    k2.nimg = B;
+    const int64_t total = (C2_ ? (m_tiles + 1) / 2 : m_tiles) * k2.n_tiles;
     if (total > 0x7fffffffLL) { set_error("conv_tc: too many tiles (%lld)", (long long)total); return FB200_ERR_UNSUPPORTED; }
     k2.total_tiles = (int)total;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("FB200_TC_DBG"); dbg = e ? atoi(e) : 0; } k2.dbg = dbg; }
     { static int rt = -1; if (rt < 0) { const char* e = getenv("FB200_TC_RES_TMA"); rt = e ? atoi(e) : 1; } k2.res_tma = (p.res && rt) ? 1 : 0; }
     if constexpr (decltype(gelu_tag)::value) return launch<BN_, ST_, __half, MB_, BK_, NS_, true>(ta, tb, td, tr, k2, st);
     else {
-      if (out16) return launch<BN_, ST_, __half, MB_, BK_, NS_, false>(ta, tb, td, tr, k2, st);
-      return launch<BN_, ST_, float, MB_, BK_, NS_, false>(ta, tb, td, tr, k2, st);
+      if (out16) return launch<BN_, ST_, __half, MB_, BK_, NS_, false, C2_>(ta, tb, td, tr, k2, st);
+      return launch<BN_, ST_, float, MB_, BK_, NS_, false, C2_>(ta, tb, td, tr, k2, st);
     }
   };
+  typedef std::false_type C1;
+  typedef std::true_type C2;
   using std::integral_constant;
   typedef integral_constant<int, 64> K64;
   typedef integral_constant<int, 32> K32;
   typedef integral_constant<int, 1> I1;
   typedef integral_constant<int, 2> I2;
   if ((p.act & 15) == FB200_ACT_GELU)  // exact-erf GELU: dedicated instantiation (fp16 out, Cin % 64 == 0; checked in conv2d_tc_supported)
-    return run(integral_constant<int, 128>{}, integral_constant<int, 4>{}, I1{}, K64{}, I2{}, std::true_type{});
+    return run(integral_constant<int, 128>{}, integral_constant<int, 4>{}, I1{}, K64{}, I2{}, std::true_type{}, C1{});
   typedef integral_constant<int, 96> K96;  // halo mode tag
   if (halo) {
-    if (p.Cout > 32) return run(integral_constant<int, 64>{}, integral_constant<int, 4>{}, I2{}, K96{}, I2{}, std::false_type{});
-    return run(integral_constant<int, 32>{}, integral_constant<int, 4>{}, I2{}, K96{}, I2{}, std::false_type{});
+    if (p.Cout > 32) return run(integral_constant<int, 64>{}, integral_constant<int, 4>{}, I2{}, K96{}, I2{}, std::false_type{}, C1{});
+    return run(integral_constant<int, 32>{}, integral_constant<int, 4>{}, I2{}, K96{}, I2{}, std::false_type{}, C1{});
   }
   if (BK == 32) {  // stem convs (Cin = 32): HBM-bound, two CTAs per SM
-    if (p.Cout > 32) return run(integral_constant<int, 64>{}, integral_constant<int, 4>{}, I2{}, K32{}, I2{}, std::false_type{});
-    return run(integral_constant<int, 32>{}, integral_constant<int, 4>{}, I2{}, K32{}, I2{}, std::false_type{});
+    if (p.Cout > 32) return run(integral_constant<int, 64>{}, integral_constant<int, 4>{}, I2{}, K32{}, I2{}, std::false_type{}, C1{});
+    return run(integral_constant<int, 32>{}, integral_constant<int, 4>{}, I2{}, K32{}, I2{}, std::false_type{}, C1{});
   }
   static int force_bn = -1;  // tuning aid: FB200_TC_BN=64|128|256
   if (force_bn < 0) { const char* e = getenv("FB200_TC_BN"); force_bn = e ? atoi(e) : 0; }
-  if (force_bn == 64) return run(integral_constant<int, 64>{}, integral_constant<int, 3>{}, I2{}, K64{}, I2{}, std::false_type{});
-  if (force_bn == 128) return run(integral_constant<int, 128>{}, integral_constant<int, 4>{}, I1{}, K64{}, I2{}, std::false_type{});
-  if (force_bn == 256) return run(integral_constant<int, 256>{}, integral_constant<int, 3>{}, I1{}, K64{}, I2{}, std::false_type{});
+  if (force_bn == 64) return run(integral_constant<int, 64>{}, integral_constant<int, 3>{}, I2{}, K64{}, I2{}, std::false_type{}, C1{});
+  if (force_bn == 128) return run(integral_constant<int, 128>{}, integral_constant<int, 4>{}, I1{}, K64{}, I2{}, std::false_type{}, C1{});
+  if (force_bn == 256) return run(integral_constant<int, 256>{}, integral_constant<int, 3>{}, I1{}, K64{}, I2{}, std::false_type{}, C1{});
   const int64_t tiles256 = m_tiles * ((p.Cout + 255) / 256);
+  // CTA pairs (cta_group::2): the 256 x BLOCK_N tile of two SMs needs each weight tile only ONCE per pair - the single-CTA kernel is bound by the L2->SM
+  // operand bandwidth on every tensor-bound layer (48 KB per 128x256x64 MMA block = 19 TB/s at the tensor peak vs ~12 TB/s of L2)
+  if (g_cta_pair_mode < 0) { const char* e = getenv("FB200_TC_CTA2"); g_cta_pair_mode = e ? atoi(e) : 1; }  // env default, fb200_set_option overrides
+  const bool pair_ok = g_cta_pair_mode != 0 && !p.rowmax && !kp.w_batched;
+  const bool force_pair = g_cta_pair_mode == 2;
+  if (pair_ok && p.Cout > 128 && (tiles256 >= 148 || force_pair))
+    return run(integral_constant<int, 256>{}, integral_constant<int, 4>{}, I1{}, K64{}, I2{}, std::false_type{}, C2{});   // 4 x 32 + 64 KiB
+  if (pair_ok && p.Cout > 64 && p.Cout <= 128 && (m_tiles >= 148 || force_pair))
+    return run(integral_constant<int, 128>{}, integral_constant<int, 6>{}, I1{}, K64{}, I2{}, std::false_type{}, C2{});   // 6 x 24 + 64 KiB
   if (p.Cout > 128 && tiles256 >= 148)
-    return run(integral_constant<int, 256>{}, integral_constant<int, 3>{}, I1{}, K64{}, I2{}, std::false_type{});   // 144 + 64 KiB
+    return run(integral_constant<int, 256>{}, integral_constant<int, 3>{}, I1{}, K64{}, I2{}, std::false_type{}, C1{});   // 144 + 64 KiB
   if (p.Cout > 64)
-    return run(integral_constant<int, 128>{}, integral_constant<int, 4>{}, I1{}, K64{}, I2{}, std::false_type{});   // 128 + 64 KiB
-  return run(integral_constant<int, 64>{}, integral_constant<int, 3>{}, I2{}, K64{}, I2{}, std::false_type{});      // 72 + 32 KiB, 2 CTAs/SM
+    return run(integral_constant<int, 128>{}, integral_constant<int, 4>{}, I1{}, K64{}, I2{}, std::false_type{}, C1{});   // 128 + 64 KiB
+  return run(integral_constant<int, 64>{}, integral_constant<int, 3>{}, I2{}, K64{}, I2{}, std::false_type{}, C1{});      // 72 + 32 KiB, 2 CTAs/SM
 }
 
 }  // namespace fb200

@@ -290,15 +290,15 @@ _reduced_cache = {}
 def _reduced_products(layer, x, fn, kw, scale, act, residual, out):
     """fp32_tc layer with fewer than three products (see `_products`); weights derived lazily from the split triple."""
     C = layer.w3.shape[-1] // 3
-    key = (id(layer), _products)
-    w = _reduced_cache.get(key)
+    key = (id(layer.w3), _products)  # the entry keeps w3 alive, so its id cannot be recycled by another layer
+    w = _reduced_cache.get(key, (None, None))[1]
     if w is None:
         if _products == 2:
             w = layer.w3.clone()
             w[..., C:2 * C] = 0
         else:
             w = layer.w3[..., :C].contiguous()
-        _reduced_cache[key] = w
+        _reduced_cache[key] = (layer.w3, w)
     xp = ops.split_pair(x)
     pos = (scale, layer.bias) if fn is ops.conv2d else (layer.bias,)
     if _products == 2:

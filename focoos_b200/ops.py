@@ -63,7 +63,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = (
-    "fb200_last_error", "fb200_version", "fb200_device_supports_tcgen05", "fb200_stem_conv3x3s2", "fb200_stem_conv3x3s2_u8", "fb200_conv2d", "fb200_conv2d_per_image_weights", "fb200_linear_rowmax",
+    "fb200_last_error", "fb200_version", "fb200_device_supports_tcgen05", "fb200_set_option", "fb200_stem_conv3x3s2", "fb200_stem_conv3x3s2_u8", "fb200_conv2d", "fb200_conv2d_per_image_weights", "fb200_linear_rowmax",
     "fb200_split_f32_pair",
     "fb200_maxpool3x3s2", "fb200_avgpool2x2_ceil", "fb200_resize_bilinear", "fb200_add", "fb200_layernorm",
     "fb200_attention", "fb200_attention_split", "fb200_msda", "fb200_row_select", "fb200_rowmax", "fb200_topk", "fb200_gather_rows",
@@ -259,6 +259,17 @@ def _be():
     if _cuda_backend is None:
         _cuda_backend = CudaBackend()
     return _cuda_backend
+
+
+OPT_CONV_CTA_PAIR = 0
+
+
+def set_option(option: int, value: int) -> int:
+    """process-wide tuning option of the C library (include/focoos_b200.h fb200_option); returns the previous value"""
+    rc = load_library().fb200_set_option(int(option), int(value))
+    if rc < 0:
+        _check(rc, "set_option")
+    return rc
 
 
 def supports_tcgen05() -> bool:

@@ -42,6 +42,11 @@ const char* fb200_last_error(void);
 int fb200_version(void);
 /* 1 if the current device is sm_100 (tcgen05 path usable), 0 otherwise, <0 on error. */
 int fb200_device_supports_tcgen05(void);
+/* Process-wide tuning options (host-only, no CUDA call).  Returns the previous value, FB200_ERR_INVALID for an unknown option.
+ *   FB200_OPT_CONV_CTA_PAIR: 0 = tcgen05 convs never use CTA pairs, 1 (default) = `tcgen05.mma.cta_group::2` on 256-pixel x BLOCK_N tiles of two SMs
+ *   whenever a layer has enough tiles to fill the chip, 2 = whenever the shape allows it (tests: small shapes, odd tile counts). */
+typedef enum { FB200_OPT_CONV_CTA_PAIR = 0 } fb200_option;
+int fb200_set_option(int option, int value);
 
 /* ---- a2: ResNet-vd stem, first conv fused with the input normalisation ------------------------
  * Replaces `(images - pixel_mean) / pixel_std` (models/fai_detr/modelling.py:1349) followed by

@@ -174,3 +174,47 @@ def test_stem_halo_mode(B, H, W, Cout):
     out = ops.conv2d(x.to(DEV), w.to(DEV), sc.to(DEV), bi.to(DEV), stride=1, pad=1, act=1, algo=ops.ALGO_TCGEN05)
     err = float((out.float().cpu() - ref).abs().max())
     assert err <= 3e-3 * max(1.0, float(ref.abs().max())), err
+
+
+# ---- CTA pairs (tcgen05.mma.cta_group::2): every shape class again with the pair mode forced, plus bit-identity against the single-CTA kernel on
+# full-size layers (same operand order inside each MMA chain -> identical fp32 accumulators)
+@pytest.fixture()
+def force_pairs():
+    old = ops.set_option(ops.OPT_CONV_CTA_PAIR, 2)
+    yield
+    ops.set_option(ops.OPT_CONV_CTA_PAIR, old)
+
+
+def test_pair_mode_small_shapes(force_pairs):
+    run_case(1, 1, 1000, 256, 256, 1, 1, seed=1)                                   # 8 M tiles, ragged last tile
+    run_case(1, 1, 777, 1024, 256, 1, 1, seed=2)                                   # 7 M tiles: odd -> phantom tile in the last pair
+    run_case(1, 1, 128, 256, 512, 1, 1, seed=3)                                    # ONE M tile: the peer CTA only has a phantom
+    run_case(1, 1, 9600, 256, 1536, 1, 1, seed=4)                                  # 6 N tiles
+    run_case(2, 20, 20, 256, 256, 3, 1, act=1, seed=5)
+    run_case(2, 40, 40, 256, 256, 3, 1, act=2, seed=6)
+    run_case(3, 24, 40, 64, 128, 3, 1, act=1, seed=7)                              # BLOCK_N = 128 pairs, 3 images x odd tiles
+    run_case(2, 80, 80, 256, 256, 3, 2, act=1, seed=8)                             # stride-2 parity view
+    run_case(2, 20, 20, 256, 1024, 1, 1, act=1, use_res=True, seed=9)              # residual through TMA
+    run_case(2, 20, 20, 256, 256, 3, 1, act=2 | 16, use_res=True, use_scale=False, seed=10)
+    run_case(1, 1, 500, 256, 368, 1, 1, out_dtype=torch.float32, use_scale=False, tolerance=2e-3)  # Cout tail inside the second half of the N tile
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,stride,res", [(32, 80, 80, 256, 256, 3, 1, False), (32, 40, 40, 1024, 256, 1, 1, False), (32, 40, 40, 256, 1024, 1, 1, True),
+                                                          (32, 80, 80, 128, 128, 3, 1, False), (5, 40, 40, 512, 512, 3, 2, False), (1, 1, 268800, 256, 1536, 1, 1, False)])
+def test_pair_mode_bit_identical_to_single_cta(B, H, W, Cin, Cout, k, stride, res):
+    x = rnd((B, H, W, Cin), torch.float16, 1).to(DEV)
+    w = rnd((Cout, k, k, Cin), torch.float16, 2, 1.0 / math.sqrt(k * k * Cin)).to(DEV)
+    bi = rnd((Cout,), torch.float32, 3, 0.2).to(DEV)
+    pad = (k - 1) // 2
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    r = rnd((B, Ho, Wo, Cout), torch.float16, 4).to(DEV) if res else None
+    outs = []
+    for mode in (0, 2):
+        old = ops.set_option(ops.OPT_CONV_CTA_PAIR, mode)
+        try:
+            outs.append(ops.conv2d(x, w, None, bi, stride=stride, pad=pad, act=1, residual=r, algo=ops.ALGO_TCGEN05))
+            torch.cuda.synchronize()
+        finally:
+            ops.set_option(ops.OPT_CONV_CTA_PAIR, old)
+    assert torch.equal(outs[0], outs[1])
+    assert float(outs[0].float().abs().max()) > 0

@@ -23,6 +23,8 @@ for s in $STAGES; do
     benchfull) (time timeout 900 python bench.py) > gpurun_out/bench_default.log 2> gpurun_out/bench_default.err ;;
     bench32) timeout 900 python bench.py --steps 3 --warmup 3 --precision fp32 --no-cpu-baseline > gpurun_out/bench_fp32.log 2> gpurun_out/bench_fp32.err; timeout 900 python bench.py --steps 10 --warmup 3 --precision fp32_tc --no-cpu-baseline > gpurun_out/bench_fp32tc.log 2> gpurun_out/bench_fp32tc.err ;;
     budget) timeout 1200 python tools/error_budget.py > gpurun_out/error_budget.txt 2>&1 ;;
+    budget2) timeout 1200 python tools/error_budget.py tc:3323 tc:3331 tc:3332 tc:2222 tc:1111 > gpurun_out/error_budget2.txt 2>&1 ;;
+    micro01) (FB200_TC_CTA2=0 timeout 300 python tools/conv_micro.py; true) > gpurun_out/conv_micro_cta1.txt 2>&1; (timeout 300 python tools/conv_micro.py; true) > gpurun_out/conv_micro_cta2.txt 2>&1 ;;
     layers) timeout 600 python tools/layer_roofline.py > gpurun_out/layer_roofline.txt 2>&1 ;;
     micro) (python tools/conv_micro.py; true) > gpurun_out/conv_micro.txt 2>&1 ;;
     micro_ncu) timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 4 -c 2 -o gpurun_out/prof_micro python tools/conv_micro.py rep_3x3_80 s0_2c_res > gpurun_out/micro_ncu.log 2>&1 ;;
