@@ -191,7 +191,9 @@ class BisenetEngine(MFEngine):
         self.dt = torch.float32 if precision == "fp32" else torch.float16
         self.nhead, self.d = 8, cfg.transformer_predictor_hidden_dim
         self._consts = {}
-        sd = {k: v.detach() for k, v in sd.items()}
+        # pack on the HOST (BN folding, re-parameterisation, concatenations are a few hundred tiny tensor ops: as device launches they were ~700 `at::`
+        # kernels in front of the first forward); only the packed tensors travel to the device
+        sd = {k: v.detach().to("cpu") for k, v in sd.items()}
         bb = "pixel_decoder.backbone.features"
         w = sd[bb + ".0.conv.weight"].float()
         s, b = _bn_fold(sd, bb + ".0.bn")

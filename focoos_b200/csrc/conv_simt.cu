@@ -218,7 +218,11 @@ using namespace fb200;
 
 extern "C" const char* fb200_last_error(void) { return fb200::g_err; }
 extern "C" int fb200_version(void) { return 100; }
-namespace fb200 { int conv_tc_set_pair_mode(int v); }  // conv_tc.cu
+namespace fb200 { int conv_tc_set_pair_mode(int v); void conv_tc_set_trace(void* buf); }  // conv_tc.cu
+extern "C" int fb200_set_conv_trace(void* device_buf) {
+  conv_tc_set_trace(device_buf);
+  return FB200_OK;
+}
 extern "C" int fb200_set_option(int option, int value) {
   if (option == FB200_OPT_CONV_CTA_PAIR && value >= 0 && value <= 2) return conv_tc_set_pair_mode(value);
   set_error("set_option: unknown option %d / value %d", option, value);

@@ -55,6 +55,7 @@ struct KParams {
   float* rowmax;                   // not null: row-max-only epilogue (query selection scores), nothing is stored
   int w_batched;                   // 1: weights differ per image (3-D weight map, third coordinate = image)
   int dbg;                         // tuning aid (env FB200_TC_DBG): 1 = skip TMA store, 2 = skip residual, 4 = skip TMEM load
+  unsigned long long* trace;       // debug timeline (fb200_set_conv_trace): 128 clock64 slots per CTA, see tools/conv_trace.py
   int nimg;                        // images in the (possibly flattened) view: M tiles beyond it are phantoms of an odd CTA-pair count
 };
 
@@ -308,6 +309,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const int tiles_per_img = p.tiles_w * p.tiles_h;
+  // debug timeline: slot 0 = kernel entry of this CTA (globaltimer ns), 1 = setup done (clock64); per tile k < 20: 2+6k = accumulator stage free,
+  // 3+6k = first operands landed, 4+6k = last MMA issued (MMA thread); 5+6k = accumulator complete seen, 6+6k = tile stored (epilogue group 0); 7+6k = producer tile start
+  unsigned long long* const trc = p.trace ? p.trace + (size_t)blockIdx.x * 128 : nullptr;
+  auto stamp = [&](int slot) { if (trc && slot < 128) trc[slot] = (unsigned long long)clock64(); };
+  if (trc && threadIdx.x == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); trc[0] = g; trc[1] = (unsigned long long)clock64(); }
   struct TileXY { int n0, mt, img, h0, w0; };
   auto tile_of = [&](int t) {
     TileXY r;
@@ -338,9 +344,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       };
       int stage = 0;
       uint32_t phase = 0;
+      int fills = 0;
+      long long wait_empty = 0;  // debug timeline slot 124: cycles the producer waited for a free ring stage
       for (int t = t_first; t < p.total_tiles; t += t_stride) {
         const TileXY tc = tile_of(t);
         const int n0 = tc.n0, mt = tc.mt, img = tc.img, h0 = tc.h0, w0 = tc.w0;
+        stamp(7 + 6 * ((t - t_first) / t_stride));
         if constexpr (HALO) {
           for (int kh = 0; kh < 3; ++kh) {  // one k-block per filter row: the input strip once, the three kw weight slices
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -366,7 +375,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          const long long e0_ = trc ? clock64() : 0;
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (trc) wait_empty += clock64() - e0_;
+          if ((p.dbg & 8) && fills >= STAGES) {  // experiment: operands stay whatever the first ring fill loaded - no TMA traffic, the MMAs run at their own pace
+            if (cta_rank == 0) mbar_arrive(&full_bar[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          ++fills;
           const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
           const int a_c0 = a_chan(cc);
           const int kh = tap / p.KW, kw = tap - kh * p.KW;
@@ -401,6 +418,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      if (trc) trc[124] = (unsigned long long)wait_empty;
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer (CTA pair: the leader only)
@@ -408,14 +426,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       constexpr uint32_t idesc = make_idesc(BLOCK_N, CTA2 ? 256 : 128);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
+      long long wait_full = 0, wait_acc = 0;  // debug timeline: cycles the issuer spent waiting for operands / for a free accumulator stage (slots 122, 123)
       if constexpr (HALO) mbar_wait(w_bar, 0);
       for (int t = t_first; t < p.total_tiles; t += t_stride) {
+        const long long a0_ = trc ? clock64() : 0;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator stage
         tcgen05_fence_after();
+        if (trc) wait_acc += clock64() - a0_;
+        const int tk = (t - t_first) / t_stride;
+        stamp(2 + 6 * tk);
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          const long long w0_ = trc ? clock64() : 0;
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
+          if (trc) wait_full += clock64() - w0_;
+          if (kb == 0) stamp(3 + 6 * tk);
           const uint64_t da = make_smem_desc<BKP>(smem_u32(smem_a + stage * A_STAGE_BYTES));
           const uint64_t db = make_smem_desc<BKP>(smem_u32(smem_b + stage * B_STAGE_BYTES));
           if constexpr (HALO) {
@@ -433,8 +459,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
             for (int k = 0; k < BLOCK_K / 16; ++k) {
               // advance 16 halves = 32 B inside the swizzle row: +2 in 16-byte units
-              if constexpr (CTA2) umma_f16_2sm(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-              else umma_f16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              const uint32_t td = ((p.dbg & 16) && (k & 1)) ? tmem_base + (uint32_t)((acc ^ 1) * BLOCK_N) : tmem_d;  // dbg 16: two independent accumulation chains
+              if constexpr (CTA2) umma_f16_2sm(td, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              else umma_f16(td, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
             }
           }
           if constexpr (CTA2) umma_commit_2sm(&empty_bar[stage]);
@@ -443,8 +470,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         if constexpr (CTA2) umma_commit_2sm(&tmem_full_bar[acc]);
         else umma_commit(&tmem_full_bar[acc]);
+        stamp(4 + 6 * tk);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      if (trc) { trc[122] = (unsigned long long)wait_full; trc[123] = (unsigned long long)wait_acc; trc[125] = (unsigned long long)clock64(); }
     }
   } else if (warp >= 4) {
     // ===================================================================== epilogue (128 threads)
@@ -520,6 +549,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       epi_bar(grp);
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
+      if (grp == 0 && et == 0) stamp(5 + 6 * ((t - t_first) / t_stride));
       const uint32_t tmem_acc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BLOCK_N);
       float row_max = -INFINITY;
       if (p.rowmax) {  // row-max-only epilogue: enc_outputs_class.max(-1) (modelling.py:1210) without materialising the [B*S, num_classes] logits
@@ -536,6 +566,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll 1
       for (int c0 = c_begin; c0 < c_end && !p.rowmax; c0 += CHUNK_COLS) {
         if (n0 + c0 >= p.Cout) break;  // uniform across the group
+        if (p.dbg & 4) break;          // experiment: no epilogue work at all
         uint8_t* stg = my_staging + (chunk_ctr % NSTG) * STAGING_BYTES;
         uint8_t* srow = stg + row * 128;
         bool res_vec = false;
@@ -642,6 +673,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // all tcgen05.ld of this accumulator stage have completed (wait::ld): hand it back to the MMA warp
       tcgen05_fence_before();
       __syncwarp();
+      if (grp == 0 && et == 0) stamp(6 + 6 * ((t - t_first) / t_stride));
       if (lane == 0) {
         if constexpr (CTA2) mbar_arrive_cluster(mapa_rank0(smem_u32(&tmem_empty_bar[acc])));
         else mbar_arrive(&tmem_empty_bar[acc]);
@@ -749,7 +781,8 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
     if (e != cudaSuccess) { set_error("conv_tc(cta pair): launch failed: %s", cudaGetErrorString(e)); return FB200_ERR_CUDA; }
     return FB200_OK;
   }
-  const int64_t cap = (int64_t)num_sms() * MIN_BLOCKS;
+  int64_t cap = (int64_t)num_sms() * MIN_BLOCKS;
+  { static int gc = -1; if (gc < 0) { const char* e = getenv("FB200_GRID_CAP"); gc = e ? atoi(e) : 0; } if (gc > 0 && gc < cap) cap = gc; }  // experiment: fewer SMs
   const unsigned grid = (unsigned)(kp.total_tiles < cap ? kp.total_tiles : cap);
   kern<<<grid, NUM_THREADS, smem, st>>>(ta, tb, td, tr, kp);
   FB_CHECK_LAUNCH("conv_tc_kernel");
@@ -759,6 +792,9 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
 }  // namespace tc
 
 static int g_cta_pair_mode = -1;  // FB200_OPT_CONV_CTA_PAIR
+static unsigned long long* g_trace = nullptr;  // fb200_set_conv_trace
+
+void conv_tc_set_trace(void* buf) { g_trace = static_cast<unsigned long long*>(buf); }
 
 int conv_tc_set_pair_mode(int v) {
   const int old = g_cta_pair_mode < 0 ? 1 : g_cta_pair_mode;
@@ -872,6 +908,7 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
     KParams k2 = kp;
     k2.n_tiles = (p.Cout + BN_ - 1) / BN_;
     k2.nimg = B;
+    k2.trace = g_trace;
     const int64_t total = (C2_ ? (m_tiles + 1) / 2 : m_tiles) * k2.n_tiles;
     if (total > 0x7fffffffLL) { set_error("conv_tc: too many tiles (%lld)", (long long)total); return FB200_ERR_UNSUPPORTED; }
     k2.total_tiles = (int)total;
@@ -912,6 +949,10 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
   if (g_cta_pair_mode < 0) { const char* e = getenv("FB200_TC_CTA2"); g_cta_pair_mode = e ? atoi(e) : 1; }  // env default, fb200_set_option overrides
   const bool pair_ok = g_cta_pair_mode != 0 && !p.rowmax && !kp.w_batched;
   const bool force_pair = g_cta_pair_mode == 2;
+  static int cfg_env = -1;  // experiment knob FB200_TC_CFG: 1 = CTA pairs with a 5-deep ring and single staging buffers
+  if (cfg_env < 0) { const char* e = getenv("FB200_TC_CFG"); cfg_env = e ? atoi(e) : 0; }
+  if (cfg_env == 1 && pair_ok && p.Cout > 128 && !p.res)
+    return run(integral_constant<int, 256>{}, integral_constant<int, 5>{}, I1{}, K64{}, I1{}, std::false_type{}, C2{});   // 5 x 32 + 32 KiB
   if (pair_ok && p.Cout > 128 && (tiles256 >= 148 || force_pair))
     return run(integral_constant<int, 256>{}, integral_constant<int, 4>{}, I1{}, K64{}, I2{}, std::false_type{}, C2{});   // 4 x 32 + 64 KiB
   if (pair_ok && p.Cout > 64 && p.Cout <= 128 && (m_tiles >= 148 || force_pair))

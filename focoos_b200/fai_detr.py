@@ -252,9 +252,11 @@ class _Conv:
     def __init__(self, w, scale, bias, stride=1, pad=0, act=ops.ACT_NONE):
         self.w, self.scale, self.bias, self.stride, self.pad, self.act, self.w3 = w, scale, bias, stride, pad, act, None
 
-    def enable_split3(self):
+    def enable_split3(self, host_w3=None):
         if self.w.dtype == torch.float32 and self.w.shape[-1] % 32 == 0:
-            self.w3 = _split3_weights(self.w)
+            self.w3 = host_w3.get(id(self.w)) if host_w3 else None
+            if self.w3 is None:
+                self.w3 = _split3_weights(self.w)
 
     def __call__(self, x, residual=None, out=None, out_dtype=None, act=None, algo=ops.ALGO_AUTO):
         act = self.act if act is None else act
@@ -272,9 +274,11 @@ class _Linear:
     def __init__(self, w, bias):
         self.w, self.bias, self.w3 = w, bias, None
 
-    def enable_split3(self):
+    def enable_split3(self, host_w3=None):
         if self.w.dtype == torch.float32 and self.w.shape[-1] % 32 == 0:
-            self.w3 = _split3_weights(self.w)
+            self.w3 = host_w3.get(id(self.w)) if host_w3 else None
+            if self.w3 is None:
+                self.w3 = _split3_weights(self.w)
 
     def __call__(self, x, act=ops.ACT_NONE, residual=None, out_dtype=None, out=None, algo=ops.ALGO_AUTO):
         if _split3_ok(x, self.w3, act, algo) and (out_dtype in (None, torch.float32)):
@@ -306,20 +310,21 @@ def _reduced_products(layer, x, fn, kw, scale, act, residual, out):
     return fn(xp[..., :C], w, *pos, act=act, residual=residual, out=out, out_dtype=torch.float32, algo=ops.ALGO_TCGEN05, **kw)
 
 
-def _enable_split3(obj, seen=None):
-    """walk an engine's packed layers (attributes / lists / dicts / tuples) and attach the split-precision weight triples"""
+def _enable_split3(obj, seen=None, host_w3=None):
+    """walk an engine's packed layers (attributes / lists / dicts / tuples) and attach the split-precision weight triples
+    (`host_w3`: triples already split on the host at pack time, keyed by id() of the packed device weight)"""
     seen = set() if seen is None else seen
     if id(obj) in seen:
         return
     seen.add(id(obj))
     if isinstance(obj, (_Conv, _Linear)):
-        obj.enable_split3()
+        obj.enable_split3(host_w3)
     elif isinstance(obj, dict):
         for v in obj.values():
-            _enable_split3(v, seen)
+            _enable_split3(v, seen, host_w3)
     elif isinstance(obj, (list, tuple)):
         for v in obj:
-            _enable_split3(v, seen)
+            _enable_split3(v, seen, host_w3)
 
 
 def _bn_fold(sd, p, eps=1e-5):
@@ -330,6 +335,7 @@ def _bn_fold(sd, p, eps=1e-5):
 class DetrEngine:
     """Packs a FAIDetr state_dict for one (device, precision) and runs the fused forward."""
 
+    _host_w3 = None  # set per instance in fp32_tc mode (see _to)
     fuse_shortcut_pool = False  # fold the vd shortcut's AvgPool2d into a 2x2/s2 conv (slower on B200, see _pack_backbone)
 
     def __init__(self, sd: Dict[str, torch.Tensor], cfg: DETRConfig, device, precision: str = "fp16", algo: int = ops.ALGO_AUTO):
@@ -340,15 +346,22 @@ class DetrEngine:
         self.nhead = cfg.transformer_predictor_nhead
         self.d = cfg.transformer_predictor_hidden_dim
         self._consts: Dict[Tuple[int, int], dict] = {}
+        self._host_w3 = {} if precision == "fp32_tc" else None  # id(packed device weight) -> [W_hi|W_lo|W_hi] split on the host in _to()
         self.mix = {"backbone": 3, "encoder": 3, "select": 3, "decoder": 3}  # fp32_tc only: tensor-core products per stage (see `_products`)
-        sd = {k: v.detach() for k, v in sd.items()}
+        # pack on the HOST (BN folding, re-parameterisation, concatenations are a few hundred tiny tensor ops: as device launches they were ~700 `at::`
+        # kernels in front of the first forward); only the packed tensors travel to the device
+        sd = {k: v.detach().to("cpu") for k, v in sd.items()}
         self._pack(sd)
         if precision == "fp32_tc":  # fp32 storage everywhere; convs/linears = three fp16 tensor-core products (fp32-accurate)
-            _enable_split3(vars(self))
+            _enable_split3(vars(self), host_w3=self._host_w3)
+        self._host_w3 = None
 
     # ---- packing -------------------------------------------------------------------------------
     def _to(self, t, dtype=None):
-        return t.to(device=self.device, dtype=dtype or self.dt).contiguous()
+        d = t.to(device=self.device, dtype=dtype or self.dt).contiguous()
+        if self._host_w3 is not None and dtype is None and t.dim() >= 2 and t.shape[-1] % 32 == 0 and not t.is_cuda:
+            self._host_w3[id(d)] = _split3_weights(t.float().contiguous()).to(self.device)
+        return d
 
     def _f32(self, t):
         return t.to(device=self.device, dtype=torch.float32).contiguous()

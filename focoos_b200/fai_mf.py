@@ -220,7 +220,9 @@ class MFEngine(DetrEngine):
         self.depth = cfg.backbone_config.depth
         self.nhead, self.d = 8, cfg.transformer_predictor_hidden_dim
         self._consts = {}
-        sd = {k: v.detach() for k, v in sd.items()}
+        # pack on the HOST (BN folding, re-parameterisation, concatenations are a few hundred tiny tensor ops: as device launches they were ~700 `at::`
+        # kernels in front of the first forward); only the packed tensors travel to the device
+        sd = {k: v.detach().to("cpu") for k, v in sd.items()}
         self._pack_backbone(sd)
         pd = "pixel_decoder"
         self.pd_in = self._conv_bias(sd, pd + ".input_proj", 0)

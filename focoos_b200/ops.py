@@ -63,7 +63,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = (
-    "fb200_last_error", "fb200_version", "fb200_device_supports_tcgen05", "fb200_set_option", "fb200_stem_conv3x3s2", "fb200_stem_conv3x3s2_u8", "fb200_conv2d", "fb200_conv2d_per_image_weights", "fb200_linear_rowmax",
+    "fb200_last_error", "fb200_version", "fb200_device_supports_tcgen05", "fb200_set_option", "fb200_set_conv_trace", "fb200_stem_conv3x3s2", "fb200_stem_conv3x3s2_u8", "fb200_conv2d", "fb200_conv2d_per_image_weights", "fb200_linear_rowmax",
     "fb200_split_f32_pair",
     "fb200_maxpool3x3s2", "fb200_avgpool2x2_ceil", "fb200_resize_bilinear", "fb200_add", "fb200_layernorm",
     "fb200_attention", "fb200_attention_split", "fb200_msda", "fb200_row_select", "fb200_rowmax", "fb200_topk", "fb200_gather_rows",
@@ -270,6 +270,11 @@ def set_option(option: int, value: int) -> int:
     if rc < 0:
         _check(rc, "set_option")
     return rc
+
+
+def set_conv_trace(buf: Optional[torch.Tensor]):
+    """debug timeline of conv_tc launches (see include/focoos_b200.h fb200_set_conv_trace); buf: int64 CUDA tensor [>= 296 * 128] or None"""
+    _check(load_library().fb200_set_conv_trace(_p(buf)), "set_conv_trace")
 
 
 def supports_tcgen05() -> bool:

@@ -47,6 +47,9 @@ int fb200_device_supports_tcgen05(void);
  *   whenever a layer has enough tiles to fill the chip, 2 = whenever the shape allows it (tests: small shapes, odd tile counts). */
 typedef enum { FB200_OPT_CONV_CTA_PAIR = 0 } fb200_option;
 int fb200_set_option(int option, int value);
+/* Debug timeline of the tcgen05 conv kernel (tools/conv_trace.py): while `device_buf` is not NULL every conv_tc launch writes 128 x uint64 clock64
+ * stamps per CTA (grid x 128 x 8 bytes, at most 296 CTAs) - tile boundaries as seen by the MMA issuer, the producer and the epilogue.  NULL switches it off. */
+int fb200_set_conv_trace(void* device_buf);
 
 /* ---- a2: ResNet-vd stem, first conv fused with the input normalisation ------------------------
  * Replaces `(images - pixel_mean) / pixel_std` (models/fai_detr/modelling.py:1349) followed by
