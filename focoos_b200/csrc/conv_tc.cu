@@ -438,7 +438,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           const long long w0_ = trc ? clock64() : 0;
-          mbar_wait(&full_bar[stage], phase);
+          if (!(p.dbg & 32)) mbar_wait(&full_bar[stage], phase);  // dbg 32: the MMAs never wait for operands (timing experiment: loads still run)
           tcgen05_fence_after();
           if (trc) wait_full += clock64() - w0_;
           if (kb == 0) stamp(3 + 6 * tk);

@@ -71,6 +71,7 @@ class FocoosModel:
         self.cuda_graphs = os.environ.get("FB200_NO_GRAPH", "0") != "1"
         self._graphs = {}  # key -> (graph, static_input, static_output, the engine whose packed weights the graph reads)
         self._graph_seen = {}
+        self._pipe = None  # infer_async state: copy stream, two staging / pinned result buffers
 
     def _forward(self, images):
         """model.forward, through a cached CUDA graph when the same input shape has been seen before (first sighting runs eagerly)."""
@@ -136,6 +137,65 @@ class FocoosModel:
             d.latency = lat
         return dets if batched else dets[0]
 
+    # ---- pipelined inference: the host edge overlapped with the device ------------------------------------------------
+    def infer_async(self, inputs, threshold: Optional[float] = None) -> "PendingDetections":
+        """Enqueue one batch and return at once; `.result()` yields what `self(inputs, batched=True)` would.
+
+        fai-detr family with a pinned uint8 [B,H,W,3] batch at the model resolution: the H2D copy runs on a COPY stream into one of two staging
+        buffers, the compute stream then (a) copies staging -> the CUDA graph's static input (device to device), (b) replays the graph, (c) runs the
+        fused post-process, (d) sends the packed detections to one of two pinned host buffers.  Nothing blocks the host, so the copy of batch k+1
+        and the Python-side object building of batch k-1 overlap with the device work of batch k.  Any other input takes the synchronous path."""
+        from .processor import _is_u8_nhwc_batch
+        fast = (isinstance(self.processor, DETRProcessor) and type(self.processor) is DETRProcessor and _is_u8_nhwc_batch(inputs) and not inputs.is_cuda
+                and self.cuda_graphs and ops._backend is None and self.model.device.type == "cuda")
+        if fast:
+            tgt = self.processor.image_size
+            tgt = (tgt, tgt) if isinstance(tgt, int) else tgt
+            fast = tgt is None or tuple(inputs.shape[1:3]) == tuple(tgt)
+        if not fast:
+            return PendingDetections(ready=self(inputs, threshold=threshold, batched=True))
+        dev = self.model.device
+        st = self._pipe
+        key = (tuple(inputs.shape), getattr(self.model, "precision", None))
+        if st is None or st["key"] != key:
+            B = inputs.shape[0]
+            K = self.processor.top_k
+            st = self._pipe = {"key": key, "copy": torch.cuda.Stream(device=dev), "k": 0,
+                               "staging": [torch.empty(inputs.shape, dtype=torch.uint8, device=dev) for _ in range(2)],
+                               "host": [torch.empty((B, K * 7 + 1), dtype=torch.int32).pin_memory() for _ in range(2)],
+                               "h2d_done": [torch.cuda.Event() for _ in range(2)], "free": [torch.cuda.Event() for _ in range(2)],
+                               "sizes": torch.tensor([(int(inputs.shape[1]), int(inputs.shape[2]))] * B, dtype=torch.int32, device=dev)}
+            for _ in range(2):  # first sighting runs eagerly, the second captures the graph (see _forward)
+                self._forward(st["staging"][0])
+            torch.cuda.synchronize(dev)
+        k = st["k"] & 1
+        st["k"] += 1
+        cur = torch.cuda.current_stream(dev)
+        with torch.cuda.stream(st["copy"]):
+            st["copy"].wait_event(st["free"][k])       # the compute stream has finished reading this staging buffer (two batches ago)
+            st["staging"][k].copy_(inputs, non_blocking=True)
+            st["h2d_done"][k].record(st["copy"])
+        cur.wait_event(st["h2d_done"][k])
+        with torch.no_grad():
+            out = self._forward(st["staging"][k])      # static_in.copy_(staging) + graph replay, all on the compute stream
+            st["free"][k].record(cur)
+            packed = self.processor.postprocess_packed(out, None, None, threshold, sizes_dev=st["sizes"])
+            st["host"][k].copy_(packed, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(cur)
+        return PendingDetections(event=done, host=st["host"][k], class_names=self.model_info.classes)
+
+    def stream(self, batches, threshold: Optional[float] = None, depth: int = 2):
+        """generator over an iterable of batches: yields each batch's detections, keeping `depth` batches in flight (see infer_async)"""
+        from collections import deque
+        q = deque()
+        for b in batches:
+            q.append(self.infer_async(b, threshold))
+            if len(q) >= depth:
+                yield q.popleft().result()
+        while q:
+            yield q.popleft().result()
+
     def infer(self, image, threshold: Optional[float] = None) -> FocoosDetections:
         """focoos_model.py:370: single image (ndarray HWC uint8 / PIL / tensor) -> FocoosDetections."""
         return self(image, threshold=threshold)
@@ -157,6 +217,20 @@ class FocoosModel:
         a = np.array(ts)
         return {"fps": int(1000 * batch / a.mean()), "mean": round(float(a.mean()), 3), "min": round(float(a.min()), 3), "max": round(float(a.max()), 3),
                 "std": round(float(a.std()), 3), "im_size": size[0], "device": str(self.device), "engine": "focoos_b200"}
+
+
+class PendingDetections:
+    """handle returned by FocoosModel.infer_async: `.result()` waits for the device (one event) and builds the FocoosDetections"""
+
+    def __init__(self, ready=None, event=None, host=None, class_names=()):
+        self._ready, self._event, self._host, self._names = ready, event, host, class_names
+
+    def result(self) -> List[FocoosDetections]:
+        if self._ready is None:
+            self._event.synchronize()
+            # the pinned buffer is reused two batches later: parse it now
+            self._ready = DETRProcessor.detections_from_packed(self._host.numpy().copy(), self._names)
+        return self._ready
 
 
 class ModelManager:

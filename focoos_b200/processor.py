@@ -109,15 +109,21 @@ class DETRProcessor:
         sizes = torch.tensor(list(image_sizes), dtype=torch.int32).to(output.logits.device, non_blocking=True)
         return ops.detr_postprocess(output.logits, output.boxes, sizes, top_k, threshold)
 
-    def postprocess(self, output: DETRModelOutput, inputs, class_names: Sequence[str] = (), top_k=None, threshold=None) -> List[FocoosDetections]:
-        image_sizes = get_image_sizes(inputs)
-        B = output.boxes.shape[0]
-        assert len(image_sizes) == B, f"Expected image sizes {len(image_sizes)} to match batch size {B}"
-        s, l, b, q, c = self.postprocess_tensors(output, image_sizes, top_k, threshold)
-        K = s.shape[1]
-        # one packed D2H copy: [B, K, 7] (score bits, label, 4 box coords, query) + counts
+    def postprocess_packed(self, output: DETRModelOutput, image_sizes, top_k=None, threshold=None, sizes_dev=None) -> torch.Tensor:
+        """the fused post-process kernel + the packing of its five outputs into ONE int32 device tensor [B, K*7 + 1]
+        (per detection: score bits, label, 4 box coords, query; then the keep count) - the single thing that travels to the host"""
+        if sizes_dev is not None:
+            s, l, b, q, c = ops.detr_postprocess(output.logits, output.boxes, sizes_dev, top_k or self.top_k, threshold or self.threshold)
+        else:
+            s, l, b, q, c = self.postprocess_tensors(output, image_sizes, top_k, threshold)
+        B = s.shape[0]
         packed = torch.cat([s.view(torch.int32).unsqueeze(-1), l.unsqueeze(-1), b, q.unsqueeze(-1)], dim=-1)
-        packed_h = torch.cat([packed.reshape(B, -1), c.unsqueeze(-1)], dim=1).cpu().numpy()
+        return torch.cat([packed.reshape(B, -1), c.unsqueeze(-1)], dim=1)
+
+    @staticmethod
+    def detections_from_packed(packed_h: np.ndarray, class_names: Sequence[str] = ()) -> List[FocoosDetections]:
+        B = packed_h.shape[0]
+        K = (packed_h.shape[1] - 1) // 7
         res = []
         for i in range(B):
             n = int(packed_h[i, -1])
@@ -129,6 +135,13 @@ class DETRProcessor:
                 FocoosDet(bbox=bx, conf=cf, cls_id=lb, label=class_names[lb] if class_names else None)
                 for bx, cf, lb in zip(boxes, confs, labels)]))
         return res
+
+    def postprocess(self, output: DETRModelOutput, inputs, class_names: Sequence[str] = (), top_k=None, threshold=None) -> List[FocoosDetections]:
+        image_sizes = get_image_sizes(inputs)
+        B = output.boxes.shape[0]
+        assert len(image_sizes) == B, f"Expected image sizes {len(image_sizes)} to match batch size {B}"
+        # one packed D2H copy: [B, K, 7] (score bits, label, 4 box coords, query) + counts
+        return self.detections_from_packed(self.postprocess_packed(output, image_sizes, top_k, threshold).cpu().numpy(), class_names)
 
     def export_postprocess(self, output, inputs, class_names=(), top_k=None, threshold: float = 0.5):
         """processor.py:219-236: output = (boxes, logits) of an exported graph."""

@@ -212,3 +212,22 @@ def test_focoos_model_cuda_graph_path_equals_eager(sd):
             for g, e in zip(got, r):
                 assert [(d.cls_id, d.bbox, d.conf) for d in g.detections] == [(d.cls_id, d.bbox, d.conf) for d in e.detections], rep
     assert len(fm._graphs) == 1
+
+
+def test_pipelined_inference_equals_the_synchronous_call(sd):
+    """FocoosModel.infer_async / stream (copy stream + two staging buffers + pinned result buffers): same detections as the blocking call, for
+    different images flowing through the same buffers, in order."""
+    from focoos_b200 import FocoosModel, ModelInfo
+
+    fm = FocoosModel(_model(sd, "fp16"), ModelInfo(name="fai-detr-l-obj365", im_size=640))
+    batches = [torch.from_numpy(np.stack(synth_images(s, [(640, 640)] * 2))).pin_memory() for s in (1, 2, 3, 4, 5)]
+    ref = [fm(b, threshold=0.5, batched=True) for b in batches]
+    key = lambda dets: [[(d.cls_id, tuple(d.bbox), d.conf) for d in x.detections] for x in dets]
+    got = list(fm.stream(batches, threshold=0.5))
+    assert [key(g) for g in got] == [key(r) for r in ref]
+    # a handle may be resolved late (its pinned buffer is only reused two submissions later) and twice
+    h1 = fm.infer_async(batches[0], threshold=0.5)
+    h2 = fm.infer_async(batches[1], threshold=0.5)
+    assert key(h2.result()) == key(ref[1]) and key(h1.result()) == key(ref[0]) and key(h1.result()) == key(ref[0])
+    # non-pinned / list inputs fall back to the synchronous path
+    assert key(fm.infer_async([b for b in batches[2].numpy()], threshold=0.5).result()) == key(ref[2])
