@@ -7,10 +7,14 @@
 
 A "step" = one pass of the hot path over one batch of 32 synthetic images: FAIDetr.forward (normalise -> ResNet50-vd ->
 hybrid encoder -> 6-layer deformable decoder) + the fused DETR post-process kernel.
-  value : whole-job images/s with inputs resident in HBM (CUDA-graph replay of the forward + post-process launch)
-  e2e   : same metric through the public API (FocoosModel.__call__) from PINNED HOST uint8 images, H2D and D2H inside
-          the timed region
-Multi-GPU: independent replicas, one process per GPU, no data-path collective ("replicas only"; weak scaling).
+  value : whole-job images/s with inputs resident in HBM (CUDA-graph replay of the forward + post-process launch), in the PARITY-GREEN
+          mode `fp32_tc` (fp32 storage, three fp16 tcgen05 products per conv/linear: meets north_star's 1e-3 / identical keep-set bars,
+          tests/test_gpu_e2e.py, profiles/r02_error_budget.md).  The fp16 mode (one product; the reference's own CUDA numerics class, but
+          outside the bars) is reported beside it as `fast_mode`.
+  e2e   : same metric through the public API (FocoosModel.stream / infer_async) from PINNED HOST uint8 images, H2D and D2H inside
+          the timed region, two batches in flight
+Multi-GPU: inference = independent replicas, one process per GPU, no data-path collective ("replicas only"; weak scaling); the fine-tune
+leg (BASELINE configs[4], `train_config5`) runs on every rank with the bucketed NCCL gradient all-reduce.
 """
 from __future__ import annotations
 
@@ -31,8 +35,21 @@ import torch  # noqa: E402
 METRIC = "images/sec fai-detr-l bs=32 640x640 inference"
 GFLOP_PER_IMG_USEFUL = 139.05  # excludes the dead mask_features conv
 IDEAL_US_PER_IMG_16BIT = 129.0  # SURVEY.md §8(d) sum-of-max roofline at 16-bit activations
-# dram__bytes_read.sum + dram__bytes_write.sum of that launch from the committed ncu --set full capture (profiles/); None until captured
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 167.8e6  # profiles/r01_trip13_summary.md §2 (106.1 MB read + 61.7 MB written; 211 MB algorithmic)
+IDEAL_US_PER_IMG_FP32 = 259.0   # fp32 activations + half-rate (tf32-class) MMA
+
+
+def ncu_traffic(kernel_substr: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, read from the committed ncu capture of THIS round
+    (profiles/r02_ncu_dominant.csv, written by tools/ncu_extract.py from an `ncu --set full` report); None when no capture matches."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r02_ncu_dominant.csv")
+    if not os.path.exists(path):
+        return None, None
+    with open(path) as f:
+        for row in csv.DictReader(f):
+            if kernel_substr in row.get("kernel", ""):
+                return float(row["dram_bytes_read"]) + float(row["dram_bytes_write"]), os.path.relpath(path, ROOT)
+    return None, None
 
 
 def measured_peaks():
@@ -171,7 +188,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32)
-    ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32", "fp32_tc"])
+    ap.add_argument("--precision", default="fp32_tc", choices=["fp16", "fp32", "fp32_tc"])
+    ap.add_argument("--no-train-leg", action="store_true", help="skip the fine-tune leg (BASELINE configs[4])")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="skip the bs=1 latency, parity-mode and other-config legs")
@@ -189,7 +207,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        cb, csteps, cwarm = 2, max(1, min(args.steps, 3)), min(args.warmup, 1)
+        cb, csteps, cwarm = 2, max(5, min(args.steps, 8)), max(1, min(args.warmup, 2))
         v, ms = cpu_reference_run(cb, csteps, cwarm, sd, cpu_threads)
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": csteps, "warmup": cwarm, "ms_per_step": ms,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
@@ -266,12 +284,14 @@ def main():
     ms_step = ms_total / args.steps
     value = B * world / (ms_step / 1e3)
 
-    # ---- e2e through the public API: pinned host uint8 -> H2D -> preprocess -> forward -> postprocess -> D2H -> FocoosDetections
-    def step_e2e():
-        return fm(host_u8, threshold=0.5, batched=True)
+    # ---- e2e through the public API: pinned host uint8 -> H2D (copy stream) -> graph replay -> fused post-process -> packed D2H -> FocoosDetections,
+    # two batches in flight (FocoosModel.stream / infer_async): every step still copies its own 39 MB input and reads its own result back
+    def batches(n):
+        for _ in range(n):
+            yield host_u8
 
-    for _ in range(5):  # call 1 runs eagerly, call 2 captures the CUDA graph of model.forward, calls 3+ replay it
-        step_e2e()
+    for _ in fm.stream(batches(5), threshold=0.5):  # first call runs eagerly, the second captures the CUDA graph of model.forward
+        pass
     torch.cuda.synchronize()
     # serving-style GC hygiene: everything allocated so far (model, packed weights, graph pools) moves to the permanent generation, so the cyclic
     # collector only ever walks the per-step detection objects (a full collection over the torch heap showed up as one ~50 ms step in 25)
@@ -280,23 +300,38 @@ def main():
     gc.freeze()
     if world > 1:
         dist.barrier()
-    e2e_steps = max(3, args.steps // 2)
+    e2e_steps = max(6, args.steps // 2)
     per_step = []
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        ts = time.perf_counter()
-        dets = step_e2e()
-        per_step.append((time.perf_counter() - ts) * 1e3)
+    ts = t0
+    for dets in fm.stream(batches(e2e_steps), threshold=0.5):
+        now = time.perf_counter()
+        per_step.append((now - ts) * 1e3)
+        ts = now
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
     e2e_ms = D.max_over_ranks(e2e_ms, dev)
     per_step.sort()
-    e2e = {"value": B * world / (e2e_ms / 1e3), "unit": "images/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(host_u8.numel()) + B * 8,
-           "d2h_bytes_per_step": B * (300 * 7 + 1) * 4, "p50_ms": per_step[len(per_step) // 2], "max_ms": per_step[-1], "steps": e2e_steps, "api": "FocoosModel.__call__(pinned uint8 [B,H,W,3], batched=True)"}
+    # the same API without pipelining (one blocking call per batch), for reference
+    for _ in range(2):
+        fm(host_u8, threshold=0.5, batched=True)
+    t0 = time.perf_counter()
+    nb = max(3, e2e_steps // 2)
+    for _ in range(nb):
+        dets = fm(host_u8, threshold=0.5, batched=True)
+    blocking_ms = D.max_over_ranks((time.perf_counter() - t0) * 1e3 / nb, dev)
+    e2e = {"value": B * world / (e2e_ms / 1e3), "unit": "images/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(host_u8.numel()),
+           "d2h_bytes_per_step": B * (300 * 7 + 1) * 4, "p50_ms": per_step[len(per_step) // 2], "max_ms": per_step[-1], "steps": e2e_steps,
+           "frac_of_value": (B * world / (e2e_ms / 1e3)) / value,
+           "api": "FocoosModel.stream(pinned uint8 [B,H,W,3] batches), 2 in flight (infer_async: copy stream + staging buffers + pinned results)",
+           "blocking_call": {"value": B * world / (blocking_ms / 1e3), "ms_per_step": blocking_ms, "api": "FocoosModel.__call__(pinned uint8 [B,H,W,3], batched=True)"}}
+    fm._pipe = None
+    fm._graphs.clear()
+    torch.cuda.empty_cache()
 
     # ---- bs=1 latency (BASELINE.json metric, second half): p50/p90 of single-image forward+post-process, CUDA graph replay, device-timed
     lat = None
-    par = None
+    fast = None
     if rank == 0 and not args.quick:
         x1, s1 = x_dev[:1].contiguous(), sizes_dev[:1].contiguous()
 
@@ -305,9 +340,9 @@ def main():
             return ops.detr_postprocess(o.logits, o.boxes, s1, 300, 0.5)
 
         lat = _latency(step1, not args.no_graph)
-        # ---- the parity-exact tensor-core mode (fp32 storage, 3 fp16 tcgen05 products per conv/linear) on the same workload
-        if args.precision == "fp16":
-            m2 = FAIDetr(DETRConfig(), precision="fp32_tc")
+        # ---- the fp16 mode (one tcgen05 product per conv/linear) on the same workload: faster, outside the parity bars
+        if args.precision == "fp32_tc":
+            m2 = FAIDetr(DETRConfig(), precision="fp16")
             m2.load_state_dict(sd, strict=True)
             m2.to(dev)
 
@@ -315,64 +350,101 @@ def main():
                 o = m2(x_dev)
                 return ops.detr_postprocess(o.logits, o.boxes, sizes_dev, 300, 0.5)
 
-            ms2 = _throughput_ms(step2, not args.no_graph, max(5, args.steps // 5))
-            par = {"precision": "fp32_tc", "value": B / (ms2 / 1e3), "unit": "images/s", "ms_per_step": ms2, "n_gpus": 1,
-                   "note": "meets the 1e-3 / identical keep-set bars against the reference golden (tests/test_gpu_e2e.py::test_fp32_tc_meets_the_parity_bars); the fp16 headline mode is within 3e-3 on boxes"}
+            ms2 = _throughput_ms(step2, not args.no_graph, max(5, args.steps // 2))
+            fast = {"precision": "fp16", "value": B / (ms2 / 1e3), "unit": "images/s", "ms_per_step": ms2, "n_gpus": 1,
+                    "frac_of_ideal_16bit": (IDEAL_US_PER_IMG_16BIT * B / 1e3) / ms2,
+                    "note": "fp16 storage, one product: the reference's own CUDA numerics class (fp16 autocast, focoos_model.py:604-609) but OUTSIDE north_star's bars (boxes 1.5e-3, "
+                            "298-299/300 queries, ~70% identical integer boxes: profiles/r02_error_budget.md); not the headline"}
             del m2
+            torch.cuda.empty_cache()
 
-    # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv), heaviest layer shape timed alone: FPN 3x3 256->256 @80x80
+    # ---- roofline of the dominant kernel, timed alone on its heaviest layer shape: FPN 3x3 256->256 @80x80
     peaks = measured_peaks()
     roof = None
-    if args.precision == "fp16":
-        xr = torch.randn((B, 80, 80, 256), device=dev).half()
-        wr = (torch.randn((256, 3, 3, 256), device=dev) * 0.02).half()
+    if args.precision in ("fp16", "fp32_tc"):
+        split = args.precision == "fp32_tc"
+        wr32 = torch.randn((256, 3, 3, 256), device=dev) * 0.02
         br = torch.zeros(256, device=dev)
-        yr = torch.empty((B, 80, 80, 256), device=dev, dtype=torch.float16)
+        if split:
+            from focoos_b200.fai_detr import _split3_weights
+            xr = ops.split_pair(torch.randn((B, 80, 80, 256), device=dev))
+            wr = _split3_weights(wr32)
+            yr = torch.empty((B, 80, 80, 256), device=dev, dtype=torch.float32)
+            run_k = lambda: ops.conv2d(xr, wr, None, br, pad=1, act=ops.ACT_SILU, out=yr, algo=ops.ALGO_TCGEN05_SPLIT3)
+        else:
+            xr = torch.randn((B, 80, 80, 256), device=dev).half()
+            wr = wr32.half()
+            yr = torch.empty((B, 80, 80, 256), device=dev, dtype=torch.float16)
+            run_k = lambda: ops.conv2d(xr, wr, None, br, pad=1, act=ops.ACT_SILU, out=yr)
         for _ in range(3):
-            ops.conv2d(xr, wr, None, br, pad=1, act=ops.ACT_SILU, out=yr)
+            run_k()
         torch.cuda.synchronize()
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         nrep = 20
         r0.record()
         for _ in range(nrep):
-            ops.conv2d(xr, wr, None, br, pad=1, act=ops.ACT_SILU, out=yr)
+            run_k()
         r1.record()
         torch.cuda.synchronize()
         k_ms = r0.elapsed_time(r1) / nrep
         flops = 2.0 * B * 80 * 80 * 256 * 256 * 9
         ach = flops / (k_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "conv_tc_kernel<256,3,half,1,64,2> on the 3x3 256->256 @80x80 conv (re-parameterised RepVGG block of the FPN CSPRepLayer; 3 launches/step at this shape, 16% of model FLOPs; conv_tc_kernel as a family = 97% of FLOPs)",
-                "achieved": ach, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": ach / peaks["tf_burst"], "peak_source": peaks["source"] + " burst (kernel timed alone)",
-                "launch_ms": k_ms, "flops_per_launch": flops, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
+        traffic, traffic_src = ncu_traffic("conv_tc_kernel")
+        ideal_ms = (IDEAL_US_PER_IMG_FP32 if split else IDEAL_US_PER_IMG_16BIT) * B / 1e3
+        roof = {"bound": "tensor", "kernel": "conv_tc_kernel on the 3x3 256->256 @80x80 conv (re-parameterised RepVGG block of the FPN CSPRepLayer; 3 launches/step at this shape, 16% of model FLOPs; "
+                                             "conv_tc_kernel as a family = 97% of FLOPs)" + (", fp32-accurate as THREE fp16 tcgen05 products" if split else ""),
+                "achieved": ach, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": ach / peaks["tf_burst"], "peak_source": peaks["source"] + " burst bf16 (kernel timed alone)",
+                "launch_ms": k_ms, "flops_per_launch": flops, "traffic": traffic, "traffic_source": traffic_src,
+                "issued": {"tflops": ach * (3 if split else 1), "frac": ach * (3 if split else 1) / peaks["tf_burst"],
+                           "note": "tensor-pipe work actually issued (3 products per algorithmic product in fp32_tc); `achieved`/`frac` count ALGORITHMIC flops only"},
                 "model": {"useful_gflop_per_img": GFLOP_PER_IMG_USEFUL, "achieved_tflops_whole_step": GFLOP_PER_IMG_USEFUL * B / ms_step,
-                          "ideal_ms_per_step_16bit": IDEAL_US_PER_IMG_16BIT * B / 1e3, "frac_of_ideal": (IDEAL_US_PER_IMG_16BIT * B / 1e3) / ms_step}}
+                          "ideal_ms_per_step": ideal_ms, "ideal_basis": "SURVEY 8(d) sum-of-max: " + ("fp32 activations + half-rate MMA (259 us/img)" if split else "16-bit activations (129 us/img)"),
+                          "frac_of_ideal": ideal_ms / ms_step}}
+        del xr, wr, yr
+        torch.cuda.empty_cache()
 
-    # ---- the other BASELINE.json configs (secondary numbers, each in its own process so that a failure there cannot touch the headline line):
-    # configs[2] MaskFormer bs=16 800^2, configs[3] BisenetFormer bs=64 1024x512, configs[4] fai-detr fine-tune step bs=16 (1 GPU here)
+    # ---- the other BASELINE.json inference configs (secondary numbers, each in its own process so that a failure there cannot touch the headline line):
+    # configs[2] MaskFormer bs=16 800^2, configs[3] BisenetFormer bs=64 1024x512
     other = None
     if rank == 0 and world == 1 and not args.quick and not args.no_other_configs:
         other = {}
         root = os.path.dirname(os.path.abspath(__file__))
-        for key, cmd in (("fai-mf-l-coco-ins bs=16 800x800 inference", ["tools/bench_mf.py"]), ("bisenetformer-l-ade bs=64 1024x512 inference", ["tools/bench_bisenet.py"]),
-                         ("fai-detr-l fine-tune step bs=16 640x640", ["tools/bench_train.py", "--steps", "3", "--warmup", "2"])):
+        for key, cmd in (("fai-mf-l-coco-ins bs=16 800x800 inference", ["tools/bench_mf.py"]), ("bisenetformer-l-ade bs=64 1024x512 inference", ["tools/bench_bisenet.py"])):
             try:
                 env = dict(os.environ, FB200_TRACE="0")
-                r = subprocess.run([sys.executable] + cmd, cwd=root, env=env, capture_output=True, text=True, timeout=240)
+                r = subprocess.run([sys.executable] + cmd, cwd=root, env=env, capture_output=True, text=True, timeout=300)
                 line = next(l for l in r.stdout.splitlines() if l.startswith("{"))
                 d = json.loads(line)
-                other[key] = {k: d[k] for k in ("images_per_s", "value", "ms_per_step", "unfused_images_per_s", "dtype", "phases_ms", "peak_mem_GB") if k in d}
+                other[key] = {k: d[k] for k in ("images_per_s", "value", "ms_per_step", "unfused_images_per_s", "dtype", "phases_ms", "peak_mem_GB", "parity_mode") if k in d}
             except Exception as e:  # noqa: BLE001
                 other[key] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+
+    # ---- BASELINE configs[4]: the fine-tune step with the data-parallel gradient all-reduce, on EVERY rank of this launch (so the driver's
+    # 1/2/4/8-GPU runs each carry a DDP number; the headline line above is unaffected by a failure here)
+    train = None
+    if not args.quick and not args.no_train_leg:
+        del fm, model
+        torch.cuda.empty_cache()
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_train
+            train = bench_train.run_leg(batch=16, size=640, steps=4, warmup=2, by_symbol=False)
+            train = {k: train[k] for k in ("value", "unit", "n_gpus", "ms_per_step", "steps", "warmup", "scaling", "dtype", "config", "kernel_launches_per_step", "phases_ms", "peak_mem_GB")}
+        except Exception as e:  # noqa: BLE001
+            train = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
 
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
-            cv, cms = cpu_reference_run(2, 2, 1, sd, cpu_threads)
-            cpu = {"value": cv, "unit": "images/s", "cores": cpu_threads, "host_cores": cores, "kind": "port", "sample": "2 timed passes of batch 2 (oracle port of the reference's torch fp32 CPU forward + post-process)"}
+            cv, cms = cpu_reference_run(2, 6, 1, sd, cpu_threads)
+            cpu = {"value": cv, "unit": "images/s", "cores": cpu_threads, "host_cores": cores, "kind": "port", "sample": "6 timed passes of batch 2 after 1 warm-up (oracle port of the reference's torch fp32 CPU forward + post-process)"}
         line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"fp16": "f16", "fp32": "f32", "fp32_tc": "f32 (3x f16 tensor-core products)"}[args.precision], "data": "synthetic",
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": {"fp16": "f16", "fp32": "f32", "fp32_tc": "f32 (storage and accumulation; every conv/linear product = 3 f16 tcgen05 products, error ~2^-21)"}[args.precision], "data": "synthetic",
+                "parity": {"fp32_tc": "meets north_star: identical query sets and (class, int box) keep-sets, boxes/scores < 1e-3 (tests/test_gpu_e2e.py::test_fp32_tc_meets_the_parity_bars, profiles/r02_error_budget.md)",
+                           "fp32": "meets north_star (CUDA-core fp32 mode)", "fp16": "outside north_star's bars (profiles/r02_error_budget.md)"}[args.precision],
                 "config": config, "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
-                "cuda_graph": graph is not None, "latency_bs1": lat, "parity_mode": par, "other_configs": other, "roofline": roof, "cpu_baseline": cpu, "detections_img0": len(dets[0])}
+                "cuda_graph": graph is not None, "latency_bs1": lat, "fast_mode": fast, "other_configs": other, "train_config5": train, "roofline": roof, "cpu_baseline": cpu, "detections_img0": len(dets[0])}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -210,6 +210,44 @@ __global__ void __launch_bounds__(TOPK_THREADS) detr_postprocess_kernel(const fl
   if (threadIdx.x == 0) out_count[b] = cnt;
 }
 
+// Evaluator post-process (fai_detr/processor.py:121-144 + detector_postprocess :19-57): per image top-k over the flattened [Q*C] scores (NO threshold),
+// label / query decode, boxes scaled to the dataset entry's (height, width) as FLOATS, clipped to the image, empty boxes dropped; the survivors are
+// written compacted in descending-score order.  One CTA per image.
+__global__ void __launch_bounds__(TOPK_THREADS) detr_eval_postprocess_kernel(const float* __restrict__ scores, const float* __restrict__ boxes,
+                                                                             const int* __restrict__ sizes, int Q, int C, int K,
+                                                                             float* __restrict__ out_scores, int* __restrict__ out_labels,
+                                                                             float* __restrict__ out_boxes, int* __restrict__ out_count) {
+  __shared__ TopkSmem s;
+  __shared__ int warp_tot[TOPK_THREADS / 32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  topk_block(scores + (int64_t)b * Q * C, Q * C, K, s);
+  const float Wimg = (float)sizes[b * 2 + 1], Himg = (float)sizes[b * 2 + 0];
+  // K <= TOPK_MAXK = TOPK_THREADS: one candidate per thread
+  float sc = 0.f; int label = 0; float4 bx = make_float4(0.f, 0.f, 0.f, 0.f); int keep = 0;
+  if (tid < K) {
+    const unsigned long long c = s.cand[tid];
+    const int flat = (int)(0xffffffffu - (uint32_t)(c & 0xffffffffull));
+    sc = key2f((uint32_t)(c >> 32));
+    label = flat % C;
+    bx = reinterpret_cast<const float4*>(boxes)[(int64_t)b * Q + flat / C];
+    bx.x = fminf(fmaxf(bx.x * Wimg, 0.f), Wimg); bx.z = fminf(fmaxf(bx.z * Wimg, 0.f), Wimg);   // Boxes.scale then Boxes.clip
+    bx.y = fminf(fmaxf(bx.y * Himg, 0.f), Himg); bx.w = fminf(fmaxf(bx.w * Himg, 0.f), Himg);
+    keep = (bx.z - bx.x > 0.f) && (bx.w - bx.y > 0.f);                                          // Boxes.nonempty(threshold=0)
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, keep);
+  if (lane == 0) warp_tot[warp] = __popc(m);
+  __syncthreads();
+  int base = 0, total = 0;
+  for (int w = 0; w < TOPK_THREADS / 32; ++w) { if (w < warp) base += warp_tot[w]; total += warp_tot[w]; }
+  if (keep) {
+    const int64_t o = (int64_t)b * K + base + __popc(m & ((1u << lane) - 1u));
+    out_scores[o] = sc;
+    out_labels[o] = label;
+    reinterpret_cast<float4*>(out_boxes)[o] = bx;
+  }
+  if (tid == 0) out_count[b] = total;
+}
+
 static inline unsigned grid_for(int64_t total, int threads) {
   int64_t g = cdiv(total, threads);
   const int64_t cap = 148LL * 32;
@@ -259,6 +297,15 @@ extern "C" int fb200_box_op(int mode, const float* x, const float* ref, const in
   const int64_t work = (mode == 3) ? n / 4 : n;
   box_op_kernel<<<(unsigned)cdiv(work, 256), 256, 0, (cudaStream_t)stream>>>(mode, x, ref, idx, out, work);
   FB_CHECK_LAUNCH("box_op");
+  return FB200_OK;
+}
+
+extern "C" int fb200_detr_eval_postprocess(const float* scores, const float* boxes, const int* sizes, int B, int Q, int C, int K, float* out_scores,
+                                           int* out_labels, float* out_boxes, int* out_count, void* stream) {
+  FB_CHECK_ARG(scores && boxes && sizes && out_scores && out_labels && out_boxes && out_count, "detr_eval_postprocess: null pointer");
+  FB_CHECK_ARG(B > 0 && K >= 1 && K <= TOPK_MAXK && (int64_t)K <= (int64_t)Q * C, "detr_eval_postprocess: bad K=%d", K);
+  detr_eval_postprocess_kernel<<<B, TOPK_THREADS, 0, (cudaStream_t)stream>>>(scores, boxes, sizes, Q, C, K, out_scores, out_labels, out_boxes, out_count);
+  FB_CHECK_LAUNCH("detr_eval_postprocess");
   return FB200_OK;
 }
 

@@ -67,7 +67,7 @@ EXPORTED_SYMBOLS = (
     "fb200_split_f32_pair",
     "fb200_maxpool3x3s2", "fb200_avgpool2x2_ceil", "fb200_resize_bilinear", "fb200_add", "fb200_layernorm",
     "fb200_attention", "fb200_attention_split", "fb200_msda", "fb200_row_select", "fb200_rowmax", "fb200_topk", "fb200_gather_rows",
-    "fb200_box_op", "fb200_detr_postprocess",
+    "fb200_box_op", "fb200_detr_postprocess", "fb200_detr_eval_postprocess",
 )
 
 _launch_count = 0
@@ -247,6 +247,12 @@ class CudaBackend:
         B, Q, C = scores.shape
         self._call("fb200_detr_postprocess", _p(scores), _p(boxes), _p(sizes), B, Q, C, K, ctypes.c_float(thr), _p(out_scores), _p(out_labels),
                    _p(out_boxes), _p(out_query), _p(out_count), _stream())
+
+
+    def detr_eval_postprocess(self, scores, boxes, sizes, K, out_scores, out_labels, out_boxes, out_count):
+        self._cuda(scores, boxes, sizes)
+        B, Q, C = scores.shape
+        self._call("fb200_detr_eval_postprocess", _p(scores), _p(boxes), _p(sizes), B, Q, C, K, _p(out_scores), _p(out_labels), _p(out_boxes), _p(out_count), _stream())
 
 
 _cuda_backend = None
@@ -510,6 +516,18 @@ def detr_postprocess(scores, boxes, sizes_i32, top_k: int, threshold: float):
     o_c = torch.empty((B,), dtype=torch.int32, device=dev)
     _be().detr_postprocess(scores.contiguous(), boxes.contiguous(), sizes_i32, top_k, float(threshold), o_s, o_l, o_b, o_q, o_c)
     return o_s, o_l, o_b, o_q, o_c
+
+
+def detr_eval_postprocess(scores, boxes, sizes_i32, top_k: int):
+    """evaluator variant: -> (scores [B,K], labels [B,K] i32, boxes [B,K,4] fp32 in pixels of sizes[b], count [B] i32); rows [0, count[b]) are valid"""
+    B = scores.shape[0]
+    dev = scores.device
+    o_s = torch.empty((B, top_k), dtype=torch.float32, device=dev)
+    o_l = torch.empty((B, top_k), dtype=torch.int32, device=dev)
+    o_b = torch.empty((B, top_k, 4), dtype=torch.float32, device=dev)
+    o_c = torch.empty((B,), dtype=torch.int32, device=dev)
+    _be().detr_eval_postprocess(scores.contiguous(), boxes.contiguous(), sizes_i32, top_k, o_s, o_l, o_b, o_c)
+    return o_s, o_l, o_b, o_c
 
 
 # ------------------------------------------------------------------------------------------------

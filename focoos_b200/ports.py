@@ -48,6 +48,48 @@ class FocoosDetections:
         return len(self.detections)
 
 
+class Boxes:
+    """structures.py `Boxes`: an [N, 4] xyxy tensor (only what the evaluators read)."""
+
+    def __init__(self, tensor: torch.Tensor):
+        self.tensor = tensor
+
+    def __len__(self):
+        return int(self.tensor.shape[0])
+
+    def to(self, *a, **k):
+        return Boxes(self.tensor.to(*a, **k))
+
+
+class Instances:
+    """structures.py `Instances`: per-image prediction container with `image_size` = (height, width) and per-instance fields
+    (`boxes: Boxes`, `scores`, `classes`), as consumed by the evaluators (trainer/evaluation/*)."""
+
+    def __init__(self, image_size, **fields_):
+        self.image_size = tuple(image_size)
+        self._fields = dict(fields_)
+
+    def __getattr__(self, name):
+        f = self.__dict__.get("_fields", {})
+        if name in f:
+            return f[name]
+        raise AttributeError(name)
+
+    def has(self, name):
+        return name in self._fields
+
+    def get_fields(self):
+        return self._fields
+
+    def __len__(self):
+        for v in self._fields.values():
+            return len(v)
+        return 0
+
+    def to(self, *a, **k):
+        return Instances(self.image_size, **{n: (v.to(*a, **k) if hasattr(v, "to") else v) for n, v in self._fields.items()})
+
+
 @dataclass
 class ResnetConfig:
     """nn/backbone/resnet.py:152-161."""

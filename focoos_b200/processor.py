@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .ports import DETRConfig, DETRModelOutput, FocoosDet, FocoosDetections
+from .ports import Boxes, DETRConfig, DETRModelOutput, FocoosDet, FocoosDetections, Instances
 
 
 def get_image_sizes(inputs) -> List[Tuple[int, int]]:
@@ -142,6 +142,23 @@ class DETRProcessor:
         assert len(image_sizes) == B, f"Expected image sizes {len(image_sizes)} to match batch size {B}"
         # one packed D2H copy: [B, K, 7] (score bits, label, 4 box coords, query) + counts
         return self.detections_from_packed(self.postprocess_packed(output, image_sizes, top_k, threshold).cpu().numpy(), class_names)
+
+    def eval_postprocess(self, output: DETRModelOutput, batched_inputs, top_k: Optional[int] = None):
+        """fai_detr/processor.py:121-144 (the evaluator path, trainer/evaluation/evaluator.py:179-190): per image top-k WITHOUT threshold, boxes scaled
+        to the dataset entry's (height, width), clipped, empty ones dropped -> [{"instances": Instances(boxes, scores, classes)}].
+        ONE kernel for the whole batch (the reference loops over images in Python) and one tiny D2H (the per-image counts); the instance tensors
+        stay on the device, as the reference's do.  `batched_inputs[i]` needs `.height` / `.width` (DatasetEntry) or the same dict keys."""
+        top_k = top_k or self.top_k
+        def hw(e):
+            h = e.get("height") if isinstance(e, dict) else getattr(e, "height", None)
+            w = e.get("width") if isinstance(e, dict) else getattr(e, "width", None)
+            return (int(h or 1), int(w or 1))  # `or 1` as the reference
+        sizes = [hw(e) for e in batched_inputs]
+        assert len(sizes) == output.logits.shape[0]
+        sizes_dev = torch.tensor(sizes, dtype=torch.int32).to(output.logits.device, non_blocking=True)
+        s, l, b, c = ops.detr_eval_postprocess(output.logits, output.boxes, sizes_dev, top_k)
+        counts = c.cpu().tolist()
+        return [{"instances": Instances(sizes[i], boxes=Boxes(b[i, :n]), scores=s[i, :n], classes=l[i, :n].long())} for i, n in enumerate(counts)]
 
     def export_postprocess(self, output, inputs, class_names=(), top_k=None, threshold: float = 0.5):
         """processor.py:219-236: output = (boxes, logits) of an exported graph."""

@@ -161,6 +161,14 @@ int fb200_detr_postprocess(const float* scores, const float* boxes, const int* s
                            float threshold, float* out_scores, int* out_labels, int* out_boxes, int* out_query,
                            int* out_count, void* stream);
 
+/* ---- f3: evaluator post-process -----------------------------------------------------------------
+ * Replaces DETRProcessor.eval_postprocess + detector_postprocess (models/fai_detr/processor.py:19-57,121-144; called per batch from
+ * trainer/evaluation/evaluator.py:179-190): per image top-K over the flattened [Q*C] scores WITHOUT threshold, label = i % C, query = i / C,
+ * xyxy boxes scaled to sizes[b] = (height, width) of the dataset entry as floats, clipped to the image, empty boxes dropped.
+ * Outputs are compacted per image in descending-score order: out_scores/out_labels [B,K], out_boxes [B,K,4] fp32, out_count [B]. */
+int fb200_detr_eval_postprocess(const float* scores, const float* boxes, const int* sizes, int B, int Q, int C, int K, float* out_scores,
+                                int* out_labels, float* out_boxes, int* out_count, void* stream);
+
 /* ======== MaskFormer family (focoos/models/fai_mf/{modelling,processor}.py) ======================== */
 
 /* out = cur + F.interpolate(y, size=(H,W), mode="nearest")   TransformerFPN top-down path (fai_mf/modelling.py:364).

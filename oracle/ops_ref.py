@@ -156,6 +156,24 @@ class RefBackend:
             out_count[b] = int((v > thr).sum())
 
 
+    def detr_eval_postprocess(self, scores, boxes, sizes, K, out_scores, out_labels, out_boxes, out_count):
+        """fai_detr/processor.py:121-144 + detector_postprocess :19-57 per image (top-k, scale, clip, drop empty boxes), compacted."""
+        B, Q, C = scores.shape
+        for b in range(B):
+            v, i = torch.sort(scores[b].flatten(), descending=True, stable=True)
+            v, i = v[:K], i[:K]
+            bx = boxes[b][i // C].clone()
+            H, W = float(sizes[b, 0]), float(sizes[b, 1])
+            bx[:, 0::2] = (bx[:, 0::2] * W).clamp(0, W)
+            bx[:, 1::2] = (bx[:, 1::2] * H).clamp(0, H)
+            keep = ((bx[:, 2] - bx[:, 0]) > 0) & ((bx[:, 3] - bx[:, 1]) > 0)
+            n = int(keep.sum())
+            out_scores[b, :n] = v[keep]
+            out_labels[b, :n] = (i % C)[keep].to(torch.int32)
+            out_boxes[b, :n] = bx[keep]
+            out_count[b] = n
+
+
 # ---- MaskFormer-family operators (same signatures as the CudaBackend extensions in focoos_b200/ops.py) -------------------
 def _ref_upsample_nearest_add(self, y, cur, out):
     up = F.interpolate(y.float().permute(0, 3, 1, 2), size=(cur.shape[1], cur.shape[2]), mode="nearest").permute(0, 2, 3, 1)

@@ -22,35 +22,29 @@ from focoos_b200.train_step import FlatAdamW, GradBucketReducer, TrainStep, get_
 from focoos_b200.utils.seeded_weights import desaturate_classifiers, seeded_state_dict  # noqa: E402
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--batch", type=int, default=16)
-    ap.add_argument("--size", type=int, default=640)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=2)
-    ap.add_argument("--precision", default="fp32_tc", choices=["fp32", "fp32_tc"])
-    args = ap.parse_args()
+def run_leg(batch=16, size=640, steps=5, warmup=2, precision="fp32_tc", by_symbol=True, sync_bn=None):
+    """One fine-tune leg on the ALREADY-INITIALISED process group (every rank calls it); returns the result dict on every rank."""
     rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
-    torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    D.init_from_env("nccl", dev)
     cfg = DETRConfig(num_classes=80)
-    m = FAIDetr(cfg, precision=args.precision)
+    m = FAIDetr(cfg, precision=precision)
     m.load_state_dict(desaturate_classifiers(seeded_state_dict(m.state_dict(), seed=0)), strict=True)  # same parameters on every rank
     m.to(dev).train()
+    if sync_bn is not None and hasattr(m, "sync_bn"):
+        m.sync_bn = bool(sync_bn)
     opt = FlatAdamW(get_optimizer_params(m, base_lr=5e-4, weight_decay=0.02, weight_decay_norm=0.0, backbone_multiplier=0.1), clip_gradients=0.1, amp=True, world_size=world)
     opt.track_unused_parameters()
     red = GradBucketReducer(opt)
     red.attach_hooks()
     step = TrainStep(m, opt, red)
     g = torch.Generator().manual_seed(4 + rank)  # SURVEY 8(d).5: seed 4 + rank
-    x = torch.randint(0, 256, (args.batch, 3, args.size, args.size), generator=g).float().to(dev)
+    x = torch.randint(0, 256, (batch, 3, size, size), generator=g).float().to(dev)
     targets = []
-    for _ in range(args.batch):
+    for _ in range(batch):
         n = int(torch.randint(1, 21, (1,), generator=g))
         box = torch.cat([0.2 + 0.6 * torch.rand((n, 2), generator=g), 0.05 + 0.30 * torch.rand((n, 2), generator=g)], 1)
         targets.append(DETRTargets(labels=torch.randint(0, 80, (n,), generator=g).to(dev), boxes=box.to(dev)))
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step(x, targets)
     torch.cuda.synchronize()
     if world > 1:
@@ -59,12 +53,12 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.reset_peak_memory_stats()
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         losses = step(x, targets)
     e1.record()
     torch.cuda.synchronize()
-    ms = D.max_over_ranks(e0.elapsed_time(e1) / args.steps, dev)
-    launches = (ops.launch_count() - l0) // args.steps
+    ms = D.max_over_ranks(e0.elapsed_time(e1) / steps, dev)
+    launches = (ops.launch_count() - l0) // steps
     # one more step, phase by phase
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
     opt.zero_grad()
@@ -81,7 +75,7 @@ def main():
     phases = {k: ev[i].elapsed_time(ev[i + 1]) for i, k in enumerate(["forward_and_criterion_ms", "backward_ms", "exchange_tail_ms", "optimizer_ms"])}
     # per-symbol device time of one more step (CUDA events around every C-ABI call; torch glue = the remainder)
     by_sym = {}
-    if os.environ.get("FB200_TRACE", "1") == "1":
+    if by_symbol and os.environ.get("FB200_TRACE", "1") == "1":
         tr = ops.enable_trace(True)
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
@@ -97,11 +91,32 @@ def main():
         by_sym["_step_total_ms"] = t0.elapsed_time(t1)
         by_sym["_kernels_ms"] = round(sum(v["ms"] for k, v in by_sym.items() if isinstance(v, dict)), 3)
     total = float(sum(v.detach() for v in losses.values()))
+    res = {"metric": "images/sec fai-detr-l fine-tune step (fwd + criterion + bwd + all-reduce + AdamW)", "value": batch * world / (ms / 1e3), "unit": "images/s",
+           "n_gpus": world, "ms_per_step": ms, "steps": steps, "warmup": warmup, "scaling": "weak", "dtype": "f32 storage; " + ("3x f16 tcgen05 products for conv/linear forward, data and weight gradients" if precision == "fp32_tc" else "SIMT f32"),
+           "config": {"workload": f"fai-detr-l (80 classes) bs={batch}/GPU {size}x{size} synthetic COCO-shape targets (BASELINE configs[4])", "global_batch": batch * world,
+                      "sync_bn": bool(getattr(m, "sync_bn", False)) and world > 1},
+           "kernel_launches_per_step": launches, "phases_ms": phases, "peak_mem_GB": torch.cuda.max_memory_allocated() / 1e9, "loss_total": total, "optimizer": opt.stats(), "by_symbol": by_sym}
+    red.detach_hooks() if hasattr(red, "detach_hooks") else None
+    del step, red, opt, m, x, targets
+    torch.cuda.empty_cache()
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--size", type=int, default=640)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--precision", default="fp32_tc", choices=["fp32", "fp32_tc"])
+    ap.add_argument("--no-sync-bn", action="store_true")
+    args = ap.parse_args()
+    rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    torch.cuda.set_device(local)
+    D.init_from_env("nccl", torch.device("cuda", local))
+    res = run_leg(args.batch, args.size, args.steps, args.warmup, args.precision, sync_bn=False if args.no_sync_bn else None)
     if rank == 0:
-        print(json.dumps({"metric": "images/sec fai-detr-l fine-tune step (fwd + criterion + bwd + all-reduce + AdamW)", "value": args.batch * world / (ms / 1e3), "unit": "images/s",
-                          "n_gpus": world, "ms_per_step": ms, "steps": args.steps, "warmup": args.warmup, "scaling": "weak", "dtype": "f32 storage; " + ("3x f16 tcgen05 products for conv/linear forward, data and weight gradients" if args.precision == "fp32_tc" else "SIMT f32"),
-                          "config": {"workload": f"fai-detr-l (80 classes) bs={args.batch}/GPU {args.size}x{args.size} synthetic COCO-shape targets (BASELINE configs[4])", "global_batch": args.batch * world},
-                          "kernel_launches_per_step": launches, "phases_ms": phases, "peak_mem_GB": torch.cuda.max_memory_allocated() / 1e9, "loss_total": total, "optimizer": opt.stats(), "by_symbol": by_sym}))
+        print(json.dumps(res))
     if world > 1:
         dist.destroy_process_group()
 

@@ -4,7 +4,7 @@ log=$1; shift
 for i in $(seq 1 20); do
   /usr/local/graft/bin/gpurun "$@" > "$log" 2>&1
   rc=$?
-  if ! grep -q "status=transient" "$log"; then exit $rc; fi
+  if ! grep -q "nothing was charged" "$log"; then exit $rc; fi
   sleep 90
 done
 exit 3
