@@ -196,6 +196,28 @@ class FocoosModel:
         while q:
             yield q.popleft().result()
 
+    # ---- export / train / eval (focoos_model.py:418-573, 221-275, 276-310) ------------------------------------------------------------
+    def export(self, runtime_type="torchscript_32", onnx_opset: int = 18, out_dir: Optional[str] = None, device: str = "auto", simplify_onnx: bool = True,
+               overwrite: bool = True, image_size=None, dynamic_axes: bool = True):
+        """focoos_model.py:418-573 for the TorchScript runtimes: `torch.jit.trace(ExportableModel)` -> `<out_dir>/model.pt` + `model_info.json`, returns an
+        InferModel serving the file.  The traced graph is one `focoos_b200::model_forward` operator over the module's own weights (focoos_b200/export.py);
+        reloading it reproduces the eager outputs bit for bit.  ONNX / TensorRT runtime types raise ValueError (the reference's other backends)."""
+        from .export import export_model
+        dev = ("cuda" if torch.cuda.is_available() else "cpu") if device == "auto" else device
+        return export_model(self, runtime_type, out_dir, dev, overwrite, image_size)
+
+    def train(self, args, data_train, data_val=None, hub=None):
+        """focoos_model.py:221-275: fine-tune on `data_train` (single process, or `args.num_gpus` processes with the NCCL gradient exchange), write
+        `<output_dir>/<run_name>/model_final.pth` + `model_info.json`, reload the trained weights and return to eval mode."""
+        from .trainer import run_train_entry
+        assert hub is None, "Focoos Hub sync is outside the B200 hot path"
+        return run_train_entry(self, args, data_train, data_val)
+
+    def eval(self, args, data_test, save_json: bool = True):
+        """focoos_model.py:276-310: `inference_on_dataset` with `processor.eval_postprocess` and the detection evaluator; returns the metrics dict."""
+        from .trainer import run_eval_entry
+        return run_eval_entry(self, args, data_test, save_json)
+
     def infer(self, image, threshold: Optional[float] = None) -> FocoosDetections:
         """focoos_model.py:370: single image (ndarray HWC uint8 / PIL / tensor) -> FocoosDetections."""
         return self(image, threshold=threshold)

@@ -206,9 +206,17 @@ class GradBucketReducer:
     contiguous slices of the flat gradient buffer.  Buckets follow reverse parameter order (the order backward fills them) and
     never split a tensor; the 1/world averaging is folded into FlatAdamW's gradient multiplier, not a separate pass."""
 
-    def __init__(self, opt: FlatAdamW, bucket_bytes: int = 25 << 20, group=None):
+    def __init__(self, opt: FlatAdamW, bucket_bytes: int = 25 << 20, group=None, model: Optional[nn.Module] = None, broadcast: bool = True):
         self.opt, self.group = opt, group
         self.enabled = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        if self.enabled and broadcast:
+            # DistributedDataParallel's constructor broadcasts rank 0's parameters and buffers (dist.py:152): replicas start identical even if the
+            # caller seeded them differently, and BatchNorm running statistics do not diverge from step 0
+            dist.broadcast(opt.flat_params, src=0, group=group)
+            if model is not None:
+                for b in model.buffers():
+                    if b.is_floating_point() or b.dtype in (torch.int64, torch.int32):
+                        dist.broadcast(b, src=0, group=group)
         ends = opt.offsets[1:] + [opt.total]
         self.buckets: List[List[int]] = []  # [start, end, first_seg, last_seg]
         cur_end, cur_start, last = opt.total, opt.total, len(opt.offsets) - 1
@@ -224,12 +232,18 @@ class GradBucketReducer:
         self._pending = [0] * len(self.buckets)
         self._handles = []
         self._hooks = []
+        self._static_unused = None  # learnt at the first finish(): tensors backward never reaches (e.g. fai-detr's dead mask_features conv)
         self.reset()
 
     def reset(self):
         self._pending = [hi - lo + 1 for _, _, lo, hi in self.buckets]
         self._launched = [False] * len(self.buckets)
+        self._seen = [False] * len(self.opt.offsets)
+        self._next = 0  # buckets go out STRICTLY in index order on every rank: collectives must be issued in the same order everywhere
         self._handles = []
+        for seg in (self._static_unused or ()):  # structurally unused tensors count as ready from the start, or they would hold every later bucket back
+            self._seen[seg] = True
+            self._pending[self.seg_bucket[seg]] -= 1
 
     def _launch(self, b: int):
         if self._launched[b]:
@@ -241,17 +255,35 @@ class GradBucketReducer:
 
     def mark_ready(self, seg: int):
         b = self.seg_bucket[seg]
+        if self._seen[seg]:
+            if self._launched[b]:  # (also: a tensor learnt as unused that now received a gradient after its bucket left)  # a second backward before finish(): its gradient would be added onto an already-summed slice
+                raise RuntimeError("GradBucketReducer: gradient accumulated into a bucket that was already exchanged - call finish() after every backward")
+            return
+        self._seen[seg] = True
         self._pending[b] -= 1
-        if self._pending[b] == 0:
-            self._launch(b)
+        # a bucket may only go out once every earlier bucket has: a parameter that is unused on ONE rank must not reorder that rank's collectives
+        while self._next < len(self.buckets) and self._pending[self._next] == 0:
+            self._launch(self._next)
+            self._next += 1
 
     def attach_hooks(self):
         """overlap with backward: each parameter's post-accumulate hook marks its slice ready; full buckets go out immediately."""
         for i, p in enumerate(self.opt.params):
             self._hooks.append(p.register_post_accumulate_grad_hook(lambda _p, i=i: self.mark_ready(i)))
 
+    def detach_hooks(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+        for h in self.opt._hooks:
+            h.remove()
+        self.opt._hooks = []
+        self.opt._fired = None
+
     def finish(self):
         """launch whatever backward did not touch (unused parameters keep zero gradients) and wait for every bucket."""
+        if self._static_unused is None and self._hooks:
+            self._static_unused = {i for i, seen in enumerate(self._seen) if not seen}
         for b in range(len(self.buckets)):
             self._launch(b)
         for h in self._handles:

@@ -168,11 +168,25 @@ def test_bucket_layout_and_unused_parameter_tracking(ref_backend):
     x, y = torch.randn(4, 7), torch.randn(4, 3)
     opt.zero_grad()
     ((m(x) - y) ** 2).mean().backward()
-    full = {b for b, (_, _, lo, hi) in enumerate(red.buckets) if not any(opt.names[i].startswith("dead") for i in range(lo, hi + 1))}
-    assert full and full.issubset(set(launched)), "every bucket whose tensors ALL received gradients is launched from the hooks, before finish()"
-    assert not (set(range(len(red.buckets))) - full) & set(launched), "a bucket holding an unused tensor waits for finish()"
+    # first pass: collectives go out STRICTLY in bucket order on every rank, so the unused tensors (the LAST parameters = bucket 0) hold everything back
+    # until finish(); finish() learns which tensors are structurally unused ...
+    assert launched == [], launched
     red.finish()
+    assert launched == list(range(len(red.buckets))), "finish() launches in index order"
+    assert red._static_unused == {i for i, n in enumerate(opt.names) if n.startswith("dead")}
     opt.step()
+    # ... and from the second pass on they count as ready: every bucket leaves from the hooks, in order, overlapped with backward
+    launched.clear()
+    opt.zero_grad()
+    ((m(x) - y) ** 2).mean().backward()
+    assert launched == list(range(len(red.buckets))), launched
+    with pytest.raises(RuntimeError):  # a second backward before finish() would add onto already-exchanged slices
+        ((m(x) - y) ** 2).mean().backward()
+    red.reset()
+    opt.zero_grad()
+    ((m(x) - y) ** 2).mean().backward()
+    red.finish()
+    before = before.clone()
     for i, n in enumerate(opt.names):
         o, cnt = opt.offsets[i], opt.params[i].numel()
         moved = not torch.equal(before[o:o + cnt], opt.flat_params[o:o + cnt])
