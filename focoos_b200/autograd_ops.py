@@ -27,7 +27,7 @@ from . import ops
 from .ops import CudaBackend, _p, _stream
 
 ops.EXPORTED_SYMBOLS = ops.EXPORTED_SYMBOLS + (
-    "fb200_conv_wgrad_workspace_bytes", "fb200_conv_wgrad", "fb200_conv_wgrad_tc_supported", "fb200_conv_wgrad_tc_workspace_bytes", "fb200_conv_wgrad_tc", "fb200_dilate2", "fb200_col_workspace_bytes", "fb200_colsum", "fb200_bn_train_fwd", "fb200_bn_train_bwd",
+    "fb200_conv_wgrad_workspace_bytes", "fb200_conv_wgrad", "fb200_conv_wgrad_tc_supported", "fb200_conv_wgrad_tc_workspace_bytes", "fb200_conv_wgrad_tc", "fb200_dilate2", "fb200_col_workspace_bytes", "fb200_colsum", "fb200_bn_train_fwd", "fb200_bn_train_bwd", "fb200_bn_stats", "fb200_bn_apply", "fb200_bn_bwd_reduce", "fb200_bn_bwd_apply",
     "fb200_add_act", "fb200_maxpool3x3s2_bwd", "fb200_avgpool2x2_ceil_bwd", "fb200_resize_bilinear_bwd", "fb200_layernorm_bwd", "fb200_attention_bwd", "fb200_msda_bwd")
 
 _f = ctypes.c_float
@@ -94,6 +94,33 @@ def _cb_bn_train_bwd(self, x2d, dy2d, y2d, gamma, beta, save_mean, save_rstd, ac
                _p(_col_ws(self, C, x2d.device)), _stream())
 
 
+def _cb_bn_stats(self, x2d, mean, var):
+    self._cuda(x2d, mean, var)
+    R, C = x2d.shape
+    self._call("fb200_bn_stats", _p(x2d), x2d.stride(0), ctypes.c_int64(R), C, _p(mean), _p(var), _p(_col_ws(self, C, x2d.device)), _stream())
+
+
+def _cb_bn_apply(self, x2d, mean, rstd, gamma, beta, res2d, act, y2d):
+    self._cuda(x2d, mean, rstd, gamma, beta, y2d)
+    R, C = x2d.shape
+    self._call("fb200_bn_apply", _p(x2d), x2d.stride(0), ctypes.c_int64(R), C, _p(mean), _p(rstd), _p(gamma), _p(beta), _p(res2d), 0 if res2d is None else res2d.stride(0), act,
+               _p(y2d), y2d.stride(0), _stream())
+
+
+def _cb_bn_bwd_reduce(self, x2d, dy2d, y2d, gamma, beta, mean, rstd, act, sum_dy, sum_dy_xhat):
+    self._cuda(x2d, dy2d, sum_dy, sum_dy_xhat)
+    R, C = x2d.shape
+    self._call("fb200_bn_bwd_reduce", _p(x2d), x2d.stride(0), _p(dy2d), dy2d.stride(0), _p(y2d), 0 if y2d is None else y2d.stride(0), ctypes.c_int64(R), C, _p(gamma), _p(beta),
+               _p(mean), _p(rstd), act, _p(sum_dy), _p(sum_dy_xhat), _p(_col_ws(self, C, x2d.device)), _stream())
+
+
+def _cb_bn_bwd_apply(self, x2d, dy2d, y2d, gamma, beta, mean, rstd, sum_dy, sum_dy_xhat, inv_count, act, dx2d, dres2d):
+    self._cuda(x2d, dy2d, dx2d)
+    R, C = x2d.shape
+    self._call("fb200_bn_bwd_apply", _p(x2d), x2d.stride(0), _p(dy2d), dy2d.stride(0), _p(y2d), 0 if y2d is None else y2d.stride(0), ctypes.c_int64(R), C, _p(gamma), _p(beta),
+               _p(mean), _p(rstd), _p(sum_dy), _p(sum_dy_xhat), _f(inv_count), act, _p(dx2d), dx2d.stride(0), _p(dres2d), 0 if dres2d is None else dres2d.stride(0), _stream())
+
+
 def _cb_add_act(self, a, b, dy, act, out):
     self._cuda(a, out)
     self._call("fb200_add_act", _p(a), _p(b), _p(dy), act, ctypes.c_int64(a.numel()), _p(out), _stream())
@@ -141,6 +168,7 @@ def _cb_msda_bwd(self, value, oa, ref, do, shapes, P, heads, dvalue, doa):
 
 
 for _n, _fn in (("conv_wgrad", _cb_conv_wgrad), ("conv_wgrad_tc_supported", _cb_conv_wgrad_tc_supported), ("conv_wgrad_tc", _cb_conv_wgrad_tc), ("dilate2", _cb_dilate2), ("colsum", _cb_colsum), ("bn_train_fwd", _cb_bn_train_fwd), ("bn_train_bwd", _cb_bn_train_bwd),
+                ("bn_stats", _cb_bn_stats), ("bn_apply", _cb_bn_apply), ("bn_bwd_reduce", _cb_bn_bwd_reduce), ("bn_bwd_apply", _cb_bn_bwd_apply),
                 ("add_act", _cb_add_act), ("maxpool_bwd", _cb_maxpool_bwd), ("avgpool_bwd", _cb_avgpool_bwd), ("resize_bwd", _cb_resize_bwd),
                 ("layernorm_bwd", _cb_layernorm_bwd), ("attention_bwd", _cb_attention_bwd), ("msda_bwd", _cb_msda_bwd)):
     setattr(CudaBackend, _n, _fn)
@@ -279,6 +307,91 @@ class BatchNormTrainFn(torch.autograd.Function):
         ops._be().bn_train_bwd(x.reshape(-1, C), dy.reshape(-1, C), None if y is None else y.reshape(-1, C), gamma, beta, mean, rstd, act, dx.reshape(-1, C),
                                None if dres is None else dres.reshape(-1, C), dgamma, dbeta)
         return dx, dgamma, dbeta, None, None, dres, None, None, None
+
+
+class SyncBatchNormTrainFn(torch.autograd.Function):
+    """BatchNormTrainFn with the statistics taken over ALL data-parallel ranks - what torch.nn.SyncBatchNorm (trainer/trainer.py:334) computes:
+    forward: local mean / biased variance -> all_gather with the local row counts -> combined mean / variance (aten batch_norm_gather_stats_with_counts);
+    backward: local sum(g), sum(g * xhat) -> all_reduce -> dx with the global sums over the global row count; dgamma / dbeta stay LOCAL (the gradient
+    exchange sums them like every other parameter gradient).  Two small collectives per layer and pass; everything else is the single-GPU kernels."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, res, act, eps, momentum, group):
+        import torch.distributed as dist
+        x = x.contiguous()
+        C = x.shape[-1]
+        x2 = x.reshape(-1, C)
+        be = ops._be()
+        stats = torch.empty((2 * C + 1,), dtype=torch.float32, device=x.device)
+        be.bn_stats(x2, stats[:C], stats[C:2 * C])
+        stats[2 * C] = float(x2.shape[0])
+        world = dist.get_world_size(group)
+        allst = torch.empty((world * (2 * C + 1),), dtype=torch.float32, device=x.device)
+        dist.all_gather_into_tensor(allst, stats, group=group)
+        allst = allst.view(world, 2 * C + 1)
+        n = allst[:, 2 * C:2 * C + 1]                                  # [world, 1]
+        total = n.sum()
+        mean = (allst[:, :C] * n).sum(0) / total
+        var = ((allst[:, C:2 * C] + (allst[:, :C] - mean) ** 2) * n).sum(0) / total
+        rstd = torch.rsqrt(var + eps)
+        with torch.no_grad():  # running statistics: unbiased variance over the GLOBAL count
+            running_mean.mul_(1 - momentum).add_(mean, alpha=momentum)
+            running_var.mul_(1 - momentum).add_(var * (total / (total - 1).clamp(min=1)), alpha=momentum)
+        y = torch.empty_like(x)
+        r2 = None if res is None else res.contiguous().reshape(-1, C)
+        be.bn_apply(x2, mean, rstd, gamma, beta, r2, act, y.reshape(-1, C))
+        ctx.save_for_backward(x, gamma, beta, mean, rstd, y if (act != ops.ACT_NONE and res is not None) else None)
+        ctx.cfg = (act, res is not None, group, float(total))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        import torch.distributed as dist
+        x, gamma, beta, mean, rstd, y = ctx.saved_tensors
+        act, has_res, group, total = ctx.cfg
+        C = x.shape[-1]
+        dy = dy.contiguous()
+        be = ops._be()
+        sums = torch.empty((2, C), dtype=torch.float32, device=x.device)
+        y2 = None if y is None else y.reshape(-1, C)
+        be.bn_bwd_reduce(x.reshape(-1, C), dy.reshape(-1, C), y2, gamma, beta, mean, rstd, act, sums[0], sums[1])
+        local = sums.clone()
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+        dx = torch.empty_like(x)
+        dres = torch.empty_like(x) if has_res else None
+        be.bn_bwd_apply(x.reshape(-1, C), dy.reshape(-1, C), y2, gamma, beta, mean, rstd, sums[0], sums[1], 1.0 / total, act, dx.reshape(-1, C),
+                        None if dres is None else dres.reshape(-1, C))
+        return dx, local[1], local[0], None, None, dres, None, None, None, None
+
+
+class FrozenBatchNormFn(torch.autograd.Function):
+    """FrozenBatchNorm2d (nn/backbone/resnet.py:226-250; TrainerArgs.freeze_bn): the affine of the RUNNING statistics in training too - nothing is
+    updated, weight / bias receive no gradient; dx = gamma * rstd * g."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, res, act, eps):
+        x = x.contiguous()
+        C = x.shape[-1]
+        rstd = torch.rsqrt(running_var + eps)
+        y = torch.empty_like(x)
+        r2 = None if res is None else res.contiguous().reshape(-1, C)
+        ops._be().bn_apply(x.reshape(-1, C), running_mean, rstd, gamma, beta, r2, act, y.reshape(-1, C))
+        ctx.save_for_backward(x, gamma, beta, running_mean.clone(), rstd, y if (act != ops.ACT_NONE and res is not None) else None)
+        ctx.cfg = (act, res is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, beta, mean, rstd, y = ctx.saved_tensors
+        act, has_res = ctx.cfg
+        C = x.shape[-1]
+        dy = dy.contiguous()
+        zero = torch.zeros(C, dtype=torch.float32, device=x.device)
+        dx = torch.empty_like(x)
+        dres = torch.empty_like(x) if has_res else None
+        ops._be().bn_bwd_apply(x.reshape(-1, C), dy.reshape(-1, C), None if y is None else y.reshape(-1, C), gamma, beta, mean, rstd, zero, zero, 0.0, act, dx.reshape(-1, C),
+                               None if dres is None else dres.reshape(-1, C))
+        return dx, None, None, None, None, dres, None, None
 
 
 class LayerNormFn(torch.autograd.Function):
@@ -450,8 +563,16 @@ def conv2d(x, w, bias=None, stride=1, pad=0, precision="fp32"):
     return Conv2dFn.apply(x, w, bias, stride, pad, precision)
 
 
-def batch_norm_train(x, bn: torch.nn.BatchNorm2d, res=None, act=ops.ACT_NONE):
-    return BatchNormTrainFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, res, act, bn.eps, 0.1 if bn.momentum is None else bn.momentum)
+def batch_norm_train(x, bn: torch.nn.BatchNorm2d, res=None, act=ops.ACT_NONE, sync_group=None, frozen=False):
+    """train-mode BatchNorm2d: batch statistics (default), statistics over all ranks of `sync_group` (SyncBatchNorm), or the frozen running statistics"""
+    if frozen:
+        return FrozenBatchNormFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, res, act, bn.eps)
+    with torch.no_grad():
+        bn.num_batches_tracked += 1  # nn.BatchNorm2d.train() bookkeeping (a state_dict buffer)
+    momentum = 0.1 if bn.momentum is None else bn.momentum
+    if sync_group is not None:
+        return SyncBatchNormTrainFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, res, act, bn.eps, momentum, None if sync_group is True else sync_group)
+    return BatchNormTrainFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, res, act, bn.eps, momentum)
 
 
 def layer_norm(x, ln: torch.nn.LayerNorm, res=None):

@@ -279,6 +279,13 @@ __global__ void col_finalize_kernel(const float* __restrict__ p0, const float* _
       run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)(R > 1.0 ? var * R / (R - 1.0) : var);
     }
   }
+  if (FIN == 5) {  // like 4, but the raw local moments: out0 = mean, out1 = BIASED variance (SyncBatchNorm exchanges these, fb200_bn_stats)
+    const double m1 = a / R;
+    double var = b / R - m1 * m1;
+    if (var < 0.0) var = 0.0;
+    out0[c] = (float)((double)mean[c] + m1);
+    out1[c] = (float)var;
+  }
 }
 
 // y = act((x - mean) * rstd * gamma + beta + res)
@@ -661,6 +668,59 @@ extern "C" int fb200_bn_train_bwd(const float* x, int x_pitch, const float* dy, 
                                                          dx, dx_pitch, dres, dres_pitch);
   col_finalize_kernel<3><<<cdiv(C, 128), 128, 0, st>>>(f0, f1, 1, C, (double)R, 0.f, 0.f, nullptr, nullptr, nullptr, dbeta, dgamma, accumulate);
   FB_CHECK_LAUNCH("bn_train_bwd");
+  return FB200_OK;
+}
+
+// ---- BatchNorm in phases (SyncBatchNorm across data-parallel ranks, FrozenBatchNorm2d): statistics | apply | backward sums | backward apply ----------
+extern "C" int fb200_bn_stats(const float* x, int x_pitch, int64_t R, int C, float* mean, float* var_biased, void* workspace, void* stream) {
+  FB_CHECK_ARG(x && mean && var_biased && workspace && R > 0 && C % 4 == 0, "bn_stats: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* p0 = reinterpret_cast<float*>(workspace);
+  const dim3 g = col_grid(C, R);
+  float* p1 = p0 + (int64_t)CR_ROWS * C;
+  col_partial_kernel<3><<<g, 256, 0, st>>>(x, x_pitch, R, C, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, 0, p0, p1);
+  col_finalize_kernel<5><<<cdiv(C, 128), 128, 0, st>>>(p0, p1, g.y, C, (double)R, 0.f, 0.f, x, nullptr, nullptr, mean, var_biased, 0);
+  FB_CHECK_LAUNCH("bn_stats");
+  return FB200_OK;
+}
+
+extern "C" int fb200_bn_apply(const float* x, int x_pitch, int64_t R, int C, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                              const float* res, int res_pitch, int act, float* y, int y_pitch, void* stream) {
+  FB_CHECK_ARG(x && mean && rstd && gamma && beta && y && R > 0 && C % 4 == 0, "bn_apply: bad arguments");
+  FB_CHECK_ARG(act == FB200_ACT_NONE || act == FB200_ACT_RELU || (act == FB200_ACT_SILU && !res), "bn_apply: act must be none/relu (or silu without residual)");
+  bn_apply_kernel<<<grid_for(R * (C / 4)), 256, 0, (cudaStream_t)stream>>>(x, x_pitch, res, res_pitch, R, C, mean, rstd, gamma, beta, act, y, y_pitch);
+  FB_CHECK_LAUNCH("bn_apply");
+  return FB200_OK;
+}
+
+extern "C" int fb200_bn_bwd_reduce(const float* x, int x_pitch, const float* dy, int dy_pitch, const float* y, int y_pitch, int64_t R, int C, const float* gamma,
+                                   const float* beta, const float* mean, const float* rstd, int act, float* sum_dy, float* sum_dy_xhat, void* workspace, void* stream) {
+  FB_CHECK_ARG(x && dy && gamma && beta && mean && rstd && sum_dy && sum_dy_xhat && workspace && R > 0, "bn_bwd_reduce: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* p0 = reinterpret_cast<float*>(workspace);
+  float* p1 = p0 + (int64_t)CR_ROWS * C;
+  const dim3 g = col_grid(C, R);
+  col_partial_kernel<2><<<g, 256, 0, st>>>(x, x_pitch, R, C, mean, rstd, gamma, beta, dy, dy_pitch, y, y_pitch, act, p0, p1);
+  col_finalize_kernel<3><<<cdiv(C, 128), 128, 0, st>>>(p0, p1, g.y, C, (double)R, 0.f, 0.f, nullptr, nullptr, nullptr, sum_dy, sum_dy_xhat, 0);
+  FB_CHECK_LAUNCH("bn_bwd_reduce");
+  return FB200_OK;
+}
+
+extern "C" int fb200_bn_bwd_apply(const float* x, int x_pitch, const float* dy, int dy_pitch, const float* y, int y_pitch, int64_t R, int C, const float* gamma,
+                                  const float* beta, const float* mean, const float* rstd, const float* sum_dy, const float* sum_dy_xhat, float inv_count, int act,
+                                  float* dx, int dx_pitch, float* dres, int dres_pitch, void* stream) {
+  FB_CHECK_ARG(x && dy && gamma && beta && mean && rstd && sum_dy && sum_dy_xhat && dx && R > 0, "bn_bwd_apply: bad arguments");
+  FB_CHECK_ARG(act == FB200_ACT_NONE || y || !dres, "bn_bwd_apply: with a fused residual the activation gradient needs the forward output");
+  const bool v4 = C % 4 == 0 && x_pitch % 4 == 0 && dy_pitch % 4 == 0 && dx_pitch % 4 == 0 && (!y || y_pitch % 4 == 0) && (!dres || dres_pitch % 4 == 0) &&
+                  ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(y) |
+                    reinterpret_cast<uintptr_t>(dres)) & 15) == 0;
+  if (v4)
+    bn_bwd_apply4_kernel<<<grid_for(R * (C / 4)), 256, 0, (cudaStream_t)stream>>>(x, x_pitch, dy, dy_pitch, y, y_pitch, R, C, mean, rstd, gamma, beta, sum_dy_xhat, sum_dy, act,
+                                                                                  inv_count, dx, dx_pitch, dres, dres_pitch);
+  else
+    bn_bwd_apply_kernel<<<grid_for(R * C), 256, 0, (cudaStream_t)stream>>>(x, x_pitch, dy, dy_pitch, y, y_pitch, R, C, mean, rstd, gamma, beta, sum_dy_xhat, sum_dy, act, inv_count,
+                                                                           dx, dx_pitch, dres, dres_pitch);
+  FB_CHECK_LAUNCH("bn_bwd_apply");
   return FB200_OK;
 }
 

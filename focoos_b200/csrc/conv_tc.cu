@@ -414,7 +414,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             tma_load_5d(&tmap_a, &full_bar[stage], dst_a, wp * p.x_pitch + a_c0, w0 + dw, hp, h0 + dh, img);
           }
           if (p.w_batched) tma_load_3d(&tmap_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb * BKP, n0, img);
-          else tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb * BKP, n0);
+          else if ((p.dbg & 64) && BLOCK_N >= 128) {  // experiment: same bytes, more TMA instructions
+            const int parts = (p.dbg & 128) ? 4 : 2;
+            for (int q = 0; q < parts; ++q)
+              tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES + q * (B_STAGE_BYTES / parts), kb * BKP, n0 + q * (BLOCK_N / parts));
+          } else tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb * BKP, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -883,7 +887,10 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
     {
       const uint64_t dims[3] = {(uint64_t)p.K, (uint64_t)p.Cout, (uint64_t)p.B};
       const uint64_t str[3] = {1, (uint64_t)p.K, (uint64_t)p.w_bs};
-      const uint32_t box[3] = {(uint32_t)phys_k<BK_>(), (uint32_t)(C2_ ? BN_ / 2 : BN_), 1};  // CTA pair: each CTA loads half of the N tile
+      static int dbg_env = -1;
+      if (dbg_env < 0) { const char* e = getenv("FB200_TC_DBG"); dbg_env = e ? atoi(e) : 0; }
+      const int split_b = (!C2_ && (dbg_env & 64) && BN_ >= 128) ? ((dbg_env & 128) ? 4 : 2) : 1;  // experiment: the B tile as 2 / 4 TMA instructions
+      const uint32_t box[3] = {(uint32_t)phys_k<BK_>(), (uint32_t)((C2_ ? BN_ / 2 : BN_) / split_b), 1};  // CTA pair: each CTA loads half of the N tile
       int r2 = encode(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, p.w_bs ? 3 : 2, const_cast<void*>(p.w), dims, str, box, "W", swz);
       if (r2) return r2;
     }

@@ -648,7 +648,10 @@ class FAIDetr(nn.Module):
         self.precision = precision
         self.algo = ops.ALGO_AUTO
         self._engine: Optional[DetrEngine] = None
-        from .train_step import freeze_backbone_norm
+        self.sync_bn = False    # training: BatchNorm statistics over all data-parallel ranks (torch.nn.SyncBatchNorm, trainer/trainer.py:334); set by the trainer
+        self.freeze_bn = False  # training: every BatchNorm as FrozenBatchNorm2d (TrainerArgs.freeze_bn, trainer/trainer.py:330)
+        from .train_step import freeze_backbone_at, freeze_backbone_norm
+        freeze_backbone_at(self, getattr(c.backbone_config, "freeze_at", -1), getattr(c.backbone_config, "num_stages", 4))  # resnet.py:221-224
         if getattr(c.backbone_config, "freeze_norm", False):  # resnet.py:226 (the registry configs ship freeze_norm=false)
             freeze_backbone_norm(self)
         self.eval()

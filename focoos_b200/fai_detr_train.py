@@ -48,7 +48,15 @@ class DetrTrainGraph:
         k = layer.conv.kernel_size[0]
         y = A.conv2d(x, layer.conv.weight, None, layer.conv.stride[0], (k - 1) // 2, self.prec)
         a = layer.act_name if act == "default" else act
-        return A.batch_norm_train(y, layer.norm, res, _ACT[a])
+        return self.bn(y, layer.norm, res, _ACT[a])
+
+    def bn(self, y, norm, res=None, act=ops.ACT_NONE):
+        """train-mode BatchNorm of one ConvNormLayer: frozen running statistics (FrozenBatchNorm2d: backbone_config.freeze_norm -> norm.frozen_stats,
+        or TrainerArgs.freeze_bn -> model.freeze_bn), statistics over all data-parallel ranks (model.sync_bn, trainer.py:334), or batch statistics"""
+        import torch.distributed as dist
+        frozen = bool(getattr(self.m, "freeze_bn", False)) or bool(getattr(norm, "frozen_stats", False))
+        sync = bool(getattr(self.m, "sync_bn", False)) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        return A.batch_norm_train(y, norm, res, act, sync_group=True if sync else None, frozen=frozen)
 
     def bottleneck(self, x, blk):
         out = self.cnl(x, blk.branch2a)
@@ -107,7 +115,7 @@ class DetrTrainGraph:
         pd = self.m.pixel_decoder
         proj = []
         for f, ip in zip(feats, pd.input_proj):
-            proj.append(A.batch_norm_train(A.conv2d(f, ip[0].weight, None, 1, 0, self.prec), ip[1]))
+            proj.append(self.bn(A.conv2d(f, ip[0].weight, None, 1, 0, self.prec), ip[1]))
         B, h, w, C = proj[2].shape
         src = proj[2].reshape(B, h * w, C)
         pos = self._aifi_pos(h, w, src.device)[None].expand(B, -1, -1).contiguous()
@@ -137,7 +145,7 @@ class DetrTrainGraph:
         tp = self.m.head.predictor
         toks, shapes = [], []
         for f, ip in zip(feats, tp.input_proj):
-            y = A.batch_norm_train(A.conv2d(f, ip.conv.weight, None, 1, 0, self.prec), ip.norm)
+            y = self.bn(A.conv2d(f, ip.conv.weight, None, 1, 0, self.prec), ip.norm)
             B, h, w, C = y.shape
             toks.append(y.reshape(B, h * w, C))
             shapes.append((h, w))

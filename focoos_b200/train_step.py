@@ -60,12 +60,27 @@ _NORM_TYPES = (nn.BatchNorm1d, nn.BatchNorm2d, nn.BatchNorm3d, nn.SyncBatchNorm,
 
 def freeze_backbone_norm(model: nn.Module) -> None:
     """With backbone_config.freeze_norm the reference swaps every backbone BatchNorm2d for FrozenBatchNorm2d
-    (nn/backbone/resnet.py:226-250): weight/bias become buffers - in the state_dict, not in model.parameters().  Same
-    effect here: requires_grad=False.  (The registry's fai-detr configs set freeze_norm=false: all 501 tensors train.)"""
+    (nn/backbone/resnet.py:226-250): weight/bias become buffers - in the state_dict, not in model.parameters() - and the layer
+    normalises with its RUNNING statistics in training too.  Here: requires_grad=False, which the training graph
+    (fai_detr_train.DetrTrainGraph.bn) reads as "frozen": running statistics, no buffer update, no weight / bias gradient.
+    (The registry's fai-detr configs set freeze_norm=false: all 501 tensors train.)"""
     for name, mod in model.named_modules():
         if "backbone" in name and isinstance(mod, nn.BatchNorm2d):
+            mod.frozen_stats = True
             for p in mod.parameters(recurse=False):
                 p.requires_grad_(False)
+
+
+def freeze_backbone_at(model: nn.Module, freeze_at: int, num_stages: int = 4) -> None:
+    """ResnetConfig.freeze_at >= 0 (nn/backbone/resnet.py:221-224): the stem and the first `freeze_at` stages get no gradient (their BatchNorms stay
+    ordinary train-mode layers unless freeze_norm is also set)."""
+    if freeze_at < 0:
+        return
+    bb = model.pixel_decoder.backbone
+    mods = [bb.conv1] + [bb.res_layers[i] for i in range(min(freeze_at, num_stages))]
+    for m in mods:
+        for p in m.parameters():
+            p.requires_grad_(False)
 
 
 def get_optimizer_params(model: nn.Module, base_lr: float, weight_decay: float, weight_decay_norm: float = 0.0, weight_decay_embed: float = 0.0,

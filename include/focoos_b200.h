@@ -306,6 +306,20 @@ int fb200_bn_train_fwd(const float* x, int x_pitch, int64_t R, int C, const floa
 int fb200_bn_train_bwd(const float* x, int x_pitch, const float* dy, int dy_pitch, const float* y, int y_pitch, int64_t R, int C, const float* gamma,
                        const float* beta, const float* save_mean, const float* save_rstd, int act, float* dx, int dx_pitch, float* dres, int dres_pitch,
                        float* dgamma, float* dbeta, int accumulate, void* workspace, void* stream);
+/* The same BatchNorm in phases, for the two variants the reference's trainer switches to:
+ *   torch.nn.SyncBatchNorm.convert_sync_batchnorm when world_size > 1 (trainer/trainer.py:334): fb200_bn_stats gives the LOCAL mean / biased variance per channel,
+ *     the host all-gathers them with the row counts and combines (what aten's batch_norm_gather_stats_with_counts does), fb200_bn_apply normalises with the GLOBAL
+ *     statistics; backward: fb200_bn_bwd_reduce gives the local sum(g), sum(g*xhat) (g = dy through the fused activation), the host all-reduces them,
+ *     fb200_bn_bwd_apply forms dx with the global sums and inv_count = 1 / total rows;
+ *   FrozenBatchNorm2d (nn/backbone/resnet.py:226-250, TrainerArgs.freeze_bn): fb200_bn_apply with the RUNNING statistics, fb200_bn_bwd_apply with zero sums. */
+int fb200_bn_stats(const float* x, int x_pitch, int64_t R, int C, float* mean, float* var_biased, void* workspace, void* stream);
+int fb200_bn_apply(const float* x, int x_pitch, int64_t R, int C, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                   const float* res, int res_pitch, int act, float* y, int y_pitch, void* stream);
+int fb200_bn_bwd_reduce(const float* x, int x_pitch, const float* dy, int dy_pitch, const float* y, int y_pitch, int64_t R, int C, const float* gamma,
+                        const float* beta, const float* mean, const float* rstd, int act, float* sum_dy, float* sum_dy_xhat, void* workspace, void* stream);
+int fb200_bn_bwd_apply(const float* x, int x_pitch, const float* dy, int dy_pitch, const float* y, int y_pitch, int64_t R, int C, const float* gamma,
+                       const float* beta, const float* mean, const float* rstd, const float* sum_dy, const float* sum_dy_xhat, float inv_count, int act,
+                       float* dx, int dx_pitch, float* dres, int dres_pitch, void* stream);
 /* out = act(a + b) when dy == NULL, else out = dy * act'(a + b)   (RepVggBlock :45, GELU of the AIFI FFN) */
 int fb200_add_act(const float* a, const float* b, const float* dy, int act, int64_t n, float* out, void* stream);
 int fb200_maxpool3x3s2_bwd(const float* x, const float* dy, int B, int H, int W, int C, float* dx, void* stream);

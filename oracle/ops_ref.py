@@ -462,6 +462,44 @@ def _rb_bn_train_bwd(self, x2d, dy2d, y2d, gamma, beta, save_mean, save_rstd, ac
     dbeta.copy_(db)
 
 
+def _bn_g(x2d, dy2d, y2d, gamma, beta, mean, rstd, act):
+    xh = (x2d - mean) * rstd
+    g = dy2d
+    if act == 1:
+        g = dy2d * ((y2d if y2d is not None else xh * gamma + beta) > 0)
+    elif act == 2:
+        z = (xh * gamma + beta).detach().requires_grad_(True)
+        with torch.enable_grad():
+            (g,) = torch.autograd.grad(F.silu(z), z, dy2d)
+    return xh, g
+
+
+def _rb_bn_stats(self, x2d, mean, var):
+    m = x2d.double().mean(0)
+    mean.copy_(m.float())
+    var.copy_(((x2d.double() - m) ** 2).mean(0).float())
+
+
+def _rb_bn_apply(self, x2d, mean, rstd, gamma, beta, res2d, act, y2d):
+    z = (x2d - mean) * rstd * gamma + beta
+    if res2d is not None:
+        z = z + res2d
+    y2d.copy_(_act_bw(act, z))
+
+
+def _rb_bn_bwd_reduce(self, x2d, dy2d, y2d, gamma, beta, mean, rstd, act, sum_dy, sum_dy_xhat):
+    xh, g = _bn_g(x2d, dy2d, y2d, gamma, beta, mean, rstd, act)
+    sum_dy.copy_(g.double().sum(0).float())
+    sum_dy_xhat.copy_((g.double() * xh.double()).sum(0).float())
+
+
+def _rb_bn_bwd_apply(self, x2d, dy2d, y2d, gamma, beta, mean, rstd, sum_dy, sum_dy_xhat, inv_count, act, dx2d, dres2d):
+    xh, g = _bn_g(x2d, dy2d, y2d, gamma, beta, mean, rstd, act)
+    dx2d.copy_(gamma * rstd * (g - sum_dy * inv_count - xh * sum_dy_xhat * inv_count))
+    if dres2d is not None:
+        dres2d.copy_(g)
+
+
 def _rb_add_act(self, a, b, dy, act, out):
     z = (a if b is None else a + b).detach().requires_grad_(dy is not None)
     if dy is None:
@@ -545,6 +583,7 @@ def _rb_msda_bwd(self, value, oa, ref, do, shapes, P, heads, dvalue, doa):
 
 
 for _n, _f in (("conv_wgrad", _rb_conv_wgrad), ("conv_wgrad_tc_supported", _rb_conv_wgrad_tc_supported), ("conv_wgrad_tc", _rb_conv_wgrad_tc), ("dilate2", _rb_dilate2), ("colsum", _rb_colsum), ("bn_train_fwd", _rb_bn_train_fwd), ("bn_train_bwd", _rb_bn_train_bwd),
+               ("bn_stats", _rb_bn_stats), ("bn_apply", _rb_bn_apply), ("bn_bwd_reduce", _rb_bn_bwd_reduce), ("bn_bwd_apply", _rb_bn_bwd_apply),
                ("add_act", _rb_add_act), ("maxpool_bwd", _rb_maxpool_bwd), ("avgpool_bwd", _rb_avgpool_bwd), ("resize_bwd", _rb_resize_bwd),
                ("layernorm_bwd", _rb_layernorm_bwd), ("attention_bwd", _rb_attention_bwd), ("msda_bwd", _rb_msda_bwd)):
     setattr(RefBackend, _n, _f)
