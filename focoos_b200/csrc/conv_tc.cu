@@ -236,29 +236,35 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
 // address is shifted by one 64-byte pixel row each - the tap boxes are no longer re-read from L2 three times (these layers run at the L2 bandwidth).
 template <int BLOCK_K> __host__ __device__ constexpr bool is_halo() { return BLOCK_K == 96; }
 template <int BLOCK_K> __host__ __device__ constexpr int phys_k() { return BLOCK_K == 96 ? 32 : BLOCK_K; }  // channels per shared-memory row
-template <int BLOCK_N, int BLOCK_K> __host__ __device__ constexpr int a_stage_bytes() { return BLOCK_K == 96 ? 9216 : BLOCK_M * BLOCK_K * 2; }  // 130 rows x 64 B, 1 KiB aligned
-template <int BLOCK_N, int BLOCK_K, bool CTA2 = false> __host__ __device__ constexpr int b_stage_bytes() { return BLOCK_K == 96 ? 0 : (CTA2 ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2; }
+// FS ("fused split", fp32-accurate mode): one ring stage holds the hi AND lo halves of both operands of a 64-channel chunk - A_hi, A_lo, B_hi, B_lo are loaded ONCE
+// and feed the three products hi x W_hi, hi x W_lo, lo x W_hi (the segmented layout streams every operand tile through the TMA engine / L2 three times)
+template <int BLOCK_N, int BLOCK_K, bool FS = false> __host__ __device__ constexpr int a_stage_bytes() { return BLOCK_K == 96 ? 9216 : (FS ? 2 : 1) * BLOCK_M * BLOCK_K * 2; }  // halo: 130 rows x 64 B, 1 KiB aligned
+template <int BLOCK_N, int BLOCK_K, bool CTA2 = false, bool FS = false> __host__ __device__ constexpr int b_stage_bytes() { return BLOCK_K == 96 ? 0 : (FS ? 2 : 1) * (CTA2 ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2; }
 // halo mode keeps ALL NINE weight taps resident in shared memory for the life of the persistent CTA (9 x BLOCK_N x 64 B <= 36 KiB): per tile only the
 // three input strips travel from L2
 template <int BLOCK_N, int BLOCK_K> __host__ __device__ constexpr int b_resident_bytes() { return BLOCK_K == 96 ? 9 * BLOCK_N * 64 : 0; }
-template <int BLOCK_N, int BLOCK_K, bool CTA2 = false> constexpr int stage_bytes() { return a_stage_bytes<BLOCK_N, BLOCK_K>() + b_stage_bytes<BLOCK_N, BLOCK_K, CTA2>(); }
-template <int BLOCK_N, int STAGES, int BLOCK_K, int NSTG, bool CTA2 = false> constexpr int smem_bytes() {
-  return STAGES * stage_bytes<BLOCK_N, BLOCK_K, CTA2>() + b_resident_bytes<BLOCK_N, BLOCK_K>() + NSTG * epi_groups<BLOCK_N>() * STAGING_BYTES + 2 * BLOCK_N * 4 +
-         (2 * STAGES + 5 + NSTG * epi_groups<BLOCK_N>()) * 8 + 16 + 1024 /*align slack*/;
+template <int BLOCK_N, int BLOCK_K, bool CTA2 = false, bool FS = false> constexpr int stage_bytes() { return a_stage_bytes<BLOCK_N, BLOCK_K, FS>() + b_stage_bytes<BLOCK_N, BLOCK_K, CTA2, FS>(); }
+template <int BLOCK_N, int STAGES, int BLOCK_K, int NSTG, bool CTA2 = false, bool FS = false> constexpr int smem_bytes() {
+  return STAGES * stage_bytes<BLOCK_N, BLOCK_K, CTA2, FS>() + b_resident_bytes<BLOCK_N, BLOCK_K>() + NSTG * epi_groups<BLOCK_N>() * STAGING_BYTES + 2 * BLOCK_N * 4 +
+         (2 * STAGES + 5 + NSTG * epi_groups<BLOCK_N>()) * 8 + 16 + (FS ? 0 : 1024) /*align slack; the FS configurations need every byte and rely on the 1024-byte alignment of dynamic shared memory (checked in the kernel)*/;
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
-template <int BLOCK_N, int STAGES, typename TOut, int MIN_BLOCKS, int BLOCK_K, int NSTG, bool GELU, bool CTA2>
+template <int BLOCK_N, int STAGES, typename TOut, int MIN_BLOCKS, int BLOCK_K, int NSTG, bool GELU, bool CTA2, bool FS>
 __global__ void __launch_bounds__(num_threads<BLOCK_N>(), MIN_BLOCKS)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r, const KParams p) {
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  if constexpr (FS) { if (smem != smem_raw) __trap(); }  // no alignment slack in the FS configurations
   constexpr bool HALO = is_halo<BLOCK_K>();
   constexpr int BKP = phys_k<BLOCK_K>();
-  constexpr int A_STAGE_BYTES = a_stage_bytes<BLOCK_N, BLOCK_K>();
-  constexpr int B_STAGE_BYTES = b_stage_bytes<BLOCK_N, BLOCK_K, CTA2>();
+  constexpr int A_STAGE_BYTES = a_stage_bytes<BLOCK_N, BLOCK_K, FS>();
+  constexpr int B_STAGE_BYTES = b_stage_bytes<BLOCK_N, BLOCK_K, CTA2, FS>();
   static_assert(!(CTA2 && HALO), "the halo mode is single-CTA");
+  static_assert(!(FS && (HALO || BLOCK_K != 64)), "the fused-split mode works on 64-channel chunks");
+  constexpr int A_HALF = BLOCK_M * 64 * 2;                                  // FS: bytes of one A half (hi or lo) inside a stage
+  constexpr int B_HALF = (CTA2 ? BLOCK_N / 2 : BLOCK_N) * 64 * 2;           // FS: bytes of one B half
   uint32_t cta_rank = 0;  // CTA pair: 0 = leader (issues the MMAs), 1 = peer
   if constexpr (CTA2) cta_rank = cluster_ctarank();
   // persistent tile walk: a CTA pair shares one tile index (two adjacent M tiles x one N tile)
@@ -374,6 +380,47 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
           }
         }
+        if constexpr (FS) {
+          for (int kb = 0; kb < p.num_k_blocks; ++kb) {  // k-block = (tap, 64-channel chunk): A_hi, A_lo, W_hi, W_lo once each
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
+            const int kh = tap / p.KW, kw = tap - kh * p.KW;
+            uint8_t* dst_a = smem_a + stage * A_STAGE_BYTES;
+            uint8_t* dst_b = smem_b + stage * B_STAGE_BYTES;
+            const int c_hi = cc * 64, c_lo = p.lo_off + cc * 64;
+            const int k_hi = tap * 3 * p.lo_off + cc * 64, k_lo = k_hi + p.lo_off;  // weights packed [W_hi | W_lo | W_hi] per tap
+            const uint32_t fs_bytes = 2u * (uint32_t)(p.BW * p.BH * 128) + (uint32_t)B_STAGE_BYTES;
+            if constexpr (CTA2) {
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * fs_bytes);
+              const uint32_t lbar = mapa_rank0(smem_u32(&full_bar[stage]));
+              if (!p.stride2) {
+                tma_load_4d_2sm(&tmap_a, lbar, dst_a, c_hi, w0 + kw - p.pad, h0 + kh - p.pad, img);
+                tma_load_4d_2sm(&tmap_a, lbar, dst_a + A_HALF, c_lo, w0 + kw - p.pad, h0 + kh - p.pad, img);
+              } else {
+                const int th = kh - p.pad, tw = kw - p.pad;
+                tma_load_5d_2sm(&tmap_a, lbar, dst_a, (tw & 1) * p.x_pitch + c_hi, w0 + (tw >> 1), th & 1, h0 + (th >> 1), img);
+                tma_load_5d_2sm(&tmap_a, lbar, dst_a + A_HALF, (tw & 1) * p.x_pitch + c_lo, w0 + (tw >> 1), th & 1, h0 + (th >> 1), img);
+              }
+              const int nb = n0 + (int)cta_rank * (BLOCK_N / 2);
+              tma_load_2d_2sm(&tmap_b, lbar, dst_b, k_hi, nb);
+              tma_load_2d_2sm(&tmap_b, lbar, dst_b + B_HALF, k_lo, nb);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], fs_bytes);
+              if (!p.stride2) {
+                tma_load_4d(&tmap_a, &full_bar[stage], dst_a, c_hi, w0 + kw - p.pad, h0 + kh - p.pad, img);
+                tma_load_4d(&tmap_a, &full_bar[stage], dst_a + A_HALF, c_lo, w0 + kw - p.pad, h0 + kh - p.pad, img);
+              } else {
+                const int th = kh - p.pad, tw = kw - p.pad;
+                tma_load_5d(&tmap_a, &full_bar[stage], dst_a, (tw & 1) * p.x_pitch + c_hi, w0 + (tw >> 1), th & 1, h0 + (th >> 1), img);
+                tma_load_5d(&tmap_a, &full_bar[stage], dst_a + A_HALF, (tw & 1) * p.x_pitch + c_lo, w0 + (tw >> 1), th & 1, h0 + (th >> 1), img);
+              }
+              tma_load_2d(&tmap_b, &full_bar[stage], dst_b, k_hi, n0);
+              tma_load_2d(&tmap_b, &full_bar[stage], dst_b + B_HALF, k_lo, n0);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          continue;
+        }
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           const long long e0_ = trc ? clock64() : 0;
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -448,7 +495,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (kb == 0) stamp(3 + 6 * tk);
           const uint64_t da = make_smem_desc<BKP>(smem_u32(smem_a + stage * A_STAGE_BYTES));
           const uint64_t db = make_smem_desc<BKP>(smem_u32(smem_b + stage * B_STAGE_BYTES));
-          if constexpr (HALO) {
+          if constexpr (FS) {
+            const uint64_t da_lo = make_smem_desc<BKP>(smem_u32(smem_a + stage * A_STAGE_BYTES + A_HALF));
+            const uint64_t db_lo = make_smem_desc<BKP>(smem_u32(smem_b + stage * B_STAGE_BYTES + B_HALF));
+            auto issue = [&](uint64_t a, uint64_t b, uint32_t acc_flag) {
+              if constexpr (CTA2) umma_f16_2sm(tmem_d, a, b, idesc, acc_flag);
+              else umma_f16(tmem_d, a, b, idesc, acc_flag);
+            };
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {  // hi x W_hi, hi x W_lo, lo x W_hi per 16-channel step, all into the same fp32 accumulator
+              const uint64_t ko = (uint64_t)(k * 2);
+              issue(da + ko, db + ko, (kb > 0 || k > 0) ? 1u : 0u);
+              issue(da + ko, db_lo + ko, 1u);
+              issue(da_lo + ko, db + ko, 1u);
+            }
+          } else if constexpr (HALO) {
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw) {
               // tap kw reads the strip shifted by kw pixels = kw * 64 B (+4 per pixel in 16-byte units); p.halo_boff: also patch the descriptor's
@@ -754,10 +815,10 @@ static int num_sms() {
   return n;
 }
 
-template <int BLOCK_N, int STAGES, typename TOut, int MIN_BLOCKS, int BLOCK_K, int NSTG, bool GELU, bool CTA2 = false>
+template <int BLOCK_N, int STAGES, typename TOut, int MIN_BLOCKS, int BLOCK_K, int NSTG, bool GELU, bool CTA2 = false, bool FS = false>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr, const KParams& kp, cudaStream_t st) {
-  auto kern = conv_tc_kernel<BLOCK_N, STAGES, TOut, MIN_BLOCKS, BLOCK_K, NSTG, GELU, CTA2>;
-  constexpr int smem = smem_bytes<BLOCK_N, STAGES, BLOCK_K, NSTG, CTA2>();
+  auto kern = conv_tc_kernel<BLOCK_N, STAGES, TOut, MIN_BLOCKS, BLOCK_K, NSTG, GELU, CTA2, FS>;
+  constexpr int smem = smem_bytes<BLOCK_N, STAGES, BLOCK_K, NSTG, CTA2, FS>();
   constexpr int NUM_THREADS = num_threads<BLOCK_N>();
   static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
   static_assert(MIN_BLOCKS * 2 * BLOCK_N <= 512, "TMEM budget exceeded (a blocked tcgen05.alloc would deadlock)");
@@ -877,8 +938,9 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
   }
   if (rc) return rc;
 
-  auto run = [&](auto blockn_tag, auto stages_tag, auto minb_tag, auto bk_tag, auto nstg_tag, auto gelu_tag, auto cta2_tag) -> int {
+  auto run = [&](auto blockn_tag, auto stages_tag, auto minb_tag, auto bk_tag, auto nstg_tag, auto gelu_tag, auto cta2_tag, auto fs_tag) -> int {
     constexpr bool C2_ = decltype(cta2_tag)::value;
+    constexpr bool FS_ = decltype(fs_tag)::value;
     constexpr int BN_ = decltype(blockn_tag)::value;
     constexpr int ST_ = decltype(stages_tag)::value;
     constexpr int MB_ = decltype(minb_tag)::value;
@@ -913,6 +975,11 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
       if (r2) return r2;
     }
     KParams k2 = kp;
+    if constexpr (FS_) {  // fused split: k-blocks run over (tap, 64-channel chunk); the hi / lo halves of both operands travel together
+      k2.cchunks = Clog / 64;
+      k2.num_k_blocks = p.KH * p.KW * k2.cchunks;
+      k2.seg_chunks = 0;
+    }
     k2.n_tiles = (p.Cout + BN_ - 1) / BN_;
     k2.nimg = B;
     k2.trace = g_trace;
@@ -922,6 +989,7 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("FB200_TC_DBG"); dbg = e ? atoi(e) : 0; } k2.dbg = dbg; }
     { static int rt = -1; if (rt < 0) { const char* e = getenv("FB200_TC_RES_TMA"); rt = e ? atoi(e) : 1; } k2.res_tma = (p.res && rt) ? 1 : 0; }
     if constexpr (decltype(gelu_tag)::value) return launch<BN_, ST_, __half, MB_, BK_, NS_, true>(ta, tb, td, tr, k2, st);
+    else if constexpr (FS_) return launch<BN_, ST_, float, MB_, BK_, NS_, false, C2_, true>(ta, tb, td, tr, k2, st);  // fp32 output only (checked by the caller)
     else {
       if (out16) return launch<BN_, ST_, __half, MB_, BK_, NS_, false, C2_>(ta, tb, td, tr, k2, st);
       return launch<BN_, ST_, float, MB_, BK_, NS_, false, C2_>(ta, tb, td, tr, k2, st);
@@ -929,27 +997,29 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
   };
   typedef std::false_type C1;
   typedef std::true_type C2;
+  typedef std::false_type NF;  // segmented K (or no split)
+  typedef std::true_type FS;   // fused split
   using std::integral_constant;
   typedef integral_constant<int, 64> K64;
   typedef integral_constant<int, 32> K32;
   typedef integral_constant<int, 1> I1;
   typedef integral_constant<int, 2> I2;
   if ((p.act & 15) == FB200_ACT_GELU)  // exact-erf GELU: dedicated instantiation (fp16 out, Cin % 64 == 0; checked in conv2d_tc_supported)
-    return run(integral_constant<int, 128>{}, integral_constant<int, 4>{}, I1{}, K64{}, I2{}, std::true_type{}, C1{});
+    return run(integral_constant<int, 128>{}, integral_constant<int, 4>{}, I1{}, K64{}, I2{}, std::true_type{}, C1{}, NF{});
   typedef integral_constant<int, 96> K96;  // halo mode tag
   if (halo) {
-    if (p.Cout > 32) return run(integral_constant<int, 64>{}, integral_constant<int, 4>{}, I2{}, K96{}, I2{}, std::false_type{}, C1{});
-    return run(integral_constant<int, 32>{}, integral_constant<int, 4>{}, I2{}, K96{}, I2{}, std::false_type{}, C1{});
+    if (p.Cout > 32) return run(integral_constant<int, 64>{}, integral_constant<int, 4>{}, I2{}, K96{}, I2{}, std::false_type{}, C1{}, NF{});
+    return run(integral_constant<int, 32>{}, integral_constant<int, 4>{}, I2{}, K96{}, I2{}, std::false_type{}, C1{}, NF{});
   }
   if (BK == 32) {  // stem convs (Cin = 32): HBM-bound, two CTAs per SM
-    if (p.Cout > 32) return run(integral_constant<int, 64>{}, integral_constant<int, 4>{}, I2{}, K32{}, I2{}, std::false_type{}, C1{});
-    return run(integral_constant<int, 32>{}, integral_constant<int, 4>{}, I2{}, K32{}, I2{}, std::false_type{}, C1{});
+    if (p.Cout > 32) return run(integral_constant<int, 64>{}, integral_constant<int, 4>{}, I2{}, K32{}, I2{}, std::false_type{}, C1{}, NF{});
+    return run(integral_constant<int, 32>{}, integral_constant<int, 4>{}, I2{}, K32{}, I2{}, std::false_type{}, C1{}, NF{});
   }
   static int force_bn = -1;  // tuning aid: FB200_TC_BN=64|128|256
   if (force_bn < 0) { const char* e = getenv("FB200_TC_BN"); force_bn = e ? atoi(e) : 0; }
-  if (force_bn == 64) return run(integral_constant<int, 64>{}, integral_constant<int, 3>{}, I2{}, K64{}, I2{}, std::false_type{}, C1{});
-  if (force_bn == 128) return run(integral_constant<int, 128>{}, integral_constant<int, 4>{}, I1{}, K64{}, I2{}, std::false_type{}, C1{});
-  if (force_bn == 256) return run(integral_constant<int, 256>{}, integral_constant<int, 3>{}, I1{}, K64{}, I2{}, std::false_type{}, C1{});
+  if (force_bn == 64) return run(integral_constant<int, 64>{}, integral_constant<int, 3>{}, I2{}, K64{}, I2{}, std::false_type{}, C1{}, NF{});
+  if (force_bn == 128) return run(integral_constant<int, 128>{}, integral_constant<int, 4>{}, I1{}, K64{}, I2{}, std::false_type{}, C1{}, NF{});
+  if (force_bn == 256) return run(integral_constant<int, 256>{}, integral_constant<int, 3>{}, I1{}, K64{}, I2{}, std::false_type{}, C1{}, NF{});
   const int64_t tiles256 = m_tiles * ((p.Cout + 255) / 256);
   // CTA pairs (cta_group::2): the 256 x BLOCK_N tile of two SMs needs each weight tile only ONCE per pair - the single-CTA kernel is bound by the L2->SM
   // operand bandwidth on every tensor-bound layer (48 KB per 128x256x64 MMA block = 19 TB/s at the tensor peak vs ~12 TB/s of L2)
@@ -958,17 +1028,30 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
   const bool force_pair = g_cta_pair_mode == 2;
   static int cfg_env = -1;  // experiment knob FB200_TC_CFG: 1 = CTA pairs with a 5-deep ring and single staging buffers
   if (cfg_env < 0) { const char* e = getenv("FB200_TC_CFG"); cfg_env = e ? atoi(e) : 0; }
+  // fp32-accurate mode on 64-channel chunks: fused split (one TMA pass over A_hi, A_lo, W_hi, W_lo per chunk instead of three segmented passes): the TMA
+  // engine delivers ~65-80 B/cycle/SM plus ~110 cycles per instruction (profiles/r02_conv_timeline.md), the segmented layout needs 96 B/cycle at the tensor peak
+  static int fs_env = -1;  // FB200_TC_FS=0 disables
+  if (fs_env < 0) { const char* e = getenv("FB200_TC_FS"); fs_env = e ? atoi(e) : 1; }
+  if (fs_env && p.split3 && BK == 64 && p.out_dtype == FB200_F32 && !p.rowmax && !kp.w_batched && p.Cout > 64) {
+    if (p.Cout > 128 && g_cta_pair_mode != 0)
+      return run(integral_constant<int, 256>{}, integral_constant<int, 3>{}, I1{}, K64{}, I1{}, std::false_type{}, C2{}, FS{});   // pair: 3 x 64 + 32 KiB
+    if (p.Cout > 128)
+      return run(integral_constant<int, 256>{}, integral_constant<int, 2>{}, I1{}, K64{}, I1{}, std::false_type{}, C1{}, FS{});   // 2 x 96 + 32 KiB
+    return run(integral_constant<int, 128>{}, integral_constant<int, 3>{}, I1{}, K64{}, I1{}, std::false_type{}, C1{}, FS{});     // 3 x 64 + 32 KiB
+  }
   if (cfg_env == 1 && pair_ok && p.Cout > 128 && !p.res)
-    return run(integral_constant<int, 256>{}, integral_constant<int, 5>{}, I1{}, K64{}, I1{}, std::false_type{}, C2{});   // 5 x 32 + 32 KiB
-  if (pair_ok && p.Cout > 128 && (tiles256 >= 148 || force_pair))
-    return run(integral_constant<int, 256>{}, integral_constant<int, 4>{}, I1{}, K64{}, I2{}, std::false_type{}, C2{});   // 4 x 32 + 64 KiB
-  if (pair_ok && p.Cout > 64 && p.Cout <= 128 && (m_tiles >= 148 || force_pair))
-    return run(integral_constant<int, 128>{}, integral_constant<int, 6>{}, I1{}, K64{}, I2{}, std::false_type{}, C2{});   // 6 x 24 + 64 KiB
+    return run(integral_constant<int, 256>{}, integral_constant<int, 5>{}, I1{}, K64{}, I1{}, std::false_type{}, C2{}, NF{});   // 5 x 32 + 32 KiB
+  // single-product pairs only pay on the deep 3x3 layers (K >= 2304); on 1x1 layers the pair's extra synchronisation costs more than the halved weight traffic gains
+  const bool pair_shape = force_pair || (p.KH == 3 && Clog >= 256);
+  if (pair_ok && pair_shape && p.Cout > 128 && (tiles256 >= 148 || force_pair))
+    return run(integral_constant<int, 256>{}, integral_constant<int, 4>{}, I1{}, K64{}, I2{}, std::false_type{}, C2{}, NF{});   // 4 x 32 + 64 KiB
+  if (pair_ok && force_pair && p.Cout > 64 && p.Cout <= 128)
+    return run(integral_constant<int, 128>{}, integral_constant<int, 6>{}, I1{}, K64{}, I2{}, std::false_type{}, C2{}, NF{});   // 6 x 24 + 64 KiB
   if (p.Cout > 128 && tiles256 >= 148)
-    return run(integral_constant<int, 256>{}, integral_constant<int, 3>{}, I1{}, K64{}, I2{}, std::false_type{}, C1{});   // 144 + 64 KiB
+    return run(integral_constant<int, 256>{}, integral_constant<int, 3>{}, I1{}, K64{}, I2{}, std::false_type{}, C1{}, NF{});   // 144 + 64 KiB
   if (p.Cout > 64)
-    return run(integral_constant<int, 128>{}, integral_constant<int, 4>{}, I1{}, K64{}, I2{}, std::false_type{}, C1{});   // 128 + 64 KiB
-  return run(integral_constant<int, 64>{}, integral_constant<int, 3>{}, I2{}, K64{}, I2{}, std::false_type{}, C1{});      // 72 + 32 KiB, 2 CTAs/SM
+    return run(integral_constant<int, 128>{}, integral_constant<int, 4>{}, I1{}, K64{}, I2{}, std::false_type{}, C1{}, NF{});   // 128 + 64 KiB
+  return run(integral_constant<int, 64>{}, integral_constant<int, 3>{}, I2{}, K64{}, I2{}, std::false_type{}, C1{}, NF{});      // 72 + 32 KiB, 2 CTAs/SM
 }
 
 }  // namespace fb200

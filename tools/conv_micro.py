@@ -21,27 +21,39 @@ SHAPES = {  # name: (B,H,W,Cin,Cout,k,stride,res,act)
     "stem2": (32, 320, 320, 32, 32, 3, 1, False, 1),
     "stem3": (32, 320, 320, 32, 64, 3, 1, False, 1),
 }
+SPLIT = "--split" in sys.argv  # fp32-accurate mode: [hi|lo] pair input, [W_hi|W_lo|W_hi] weights, fp32 output (TF/s = algorithmic flops)
 names = [a for a in sys.argv[1:] if a in SHAPES] or list(SHAPES)
 reps = 10
 print(f"{'name':12} {'us':>8} {'TF/s':>7} {'GB/s':>7}  shape   (FB200_TC_BN={os.environ.get('FB200_TC_BN','auto')})")
 for n in names:
     B, H, W, Cin, Cout, k, s, res, act = SHAPES[n]
-    x = torch.randn((B, H, W, Cin), device="cuda").half()
-    w = (torch.randn((Cout, k, k, Cin), device="cuda") * 0.05).half()
     bi = torch.zeros(Cout, device="cuda")
     Ho, Wo = (H - 1) // s + 1, (W - 1) // s + 1
-    r = torch.randn((B, Ho, Wo, Cout), device="cuda").half() if res else None
-    y = torch.empty((B, Ho, Wo, Cout), device="cuda", dtype=torch.float16)
+    if SPLIT:
+        if Cin % 32:
+            continue
+        from focoos_b200.fai_detr import _split3_weights
+        x = ops.split_pair(torch.randn((B, H, W, Cin), device="cuda"))
+        w = _split3_weights(torch.randn((Cout, k, k, Cin), device="cuda") * 0.05)
+        r = torch.randn((B, Ho, Wo, Cout), device="cuda") if res else None
+        y = torch.empty((B, Ho, Wo, Cout), device="cuda", dtype=torch.float32)
+        ALGO = ops.ALGO_TCGEN05_SPLIT3
+    else:
+        x = torch.randn((B, H, W, Cin), device="cuda").half()
+        w = (torch.randn((Cout, k, k, Cin), device="cuda") * 0.05).half()
+        r = torch.randn((B, Ho, Wo, Cout), device="cuda").half() if res else None
+        y = torch.empty((B, Ho, Wo, Cout), device="cuda", dtype=torch.float16)
+        ALGO = ops.ALGO_TCGEN05
     for _ in range(2):
-        ops.conv2d(x, w, None, bi, stride=s, pad=(k - 1) // 2, act=act, residual=r, out=y, algo=ops.ALGO_TCGEN05)
+        ops.conv2d(x, w, None, bi, stride=s, pad=(k - 1) // 2, act=act, residual=r, out=y, algo=ALGO)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        ops.conv2d(x, w, None, bi, stride=s, pad=(k - 1) // 2, act=act, residual=r, out=y, algo=ops.ALGO_TCGEN05)
+        ops.conv2d(x, w, None, bi, stride=s, pad=(k - 1) // 2, act=act, residual=r, out=y, algo=ALGO)
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / reps
     M = B * Ho * Wo
     fl = 2.0 * M * Cout * k * k * Cin
-    by = 2.0 * (B * H * W * Cin + Cout * k * k * Cin + M * Cout * (2 if res else 1))
+    by = (4.0 if SPLIT else 2.0) * (B * H * W * Cin + Cout * k * k * Cin + M * Cout * (2 if res else 1))
     print(f"{n:12} {us:8.1f} {fl/us/1e6:7.0f} {by/us/1e3:7.0f}  {H}x{W} {Cin}->{Cout} k{k} s{s}{' +res' if res else ''}")

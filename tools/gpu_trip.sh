@@ -30,6 +30,7 @@ for s in $STAGES; do
     trace4) (for d in 8 12 28 24; do for c in 0 1; do echo "### DBG=$d CTA2=$c"; FB200_TC_DBG=$d FB200_TC_CTA2=$c timeout 300 python tools/conv_trace.py rep_3x3_80; done; done; echo "### DBG=12 BN=128"; FB200_TC_DBG=12 FB200_TC_CTA2=0 FB200_TC_BN=128 timeout 300 python tools/conv_trace.py rep_3x3_80; echo "### DBG=28 BN=128"; FB200_TC_DBG=28 FB200_TC_CTA2=0 FB200_TC_BN=128 timeout 300 python tools/conv_trace.py rep_3x3_80; echo "### DBG=4 (TMA on, epilogue off)"; FB200_TC_DBG=4 FB200_TC_CTA2=0 timeout 300 python tools/conv_trace.py rep_3x3_80; FB200_TC_DBG=4 FB200_TC_CTA2=1 timeout 300 python tools/conv_trace.py rep_3x3_80; true) 2>&1 | grep -v "^cta\|tile[0-9]" > gpurun_out/conv_trace4.txt ;;
     trace5) (for d in 36 4; do for c in 0 1; do echo "### DBG=$d CTA2=$c"; FB200_TC_DBG=$d FB200_TC_CTA2=$c timeout 300 python tools/conv_trace.py rep_3x3_80 s2_2a; done; done; true) 2>&1 | grep -v "^cta\|tile[0-9]" > gpurun_out/conv_trace5.txt ;;
     trace6) (for d in 0 64 192; do echo "### DBG=$d CTA2=0"; FB200_TC_DBG=$d FB200_TC_CTA2=0 timeout 300 python tools/conv_trace.py rep_3x3_80; done; true) 2>&1 | grep -v "^cta\|tile[0-9]" > gpurun_out/conv_trace6.txt ;;
+    microfs) (FB200_TC_FS=0 timeout 300 python tools/conv_micro.py --split; true) > gpurun_out/conv_micro_split_seg.txt 2>&1; (timeout 300 python tools/conv_micro.py --split; true) > gpurun_out/conv_micro_split_fs.txt 2>&1 ;;
     trace) (FB200_TC_CTA2=0 timeout 300 python tools/conv_trace.py rep_3x3_80 rep_3x3_40 s3_2b s2_2a s0_2c; timeout 300 python tools/conv_trace.py rep_3x3_80 rep_3x3_40; true) > gpurun_out/conv_trace.txt 2>&1 ;;
     budget2) timeout 1200 python tools/error_budget.py tc:3323 tc:3331 tc:3332 tc:2222 tc:1111 > gpurun_out/error_budget2.txt 2>&1 ;;
     micro01) (FB200_TC_CTA2=0 timeout 300 python tools/conv_micro.py; true) > gpurun_out/conv_micro_cta1.txt 2>&1; (timeout 300 python tools/conv_micro.py; true) > gpurun_out/conv_micro_cta2.txt 2>&1 ;;
