@@ -238,14 +238,14 @@ template <int BLOCK_K> __host__ __device__ constexpr bool is_halo() { return BLO
 template <int BLOCK_K> __host__ __device__ constexpr int phys_k() { return BLOCK_K == 96 ? 32 : BLOCK_K; }  // channels per shared-memory row
 // FS ("fused split", fp32-accurate mode): one ring stage holds the hi AND lo halves of both operands of a 64-channel chunk - A_hi, A_lo, B_hi, B_lo are loaded ONCE
 // and feed the three products hi x W_hi, hi x W_lo, lo x W_hi (the segmented layout streams every operand tile through the TMA engine / L2 three times)
-template <int BLOCK_N, int BLOCK_K, bool FS = false> __host__ __device__ constexpr int a_stage_bytes() { return BLOCK_K == 96 ? 9216 : (FS ? 2 : 1) * BLOCK_M * BLOCK_K * 2; }  // halo: 130 rows x 64 B, 1 KiB aligned
+template <int BLOCK_N, int BLOCK_K, bool FS = false> __host__ __device__ constexpr int a_stage_bytes() { return BLOCK_K == 96 ? (FS ? 2 : 1) * 9216 : (FS ? 2 : 1) * BLOCK_M * BLOCK_K * 2; }  // halo: 130 rows x 64 B, 1 KiB aligned
 template <int BLOCK_N, int BLOCK_K, bool CTA2 = false, bool FS = false> __host__ __device__ constexpr int b_stage_bytes() { return BLOCK_K == 96 ? 0 : (FS ? 2 : 1) * (CTA2 ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2; }
 // halo mode keeps ALL NINE weight taps resident in shared memory for the life of the persistent CTA (9 x BLOCK_N x 64 B <= 36 KiB): per tile only the
 // three input strips travel from L2
-template <int BLOCK_N, int BLOCK_K> __host__ __device__ constexpr int b_resident_bytes() { return BLOCK_K == 96 ? 9 * BLOCK_N * 64 : 0; }
+template <int BLOCK_N, int BLOCK_K, bool FS = false> __host__ __device__ constexpr int b_resident_bytes() { return BLOCK_K == 96 ? (FS ? 18 : 9) * BLOCK_N * 64 : 0; }  // FS: W_hi and W_lo of every tap
 template <int BLOCK_N, int BLOCK_K, bool CTA2 = false, bool FS = false> constexpr int stage_bytes() { return a_stage_bytes<BLOCK_N, BLOCK_K, FS>() + b_stage_bytes<BLOCK_N, BLOCK_K, CTA2, FS>(); }
 template <int BLOCK_N, int STAGES, int BLOCK_K, int NSTG, bool CTA2 = false, bool FS = false> constexpr int smem_bytes() {
-  return STAGES * stage_bytes<BLOCK_N, BLOCK_K, CTA2, FS>() + b_resident_bytes<BLOCK_N, BLOCK_K>() + NSTG * epi_groups<BLOCK_N>() * STAGING_BYTES + 2 * BLOCK_N * 4 +
+  return STAGES * stage_bytes<BLOCK_N, BLOCK_K, CTA2, FS>() + b_resident_bytes<BLOCK_N, BLOCK_K, FS>() + NSTG * epi_groups<BLOCK_N>() * STAGING_BYTES + 2 * BLOCK_N * 4 +
          (2 * STAGES + 5 + NSTG * epi_groups<BLOCK_N>()) * 8 + 16 + (FS ? 0 : 1024) /*align slack; the FS configurations need every byte and rely on the 1024-byte alignment of dynamic shared memory (checked in the kernel)*/;
 }
 
@@ -262,7 +262,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   constexpr int A_STAGE_BYTES = a_stage_bytes<BLOCK_N, BLOCK_K, FS>();
   constexpr int B_STAGE_BYTES = b_stage_bytes<BLOCK_N, BLOCK_K, CTA2, FS>();
   static_assert(!(CTA2 && HALO), "the halo mode is single-CTA");
-  static_assert(!(FS && (HALO || BLOCK_K != 64)), "the fused-split mode works on 64-channel chunks");
+  static_assert(!(FS && !HALO && BLOCK_K != 64), "the fused-split mode works on 64-channel chunks (or on the 32-channel halo strips)");
   constexpr int A_HALF = BLOCK_M * 64 * 2;                                  // FS: bytes of one A half (hi or lo) inside a stage
   constexpr int B_HALF = (CTA2 ? BLOCK_N / 2 : BLOCK_N) * 64 * 2;           // FS: bytes of one B half
   uint32_t cta_rank = 0;  // CTA pair: 0 = leader (issues the MMAs), 1 = peer
@@ -274,7 +274,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
   constexpr int EPI_GROUPS = epi_groups<BLOCK_N>();
   uint8_t* smem_w = smem_b + STAGES * B_STAGE_BYTES;   // halo mode: the nine resident weight taps
-  uint8_t* staging = smem_w + b_resident_bytes<BLOCK_N, BLOCK_K>();  // EPI_GROUPS x NSTG x 16 KiB
+  uint8_t* staging = smem_w + b_resident_bytes<BLOCK_N, BLOCK_K, FS>();  // EPI_GROUPS x NSTG x 16 KiB
   float* s_scale = reinterpret_cast<float*>(staging + EPI_GROUPS * NSTG * STAGING_BYTES);
   float* s_bias = s_scale + BLOCK_N;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_bias + BLOCK_N);
@@ -336,10 +336,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 0) {
     // ===================================================================== TMA producer
     if (lane == 0) {
-      const uint32_t tx_bytes = HALO ? (uint32_t)((p.BW + 2) * 64) : (uint32_t)(p.BW * p.BH * BKP * 2) + (uint32_t)B_STAGE_BYTES;
-      if constexpr (HALO) {  // the nine weight taps, once
-        mbar_arrive_expect_tx(w_bar, (uint32_t)b_resident_bytes<BLOCK_N, BLOCK_K>());
-        for (int tap = 0; tap < 9; ++tap) tma_load_2d(&tmap_b, w_bar, smem_w + tap * (BLOCK_N * 64), tap * 32, 0);
+      const uint32_t tx_bytes = HALO ? (uint32_t)((FS ? 2 : 1) * (p.BW + 2) * 64) : (uint32_t)(p.BW * p.BH * BKP * 2) + (uint32_t)B_STAGE_BYTES;
+      if constexpr (HALO) {  // the nine weight taps, once (fused split: W_hi and W_lo of each tap; the packed row of a tap is [W_hi | W_lo | W_hi] = 96 halves)
+        mbar_arrive_expect_tx(w_bar, (uint32_t)b_resident_bytes<BLOCK_N, BLOCK_K, FS>());
+        if constexpr (FS) {
+          for (int tap = 0; tap < 9; ++tap) {
+            tma_load_2d(&tmap_b, w_bar, smem_w + (tap * 2) * (BLOCK_N * 64), tap * 96, 0);
+            tma_load_2d(&tmap_b, w_bar, smem_w + (tap * 2 + 1) * (BLOCK_N * 64), tap * 96 + 32, 0);
+          }
+        } else {
+          for (int tap = 0; tap < 9; ++tap) tma_load_2d(&tmap_b, w_bar, smem_w + tap * (BLOCK_N * 64), tap * 32, 0);
+        }
       }
       // channel coordinate of K-chunk cc.  Split-precision mode (fp32-accurate products from fp16 tensor cores): the stored tensor is
       // [hi(C) | lo(C)] and K runs over three segments  hi x W_hi,  hi x W_lo,  lo x W_hi  (weights packed [W_hi | W_lo | W_hi]).
@@ -361,6 +368,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             mbar_wait(&empty_bar[stage], phase ^ 1);
             mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
             tma_load_4d(&tmap_a, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, 0, w0 - 1, h0 + kh - 1, img);
+            if constexpr (FS) tma_load_4d(&tmap_a, &full_bar[stage], smem_a + stage * A_STAGE_BYTES + 9216, p.lo_off, w0 - 1, h0 + kh - 1, img);  // the lo strip
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
           continue;
@@ -495,7 +503,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (kb == 0) stamp(3 + 6 * tk);
           const uint64_t da = make_smem_desc<BKP>(smem_u32(smem_a + stage * A_STAGE_BYTES));
           const uint64_t db = make_smem_desc<BKP>(smem_u32(smem_b + stage * B_STAGE_BYTES));
-          if constexpr (FS) {
+          if constexpr (FS && HALO) {
+            const uint64_t da_lo = make_smem_desc<BKP>(smem_u32(smem_a + stage * A_STAGE_BYTES + 9216));
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {  // the strip shifted by kw pixels; three products per 16-channel step
+              const uint64_t ah = da + (uint64_t)(kw * 4), al = da_lo + (uint64_t)(kw * 4);
+              const uint64_t bh = make_smem_desc<BKP>(smem_u32(smem_w + ((kb * 3 + kw) * 2) * (BLOCK_N * 64)));
+              const uint64_t bl = make_smem_desc<BKP>(smem_u32(smem_w + ((kb * 3 + kw) * 2 + 1) * (BLOCK_N * 64)));
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                const uint64_t ko = (uint64_t)(k * 2);
+                umma_f16(tmem_d, ah + ko, bh + ko, idesc, (kb > 0 || kw > 0 || k > 0) ? 1u : 0u);
+                umma_f16(tmem_d, ah + ko, bl + ko, idesc, 1u);
+                umma_f16(tmem_d, al + ko, bh + ko, idesc, 1u);
+              }
+            }
+          } else if constexpr (FS) {
             const uint64_t da_lo = make_smem_desc<BKP>(smem_u32(smem_a + stage * A_STAGE_BYTES + A_HALF));
             const uint64_t db_lo = make_smem_desc<BKP>(smem_u32(smem_b + stage * B_STAGE_BYTES + B_HALF));
             auto issue = [&](uint64_t a, uint64_t b, uint32_t acc_flag) {
@@ -913,8 +936,9 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
   // halo mode (see is_halo): 32-channel 3x3 stride-1 convs, fp16 in, no residual.  FB200_TC_HALO=0 disables, =2 also sets the descriptor base offset
   static int halo_env = -1;
   if (halo_env < 0) { const char* e = getenv("FB200_TC_HALO"); halo_env = e ? atoi(e) : 1; }
-  const bool halo = halo_env != 0 && BK == 32 && p.Cin == 32 && !p.split3 && p.KH == 3 && p.KW == 3 && p.stride == 1 && p.pad == 1 && !p.res && p.w_bs == 0 &&
-                    !p.rowmax && (p.act & 15) != FB200_ACT_GELU && Wo >= 64 && p.Cout <= 64;
+  const bool halo_shape = halo_env != 0 && BK == 32 && Clog == 32 && p.KH == 3 && p.KW == 3 && p.stride == 1 && p.pad == 1 && !p.res && p.w_bs == 0 &&
+                          !p.rowmax && (p.act & 15) != FB200_ACT_GELU && Wo >= 64 && p.Cout <= 64;
+  const bool halo = halo_shape && (!p.split3 || p.out_dtype == FB200_F32);
   kp.halo_boff = halo_env == 2 ? 1 : 0;
   int BW = 1, BH = 1;
   if (halo) { BW = 128; BH = 1; kp.num_k_blocks = 3; }
@@ -975,7 +999,7 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
       if (r2) return r2;
     }
     KParams k2 = kp;
-    if constexpr (FS_) {  // fused split: k-blocks run over (tap, 64-channel chunk); the hi / lo halves of both operands travel together
+    if constexpr (FS_ && BK_ != 96) {  // fused split: k-blocks run over (tap, 64-channel chunk); the hi / lo halves of both operands travel together
       k2.cchunks = Clog / 64;
       k2.num_k_blocks = p.KH * p.KW * k2.cchunks;
       k2.seg_chunks = 0;
@@ -1007,6 +1031,10 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
   if ((p.act & 15) == FB200_ACT_GELU)  // exact-erf GELU: dedicated instantiation (fp16 out, Cin % 64 == 0; checked in conv2d_tc_supported)
     return run(integral_constant<int, 128>{}, integral_constant<int, 4>{}, I1{}, K64{}, I2{}, std::true_type{}, C1{}, NF{});
   typedef integral_constant<int, 96> K96;  // halo mode tag
+  if (halo && p.split3) {  // fp32-accurate: hi and lo strips, W_hi and W_lo of all nine taps resident (74 / 37 KiB), one CTA per SM
+    if (p.Cout > 32) return run(integral_constant<int, 64>{}, integral_constant<int, 4>{}, I1{}, K96{}, I2{}, std::false_type{}, C1{}, FS{});
+    return run(integral_constant<int, 32>{}, integral_constant<int, 4>{}, I1{}, K96{}, I2{}, std::false_type{}, C1{}, FS{});
+  }
   if (halo) {
     if (p.Cout > 32) return run(integral_constant<int, 64>{}, integral_constant<int, 4>{}, I2{}, K96{}, I2{}, std::false_type{}, C1{}, NF{});
     return run(integral_constant<int, 32>{}, integral_constant<int, 4>{}, I2{}, K96{}, I2{}, std::false_type{}, C1{}, NF{});
@@ -1032,12 +1060,21 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
   // engine delivers ~65-80 B/cycle/SM plus ~110 cycles per instruction (profiles/r02_conv_timeline.md), the segmented layout needs 96 B/cycle at the tensor peak
   static int fs_env = -1;  // FB200_TC_FS=0 disables
   if (fs_env < 0) { const char* e = getenv("FB200_TC_FS"); fs_env = e ? atoi(e) : 1; }
-  if (fs_env && p.split3 && BK == 64 && p.out_dtype == FB200_F32 && !p.rowmax && !kp.w_batched && p.Cout > 64) {
-    if (p.Cout > 128 && g_cta_pair_mode != 0)
-      return run(integral_constant<int, 256>{}, integral_constant<int, 3>{}, I1{}, K64{}, I1{}, std::false_type{}, C2{}, FS{});   // pair: 3 x 64 + 32 KiB
+  if (fs_env && p.split3 && BK == 64 && p.out_dtype == FB200_F32 && !p.rowmax && !kp.w_batched) {
+    // deep K loops want the 3-stage ring (and have a long main loop to hide a single staging buffer behind); layers with a residual (fetched by TMA into the
+    // SECOND staging buffer) or a short K loop are bound by the epilogue / HBM: two stages, double-buffered staging
+    const bool deep = !p.res && p.KH * p.KW * (Clog / 64) > 4;
+    if (p.Cout > 128 && g_cta_pair_mode != 0) {
+      if (deep) return run(integral_constant<int, 256>{}, integral_constant<int, 3>{}, I1{}, K64{}, I1{}, std::false_type{}, C2{}, FS{});   // pair: 3 x 64 + 32 KiB
+      return run(integral_constant<int, 256>{}, integral_constant<int, 2>{}, I1{}, K64{}, I2{}, std::false_type{}, C2{}, FS{});             // pair: 2 x 64 + 64 KiB
+    }
     if (p.Cout > 128)
       return run(integral_constant<int, 256>{}, integral_constant<int, 2>{}, I1{}, K64{}, I1{}, std::false_type{}, C1{}, FS{});   // 2 x 96 + 32 KiB
-    return run(integral_constant<int, 128>{}, integral_constant<int, 3>{}, I1{}, K64{}, I1{}, std::false_type{}, C1{}, FS{});     // 3 x 64 + 32 KiB
+    if (p.Cout > 64) {
+      if (deep) return run(integral_constant<int, 128>{}, integral_constant<int, 3>{}, I1{}, K64{}, I1{}, std::false_type{}, C1{}, FS{});   // 3 x 64 + 32 KiB
+      return run(integral_constant<int, 128>{}, integral_constant<int, 2>{}, I1{}, K64{}, I2{}, std::false_type{}, C1{}, FS{});             // 2 x 64 + 64 KiB
+    }
+    return run(integral_constant<int, 64>{}, integral_constant<int, 3>{}, I1{}, K64{}, I2{}, std::false_type{}, C1{}, FS{});      // 3 x 48 + 32 KiB (HBM-bound layers)
   }
   if (cfg_env == 1 && pair_ok && p.Cout > 128 && !p.res)
     return run(integral_constant<int, 256>{}, integral_constant<int, 5>{}, I1{}, K64{}, I1{}, std::false_type{}, C2{}, NF{});   // 5 x 32 + 32 KiB

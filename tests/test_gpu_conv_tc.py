@@ -96,7 +96,10 @@ def test_conv_cin32_swizzle64(H, W, Cin, Cout, k):
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,k,stride,res", [(2, 20, 20, 256, 256, 3, 1, False), (1, 1, 1000, 256, 512, 1, 1, True), (2, 40, 40, 128, 128, 3, 2, False),
-                                                          (2, 32, 32, 32, 64, 3, 1, False), (1, 1, 300, 1024, 256, 1, 1, True)])
+                                                          (2, 32, 32, 32, 64, 3, 1, False), (1, 1, 300, 1024, 256, 1, 1, True),
+                                                          (2, 40, 200, 32, 64, 3, 1, False), (1, 33, 130, 32, 32, 3, 1, False),   # halo strips (hi + lo), resident W_hi / W_lo
+                                                          (2, 24, 40, 256, 64, 1, 1, False), (2, 40, 40, 64, 64, 3, 1, False),     # fused split, N = 64
+                                                          (3, 20, 20, 512, 2048, 1, 1, True), (2, 80, 80, 256, 256, 3, 2, False)])  # pair + residual (2-stage ring), stride-2 pair
 def test_split_precision_conv_matches_fp32(B, H, W, Cin, Cout, k, stride, res):
     """precision="fp32_tc": fp32 tensors, three fp16 tensor-core products (hi*hi + hi*lo + lo*hi) -> fp32-level agreement."""
     from focoos_b200.fai_detr import _split3_weights
