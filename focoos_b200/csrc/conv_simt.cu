@@ -66,6 +66,22 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const void* __restrict__
       }
     }
   }
+  if (act & 256) {  // FB200_F16PAIR output: [hi(COUT) | lo(COUT)] fp16 per pixel (TOut is __half)
+    __half* o = reinterpret_cast<__half*>(out) + pix * 2 * COUT;
+#pragma unroll
+    for (int co = 0; co < COUT; co += 4) {
+      float v[4], h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[j] = apply_act(acc[co + j] * sc[co + j] + bi[co + j], act);
+        h[j] = __half2float(__float2half_rn(v[j]));
+        l[j] = v[j] - h[j];
+      }
+      store4(o + co, h);
+      store4(o + COUT + co, l);
+    }
+    return;
+  }
   TOut* o = out + pix * COUT;
 #pragma unroll
   for (int co = 0; co < COUT; co += 4) {
@@ -248,6 +264,7 @@ static int stem_launch(const void* img, bool u8, int B, int H, int W, const floa
 #define STEM_LAUNCH(T, U8) stem_conv_kernel<T, 32, U8><<<grid, 128, 0, st>>>(img, B, H, W, w, scale, bias, m[0], m[1], m[2], s[0], s[1], s[2], act, (T*)out)
   if (out_dtype == FB200_F32) { if (u8) STEM_LAUNCH(float, true); else STEM_LAUNCH(float, false); }
   else if (out_dtype == FB200_F16) { if (u8) STEM_LAUNCH(__half, true); else STEM_LAUNCH(__half, false); }
+  else if (out_dtype == FB200_F16PAIR) { act |= 256; if (u8) STEM_LAUNCH(__half, true); else STEM_LAUNCH(__half, false); }  // dense [hi(32) | lo(32)] pair per pixel
   else { set_error("stem_conv: bad dtype"); return FB200_ERR_INVALID; }
 #undef STEM_LAUNCH
   FB_CHECK_LAUNCH("stem_conv_kernel");
@@ -284,6 +301,30 @@ extern "C" int fb200_conv2d_per_image_weights(const void* x, int x_dtype, int B,
   FB_CHECK_ARG(w_batch_stride >= (int64_t)Cout * KH * KW * Cin, "conv2d_per_image_weights: weight batch stride smaller than one weight set");
   return conv2d_impl(x, x_dtype, B, H, W, Cin, x_pitch, w, w_batch_stride, KH, KW, stride, pad, scale, bias, nullptr, 0, act, out, out_dtype, out_pitch, 0, Cout, algo,
                      stream);
+}
+
+extern "C" int fb200_conv2d_pair(const void* x, int B, int H, int W, int C, int x_pitch, int64_t x_lo_off, const void* w3, int KH, int KW, int stride, int pad,
+                                 const float* scale, const float* bias, const void* residual, int res_pitch, int64_t res_lo_off, int act, void* out, int out_dtype,
+                                 int out_pitch, int64_t out_lo_off, int64_t out_batch_stride, int Cout, void* stream) {
+  FB_CHECK_ARG(x && w3 && out, "conv2d_pair: null pointer");
+  FB_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && Cout > 0 && KH > 0 && KW > 0 && stride > 0 && pad >= 0, "conv2d_pair: bad shape");
+  FB_CHECK_ARG(out_dtype == FB200_F32 || out_dtype == FB200_F16PAIR, "conv2d_pair: output is fp32 or the fp16 pair");
+  FB_CHECK_ARG(x_lo_off >= C && x_pitch >= x_lo_off + C, "conv2d_pair: the lo plane must lie inside the pixel pitch, after the hi plane");
+  ConvParams p;
+  p.split3 = 1;
+  p.x = x; p.w = w3; p.scale = scale; p.bias = bias; p.res = residual; p.out = out;
+  p.B = B; p.H = H; p.W = W; p.Cin = 3 * C; p.x_pitch = x_pitch; p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad;
+  p.Ho = (H + 2 * pad - KH) / stride + 1; p.Wo = (W + 2 * pad - KW) / stride + 1;
+  FB_CHECK_ARG(p.Ho > 0 && p.Wo > 0, "conv2d_pair: empty output");
+  p.Cout = Cout; p.res_pitch = res_pitch; p.out_pitch = out_pitch; p.act = act;
+  p.M = (int64_t)B * p.Ho * p.Wo; p.K = KH * KW * 3 * C; p.x_dtype = FB200_F16; p.out_dtype = out_dtype; p.vec_ok = 1;
+  p.out_bs = out_batch_stride > 0 ? out_batch_stride : (int64_t)p.Ho * p.Wo * out_pitch;
+  p.x_lo_off = x_lo_off; p.out_lo_off = out_lo_off; p.res_lo_off = res_lo_off;
+  if (!conv2d_tc_supported(p, FB200_F16, out_dtype)) {
+    set_error("conv2d_pair: shape / alignment not supported by the tcgen05 split path (C=%d Cout=%d k=%dx%d s=%d out_dtype=%d)", C, Cout, KH, KW, stride, out_dtype);
+    return FB200_ERR_UNSUPPORTED;
+  }
+  return conv2d_tc(p, (cudaStream_t)stream);
 }
 
 extern "C" int fb200_linear_rowmax(const void* x, int64_t M, int K, int x_pitch, const void* w, const float* bias, int Cout, float* rowmax, void* stream) {

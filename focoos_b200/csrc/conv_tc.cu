@@ -39,11 +39,19 @@ constexpr int PRODUCER_THREADS = 128;  // warps 0-3: TMA, MMA, TMEM alloc, spare
 template <int BLOCK_N> __host__ __device__ constexpr int epi_groups() { return BLOCK_N >= 128 ? 2 : 1; }
 template <int BLOCK_N> __host__ __device__ constexpr int num_threads() { return PRODUCER_THREADS + 128 * epi_groups<BLOCK_N>(); }
 
+// Output / residual stored as the fp16 [hi | lo] PAIR of the fp32 value (hi = fp16(v), lo = fp16(v - hi)): the operand format of the fp32-accurate convs,
+// written straight from the epilogue so that no separate split pass runs between two convs.  sizeof == 4: a staging chunk is 32 columns like fp32, laid out as
+// two dense [128 rows x 64 B] tiles (hi, then lo at +8 KiB), 64-byte swizzle, each stored / loaded with its own tensor map.
+struct PairOut { __half hi, lo; };
+template <typename T> struct is_pair { static constexpr bool value = false; };
+template <> struct is_pair<PairOut> { static constexpr bool value = true; };
+
 struct KParams {
   const float* scale; const float* bias; const void* res;
   int res_pitch, act, Cout;
   int KH, KW, pad, cchunks;        // cchunks = Cin / BLOCK_K (3C/BLOCK_K in split-precision mode)
-  int seg_chunks, lo_off;          // split-precision: chunks per K segment (C/BLOCK_K) and channel offset of the lo half (C); 0 = off
+  int seg_chunks, lo_off;          // split-precision: chunks per K segment (C/BLOCK_K) and channel offset of the A operand's lo half (C unless the input is a channel slice of a wider pair buffer); 0 = off
+  int w_seg;                       // split-precision: channels per weight segment ([W_hi | W_lo | W_hi] per tap)
   int BW, BH, tiles_w, tiles_h;    // output tile rectangle and tile counts per image
   int Ho, Wo;                      // output spatial size (residual addressing / validity)
   int x_pitch;                     // stride-2 view only (c' = wp * pitch + c)
@@ -253,7 +261,9 @@ template <int BLOCK_N, int STAGES, int BLOCK_K, int NSTG, bool CTA2 = false, boo
 template <int BLOCK_N, int STAGES, typename TOut, int MIN_BLOCKS, int BLOCK_K, int NSTG, bool GELU, bool CTA2, bool FS>
 __global__ void __launch_bounds__(num_threads<BLOCK_N>(), MIN_BLOCKS)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r, const KParams p) {
+               const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r,
+               const __grid_constant__ CUtensorMap tmap_d2, const __grid_constant__ CUtensorMap tmap_r2, const KParams p) {
+  constexpr bool PAIR = is_pair<TOut>::value;  // tmap_d2 / tmap_r2: the lo planes of the output / residual (pair format only)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   if constexpr (FS) { if (smem != smem_raw) __trap(); }  // no alignment slack in the FS configurations
@@ -396,7 +406,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             uint8_t* dst_a = smem_a + stage * A_STAGE_BYTES;
             uint8_t* dst_b = smem_b + stage * B_STAGE_BYTES;
             const int c_hi = cc * 64, c_lo = p.lo_off + cc * 64;
-            const int k_hi = tap * 3 * p.lo_off + cc * 64, k_lo = k_hi + p.lo_off;  // weights packed [W_hi | W_lo | W_hi] per tap
+            const int k_hi = tap * 3 * p.w_seg + cc * 64, k_lo = k_hi + p.w_seg;  // weights packed [W_hi | W_lo | W_hi] per tap
             const uint32_t fs_bytes = 2u * (uint32_t)(p.BW * p.BH * 128) + (uint32_t)B_STAGE_BYTES;
             if constexpr (CTA2) {
               if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * fs_bytes);
@@ -585,7 +595,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const bool has_res = p.res != nullptr && !(p.dbg & 2);
     uint4 rcur[RES_VECS];
     auto res_fetch = [&](int tt, int cc0, uint4 (&dst)[RES_VECS]) -> bool {
-      if (!has_res || tt >= p.total_tiles) return false;
+      if (PAIR || !has_res || tt >= p.total_tiles) return false;  // pair residuals always come through TMA
       const TileXY tx = tile_of(tt);
       const int n0_ = tx.n0, img_ = tx.img;
       if (n0_ + cc0 + CHUNK_COLS > p.Cout || cc0 + CHUNK_COLS > c_end) return false;
@@ -610,6 +620,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint64_t* bar = &my_res_bar[k % NSTG];
       mbar_arrive_expect_tx(bar, res_box_bytes);
       tma_load_4d(&tmap_r, bar, my_staging + (k % NSTG) * STAGING_BYTES, n0_ + cc0, w0_, h0_, img_);
+      if constexpr (PAIR) tma_load_4d(&tmap_r2, bar, my_staging + (k % NSTG) * STAGING_BYTES + STAGING_BYTES / 2, n0_ + cc0, w0_, h0_, img_);
     };
     if (res_tma && et == 0 && chunk_valid(t_first, c_begin)) issue_res(t_first, c_begin, 0);
     for (int t = t_first; t < p.total_tiles; t += t_stride) {
@@ -617,7 +628,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int n0 = tc.n0, img = tc.img, h0 = tc.h0, w0 = tc.w0;
       const int ho = h0 + bh, wo = w0 + bw;
       const bool row_valid = (row < p.BW * p.BH) && ho < p.Ho && wo < p.Wo && img < p.nimg;
-      const TOut* res_row = has_res ? reinterpret_cast<const TOut*>(p.res) + (((int64_t)img * p.Ho + ho) * p.Wo + wo) * p.res_pitch : nullptr;
       if (has_res && !res_tma && et == 0) {  // L2 prefetch of the NEXT tile's residual columns owned by this group
         const int tn = t + t_stride;
         if (tn < p.total_tiles) {
@@ -691,7 +701,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           auto add_residual = [&]() {
             if (res_tma) {  // this thread's row of the TMA-loaded residual box, 16-byte pieces at the swizzled positions it will overwrite below
-              if constexpr (sizeof(TOut) == 2) {
+              if constexpr (PAIR) {
+                const uint8_t* hrow = stg + row * 64;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const int ph = (q ^ ((row >> 1) & 3)) << 4;
+                  const uint4 th = *reinterpret_cast<const uint4*>(hrow + ph), tl = *reinterpret_cast<const uint4*>(hrow + STAGING_BYTES / 2 + ph);
+                  const uint32_t hw[4] = {th.x, th.y, th.z, th.w}, lw[4] = {tl.x, tl.y, tl.z, tl.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&hw[e])), fl = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
+                    v[q * 8 + 2 * e] += fh.x + fl.x;
+                    v[q * 8 + 2 * e + 1] += fh.y + fl.y;
+                  }
+                }
+              } else if constexpr (sizeof(TOut) == 2) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                   const uint4 t4 = *reinterpret_cast<const uint4*>(srow + (((sub * 4 + q) ^ (row & 7)) << 4));
@@ -732,7 +756,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           act32<GELU>(v, p.act);
           if (post) add_residual();
           // 16-byte pieces into the 128B-swizzled staging row: physical chunk = logical chunk ^ (row & 7)
-          if constexpr (sizeof(TOut) == 2) {
+          if constexpr (PAIR) {  // two dense 64-byte-row tiles (hi, lo), 64-byte swizzle: physical chunk = logical chunk ^ ((row >> 1) & 3)
+            uint8_t* hrow = stg + row * 64;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint32_t hw[4], lw[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float a = v[q * 8 + 2 * e], b = v[q * 8 + 2 * e + 1];
+                const __half2 h = __floats2half2_rn(a, b);
+                const float2 hf = __half22float2(h);
+                const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+                hw[e] = *reinterpret_cast<const uint32_t*>(&h);
+                lw[e] = *reinterpret_cast<const uint32_t*>(&l);
+              }
+              const int ph = (q ^ ((row >> 1) & 3)) << 4;
+              *reinterpret_cast<uint4*>(hrow + ph) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              *reinterpret_cast<uint4*>(hrow + STAGING_BYTES / 2 + ph) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
+          } else if constexpr (sizeof(TOut) == 2) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {  // 8 halves per 16 B
               __half2 h0_ = __floats2half2_rn(v[q * 8 + 0], v[q * 8 + 1]), h1_ = __floats2half2_rn(v[q * 8 + 2], v[q * 8 + 3]);
@@ -753,7 +795,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         fence_proxy_async();
         epi_bar(grp);
         if (et == 0) {
-          if (!(p.dbg & 1)) tma_store_4d(&tmap_d, stg, n0 + c0, w0, h0, img);
+          if (!(p.dbg & 1)) {
+            tma_store_4d(&tmap_d, stg, n0 + c0, w0, h0, img);
+            if constexpr (PAIR) tma_store_4d(&tmap_d2, stg + STAGING_BYTES / 2, n0 + c0, w0, h0, img);
+          }
           tma_store_commit();
         }
         ++chunk_ctr;
@@ -839,7 +884,8 @@ static int num_sms() {
 }
 
 template <int BLOCK_N, int STAGES, typename TOut, int MIN_BLOCKS, int BLOCK_K, int NSTG, bool GELU, bool CTA2 = false, bool FS = false>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr, const KParams& kp, cudaStream_t st) {
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr, const CUtensorMap& td2, const CUtensorMap& tr2,
+                  const KParams& kp, cudaStream_t st) {
   auto kern = conv_tc_kernel<BLOCK_N, STAGES, TOut, MIN_BLOCKS, BLOCK_K, NSTG, GELU, CTA2, FS>;
   constexpr int smem = smem_bytes<BLOCK_N, STAGES, BLOCK_K, NSTG, CTA2, FS>();
   constexpr int NUM_THREADS = num_threads<BLOCK_N>();
@@ -865,14 +911,14 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, td, tr, kp);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, td, tr, td2, tr2, kp);
     if (e != cudaSuccess) { set_error("conv_tc(cta pair): launch failed: %s", cudaGetErrorString(e)); return FB200_ERR_CUDA; }
     return FB200_OK;
   }
   int64_t cap = (int64_t)num_sms() * MIN_BLOCKS;
   { static int gc = -1; if (gc < 0) { const char* e = getenv("FB200_GRID_CAP"); gc = e ? atoi(e) : 0; } if (gc > 0 && gc < cap) cap = gc; }  // experiment: fewer SMs
   const unsigned grid = (unsigned)(kp.total_tiles < cap ? kp.total_tiles : cap);
-  kern<<<grid, NUM_THREADS, smem, st>>>(ta, tb, td, tr, kp);
+  kern<<<grid, NUM_THREADS, smem, st>>>(ta, tb, td, tr, td2, tr2, kp);
   FB_CHECK_LAUNCH("conv_tc_kernel");
   return FB200_OK;
 }
@@ -892,15 +938,21 @@ int conv_tc_set_pair_mode(int v) {
 
 bool conv2d_tc_supported(const ConvParams& p, int x_dtype, int out_dtype) {
   if (x_dtype != FB200_F16) return false;
-  if (out_dtype != FB200_F16 && out_dtype != FB200_F32) return false;
+  if (out_dtype != FB200_F16 && out_dtype != FB200_F32 && out_dtype != FB200_F16PAIR) return false;
   const int Clog = p.split3 ? p.Cin / 3 : p.Cin;  // channels of one K segment
+  if (out_dtype == FB200_F16PAIR) {  // pair output: fused-split layers (64-channel chunks or the 32-channel halo strips), planes 16-byte aligned
+    if (!p.split3 || (Clog % 64 != 0 && Clog != 32) || p.rowmax || p.w_bs != 0 || p.Cout % 8 != 0) return false;
+    if ((p.out_lo_off * 2) % 16 != 0 || (p.out_pitch * 2) % 16 != 0 || (p.out_bs * 2) % 16 != 0) return false;
+    if (p.res && ((p.res_lo_off * 2) % 16 != 0 || (p.res_pitch * 2) % 16 != 0 || p.Cout % 32 != 0)) return false;
+  }
+  if (p.split3 && p.x_lo_off && (p.x_lo_off * 2) % 16 != 0) return false;
   if (Clog % 32 != 0 || p.x_pitch % 8 != 0) return false;
   if (p.split3 && p.Cin % 3 != 0) return false;
   if ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.w) | reinterpret_cast<uintptr_t>(p.out)) & 15) return false;
-  const int oelt = out_dtype == FB200_F16 ? 2 : 4;
+  const int oelt = out_dtype == FB200_F32 ? 4 : 2;   // element size of one stored plane
   if ((p.out_pitch * oelt) % 16 != 0) return false;
   if (p.res && ((p.res_pitch * oelt) % 16 != 0 || (reinterpret_cast<uintptr_t>(p.res) & 15))) return false;
-  if (p.res && p.Cout % (128 / oelt) != 0) return false;  // residual is consumed in whole 128-byte row chunks
+  if (p.res && out_dtype != FB200_F16PAIR && p.Cout % (128 / oelt) != 0) return false;  // residual is consumed in whole 128-byte row chunks
   if (p.KH != p.KW) return false;
   if (p.w_bs != 0 && (p.w_bs * 2) % 16 != 0) return false;
   if ((p.act & 15) == FB200_ACT_GELU && (out_dtype != FB200_F16 || Clog % 64 != 0)) return false;
@@ -919,7 +971,8 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
   const int Clog = p.split3 ? p.Cin / 3 : p.Cin;
   const int BK = (Clog % 64 == 0) ? 64 : 32;
   kp.seg_chunks = p.split3 ? Clog / BK : 0;
-  kp.lo_off = Clog;
+  kp.lo_off = (p.split3 && p.x_lo_off) ? (int)p.x_lo_off : Clog;
+  kp.w_seg = Clog;
   const CUtensorMapSwizzle swz = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   kp.cchunks = p.Cin / BK; kp.x_pitch = p.x_pitch;
   kp.stride2 = (p.stride == 2) ? 1 : 0;
@@ -938,7 +991,7 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
   if (halo_env < 0) { const char* e = getenv("FB200_TC_HALO"); halo_env = e ? atoi(e) : 1; }
   const bool halo_shape = halo_env != 0 && BK == 32 && Clog == 32 && p.KH == 3 && p.KW == 3 && p.stride == 1 && p.pad == 1 && !p.res && p.w_bs == 0 &&
                           !p.rowmax && (p.act & 15) != FB200_ACT_GELU && Wo >= 64 && p.Cout <= 64;
-  const bool halo = halo_shape && (!p.split3 || p.out_dtype == FB200_F32);
+  const bool halo = halo_shape && (!p.split3 || p.out_dtype == FB200_F32 || p.out_dtype == FB200_F16PAIR);
   kp.halo_boff = halo_env == 2 ? 1 : 0;
   int BW = 1, BH = 1;
   if (halo) { BW = 128; BH = 1; kp.num_k_blocks = 3; }
@@ -950,7 +1003,7 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
   int rc;
   const uint64_t P = (uint64_t)p.x_pitch;
   if (!kp.stride2) {
-    const uint64_t dims[4] = {(uint64_t)(p.split3 ? 2 * Clog : p.Cin), (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t dims[4] = {(uint64_t)(p.split3 ? kp.lo_off + Clog : p.Cin), (uint64_t)W, (uint64_t)H, (uint64_t)B};
     const uint64_t str[4] = {1, P, P * W, P * W * H};
     const uint32_t box[4] = {(uint32_t)BK, (uint32_t)(halo ? BW + 2 : BW), (uint32_t)BH, 1};
     rc = encode(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4, const_cast<void*>(p.x), dims, str, box, "A", swz);
@@ -981,16 +1034,37 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
       if (r2) return r2;
     }
     const bool out16 = p.out_dtype == FB200_F16;
-    {
+    const bool outp = p.out_dtype == FB200_F16PAIR;
+    CUtensorMap tr, td2, tr2;
+    if (outp) {  // two fp16 planes (hi at `out`, lo `out_lo_off` elements further), 32-channel boxes with 64-byte swizzle
+      const uint64_t OP = (uint64_t)p.out_pitch;
+      const uint64_t dims[4] = {(uint64_t)p.Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)B};
+      const uint64_t str[4] = {1, OP, OP * Wo, flat ? OP * Wo * Ho : (uint64_t)p.out_bs};
+      const uint32_t box[4] = {32, (uint32_t)BW, (uint32_t)BH, 1};
+      int r2 = encode(&td, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4, p.out, dims, str, box, "D(hi)", CU_TENSOR_MAP_SWIZZLE_64B);
+      if (r2) return r2;
+      r2 = encode(&td2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4, static_cast<__half*>(p.out) + p.out_lo_off, dims, str, box, "D(lo)", CU_TENSOR_MAP_SWIZZLE_64B);
+      if (r2) return r2;
+      tr = td; tr2 = td2;
+      if (p.res) {
+        const uint64_t RP = (uint64_t)p.res_pitch;
+        const uint64_t rstr[4] = {1, RP, RP * Wo, RP * Wo * Ho};
+        r2 = encode(&tr, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4, const_cast<void*>(p.res), dims, rstr, box, "R(hi)", CU_TENSOR_MAP_SWIZZLE_64B);
+        if (r2) return r2;
+        r2 = encode(&tr2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 4, const_cast<__half*>(static_cast<const __half*>(p.res)) + p.res_lo_off, dims, rstr, box, "R(lo)", CU_TENSOR_MAP_SWIZZLE_64B);
+        if (r2) return r2;
+      }
+    } else {
       const uint64_t OP = (uint64_t)p.out_pitch;
       const uint64_t dims[4] = {(uint64_t)p.Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)B};
       const uint64_t str[4] = {1, OP, OP * Wo, flat ? OP * Wo * Ho : (uint64_t)p.out_bs};
       const uint32_t box[4] = {(uint32_t)(out16 ? 64 : 32), (uint32_t)BW, (uint32_t)BH, 1};
       int r2 = encode(&td, out16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, out16 ? 2 : 4, 4, p.out, dims, str, box, "D");
       if (r2) return r2;
+      td2 = td;
     }
-    CUtensorMap tr = td;  // residual: same geometry as the output, its own pointer / pitch (used for L2 prefetch only)
-    if (p.res) {
+    if (!outp) { tr = td; tr2 = td; }  // residual: same geometry as the output, its own pointer / pitch
+    if (p.res && !outp) {
       const uint64_t RP = (uint64_t)p.res_pitch;
       const uint64_t dims[4] = {(uint64_t)p.Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)B};
       const uint64_t str[4] = {1, RP, RP * Wo, RP * Wo * Ho};
@@ -1012,11 +1086,16 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
     k2.total_tiles = (int)total;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("FB200_TC_DBG"); dbg = e ? atoi(e) : 0; } k2.dbg = dbg; }
     { static int rt = -1; if (rt < 0) { const char* e = getenv("FB200_TC_RES_TMA"); rt = e ? atoi(e) : 1; } k2.res_tma = (p.res && rt) ? 1 : 0; }
-    if constexpr (decltype(gelu_tag)::value) return launch<BN_, ST_, __half, MB_, BK_, NS_, true>(ta, tb, td, tr, k2, st);
-    else if constexpr (FS_) return launch<BN_, ST_, float, MB_, BK_, NS_, false, C2_, true>(ta, tb, td, tr, k2, st);  // fp32 output only (checked by the caller)
-    else {
-      if (out16) return launch<BN_, ST_, __half, MB_, BK_, NS_, false, C2_>(ta, tb, td, tr, k2, st);
-      return launch<BN_, ST_, float, MB_, BK_, NS_, false, C2_>(ta, tb, td, tr, k2, st);
+    if (outp) k2.res_tma = p.res ? 1 : 0;  // pair residuals only come through TMA
+    if constexpr (decltype(gelu_tag)::value) return launch<BN_, ST_, __half, MB_, BK_, NS_, true>(ta, tb, td, tr, td2, tr2, k2, st);
+    else if constexpr (FS_) {  // fp32 or pair output (checked by the caller)
+      if constexpr (NS_ >= 2) { if (outp) return launch<BN_, ST_, PairOut, MB_, BK_, NS_, false, C2_, true>(ta, tb, td, tr, td2, tr2, k2, st); }
+      if (outp) { set_error("conv_tc: pair output needs a double-buffered staging configuration"); return FB200_ERR_UNSUPPORTED; }
+      return launch<BN_, ST_, float, MB_, BK_, NS_, false, C2_, true>(ta, tb, td, tr, td2, tr2, k2, st);
+    } else {
+      if (outp) { set_error("conv_tc: pair output is only produced by the fused-split configurations"); return FB200_ERR_UNSUPPORTED; }
+      if (out16) return launch<BN_, ST_, __half, MB_, BK_, NS_, false, C2_>(ta, tb, td, tr, td2, tr2, k2, st);
+      return launch<BN_, ST_, float, MB_, BK_, NS_, false, C2_>(ta, tb, td, tr, td2, tr2, k2, st);
     }
   };
   typedef std::false_type C1;
@@ -1060,15 +1139,16 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
   // engine delivers ~65-80 B/cycle/SM plus ~110 cycles per instruction (profiles/r02_conv_timeline.md), the segmented layout needs 96 B/cycle at the tensor peak
   static int fs_env = -1;  // FB200_TC_FS=0 disables
   if (fs_env < 0) { const char* e = getenv("FB200_TC_FS"); fs_env = e ? atoi(e) : 1; }
-  if (fs_env && p.split3 && BK == 64 && p.out_dtype == FB200_F32 && !p.rowmax && !kp.w_batched) {
+  const bool out_pair = p.out_dtype == FB200_F16PAIR;
+  if (fs_env && p.split3 && BK == 64 && (p.out_dtype == FB200_F32 || out_pair) && !p.rowmax && !kp.w_batched) {
     // deep K loops want the 3-stage ring (and have a long main loop to hide a single staging buffer behind); layers with a residual (fetched by TMA into the
     // SECOND staging buffer) or a short K loop are bound by the epilogue / HBM: two stages, double-buffered staging
-    const bool deep = !p.res && p.KH * p.KW * (Clog / 64) > 4;
+    const bool deep = !p.res && !out_pair && p.KH * p.KW * (Clog / 64) > 4;  // (pair output needs both staging buffers: one per plane pair in flight)
     if (p.Cout > 128 && g_cta_pair_mode != 0) {
       if (deep) return run(integral_constant<int, 256>{}, integral_constant<int, 3>{}, I1{}, K64{}, I1{}, std::false_type{}, C2{}, FS{});   // pair: 3 x 64 + 32 KiB
       return run(integral_constant<int, 256>{}, integral_constant<int, 2>{}, I1{}, K64{}, I2{}, std::false_type{}, C2{}, FS{});             // pair: 2 x 64 + 64 KiB
     }
-    if (p.Cout > 128)
+    if (p.Cout > 128 && !out_pair)
       return run(integral_constant<int, 256>{}, integral_constant<int, 2>{}, I1{}, K64{}, I1{}, std::false_type{}, C1{}, FS{});   // 2 x 96 + 32 KiB
     if (p.Cout > 64) {
       if (deep) return run(integral_constant<int, 128>{}, integral_constant<int, 3>{}, I1{}, K64{}, I1{}, std::false_type{}, C1{}, FS{});   // 3 x 64 + 32 KiB

@@ -236,6 +236,84 @@ __global__ void split_f32_pair8_kernel(const float* __restrict__ x, int64_t rows
   }
 }
 
+// ---- pair-format (fp32 value = fp16 hi plane + fp16 lo plane, see FB200_F16PAIR) variants of the three HBM-bound spatial operators between convs of the fp32-accurate
+// mode: 8 channels per thread (16 B of hi + 16 B of lo), arithmetic in fp32 on hi + lo, the result re-split.  mode 0: max_pool2d(3,2,1); 1: AvgPool2d(2,2,ceil_mode);
+// 2: bilinear resize (align_corners=False).
+struct PairPtr { const __half* hi; int64_t lo_off; int pitch; };
+__device__ __forceinline__ void pair_load8(const __half* hi, int64_t lo_off, float (&v)[8]) {
+  float a[8], b[8];
+  Vec16<__half>::load(hi, a);
+  Vec16<__half>::load(hi + lo_off, b);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = a[j] + b[j];
+}
+__device__ __forceinline__ void pair_store8(__half* hi, int64_t lo_off, const float (&v)[8]) {
+  float h[8], l[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { h[j] = __half2float(__float2half_rn(v[j])); l[j] = v[j] - h[j]; }
+  Vec16<__half>::store(hi, h);
+  Vec16<__half>::store(hi + lo_off, l);
+}
+
+template <int MODE>
+__global__ void pair_pool_kernel(const __half* __restrict__ x, int64_t x_lo, int x_pitch, int B, int H, int W, int C, __half* __restrict__ out, int64_t o_lo, int o_pitch,
+                                 int Ho, int Wo, float sh, float sw) {
+  const int cv = C / 8;
+  const int64_t total = (int64_t)B * Ho * Wo * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (i % cv) * 8;
+    const int64_t pix = i / cv;
+    const int wo = pix % Wo, ho = (pix / Wo) % Ho, b = pix / ((int64_t)Wo * Ho);
+    const __half* base = x + (int64_t)b * H * W * x_pitch + c;
+    float r[8];
+    if (MODE == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = -INFINITY;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int hi = ho * 2 - 1 + kh;
+        if (hi < 0 || hi >= H) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int wi = wo * 2 - 1 + kw;
+          if (wi < 0 || wi >= W) continue;
+          float v[8];
+          pair_load8(base + ((int64_t)hi * W + wi) * x_pitch, x_lo, v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r[j] = fmaxf(r[j], v[j]);
+        }
+      }
+    } else if (MODE == 1) {
+      const int h0 = ho * 2, w0 = wo * 2, h1 = min(h0 + 2, H), w1 = min(w0 + 2, W);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = 0.f;
+      for (int hi = h0; hi < h1; ++hi)
+        for (int wi = w0; wi < w1; ++wi) {
+          float v[8];
+          pair_load8(base + ((int64_t)hi * W + wi) * x_pitch, x_lo, v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r[j] += v[j];
+        }
+      const float inv = 1.f / (float)((h1 - h0) * (w1 - w0));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] *= inv;
+    } else {
+      const float fh = fmaxf(((float)ho + 0.5f) * sh - 0.5f, 0.f), fw = fmaxf(((float)wo + 0.5f) * sw - 0.5f, 0.f);
+      const int h0 = (int)fh, w0 = (int)fw;
+      const int h1 = h0 + (h0 < H - 1 ? 1 : 0), w1 = w0 + (w0 < W - 1 ? 1 : 0);
+      const float lh1 = fh - (float)h0, lh0 = 1.f - lh1, lw1 = fw - (float)w0, lw0 = 1.f - lw1;
+      float v00[8], v01[8], v10[8], v11[8];
+      pair_load8(base + ((int64_t)h0 * W + w0) * x_pitch, x_lo, v00);
+      pair_load8(base + ((int64_t)h0 * W + w1) * x_pitch, x_lo, v01);
+      pair_load8(base + ((int64_t)h1 * W + w0) * x_pitch, x_lo, v10);
+      pair_load8(base + ((int64_t)h1 * W + w1) * x_pitch, x_lo, v11);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = lh0 * (lw0 * v00[j] + lw1 * v01[j]) + lh1 * (lw0 * v10[j] + lw1 * v11[j]);
+    }
+    pair_store8(out + pix * o_pitch + c, o_lo, r);
+  }
+}
+
 static inline unsigned grid_for(int64_t total, int threads) {
   int64_t g = cdiv(total, threads);
   const int64_t cap = 148LL * 32;
@@ -288,6 +366,24 @@ extern "C" int fb200_resize_bilinear(const void* x, int dtype, int B, int H, int
   }
   FB_DISPATCH_DTYPE(dtype, T, (resize_bilinear_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, B, H, W, C, x_pitch, (T*)out, Ho, Wo, out_pitch, sh, sw)));
   FB_CHECK_LAUNCH("resize_bilinear");
+  return FB200_OK;
+}
+
+extern "C" int fb200_pair_pool(int mode, const void* x, int64_t x_lo_off, int x_pitch, int B, int H, int W, int C, void* out, int64_t out_lo_off, int out_pitch, int Ho, int Wo,
+                               void* stream) {
+  FB_CHECK_ARG(x && out && mode >= 0 && mode <= 2 && C % 8 == 0 && x_pitch % 8 == 0 && out_pitch % 8 == 0 && x_lo_off % 8 == 0 && out_lo_off % 8 == 0, "pair_pool: bad arguments");
+  FB_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 && B > 0 && Ho > 0 && Wo > 0, "pair_pool: unaligned planes or empty output");
+  FB_CHECK_ARG(mode != 0 || (Ho == (H - 1) / 2 + 1 && Wo == (W - 1) / 2 + 1), "pair_pool: max_pool2d(3,2,1) output size");
+  FB_CHECK_ARG(mode != 1 || (Ho == (H + 1) / 2 && Wo == (W + 1) / 2), "pair_pool: AvgPool2d(2,2,ceil) output size");
+  const int64_t total = (int64_t)B * Ho * Wo * (C / 8);
+  const float sh = (float)H / (float)Ho, sw = (float)W / (float)Wo;
+  const __half* xp = static_cast<const __half*>(x);
+  __half* op = static_cast<__half*>(out);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == 0) pair_pool_kernel<0><<<grid_for(total, 256), 256, 0, st>>>(xp, x_lo_off, x_pitch, B, H, W, C, op, out_lo_off, out_pitch, Ho, Wo, sh, sw);
+  else if (mode == 1) pair_pool_kernel<1><<<grid_for(total, 256), 256, 0, st>>>(xp, x_lo_off, x_pitch, B, H, W, C, op, out_lo_off, out_pitch, Ho, Wo, sh, sw);
+  else pair_pool_kernel<2><<<grid_for(total, 256), 256, 0, st>>>(xp, x_lo_off, x_pitch, B, H, W, C, op, out_lo_off, out_pitch, Ho, Wo, sh, sw);
+  FB_CHECK_LAUNCH("pair_pool");
   return FB200_OK;
 }
 

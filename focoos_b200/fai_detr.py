@@ -527,6 +527,88 @@ class DetrEngine:
         f = blk["l2"](blk["l1"](x, act=act, algo=self.algo), residual=x, algo=self.algo)
         return ops.layernorm(f, *blk["n_ffn"])
 
+    # ---- pair-native fp32_tc path: conv activations stay in the fp16 [hi | lo] pair format between convs (written by the conv epilogue), so the split kernel
+    # only runs where a non-conv operator (LayerNorm, attention, selection) produced fp32 --------------------------------------------------------------
+    pair_native = True  # precision == "fp32_tc" only; False = fp32 storage + one split launch in front of every conv (the round-1 data flow)
+
+    def _pc(self, conv, x, residual=None, out=None, out_pair=True, act=None):
+        """packed _Conv on a pair-format input (an fp32 tensor is split first) -> Pair, or fp32 tensor with out_pair=False"""
+        return ops.conv2d_pair(ops.to_pair(x), conv.w3, conv.scale, conv.bias, stride=conv.stride, pad=conv.pad, act=conv.act if act is None else act,
+                               residual=residual, out=out, out_pair=out_pair)
+
+    def _plin(self, lin, xp: "ops.Pair", act=ops.ACT_NONE):
+        """packed _Linear on pair-format tokens [B,S,K] -> fp32 [B,S,N]"""
+        buf = xp.buf
+        assert buf.is_contiguous() and xp.c0 == 0 and xp.C == xp.Ctot
+        lead = buf.shape[:-1]
+        x4 = ops.Pair(buf.reshape(1, 1, -1, buf.shape[-1]))
+        N = lin.w3.shape[0]
+        y = ops.conv2d_pair(x4, lin.w3.reshape(N, 1, 1, lin.w3.shape[-1]), None, lin.bias, act=act, out_pair=False)
+        return y.reshape(*lead, N)
+
+    def _csp_run_pair(self, packed, cat, out=None):
+        both, reps = packed
+        C = both.w.shape[0] // 2
+        y12 = self._pc(both, cat)
+        x = y12.slice(0, C)
+        for i, r in enumerate(reps):
+            last = i == len(reps) - 1
+            x = self._pc(r, x, residual=y12.slice(C, 2 * C) if last else None, act=(ops.ACT_SILU | 16) if last else None, out=out if last else None)
+        return x
+
+    def _forward_pair_trunk(self, images, taps):
+        """backbone + hybrid encoder + decoder input projection in the pair format -> (memory Pair [B,S,d], shapes, constants)"""
+        cfg = self.cfg
+        P = ops.Pair
+        x = ops.stem_conv(images.contiguous(), self.stem_w, self.stem_s, self.stem_b, cfg.pixel_mean, cfg.pixel_std, ops.ACT_RELU, out_pair=True)
+        x = self._pc(self.stem3, self._pc(self.stem2, x))
+        x = ops.pair_maxpool3x3s2(x)
+        feats = []
+        for blocks in self.stages:
+            for blk in blocks:
+                y = self._pc(blk["b"], self._pc(blk["a"], x))
+                short = x if blk["short"] is None else self._pc(blk["short"], ops.pair_avgpool2x2(x) if blk["stride"] == 2 else x)
+                x = self._pc(blk["c"], y, residual=short)
+            feats.append(x)
+        res3, res4, res5 = feats[1], feats[2], feats[3]
+        B, h32, w32, _ = res5.shape
+        K = self._constants(h32, w32)
+        C = cfg.pixel_decoder_feat_dim
+        dev = images.device
+        cat1 = P.empty((B, h32 * 2, w32 * 2, 2 * C), dev)  # [up(lat0) | proj(res4)]
+        cat2 = P.empty((B, h32 * 4, w32 * 4, 2 * C), dev)  # [up(lat1) | proj(res3)]
+        cat3 = P.empty((B, h32 * 2, w32 * 2, 2 * C), dev)  # [down(fpn1) | lat1]
+        cat4 = P.empty((B, h32, w32, 2 * C), dev)          # [down(pan0) | lat0]
+        self._pc(self.enc_in[0], res3, out=cat2.slice(C, 2 * C))
+        self._pc(self.enc_in[1], res4, out=cat1.slice(C, 2 * C))
+        p5 = self._pc(self.enc_in[2], res5, out_pair=False)          # fp32 tokens for the AIFI block (LayerNorm / attention work on fp32)
+        src = p5.reshape(B, h32 * w32, C)
+        src = self._mha(self.aifi, src, K["pos"])
+        src = self._ffn(self.aifi, src, ops.ACT_GELU)
+        p5 = src.reshape(B, h32, w32, C)
+        lat0 = self._pc(self.lateral[0], p5, out=cat4.slice(C, 2 * C))
+        ops.pair_resize_bilinear(lat0, (h32 * 2, w32 * 2), out=cat1.slice(0, C))
+        fpn0 = self._csp_run_pair(self.fpn[0], cat1)
+        lat1 = self._pc(self.lateral[1], fpn0, out=cat3.slice(C, 2 * C))
+        ops.pair_resize_bilinear(lat1, (h32 * 4, w32 * 4), out=cat2.slice(0, C))
+        fpn1 = self._csp_run_pair(self.fpn[1], cat2)
+        self._pc(self.down[0], ops.pair_resize_bilinear(fpn1, (h32 * 2, w32 * 2)), out=cat3.slice(0, C))
+        pan0 = self._csp_run_pair(self.pan[0], cat3)
+        self._pc(self.down[1], ops.pair_resize_bilinear(pan0, (h32, w32)), out=cat4.slice(0, C))
+        pan1 = self._csp_run_pair(self.pan[1], cat4)
+        enc_outs = [pan1, pan0, fpn1]
+        if taps is not None:
+            taps.update(res3=res3.float(), res4=res4.float(), res5=res5.float(), aifi=p5, fpn0=fpn0.float(), fpn1=fpn1.float(), pan0=pan0.float(), pan1=pan1.float())
+        shapes = K["shapes"]
+        S = sum(h * w for h, w in shapes)
+        d = self.d
+        membuf = torch.empty((B, S, 2 * d), dtype=torch.float16, device=dev)
+        start = 0
+        for i, (f, (h, w)) in enumerate(zip(enc_outs, shapes)):
+            self._pc(self.dec_in[i], f, out=P(membuf[:, start:start + h * w].unflatten(1, (h, w))))
+            start += h * w
+        return P(membuf), shapes, K
+
     @torch.no_grad()
     def forward(self, images: torch.Tensor, taps: Optional[dict] = None):
         """images [B,3,H,W] fp32 0..255 (H,W multiples of 32) -> (scores [B,Q,C] fp32, boxes xyxy [B,Q,4] fp32)."""
@@ -539,6 +621,16 @@ class DetrEngine:
             B, _, H, W = images.shape
         assert H % 32 == 0 and W % 32 == 0, "input size must be a multiple of 32"
         global _products
+        use_pair = (self.precision == "fp32_tc" and self.pair_native and A == ops.ALGO_AUTO and all(v == 3 for v in self.mix.values())
+                    and (ops._backend is not None or ops.supports_tcgen05_cached()))
+        if use_pair:
+            mem_pair, shapes, K = self._forward_pair_trunk(images, taps)
+            dev = images.device
+            S, d = mem_pair.buf.shape[1], self.d
+            value_all = self._plin(self.value_all, mem_pair)
+            t = self._plin(self.enc_output, mem_pair)
+            memory = None
+            return self._forward_head(t, value_all, memory, shapes, K, B, S, taps, mem_pair)
         _products = self.mix["backbone"]
         feats = self._run_backbone(images)
         _products = self.mix["encoder"]
@@ -587,6 +679,13 @@ class DetrEngine:
         value_all = self.value_all(memory, algo=A)  # [B,S,6*d], layer i uses columns [i*d,(i+1)*d)
         # query selection (modelling.py:1191-1232)
         t = self.enc_output(memory, algo=A)
+        return self._forward_head(t, value_all, memory, shapes, K, B, S, taps, None)
+
+    def _forward_head(self, t, value_all, memory, shapes, K, B, S, taps, mem_pair):
+        """query selection + decoder + head on the encoder memory (shared by the fp16 / fp32 / pair-native trunks)"""
+        global _products
+        cfg, dt, A, d = self.cfg, self.dt, self.algo, self.d
+        dev = t.device
         t = ops.row_select(t, K["valid"], self.enc_output.bias)
         output_memory = ops.layernorm(t, *self.enc_output_ln)
         ncls = cfg.num_classes
@@ -603,7 +702,7 @@ class DetrEngine:
         ref_unact = ops.box_add_anchors(bb, K["anchors"], topk_ind)
         ref = ops.box_sigmoid(ref_unact)
         if taps is not None:
-            taps.update(memory=memory, enc_scores=scores, topk_ind=topk_ind, target=tgt, ref_unact=ref_unact)
+            taps.update(memory=memory if mem_pair is None else mem_pair.float(), enc_scores=scores, topk_ind=topk_ind, target=tgt, ref_unact=ref_unact)
         # decoder (modelling.py:969-1020, eval: logits only from the last layer)
         _products = self.mix["decoder"]
         for i, blk in enumerate(self.dec):

@@ -21,7 +21,7 @@ from typing import Optional, Sequence, Tuple
 
 import torch
 
-F32, F16 = 0, 1
+F32, F16, F16PAIR = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_SILU, ACT_GELU = 0, 1, 2, 3
 ACT = {None: 0, "none": 0, "relu": 1, "silu": 2, "gelu": 3}
 ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05, ALGO_TCGEN05_SPLIT3 = 0, 1, 2, 3
@@ -64,7 +64,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = (
     "fb200_last_error", "fb200_version", "fb200_device_supports_tcgen05", "fb200_set_option", "fb200_set_conv_trace", "fb200_stem_conv3x3s2", "fb200_stem_conv3x3s2_u8", "fb200_conv2d", "fb200_conv2d_per_image_weights", "fb200_linear_rowmax",
-    "fb200_split_f32_pair",
+    "fb200_split_f32_pair", "fb200_conv2d_pair", "fb200_pair_pool",
     "fb200_maxpool3x3s2", "fb200_avgpool2x2_ceil", "fb200_resize_bilinear", "fb200_add", "fb200_layernorm",
     "fb200_attention", "fb200_attention_split", "fb200_msda", "fb200_row_select", "fb200_rowmax", "fb200_topk", "fb200_gather_rows",
     "fb200_box_op", "fb200_detr_postprocess", "fb200_detr_eval_postprocess",
@@ -142,11 +142,14 @@ class CudaBackend:
         _trace.append([name, _trace_note.pop() if _trace_note else "", e0, e1])
 
     def stem_conv(self, img, w, scale, bias, mean, std, act, out):
-        self._cuda(img, w, out)
+        self._cuda(img, w, out.buf if isinstance(out, Pair) else out)
         u8 = img.dtype == torch.uint8
         B, H, W = (img.shape[0], img.shape[1], img.shape[2]) if u8 else (img.shape[0], img.shape[2], img.shape[3])
         m = (ctypes.c_float * 3)(*mean)
         s = (ctypes.c_float * 3)(*std)
+        if isinstance(out, Pair):
+            self._call("fb200_stem_conv3x3s2_u8" if u8 else "fb200_stem_conv3x3s2", _p(img), B, H, W, _p(w), _p(scale), _p(bias), m, s, act, _p(out.buf), F16PAIR, out.C, _stream())
+            return
         self._call("fb200_stem_conv3x3s2_u8" if u8 else "fb200_stem_conv3x3s2", _p(img), B, H, W, _p(w), _p(scale), _p(bias), m, s, act, _p(out), _dt(out), out.shape[-1], _stream())
 
     def conv2d(self, x, w, scale, bias, stride, pad, act, residual, out, algo):
@@ -168,6 +171,27 @@ class CudaBackend:
     def linear_rowmax(self, x2d, w, bias, out):
         self._cuda(x2d, w, out)
         self._call("fb200_linear_rowmax", _p(x2d), ctypes.c_int64(x2d.shape[0]), x2d.shape[1], x2d.stride(0), _p(w), _p(bias), w.shape[0], _p(out), _stream())
+
+    def conv2d_pair(self, x, w3, scale, bias, stride, pad, act, residual, out):
+        """x / residual / out: `Pair` (hi + lo fp16 planes) - residual and out may also be plain fp32 tensors (both, or neither)"""
+        out_pair = isinstance(out, Pair)
+        xh = x.hi
+        self._cuda(xh, w3, out.hi if out_pair else out)
+        B, H, W, C = xh.shape
+        Cout, KH, KW, _ = w3.shape
+        oh = out.hi if out_pair else out
+        rh = None if residual is None else (residual.hi if out_pair else residual)
+        if _trace is not None:
+            _trace_note.append(dict(op="conv", B=B, H=H, W=W, Cin=C, Cout=Cout, k=KH, stride=stride, res=residual is not None, xdt="pair", odt="pair" if out_pair else "float32", algo=3))
+        self._call("fb200_conv2d_pair", _p(xh), B, H, W, C, _pitch(xh), ctypes.c_int64(x.lo_off), _p(w3), KH, KW, stride, pad, _p(scale), _p(bias), _p(rh),
+                   0 if rh is None else _pitch(rh), ctypes.c_int64(residual.lo_off if (out_pair and residual is not None) else 0), act, _p(oh), F16PAIR if out_pair else F32,
+                   _pitch(oh, True), ctypes.c_int64(out.lo_off if out_pair else 0), ctypes.c_int64(_batch_stride(oh)), Cout, _stream())
+
+    def pair_pool(self, mode, x, out):
+        xh, oh = x.hi, out.hi
+        self._cuda(xh, oh)
+        B, H, W, C = xh.shape
+        self._call("fb200_pair_pool", mode, _p(xh), ctypes.c_int64(x.lo_off), _pitch(xh), B, H, W, C, _p(oh), ctypes.c_int64(out.lo_off), _pitch(oh), oh.shape[1], oh.shape[2], _stream())
 
     def split_pair(self, x, out):
         self._cuda(x, out)
@@ -255,6 +279,55 @@ class CudaBackend:
         self._call("fb200_detr_eval_postprocess", _p(scores), _p(boxes), _p(sizes), B, Q, C, K, _p(out_scores), _p(out_labels), _p(out_boxes), _p(out_count), _stream())
 
 
+class Pair:
+    """An fp32 NHWC activation stored as TWO fp16 planes (hi = fp16(v), lo = fp16(v - hi), exact to ~2^-22) inside one buffer `buf` [..., 2 * Ctot]:
+    hi planes of all channels in buf[..., :Ctot], lo planes in buf[..., Ctot:] - the operand format of the fp32-accurate tensor-core convs, which also
+    WRITE it (conv2d_pair), so activations never pass through a separate split kernel between two convs.  A Pair may be a channel slice [c0, c0 + C)
+    of a wider pair buffer (concat-free CSP / FPN blocks): hi and lo are then strided views with the same pixel pitch."""
+
+    __slots__ = ("buf", "c0", "C")
+
+    def __init__(self, buf: torch.Tensor, c0: int = 0, C: Optional[int] = None):
+        assert buf.dtype == torch.float16 and buf.shape[-1] % 2 == 0
+        self.buf, self.c0 = buf, c0
+        self.C = buf.shape[-1] // 2 - c0 if C is None else C
+
+    @staticmethod
+    def empty(shape, device) -> "Pair":
+        return Pair(torch.empty((*shape[:-1], 2 * shape[-1]), dtype=torch.float16, device=device))
+
+    @property
+    def Ctot(self) -> int:
+        return self.buf.shape[-1] // 2
+
+    @property
+    def hi(self) -> torch.Tensor:
+        return self.buf[..., self.c0:self.c0 + self.C]
+
+    @property
+    def lo(self) -> torch.Tensor:
+        return self.buf[..., self.Ctot + self.c0:self.Ctot + self.c0 + self.C]
+
+    @property
+    def lo_off(self) -> int:
+        return self.Ctot
+
+    @property
+    def shape(self):
+        return (*self.buf.shape[:-1], self.C)
+
+    @property
+    def device(self):
+        return self.buf.device
+
+    def slice(self, a: int, b: int) -> "Pair":
+        return Pair(self.buf, self.c0 + a, b - a)
+
+    def float(self) -> torch.Tensor:
+        """the fp32 values (a torch op: taps / tests only, never on the forward path)"""
+        return self.hi.float() + self.lo.float()
+
+
 _cuda_backend = None
 
 
@@ -303,7 +376,7 @@ def supports_tcgen05_cached() -> bool:
 # ------------------------------------------------------------------------------------------------
 # public tensor-level API
 # ------------------------------------------------------------------------------------------------
-def stem_conv(img: torch.Tensor, w, scale, bias, mean: Sequence[float], std: Sequence[float], act=ACT_RELU, out_dtype=torch.float32):
+def stem_conv(img: torch.Tensor, w, scale, bias, mean: Sequence[float], std: Sequence[float], act=ACT_RELU, out_dtype=torch.float32, out_pair: bool = False):
     """[B,3,H,W] fp32 NCHW 0..255 -> normalise -> conv3x3/s2 + BN + act -> NHWC [B,H/2,W/2,32]."""
     assert img.dim() == 4 and img.is_contiguous()
     if img.dtype == torch.uint8:  # decoded images as they come: [B,H,W,3] uint8
@@ -312,6 +385,10 @@ def stem_conv(img: torch.Tensor, w, scale, bias, mean: Sequence[float], std: Seq
     else:
         assert img.dtype == torch.float32 and img.shape[1] == 3
         B, _, H, W = img.shape
+    if out_pair:  # the result as a Pair: [hi(Cout) | lo(Cout)] fp16 per pixel
+        pr = Pair.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, w.shape[0]), img.device)
+        _be().stem_conv(img, w, scale, bias, [float(v) for v in mean], [float(v) for v in std], act, pr)
+        return pr
     out = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, w.shape[0]), dtype=out_dtype, device=img.device)
     _be().stem_conv(img, w, scale, bias, [float(v) for v in mean], [float(v) for v in std], act, out)
     return out
@@ -365,6 +442,50 @@ def split_pair(x):
     assert x.dtype == torch.float32
     out = torch.empty((*x.shape[:-1], 2 * x.shape[-1]), dtype=torch.float16, device=x.device)
     _be().split_pair(x, out)
+    return out
+
+
+def to_pair(x) -> Pair:
+    """fp32 tensor -> Pair (one split launch); a Pair passes through"""
+    return x if isinstance(x, Pair) else Pair(split_pair(x))
+
+
+def conv2d_pair(x: Pair, w3, scale=None, bias=None, *, stride=1, pad=0, act=ACT_NONE, residual=None, out=None, out_pair: bool = True):
+    """fp32-accurate conv (three fp16 tcgen05 products) on a pair-format input.  `out_pair`: write the result as a Pair (for a following conv / pair pool) or
+    as a plain fp32 tensor (for the non-conv consumers: LayerNorm, attention, deformable attention, selection).  The residual has the output's format."""
+    assert isinstance(x, Pair) and w3.dtype == torch.float16 and w3.shape[3] == 3 * x.C, (w3.shape, x.C)
+    B, H, W, _ = x.shape
+    Cout, KH, KW, _ = w3.shape
+    Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+    if out is None:
+        out = Pair.empty((B, Ho, Wo, Cout), x.device) if out_pair else torch.empty((B, Ho, Wo, Cout), dtype=torch.float32, device=x.device)
+    assert tuple(out.shape) == (B, Ho, Wo, Cout), (tuple(out.shape), (B, Ho, Wo, Cout))
+    if residual is not None:
+        assert isinstance(residual, Pair) == isinstance(out, Pair) and tuple(residual.shape) == tuple(out.shape)
+    _be().conv2d_pair(x, w3, scale, bias, stride, pad, act, residual, out)
+    return out
+
+
+def pair_maxpool3x3s2(x: Pair) -> Pair:
+    B, H, W, C = x.shape
+    out = Pair.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C), x.device)
+    _be().pair_pool(0, x, out)
+    return out
+
+
+def pair_avgpool2x2(x: Pair) -> Pair:
+    B, H, W, C = x.shape
+    out = Pair.empty((B, (H + 1) // 2, (W + 1) // 2, C), x.device)
+    _be().pair_pool(1, x, out)
+    return out
+
+
+def pair_resize_bilinear(x: Pair, size: Tuple[int, int], out: Optional[Pair] = None) -> Pair:
+    B, H, W, C = x.shape
+    if out is None:
+        out = Pair.empty((B, size[0], size[1], C), x.device)
+    assert tuple(out.shape) == (B, size[0], size[1], C)
+    _be().pair_pool(2, x, out)
     return out
 
 

@@ -30,7 +30,10 @@ extern "C" {
 #endif
 
 typedef enum { FB200_OK = 0, FB200_ERR_INVALID = -1, FB200_ERR_UNSUPPORTED = -2, FB200_ERR_CUDA = -3 } fb200_status;
-typedef enum { FB200_F32 = 0, FB200_F16 = 1 } fb200_dtype;
+typedef enum { FB200_F32 = 0, FB200_F16 = 1,
+               /* an fp32 value stored as TWO fp16 planes: hi = fp16(v), lo = fp16(v - hi) (exact to ~2^-22): the operand format of FB200_ALGO_TCGEN05_SPLIT3, accepted as
+                * conv output / residual so that activations stay in it between two convs (fb200_conv2d_pair) */
+               FB200_F16PAIR = 2 } fb200_dtype;
 typedef enum { FB200_ACT_NONE = 0, FB200_ACT_RELU = 1, FB200_ACT_SILU = 2, FB200_ACT_GELU = 3, FB200_ACT_SIGMOID = 4 /* SIMT path only */,
                FB200_ACT_RESIDUAL_AFTER = 16 /* OR-ed flag: out = act(conv) + residual instead of act(conv + residual) */ } fb200_act;
 typedef enum { FB200_ALGO_AUTO = 0, FB200_ALGO_SIMT = 1, FB200_ALGO_TCGEN05 = 2,
@@ -79,6 +82,21 @@ int fb200_stem_conv3x3s2_u8(const uint8_t* img_nhwc, int B, int H, int W, const 
 int fb200_conv2d(const void* x, int x_dtype, int B, int H, int W, int Cin, int x_pitch, const void* w, int KH, int KW,
                  int stride, int pad, const float* scale, const float* bias, const void* residual, int res_pitch,
                  int act, void* out, int out_dtype, int out_pitch, int64_t out_batch_stride, int Cout, int algo, void* stream);
+
+/* fp32-accurate conv on pair-format activations (precision "fp32_tc"): x is the HI plane of a [hi | lo] pair tensor with C logical channels, its lo plane
+ * `x_lo_off` elements further (pitch x_pitch covers both); w3 = [Cout][KH][KW][W_hi | W_lo | W_hi] (3C); three fp16 tcgen05 products per chunk, fp32 accumulation.
+ * out_dtype FB200_F32: fp32 output / residual as in fb200_conv2d.  out_dtype FB200_F16PAIR: the epilogue writes the result AS a pair (hi plane at `out`, lo plane
+ * `out_lo_off` elements further, pitch out_pitch) and reads the residual as a pair (`res_lo_off`), so consecutive convs exchange activations without a split pass
+ * (replaces the fb200_split_f32_pair launch in front of every conv: nn/layers/conv.py:78-98 chains such as resnet.py:106-121). */
+int fb200_conv2d_pair(const void* x, int B, int H, int W, int C, int x_pitch, int64_t x_lo_off, const void* w3, int KH, int KW, int stride, int pad,
+                      const float* scale, const float* bias, const void* residual, int res_pitch, int64_t res_lo_off, int act, void* out, int out_dtype,
+                      int out_pitch, int64_t out_lo_off, int64_t out_batch_stride, int Cout, void* stream);
+
+/* The HBM-bound spatial operators between convs, on pair-format activations (hi plane at the pointer, lo plane `*_lo_off` elements further, C % 8 == 0):
+ * mode 0 = F.max_pool2d(3,2,1) (resnet.py:254), 1 = AvgPool2d(2,2,ceil_mode) of the vd shortcut (resnet.py:91-102), 2 = F.interpolate(bilinear,
+ * align_corners=False) of the FPN / PAN (fai_detr/modelling.py:334,342).  Arithmetic in fp32 on hi + lo, result re-split. */
+int fb200_pair_pool(int mode, const void* x, int64_t x_lo_off, int x_pitch, int B, int H, int W, int C, void* out, int64_t out_lo_off, int out_pitch, int Ho, int Wo,
+                    void* stream);
 
 /* Same conv with one weight set PER IMAGE: w [B][Cout][KH][KW][Cin] (w_batch_stride elements apart).  This is the per-query mask product
  * einsum("bqc,bchw->bqhw") of PredictionHeads.forward (models/fai_mf/modelling.py:86, bisenetformer/modelling.py:364): x = mask features

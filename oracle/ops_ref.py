@@ -34,6 +34,9 @@ class RefBackend:
             y = y * scale.view(1, -1, 1, 1)
         if bias is not None:
             y = y + bias.view(1, -1, 1, 1)
+        if hasattr(out, "hi"):
+            self._pair_write(out, _act(y, act).permute(0, 2, 3, 1))
+            return
         out.copy_(_act(y, act).permute(0, 2, 3, 1).to(out.dtype))
 
     def conv2d(self, x, w, scale, bias, stride, pad, act, residual, out, algo):
@@ -51,6 +54,40 @@ class RefBackend:
         r = 0.0 if residual is None else residual.float()
         y = _act(y, act & 15) + r if post else _act(y + r, act & 15)
         out.copy_(y.to(out.dtype))
+
+    @staticmethod
+    def _pair_write(pr, v):
+        hi = v.half()
+        pr.hi.copy_(hi)
+        pr.lo.copy_((v - hi.float()).half())
+
+    def conv2d_pair(self, x, w3, scale, bias, stride, pad, act, residual, out):
+        """the fp32 conv the pair operands encode; pair outputs are re-split exactly as the CUDA epilogue does (hi = fp16(v), lo = fp16(v - hi))"""
+        C = x.C
+        xv = x.float()
+        w = w3[..., :C].float() + w3[..., C:2 * C].float()
+        y = F.conv2d(xv.permute(0, 3, 1, 2), w.permute(0, 3, 1, 2), None, stride, pad)
+        if scale is not None:
+            y = y * scale.view(1, -1, 1, 1)
+        if bias is not None:
+            y = y + bias.view(1, -1, 1, 1)
+        y = y.permute(0, 2, 3, 1)
+        r = 0.0 if residual is None else residual.float()
+        y = _act(y, act & 15) + r if (act & 16) else _act(y + r, act & 15)
+        if hasattr(out, "hi"):
+            self._pair_write(out, y)
+        else:
+            out.copy_(y)
+
+    def pair_pool(self, mode, x, out):
+        v = x.float().permute(0, 3, 1, 2)
+        if mode == 0:
+            y = F.max_pool2d(v, 3, 2, 1)
+        elif mode == 1:
+            y = F.avg_pool2d(v, 2, 2, 0, ceil_mode=True)
+        else:
+            y = F.interpolate(v, size=(out.shape[1], out.shape[2]), mode="bilinear", align_corners=False)
+        self._pair_write(out, y.permute(0, 2, 3, 1))
 
     def split_pair(self, x, out):
         C = x.shape[-1]

@@ -221,3 +221,73 @@ def test_pair_mode_bit_identical_to_single_cta(B, H, W, Cin, Cout, k, stride, re
             ops.set_option(ops.OPT_CONV_CTA_PAIR, old)
     assert torch.equal(outs[0], outs[1])
     assert float(outs[0].float().abs().max()) > 0
+
+
+# ---- pair-format activations: the conv epilogue writes [hi | lo] fp16 planes, reads pair residuals; pools / resize on pairs -------------------------
+def _pair_from(x32):
+    return ops.Pair(ops.split_pair(x32.to(DEV)))
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,stride,res", [(2, 20, 20, 256, 256, 3, 1, False), (2, 20, 20, 256, 1024, 1, 1, True), (2, 40, 40, 128, 128, 3, 2, False),
+                                                          (2, 40, 200, 32, 64, 3, 1, False), (1, 33, 130, 32, 32, 3, 1, False), (2, 24, 40, 256, 64, 1, 1, True),
+                                                          (3, 20, 20, 512, 2048, 1, 1, True), (1, 1, 1000, 256, 512, 1, 1, False), (2, 7, 9, 64, 128, 3, 1, True)])
+def test_conv2d_pair_output_and_residual(B, H, W, Cin, Cout, k, stride, res):
+    """out = Pair: hi + lo reproduce the fp32 reference conv to split precision; the pair residual is read back as hi + lo"""
+    from focoos_b200.fai_detr import _split3_weights
+    x = rnd((B, H, W, Cin), torch.float32, 1, 3.0)
+    w = rnd((Cout, k, k, Cin), torch.float32, 2, 1.0 / math.sqrt(k * k * Cin))
+    bi, sc = rnd((Cout,), torch.float32, 3, 0.2), torch.rand(Cout) + 0.5
+    pad = (k - 1) // 2
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    r = rnd((B, Ho, Wo, Cout), torch.float32, 4) if res else None
+    ref = torch.empty((B, Ho, Wo, Cout), dtype=torch.float32)
+    REF.conv2d(x, w, sc, bi, stride, pad, 1, r, ref, 0)
+    rp = None if r is None else _pair_from(r)
+    out = ops.conv2d_pair(_pair_from(x), _split3_weights(w).to(DEV), sc.to(DEV), bi.to(DEV), stride=stride, pad=pad, act=1, residual=rp, out_pair=True)
+    torch.cuda.synchronize()
+    got = out.float().cpu()
+    scale = max(1.0, float(ref.abs().max()))
+    assert float((got - ref).abs().max()) <= 2e-5 * scale
+    hi = out.hi.float().cpu()
+    assert torch.equal(out.hi.cpu(), got.half()) or float((hi - got).abs().max()) <= 1e-3 * scale, "hi plane = fp16 of the value"
+    # the same conv with fp32 output and fp32 residual must agree with the pair output to the pair's own resolution
+    out32 = ops.conv2d_pair(_pair_from(x), _split3_weights(w).to(DEV), sc.to(DEV), bi.to(DEV), stride=stride, pad=pad, act=1, residual=None if r is None else r.to(DEV), out_pair=False)
+    assert float((out32.cpu() - got).abs().max()) <= 4e-6 * scale
+
+
+def test_conv2d_pair_channel_slices_of_a_wider_pair_buffer():
+    """CSP pattern: input = channels [0, C) of a 2C pair buffer, residual = channels [C, 2C), output = a slice of another pair buffer"""
+    from focoos_b200.fai_detr import _split3_weights
+    C = 128
+    y12 = rnd((2, 20, 24, 2 * C), torch.float32, 11, 2.0)
+    w = rnd((C, 3, 3, C), torch.float32, 12, 0.03)
+    bi = rnd((C,), torch.float32, 13, 0.2)
+    ref = torch.empty((2, 20, 24, C), dtype=torch.float32)
+    REF.conv2d(y12[..., :C].contiguous(), w, None, bi, 1, 1, 2 | 16, y12[..., C:].contiguous(), ref, 0)
+    yp = _pair_from(y12)
+    dst = ops.Pair(torch.zeros((2, 20, 24, 4 * C), dtype=torch.float16, device=DEV))
+    ops.conv2d_pair(yp.slice(0, C), _split3_weights(w).to(DEV), None, bi.to(DEV), pad=1, act=2 | 16, residual=yp.slice(C, 2 * C), out=dst.slice(C, 2 * C))
+    assert float((dst.slice(C, 2 * C).float().cpu() - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
+    assert float(dst.slice(0, C).float().abs().max()) == 0.0, "neighbouring channels untouched"
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_pair_pool_matches_the_fp32_operator(mode):
+    x = rnd((2, 37, 50, 64), torch.float32, 21, 3.0)
+    xp = _pair_from(x)
+    if mode == 0:
+        got, ref = ops.pair_maxpool3x3s2(xp), torch.nn.functional.max_pool2d(x.permute(0, 3, 1, 2), 3, 2, 1)
+    elif mode == 1:
+        got, ref = ops.pair_avgpool2x2(xp), torch.nn.functional.avg_pool2d(x.permute(0, 3, 1, 2), 2, 2, 0, ceil_mode=True)
+    else:
+        got, ref = ops.pair_resize_bilinear(xp, (74, 100)), torch.nn.functional.interpolate(x.permute(0, 3, 1, 2), size=(74, 100), mode="bilinear", align_corners=False)
+    assert float((got.float().cpu() - ref.permute(0, 2, 3, 1)).abs().max()) <= 3e-6 * 12
+
+
+def test_stem_conv_pair_output():
+    img = torch.randint(0, 256, (2, 64, 96, 3), dtype=torch.uint8)
+    w, sc, bi = rnd((32, 3, 3, 3), torch.float32, 31, 0.2), torch.rand(32) + 0.5, rnd((32,), torch.float32, 32, 0.1)
+    mean, std = [123.675, 116.28, 103.53], [58.395, 57.12, 57.375]
+    a = ops.stem_conv(img.to(DEV), w.to(DEV), sc.to(DEV), bi.to(DEV), mean, std, out_dtype=torch.float32)
+    p = ops.stem_conv(img.to(DEV), w.to(DEV), sc.to(DEV), bi.to(DEV), mean, std, out_pair=True)
+    assert float((p.float() - a).abs().max()) <= 1e-6 * max(1.0, float(a.abs().max()))
