@@ -188,7 +188,9 @@ class BisenetFormerHead(nn.Module):
 class BisenetEngine(MFEngine):
     def __init__(self, sd: Dict[str, torch.Tensor], cfg: BisenetFormerConfig, device, precision: str = "fp16", algo: int = ops.ALGO_AUTO):
         self.cfg, self.device, self.precision, self.algo = cfg, torch.device(device), precision, algo
-        self.dt = torch.float32 if precision == "fp32" else torch.float16
+        assert precision in ("fp32", "fp16", "fp32_tc")
+        self.dt = torch.float16 if precision == "fp16" else torch.float32
+        self._host_w3 = {} if precision == "fp32_tc" else None  # fp32 storage, three fp16 tensor-core products per conv / linear (fai_detr._split3_weights)
         self.nhead, self.d = 8, cfg.transformer_predictor_hidden_dim
         self._consts = {}
         # pack on the HOST (BN folding, re-parameterisation, concatenations are a few hundred tiny tensor ops: as device launches they were ~700 `at::`
@@ -231,6 +233,7 @@ class BisenetEngine(MFEngine):
         self.ffm_c2 = _Conv(self._to(sd[ffm + ".conv2.weight"].float().permute(0, 2, 3, 1)), None, None, 1, 0, ops.ACT_SIGMOID)
         self.conv_out = self._convx(sd, "pixel_decoder.conv_out", 1)
         self._pack_decoder(sd, 2)
+        self._finish_pack()
 
     def _convx(self, sd, p, stride):
         w = sd[p + ".conv.weight"].float()

@@ -26,7 +26,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .fai_detr import MLP, DetrEngine, ResNet, _bn_fold, _Conv, _CriterionStub, _Linear
+from .fai_detr import MLP, DetrEngine, ResNet, _bn_fold, _Conv, _CriterionStub, _enable_split3, _Linear
 from .ports import ModelOutput, ResnetConfig
 
 
@@ -216,7 +216,9 @@ class MFEngine(DetrEngine):
 
     def __init__(self, sd: Dict[str, torch.Tensor], cfg: MaskFormerConfig, device, precision: str = "fp16", algo: int = ops.ALGO_AUTO):
         self.cfg, self.device, self.precision, self.algo = cfg, torch.device(device), precision, algo
-        self.dt = torch.float32 if precision == "fp32" else torch.float16
+        assert precision in ("fp32", "fp16", "fp32_tc")
+        self.dt = torch.float16 if precision == "fp16" else torch.float32
+        self._host_w3 = {} if precision == "fp32_tc" else None  # fp32 storage, three fp16 tensor-core products per conv / linear (fai_detr._split3_weights)
         self.depth = cfg.backbone_config.depth
         self.nhead, self.d = 8, cfg.transformer_predictor_hidden_dim
         self._consts = {}
@@ -232,6 +234,12 @@ class MFEngine(DetrEngine):
         self.adapter = {i: self._conv_bn(sd, f"{pd}.adapter_{i}", 0, ops.ACT_NONE) for i in (1, 2, 3)}
         self.mask_features = self._conv_bias(sd, pd + ".mask_features", 1)
         self._pack_decoder(sd, 3)
+        self._finish_pack()
+
+    def _finish_pack(self):
+        if self.precision == "fp32_tc":
+            _enable_split3(vars(self), host_w3=self._host_w3)
+        self._host_w3 = None
 
     def _pack_decoder(self, sd, num_levels):
         """head.predictor.* of the masked transformer decoder (same key names in fai_mf and bisenetformer)."""

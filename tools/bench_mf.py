@@ -13,7 +13,8 @@ S = int(sys.argv[2]) if len(sys.argv) > 2 else 800
 with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "fai_mf_l_coco_ins_state_dict_manifest.json")) as f:
     man = json.load(f)
 sd = seeded_state_dict({k: torch.empty(v[0], dtype=getattr(torch, v[1])) for k, v in man.items()}, 0)
-m = FAIMaskFormer(MaskFormerConfig(), precision="fp16"); m.load_state_dict(sd, strict=True); m.cuda()
+PREC = os.environ.get("FB200_BENCH_PRECISION", "fp16")
+m = FAIMaskFormer(MaskFormerConfig(), precision=PREC); m.load_state_dict(sd, strict=True); m.cuda()
 x = torch.randint(0, 256, (B, S, S, 3), dtype=torch.uint8, device="cuda")
 def step_unfused():  # the reference's split: model.forward returns [B,Q,H,W] probabilities, the processor reads them back
     out = m(x)
@@ -38,7 +39,14 @@ agg = collections.defaultdict(lambda: [0, 0.0])
 for name, note, a, b in tr:
     agg[name][0] += 1; agg[name][1] += a.elapsed_time(b)
 tot = sum(v[1] for v in agg.values())
-print(json.dumps({"workload": f"fai-mf-l-coco-ins bs={B} {S}x{S} (BASELINE configs[2])", "images_per_s": B / ms * 1e3, "ms_per_step": ms, "unfused_images_per_s": B / ms_unfused * 1e3, "unfused_ms_per_step": ms_unfused, "dtype": "f16", "launches": len(tr),
+print(json.dumps({"workload": f"fai-mf-l-coco-ins bs={B} {S}x{S} (BASELINE configs[2])", "images_per_s": B / ms * 1e3, "ms_per_step": ms, "unfused_images_per_s": B / ms_unfused * 1e3, "unfused_ms_per_step": ms_unfused, "dtype": {"fp16": "f16", "fp32_tc": "f32 (3x f16 tcgen05 products)", "fp32": "f32 SIMT"}[PREC], "precision": PREC, "launches": len(tr),
                   "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}))
 for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"{t:9.2f} ms {100*t/tot:5.1f}%  n={c:4d}  {k}")
+if PREC == "fp16" and os.environ.get("FB200_BENCH_PARITY_MODE", "1") == "1":  # the parity-green mode (fp32_tc) of the same workload, in its own process
+    import subprocess
+    del m, x
+    torch.cuda.empty_cache()
+    r = subprocess.run([sys.executable] + sys.argv, env=dict(os.environ, FB200_BENCH_PRECISION="fp32_tc", FB200_BENCH_PARITY_MODE="0"), capture_output=True, text=True, timeout=280)
+    line = next((l for l in r.stdout.splitlines() if l.startswith("{")), None)
+    print("PARITY_MODE " + (line or json.dumps({"error": r.stderr[-300:]})))
