@@ -174,15 +174,36 @@ class DETRProcessor:
 # MaskFormerProcessor — mirror of `focoos/models/fai_mf/processor.py`, instance mode
 # ==================================================================================================
 def binary_mask_to_base64(mask: np.ndarray) -> str:
-    """utils/vision.py:270-293: PNG (0/255, single channel) -> base64.  The reference encodes with OpenCV; PIL yields the same image."""
+    """utils/vision.py:270-293: PNG (0/255, single channel) -> base64, encoded with OpenCV exactly as the reference does (`cv2.imencode(".png", mask * 255)`),
+    so the string is byte-identical to the reference's (pinned by tests/test_png_tail.py against strings produced by the unmodified reference function).
+    Without OpenCV the image is encoded with PIL: a different byte stream that decodes to the same mask."""
+    import base64
+
+    m = (np.asarray(mask) * 255).astype(np.uint8)
+    try:
+        import cv2
+    except ImportError:  # pragma: no cover - the image ships OpenCV
+        import io
+
+        from PIL import Image
+
+        buf = io.BytesIO()
+        Image.fromarray(m, mode="L").save(buf, format="PNG")
+        return base64.b64encode(buf.getvalue()).decode("utf-8")
+    ok, enc = cv2.imencode(".png", m)
+    if not ok:
+        raise ValueError("Failed to encode image")
+    return base64.b64encode(enc.tobytes()).decode("utf-8")
+
+
+def base64_to_binary_mask(b64: str) -> np.ndarray:
+    """inverse of binary_mask_to_base64 (utils/vision.py:296-320 decodes the same way for fai_detections_to_sv): PNG -> bool mask"""
     import base64
     import io
 
     from PIL import Image
 
-    buf = io.BytesIO()
-    Image.fromarray((mask.astype(np.uint8) * 255), mode="L").save(buf, format="PNG")
-    return base64.b64encode(buf.getvalue()).decode("utf-8")
+    return np.array(Image.open(io.BytesIO(base64.b64decode(b64)))) > 0
 
 
 class MaskFormerProcessor(DETRProcessor):
