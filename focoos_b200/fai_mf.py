@@ -305,7 +305,10 @@ class MFEngine(DetrEngine):
         else:
             assert images.dim() == 4 and images.shape[1] == 3 and images.dtype == torch.float32
             B, _, H, W = images.shape
-        assert H % 32 == 0 and W % 32 == 0, "input size must be a multiple of 32"
+        if H % 32 or W % 32:
+            # the reference's torch graph takes any size (odd feature maps from ceil-mode pools / stride-2 convs); the B200 kernels tile the stride-2 layers on even
+            # maps, so the engine takes multiples of 32 - resize or pad in the processor (image_size) for other inputs
+            raise ValueError(f"focoos_b200: input size {H}x{W} is not a multiple of 32; resize/pad the image (e.g. ModelInfo.im_size) before the model")
         res2, res3, res4, res5 = self._run_backbone(images)
         d, nh = self.d, self.nhead
         scale = 1.0 / math.sqrt(d // nh)

@@ -21,6 +21,8 @@ def get_image_sizes(inputs) -> List[Tuple[int, int]]:
     """base_processor.py:176-221: (height, width) of every ORIGINAL input image."""
     if _is_u8_nhwc_batch(inputs):
         return [(int(inputs.shape[1]), int(inputs.shape[2]))] * int(inputs.shape[0])
+    if _is_nchw_batch(inputs):
+        return [(int(inputs.shape[2]), int(inputs.shape[3]))] * int(inputs.shape[0])
     if isinstance(inputs, (torch.Tensor, np.ndarray)) or not isinstance(inputs, (list, tuple)):
         inputs = [inputs]
     sizes = []
@@ -40,6 +42,11 @@ def get_image_sizes(inputs) -> List[Tuple[int, int]]:
 def _is_u8_nhwc_batch(x) -> bool:
     """Extension over the reference (which mis-stacks 4-D tensors): a uint8 [B,H,W,3] tensor is a batch."""
     return isinstance(x, torch.Tensor) and x.dim() == 4 and x.dtype == torch.uint8 and x.shape[-1] == 3
+
+
+def _is_nchw_batch(x) -> bool:
+    """a [B,3,H,W] tensor / array with B > 1 is a BATCH of images (the reference stacks it into a 5-D tensor and fails)"""
+    return isinstance(x, (torch.Tensor, np.ndarray)) and x.ndim == 4 and x.shape[1] == 3 and x.shape[0] > 1 and x.shape[-1] != 3
 
 
 class DETRProcessor:
@@ -73,6 +80,13 @@ class DETRProcessor:
             if x.dtype == torch.uint8:
                 return x.contiguous()  # FAIDetr's stem kernel reads uint8 NHWC directly (no float CHW copy)
             return x.permute(0, 3, 1, 2).to(dtype).contiguous()
+        if _is_nchw_batch(inputs):  # one H2D copy, one batched resize
+            x = (torch.from_numpy(np.ascontiguousarray(inputs)) if isinstance(inputs, np.ndarray) else inputs).to(device, non_blocking=True).to(dtype)
+            if target_size is not None and tuple(x.shape[-2:]) != tuple(target_size):
+                x4 = torch.zeros((x.shape[0], x.shape[2], x.shape[3], 4), dtype=dtype, device=x.device)
+                x4[..., :3] = x.permute(0, 2, 3, 1)
+                x = ops.resize_bilinear(x4, target_size)[..., :3].permute(0, 3, 1, 2)
+            return x.contiguous()
         if not isinstance(inputs, (list, tuple)):
             inputs = [inputs]
         outs = []

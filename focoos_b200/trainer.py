@@ -27,6 +27,7 @@ import torch
 import torch.distributed as dist
 
 from . import distributed as D
+from . import ops
 from .criterion import DETRTargets
 from .ports import Boxes, Instances
 
@@ -110,7 +111,10 @@ def _train_worker(rank: int, world: int, fm, args: TrainerArgs, data_train, data
         os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(args.master_port))
         torch.cuda.set_device(rank)
         D.init_from_env("nccl", torch.device("cuda", rank))
-    dev = torch.device("cuda", rank if world > 1 else torch.cuda.current_device())
+    if ops._backend is not None and not torch.cuda.is_available():  # tests: host logic on the CPU reference operators
+        dev = torch.device("cpu")
+    else:
+        dev = torch.device("cuda", rank if world > 1 else torch.cuda.current_device())
     model = fm.model.to(dev)
     model.train()
     if args.freeze_bn and hasattr(model, "freeze_bn"):
