@@ -231,3 +231,39 @@ def test_pipelined_inference_equals_the_synchronous_call(sd):
     assert key(h2.result()) == key(ref[1]) and key(h1.result()) == key(ref[0]) and key(h1.result()) == key(ref[0])
     # non-pinned / list inputs fall back to the synchronous path
     assert key(fm.infer_async([b for b in batches[2].numpy()], threshold=0.5).result()) == key(ref[2])
+
+
+def test_export_roundtrip_on_gpu(sd, tmp_path):
+    """FocoosModel.export on the B200: the TorchScript file (one focoos_b200::model_forward op over its own weights) reloads and reproduces the eager
+    tensors bit for bit, in the parity-green tensor-core mode; the exported InferModel returns the same detections as FocoosModel.infer."""
+    from focoos_b200 import FocoosModel, ModelInfo
+
+    fm = FocoosModel(_model(sd, "fp32_tc"), ModelInfo(name="fai-detr-l-obj365", im_size=640))
+    im = fm.export(out_dir=str(tmp_path), image_size=640)
+    x = 128 * torch.randn(2, 3, 640, 640, device="cuda")
+    eager = fm.model(x)
+    loaded = torch.jit.load(str(tmp_path / "model.pt"))
+    boxes, logits = loaded(x)
+    assert torch.equal(boxes, eager.boxes) and torch.equal(logits, eager.logits)
+    img = synth_images(31, [(480, 600)])[0]
+    d1, d2 = im.infer(img, threshold=0.5), fm.infer(img, threshold=0.5)
+    assert [(d.cls_id, d.bbox, d.conf) for d in d1.detections] == [(d.cls_id, d.bbox, d.conf) for d in d2.detections]
+
+
+def test_pair_native_trunk_equals_the_split_per_conv_flow(sd):
+    """fp32_tc: activations kept in the fp16 [hi|lo] pair format between convs (written by the conv epilogue) against the round-1 data flow (fp32 storage, one split
+    launch in front of every conv): same selected queries, outputs within the pair format's own resolution"""
+    imgs = synth_images(41, [(640, 640)] * 2)
+    outs = []
+    for pair_native in (True, False):
+        m = _model(sd, "fp32_tc")
+        m.engine().pair_native = pair_native
+        proc = DETRProcessor(m.config, image_size=640)
+        x, _ = proc.preprocess(imgs, device=m.device)
+        taps = {}
+        o = m(x, taps=taps)
+        outs.append((o, taps["topk_ind"].cpu().numpy(), taps["res5"].float().cpu().numpy()))
+    assert _set_stats(outs[0][1], outs[1][1]) == [300, 300]
+    ds, db = compare_queries(outs[0][0].logits.cpu().numpy(), outs[0][0].boxes.cpu().numpy(), outs[0][1], outs[1][0].logits.cpu().numpy(), outs[1][0].boxes.cpu().numpy(), outs[1][1])
+    assert ds < 2e-4 and db < 5e-5, (ds, db)
+    assert np.abs(outs[0][2] - outs[1][2]).max() <= 2e-4 * np.abs(outs[1][2]).max()
