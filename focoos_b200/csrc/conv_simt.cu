@@ -282,6 +282,26 @@ extern "C" int fb200_stem_conv3x3s2_u8(const uint8_t* img_nhwc, int B, int H, in
   return stem_launch(img_nhwc, true, B, H, W, w, scale, bias, mean3, std3, act, out, out_dtype, Cout, stream);
 }
 
+extern "C" int fb200_linear_rowmax_pair(const void* x, int64_t M, int K, int x_pitch, int64_t x_lo_off, const void* w3, const float* bias, int Cout, float* rowmax, void* stream) {
+  FB_CHECK_ARG(x && w3 && rowmax && M > 0 && M <= 0x7fffffffLL && K > 0 && Cout > 0, "linear_rowmax_pair: bad arguments");
+  FB_CHECK_ARG(x_lo_off >= K && x_pitch >= x_lo_off + K && K % 64 == 0, "linear_rowmax_pair: K must be a multiple of 64 and the lo plane must lie inside the row pitch");
+  ConvParams p;
+  p.split3 = 1;
+  p.x = x; p.w = w3; p.scale = nullptr; p.bias = bias; p.res = nullptr;
+  p.out = const_cast<void*>(x);  // never written
+  p.B = 1; p.H = 1; p.W = (int)M; p.Cin = 3 * K; p.x_pitch = x_pitch; p.KH = 1; p.KW = 1; p.stride = 1; p.pad = 0; p.Ho = 1; p.Wo = (int)M;
+  p.Cout = Cout; p.res_pitch = 0; p.out_pitch = (Cout + 3) / 4 * 4; p.act = FB200_ACT_NONE;
+  p.M = M; p.K = 3 * K; p.x_dtype = FB200_F16; p.out_dtype = FB200_F32; p.vec_ok = 1;
+  p.out_bs = (int64_t)M * p.out_pitch;
+  p.x_lo_off = x_lo_off;
+  p.rowmax = rowmax;
+  if (!conv2d_tc_supported(p, FB200_F16, FB200_F32)) {
+    set_error("linear_rowmax_pair: shape not supported by the tcgen05 split path (K=%d)", K);
+    return FB200_ERR_UNSUPPORTED;
+  }
+  return conv2d_tc(p, (cudaStream_t)stream);
+}
+
 static int conv2d_impl(const void* x, int x_dtype, int B, int H, int W, int Cin, int x_pitch, const void* w, int64_t w_bs, int KH,
                        int KW, int stride, int pad, const float* scale, const float* bias, const void* residual,
                        int res_pitch, int act, void* out, int out_dtype, int out_pitch, int64_t out_batch_stride, int Cout,

@@ -1140,7 +1140,7 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
   static int fs_env = -1;  // FB200_TC_FS=0 disables
   if (fs_env < 0) { const char* e = getenv("FB200_TC_FS"); fs_env = e ? atoi(e) : 1; }
   const bool out_pair = p.out_dtype == FB200_F16PAIR;
-  if (fs_env && p.split3 && BK == 64 && (p.out_dtype == FB200_F32 || out_pair) && !p.rowmax && !kp.w_batched) {
+  if (fs_env && p.split3 && BK == 64 && (p.out_dtype == FB200_F32 || out_pair) && !kp.w_batched) {
     // deep K loops want the 3-stage ring (and have a long main loop to hide a single staging buffer behind); layers with a residual (fetched by TMA into the
     // SECOND staging buffer) or a short K loop are bound by the epilogue / HBM: two stages, double-buffered staging
     const bool deep = !p.res && !out_pair && p.KH * p.KW * (Clog / 64) > 4;  // (pair output needs both staging buffers: one per plane pair in flight)

@@ -692,7 +692,10 @@ class DetrEngine:
         t = ops.row_select(t, K["valid"], self.enc_output.bias)
         output_memory = ops.layernorm(t, *self.enc_output_ln)
         ncls = cfg.num_classes
-        if self.precision == "fp16" and A == ops.ALGO_AUTO and ops.supports_tcgen05_cached():
+        if mem_pair is not None and self.enc_score.w3 is not None:
+            # fp32-accurate row maxima straight from the tensor-core epilogue: the [B,S,365] fp32 logits (393 MB at bs=32) are never written
+            scores = ops.linear_rowmax_pair(ops.to_pair(output_memory), self.enc_score.w3, self.enc_score.bias)
+        elif self.precision == "fp16" and A == ops.ALGO_AUTO and ops.supports_tcgen05_cached():
             # only the per-anchor maximum is ever used in eval (modelling.py:1210-1214): the [B,S,365] fp32 logits (395 MB at bs=32) are never materialised
             scores = ops.linear_rowmax(output_memory, self.enc_score.w, self.enc_score.bias)
         else:

@@ -19,6 +19,7 @@ import ctypes
 import os
 from typing import Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 
 F32, F16, F16PAIR = 0, 1, 2
@@ -64,7 +65,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = (
     "fb200_last_error", "fb200_version", "fb200_device_supports_tcgen05", "fb200_set_option", "fb200_set_conv_trace", "fb200_stem_conv3x3s2", "fb200_stem_conv3x3s2_u8", "fb200_conv2d", "fb200_conv2d_per_image_weights", "fb200_linear_rowmax",
-    "fb200_split_f32_pair", "fb200_conv2d_pair", "fb200_pair_pool",
+    "fb200_split_f32_pair", "fb200_conv2d_pair", "fb200_pair_pool", "fb200_linear_rowmax_pair",
     "fb200_maxpool3x3s2", "fb200_avgpool2x2_ceil", "fb200_resize_bilinear", "fb200_add", "fb200_layernorm",
     "fb200_attention", "fb200_attention_split", "fb200_msda", "fb200_row_select", "fb200_rowmax", "fb200_topk", "fb200_gather_rows",
     "fb200_box_op", "fb200_detr_postprocess", "fb200_detr_eval_postprocess",
@@ -192,6 +193,12 @@ class CudaBackend:
         self._cuda(xh, oh)
         B, H, W, C = xh.shape
         self._call("fb200_pair_pool", mode, _p(xh), ctypes.c_int64(x.lo_off), _pitch(xh), B, H, W, C, _p(oh), ctypes.c_int64(out.lo_off), _pitch(oh), oh.shape[1], oh.shape[2], _stream())
+
+    def linear_rowmax_pair(self, xp, w3, bias, out):
+        xh = xp.hi
+        self._cuda(xh, w3, out)
+        M = xh.numel() // xh.shape[-1]
+        self._call("fb200_linear_rowmax_pair", _p(xh), ctypes.c_int64(M), xh.shape[-1], _pitch(xh), ctypes.c_int64(xp.lo_off), _p(w3), _p(bias), w3.shape[0], _p(out), _stream())
 
     def split_pair(self, x, out):
         self._cuda(x, out)
@@ -433,6 +440,14 @@ def linear_rowmax(x, w, bias=None):
     x2 = x.reshape(-1, x.shape[-1])
     out = torch.full((x2.shape[0],), float("-inf"), dtype=torch.float32, device=x.device)
     _be().linear_rowmax(x2, w.reshape(w.shape[0], -1).contiguous(), bias, out)
+    return out.reshape(lead)
+
+
+def linear_rowmax_pair(xp: "Pair", w3, bias=None):
+    """linear_rowmax on pair-format rows with the split weight triple: fp32-accurate row maxima, the [rows, N] product never materialised"""
+    lead = xp.shape[:-1]
+    out = torch.full((int(np.prod(lead)),), float("-inf"), dtype=torch.float32, device=xp.device)
+    _be().linear_rowmax_pair(xp, w3.reshape(w3.shape[0], -1).contiguous(), bias, out)
     return out.reshape(lead)
 
 

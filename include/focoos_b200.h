@@ -109,6 +109,8 @@ int fb200_conv2d_per_image_weights(const void* x, int x_dtype, int B, int H, int
  * the query-selection score enc_outputs_class.max(-1) of _get_decoder_input (models/fai_detr/modelling.py:1204-1214; 268 800 x 365 fp32 logits = 395 MB at
  * bs=32 that are otherwise written and read back).  rowmax must be pre-filled with -inf (combined with integer atomics across N tiles). */
 int fb200_linear_rowmax(const void* x, int64_t M, int K, int x_pitch, const void* w, const float* bias, int Cout, float* rowmax, void* stream);
+/* Same on pair-format rows (fp32-accurate mode): x = hi plane of [M, K] rows, lo plane x_lo_off elements further, w3 = [Cout][W_hi | W_lo | W_hi]. */
+int fb200_linear_rowmax_pair(const void* x, int64_t M, int K, int x_pitch, int64_t x_lo_off, const void* w3, const float* bias, int Cout, float* rowmax, void* stream);
 
 /* x fp32 [rows, C] (row pitch x_pitch) -> out fp16 [rows, 2C]: out[:, :C] = hi = fp16(x), out[:, C:] = lo = fp16(x - hi).
  * Operand preparation of the split-precision conv/linear mode (precision="fp32_tc"). */

@@ -79,6 +79,12 @@ class RefBackend:
         else:
             out.copy_(y)
 
+    def linear_rowmax_pair(self, xp, w3, bias, out):
+        K = xp.C
+        w = w3[..., :K].float() + w3[..., K:2 * K].float()
+        y = xp.float().reshape(-1, K) @ w.reshape(w.shape[0], K).t()
+        out.copy_((y + (bias if bias is not None else 0.0)).max(-1).values)
+
     def pair_pool(self, mode, x, out):
         v = x.float().permute(0, 3, 1, 2)
         if mode == 0:

@@ -291,3 +291,14 @@ def test_stem_conv_pair_output():
     a = ops.stem_conv(img.to(DEV), w.to(DEV), sc.to(DEV), bi.to(DEV), mean, std, out_dtype=torch.float32)
     p = ops.stem_conv(img.to(DEV), w.to(DEV), sc.to(DEV), bi.to(DEV), mean, std, out_pair=True)
     assert float((p.float() - a).abs().max()) <= 1e-6 * max(1.0, float(a.abs().max()))
+
+
+def test_linear_rowmax_pair_matches_fp32():
+    """query-selection scores of the fp32-accurate mode: max over the 365 class logits per row, straight from the tensor-core epilogue"""
+    from focoos_b200.fai_detr import _split3_weights
+    x = rnd((3, 1000, 256), torch.float32, 1, 2.0)
+    w = rnd((365, 256), torch.float32, 2, 0.08)
+    b = rnd((365,), torch.float32, 3, 0.5)
+    ref = (x.reshape(-1, 256).double() @ w.double().t() + b.double()).max(-1).values.float().reshape(3, 1000)
+    got = ops.linear_rowmax_pair(ops.Pair(ops.split_pair(x.to(DEV))), _split3_weights(w).to(DEV), b.to(DEV))
+    assert float((got.cpu() - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
