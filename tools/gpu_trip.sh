@@ -31,10 +31,13 @@ for s in $STAGES; do
     trace5) (for d in 36 4; do for c in 0 1; do echo "### DBG=$d CTA2=$c"; FB200_TC_DBG=$d FB200_TC_CTA2=$c timeout 300 python tools/conv_trace.py rep_3x3_80 s2_2a; done; done; true) 2>&1 | grep -v "^cta\|tile[0-9]" > gpurun_out/conv_trace5.txt ;;
     trace6) (for d in 0 64 192; do echo "### DBG=$d CTA2=0"; FB200_TC_DBG=$d FB200_TC_CTA2=0 timeout 300 python tools/conv_trace.py rep_3x3_80; done; true) 2>&1 | grep -v "^cta\|tile[0-9]" > gpurun_out/conv_trace6.txt ;;
     microfs) (FB200_TC_FS=0 timeout 300 python tools/conv_micro.py --split; true) > gpurun_out/conv_micro_split_seg.txt 2>&1; (timeout 300 python tools/conv_micro.py --split; true) > gpurun_out/conv_micro_split_fs.txt 2>&1 ;;
+    benchfp16) timeout 900 python bench.py --steps 20 --warmup 3 --precision fp16 --quick --no-cpu-baseline > gpurun_out/bench_fp16.log 2> gpurun_out/bench_fp16.err ;;
+    ncu_fs) timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 2 -c 1 -o gpurun_out/prof_fs python tools/conv_micro.py --split rep_3x3_80 > gpurun_out/ncu_fs.log 2>&1 ;;
+    alltests) timeout 2400 python -m pytest tests -q -m gpu -x 2>&1 | tail -30 > gpurun_out/t_all.log ;;
     trace) (FB200_TC_CTA2=0 timeout 300 python tools/conv_trace.py rep_3x3_80 rep_3x3_40 s3_2b s2_2a s0_2c; timeout 300 python tools/conv_trace.py rep_3x3_80 rep_3x3_40; true) > gpurun_out/conv_trace.txt 2>&1 ;;
     budget2) timeout 1200 python tools/error_budget.py tc:3323 tc:3331 tc:3332 tc:2222 tc:1111 > gpurun_out/error_budget2.txt 2>&1 ;;
     micro01) (FB200_TC_CTA2=0 timeout 300 python tools/conv_micro.py; true) > gpurun_out/conv_micro_cta1.txt 2>&1; (timeout 300 python tools/conv_micro.py; true) > gpurun_out/conv_micro_cta2.txt 2>&1 ;;
-    layers) timeout 600 python tools/layer_roofline.py > gpurun_out/layer_roofline.txt 2>&1 ;;
+    layers) timeout 600 python tools/layer_roofline.py 32 fp32_tc > gpurun_out/layer_roofline_fp32_tc.txt 2>&1; timeout 600 python tools/layer_roofline.py 32 fp16 > gpurun_out/layer_roofline_fp16.txt 2>&1 ;;
     micro) (python tools/conv_micro.py; true) > gpurun_out/conv_micro.txt 2>&1 ;;
     micro_ncu) timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 4 -c 2 -o gpurun_out/prof_micro python tools/conv_micro.py rep_3x3_80 s0_2c_res > gpurun_out/micro_ncu.log 2>&1 ;;
     mf)    timeout 900 python -m pytest tests/test_gpu_mf.py -q -m gpu 2>&1 | tail -40 > gpurun_out/t_mf.log ;;
