@@ -281,6 +281,13 @@ class _Linear:
                 self.w3 = _split3_weights(self.w)
 
     def __call__(self, x, act=ops.ACT_NONE, residual=None, out_dtype=None, out=None, algo=ops.ALGO_AUTO):
+        if (act & 15) == ops.ACT_GELU and residual is None and _split3_ok(x, self.w3, ops.ACT_NONE, algo) and (out_dtype in (None, torch.float32)):
+            # exact-erf GELU (AIFI FFN) in the fp32-accurate mode: the tensor-core product without activation, then GELU in place (the GELU epilogue instantiation
+            # is fp16-only; without this the layer fell back to the CUDA-core fp32 GEMM: 256 us vs ~30)
+            from . import autograd_ops  # noqa: F401  (binds fb200_add_act)
+            y = self(x, act=ops.ACT_NONE, out_dtype=out_dtype, out=out, algo=algo)
+            ops._be().add_act(y, None, None, ops.ACT_GELU, y)
+            return y
         if _split3_ok(x, self.w3, act, algo) and (out_dtype in (None, torch.float32)):
             if _products != 3:
                 return _reduced_products(self, x, ops.linear, {}, None, act, residual, out)
