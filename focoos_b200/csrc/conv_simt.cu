@@ -92,6 +92,97 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const void* __restrict__
   }
 }
 
+// Tiled stem: a CTA computes a 16 x 16 tile of output pixels.  The 33 x 33 x 3 input patch is read ONCE (coalesced rows), normalised ONCE per input pixel and kept in
+// shared memory as even / odd column planes (the stride-2 taps of 16 neighbouring threads then hit 16 consecutive floats: no bank conflicts); the 27 x 32 weights are
+// read as float4 broadcasts.  The per-pixel kernel above re-loaded and re-normalised (with a division) every input byte for each of the up to nine taps that use it.
+template <typename TOut, bool U8_NHWC>
+__global__ void __launch_bounds__(256) stem_conv_tiled_kernel(const void* __restrict__ img_, int B, int H, int W, const float* __restrict__ w,
+                                                              const float* __restrict__ scale, const float* __restrict__ bias, float m0, float m1, float m2,
+                                                              float s0, float s1, float s2, int act, TOut* __restrict__ out, int tiles_w, int tiles_h) {
+  constexpr int COUT = 32, T = 16, PR = 2 * T + 1, HC = T + 1;   // patch rows, columns per parity plane
+  __shared__ __align__(16) float ws[27 * COUT];
+  __shared__ float sc[COUT], bi[COUT];
+  __shared__ float sin_[3][PR][2][HC + 1];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 27 * COUT; i += 256) { const int co = i % COUT, t = i / COUT; ws[i] = w[co * 27 + t]; }
+  if (tid < COUT) { sc[tid] = scale ? scale[tid] : 1.f; bi[tid] = bias ? bias[tid] : 0.f; }
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  int t = blockIdx.x;
+  const int tw = t % tiles_w; t /= tiles_w;
+  const int th = t % tiles_h; const int b = t / tiles_h;
+  const int ho0 = th * T, wo0 = tw * T;
+  const int hi0 = 2 * ho0 - 1, wi0 = 2 * wo0 - 1;
+  const float mean[3] = {m0, m1, m2}, stdv[3] = {s0, s1, s2};
+  if (U8_NHWC) {
+    const uint8_t* ub = reinterpret_cast<const uint8_t*>(img_) + (int64_t)b * H * W * 3;
+    for (int i = tid; i < PR * PR * 3; i += 256) {  // consecutive threads -> consecutive bytes of a patch row
+      const int ci = i % 3, c = (i / 3) % PR, r = i / (3 * PR);
+      const int hi = hi0 + r, wi = wi0 + c;
+      float v = 0.f;  // the conv pads the NORMALISED image with zeros
+      if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = ((float)ub[((int64_t)hi * W + wi) * 3 + ci] - mean[ci]) / stdv[ci];
+      sin_[ci][r][c & 1][c >> 1] = v;
+    }
+  } else {
+    const float* ib = reinterpret_cast<const float*>(img_) + (int64_t)b * 3 * H * W;
+    for (int i = tid; i < PR * PR * 3; i += 256) {
+      const int c = i % PR, r = (i / PR) % PR, ci = i / (PR * PR);
+      const int hi = hi0 + r, wi = wi0 + c;
+      float v = 0.f;
+      if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = (ib[((int64_t)ci * H + hi) * W + wi] - mean[ci]) / stdv[ci];
+      sin_[ci][r][c & 1][c >> 1] = v;
+    }
+  }
+  __syncthreads();
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[COUT];
+#pragma unroll
+  for (int i = 0; i < COUT; ++i) acc[i] = 0.f;
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        const float v = sin_[ci][2 * ty + kh][kw & 1][tx + (kw >> 1)];
+        const float4* wr = reinterpret_cast<const float4*>(&ws[((kh * 3 + kw) * 3 + ci) * COUT]);
+#pragma unroll
+        for (int q = 0; q < COUT / 4; ++q) {
+          const float4 wv = wr[q];
+          acc[q * 4 + 0] = fmaf(v, wv.x, acc[q * 4 + 0]); acc[q * 4 + 1] = fmaf(v, wv.y, acc[q * 4 + 1]);
+          acc[q * 4 + 2] = fmaf(v, wv.z, acc[q * 4 + 2]); acc[q * 4 + 3] = fmaf(v, wv.w, acc[q * 4 + 3]);
+        }
+      }
+    }
+  }
+  const int ho = ho0 + ty, wo = wo0 + tx;
+  if (ho >= Ho || wo >= Wo) return;
+  const int64_t pix = ((int64_t)b * Ho + ho) * Wo + wo;
+  if (act & 256) {  // FB200_F16PAIR output: [hi(32) | lo(32)] fp16 per pixel
+    __half* o = reinterpret_cast<__half*>(out) + pix * 2 * COUT;
+#pragma unroll
+    for (int co = 0; co < COUT; co += 4) {
+      float v[4], h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[j] = apply_act(acc[co + j] * sc[co + j] + bi[co + j], act);
+        h[j] = __half2float(__float2half_rn(v[j]));
+        l[j] = v[j] - h[j];
+      }
+      store4(o + co, h);
+      store4(o + COUT + co, l);
+    }
+    return;
+  }
+  TOut* o = out + pix * COUT;
+#pragma unroll
+  for (int co = 0; co < COUT; co += 4) {
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = apply_act(acc[co + j] * sc[co + j] + bi[co + j], act);
+    store4(o + co, v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // generic implicit GEMM.  M = B*Ho*Wo, N = Cout, K = KH*KW*Cin (k = (kh*KW+kw)*Cin + c).
 // 64x64x16 tile, 256 threads, 4x4 micro-tile, register-prefetch double buffering.
@@ -260,8 +351,15 @@ static int stem_launch(const void* img, bool u8, int B, int H, int W, const floa
   const int64_t total = (int64_t)B * Ho * Wo;
   cudaStream_t st = (cudaStream_t)stream;
   const float* m = mean3; const float* s = std3;  // HOST pointers (3 floats each)
-  const unsigned grid = (unsigned)cdiv(total, 128);
-#define STEM_LAUNCH(T, U8) stem_conv_kernel<T, 32, U8><<<grid, 128, 0, st>>>(img, B, H, W, w, scale, bias, m[0], m[1], m[2], s[0], s[1], s[2], act, (T*)out)
+  const int tiles_w = (Wo + 15) / 16, tiles_h = (Ho + 15) / 16;
+  static int tiled = -1;  // FB200_STEM_TILED=0: the per-pixel kernel (A/B)
+  if (tiled < 0) { const char* e = getenv("FB200_STEM_TILED"); tiled = e ? atoi(e) : 1; }
+  const unsigned grid = tiled ? (unsigned)((int64_t)B * tiles_w * tiles_h) : (unsigned)cdiv(total, 128);
+#define STEM_LAUNCH(T, U8)                                                                                                                                              \
+  do {                                                                                                                                                                  \
+    if (tiled) stem_conv_tiled_kernel<T, U8><<<grid, 256, 0, st>>>(img, B, H, W, w, scale, bias, m[0], m[1], m[2], s[0], s[1], s[2], act, (T*)out, tiles_w, tiles_h);   \
+    else stem_conv_kernel<T, 32, U8><<<grid, 128, 0, st>>>(img, B, H, W, w, scale, bias, m[0], m[1], m[2], s[0], s[1], s[2], act, (T*)out);                              \
+  } while (0)
   if (out_dtype == FB200_F32) { if (u8) STEM_LAUNCH(float, true); else STEM_LAUNCH(float, false); }
   else if (out_dtype == FB200_F16) { if (u8) STEM_LAUNCH(__half, true); else STEM_LAUNCH(__half, false); }
   else if (out_dtype == FB200_F16PAIR) { act |= 256; if (u8) STEM_LAUNCH(__half, true); else STEM_LAUNCH(__half, false); }  // dense [hi(32) | lo(32)] pair per pixel
