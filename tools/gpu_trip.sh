@@ -35,6 +35,11 @@ for s in $STAGES; do
     ncu_fs) timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 2 -c 1 -o gpurun_out/prof_fs python tools/conv_micro.py --split rep_3x3_80 > gpurun_out/ncu_fs.log 2>&1 ;;
     alltests) timeout 2400 python -m pytest tests -q -m gpu -x 2>&1 | tail -30 > gpurun_out/t_all.log ;;
     ablib) timeout 600 python tools/ab_lib.py focoos_b200/lib/libfocoos_b200_r01.so focoos_b200/lib/libfocoos_b200.so > gpurun_out/ab_lib.txt 2>&1 ;;
+    ddp2) timeout 1500 python -m pytest tests/test_gpu_train_ddp.py -q -m gpu -s 2>&1 | tail -15 > gpurun_out/t_ddp2.log ;;
+    bench2) timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 2 --steps 20 --warmup 3 --no-other-configs > gpurun_out/bench_2gpu.log 2> gpurun_out/bench_2gpu.err ;;
+    bench8) timeout 1800 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus 8 --steps 20 --warmup 3 --no-other-configs > gpurun_out/bench_8gpu.log 2> gpurun_out/bench_8gpu.err ;;
+    benchdefault) (time timeout 1500 python bench.py) > gpurun_out/bench_default.log 2> gpurun_out/bench_default.err ;;
+    ncu_list32) timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_fp32_tc.csv python tools/profile_step.py fp32_tc > gpurun_out/ncu_list_fp32_tc.log 2>&1 ;;
     trace) (FB200_TC_CTA2=0 timeout 300 python tools/conv_trace.py rep_3x3_80 rep_3x3_40 s3_2b s2_2a s0_2c; timeout 300 python tools/conv_trace.py rep_3x3_80 rep_3x3_40; true) > gpurun_out/conv_trace.txt 2>&1 ;;
     budget2) timeout 1200 python tools/error_budget.py tc:3323 tc:3331 tc:3332 tc:2222 tc:1111 > gpurun_out/error_budget2.txt 2>&1 ;;
     micro01) (FB200_TC_CTA2=0 timeout 300 python tools/conv_micro.py; true) > gpurun_out/conv_micro_cta1.txt 2>&1; (timeout 300 python tools/conv_micro.py; true) > gpurun_out/conv_micro_cta2.txt 2>&1 ;;
