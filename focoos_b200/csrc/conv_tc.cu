@@ -32,6 +32,19 @@ namespace fb200 {
 
 namespace tc {
 
+// The debug timeline (fb200_set_conv_trace) and the experiment knobs (FB200_TC_DBG) are compiled in by default; -DFB200_TC_NO_TRACE / -DFB200_TC_NO_DBG strip them
+// (A/B builds: tools/ab_lib.py)
+#ifdef FB200_TC_NO_TRACE
+constexpr bool kTrace = false;
+#else
+constexpr bool kTrace = true;
+#endif
+#ifdef FB200_TC_NO_DBG
+constexpr bool kDbg = false;
+#else
+constexpr bool kDbg = true;
+#endif
+
 constexpr int BLOCK_M = 128;
 constexpr int STAGING_BYTES = BLOCK_M * 128;  // one staging tile: 128 rows x 128 B
 constexpr int PRODUCER_THREADS = 128;  // warps 0-3: TMA, MMA, TMEM alloc, spare
@@ -327,7 +340,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int tiles_per_img = p.tiles_w * p.tiles_h;
   // debug timeline: slot 0 = kernel entry of this CTA (globaltimer ns), 1 = setup done (clock64); per tile k < 20: 2+6k = accumulator stage free,
   // 3+6k = first operands landed, 4+6k = last MMA issued (MMA thread); 5+6k = accumulator complete seen, 6+6k = tile stored (epilogue group 0); 7+6k = producer tile start
-  unsigned long long* const trc = p.trace ? p.trace + (size_t)blockIdx.x * 128 : nullptr;
+  unsigned long long* const trc = (kTrace && p.trace) ? p.trace + (size_t)blockIdx.x * 128 : nullptr;
+  const int dbgv = kDbg ? p.dbg : 0;
   auto stamp = [&](int slot) { if (trc && slot < 128) trc[slot] = (unsigned long long)clock64(); };
   if (trc && threadIdx.x == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); trc[0] = g; trc[1] = (unsigned long long)clock64(); }
   struct TileXY { int n0, mt, img, h0, w0; };
@@ -443,7 +457,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const long long e0_ = trc ? clock64() : 0;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (trc) wait_empty += clock64() - e0_;
-          if ((p.dbg & 8) && fills >= STAGES) {  // experiment: operands stay whatever the first ring fill loaded - no TMA traffic, the MMAs run at their own pace
+          if ((dbgv & 8) && fills >= STAGES) {  // experiment: operands stay whatever the first ring fill loaded - no TMA traffic, the MMAs run at their own pace
             if (cta_rank == 0) mbar_arrive(&full_bar[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
             continue;
@@ -479,8 +493,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             tma_load_5d(&tmap_a, &full_bar[stage], dst_a, wp * p.x_pitch + a_c0, w0 + dw, hp, h0 + dh, img);
           }
           if (p.w_batched) tma_load_3d(&tmap_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb * BKP, n0, img);
-          else if ((p.dbg & 64) && BLOCK_N >= 128) {  // experiment: same bytes, more TMA instructions
-            const int parts = (p.dbg & 128) ? 4 : 2;
+          else if ((dbgv & 64) && BLOCK_N >= 128) {  // experiment: same bytes, more TMA instructions
+            const int parts = (dbgv & 128) ? 4 : 2;
             for (int q = 0; q < parts; ++q)
               tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES + q * (B_STAGE_BYTES / parts), kb * BKP, n0 + q * (BLOCK_N / parts));
           } else tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb * BKP, n0);
@@ -507,7 +521,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           const long long w0_ = trc ? clock64() : 0;
-          if (!(p.dbg & 32)) mbar_wait(&full_bar[stage], phase);  // dbg 32: the MMAs never wait for operands (timing experiment: loads still run)
+          if (!(dbgv & 32)) mbar_wait(&full_bar[stage], phase);  // dbg 32: the MMAs never wait for operands (timing experiment: loads still run)
           tcgen05_fence_after();
           if (trc) wait_full += clock64() - w0_;
           if (kb == 0) stamp(3 + 6 * tk);
@@ -557,7 +571,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
             for (int k = 0; k < BLOCK_K / 16; ++k) {
               // advance 16 halves = 32 B inside the swizzle row: +2 in 16-byte units
-              const uint32_t td = ((p.dbg & 16) && (k & 1)) ? tmem_base + (uint32_t)((acc ^ 1) * BLOCK_N) : tmem_d;  // dbg 16: two independent accumulation chains
+              const uint32_t td = ((dbgv & 16) && (k & 1)) ? tmem_base + (uint32_t)((acc ^ 1) * BLOCK_N) : tmem_d;  // dbg 16: two independent accumulation chains
               if constexpr (CTA2) umma_f16_2sm(td, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
               else umma_f16(td, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
             }
@@ -592,7 +606,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // each chunk, before the staging-buffer wait / TMEM load, and consumed after them.  (A one-chunk-ahead register
     // pipeline was measured slower — profiles/r01_trip11 vs trip12; deeper prefetch needs an smem ring: next round.)
     constexpr int RES_VECS = 8;  // 16-byte vectors per 128-byte row chunk
-    const bool has_res = p.res != nullptr && !(p.dbg & 2);
+    const bool has_res = p.res != nullptr && !(dbgv & 2);
     uint4 rcur[RES_VECS];
     auto res_fetch = [&](int tt, int cc0, uint4 (&dst)[RES_VECS]) -> bool {
       if (PAIR || !has_res || tt >= p.total_tiles) return false;  // pair residuals always come through TMA
@@ -664,7 +678,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll 1
       for (int c0 = c_begin; c0 < c_end && !p.rowmax; c0 += CHUNK_COLS) {
         if (n0 + c0 >= p.Cout) break;  // uniform across the group
-        if (p.dbg & 4) break;          // experiment: no epilogue work at all
+        if (dbgv & 4) break;          // experiment: no epilogue work at all
         uint8_t* stg = my_staging + (chunk_ctr % NSTG) * STAGING_BYTES;
         uint8_t* srow = stg + row * 128;
         bool res_vec = false;
@@ -795,7 +809,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         fence_proxy_async();
         epi_bar(grp);
         if (et == 0) {
-          if (!(p.dbg & 1)) {
+          if (!(dbgv & 1)) {
             tma_store_4d(&tmap_d, stg, n0 + c0, w0, h0, img);
             if constexpr (PAIR) tma_store_4d(&tmap_d2, stg + STAGING_BYTES / 2, n0 + c0, w0, h0, img);
           }

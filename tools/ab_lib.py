@@ -3,13 +3,14 @@
 import ctypes, sys, os
 import torch
 
-libs = [ctypes.CDLL(os.path.abspath(p)) for p in sys.argv[1:3]]
+paths = [a for a in sys.argv[1:] if a.endswith(".so")]
+libs = [ctypes.CDLL(os.path.abspath(p)) for p in paths]
 SHAPES = {"s0_2c_res": (32, 160, 160, 64, 256, 1, 1, True), "s0_2b": (32, 160, 160, 64, 64, 3, 1, False), "s1_2c_res": (32, 80, 80, 128, 512, 1, 1, True),
           "s2_2b": (32, 40, 40, 256, 256, 3, 1, False), "s2_2a": (32, 40, 40, 1024, 256, 1, 1, False), "rep_3x3_80": (32, 80, 80, 256, 256, 3, 1, False),
           "csp_1x1_80": (32, 80, 80, 512, 512, 1, 1, False), "value_all": (1, 1, 268800, 256, 1536, 1, 1, False), "stem3": (32, 320, 320, 32, 64, 3, 1, False),
           "dec_lin": (1, 1, 9600, 256, 256, 1, 1, False)}
 P = lambda t: ctypes.c_void_p(0 if t is None else t.data_ptr())
-print(f"{'shape':12} " + " ".join(f"{os.path.basename(p)[:24]:>24}" for p in sys.argv[1:3]) + "   ratio")
+print(f"{'shape':12} " + " ".join(f"{os.path.basename(p)[15:-3][-22:]:>22}" for p in paths) + "   (us; ratios vs the first)")
 for name, (B, H, W, Cin, Cout, k, s, res) in SHAPES.items():
     x = torch.randn((B, H, W, Cin), device="cuda").half()
     w = (torch.randn((Cout, k, k, Cin), device="cuda") * 0.05).half()
@@ -34,4 +35,4 @@ for name, (B, H, W, Cin, Cout, k, s, res) in SHAPES.items():
             row.append(e0.elapsed_time(e1) * 100)
         ts.append(row)
     best = [min(t[i] for t in ts) for i in range(len(libs))]
-    print(f"{name:12} " + " ".join(f"{b:24.1f}" for b in best) + f"   {best[1] / best[0]:.3f}")
+    print(f"{name:12} " + " ".join(f"{b:22.1f}" for b in best) + "   " + " ".join(f"{b / best[0]:.3f}" for b in best[1:]))

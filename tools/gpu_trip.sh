@@ -34,7 +34,7 @@ for s in $STAGES; do
     benchfp16) timeout 900 python bench.py --steps 20 --warmup 3 --precision fp16 --quick --no-cpu-baseline > gpurun_out/bench_fp16.log 2> gpurun_out/bench_fp16.err ;;
     ncu_fs) timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 2 -c 1 -o gpurun_out/prof_fs python tools/conv_micro.py --split rep_3x3_80 > gpurun_out/ncu_fs.log 2>&1 ;;
     alltests) timeout 2400 python -m pytest tests -q -m gpu -x 2>&1 | tail -30 > gpurun_out/t_all.log ;;
-    ablib) timeout 600 python tools/ab_lib.py focoos_b200/lib/libfocoos_b200_r01.so focoos_b200/lib/libfocoos_b200.so > gpurun_out/ab_lib.txt 2>&1 ;;
+    ablib) timeout 900 python tools/ab_lib.py focoos_b200/lib/libfocoos_b200_r01.so $(ls focoos_b200/lib/libfocoos_b200_*.so | grep -v r01) focoos_b200/lib/libfocoos_b200.so > gpurun_out/ab_lib.txt 2>&1 ;;
     ddp2) timeout 1500 python -m pytest tests/test_gpu_train_ddp.py -q -m gpu -s 2>&1 | tail -15 > gpurun_out/t_ddp2.log ;;
     bench2) timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 2 --steps 20 --warmup 3 --no-other-configs > gpurun_out/bench_2gpu.log 2> gpurun_out/bench_2gpu.err ;;
     bench8) timeout 1800 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus 8 --steps 20 --warmup 3 --no-other-configs > gpurun_out/bench_8gpu.log 2> gpurun_out/bench_8gpu.err ;;
