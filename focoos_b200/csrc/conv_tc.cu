@@ -78,6 +78,7 @@ struct KParams {
   int dbg;                         // tuning aid (env FB200_TC_DBG): 1 = skip TMA store, 2 = skip residual, 4 = skip TMEM load
   unsigned long long* trace;       // debug timeline (fb200_set_conv_trace): 128 clock64 slots per CTA, see tools/conv_trace.py
   int nimg;                        // images in the (possibly flattened) view: M tiles beyond it are phantoms of an odd CTA-pair count
+  int ncat;                        // fused split with BLOCK_N <= 128: A_hi x [W_hi | W_lo] as ONE MMA of N = 2 * BLOCK_N (see NCAT in conv_tc_kernel)
 };
 
 // ---------------------------------------------------------------------------------------------- PTX
@@ -309,7 +310,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr uint32_t TMEM_COLS = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);  // two accumulator stages
+  // N-concatenated split products: a tcgen05.mma with both operands in shared memory costs ~128 cycles for its 128 x 16 A slice whatever N is
+  // (profiles/r02_conv_timeline.md), so with BLOCK_N <= 128 the products A_hi x W_hi and A_hi x W_lo are issued as ONE MMA against the adjacent [W_hi | W_lo] rows
+  // (N = 2 * BLOCK_N, accumulator columns [0, 2 * BLOCK_N)); A_lo x W_hi accumulates into columns [0, BLOCK_N) and the epilogue adds the two halves: two MMAs per
+  // 16-channel step instead of three.  Enabled per launch by p.ncat.
+  constexpr bool NCAT_OK = FS && !CTA2 && BLOCK_N <= 128;
+  constexpr int ACC_COLS = NCAT_OK ? 2 * BLOCK_N : BLOCK_N;  // TMEM columns of one accumulator stage
+  constexpr uint32_t TMEM_COLS = (2 * ACC_COLS) < 32 ? 32 : (2 * ACC_COLS);  // two accumulator stages
+  const bool ncat = NCAT_OK && p.ncat;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
@@ -518,7 +526,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (trc) wait_acc += clock64() - a0_;
         const int tk = (t - t_first) / t_stride;
         stamp(2 + 6 * tk);
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * ACC_COLS);
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           const long long w0_ = trc ? clock64() : 0;
           if (!(dbgv & 32)) mbar_wait(&full_bar[stage], phase);  // dbg 32: the MMAs never wait for operands (timing experiment: loads still run)
@@ -534,6 +542,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               const uint64_t ah = da + (uint64_t)(kw * 4), al = da_lo + (uint64_t)(kw * 4);
               const uint64_t bh = make_smem_desc<BKP>(smem_u32(smem_w + ((kb * 3 + kw) * 2) * (BLOCK_N * 64)));
               const uint64_t bl = make_smem_desc<BKP>(smem_u32(smem_w + ((kb * 3 + kw) * 2 + 1) * (BLOCK_N * 64)));
+              if constexpr (NCAT_OK) {
+                if (ncat) {  // W_lo of a tap follows its W_hi in the resident weights: one N = 2 * BLOCK_N MMA for both
+                  constexpr uint32_t idesc2 = make_idesc(2 * BLOCK_N, 128);
+#pragma unroll
+                  for (int k = 0; k < 2; ++k) {
+                    const uint64_t ko = (uint64_t)(k * 2);
+                    umma_f16(tmem_d, ah + ko, bh + ko, idesc2, (kb > 0 || kw > 0 || k > 0) ? 1u : 0u);
+                    umma_f16(tmem_d, al + ko, bh + ko, idesc, 1u);
+                  }
+                  continue;
+                }
+              }
 #pragma unroll
               for (int k = 0; k < 2; ++k) {
                 const uint64_t ko = (uint64_t)(k * 2);
@@ -549,12 +569,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               if constexpr (CTA2) umma_f16_2sm(tmem_d, a, b, idesc, acc_flag);
               else umma_f16(tmem_d, a, b, idesc, acc_flag);
             };
+            bool done = false;
+            if constexpr (NCAT_OK) {
+              if (ncat) {  // the W_lo half of the stage follows the W_hi half (B_HALF = BLOCK_N rows of 128 B): one N = 2 * BLOCK_N MMA for both
+                constexpr uint32_t idesc2 = make_idesc(2 * BLOCK_N, 128);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {  // hi x W_hi, hi x W_lo, lo x W_hi per 16-channel step, all into the same fp32 accumulator
-              const uint64_t ko = (uint64_t)(k * 2);
-              issue(da + ko, db + ko, (kb > 0 || k > 0) ? 1u : 0u);
-              issue(da + ko, db_lo + ko, 1u);
-              issue(da_lo + ko, db + ko, 1u);
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t ko = (uint64_t)(k * 2);
+                  umma_f16(tmem_d, da + ko, db + ko, idesc2, (kb > 0 || k > 0) ? 1u : 0u);
+                  umma_f16(tmem_d, da_lo + ko, db + ko, idesc, 1u);
+                }
+                done = true;
+              }
+            }
+            if (!done) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {  // hi x W_hi, hi x W_lo, lo x W_hi per 16-channel step, all into the same fp32 accumulator
+                const uint64_t ko = (uint64_t)(k * 2);
+                issue(da + ko, db + ko, (kb > 0 || k > 0) ? 1u : 0u);
+                issue(da + ko, db_lo + ko, 1u);
+                issue(da_lo + ko, db + ko, 1u);
+              }
             }
           } else if constexpr (HALO) {
 #pragma unroll
@@ -662,7 +697,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
       if (grp == 0 && et == 0) stamp(5 + 6 * ((t - t_first) / t_stride));
-      const uint32_t tmem_acc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      const uint32_t tmem_acc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * ACC_COLS);
       float row_max = -INFINITY;
       if (p.rowmax) {  // row-max-only epilogue: enc_outputs_class.max(-1) (modelling.py:1210) without materialising the [B*S, num_classes] logits
 #pragma unroll 1
@@ -703,6 +738,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (c0 + sub * 32 >= c_end) break;  // BLOCK_N = 32 with fp16 output: half a staging row
           uint32_t r[32];
           tmem_ld32(tmem_acc + (uint32_t)(c0 + sub * 32), r);
+          if constexpr (NCAT_OK) {
+            if (ncat) {  // second half of the accumulator: the A_hi x W_lo product
+              uint32_t r2[32];
+              tmem_ld32(tmem_acc + (uint32_t)(BLOCK_N + c0 + sub * 32), r2);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+            }
+          }
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -904,7 +947,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
   constexpr int smem = smem_bytes<BLOCK_N, STAGES, BLOCK_K, NSTG, CTA2, FS>();
   constexpr int NUM_THREADS = num_threads<BLOCK_N>();
   static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
-  static_assert(MIN_BLOCKS * 2 * BLOCK_N <= 512, "TMEM budget exceeded (a blocked tcgen05.alloc would deadlock)");
+  static_assert(MIN_BLOCKS * 2 * ((FS && !CTA2 && BLOCK_N <= 128) ? 2 * BLOCK_N : BLOCK_N) <= 512, "TMEM budget exceeded (a blocked tcgen05.alloc would deadlock)");
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1101,6 +1144,7 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("FB200_TC_DBG"); dbg = e ? atoi(e) : 0; } k2.dbg = dbg; }
     { static int rt = -1; if (rt < 0) { const char* e = getenv("FB200_TC_RES_TMA"); rt = e ? atoi(e) : 1; } k2.res_tma = (p.res && rt) ? 1 : 0; }
     if (outp) k2.res_tma = p.res ? 1 : 0;  // pair residuals only come through TMA
+    { static int nc = -1; if (nc < 0) { const char* e = getenv("FB200_TC_NCAT"); nc = e ? atoi(e) : 1; } k2.ncat = (nc && !p.rowmax) ? 1 : 0; }
     if constexpr (decltype(gelu_tag)::value) return launch<BN_, ST_, __half, MB_, BK_, NS_, true>(ta, tb, td, tr, td2, tr2, k2, st);
     else if constexpr (FS_) {  // fp32 or pair output (checked by the caller)
       if constexpr (NS_ >= 2) { if (outp) return launch<BN_, ST_, PairOut, MB_, BK_, NS_, false, C2_, true>(ta, tb, td, tr, td2, tr2, k2, st); }

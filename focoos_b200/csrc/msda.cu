@@ -84,7 +84,7 @@ template <> struct Quad<__half> {
 template <typename TV, typename TOA, typename TO>
 __global__ void __launch_bounds__(256) msda_quad_kernel(const TV* __restrict__ value, int v_pitch, const TOA* __restrict__ oa, int oa_pitch,
                                                         const float* __restrict__ ref, MsdaShapes sh, int L, int P, int S, int Q, int heads, int64_t total,
-                                                        TO* __restrict__ out, int out_pitch) {
+                                                        TO* __restrict__ out, int out_pitch, int pair_lo_off = 0) {
   const int lane = threadIdx.x & 31;
   const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (wid >= total) return;
@@ -133,7 +133,15 @@ __global__ void __launch_bounds__(256) msda_quad_kernel(const TV* __restrict__ v
   if (lane < 8) {
     TO* o = out + bq * out_pitch + h * 32 + lane * 4;
     float v[4] = {acc[0], acc[1], acc[2], acc[3]};
-    store4(o, v);
+    if (pair_lo_off) {  // FB200_F16PAIR rows [hi | lo] (TO = __half): the operand format of the output_proj tensor-core linear
+      float hi[4], lo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { hi[j] = __half2float(__float2half_rn(v[j])); lo[j] = v[j] - hi[j]; }
+      store4(o, hi);
+      store4(o + pair_lo_off, lo);
+    } else {
+      store4(o, v);
+    }
   }
 }
 
@@ -161,7 +169,7 @@ extern "C" int fb200_msda(const void* value, int v_dtype, int v_pitch, const voi
   // 4-channel vector loads need 8/16-byte aligned rows; FB200_MSDA_SCALAR=1 selects the one-tap-per-load kernel (A/B timing, debugging)
   static int scalar = -1;
   if (scalar < 0) { const char* e = getenv("FB200_MSDA_SCALAR"); scalar = e ? atoi(e) : 0; }
-  const size_t velt = v_dtype == FB200_F16 ? 2 : 4, oelt = out_dtype == FB200_F16 ? 2 : 4;
+  const size_t velt = v_dtype == FB200_F16 ? 2 : 4, oelt = out_dtype == FB200_F32 ? 4 : 2;
   const bool quad = !scalar && (v_pitch * velt) % (4 * velt) == 0 && (reinterpret_cast<uintptr_t>(value) % (4 * velt)) == 0 && (out_pitch * oelt) % (4 * oelt) == 0 &&
                     (reinterpret_cast<uintptr_t>(out) % (4 * oelt)) == 0;
 #define MSDA_LAUNCH(TV, TOA, TO)                                                                                                                                   \
@@ -169,7 +177,11 @@ extern "C" int fb200_msda(const void* value, int v_dtype, int v_pitch, const voi
     if (quad) msda_quad_kernel<TV, TOA, TO><<<grid, 256, 0, st>>>((const TV*)value, v_pitch, (const TOA*)oa, oa_pitch, ref, sh, L, P, S, Q, heads, total, (TO*)out, out_pitch); \
     else msda_kernel<TV, TOA, TO><<<grid, 256, 0, st>>>((const TV*)value, v_pitch, (const TOA*)oa, oa_pitch, ref, sh, L, P, S, Q, heads, total, (TO*)out, out_pitch);        \
   } while (0)
-  if (v_dtype == FB200_F32 && oa_dtype == FB200_F32 && out_dtype == FB200_F32) MSDA_LAUNCH(float, float, float);
+  if (v_dtype == FB200_F32 && oa_dtype == FB200_F32 && out_dtype == FB200_F16PAIR) {
+    FB_CHECK_ARG(quad && out_pitch >= 2 * heads * 32, "msda: pair output needs 16-byte aligned rows of [hi(heads*32) | lo(heads*32)] halves");
+    msda_quad_kernel<float, float, __half><<<grid, 256, 0, st>>>((const float*)value, v_pitch, (const float*)oa, oa_pitch, ref, sh, L, P, S, Q, heads, total, (__half*)out, out_pitch,
+                                                                 heads * 32);
+  } else if (v_dtype == FB200_F32 && oa_dtype == FB200_F32 && out_dtype == FB200_F32) MSDA_LAUNCH(float, float, float);
   else if (v_dtype == FB200_F16 && oa_dtype == FB200_F32 && out_dtype == FB200_F16) MSDA_LAUNCH(__half, float, __half);
   else if (v_dtype == FB200_F16 && oa_dtype == FB200_F16 && out_dtype == FB200_F16) MSDA_LAUNCH(__half, __half, __half);
   else { set_error("msda: unsupported dtype combination %d/%d/%d", v_dtype, oa_dtype, out_dtype); return FB200_ERR_UNSUPPORTED; }

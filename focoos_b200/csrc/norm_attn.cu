@@ -1,4 +1,6 @@
 // LayerNorm(+residual) and small-sequence multi-head attention (L = 300/400, head_dim = 32).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace fb200 {
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(256) attention_kernel(const T* __restrict__ q,
 }
 
 int attention_mma_split(const float* q, int q_pitch, const float* k, int k_pitch, const float* v, int v_pitch, float* out, int out_pitch, int B, int Lq, int Lk,
-                        int heads, float scale, cudaStream_t st);
+                        int heads, float scale, int out_pair, cudaStream_t st);
 int attention_mma(const __half* q, int q_pitch, const __half* k, int k_pitch, const __half* v, int v_pitch, __half* out, int out_pitch, int B,
                   int Lq, int Lk, int heads, float scale, cudaStream_t st);
 }  // namespace fb200
@@ -156,13 +158,15 @@ extern "C" int fb200_attention(const void* q, int q_pitch, const void* k, int k_
   return FB200_OK;
 }
 
-extern "C" int fb200_attention_split(const float* q, int q_pitch, const float* k, int k_pitch, const float* v, int v_pitch, float* out, int out_pitch, int B,
+extern "C" int fb200_attention_split(const float* q, int q_pitch, const float* k, int k_pitch, const float* v, int v_pitch, void* out, int out_dtype, int out_pitch, int B,
                                      int Lq, int Lk, int heads, int head_dim, float scale, void* stream) {
   FB_CHECK_ARG(q && k && v && out, "attention_split: null pointer");
   FB_CHECK_ARG(head_dim == 32, "attention_split: head_dim must be 32 (got %d)", head_dim);
   FB_CHECK_ARG(q_pitch % 4 == 0 && k_pitch % 4 == 0 && v_pitch % 4 == 0 && out_pitch % 2 == 0 && (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) & 15) == 0 &&
                    ((uintptr_t)out & 7) == 0, "attention_split: pitches / alignment");
-  return attention_mma_split(q, q_pitch, k, k_pitch, v, v_pitch, out, out_pitch, B, Lq, Lk, heads, scale, (cudaStream_t)stream);
+  FB_CHECK_ARG(out_dtype == FB200_F32 || out_dtype == FB200_F16PAIR, "attention_split: out_dtype must be F32 or F16PAIR");
+  FB_CHECK_ARG(out_dtype != FB200_F16PAIR || out_pitch >= 2 * heads * 32, "attention_split: pair rows are [hi(heads*32) | lo(heads*32)]");
+  return attention_mma_split(q, q_pitch, k, k_pitch, v, v_pitch, (float*)out, out_pitch, B, Lq, Lk, heads, scale, out_dtype == FB200_F16PAIR ? 1 : 0, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -307,18 +311,21 @@ __device__ __forceinline__ void split_store4(__half* hi, __half* lo, const float
   *reinterpret_cast<__half2*>(lo) = l0; *reinterpret_cast<__half2*>(lo + 2) = l1;
 }
 
-__global__ void __launch_bounds__(128) attention_mma_split_kernel(const float* __restrict__ q, int q_pitch, const float* __restrict__ k, int k_pitch,
+// blockDim.x = 32 * NW (NW <= 12 warps, 16 queries each): the K/V planes of a (batch, head) are staged once per 16*NW queries.  out_pair: the output is written as the
+// fp16 [hi | lo] pair (row = [hi(heads*32) | lo(heads*32)], pitch out_pitch in halves) for the out_proj tensor-core linear that follows.
+__global__ void __launch_bounds__(384) attention_mma_split_kernel(const float* __restrict__ q, int q_pitch, const float* __restrict__ k, int k_pitch,
                                                                   const float* __restrict__ v, int v_pitch, float* __restrict__ out, int out_pitch,
-                                                                  int Lq, int Lk, int heads, float scale_log2) {
+                                                                  int Lq, int Lk, int heads, float scale_log2, int out_pair) {
   extern __shared__ __align__(16) __half smh[];
   const int LkP = (Lk + 63) & ~63;
   const size_t kv = (size_t)LkP * AM_PITCH;
   __half* Kh = smh; __half* Kl = Kh + kv; __half* Vh = Kl + kv; __half* Vl = Vh + kv;
-  __half* Qh = Vl + kv; __half* Ql = Qh + 64 * AM_PITCH;
+  const int QB = (int)(blockDim.x >> 5) * 16;  // queries per CTA
+  __half* Qh = Vl + kv; __half* Ql = Qh + QB * AM_PITCH;
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
-  const int q0 = blockIdx.y * 64;
+  const int q0 = blockIdx.y * QB;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < LkP * 8; i += 128) {  // 8 x float4 per 32-wide row
+  for (int i = tid; i < LkP * 8; i += (int)blockDim.x) {  // 8 x float4 per 32-wide row
     const int r = i >> 3, c = (i & 7) * 4;
     float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
     if (r < Lk) {
@@ -328,7 +335,7 @@ __global__ void __launch_bounds__(128) attention_mma_split_kernel(const float* _
     split_store4(Kh + r * AM_PITCH + c, Kl + r * AM_PITCH + c, kk);
     split_store4(Vh + r * AM_PITCH + c, Vl + r * AM_PITCH + c, vv);
   }
-  for (int i = tid; i < 64 * 8; i += 128) {
+  for (int i = tid; i < QB * 8; i += (int)blockDim.x) {
     const int r = i >> 3, c = (i & 7) * 4;
     float4 qq = make_float4(0.f, 0.f, 0.f, 0.f);
     if (q0 + r < Lq) qq = *reinterpret_cast<const float4*>(q + ((int64_t)b * Lq + q0 + r) * q_pitch + h * 32 + c);
@@ -414,23 +421,49 @@ __global__ void __launch_bounds__(128) attention_mma_split_kernel(const float* _
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) {
     const int c = h * 32 + nt * 8 + (lane & 3) * 2;
+    if (out_pair) {
+      __half* oh = reinterpret_cast<__half*>(out);
+      const int lo_off = heads * 32;
+      if (r0 < Lq) {
+        const float a0 = o[nt][0] * i0, a1 = o[nt][1] * i0;
+        const __half2 hh = __floats2half2_rn(a0, a1);
+        const float2 hf = __half22float2(hh);
+        __half* dst = oh + ((int64_t)b * Lq + r0) * out_pitch + c;
+        *reinterpret_cast<__half2*>(dst) = hh;
+        *reinterpret_cast<__half2*>(dst + lo_off) = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+      }
+      if (r1 < Lq) {
+        const float a0 = o[nt][2] * i1, a1 = o[nt][3] * i1;
+        const __half2 hh = __floats2half2_rn(a0, a1);
+        const float2 hf = __half22float2(hh);
+        __half* dst = oh + ((int64_t)b * Lq + r1) * out_pitch + c;
+        *reinterpret_cast<__half2*>(dst) = hh;
+        *reinterpret_cast<__half2*>(dst + lo_off) = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+      }
+      continue;
+    }
     if (r0 < Lq) *reinterpret_cast<float2*>(out + ((int64_t)b * Lq + r0) * out_pitch + c) = make_float2(o[nt][0] * i0, o[nt][1] * i0);
     if (r1 < Lq) *reinterpret_cast<float2*>(out + ((int64_t)b * Lq + r1) * out_pitch + c) = make_float2(o[nt][2] * i1, o[nt][3] * i1);
   }
 }
 
 int attention_mma_split(const float* q, int q_pitch, const float* k, int k_pitch, const float* v, int v_pitch, float* out, int out_pitch, int B, int Lq, int Lk,
-                        int heads, float scale, cudaStream_t st) {
+                        int heads, float scale, int out_pair, cudaStream_t st) {
   const int LkP = (Lk + 63) & ~63;
-  const size_t smem = ((size_t)4 * LkP + 128) * AM_PITCH * sizeof(__half);
+  // queries per CTA: as few CTAs per (batch, head) as 16 warps allow (each CTA stages the whole K and V of its head), warps rounded to what the last block needs
+  static int max_q = -1;  // FB200_ATTN_QB: upper bound of queries per CTA (multiple of 16, <= 192); tuning knob
+  if (max_q < 0) { const char* e = getenv("FB200_ATTN_QB"); max_q = e ? atoi(e) : 192; if (max_q < 16 || max_q > 192) max_q = 192; }
+  const int nblk = (int)cdiv(Lq, max_q);
+  const int NW = (int)cdiv(cdiv(Lq, nblk), 16);
+  const size_t smem = ((size_t)4 * LkP + 2 * 16 * NW) * AM_PITCH * sizeof(__half);
   if (smem > 227 * 1024) { set_error("attention(split): Lk=%d does not fit shared memory", Lk); return FB200_ERR_UNSUPPORTED; }
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(attention_mma_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     configured = true;
   }
-  dim3 grid(B * heads, (unsigned)cdiv(Lq, 64));
-  attention_mma_split_kernel<<<grid, 128, smem, st>>>(q, q_pitch, k, k_pitch, v, v_pitch, out, out_pitch, Lq, Lk, heads, scale * 1.4426950408889634f);
+  dim3 grid(B * heads, (unsigned)cdiv(Lq, 16 * NW));
+  attention_mma_split_kernel<<<grid, 32 * NW, smem, st>>>(q, q_pitch, k, k_pitch, v, v_pitch, out, out_pitch, Lq, Lk, heads, scale * 1.4426950408889634f, out_pair);
   FB_CHECK_LAUNCH("attention_mma_split");
   return FB200_OK;
 }

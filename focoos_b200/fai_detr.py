@@ -543,15 +543,41 @@ class DetrEngine:
         return ops.conv2d_pair(ops.to_pair(x), conv.w3, conv.scale, conv.bias, stride=conv.stride, pad=conv.pad, act=conv.act if act is None else act,
                                residual=residual, out=out, out_pair=out_pair)
 
-    def _plin(self, lin, xp: "ops.Pair", act=ops.ACT_NONE):
-        """packed _Linear on pair-format tokens [B,S,K] -> fp32 [B,S,N]"""
+    def _plin(self, lin, xp: "ops.Pair", act=ops.ACT_NONE, residual=None, out_pair=False, out=None):
+        """packed _Linear on pair-format tokens [B,S,K] -> fp32 [B,S,N] (+ fp32 residual), or a Pair [B,S,N] with out_pair=True.
+        `out`: an fp32 [B,S,>=N] buffer whose first N columns receive the result (row pitch = its last dimension)"""
         buf = xp.buf
         assert buf.is_contiguous() and xp.c0 == 0 and xp.C == xp.Ctot
         lead = buf.shape[:-1]
         x4 = ops.Pair(buf.reshape(1, 1, -1, buf.shape[-1]))
         N = lin.w3.shape[0]
-        y = ops.conv2d_pair(x4, lin.w3.reshape(N, 1, 1, lin.w3.shape[-1]), None, lin.bias, act=act, out_pair=False)
-        return y.reshape(*lead, N)
+        w4 = lin.w3.reshape(N, 1, 1, lin.w3.shape[-1])
+        if out_pair:
+            y = ops.conv2d_pair(x4, w4, None, lin.bias, act=act, out_pair=True)
+            return ops.Pair(y.buf.reshape(*lead, 2 * N))
+        r4 = None if residual is None else residual.reshape(1, 1, -1, N)
+        o4 = None if out is None else out.reshape(1, 1, -1, out.shape[-1])[..., :N]
+        y = ops.conv2d_pair(x4, w4, None, lin.bias, act=act, residual=r4, out=o4, out_pair=False)
+        return y.reshape(*lead, N) if out is None else out[..., :N]
+
+    # fused row glue (csrc/head_fused.cu): LayerNorm / positional add / GELU / gather / mask kernels write the pair operand of the next tensor-core linear themselves
+    # (and attention / deformable attention write pair rows), so no split_f32_pair / add / row_select launch remains in the AIFI, selection and decoder chains
+    fused_glue = True
+
+    def _aifi_pair(self, src, pos):
+        """AIFI encoder layer (nn/layers/transformer.py:583-601, post-norm, GELU) on fp32 tokens [B,L,d] -> (fp32 tokens, their Pair)"""
+        blk, d = self.aifi, src.shape[-1]
+        sp, spp = ops.split_pair_ex(src, pos=pos, want_pair=True, want_pair_pos=True)
+        qk = self._plin(blk["qk"], spp)
+        v = self._plin(blk["v"], sp)
+        a = ops.attention(qk[..., :d], qk[..., d:], v, self.nhead, 1.0 / math.sqrt(d // self.nhead), split=True, out_pair=True)
+        y = self._plin(blk["out"], a, residual=src)
+        x1, x1p, _ = ops.layernorm_ex(y, *blk["n_attn"])
+        h = self._plin(blk["l1"], x1p)
+        hp, _ = ops.split_pair_ex(h, act=ops.ACT_GELU)
+        y = self._plin(blk["l2"], hp, residual=x1)
+        x2, x2p, _ = ops.layernorm_ex(y, *blk["n_ffn"])
+        return x2, x2p
 
     def _csp_run_pair(self, packed, cat, out=None):
         both, reps = packed
@@ -590,10 +616,15 @@ class DetrEngine:
         self._pc(self.enc_in[1], res4, out=cat1.slice(C, 2 * C))
         p5 = self._pc(self.enc_in[2], res5, out_pair=False)          # fp32 tokens for the AIFI block (LayerNorm / attention work on fp32)
         src = p5.reshape(B, h32 * w32, C)
-        src = self._mha(self.aifi, src, K["pos"])
-        src = self._ffn(self.aifi, src, ops.ACT_GELU)
-        p5 = src.reshape(B, h32, w32, C)
-        lat0 = self._pc(self.lateral[0], p5, out=cat4.slice(C, 2 * C))
+        if self.fused_glue:
+            src, src_p = self._aifi_pair(src, K["pos"])
+            p5 = src.reshape(B, h32, w32, C)
+            lat0 = self._pc(self.lateral[0], P(src_p.buf.reshape(B, h32, w32, 2 * C)), out=cat4.slice(C, 2 * C))
+        else:
+            src = self._mha(self.aifi, src, K["pos"])
+            src = self._ffn(self.aifi, src, ops.ACT_GELU)
+            p5 = src.reshape(B, h32, w32, C)
+            lat0 = self._pc(self.lateral[0], p5, out=cat4.slice(C, 2 * C))
         ops.pair_resize_bilinear(lat0, (h32 * 2, w32 * 2), out=cat1.slice(0, C))
         fpn0 = self._csp_run_pair(self.fpn[0], cat1)
         lat1 = self._pc(self.lateral[1], fpn0, out=cat3.slice(C, 2 * C))
@@ -640,6 +671,8 @@ class DetrEngine:
             value_all = self._plin(self.value_all, mem_pair)
             t = self._plin(self.enc_output, mem_pair)
             memory = None
+            if self.fused_glue:
+                return self._forward_head_pair(t, value_all, shapes, K, B, S, taps, mem_pair)
             return self._forward_head(t, value_all, memory, shapes, K, B, S, taps, mem_pair)
         _products = self.mix["backbone"]
         feats = self._run_backbone(images)
@@ -735,6 +768,56 @@ class DetrEngine:
             taps.update(pred_logits=logits, pred_boxes_cxcywh=ref)
         _products = 3
         return ops.box_sigmoid(logits), ops.box_cxcywh_to_xyxy(ref)
+
+
+    def _forward_head_pair(self, t, value_all, shapes, K, B, S, taps, mem_pair):
+        """query selection + decoder + head of the fp32-accurate mode with the fused row glue: the same operators and arithmetic as _forward_head, ~18 launches per
+        decoder layer instead of 31.  t = enc_output.0(memory) BEFORE the valid-mask fill (modelling.py:1202-1207)."""
+        cfg, d = self.cfg, self.d
+        nq, ncls = cfg.num_queries, cfg.num_classes
+        ln_w, ln_b = self.enc_output_ln
+        # output_memory = LayerNorm(where(valid, t, bias)) only ever feeds the score head (as a pair) and the 300 gathered rows (recomputed below from t: same arithmetic)
+        _, om_pair, _ = ops.layernorm_ex(t, ln_w, ln_b, valid=K["valid"], fill=self.enc_output.bias, want_f32=False)
+        scores = ops.linear_rowmax_pair(om_pair, self.enc_score.w3, self.enc_score.bias)
+        _, topk_ind = ops.topk(scores, nq)
+        tgt, tgt_p, _ = ops.layernorm_ex(t, ln_w, ln_b, gather=topk_ind, valid=K["valid"], fill=self.enc_output.bias)
+        h = self._plin(self.enc_bbox[1], self._plin(self.enc_bbox[0], tgt_p, act=ops.ACT_RELU, out_pair=True), act=ops.ACT_RELU, out_pair=True)
+        bb = self._plin(self.enc_bbox[2], h)
+        ref_unact = ops.box_add_anchors(bb, K["anchors"], topk_ind)
+        ref = ops.box_sigmoid(ref_unact)
+        if taps is not None:
+            taps.update(memory=mem_pair.float(), enc_scores=scores, topk_ind=topk_ind, target=tgt, ref_unact=ref_unact)
+        q0w, q0b = self.qpos[0].w, self.qpos[0].bias   # query_pos_head layer 0: fp32 [2d, 4]
+        _, qp = ops.box_refine_qpos(None, ref, q0w, q0b)
+        scale = 1.0 / math.sqrt(d // self.nhead)
+        L = len(self.dec)
+        for i, blk in enumerate(self.dec):
+            pos = self._plin(self.qpos[1], qp)
+            _, tpp = ops.split_pair_ex(tgt, pos=pos, want_pair=False, want_pair_pos=True)
+            qk = self._plin(blk["qk"], tpp)
+            v = self._plin(blk["v"], tgt_p)
+            a = ops.attention(qk[..., :d], qk[..., d:], v, self.nhead, scale, split=True, out_pair=True)
+            y = self._plin(blk["out"], a, residual=tgt)
+            tgt, _, tpp = ops.layernorm_ex(y, *blk["n_attn"], pos=pos, want_pair=False, want_pair_pos=True)
+            oa = self._plin(blk["oa"], tpp)
+            c = ops.msda(value_all[..., i * d:(i + 1) * d], oa, ref, shapes, cfg_points(cfg), self.nhead, out_pair=True)
+            y = self._plin(blk["cross_out"], c, residual=tgt)
+            tgt, tgt_p, _ = ops.layernorm_ex(y, *blk["n_cross"])
+            y = self._plin(blk["l2"], self._plin(blk["l1"], tgt_p, act=ops.ACT_RELU, out_pair=True), residual=tgt)
+            tgt, tgt_p, _ = ops.layernorm_ex(y, *blk["n_ffn"])
+            h = self._plin(blk["bbox"][1], self._plin(blk["bbox"][0], tgt_p, act=ops.ACT_RELU, out_pair=True), act=ops.ACT_RELU, out_pair=True)
+            delta = self._plin(blk["bbox"][2], h)
+            last = i == L - 1
+            ref, qp = ops.box_refine_qpos(delta, ref, None if last else q0w, None if last else q0b)
+            if taps is not None:
+                taps[f"dec{i}_out"] = tgt
+                taps[f"dec{i}_ref"] = ref
+        # class logits on the tensor cores into a 16-byte-padded row (TMA store pitch), then sigmoid into the dense [B,Q,C] scores
+        lbuf = torch.empty((B, nq, (ncls + 3) // 4 * 4), dtype=torch.float32, device=t.device)
+        logits = self._plin(self.dec_score, tgt_p, out=lbuf)
+        if taps is not None:
+            taps.update(pred_logits=logits, pred_boxes_cxcywh=ref)
+        return ops.sigmoid_rows(logits), ops.box_cxcywh_to_xyxy(ref)
 
 
 def cfg_points(cfg) -> int:

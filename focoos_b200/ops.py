@@ -69,6 +69,7 @@ EXPORTED_SYMBOLS = (
     "fb200_maxpool3x3s2", "fb200_avgpool2x2_ceil", "fb200_resize_bilinear", "fb200_add", "fb200_layernorm",
     "fb200_attention", "fb200_attention_split", "fb200_msda", "fb200_row_select", "fb200_rowmax", "fb200_topk", "fb200_gather_rows",
     "fb200_box_op", "fb200_detr_postprocess", "fb200_detr_eval_postprocess",
+    "fb200_layernorm_ex", "fb200_split_pair_ex", "fb200_box_refine_qpos", "fb200_sigmoid_rows",
 )
 
 _launch_count = 0
@@ -231,23 +232,56 @@ class CudaBackend:
         self._call("fb200_layernorm", _p(x), _p(res), _p(gamma), _p(beta), _p(out), _dt(x), ctypes.c_int64(x.numel() // C), C, ctypes.c_float(eps), _stream())
 
     def attention(self, q, k, v, out, heads, scale, split=False):
-        self._cuda(q, k, v, out)
+        self._cuda(q, k, v)
         B, Lq, C = q.shape
         if split and q.dtype == torch.float32:
-            self._call("fb200_attention_split", _p(q), _pitch(q), _p(k), _pitch(k), _p(v), _pitch(v), _p(out), _pitch(out), B, Lq, k.shape[1], heads, C // heads,
-                       ctypes.c_float(scale), _stream())
+            pair = isinstance(out, Pair)
+            o = out.buf if pair else out
+            self._cuda(o)
+            self._call("fb200_attention_split", _p(q), _pitch(q), _p(k), _pitch(k), _p(v), _pitch(v), _p(o), F16PAIR if pair else F32, _pitch(o), B, Lq, k.shape[1],
+                       heads, C // heads, ctypes.c_float(scale), _stream())
             return
         self._call("fb200_attention", _p(q), _pitch(q), _p(k), _pitch(k), _p(v), _pitch(v), _p(out), _pitch(out), _dt(q), B, Lq, k.shape[1],
                    heads, C // heads, ctypes.c_float(scale), _stream())
 
     def msda(self, value, oa, ref, shapes, P, heads, out):
-        self._cuda(value, oa, ref, out)
+        self._cuda(value, oa, ref)
         B, S, _ = value.shape
         Q = oa.shape[1]
         flat = [int(v) for hw in shapes for v in hw]
         sh = (ctypes.c_int * len(flat))(*flat)
+        pair = isinstance(out, Pair)
+        o = out.buf if pair else out
+        self._cuda(o)
         self._call("fb200_msda", _p(value), _dt(value), _pitch(value), _p(oa), _dt(oa), _pitch(oa), _p(ref), sh, len(shapes), P, B, S, Q, heads,
-                   _p(out), _dt(out), _pitch(out), _stream())
+                   _p(o), F16PAIR if pair else _dt(o), _pitch(o), _stream())
+
+    def layernorm_ex(self, x, res, gather, valid, fill, gamma, beta, eps, M, out_f32, out_pair, pos, out_pair_pos):
+        """x [.., C] fp32 rows (last-dim pitch); gather int32 [B, K] or None; valid uint8 [S] or None; outputs: fp32 tensor / Pair / Pair (each optional)"""
+        self._cuda(x, gamma, beta)
+        C = x.shape[-1]
+        S = 0 if valid is None else valid.numel()
+        if gather is not None and valid is None:
+            S = x.shape[-2]
+        self._call("fb200_layernorm_ex", _p(x), _pitch(x), _p(res), _p(gather), 0 if gather is None else gather.shape[-1], _p(valid), S, _p(fill), _p(gamma), _p(beta),
+                   ctypes.c_float(eps), ctypes.c_int64(M), C, _p(out_f32), _p(None if out_pair is None else out_pair.buf), _p(pos),
+                   ctypes.c_int64(0 if pos is None else pos.numel() // C), _p(None if out_pair_pos is None else out_pair_pos.buf), _stream())
+
+    def split_pair_ex(self, x, act, pos, out_pair, out_pair_pos):
+        self._cuda(x)
+        C = x.shape[-1]
+        self._call("fb200_split_pair_ex", _p(x), ctypes.c_int64(x.numel() // C), C, _pitch(x), act, _p(pos), ctypes.c_int64(0 if pos is None else pos.numel() // C),
+                   _p(None if out_pair is None else out_pair.buf), _p(None if out_pair_pos is None else out_pair_pos.buf), _stream())
+
+    def box_refine_qpos(self, delta, ref_in, ref_out, w0, b0, qpos_pair):
+        self._cuda(ref_in)
+        self._call("fb200_box_refine_qpos", _p(delta), _p(ref_in), _p(ref_out), _p(w0), _p(b0), 0 if w0 is None else w0.shape[0],
+                   _p(None if qpos_pair is None else qpos_pair.buf), ctypes.c_int64(ref_in.numel() // 4), _stream())
+
+    def sigmoid_rows(self, x, out):
+        self._cuda(x, out)
+        C = x.shape[-1]
+        self._call("fb200_sigmoid_rows", _p(x), _pitch(x), ctypes.c_int64(x.numel() // C), C, _p(out), _stream())
 
     def row_select(self, x, valid, fill, out):
         self._cuda(x, valid, fill, out)
@@ -565,10 +599,15 @@ def layernorm(x, gamma, beta, residual=None, eps=1e-5):
     return out
 
 
-def attention(q, k, v, heads: int, scale: float, split: bool = False):
+def attention(q, k, v, heads: int, scale: float, split: bool = False, out_pair: bool = False):
     """softmax(q k^T * scale) v per head; q [B,Lq,C], k,v [B,Lk,C] (may be column slices of one buffer).
     split=True (fp32 tensors only): tensor-core kernel with split-precision products instead of the CUDA-core fp32 kernel."""
     B, Lq, C = q.shape
+    if out_pair:  # fp32 split kernel writing the [hi | lo] pair rows the out_proj linear reads
+        assert split and q.dtype == torch.float32
+        out = Pair.empty((B, Lq, C), q.device)
+        _be().attention(q, k, v, out, heads, scale, True)
+        return out
     out = torch.empty((B, Lq, C), dtype=q.dtype, device=q.device)
     if split and q.dtype == torch.float32:
         _be().attention(q, k, v, out, heads, scale, True)
@@ -577,11 +616,57 @@ def attention(q, k, v, heads: int, scale: float, split: bool = False):
     return out
 
 
-def msda(value, oa, ref, shapes, num_points: int, heads: int, out_dtype=None):
+def msda(value, oa, ref, shapes, num_points: int, heads: int, out_dtype=None, out_pair: bool = False):
     """value [B,S,heads*32]; oa [B,Q,heads*L*P*3] (offsets then logits); ref [B,Q,4] fp32 -> [B,Q,heads*32]."""
     B, Q = oa.shape[0], oa.shape[1]
-    out = torch.empty((B, Q, heads * 32), dtype=out_dtype or value.dtype, device=value.device)
+    if out_pair:
+        out = Pair.empty((B, Q, heads * 32), value.device)
+    else:
+        out = torch.empty((B, Q, heads * 32), dtype=out_dtype or value.dtype, device=value.device)
     _be().msda(value, oa, ref.contiguous(), [tuple(s) for s in shapes], num_points, heads, out)
+    return out
+
+
+def layernorm_ex(x, gamma, beta, *, residual=None, gather=None, valid=None, fill=None, pos=None, want_f32=True, want_pair=True, want_pair_pos=False, eps=1e-5):
+    """Fused row glue of the fp32-accurate head (csrc/head_fused.cu): LayerNorm of fp32 rows x [B, S, C] - optionally gathered by top-k indices `gather` [B, K]
+    and masked by `valid` [S] / `fill` [C] - returned as (fp32 tensor | None, Pair | None, Pair of (y + pos) | None)."""
+    C = x.shape[-1]
+    if gather is not None:
+        lead = (x.shape[0], gather.shape[-1])
+    else:
+        lead = tuple(x.shape[:-1])
+    M = 1
+    for d in lead:
+        M *= d
+    of = torch.empty((*lead, C), dtype=torch.float32, device=x.device) if want_f32 else None
+    op = Pair.empty((*lead, C), x.device) if want_pair else None
+    opp = Pair.empty((*lead, C), x.device) if want_pair_pos else None
+    _be().layernorm_ex(x, residual, gather, valid, fill, gamma, beta, eps, M, of, op, pos if want_pair_pos else None, opp)
+    return of, op, opp
+
+
+def split_pair_ex(x, *, act=ACT_NONE, pos=None, want_pair=True, want_pair_pos=False):
+    """(Pair of act(x) | None, Pair of (x + pos) | None) of an fp32 tensor in one pass; pos broadcasts over leading rows"""
+    x = x if x.stride(-1) == 1 else x.contiguous()
+    op = Pair.empty(tuple(x.shape), x.device) if want_pair else None
+    opp = Pair.empty(tuple(x.shape), x.device) if want_pair_pos else None
+    _be().split_pair_ex(x, act, pos if want_pair_pos else None, op, opp)
+    return op, opp
+
+
+def box_refine_qpos(delta, ref, w0=None, b0=None):
+    """(new reference boxes, Pair of relu(boxes . w0^T + b0) | None): bbox refinement (delta may be None: boxes = ref) + first query_pos_head layer"""
+    ref = ref.contiguous()
+    new_ref = torch.empty_like(ref) if delta is not None else ref
+    qp = Pair.empty((*ref.shape[:-1], w0.shape[0]), ref.device) if w0 is not None else None
+    _be().box_refine_qpos(None if delta is None else delta.contiguous(), ref, new_ref if delta is not None else None, w0, b0, qp)
+    return new_ref, qp
+
+
+def sigmoid_rows(x):
+    """dense sigmoid(x) of a (possibly pitched) fp32 [.., C] view"""
+    out = torch.empty(tuple(x.shape), dtype=torch.float32, device=x.device)
+    _be().sigmoid_rows(x, out)
     return out
 
 

@@ -135,13 +135,32 @@ int fb200_add(const void* a, const void* b, void* out, int dtype, int64_t rows, 
 int fb200_layernorm(const void* x, const void* res, const float* gamma, const float* beta, void* out, int dtype,
                     int64_t M, int C, float eps, void* stream);
 
+/* ---- a8,a9,a4 in the fp32-accurate mode: the row-wise glue between two tensor-core linears, fused so that each linear finds its operand already in the pair
+ * format (csrc/head_fused.cu).  Arithmetic identical to the separate launches they replace.
+ * fb200_layernorm_ex: y = LayerNorm(sel(x)[src(m)] (+ res[m])) * gamma + beta for output rows m < M, where src(m) = m, or (m / gather_k) * S + gather_idx[m] with a
+ * top-k index tensor [B, gather_k] (torch.gather of the selected queries, modelling.py:1216-1229), and sel() replaces a source row r with !valid[r % S] by fill[C]
+ * (memory * valid_mask folded behind enc_output.0, modelling.py:1202-1207).  Outputs (each optional): out_f32 [M, C]; out_pair [M, 2C] = [hi | lo] fp16;
+ * out_pair_pos = pair of (y + pos[m % pos_rows]) - with_pos_embed in front of the q/k and sampling-offset projections (modelling.py:918-919, 934-947). */
+int fb200_layernorm_ex(const float* x, int x_pitch, const float* res, const int* gather_idx, int gather_k, const uint8_t* valid, int S, const float* fill,
+                       const float* gamma, const float* beta, float eps, int64_t M, int C, float* out_f32, void* out_pair, const float* pos, int64_t pos_rows,
+                       void* out_pair_pos, void* stream);
+/* out_pair = pair(act(x)) and / or out_pair_pos = pair(x + pos[r % pos_rows]) of fp32 rows x [rows, C] (pitch x_pitch); act as fb200_act (exact-erf GELU of the AIFI FFN,
+ * nn/layers/transformer.py:600) */
+int fb200_split_pair_ex(const float* x, int64_t rows, int C, int x_pitch, int act, const float* pos, int64_t pos_rows, void* out_pair, void* out_pair_pos, void* stream);
+/* decoder box refinement + first query_pos_head layer in one pass (modelling.py:990-1008): ref_out = sigmoid(delta + inverse_sigmoid(ref_in)) when delta != NULL (else the
+ * boxes are ref_in), qpos_pair [M, 2N] = pair(relu(box . w0[N,4]^T + b0)) when qpos_pair != NULL (N % 64 == 0). */
+int fb200_box_refine_qpos(const float* delta, const float* ref_in, float* ref_out, const float* w0, const float* b0, int N, void* qpos_pair, int64_t M, void* stream);
+/* out[M, C] dense = sigmoid(x[M, C] with row pitch x_pitch): class scores from the 16-byte-padded logits of the tensor-core score head (modelling.py:378) */
+int fb200_sigmoid_rows(const float* x, int x_pitch, int64_t M, int C, float* out, void* stream);
+
 /* ---- a4,a9: softmax(Q K^T * scale) V per (batch, head); nn.MultiheadAttention core
  * (SURVEY A.6).  q/k/v/out rows are tokens; head h uses columns [h*hd, (h+1)*hd). hd must be 32. */
 int fb200_attention(const void* q, int q_pitch, const void* k, int k_pitch, const void* v, int v_pitch, void* out,
                     int out_pitch, int dtype, int B, int Lq, int Lk, int heads, int head_dim, float scale, void* stream);
 /* fp32 tensors on the fp16 tensor cores (precision="fp32_tc"): Q, K, V are split into [hi|lo] halves on the way into shared memory and every product
- * is formed as hi*hi + hi*lo + lo*hi with fp32 accumulation (mma.sync m16n8k16), softmax in fp32.  Same semantics as fb200_attention(FB200_F32). */
-int fb200_attention_split(const float* q, int q_pitch, const float* k, int k_pitch, const float* v, int v_pitch, float* out, int out_pitch, int B,
+ * is formed as hi*hi + hi*lo + lo*hi with fp32 accumulation (mma.sync m16n8k16), softmax in fp32.  Same semantics as fb200_attention(FB200_F32).
+ * out_dtype FB200_F32: fp32 rows.  FB200_F16PAIR: rows written as [hi(heads*32) | lo(heads*32)] fp16 (out_pitch in halves) - the operand of the out_proj linear. */
+int fb200_attention_split(const float* q, int q_pitch, const float* k, int k_pitch, const float* v, int v_pitch, void* out, int out_dtype, int out_pitch, int B,
                           int Lq, int Lk, int heads, int head_dim, float scale, void* stream);
 
 /* ---- a10: multi-scale deformable attention core, softmax over levels*points fused.
@@ -149,7 +168,8 @@ int fb200_attention_split(const float* q, int q_pitch, const float* k, int k_pit
  * ms_deform_attn_core_pytorch (nn/layers/deformable.py:10-35).
  * value: [B,S,heads*32] (pitch v_pitch).  oa: [B*Q, heads*L*P*3] fp32 or fp16 = sampling offsets
  * [heads][L][P][2] followed by attention logits [heads][L*P] (one fused linear).  ref: [B*Q,4] fp32
- * (cx,cy,w,h in sigmoid space).  shapes_host: L pairs (H_l, W_l) in HOST memory.  out: [B*Q, heads*32]. */
+ * (cx,cy,w,h in sigmoid space).  shapes_host: L pairs (H_l, W_l) in HOST memory.  out: [B*Q, heads*32]
+ * (out_dtype FB200_F16PAIR with fp32 value / oa: rows [hi(heads*32) | lo(heads*32)] fp16, out_pitch in halves). */
 int fb200_msda(const void* value, int v_dtype, int v_pitch, const void* oa, int oa_dtype, int oa_pitch, const float* ref,
                const int* shapes_host, int L, int P, int B, int S, int Q, int heads, void* out, int out_dtype,
                int out_pitch, void* stream);

@@ -128,7 +128,11 @@ class RefBackend:
         kh = k.float().reshape(B, Lk, heads, hd).transpose(1, 2)
         vh = v.float().reshape(B, Lk, heads, hd).transpose(1, 2)
         a = torch.softmax((qh @ kh.transpose(-1, -2)) * scale, dim=-1)
-        out.copy_((a @ vh).transpose(1, 2).reshape(B, Lq, C).to(out.dtype))
+        o = (a @ vh).transpose(1, 2).reshape(B, Lq, C)
+        if hasattr(out, "hi"):
+            self._pair_write(out, o)
+        else:
+            out.copy_(o.to(out.dtype))
 
     def msda(self, value, oa, ref, shapes, P, heads, out):
         B, S, C = value.shape
@@ -150,7 +154,55 @@ class RefBackend:
             sampled.append(F.grid_sample(vl, g, mode="bilinear", padding_mode="zeros", align_corners=False))
         awt = aw.transpose(1, 2).reshape(B * heads, 1, Q, L * P)
         o = (torch.stack(sampled, dim=-2).flatten(-2) * awt).sum(-1).view(B, heads * hd, Q).transpose(1, 2)
-        out.copy_(o.to(out.dtype))
+        if hasattr(out, "hi"):
+            self._pair_write(out, o)
+        else:
+            out.copy_(o.to(out.dtype))
+
+    def layernorm_ex(self, x, res, gather, valid, fill, gamma, beta, eps, M, out_f32, out_pair, pos, out_pair_pos):
+        """fb200_layernorm_ex: optional valid-mask fill and top-k gather of the source rows, LayerNorm, outputs as fp32 / pair / pair(y + pos)"""
+        C = x.shape[-1]
+        v = x.float()
+        if valid is not None:
+            S = valid.numel()
+            v = torch.where(valid.bool().view(1, S, 1), v.reshape(-1, S, C), fill.view(1, 1, C))
+        if gather is not None:
+            v = v.reshape(gather.shape[0], -1, C)
+            v = torch.gather(v, 1, gather.long().unsqueeze(-1).expand(-1, -1, C))
+        v = v.reshape(M, C)
+        if res is not None:
+            v = v + res.float().reshape(M, C)
+        y = F.layer_norm(v, (C,), gamma, beta, eps)
+        if out_f32 is not None:
+            out_f32.copy_(y.reshape(out_f32.shape))
+        if out_pair is not None:
+            self._pair_write(out_pair, y.reshape(out_pair.shape))
+        if out_pair_pos is not None:
+            pr = pos.numel() // C
+            yp = (y.reshape(M // pr, pr, C) + pos.float().reshape(1, pr, C)).reshape(out_pair_pos.shape)
+            self._pair_write(out_pair_pos, yp)
+
+    def split_pair_ex(self, x, act, pos, out_pair, out_pair_pos):
+        C = x.shape[-1]
+        v = x.float()
+        if out_pair is not None:
+            self._pair_write(out_pair, _act(v, act & 15))
+        if out_pair_pos is not None:
+            pr = pos.numel() // C
+            rows = v.numel() // C
+            self._pair_write(out_pair_pos, (v.reshape(rows // pr, pr, C) + pos.float().reshape(1, pr, C)).reshape(v.shape))
+
+    def box_refine_qpos(self, delta, ref_in, ref_out, w0, b0, qpos_pair):
+        r = ref_in.float()
+        if delta is not None:
+            x = r.clamp(0, 1)
+            r = torch.sigmoid(delta.float() + torch.log(x.clamp(min=1e-5) / (1 - x).clamp(min=1e-5)))
+            ref_out.copy_(r)
+        if qpos_pair is not None:
+            self._pair_write(qpos_pair, torch.relu(r @ w0.float().t() + b0.float()))
+
+    def sigmoid_rows(self, x, out):
+        out.copy_(torch.sigmoid(x.float()))
 
     def row_select(self, x, valid, fill, out):
         C = x.shape[-1]

@@ -246,3 +246,74 @@ def test_attention_split_precision(B, Lq, Lk, heads):
     out = ops.attention(qg, kg, v.to(DEV), heads, scale, split=True)
     err = float((out.cpu() - ref).abs().max())
     assert err <= 2e-5 * max(1.0, float(ref.abs().max())), err
+    # pair rows for the out_proj linear: exactly the split of the fp32 result
+    op = ops.attention(qg, kg, v.to(DEV), heads, scale, split=True, out_pair=True)
+    assert torch.equal(op.buf, ops.split_pair(out))
+
+
+def _pair_eq(p, f32):
+    """a Pair holds exactly the [hi | lo] split of an fp32 tensor"""
+    return torch.equal(p.buf, ops.split_pair(f32.contiguous()))
+
+
+def test_fused_row_glue_equals_the_separate_launches():
+    """csrc/head_fused.cu against the launches it replaces (bit for bit): layernorm_ex (mask fill, top-k gather, residual, fp32 / pair / pair + pos outputs),
+    split_pair_ex (GELU, + pos), box_refine_qpos (refinement + query_pos layer 0), sigmoid_rows (pitched), msda pair rows."""
+    B, S, C, K = 3, 500, 256, 40
+    x = rnd((B, S, C), torch.float32, 1, 2.0).to(DEV)
+    res = rnd((B, S, C), torch.float32, 2).to(DEV)
+    g, b_ = (torch.rand(C) + 0.5).to(DEV), rnd((C,), torch.float32, 3, 0.2).to(DEV)
+    valid = (torch.rand(S, generator=torch.Generator().manual_seed(4)) > 0.2).to(torch.uint8).to(DEV)
+    fill = rnd((C,), torch.float32, 5).to(DEV)
+    pos = rnd((B, S, C), torch.float32, 6).to(DEV)
+    # plain LayerNorm(x + res): fp32, pair, pair(y + pos)
+    y_ref = ops.layernorm(x + res, g, b_)
+    y, yp, ypp = ops.layernorm_ex(x, g, b_, residual=res, pos=pos, want_pair_pos=True)
+    assert torch.equal(y, y_ref) and _pair_eq(yp, y_ref) and _pair_eq(ypp, ops.add(y_ref, pos))
+    # masked rows (memory * valid_mask behind enc_output.0) and gathered rows
+    sel = ops.row_select(x, valid, fill)
+    full = ops.layernorm(sel, g, b_)
+    _, fp, _ = ops.layernorm_ex(x, g, b_, valid=valid, fill=fill, want_f32=False)
+    assert _pair_eq(fp, full)
+    idx = torch.stack([torch.randperm(S, generator=torch.Generator().manual_seed(7 + i))[:K] for i in range(B)]).to(torch.int32).to(DEV)
+    gat = ops.gather_rows(full, idx)
+    gy, gp, _ = ops.layernorm_ex(x, g, b_, gather=idx, valid=valid, fill=fill)
+    assert torch.equal(gy, gat) and _pair_eq(gp, gat)
+    # broadcast positional term (AIFI: pos [L, C] for every image), GELU
+    pos1 = rnd((S, C), torch.float32, 8).to(DEV)
+    sp, spp = ops.split_pair_ex(x, pos=pos1, want_pair=True, want_pair_pos=True)
+    assert _pair_eq(sp, x) and _pair_eq(spp, ops.add(x, pos1))
+    hp, _ = ops.split_pair_ex(x, act=ops.ACT_GELU)
+    ref_gelu = torch.nn.functional.gelu(x.cpu())
+    assert float((hp.float().cpu() - ref_gelu).abs().max()) < 1e-5
+    # box refinement + query_pos_head layer 0
+    M = 700
+    ref = torch.rand((2, M // 2, 4), generator=torch.Generator().manual_seed(9)).to(DEV)
+    delta = rnd((2, M // 2, 4), torch.float32, 10, 0.5).to(DEV)
+    w0, b0 = rnd((512, 4), torch.float32, 11, 0.7).to(DEV), rnd((512,), torch.float32, 12, 0.3).to(DEV)
+    new_ref, qp = ops.box_refine_qpos(delta, ref, w0, b0)
+    want_ref = ops.box_refine(delta, ref)
+    assert torch.equal(new_ref, want_ref)
+    want_q = ops.linear(want_ref, w0, b0, act=ops.ACT_RELU, out_dtype=torch.float32, algo=ops.ALGO_SIMT)
+    assert _pair_eq(qp, want_q)
+    same_ref, qp0 = ops.box_refine_qpos(None, ref, w0, b0)
+    assert same_ref is ref or torch.equal(same_ref, ref)
+    assert _pair_eq(qp0, ops.linear(ref, w0, b0, act=ops.ACT_RELU, out_dtype=torch.float32, algo=ops.ALGO_SIMT))
+    only_ref, none = ops.box_refine_qpos(delta, ref)
+    assert none is None and torch.equal(only_ref, want_ref)
+    # pitched sigmoid
+    buf = rnd((2, 300, 368), torch.float32, 13, 3.0).to(DEV)
+    sg = ops.sigmoid_rows(buf[..., :365])
+    assert sg.is_contiguous() and torch.equal(sg, ops.box_sigmoid(buf[..., :365].contiguous()))
+
+
+def test_msda_pair_rows_equal_the_split_fp32_output():
+    shapes = [(20, 20), (40, 40), (80, 80)]
+    Sv = sum(h * w for h, w in shapes)
+    B, Q, heads, P = 2, 300, 8, 4
+    value = rnd((B, Sv, 6 * 256), torch.float32, 1).to(DEV)[..., 256:512]   # a layer's column slice of the fused value projection
+    oa = rnd((B, Q, heads * 3 * P * 3), torch.float32, 2).to(DEV)
+    ref = torch.rand((B, Q, 4), generator=torch.Generator().manual_seed(3)).to(DEV)
+    out = ops.msda(value, oa, ref, shapes, P, heads)
+    op = ops.msda(value, oa, ref, shapes, P, heads, out_pair=True)
+    assert _pair_eq(op, out)

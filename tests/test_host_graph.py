@@ -71,3 +71,33 @@ def test_processor_ragged_sizes(ref_backend):
         assert len(d) == n
         assert [x.cls_id for x in d.detections] == g["det_labels"][i, :n].tolist() or sorted(x.cls_id for x in d.detections) == sorted(g["det_labels"][i, :n].tolist())
         assert sorted(tuple(x.bbox) for x in d.detections) == sorted(map(tuple, g["det_boxes"][i, :n].tolist()))
+
+
+def test_fp32_tc_pair_graph_with_fused_glue_matches_golden(ref_backend):
+    """precision="fp32_tc" host orchestration (pair-format trunk, fused row glue of csrc/head_fused.cu in the AIFI / selection / decoder chains) through the CPU
+    operator references: same golden bars as the fp32 graph, and the fused-glue flow equals the one-operator-per-launch flow it replaces."""
+    g = load_golden("detr_l_obj365_b2_640")
+    m = FAIDetr(DETRConfig(), precision="fp32_tc")
+    m.load_state_dict(seeded_sd(0), strict=True)
+    proc = DETRProcessor(m.config, image_size=640)
+    imgs = synth_images(1, [(640, 640)] * 2)
+    x, _ = proc.preprocess(imgs, device=torch.device("cpu"))
+    outs = {}
+    for fused in (True, False):
+        m.engine().fused_glue = fused
+        taps = {}
+        out = m(x, taps=taps)
+        outs[fused] = (out, taps)
+        ds, db = compare_queries(g["scores"], g["boxes"], g["enc_topk_ind"], out.logits.numpy(), out.boxes.numpy(), taps["topk_ind"].numpy())
+        assert ds < 2e-4 and db < 2e-4, (fused, ds, db)
+    (a, ta), (b, tb) = outs[True], outs[False]
+    assert np.array_equal(np.sort(ta["topk_ind"].numpy(), -1), np.sort(tb["topk_ind"].numpy(), -1))
+    assert tuple(a.logits.shape) == tuple(b.logits.shape) and a.logits.is_contiguous()
+    assert (a.logits - b.logits).abs().max() < 1e-5 and (a.boxes - b.boxes).abs().max() < 1e-5
+    for k in ("aifi", "dec0_out", "dec5_out", "dec5_ref", "pred_logits"):
+        assert (ta[k] - tb[k]).abs().max() <= 1e-4 * max(1.0, float(tb[k].abs().max())), k
+    dets = proc.postprocess(a, imgs, threshold=0.5)
+    for i, d in enumerate(dets):
+        n = int(g["det_count"][i])
+        assert len(d) == n
+        assert sorted(tuple(x.bbox) for x in d.detections) == sorted(map(tuple, g["det_boxes"][i, :n].tolist()))

@@ -44,6 +44,9 @@ for s in $STAGES; do
     budget2) timeout 1200 python tools/error_budget.py tc:3323 tc:3331 tc:3332 tc:2222 tc:1111 > gpurun_out/error_budget2.txt 2>&1 ;;
     micro01) (FB200_TC_CTA2=0 timeout 300 python tools/conv_micro.py; true) > gpurun_out/conv_micro_cta1.txt 2>&1; (timeout 300 python tools/conv_micro.py; true) > gpurun_out/conv_micro_cta2.txt 2>&1 ;;
     layers) timeout 600 python tools/layer_roofline.py 32 fp32_tc > gpurun_out/layer_roofline_fp32_tc.txt 2>&1; timeout 600 python tools/layer_roofline.py 32 fp16 > gpurun_out/layer_roofline_fp16.txt 2>&1 ;;
+    micropair) (for nc in 0 1; do echo "### FB200_TC_NCAT=$nc"; FB200_TC_NCAT=$nc timeout 300 python tools/conv_micro.py --pair stem2 stem3 s0_2b s1_2b s0_2a s0_2c s1_2a s2_2b; done; true) > gpurun_out/conv_micro_pair.txt 2>&1 ;;
+    attnqb) (for qb in 64 96 128 160 192; do echo "### FB200_ATTN_QB=$qb"; FB200_ATTN_QB=$qb timeout 300 python tools/head_micro.py attn; done; true) > gpurun_out/attn_qb.txt 2>&1 ;;
+    headmicro) (timeout 600 python tools/head_micro.py; true) > gpurun_out/head_micro.txt 2>&1 ;;
     micro) (python tools/conv_micro.py; true) > gpurun_out/conv_micro.txt 2>&1 ;;
     micro_ncu) timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 4 -c 2 -o gpurun_out/prof_micro python tools/conv_micro.py rep_3x3_80 s0_2c_res > gpurun_out/micro_ncu.log 2>&1 ;;
     mf)    timeout 900 python -m pytest tests/test_gpu_mf.py -q -m gpu 2>&1 | tail -40 > gpurun_out/t_mf.log ;;
