@@ -14,7 +14,9 @@ H=1); weights stay in the reference's state_dict layout (OIHW / [N,K]) and are r
     AttentionFn       nn.MultiheadAttention core   softmax(QK^T s)V per head
     MSDAFn            ms_deform_attn_core_pytorch  (+ softmax over levels*points, sampling-location arithmetic)
 
-`conv_precision`: "fp32" = SIMT fp32 kernels; "fp32_tc" = tcgen05 split-precision products (fp32 storage) where the shape allows.
+`conv_precision`: "fp32" = SIMT fp32 kernels; "fp32_tc" = tcgen05 split-precision products (fp32 storage) where the shape allows;
+"amp" = ONE tcgen05 product on fp16-rounded operands with fp32 accumulation and fp32 storage - the arithmetic class of the reference's own
+training (torch.autocast(fp16) + GradScaler, trainer/trainer.py:645,735-771), a third of the tensor work of "fp32_tc".
 """
 from __future__ import annotations
 
@@ -27,7 +29,7 @@ from . import ops
 from .ops import CudaBackend, _p, _stream
 
 ops.EXPORTED_SYMBOLS = ops.EXPORTED_SYMBOLS + (
-    "fb200_conv_wgrad_workspace_bytes", "fb200_conv_wgrad", "fb200_conv_wgrad_tc_supported", "fb200_conv_wgrad_tc_workspace_bytes", "fb200_conv_wgrad_tc", "fb200_dilate2", "fb200_col_workspace_bytes", "fb200_colsum", "fb200_bn_train_fwd", "fb200_bn_train_bwd", "fb200_bn_stats", "fb200_bn_apply", "fb200_bn_bwd_reduce", "fb200_bn_bwd_apply",
+    "fb200_conv_wgrad_workspace_bytes", "fb200_conv_wgrad", "fb200_conv_wgrad_tc_supported", "fb200_conv_wgrad_tc_workspace_bytes", "fb200_conv_wgrad_tc", "fb200_conv_wgrad_tc_f16", "fb200_dilate2", "fb200_col_workspace_bytes", "fb200_colsum", "fb200_bn_train_fwd", "fb200_bn_train_bwd", "fb200_bn_stats", "fb200_bn_apply", "fb200_bn_bwd_reduce", "fb200_bn_bwd_apply",
     "fb200_add_act", "fb200_maxpool3x3s2_bwd", "fb200_avgpool2x2_ceil_bwd", "fb200_resize_bilinear_bwd", "fb200_layernorm_bwd", "fb200_attention_bwd", "fb200_msda_bwd")
 
 _f = ctypes.c_float
@@ -60,6 +62,15 @@ def _cb_conv_wgrad_tc(self, x_pair, dy_pair, KH, KW, stride, pad, dw):
     self.lib.fb200_conv_wgrad_tc_workspace_bytes.restype = ctypes.c_int64
     ws = _ws(self.lib.fb200_conv_wgrad_tc_workspace_bytes(B, dy_pair.shape[1], dy_pair.shape[2], Cin, Cout, KH, KW), x_pair.device)
     self._call("fb200_conv_wgrad_tc", _p(x_pair), B, H, W, Cin, _p(dy_pair), Cout, KH, KW, stride, pad, _p(dw), 0, _p(ws), _stream())
+
+
+def _cb_conv_wgrad_tc_f16(self, x16, dy16, KH, KW, stride, pad, dw):
+    self._cuda(x16, dy16, dw)
+    B, H, W, Cin = x16.shape
+    Cout = dy16.shape[-1]
+    self.lib.fb200_conv_wgrad_tc_workspace_bytes.restype = ctypes.c_int64
+    ws = _ws(self.lib.fb200_conv_wgrad_tc_workspace_bytes(B, dy16.shape[1], dy16.shape[2], Cin, Cout, KH, KW), x16.device)
+    self._call("fb200_conv_wgrad_tc_f16", _p(x16), B, H, W, Cin, _p(dy16), Cout, KH, KW, stride, pad, _p(dw), 0, _p(ws), _stream())
 
 
 def _cb_dilate2(self, dy, out):
@@ -167,7 +178,7 @@ def _cb_msda_bwd(self, value, oa, ref, do, shapes, P, heads, dvalue, doa):
                dvalue.stride(1), _p(doa), doa.stride(1), _stream())
 
 
-for _n, _fn in (("conv_wgrad", _cb_conv_wgrad), ("conv_wgrad_tc_supported", _cb_conv_wgrad_tc_supported), ("conv_wgrad_tc", _cb_conv_wgrad_tc), ("dilate2", _cb_dilate2), ("colsum", _cb_colsum), ("bn_train_fwd", _cb_bn_train_fwd), ("bn_train_bwd", _cb_bn_train_bwd),
+for _n, _fn in (("conv_wgrad", _cb_conv_wgrad), ("conv_wgrad_tc_supported", _cb_conv_wgrad_tc_supported), ("conv_wgrad_tc", _cb_conv_wgrad_tc), ("conv_wgrad_tc_f16", _cb_conv_wgrad_tc_f16), ("dilate2", _cb_dilate2), ("colsum", _cb_colsum), ("bn_train_fwd", _cb_bn_train_fwd), ("bn_train_bwd", _cb_bn_train_bwd),
                 ("bn_stats", _cb_bn_stats), ("bn_apply", _cb_bn_apply), ("bn_bwd_reduce", _cb_bn_bwd_reduce), ("bn_bwd_apply", _cb_bn_bwd_apply),
                 ("add_act", _cb_add_act), ("maxpool_bwd", _cb_maxpool_bwd), ("avgpool_bwd", _cb_avgpool_bwd), ("resize_bwd", _cb_resize_bwd),
                 ("layernorm_bwd", _cb_layernorm_bwd), ("attention_bwd", _cb_attention_bwd), ("msda_bwd", _cb_msda_bwd)):
@@ -189,8 +200,12 @@ def conv_any(x, w_khwc, bias, stride: int, pad: int, precision: str, act=ops.ACT
     Cout, KH, KW, _ = w_khwc.shape
     Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
     geom = (stride == 1 and (2 * pad == KH - 1)) or (stride == 2 and KH == 3 and pad == 1 and H % 2 == 0 and W % 2 == 0)  # conv_tc.cu: conv2d_tc_supported
-    ok = (precision == "fp32_tc" and (x.is_cuda or ops._backend is not None) and C % 32 == 0 and Cout % 4 == 0 and B * Ho * Wo >= 64 and x.is_contiguous()
+    ok = (precision in ("fp32_tc", "amp") and (x.is_cuda or ops._backend is not None) and C % 32 == 0 and Cout % 4 == 0 and B * Ho * Wo >= 64 and x.is_contiguous()
           and KH == KW and geom and act in (ops.ACT_NONE, ops.ACT_RELU, ops.ACT_SILU))
+    if ok and precision == "amp":  # fp16 operands (x_pair carries the fp16 copy of x when the caller already has it), one product, fp32 out
+        x16 = x_pair if x_pair is not None else x.half()
+        y = ops.conv2d(x16, w_khwc.half(), None, bias, stride=stride, pad=pad, act=act, out_dtype=torch.float32, algo=ops.ALGO_TCGEN05)
+        return (y, x16) if return_pair else y
     if ok:
         xp = x_pair if x_pair is not None else ops.split_pair(x)
         y = ops.conv2d(xp, _split3_weights(w_khwc), None, bias, stride=stride, pad=pad, act=act, out_dtype=torch.float32, algo=ops.ALGO_TCGEN05_SPLIT3)
@@ -204,22 +219,28 @@ def conv_any(x, w_khwc, bias, stride: int, pad: int, precision: str, act=ops.ACT
 
 
 def wgrad_on_tensor_cores(x_shape, dy_shape, KH, KW, stride, pad, precision) -> bool:
-    return precision == "fp32_tc" and ops._be().conv_wgrad_tc_supported(tuple(x_shape), tuple(dy_shape), KH, KW, stride, pad)
+    return precision in ("fp32_tc", "amp") and ops._be().conv_wgrad_tc_supported(tuple(x_shape), tuple(dy_shape), KH, KW, stride, pad)
+
+
+def tc_operand(x, precision):
+    """the tensor-core operand form of an fp32 NHWC tensor: its [hi | lo] fp16 pair ("fp32_tc") or its fp16 rounding ("amp")"""
+    return x.half() if precision == "amp" else ops.split_pair(x)
 
 
 def weight_grad(x, dy, KH, KW, stride, pad, precision, x_pair=None, dy_pair=None):
     """dW [Cout,KH,KW,Cin] fp32 of a conv (or a linear as 1x1 over [1,1,M,K]): tensor cores (split precision) when the shape allows, else SIMT fp32.
     x / dy may be None when the corresponding pair is given and the shape takes the tensor-core path."""
     be = ops._be()
-    Cout = dy.shape[-1] if dy is not None else dy_pair.shape[-1] // 2
-    xs = tuple(x.shape) if x is not None else (*x_pair.shape[:-1], x_pair.shape[-1] // 2)
+    planes = 1 if precision == "amp" else 2
+    Cout = dy.shape[-1] if dy is not None else dy_pair.shape[-1] // planes
+    xs = tuple(x.shape) if x is not None else (*x_pair.shape[:-1], x_pair.shape[-1] // planes)
     ds = (*xs[:1], (xs[1] + 2 * pad - KH) // stride + 1, (xs[2] + 2 * pad - KW) // stride + 1, Cout)
     dev = (dy if dy is not None else dy_pair).device
     dwk = torch.empty((Cout, KH, KW, xs[-1]), dtype=torch.float32, device=dev)
     if wgrad_on_tensor_cores(xs, ds, KH, KW, stride, pad, precision):
-        xp = x_pair if x_pair is not None else ops.split_pair(x.contiguous())
-        dp = dy_pair if dy_pair is not None else ops.split_pair(dy.contiguous())
-        be.conv_wgrad_tc(xp, dp, KH, KW, stride, pad, dwk)
+        xp = x_pair if x_pair is not None else tc_operand(x.contiguous(), precision)
+        dp = dy_pair if dy_pair is not None else tc_operand(dy.contiguous(), precision)
+        (be.conv_wgrad_tc_f16 if precision == "amp" else be.conv_wgrad_tc)(xp, dp, KH, KW, stride, pad, dwk)
     else:
         be.conv_wgrad(x, dy, KH, KW, stride, pad, dwk)
     return dwk
@@ -250,8 +271,8 @@ class Conv2dFn(torch.autograd.Function):
         be = ops._be()
         dx = dw = db = None
         dyp = None
-        if keep_pair or (precision == "fp32_tc" and stride == 1 and ctx.needs_input_grad[0] and Cout % 32 == 0):
-            dyp = ops.split_pair(dy)  # shared by the data-gradient conv and the weight-gradient GEMM
+        if keep_pair or (precision in ("fp32_tc", "amp") and stride == 1 and ctx.needs_input_grad[0] and Cout % 32 == 0):
+            dyp = tc_operand(dy, precision)  # shared by the data-gradient conv and the weight-gradient GEMM
         if ctx.needs_input_grad[0]:
             # data gradient: correlation of (dilated) dy with the spatially flipped, in/out-transposed filter
             wt = w.flip(2, 3).permute(1, 2, 3, 0).contiguous()  # [Cin,KH,KW,Cout]
@@ -444,7 +465,7 @@ class LinearFn(torch.autograd.Function):
             be.add_act(y, None, g, ops.ACT_RELU, gm)
             g = gm
         g2 = g.reshape(1, 1, -1, N)
-        gp = ops.split_pair(g2) if (keep_pair or (precision == "fp32_tc" and N % 32 == 0 and g2.shape[2] >= 64 and ctx.needs_input_grad[0])) else None
+        gp = tc_operand(g2, precision) if (keep_pair or (precision in ("fp32_tc", "amp") and N % 32 == 0 and g2.shape[2] >= 64 and ctx.needs_input_grad[0])) else None
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = conv_any(g2, w.t().contiguous().reshape(K, 1, 1, N), None, 1, 0, precision, x_pair=gp).reshape(xshape)

@@ -134,6 +134,18 @@ class BoxHungarianMatcher(torch.nn.Module):
         return out
 
 
+def global_num_boxes(targets, dev) -> float:
+    """number of target boxes averaged over the data-parallel ranks, clamped at 1 (modelling.py:566-571).  One process: host arithmetic only.  Several ranks: a scalar
+    all-reduce and a read-back - a host synchronisation, which is why TrainStep calls this BEFORE the forward pass is enqueued (SetCriterion.num_boxes_hint) instead
+    of stalling the launch queue between the forward and the backward pass."""
+    n = float(sum(int(t.labels.shape[0]) for t in targets))
+    if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+        nb = torch.tensor([n], dtype=torch.float32, device=dev)
+        torch.distributed.all_reduce(nb)
+        n = float(nb.item()) / torch.distributed.get_world_size()
+    return max(n, 1.0)
+
+
 class SetCriterion(torch.nn.Module):
     """modelling.py:408-612 with losses ["vfl", "boxes"] (fai_detr/config.py:47) and deep supervision."""
 
@@ -144,6 +156,7 @@ class SetCriterion(torch.nn.Module):
             raise NotImplementedError(f"focoos_b200: criterion losses {list(losses)} not built (only ['vfl', 'boxes'])")
         self.num_classes, self.matcher, self.weight_dict, self.losses = num_classes, matcher, dict(weight_dict), list(losses)
         self.deep_supervision, self.focal_alpha, self.focal_gamma, self.eos_coef = deep_supervision, float(focal_alpha), float(focal_gamma), eos_coef
+        self.num_boxes_hint = None  # optional float: global_num_boxes(targets) computed by the caller ahead of the forward pass (consumed by the next forward)
         self.forced_match = None  # optional [L,T] int tensor: use these assignments instead of running the matcher (teacher forcing in parity tests)
         self.last_match = None    # the assignments used by the most recent forward, [L,T] int32 on the device
 
@@ -155,12 +168,8 @@ class SetCriterion(torch.nn.Module):
             raise RuntimeError("focoos_b200: the criterion runs on a CUDA device only (no CPU fallback)")
         dev = logits.device
         # number of target boxes averaged over the ranks (modelling.py:566-571)
-        nb = torch.tensor([float(sum(int(t.labels.shape[0]) for t in targets))], dtype=torch.float32, device=dev)
-        world = 1
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            torch.distributed.all_reduce(nb)
-            world = torch.distributed.get_world_size()
-        num_boxes = max(float(nb.item()) / world, 1.0)
+        num_boxes = self.num_boxes_hint if self.num_boxes_hint is not None else global_num_boxes(targets, dev)
+        self.num_boxes_hint = None
         tl, tb, toff, counts = _pack_targets(targets, dev)
         with torch.no_grad():
             if self.forced_match is not None:

@@ -14,7 +14,7 @@ namespace {
 
 constexpr int HD = 32, HDP = 33;
 
-__global__ void __launch_bounds__(256) attention_bwd_kernel(const float* __restrict__ q, int q_pitch, const float* __restrict__ k, int k_pitch,
+__global__ void __launch_bounds__(384) attention_bwd_kernel(const float* __restrict__ q, int q_pitch, const float* __restrict__ k, int k_pitch,
                                                             const float* __restrict__ v, int v_pitch, const float* __restrict__ o, int o_pitch,
                                                             const float* __restrict__ dout, int do_pitch, int Lq, int Lk, int heads, float scale,
                                                             float* __restrict__ dq, int dq_pitch, float* __restrict__ dk, int dk_pitch,
@@ -181,7 +181,10 @@ extern "C" int fb200_attention_bwd(const float* q, int q_pitch, const float* k, 
   FB_CHECK_ARG(smem <= 227 * 1024, "attention_bwd: Lq=%d Lk=%d exceed the shared-memory-resident design (Lq+Lk <= ~850)", Lq, Lk);
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
-  attention_bwd_kernel<<<B * heads, 256, smem, (cudaStream_t)stream>>>(q, q_pitch, k, k_pitch, v, v_pitch, o, o_pitch, dout, do_pitch, Lq, Lk, heads, scale, dq, dq_pitch,
+  // one thread per query (phase 1) / key (phase 2): with 256 threads the 300 decoder queries took two rounds, the second with 44 active threads
+  int threads = ((Lq > Lk ? Lq : Lk) + 31) / 32 * 32;
+  threads = threads < 128 ? 128 : (threads > 384 ? 384 : threads);
+  attention_bwd_kernel<<<B * heads, threads, smem, (cudaStream_t)stream>>>(q, q_pitch, k, k_pitch, v, v_pitch, o, o_pitch, dout, do_pitch, Lq, Lk, heads, scale, dq, dq_pitch,
                                                                         dk, dk_pitch, dv, dv_pitch);
   FB_CHECK_LAUNCH("attention_bwd");
   return FB200_OK;

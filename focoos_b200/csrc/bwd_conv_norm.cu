@@ -238,6 +238,75 @@ __global__ void __launch_bounds__(256) col_partial_kernel(const float* __restric
   }
 }
 
+// float4 version of col_partial_kernel for MODE 0 / 2 / 3 (the passes that read whole activation tensors): a thread owns FOUR consecutive channels of a row, a block covers a
+// chunk of CW = min(C, 128) channels x (1024 / CW) rows per step, four row steps unrolled -> 64 B (MODE 0 / 3) or 128-192 B (MODE 2) of loads in flight per thread.  The
+// scalar kernel keeps 16 B per thread in flight and ran the BatchNorm statistics passes at about a third of the HBM bandwidth (trip r02-14: bn_train_fwd 9.5 ms,
+// bn_train_bwd 15.4 ms per fine-tune step).  Requires C in {32, 64, 128} or C % 128 == 0, pitches % 4 == 0, 16-byte aligned bases (col_vec_ok).
+template <int MODE>
+__global__ void __launch_bounds__(256) col_partial4_kernel(const float* __restrict__ x, int x_pitch, int64_t R, int C, const float* __restrict__ mean,
+                                                           const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           const float* __restrict__ dy, int dy_pitch, const float* __restrict__ y, int y_pitch, int act,
+                                                           float* __restrict__ p0, float* __restrict__ p1) {
+  const int CW = C < 128 ? C : 128;           // channels of this block's chunk
+  const int TPR = CW / 4;                     // threads per row (8, 16 or 32)
+  const int RPB = 256 / TPR;                  // rows per block step
+  const int tc = threadIdx.x % TPR, tr = threadIdx.x / TPR;
+  const int c = blockIdx.x * CW + tc * 4;
+  float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+  float mu[4] = {0.f, 0.f, 0.f, 0.f}, rs[4] = {0.f, 0.f, 0.f, 0.f}, ga[4] = {0.f, 0.f, 0.f, 0.f}, be[4] = {0.f, 0.f, 0.f, 0.f}, pv[4] = {0.f, 0.f, 0.f, 0.f};
+  if (MODE == 2) { load4(mean + c, mu); load4(rstd + c, rs); load4(gamma + c, ga); load4(beta + c, be); }
+  if (MODE == 3) load4(x + c, pv);  // pivot row (see col_partial_kernel)
+  const bool has_y = (MODE == 2) && act != FB200_ACT_NONE && y != nullptr;
+  const int64_t rstep = (int64_t)gridDim.y * RPB;
+  int64_t r = (int64_t)blockIdx.y * RPB + tr;
+  auto accum = [&](const float (&xv)[4], const float (&gv)[4], const float (&yv)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (MODE == 0) s0[j] += xv[j];
+      else if (MODE == 3) { const float d = xv[j] - pv[j]; s0[j] += d; s1[j] += d * d; }
+      else {
+        const float xh = (xv[j] - mu[j]) * rs[j];
+        float g = gv[j];
+        if (act != FB200_ACT_NONE) {
+          const float z = xh * ga[j] + be[j];
+          g *= act_grad(act, z, has_y ? yv[j] : z);
+        }
+        s0[j] += g;
+        s1[j] += g * xh;
+      }
+    }
+  };
+  for (; r + 3 * rstep < R; r += 4 * rstep) {
+    float xv[4][4], gv[4][4], yv[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      load4(x + (r + u * rstep) * x_pitch + c, xv[u]);
+      if (MODE == 2) load4(dy + (r + u * rstep) * dy_pitch + c, gv[u]);
+      if (MODE == 2 && has_y) load4(y + (r + u * rstep) * y_pitch + c, yv[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) accum(xv[u], gv[u], yv[u]);
+  }
+  for (; r < R; r += rstep) {
+    float xv[4], gv[4] = {0.f, 0.f, 0.f, 0.f}, yv[4] = {0.f, 0.f, 0.f, 0.f};
+    load4(x + r * x_pitch + c, xv);
+    if (MODE == 2) load4(dy + r * dy_pitch + c, gv);
+    if (MODE == 2 && has_y) load4(y + r * y_pitch + c, yv);
+    accum(xv, gv, yv);
+  }
+  __shared__ float red0[32][129], red1[32][129];   // [row lane][channel of the chunk]
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { red0[tr][tc * 4 + j] = s0[j]; if (MODE >= 2) red1[tr][tc * 4 + j] = s1[j]; }
+  __syncthreads();
+  if ((int)threadIdx.x < CW) {
+    float a = 0.f, b = 0.f;
+    for (int k = 0; k < RPB; ++k) { a += red0[k][threadIdx.x]; if (MODE >= 2) b += red1[k][threadIdx.x]; }
+    const int co = blockIdx.x * CW + threadIdx.x;
+    p0[(int64_t)blockIdx.y * C + co] = a;
+    if (MODE >= 2) p1[(int64_t)blockIdx.y * C + co] = b;
+  }
+}
+
 // FIN 0: out0 = sum                       (colsum)
 // FIN 1: out0 = mean = sum / R            (BN pass 1)
 // FIN 2: out0 = rstd from sum of squared deviations; running stats update (BN pass 2)
@@ -306,6 +375,93 @@ __global__ void bn_apply_kernel(const float* __restrict__ x, int x_pitch, const 
       z.x += q.x; z.y += q.y; z.z += q.z; z.w += q.w;
     }
     *reinterpret_cast<float4*>(y + r * y_pitch + c) = make_float4(act_fwd(act, z.x), act_fwd(act, z.y), act_fwd(act, z.z), act_fwd(act, z.w));
+  }
+}
+
+// "column-fixed" variants of the two element-wise BatchNorm passes: the launch has a multiple of C/4 threads, so a thread keeps ONE group of four channels for its whole
+// grid-stride walk over the rows - the per-channel parameters are loaded once, the loop has no 64-bit division (the generic kernels spend ~150 instructions per float4 on
+// index arithmetic and parameter reloads and were instruction-bound at ~2.3 TB/s), and two rows are in flight per iteration.
+__global__ void __launch_bounds__(256) bn_apply_cf_kernel(const float* __restrict__ x, int x_pitch, const float* __restrict__ res, int res_pitch, int64_t R, int C,
+                                                          const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, int act, float* __restrict__ y, int y_pitch) {
+  const int cv = C / 4;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, T = (int64_t)gridDim.x * blockDim.x;
+  const int c = (int)(tid % cv) * 4;
+  const int64_t rstep = T / cv;
+  float mu[4], rs[4], ga[4], b[4];
+  load4(mean + c, mu); load4(rstd + c, rs); load4(gamma + c, ga); load4(beta + c, b);
+  auto one = [&](int64_t r, const float (&v)[4], const float (&q)[4]) {
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float z = (v[j] - mu[j]) * rs[j] * ga[j] + b[j];   // the arithmetic (and rounding order) of bn_apply_kernel
+      if (res) z += q[j];
+      o[j] = act_fwd(act, z);
+    }
+    store4(y + r * y_pitch + c, o);
+  };
+  int64_t r = tid / cv;
+  for (; r + rstep < R; r += 2 * rstep) {
+    float v0[4], v1[4], q0[4] = {0.f, 0.f, 0.f, 0.f}, q1[4] = {0.f, 0.f, 0.f, 0.f};
+    load4(x + r * x_pitch + c, v0);
+    load4(x + (r + rstep) * x_pitch + c, v1);
+    if (res) { load4(res + r * res_pitch + c, q0); load4(res + (r + rstep) * res_pitch + c, q1); }
+    one(r, v0, q0);
+    one(r + rstep, v1, q1);
+  }
+  if (r < R) {
+    float v0[4], q0[4] = {0.f, 0.f, 0.f, 0.f};
+    load4(x + r * x_pitch + c, v0);
+    if (res) load4(res + r * res_pitch + c, q0);
+    one(r, v0, q0);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_cf_kernel(const float* __restrict__ x, int x_pitch, const float* __restrict__ dy, int dy_pitch, const float* __restrict__ y,
+                                                              int y_pitch, int64_t R, int C, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ dgamma,
+                                                              const float* __restrict__ dbeta, int act, float inv_R, float* __restrict__ dx, int dx_pitch,
+                                                              float* __restrict__ dres, int dres_pitch) {
+  const int cv = C / 4;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, T = (int64_t)gridDim.x * blockDim.x;
+  const int c = (int)(tid % cv) * 4;
+  const int64_t rstep = T / cv;
+  float mu[4], rs[4], ga[4], be[4], dg[4], db[4];
+  load4(mean + c, mu); load4(rstd + c, rs); load4(gamma + c, ga); load4(beta + c, be); load4(dgamma + c, dg); load4(dbeta + c, db);
+  const bool has_y = act != FB200_ACT_NONE && y != nullptr;
+  auto one = [&](int64_t r, const float (&xv)[4], const float (&gv)[4], const float (&yv)[4]) {
+    float o[4], gr[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {   // the arithmetic of bn_bwd_apply4_kernel
+      const float xh = (xv[j] - mu[j]) * rs[j];
+      float g = gv[j];
+      if (act != FB200_ACT_NONE) {
+        const float z = xh * ga[j] + be[j];
+        g *= act_grad(act, z, y ? yv[j] : z);
+      }
+      gr[j] = g;
+      o[j] = ga[j] * rs[j] * (g - db[j] * inv_R - xh * dg[j] * inv_R);
+    }
+    store4(dx + r * dx_pitch + c, o);
+    if (dres) store4(dres + r * dres_pitch + c, gr);
+  };
+  int64_t r = tid / cv;
+  for (; r + rstep < R; r += 2 * rstep) {
+    float x0[4], x1[4], g0[4], g1[4], y0[4] = {0.f, 0.f, 0.f, 0.f}, y1[4] = {0.f, 0.f, 0.f, 0.f};
+    load4(x + r * x_pitch + c, x0);
+    load4(x + (r + rstep) * x_pitch + c, x1);
+    load4(dy + r * dy_pitch + c, g0);
+    load4(dy + (r + rstep) * dy_pitch + c, g1);
+    if (has_y) { load4(y + r * y_pitch + c, y0); load4(y + (r + rstep) * y_pitch + c, y1); }
+    one(r, x0, g0, y0);
+    one(r + rstep, x1, g1, y1);
+  }
+  if (r < R) {
+    float x0[4], g0[4], y0[4] = {0.f, 0.f, 0.f, 0.f};
+    load4(x + r * x_pitch + c, x0);
+    load4(dy + r * dy_pitch + c, g0);
+    if (has_y) load4(y + r * y_pitch + c, y0);
+    one(r, x0, g0, y0);
   }
 }
 
@@ -502,6 +658,8 @@ __global__ void resize_bwd_kernel(const float* __restrict__ dy, int dy_pitch, in
 // LayerNorm backward over s = x (+ res): one warp per row (C <= 1024, C % 32 == 0), row statistics recomputed;
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma.  Per-block partial sums of dy*xhat / dy for dgamma / dbeta.
 constexpr int LN_MAXV = 32;
+// MAXV = register slots per thread (C <= 32 * MAXV): the C = 256 LayerNorms of the decoder take the 8-slot instantiation (the 32-slot one keeps 128 array registers live)
+template <int MAXV>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ res, const float* __restrict__ gamma,
                                                             const float* __restrict__ dy, int64_t M, int C, float eps, float* __restrict__ dx,
                                                             float* __restrict__ pg, float* __restrict__ pb) {
@@ -509,14 +667,14 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nv = C / 32;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) ln_sm[i] = 0.f;
   __syncthreads();
-  float ag[LN_MAXV], ab[LN_MAXV];
+  float ag[MAXV], ab[MAXV];
 #pragma unroll
-  for (int k = 0; k < LN_MAXV; ++k) { ag[k] = 0.f; ab[k] = 0.f; }
+  for (int k = 0; k < MAXV; ++k) { ag[k] = 0.f; ab[k] = 0.f; }
   for (int64_t row = (int64_t)blockIdx.x * 8 + wid; row < M; row += (int64_t)gridDim.x * 8) {
-    float v[LN_MAXV], g[LN_MAXV];
+    float v[MAXV], g[MAXV];
     float sum = 0.f;
 #pragma unroll
-    for (int k = 0; k < LN_MAXV; ++k)
+    for (int k = 0; k < MAXV; ++k)
       if (k < nv) {
         const int c = k * 32 + lane;
         v[k] = x[row * C + c] + (res ? res[row * C + c] : 0.f);
@@ -525,12 +683,12 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     const float mean = warp_sum(sum) / (float)C;
     float sq = 0.f;
 #pragma unroll
-    for (int k = 0; k < LN_MAXV; ++k)
+    for (int k = 0; k < MAXV; ++k)
       if (k < nv) { const float d = v[k] - mean; sq += d * d; }
     const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
     float sg = 0.f, sgx = 0.f;
 #pragma unroll
-    for (int k = 0; k < LN_MAXV; ++k)
+    for (int k = 0; k < MAXV; ++k)
       if (k < nv) {
         const int c = k * 32 + lane;
         const float d = dy[row * C + c];
@@ -544,14 +702,14 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     sg = warp_sum(sg) / (float)C;
     sgx = warp_sum(sgx) / (float)C;
 #pragma unroll
-    for (int k = 0; k < LN_MAXV; ++k)
+    for (int k = 0; k < MAXV; ++k)
       if (k < nv) dx[row * C + k * 32 + lane] = rstd * (g[k] - sg - v[k] * sgx);
   }
   // deterministic in-block combine: warps add their accumulators one after the other
   for (int w = 0; w < 8; ++w) {
     if (wid == w) {
 #pragma unroll
-      for (int k = 0; k < LN_MAXV; ++k)
+      for (int k = 0; k < MAXV; ++k)
         if (k < nv) { ln_sm[k * 32 + lane] += ag[k]; ln_sm[C + k * 32 + lane] += ab[k]; }
     }
     __syncthreads();
@@ -615,14 +773,55 @@ extern "C" int64_t fb200_col_workspace_bytes(int C) { return (int64_t)(2 * CR_RO
 
 static inline dim3 col_grid(int C, int64_t R) { return dim3((unsigned)cdiv(C, 32), (unsigned)std::min<int64_t>(CR_ROWS, cdiv(R, 8))); }
 
+static inline bool col_vec_ok(int C, const void* x, int x_pitch, const void* dy, int dy_pitch, const void* y, int y_pitch) {
+  static int on = -1;  // FB200_COL_VEC=0: the scalar kernels (A/B)
+  if (on < 0) { const char* e = getenv("FB200_COL_VEC"); on = e ? atoi(e) : 1; }
+  if (!on || !(C == 32 || C == 64 || C == 128 || (C > 128 && C % 128 == 0))) return false;
+  if (x_pitch % 4 || (dy && dy_pitch % 4) || (y && y_pitch % 4)) return false;
+  return ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+}
+// grid of the column-fixed element-wise kernels: a multiple of C/4 threads (0 = use the generic kernel)
+static inline unsigned cf_grid(int64_t R, int C) {
+  static int on = -1;  // FB200_BN_CF=0: the generic kernels (A/B)
+  if (on < 0) { const char* e = getenv("FB200_BN_CF"); on = e ? atoi(e) : 1; }
+  const int cv = C / 4;
+  if (!on || C % 4 || cv <= 0) return 0;
+  int64_t blocks = std::min<int64_t>(cdiv(R * cv, 256), 148 * 16);
+  if (cv <= 256) { if (256 % cv) return 0; }           // every block holds whole rows' worth of column groups
+  else { if (cv % 256) return 0; const int64_t m = cv / 256; blocks = blocks / m * m; }
+  return (unsigned)std::max<int64_t>(blocks, cv > 256 ? cv / 256 : 1);
+}
+static void bn_apply_launch(const float* x, int x_pitch, const float* res, int res_pitch, int64_t R, int C, const float* mean, const float* rstd, const float* gamma,
+                            const float* beta, int act, float* y, int y_pitch, cudaStream_t st) {
+  const unsigned g = cf_grid(R, C);
+  const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 && x_pitch % 4 == 0 && y_pitch % 4 == 0 &&
+                  (!res || res_pitch % 4 == 0);
+  if (g && al) bn_apply_cf_kernel<<<g, 256, 0, st>>>(x, x_pitch, res, res_pitch, R, C, mean, rstd, gamma, beta, act, y, y_pitch);
+  else bn_apply_kernel<<<grid_for(R * (C / 4)), 256, 0, st>>>(x, x_pitch, res, res_pitch, R, C, mean, rstd, gamma, beta, act, y, y_pitch);
+}
+
+// one column pass (MODE 0 colsum / 2 BN backward sums / 3 shifted moments) -> partials p0 / p1 [parts][C]; returns the number of parts
+template <int MODE>
+static int col_partial_launch(const float* x, int x_pitch, int64_t R, int C, const float* mean, const float* rstd, const float* gamma, const float* beta, const float* dy,
+                              int dy_pitch, const float* y, int y_pitch, int act, float* p0, float* p1, cudaStream_t st) {
+  if (col_vec_ok(C, x, x_pitch, dy, dy_pitch, y, y_pitch)) {
+    const int CW = C < 128 ? C : 128, RPB = 256 / (CW / 4);
+    const dim3 g((unsigned)(C / CW), (unsigned)std::min<int64_t>(CR_ROWS, cdiv(R, (int64_t)RPB)));
+    col_partial4_kernel<MODE><<<g, 256, 0, st>>>(x, x_pitch, R, C, mean, rstd, gamma, beta, dy, dy_pitch, y, y_pitch, act, p0, p1);
+    return (int)g.y;
+  }
+  const dim3 g = col_grid(C, R);
+  col_partial_kernel<MODE><<<g, 256, 0, st>>>(x, x_pitch, R, C, mean, rstd, gamma, beta, dy, dy_pitch, y, y_pitch, act, p0, p1);
+  return (int)g.y;
+}
+
 extern "C" int fb200_colsum(const float* x, int64_t R, int C, int pitch, float* out, int accumulate, void* workspace, void* stream) {
   FB_CHECK_ARG(x && out && workspace && R > 0 && C > 0, "colsum: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   float* p0 = reinterpret_cast<float*>(workspace);
-  const dim3 g = col_grid(C, R);
-  col_partial_kernel<0><<<g, 256, 0, st>>>(x, pitch, R, C, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, 0, p0, nullptr);
+  const int parts = col_partial_launch<0>(x, pitch, R, C, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, 0, p0, nullptr, st);
   FB_CHECK_LAUNCH("colsum");
-  col_finalize_kernel<0><<<cdiv(C, 128), 128, 0, st>>>(p0, nullptr, g.y, C, (double)R, 0.f, 0.f, nullptr, nullptr, nullptr, out, nullptr, accumulate);
+  col_finalize_kernel<0><<<cdiv(C, 128), 128, 0, st>>>(p0, nullptr, parts, C, (double)R, 0.f, 0.f, nullptr, nullptr, nullptr, out, nullptr, accumulate);
   FB_CHECK_LAUNCH("colsum(finalize)");
   return FB200_OK;
 }
@@ -634,12 +833,11 @@ extern "C" int fb200_bn_train_fwd(const float* x, int x_pitch, int64_t R, int C,
   FB_CHECK_ARG(act == FB200_ACT_NONE || act == FB200_ACT_RELU || (act == FB200_ACT_SILU && !res), "bn_train_fwd: act must be none/relu (or silu without residual)");
   cudaStream_t st = (cudaStream_t)stream;
   float* p0 = reinterpret_cast<float*>(workspace);
-  const dim3 g = col_grid(C, R);
   float* p1 = p0 + (int64_t)CR_ROWS * C;
   // ONE pass over x for both moments (sums shifted by the first row, finalised in double); `x` itself serves as the pivot row for the finaliser
-  col_partial_kernel<3><<<g, 256, 0, st>>>(x, x_pitch, R, C, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, 0, p0, p1);
-  col_finalize_kernel<4><<<cdiv(C, 128), 128, 0, st>>>(p0, p1, g.y, C, (double)R, eps, momentum, x, running_mean, running_var, save_mean, save_rstd, 0);
-  bn_apply_kernel<<<grid_for(R * (C / 4)), 256, 0, st>>>(x, x_pitch, res, res_pitch, R, C, save_mean, save_rstd, gamma, beta, act, y, y_pitch);
+  const int parts = col_partial_launch<3>(x, x_pitch, R, C, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, 0, p0, p1, st);
+  col_finalize_kernel<4><<<cdiv(C, 128), 128, 0, st>>>(p0, p1, parts, C, (double)R, eps, momentum, x, running_mean, running_var, save_mean, save_rstd, 0);
+  bn_apply_launch(x, x_pitch, res, res_pitch, R, C, save_mean, save_rstd, gamma, beta, act, y, y_pitch, st);
   FB_CHECK_LAUNCH("bn_train_fwd");
   return FB200_OK;
 }
@@ -652,15 +850,17 @@ extern "C" int fb200_bn_train_bwd(const float* x, int x_pitch, const float* dy, 
   cudaStream_t st = (cudaStream_t)stream;
   float* p0 = reinterpret_cast<float*>(workspace);
   float* p1 = p0 + (int64_t)CR_ROWS * C;
-  const dim3 g = col_grid(C, R);
   float* f0 = p1 + (int64_t)CR_ROWS * C;  // this step's dbeta / dgamma: needed by dx before they may be accumulated into the caller's buffers
   float* f1 = f0 + C;
-  col_partial_kernel<2><<<g, 256, 0, st>>>(x, x_pitch, R, C, save_mean, save_rstd, gamma, beta, dy, dy_pitch, y, y_pitch, act, p0, p1);
-  col_finalize_kernel<3><<<cdiv(C, 128), 128, 0, st>>>(p0, p1, g.y, C, (double)R, 0.f, 0.f, nullptr, nullptr, nullptr, f0, f1, 0);
+  const int parts = col_partial_launch<2>(x, x_pitch, R, C, save_mean, save_rstd, gamma, beta, dy, dy_pitch, y, y_pitch, act, p0, p1, st);
+  col_finalize_kernel<3><<<cdiv(C, 128), 128, 0, st>>>(p0, p1, parts, C, (double)R, 0.f, 0.f, nullptr, nullptr, nullptr, f0, f1, 0);
   const bool v4 = C % 4 == 0 && x_pitch % 4 == 0 && dy_pitch % 4 == 0 && dx_pitch % 4 == 0 && (!y || y_pitch % 4 == 0) && (!dres || dres_pitch % 4 == 0) &&
                   ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(y) |
                     reinterpret_cast<uintptr_t>(dres)) & 15) == 0;
-  if (v4)
+  if (v4 && cf_grid(R, C))
+    bn_bwd_apply_cf_kernel<<<cf_grid(R, C), 256, 0, st>>>(x, x_pitch, dy, dy_pitch, y, y_pitch, R, C, save_mean, save_rstd, gamma, beta, f1, f0, act, (float)(1.0 / (double)R),
+                                                         dx, dx_pitch, dres, dres_pitch);
+  else if (v4)
     bn_bwd_apply4_kernel<<<grid_for(R * (C / 4)), 256, 0, st>>>(x, x_pitch, dy, dy_pitch, y, y_pitch, R, C, save_mean, save_rstd, gamma, beta, f1, f0, act,
                                                                (float)(1.0 / (double)R), dx, dx_pitch, dres, dres_pitch);
   else
@@ -676,10 +876,9 @@ extern "C" int fb200_bn_stats(const float* x, int x_pitch, int64_t R, int C, flo
   FB_CHECK_ARG(x && mean && var_biased && workspace && R > 0 && C % 4 == 0, "bn_stats: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   float* p0 = reinterpret_cast<float*>(workspace);
-  const dim3 g = col_grid(C, R);
   float* p1 = p0 + (int64_t)CR_ROWS * C;
-  col_partial_kernel<3><<<g, 256, 0, st>>>(x, x_pitch, R, C, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, 0, p0, p1);
-  col_finalize_kernel<5><<<cdiv(C, 128), 128, 0, st>>>(p0, p1, g.y, C, (double)R, 0.f, 0.f, x, nullptr, nullptr, mean, var_biased, 0);
+  const int parts = col_partial_launch<3>(x, x_pitch, R, C, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, 0, p0, p1, st);
+  col_finalize_kernel<5><<<cdiv(C, 128), 128, 0, st>>>(p0, p1, parts, C, (double)R, 0.f, 0.f, x, nullptr, nullptr, mean, var_biased, 0);
   FB_CHECK_LAUNCH("bn_stats");
   return FB200_OK;
 }
@@ -688,7 +887,7 @@ extern "C" int fb200_bn_apply(const float* x, int x_pitch, int64_t R, int C, con
                               const float* res, int res_pitch, int act, float* y, int y_pitch, void* stream) {
   FB_CHECK_ARG(x && mean && rstd && gamma && beta && y && R > 0 && C % 4 == 0, "bn_apply: bad arguments");
   FB_CHECK_ARG(act == FB200_ACT_NONE || act == FB200_ACT_RELU || (act == FB200_ACT_SILU && !res), "bn_apply: act must be none/relu (or silu without residual)");
-  bn_apply_kernel<<<grid_for(R * (C / 4)), 256, 0, (cudaStream_t)stream>>>(x, x_pitch, res, res_pitch, R, C, mean, rstd, gamma, beta, act, y, y_pitch);
+  bn_apply_launch(x, x_pitch, res, res_pitch, R, C, mean, rstd, gamma, beta, act, y, y_pitch, (cudaStream_t)stream);
   FB_CHECK_LAUNCH("bn_apply");
   return FB200_OK;
 }
@@ -699,9 +898,8 @@ extern "C" int fb200_bn_bwd_reduce(const float* x, int x_pitch, const float* dy,
   cudaStream_t st = (cudaStream_t)stream;
   float* p0 = reinterpret_cast<float*>(workspace);
   float* p1 = p0 + (int64_t)CR_ROWS * C;
-  const dim3 g = col_grid(C, R);
-  col_partial_kernel<2><<<g, 256, 0, st>>>(x, x_pitch, R, C, mean, rstd, gamma, beta, dy, dy_pitch, y, y_pitch, act, p0, p1);
-  col_finalize_kernel<3><<<cdiv(C, 128), 128, 0, st>>>(p0, p1, g.y, C, (double)R, 0.f, 0.f, nullptr, nullptr, nullptr, sum_dy, sum_dy_xhat, 0);
+  const int parts = col_partial_launch<2>(x, x_pitch, R, C, mean, rstd, gamma, beta, dy, dy_pitch, y, y_pitch, act, p0, p1, st);
+  col_finalize_kernel<3><<<cdiv(C, 128), 128, 0, st>>>(p0, p1, parts, C, (double)R, 0.f, 0.f, nullptr, nullptr, nullptr, sum_dy, sum_dy_xhat, 0);
   FB_CHECK_LAUNCH("bn_bwd_reduce");
   return FB200_OK;
 }
@@ -714,7 +912,10 @@ extern "C" int fb200_bn_bwd_apply(const float* x, int x_pitch, const float* dy, 
   const bool v4 = C % 4 == 0 && x_pitch % 4 == 0 && dy_pitch % 4 == 0 && dx_pitch % 4 == 0 && (!y || y_pitch % 4 == 0) && (!dres || dres_pitch % 4 == 0) &&
                   ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(y) |
                     reinterpret_cast<uintptr_t>(dres)) & 15) == 0;
-  if (v4)
+  if (v4 && cf_grid(R, C))
+    bn_bwd_apply_cf_kernel<<<cf_grid(R, C), 256, 0, (cudaStream_t)stream>>>(x, x_pitch, dy, dy_pitch, y, y_pitch, R, C, mean, rstd, gamma, beta, sum_dy_xhat, sum_dy, act,
+                                                                           inv_count, dx, dx_pitch, dres, dres_pitch);
+  else if (v4)
     bn_bwd_apply4_kernel<<<grid_for(R * (C / 4)), 256, 0, (cudaStream_t)stream>>>(x, x_pitch, dy, dy_pitch, y, y_pitch, R, C, mean, rstd, gamma, beta, sum_dy_xhat, sum_dy, act,
                                                                                   inv_count, dx, dx_pitch, dres, dres_pitch);
   else
@@ -764,7 +965,8 @@ extern "C" int fb200_layernorm_bwd(const float* x, const float* res, const float
   const int nblk = (int)std::min<int64_t>(CR_ROWS, cdiv(M, 8));
   float* pg = reinterpret_cast<float*>(workspace);
   float* pb = pg + (int64_t)CR_ROWS * C;
-  layernorm_bwd_kernel<<<nblk, 256, 2 * C * sizeof(float), st>>>(x, res, gamma, dy, M, C, eps, dx, pg, pb);
+  if (C <= 256) layernorm_bwd_kernel<8><<<nblk, 256, 2 * C * sizeof(float), st>>>(x, res, gamma, dy, M, C, eps, dx, pg, pb);
+  else layernorm_bwd_kernel<LN_MAXV><<<nblk, 256, 2 * C * sizeof(float), st>>>(x, res, gamma, dy, M, C, eps, dx, pg, pb);
   FB_CHECK_LAUNCH("layernorm_bwd");
   col_finalize_kernel<3><<<cdiv(C, 128), 128, 0, st>>>(pb, pg, nblk, C, 1.0, 0.f, 0.f, nullptr, nullptr, nullptr, dbeta, dgamma, accumulate);
   FB_CHECK_LAUNCH("layernorm_bwd(finalize)");

@@ -35,6 +35,7 @@ struct WParams {
   int pt_total, pt_per_split;          // pixel tiles
   int total_items;
   float* part;                         // [splits][Cout][KH*KW][Cin]
+  int single;                          // 1: plain fp16 operands, ONE product per chunk (the reference's fp16-autocast numerics class); 0: [hi | lo] pairs, three products
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -154,11 +155,11 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const __grid_constant_
           const int img = pt / tiles_per_img, rem = pt - img * tiles_per_img;
           const int h0 = (rem / p.tiles_w) * p.BH, w0 = (rem % p.tiles_w) * p.BW;
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)STAGE_BYTES);
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(p.single ? STAGE_BYTES / 2 : STAGE_BYTES));
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BOXES * BOX_BYTES;
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {  // 0 = hi, 1 = lo (channel offset C in the pair tensor)
+          const int halves = p.single ? 1 : 2;
+          for (int half = 0; half < halves; ++half) {  // 0 = hi, 1 = lo (channel offset C in the pair tensor)
 #pragma unroll
             for (int j = 0; j < BLOCK_M / 64; ++j)
               tma_load_4d(&tmap_dy, &full_bar[stage], sa + half * A_HALF + j * BOX_BYTES, half * p.Cout + m0 + j * 64, w0, h0, img);
@@ -195,8 +196,10 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const __grid_constant_
             const uint64_t adv = (uint64_t)(k * 128);
             umma_f16(tmem_d, a_hi + adv, b_hi + adv, idesc, first ? 0u : 1u);
             first = false;
-            umma_f16(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
-            umma_f16(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
+            if (!p.single) {
+              umma_f16(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
+              umma_f16(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
+            }
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -336,9 +339,8 @@ extern "C" int64_t fb200_conv_wgrad_tc_workspace_bytes(int B, int Ho, int Wo, in
   return (int64_t)pl.splits * Cout * KH * KW * Cin * 4 + 16;
 }
 
-/* x_pair [B,H,W,2*Cin] fp16, dy_pair [B,Ho,Wo,2*Cout] fp16 (both from fb200_split_f32_pair, dense) -> dw [Cout][KH][KW][Cin] fp32 */
-extern "C" int fb200_conv_wgrad_tc(const void* x_pair, int B, int H, int W, int Cin, const void* dy_pair, int Cout, int KH, int KW, int stride, int pad, float* dw,
-                                   int accumulate, void* workspace, void* stream) {
+static int wgrad_tc_launch(const void* x_pair, int B, int H, int W, int Cin, const void* dy_pair, int Cout, int KH, int KW, int stride, int pad, float* dw,
+                           int accumulate, void* workspace, void* stream, int single) {
   FB_CHECK_ARG(x_pair && dy_pair && dw && workspace, "conv_wgrad_tc: null pointer");
   const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
   FB_CHECK_ARG(fb200_conv_wgrad_tc_supported(B, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad), "conv_wgrad_tc: unsupported shape (B=%d H=%d W=%d Cin=%d Cout=%d k=%d s=%d)", B, H, W,
@@ -349,9 +351,10 @@ extern "C" int fb200_conv_wgrad_tc(const void* x_pair, int B, int H, int W, int 
   const int taps = KH * KW;
   const Plan pl = make_plan(B, Ho, Wo, Cin, Cout, taps);
   CUtensorMap tdy, tx;
-  int rc = encode_pair(&tdy, dy_pair, 2 * Cout, Wo, Ho, B, pl.BW, pl.BH, "dY");
+  const int planes = single ? 1 : 2;  // channels per pixel of the operand tensors: C (plain fp16) or 2C ([hi | lo] pair)
+  int rc = encode_pair(&tdy, dy_pair, planes * Cout, Wo, Ho, B, pl.BW, pl.BH, "dY");
   if (rc) return rc;
-  rc = encode_pair(&tx, x_pair, 2 * Cin, W, H, B, pl.BW, pl.BH, "X", stride);
+  rc = encode_pair(&tx, x_pair, planes * Cin, W, H, B, pl.BW, pl.BH, "X", stride);
   if (rc) return rc;
   WParams p;
   p.Cout = Cout; p.Cin = Cin; p.KH = KH; p.KW = KW; p.pad = pad; p.stride = stride;
@@ -362,6 +365,7 @@ extern "C" int fb200_conv_wgrad_tc(const void* x_pair, int B, int H, int W, int 
   FB_CHECK_ARG(items <= 0x7fffffffLL, "conv_wgrad_tc: too many work items");
   p.total_items = (int)items;
   p.part = reinterpret_cast<float*>(workspace);
+  p.single = single;
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = (unsigned)(items < num_sms() ? items : num_sms());
   if (pl.block_n == 128) {
@@ -379,4 +383,17 @@ extern "C" int fb200_conv_wgrad_tc(const void* x_pair, int B, int H, int W, int 
   wgrad_reduce_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(p.part, pl.splits, n, dw, accumulate);
   FB_CHECK_LAUNCH("conv_wgrad_tc(reduce)");
   return FB200_OK;
+}
+
+/* x_pair [B,H,W,2*Cin] fp16, dy_pair [B,Ho,Wo,2*Cout] fp16 (both from fb200_split_f32_pair, dense) -> dw [Cout][KH][KW][Cin] fp32 */
+extern "C" int fb200_conv_wgrad_tc(const void* x_pair, int B, int H, int W, int Cin, const void* dy_pair, int Cout, int KH, int KW, int stride, int pad, float* dw,
+                                   int accumulate, void* workspace, void* stream) {
+  return wgrad_tc_launch(x_pair, B, H, W, Cin, dy_pair, Cout, KH, KW, stride, pad, dw, accumulate, workspace, stream, 0);
+}
+
+/* the same GEMM on PLAIN fp16 operands (x [B,H,W,Cin], dy [B,Ho,Wo,Cout], dense), one tensor-core product, fp32 accumulation and output: the arithmetic of
+   the reference's training under torch.autocast(fp16) (trainer/trainer.py:735), used by the "amp" training precision */
+extern "C" int fb200_conv_wgrad_tc_f16(const void* x, int B, int H, int W, int Cin, const void* dy, int Cout, int KH, int KW, int stride, int pad, float* dw,
+                                       int accumulate, void* workspace, void* stream) {
+  return wgrad_tc_launch(x, B, H, W, Cin, dy, Cout, KH, KW, stride, pad, dw, accumulate, workspace, stream, 1);
 }

@@ -843,6 +843,7 @@ class FAIDetr(nn.Module):
         self.precision = precision
         self.algo = ops.ALGO_AUTO
         self._engine: Optional[DetrEngine] = None
+        self.train_precision = None  # training arithmetic: None (follow `precision`), "fp32", "fp32_tc" or "amp" (see train_graph)
         self.sync_bn = False    # training: BatchNorm statistics over all data-parallel ranks (torch.nn.SyncBatchNorm, trainer/trainer.py:334); set by the trainer
         self.freeze_bn = False  # training: every BatchNorm as FrozenBatchNorm2d (TrainerArgs.freeze_bn, trainer/trainer.py:330)
         from .train_step import freeze_backbone_at, freeze_backbone_norm
@@ -888,7 +889,9 @@ class FAIDetr(nn.Module):
     def train_graph(self):
         """training-mode forward built from the autograd ops (fai_detr_train.py); fp32 storage, tensor-core split products by default"""
         from .fai_detr_train import DetrTrainGraph
-        prec = "fp32" if self.precision == "fp32" else "fp32_tc"
+        # train_precision: "amp" = one tensor-core product on fp16-rounded operands, fp32 accumulation / storage (the reference's torch.autocast(fp16) arithmetic,
+        # trainer/trainer.py:735; the trainer sets it from TrainerArgs.amp_enabled); None = follow the inference precision (fp32-accurate products / CUDA-core fp32)
+        prec = getattr(self, "train_precision", None) or ("fp32" if self.precision == "fp32" else "fp32_tc")
         if getattr(self, "_train_graph", None) is None or self._train_graph.prec != prec:
             self._train_graph = DetrTrainGraph(self, prec)
         return self._train_graph

@@ -32,11 +32,17 @@ def _inverse_sigmoid(x, eps=1e-5):  # nn/layers/functional.py:4-6
 
 class DetrTrainGraph:
     def __init__(self, model, precision: str = "fp32_tc"):
-        assert precision in ("fp32", "fp32_tc")
+        assert precision in ("fp32", "fp32_tc", "amp")
         self.m, self.prec = model, precision
         self._const = {}
         self.taps = None  # optional dict: named intermediate tensors (detached) for parity debugging
         self.forced_topk = None  # optional [B, num_queries] int tensor: use this query selection instead of the top-k (teacher forcing in parity tests)
+
+    @property
+    def last_topk(self):
+        """query selection of the last forward, on the host (parity tests)"""
+        t = getattr(self, "_last_topk_dev", None)
+        return None if t is None else t.cpu()
 
     def _tap(self, name, t):
         if self.taps is not None:
@@ -94,7 +100,7 @@ class DetrTrainGraph:
         q = A.linear(q_in, w[:d], b[:d], precision=self.prec)
         k = A.linear(k_in, w[d:2 * d], b[d:2 * d], precision=self.prec)
         v = A.linear(v_in, w[2 * d:], b[2 * d:], precision=self.prec)
-        o = A.AttentionFn.apply(q, k, v, h, 1.0 / math.sqrt(d // h), self.prec == "fp32_tc")
+        o = A.AttentionFn.apply(q, k, v, h, 1.0 / math.sqrt(d // h), self.prec in ("fp32_tc", "amp"))
         return A.linear(o, attn.out_proj.weight, attn.out_proj.bias, precision=self.prec)
 
     def mlp(self, x, mlp):
@@ -206,7 +212,7 @@ class DetrTrainGraph:
                "aux_outputs": [{"pred_logits": a, "pred_boxes": b} for a, b in zip(dec_logits[:-1], dec_boxes[:-1])]}
         res["aux_outputs"].append({"pred_logits": enc_topk_logits, "pred_boxes": enc_topk_bboxes})
         res["_topk_ind"] = topk_ind
-        self.last_topk = topk_ind.detach().cpu()
+        self._last_topk_dev = topk_ind.detach()  # read back lazily (last_topk): a .cpu() here would stall the launch queue in every training step
         return res
 
     def forward(self, images) -> Dict:

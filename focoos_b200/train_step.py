@@ -314,6 +314,13 @@ class TrainStep:
 
     def __call__(self, images, targets, lr_factor: float = 1.0) -> Dict[str, torch.Tensor]:
         self.opt.zero_grad()
+        crit = getattr(self.model, "criterion", None)
+        if callable(crit) and targets and hasattr(targets[0], "labels"):
+            # the rank-averaged box count needs a host read-back when several ranks train: do it before anything of this step is enqueued
+            from .criterion import global_num_boxes
+            c = crit()
+            if hasattr(c, "num_boxes_hint"):
+                c.num_boxes_hint = global_num_boxes(targets, images.device)
         loss_dict = self.model(images, targets).loss
         if isinstance(loss_dict, torch.Tensor):
             losses, loss_dict = loss_dict, {"total_loss": loss_dict}

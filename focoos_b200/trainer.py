@@ -121,6 +121,10 @@ def _train_worker(rank: int, world: int, fm, args: TrainerArgs, data_train, data
         model.freeze_bn = True
     if hasattr(model, "sync_bn"):
         model.sync_bn = bool(args.sync_bn) and world > 1
+    if hasattr(model, "train_precision") and model.train_precision is None and getattr(model, "precision", "fp32") != "fp32" and dev.type == "cuda":
+        # TrainerArgs.amp_enabled (ports.py:1029, default True): the reference's iteration runs under torch.autocast(fp16) + GradScaler -> one fp16 tensor-core product
+        # per conv/linear here; amp_enabled=False: fp32-accurate (three-product) arithmetic
+        model.train_precision = "amp" if args.amp_enabled else "fp32_tc"
     opt = FlatAdamW(get_optimizer_params(model, args.learning_rate, args.weight_decay, args.weight_decay_norm, args.weight_decay_embed, args.backbone_multiplier,
                                          args.decoder_multiplier, args.head_multiplier), clip_gradients=args.clip_gradients, amp=args.amp_enabled, world_size=world)
     opt.track_unused_parameters()

@@ -333,6 +333,10 @@ int fb200_conv_wgrad_tc_supported(int B, int H, int W, int Cin, int Ho, int Wo, 
 int64_t fb200_conv_wgrad_tc_workspace_bytes(int B, int Ho, int Wo, int Cin, int Cout, int KH, int KW);
 int fb200_conv_wgrad_tc(const void* x_pair, int B, int H, int W, int Cin, const void* dy_pair, int Cout, int KH, int KW, int stride, int pad, float* dw,
                         int accumulate, void* workspace, void* stream);
+/* The same tensor-core weight gradient on PLAIN fp16 operands x [B,H,W,Cin], dy [B,Ho,Wo,Cout] (dense), one product per chunk, fp32 accumulation and fp32 dw: the arithmetic of
+ * the reference's fine-tuning under torch.autocast(fp16) + GradScaler (trainer/trainer.py:645,735-771); used by the "amp" training precision. */
+int fb200_conv_wgrad_tc_f16(const void* x, int B, int H, int W, int Cin, const void* dy, int Cout, int KH, int KW, int stride, int pad, float* dw,
+                            int accumulate, void* workspace, void* stream);
 /* zero-dilation of dy for the stride-2 data gradient (dx = conv(dilate(dy), flipped transposed weights) through fb200_conv2d) */
 int fb200_dilate2(const float* dy, int B, int Ho, int Wo, int C, int Hd, int Wd, float* out, void* stream);
 /* column sums of [R,C] (bias gradients); workspace of fb200_col_workspace_bytes(C) also serves the BN / LayerNorm calls below */

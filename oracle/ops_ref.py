@@ -513,6 +513,13 @@ def _rb_conv_wgrad_tc(self, x_pair, dy_pair, KH, KW, stride, pad, dw):
     dw.copy_((g(xh, dh) + g(xl, dh) + g(xh, dl)).permute(0, 2, 3, 1))
 
 
+def _rb_conv_wgrad_tc_f16(self, x16, dy16, KH, KW, stride, pad, dw):
+    """fb200_conv_wgrad_tc_f16: the weight gradient of the fp16-rounded operands, fp32 accumulation (the "amp" training precision)"""
+    Cin, Cout = x16.shape[-1], dy16.shape[-1]
+    g = torch.nn.grad.conv2d_weight(_nchw(x16.float()).contiguous(), (Cout, Cin, KH, KW), _nchw(dy16.float()).contiguous(), stride=stride, padding=pad)
+    dw.copy_(g.permute(0, 2, 3, 1))
+
+
 def _rb_dilate2(self, dy, out):
     out.zero_()
     out[:, : 2 * dy.shape[1] : 2, : 2 * dy.shape[2] : 2] = dy
@@ -677,7 +684,7 @@ def _rb_msda_bwd(self, value, oa, ref, do, shapes, P, heads, dvalue, doa):
     doa.copy_(go)
 
 
-for _n, _f in (("conv_wgrad", _rb_conv_wgrad), ("conv_wgrad_tc_supported", _rb_conv_wgrad_tc_supported), ("conv_wgrad_tc", _rb_conv_wgrad_tc), ("dilate2", _rb_dilate2), ("colsum", _rb_colsum), ("bn_train_fwd", _rb_bn_train_fwd), ("bn_train_bwd", _rb_bn_train_bwd),
+for _n, _f in (("conv_wgrad", _rb_conv_wgrad), ("conv_wgrad_tc_supported", _rb_conv_wgrad_tc_supported), ("conv_wgrad_tc", _rb_conv_wgrad_tc), ("conv_wgrad_tc_f16", _rb_conv_wgrad_tc_f16), ("dilate2", _rb_dilate2), ("colsum", _rb_colsum), ("bn_train_fwd", _rb_bn_train_fwd), ("bn_train_bwd", _rb_bn_train_bwd),
                ("bn_stats", _rb_bn_stats), ("bn_apply", _rb_bn_apply), ("bn_bwd_reduce", _rb_bn_bwd_reduce), ("bn_bwd_apply", _rb_bn_bwd_apply),
                ("add_act", _rb_add_act), ("maxpool_bwd", _rb_maxpool_bwd), ("avgpool_bwd", _rb_avgpool_bwd), ("resize_bwd", _rb_resize_bwd),
                ("layernorm_bwd", _rb_layernorm_bwd), ("attention_bwd", _rb_attention_bwd), ("msda_bwd", _rb_msda_bwd)):

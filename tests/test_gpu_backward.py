@@ -223,6 +223,41 @@ def test_stride2_weight_gradient_on_tensor_cores(B, H, W, Cin, Cout):
     close(got, ref.float(), "wgrad tc stride 2", 2e-5)
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,stride", [(2, 40, 40, 256, 256, 3, 1), (1, 1, 600, 256, 1024, 1, 1), (2, 23, 37, 128, 64, 3, 1), (2, 31, 45, 64, 256, 3, 2)])
+def test_weight_gradient_single_product(B, H, W, Cin, Cout, k, stride):
+    """"amp" training precision: ONE tensor-core product on fp16-rounded operands (fb200_conv_wgrad_tc_f16), fp32 accumulation: exact (to fp32 summation order)
+    for operands that ARE fp16 values, and within the fp16 operand rounding (2^-11 relative per element) of the fp32 gradient otherwise."""
+    pad = (k - 1) // 2
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    x, dy = rnd((B, H, W, Cin), 1), rnd((B, Ho, Wo, Cout), 2)
+    xh, dyh = x.half().float(), dy.half().float()
+    ref = torch.nn.grad.conv2d_weight(nchw(xh).double().contiguous(), (Cout, Cin, k, k), nchw(dyh).double().contiguous(), stride=stride, padding=pad).permute(0, 2, 3, 1)
+    assert ops._be().conv_wgrad_tc_supported(tuple(x.shape), tuple(dy.shape), k, k, stride, pad)
+    got = A.weight_grad(x.to(DEV), dy.to(DEV), k, k, stride, pad, "amp")
+    close(got, ref.float(), "wgrad amp (fp16-rounded operands)", 2e-5)
+    full = torch.nn.grad.conv2d_weight(nchw(x).double().contiguous(), (Cout, Cin, k, k), nchw(dy).double().contiguous(), stride=stride, padding=pad).permute(0, 2, 3, 1)
+    rel = float((got.cpu().double() - full).norm() / full.norm())
+    assert rel < 1e-3, rel
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,stride", [(2, 40, 40, 64, 128, 3, 1), (2, 40, 40, 128, 128, 3, 2), (2, 20, 20, 256, 64, 1, 1)])
+def test_conv2d_grads_amp(B, H, W, Cin, Cout, k, stride):
+    """Conv2dFn in the "amp" precision: forward, data gradient and weight gradient are single fp16 products with fp32 accumulation - compared with torch fp64 on
+    the fp16-rounded operands (forward / dw) and with the fp32 result at the fp16-rounding tolerance (dx: the weights AND dy are rounded)."""
+    pad = (k - 1) // 2
+    x, w = rnd((B, H, W, Cin), 1), rnd((Cout, Cin, k, k), 2, 0.05)
+    xr, wr = leaf(x.half().float()), leaf(w.half().float())
+    yr = nhwc(F.conv2d(nchw(xr), wr, None, stride, pad))
+    dy = rnd(tuple(yr.shape), 4).half().float()
+    yr.backward(dy)
+    xg, wg = leaf(x, DEV), leaf(w, DEV)
+    yg = A.conv2d(xg, wg, None, stride, pad, "amp")
+    yg.backward(dy.to(DEV))
+    close(yg, yr, "amp fwd", 2e-5)
+    close(wg.grad, wr.grad, "amp dw", 2e-5)
+    close(xg.grad, xr.grad, "amp dx", 2e-5)
+
+
 def test_stem_weight_gradient_kernel():
     """3x3 stride-2 conv on the 3-channel image (conv1_1): dedicated CUDA-core kernel (8x16 dY tile + input halo in shared memory)."""
     B, H, W, Cin, Cout = 2, 70, 100, 3, 32

@@ -11,7 +11,7 @@ from oracle.gen_golden import synth_images
 from oracle.gen_golden_train import synth_targets
 from focoos_b200.utils.seeded_weights import desaturate_classifiers
 from tests.parity_utils import load_golden, seeded_sd
-from tests.test_train_graph_cpu import check_against_golden, run_step
+from tests.test_train_graph_cpu import check_against_golden, check_amp_gradients, run_step
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
 DEV = torch.device("cuda", 0)
@@ -41,6 +41,28 @@ def test_train_step_gradients_match_reference(precision):
         assert sorted(m.train_graph().last_topk[0].tolist()) == sorted(g["topk_ind"][0].tolist()), "and the same query set"
     worst = check_against_golden(m, losses, g, loss_rtol=5e-4, grad_rtol=4e-3)
     print(f"[{precision}] worst gradient-norm error / tolerance: {worst}; kernels launched: {ops.launch_count() - n0}")
+
+
+def test_train_step_amp_precision():
+    """train_precision="amp" (TrainerArgs.amp_enabled, the reference's torch.autocast(fp16) arithmetic: one fp16 tensor-core product per conv/linear, fp32
+    accumulation and storage) against the reference's fp32 training-step golden, assignments teacher-forced: losses within 2e-2 relative and gradient norms within 2e-2 (median) / 8e-2 (p90) - the fp16 operand-rounding class, not the fp32 bars of the other two modes."""
+    g = load_golden("detr_l_train_b2_192")
+    m = FAIDetr(DETRConfig(), precision="fp32_tc")
+    m.train_precision = "amp"
+    m.load_state_dict(desaturate_classifiers(seeded_sd(0)), strict=True)
+    m.to(DEV)
+    m.criterion().forced_match = torch.from_numpy(g["match_q"])
+    m.train_graph().forced_topk = torch.from_numpy(g["topk_ind"])
+    assert m.train_graph().prec == "amp"
+    losses = run_step(m, g, DEV)
+    torch.cuda.synchronize()
+    keys = g["loss_keys"].tolist()
+    got = np.array([float(losses[k].detach()) for k in keys])
+    np.testing.assert_allclose(got, g["loss_values"], rtol=2e-2, atol=1e-4)
+    params = dict(m.named_parameters())
+    total = float(np.sqrt((g["grad_norm"] ** 2).sum()))
+    errs = check_amp_gradients(params, g, total)
+    print(f"[amp] losses {got} vs {g['loss_values']}; gradient-norm errors: median {errs[len(errs) // 2]:.3e}, p90 {errs[int(0.9 * len(errs))]:.3e}, max {errs[-1]:.3e}")
 
 
 def test_full_iteration_on_gpu():

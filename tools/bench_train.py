@@ -27,7 +27,8 @@ def run_leg(batch=16, size=640, steps=5, warmup=2, precision="fp32_tc", by_symbo
     rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     dev = torch.device("cuda", local)
     cfg = DETRConfig(num_classes=80)
-    m = FAIDetr(cfg, precision=precision)
+    m = FAIDetr(cfg, precision="fp32_tc" if precision == "amp" else precision)
+    m.train_precision = precision
     m.load_state_dict(desaturate_classifiers(seeded_state_dict(m.state_dict(), seed=0)), strict=True)  # same parameters on every rank
     m.to(dev).train()
     if sync_bn is not None and hasattr(m, "sync_bn"):
@@ -92,7 +93,9 @@ def run_leg(batch=16, size=640, steps=5, warmup=2, precision="fp32_tc", by_symbo
         by_sym["_kernels_ms"] = round(sum(v["ms"] for k, v in by_sym.items() if isinstance(v, dict)), 3)
     total = float(sum(v.detach() for v in losses.values()))
     res = {"metric": "images/sec fai-detr-l fine-tune step (fwd + criterion + bwd + all-reduce + AdamW)", "value": batch * world / (ms / 1e3), "unit": "images/s",
-           "n_gpus": world, "ms_per_step": ms, "steps": steps, "warmup": warmup, "scaling": "weak", "dtype": "f32 storage; " + ("3x f16 tcgen05 products for conv/linear forward, data and weight gradients" if precision == "fp32_tc" else "SIMT f32"),
+           "n_gpus": world, "ms_per_step": ms, "steps": steps, "warmup": warmup, "scaling": "weak", "dtype": "f32 storage; " + {"fp32_tc": "3x f16 tcgen05 products for conv/linear forward, data and weight gradients", "fp32": "SIMT f32",
+                                                                      "amp": "ONE f16 tcgen05 product (fp16-rounded operands, f32 accumulation) for conv/linear forward, data and weight gradients - the reference's torch.autocast(fp16) + GradScaler arithmetic (trainer/trainer.py:735)"}[precision],
+           "precision": precision,
            "config": {"workload": f"fai-detr-l (80 classes) bs={batch}/GPU {size}x{size} synthetic COCO-shape targets (BASELINE configs[4])", "global_batch": batch * world,
                       "sync_bn": bool(getattr(m, "sync_bn", False)) and world > 1},
            "kernel_launches_per_step": launches, "phases_ms": phases, "peak_mem_GB": torch.cuda.max_memory_allocated() / 1e9, "loss_total": total, "optimizer": opt.stats(), "by_symbol": by_sym}
@@ -108,7 +111,7 @@ def main():
     ap.add_argument("--size", type=int, default=640)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
-    ap.add_argument("--precision", default="fp32_tc", choices=["fp32", "fp32_tc"])
+    ap.add_argument("--precision", default="fp32_tc", choices=["fp32", "fp32_tc", "amp"])
     ap.add_argument("--no-sync-bn", action="store_true")
     args = ap.parse_args()
     rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
