@@ -161,3 +161,36 @@ def test_focoos_model_fused_semantic_path_equals_unfused():
     for a, b in zip(ref, got):
         assert [(d.cls_id, d.bbox, d.mask) for d in a.detections] == [(d.cls_id, d.bbox, d.mask) for d in b.detections]
         assert np.allclose([d.conf for d in a.detections], [d.conf for d in b.detections], atol=0)
+
+
+@pytest.mark.timeout(1200)
+def test_bisenet_full_size_batch_invariance_and_oracle():
+    """BASELINE configs[3] size (bs=64, 1024x512), parity-green mode: per-image results do not depend on the batch (bit-exact) and one full-size image agrees with
+    the CPU oracle (class / mask probabilities within 1e-3, the semantic argmax map identical on all but boundary pixels)."""
+    from oracle import bisenet_oracle as O
+
+    sd = seeded_state_dict(manifest_template("bisenetformer_l_ade"), 0)
+    m = BisenetFormer(BisenetFormerConfig(), precision="fp32_tc")
+    m.load_state_dict(sd, strict=True)
+    m.cuda()
+    imgs = synth_images(41, [(512, 1024)] * 64)
+    x = torch.stack([torch.from_numpy(im).permute(2, 0, 1).float() for im in imgs]).cuda()
+    out64 = m(x)
+    out2 = m(x[10:12].contiguous())
+    torch.cuda.synchronize()
+    assert torch.equal(out64.logits[10:12], out2.logits), "class probabilities depend on the batch"
+    assert torch.equal(out64.masks[10:12], out2.masks), "mask probabilities depend on the batch"
+    with torch.no_grad():
+        probs, masks = O.bisenet_forward(sd, x[10:11].cpu(), O.BisenetOracleConfig())
+    e_cls = float((out64.logits[10:11].cpu() - probs).abs().max())
+    e_mask = float((out64.masks[10:11].cpu() - masks).abs().max())
+    sem_g = (out64.logits[10].max(-1).values.view(-1, 1, 1) * out64.masks[10]).argmax(0).cpu()
+    sem_o = (probs[0].max(-1).values.view(-1, 1, 1) * masks[0]).argmax(0)
+    differ = float((sem_g != sem_o).float().mean())
+    path = "gpurun_out/parity_report_bisenet.json"
+    os.makedirs("gpurun_out", exist_ok=True)
+    d0 = json.load(open(path)) if os.path.exists(path) else {}
+    d0["fp32_tc_full_size_1024x512"] = {"class_prob_max_abs": e_cls, "mask_prob_max_abs": e_mask, "argmax_pixels_differing": differ}
+    json.dump(d0, open(path, "w"), indent=1)
+    assert e_cls <= 1e-3 and e_mask <= 1e-3, (e_cls, e_mask)
+    assert differ <= 1e-4, differ
