@@ -180,6 +180,11 @@ class SetCriterion(torch.nn.Module):
             self.last_match = mq
         w = (float(self.weight_dict.get("loss_vfl", 1.0)), float(self.weight_dict.get("loss_bbox", 1.0)), float(self.weight_dict.get("loss_giou", 1.0)))
         table = _DetrLossFn.apply(logits, boxes, tl, tb, toff, mq, num_boxes, w, self.focal_alpha, self.focal_gamma)
+        if mq is not None and self.forced_match is None:
+            # the device Hungarian writes -1 for an image whose cost matrix holds NaN / inf (scipy's linear_sum_assignment raises "matrix contains invalid numeric
+            # entries" in the reference, matcher :744): poison the losses instead of silently training on dropped targets - the loss scaler's found_inf then
+            # skips the step (amp), and without a scaler the NaN is visible in the very next log line.  Device-side select: no host synchronisation.
+            table = torch.where((mq < 0).any(), torch.full_like(table, float("nan")), table)
         out = {}
         for l in range(table.shape[0]):
             sfx = "" if l == 0 else f"_{l - 1}"

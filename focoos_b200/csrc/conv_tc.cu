@@ -345,6 +345,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if constexpr (CTA2) cluster_sync_all();  // the peer's barriers are initialised before any remote arrive / complete_tx can reach them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // Programmatic dependent launch (host side: launch(), FB200_TC_PDL): this grid may have been started while the previous kernel of the stream was still draining its
+  // last tiles - everything above (tensor-map prefetch, barrier init, TMEM allocation, cluster handshake) touched no global data.  Let OUR dependents start the same
+  // way, then wait until the prerequisite grid has completed and its writes are visible before any role reads activations / residuals or writes outputs.
+  // Both instructions are no-ops for a launch without the attribute.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int tiles_per_img = p.tiles_w * p.tiles_h;
   // debug timeline: slot 0 = kernel entry of this CTA (globaltimer ns), 1 = setup done (clock64); per tile k < 20: 2+6k = accumulator stage free,
   // 3+6k = first operands landed, 4+6k = last MMA issued (MMA thread); 5+6k = accumulator complete seen, 6+6k = tile stored (epilogue group 0); 7+6k = producer tile start
@@ -940,6 +946,15 @@ static int num_sms() {
   return n;
 }
 
+// programmatic dependent launch of consecutive conv_tc kernels (the prologue of launch n+1 overlaps the tail of launch n, see conv_tc_kernel).  Measured on the B200
+// (trip r02-20, graph replay of the whole step): 18.41 ms with, 18.40 ms without - the ~2 us prologue is already hidden behind the persistent CTAs' first TMA
+// round trip - so it is OFF by default; FB200_TC_PDL=1 turns it on.
+static bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("FB200_TC_PDL"); on = e ? atoi(e) : 0; }
+  return on != 0;
+}
+
 template <int BLOCK_N, int STAGES, typename TOut, int MIN_BLOCKS, int BLOCK_K, int NSTG, bool GELU, bool CTA2 = false, bool FS = false>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr, const CUtensorMap& td2, const CUtensorMap& tr2,
                   const KParams& kp, cudaStream_t st) {
@@ -963,11 +978,13 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
     cfg.blockDim = dim3(NUM_THREADS, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, td, tr, td2, tr2, kp);
     if (e != cudaSuccess) { set_error("conv_tc(cta pair): launch failed: %s", cudaGetErrorString(e)); return FB200_ERR_CUDA; }
     return FB200_OK;
@@ -975,6 +992,21 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
   int64_t cap = (int64_t)num_sms() * MIN_BLOCKS;
   { static int gc = -1; if (gc < 0) { const char* e = getenv("FB200_GRID_CAP"); gc = e ? atoi(e) : 0; } if (gc > 0 && gc < cap) cap = gc; }  // experiment: fewer SMs
   const unsigned grid = (unsigned)(kp.total_tiles < cap ? kp.total_tiles : cap);
+  if (pdl_enabled()) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, td, tr, td2, tr2, kp);
+    if (e != cudaSuccess) { set_error("conv_tc: launch failed: %s", cudaGetErrorString(e)); return FB200_ERR_CUDA; }
+    return FB200_OK;
+  }
   kern<<<grid, NUM_THREADS, smem, st>>>(ta, tb, td, tr, td2, tr2, kp);
   FB_CHECK_LAUNCH("conv_tc_kernel");
   return FB200_OK;

@@ -234,13 +234,18 @@ class MaskFormerProcessor(DETRProcessor):
         self.mask_threshold, self.use_mask_score, self.predict_all_pixels = config.mask_threshold, config.use_mask_score, config.predict_all_pixels
         self.training = False
 
-    def postprocess_tensors(self, output, threshold=None, use_mask_score=None):
+    def postprocess_tensors(self, output, threshold=None, use_mask_score=None, predict_all_pixels=None):
         """-> list over images of (query idx [n], scores [n], labels [n]) on the host, plus the device masks tensor."""
         threshold = threshold or self.threshold
         use_mask_score = use_mask_score or self.use_mask_score
+        predict_all_pixels = predict_all_pixels or self.predict_all_pixels  # fai_mf/processor.py:188-190: the argument ORs with the configured default
         self._labels = self._masks = self._lazy = None
         lazy = hasattr(output.masks, "materialize")  # fai_mf.LazyMasks: low-resolution logits, upsampling not done yet
-        if self.predict_all_pixels:  # semantic: every pixel goes to argmax_q(score_q * prob_q) (processor.py:208-220)
+        if predict_all_pixels and use_mask_score:
+            # the reference's mask score of a semantic region is its mean probability over the argmax pixels (:249-257); the fused argmax kernels return pixel
+            # counts only, so this combination (no shipped config uses it) is refused rather than scored differently
+            raise NotImplementedError("focoos_b200: use_mask_score together with predict_all_pixels is not supported")
+        if predict_all_pixels:  # semantic: every pixel goes to argmax_q(score_q * prob_q) (processor.py:208-220)
             scores_dev = output.logits.max(-1).values  # [B,Q]; tiny reduction, stays on the device for the argmax kernel
             if lazy:  # sigmoid + bilinear upsampling + argmax in one kernel: the [B,Q,H,W] tensor is never written
                 self._labels, count = ops.mask_sigmoid_upsample_argmax(output.masks.logits, output.masks.num_queries, output.masks.size, scores_dev)
@@ -273,7 +278,8 @@ class MaskFormerProcessor(DETRProcessor):
         image_sizes = get_image_sizes(inputs)
         B = output.logits.shape[0]
         assert len(image_sizes) == B, f"Expected image sizes {len(image_sizes)} to match batch size {B}"
-        kept = self.postprocess_tensors(output, threshold, use_mask_score)
+        # top_k is accepted for signature compatibility: the reference's MaskFormerProcessor.postprocess never reads it either (fai_mf/processor.py:170-262)
+        kept = self.postprocess_tensors(output, threshold, use_mask_score, predict_all_pixels)
         results = []
         for b, (q, s, l) in enumerate(kept):
             if len(q) == 0:
