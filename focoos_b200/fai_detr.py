@@ -589,10 +589,14 @@ class DetrEngine:
             x = self._pc(r, x, residual=y12.slice(C, 2 * C) if last else None, act=(ops.ACT_SILU | 16) if last else None, out=out if last else None)
         return x
 
-    def _forward_pair_trunk(self, images, taps):
-        """backbone + hybrid encoder + decoder input projection in the pair format -> (memory Pair [B,S,d], shapes, constants)"""
+    def pair_capable(self) -> bool:
+        """the pair-native fp32_tc data flow is available (three products in every stage, default algorithm choice, a tcgen05 device or the CPU test backend)"""
+        return (self.precision == "fp32_tc" and self.pair_native and self.algo == ops.ALGO_AUTO and all(v == 3 for v in getattr(self, "mix", {}).values())
+                and (ops._backend is not None or ops.supports_tcgen05_cached()))
+
+    def _run_backbone_pair(self, images):
+        """ResNet-vd in the pair format -> [res2, res3, res4, res5] as Pairs (nn/backbone/resnet.py:252-266); shared by every model family with this backbone"""
         cfg = self.cfg
-        P = ops.Pair
         x = ops.stem_conv(images.contiguous(), self.stem_w, self.stem_s, self.stem_b, cfg.pixel_mean, cfg.pixel_std, ops.ACT_RELU, out_pair=True)
         x = self._pc(self.stem3, self._pc(self.stem2, x))
         x = ops.pair_maxpool3x3s2(x)
@@ -603,6 +607,13 @@ class DetrEngine:
                 short = x if blk["short"] is None else self._pc(blk["short"], ops.pair_avgpool2x2(x) if blk["stride"] == 2 else x)
                 x = self._pc(blk["c"], y, residual=short)
             feats.append(x)
+        return feats
+
+    def _forward_pair_trunk(self, images, taps):
+        """backbone + hybrid encoder + decoder input projection in the pair format -> (memory Pair [B,S,d], shapes, constants)"""
+        cfg = self.cfg
+        P = ops.Pair
+        feats = self._run_backbone_pair(images)
         res3, res4, res5 = feats[1], feats[2], feats[3]
         B, h32, w32, _ = res5.shape
         K = self._constants(h32, w32)
@@ -662,8 +673,7 @@ class DetrEngine:
             # maps, so the engine takes multiples of 32 - resize or pad in the processor (image_size) for other inputs
             raise ValueError(f"focoos_b200: input size {H}x{W} is not a multiple of 32; resize/pad the image (e.g. ModelInfo.im_size) before the model")
         global _products
-        use_pair = (self.precision == "fp32_tc" and self.pair_native and A == ops.ALGO_AUTO and all(v == 3 for v in self.mix.values())
-                    and (ops._backend is not None or ops.supports_tcgen05_cached()))
+        use_pair = self.pair_capable()
         if use_pair:
             mem_pair, shapes, K = self._forward_pair_trunk(images, taps)
             dev = images.device

@@ -26,7 +26,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .fai_detr import MLP, DetrEngine, ResNet, _bn_fold, _Conv, _CriterionStub, _enable_split3, _Linear
+from .fai_detr import _split3_weights, MLP, DetrEngine, ResNet, _bn_fold, _Conv, _CriterionStub, _enable_split3, _Linear
 from .ports import ModelOutput, ResnetConfig
 
 
@@ -290,7 +290,13 @@ class MFEngine(DetrEngine):
         Qp = (Q + 7) // 8 * 8
         masks = torch.zeros((B, h4, w4, Qp), dtype=dt, device=out.device)
         # einsum("bqc,bchw->bqhw"): a [h4*w4, C] x [C, Q] GEMM per image whose "weights" (the mask embeddings) differ per image - ONE launch
-        ops.conv2d_per_image(mask_features, me.reshape(B, Q, 1, 1, C), out=masks[..., :Q], algo=A)
+        mfp = getattr(self, "_mf_pair", None)
+        if mfp is not None and mfp[0] is mask_features:
+            # fp32_tc: the same GEMM as three fp16 tensor-core products - mask_features split ONCE per forward (_run_decoder), the per-image embeddings as
+            # [W_hi | W_lo | W_hi] triples.  (On the CUDA-core fp32 kernel this product was a third of the parity-mode step: 16.9 of 50.4 ms at bs=16 800x800.)
+            ops.conv2d_per_image(mfp[1], _split3_weights(me).reshape(B, Q, 1, 1, 3 * C), out=masks[..., :Q], algo=ops.ALGO_TCGEN05_SPLIT3)
+        else:
+            ops.conv2d_per_image(mask_features, me.reshape(B, Q, 1, 1, C), out=masks[..., :Q], algo=A)
         attn = None
         if size is not None:
             low = masks if (h4, w4) == tuple(size) else ops.resize_bilinear(masks, size)
@@ -309,11 +315,19 @@ class MFEngine(DetrEngine):
             # the reference's torch graph takes any size (odd feature maps from ceil-mode pools / stride-2 convs); the B200 kernels tile the stride-2 layers on even
             # maps, so the engine takes multiples of 32 - resize or pad in the processor (image_size) for other inputs
             raise ValueError(f"focoos_b200: input size {H}x{W} is not a multiple of 32; resize/pad the image (e.g. ModelInfo.im_size) before the model")
-        res2, res3, res4, res5 = self._run_backbone(images)
+        pair = self.pair_capable() and all(getattr(c, "w3", None) is not None for c in [self.pd_in] + [self.adapter[i] for i in (1, 2, 3)])
+        if pair:
+            # fp32_tc: the backbone keeps its activations as fp16 [hi | lo] planes between convs (no split pass in front of every conv, DetrEngine._run_backbone_pair);
+            # the four pixel-decoder convs that consume res2..res5 read the pairs and write the fp32 tensors the transformer / FPN arithmetic below works on
+            res2, res3, res4, res5 = self._run_backbone_pair(images)
+            in_conv = lambda conv, f: self._pc(conv, f, out_pair=False)  # noqa: E731
+        else:
+            res2, res3, res4, res5 = self._run_backbone(images)
+            in_conv = lambda conv, f: conv(f, algo=A)  # noqa: E731
         d, nh = self.d, self.nhead
         scale = 1.0 / math.sqrt(d // nh)
         # ---- pixel decoder (TransformerFPN.forward_features)
-        x = self.pd_in(res5, algo=A)
+        x = in_conv(self.pd_in, res5)
         h, w = x.shape[1], x.shape[2]
         pos = self._pos(h, w)
         src = x.reshape(B, h * w, d)
@@ -328,12 +342,12 @@ class MFEngine(DetrEngine):
         y = self.layer[4](src.reshape(B, h, w, d), algo=A)
         ms = [y]
         for idx, f in ((3, res4), (2, res3), (1, res2)):
-            y = self.layer[idx](ops.upsample_nearest_add(y, self.adapter[idx](f, algo=A)), algo=A)
+            y = self.layer[idx](ops.upsample_nearest_add(y, in_conv(self.adapter[idx], f)), algo=A)
             if len(ms) < 3:
                 ms.append(y)
         mask_features = self.mask_features(y, algo=A)
         if taps is not None:
-            taps.update(res5=res5, enc_memory=src.reshape(B, h, w, d), mask_features=mask_features, multi_scale=ms)
+            taps.update(res5=res5.float() if pair else res5, enc_memory=src.reshape(B, h, w, d), mask_features=mask_features, multi_scale=ms)
         return self._run_decoder(ms, mask_features, B, H, W, taps)
 
     def _run_decoder(self, ms, mask_features, B, H, W, taps=None):
@@ -343,6 +357,10 @@ class MFEngine(DetrEngine):
         d, nh = self.d, self.nhead
         scale = 1.0 / math.sqrt(d // nh)
         nl = len(ms)
+        self._mf_pair = None
+        if (self.precision == "fp32_tc" and A == ops.ALGO_AUTO and mask_features.dtype == torch.float32 and mask_features.shape[-1] % 64 == 0
+                and (ops._backend is not None or ops.supports_tcgen05_cached())):
+            self._mf_pair = (mask_features, ops.split_pair(mask_features))  # consumed by every _heads call of this forward
         srcs, kpos, sizes = [], [], []
         for i in range(nl):
             hh, ww = ms[i].shape[1], ms[i].shape[2]
@@ -376,6 +394,7 @@ class MFEngine(DetrEngine):
             taps.update(pred_logits=cls, pred_masks=masks)  # masks: NHWC [B,h4,w4,Qp] pre-sigmoid logits
         probs = ops.softmax_drop_last(cls)
         lazy = LazyMasks(masks, Q, (H, W))
+        self._mf_pair = None
         return probs, (lazy if self.lazy_masks else lazy.materialize())
 
 

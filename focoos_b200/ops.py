@@ -457,7 +457,12 @@ def conv2d(x, w, scale=None, bias=None, *, stride=1, pad=0, act=ACT_NONE, residu
 
 def conv2d_per_image(x, w, *, act=ACT_NONE, out=None, out_dtype=None, algo=ALGO_AUTO):
     """conv with one weight set per image: x [B,H,W,Cin], w [B,Cout,KH,KW,Cin] -> [B,H,W,Cout]  (the per-query mask product, one launch per batch)."""
-    assert x.dim() == 4 and w.dim() == 5 and w.shape[0] == x.shape[0] and w.shape[-1] == x.shape[-1] and w.dtype == x.dtype and w.stride(-1) == 1
+    assert x.dim() == 4 and w.dim() == 5 and w.shape[0] == x.shape[0] and w.dtype == x.dtype and w.stride(-1) == 1
+    if algo == ALGO_TCGEN05_SPLIT3:  # fp32-accurate: x = the [hi|lo] pair of the fp32 activation (2C channels), w = per-image [W_hi|W_lo|W_hi] triples (3C), fp32 out
+        assert x.dtype == torch.float16 and w.shape[-1] * 2 == x.shape[-1] * 3, (w.shape, x.shape)
+        out_dtype = out_dtype or torch.float32
+    else:
+        assert w.shape[-1] == x.shape[-1]
     B, H, W, _ = x.shape
     Cout = w.shape[1]
     if out is None:

@@ -71,3 +71,18 @@ def test_mf_fused_graph_matches_golden(ref_backend):
     for a_, b_ in zip(dets, dets2):
         assert [(d.cls_id, d.bbox, d.mask) for d in a_.detections] == [(d.cls_id, d.bbox, d.mask) for d in b_.detections]
         assert np.allclose([d.conf for d in a_.detections], [d.conf for d in b_.detections], rtol=1e-6)
+
+
+def test_mf_pair_native_backbone_host_logic(ref_backend):
+    """precision="fp32_tc": the ResNet backbone runs in the pair format (fp16 hi/lo planes between convs, DetrEngine._run_backbone_pair) and the four pixel-decoder
+    convs read the pairs - host-side bookkeeping on the CPU references: same outputs as the fp32 graph up to the pair rounding (2^-22 relative per activation)."""
+    g = load_golden("mf_l_coco_ins_b2_320x416")
+    m = FAIMaskFormer(MaskFormerConfig(), precision="fp32_tc")
+    m.load_state_dict(_sd(), strict=True)
+    assert m.engine().pair_capable()
+    imgs = synth_images(3, [tuple(s) for s in g["sizes"].tolist()])
+    x = torch.stack([torch.from_numpy(im).permute(2, 0, 1).float() for im in imgs])
+    taps = {}
+    out = m(x, taps=taps)
+    assert np.abs(out.logits.numpy() - g["logits"]).max() <= 1e-3
+    assert np.abs(out.masks[:, ::10, ::4, ::4].numpy() - g["masks_q10_s4"]).max() <= 2e-3
