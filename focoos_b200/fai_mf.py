@@ -378,7 +378,8 @@ class MFEngine(DetrEngine):
             lvl = i % nl
             t2 = ops.layernorm(out, *blk["cn"])
             q = blk["cq"](ops.add(t2, qpos), algo=A)
-            a = ops.attention_masked(q, blk["ck"](kpos[lvl], algo=A), blk["cv"](srcs[lvl], algo=A), attn[0], attn[1], nh, scale)
+            a = ops.attention_masked(q, blk["ck"](kpos[lvl], algo=A), blk["cv"](srcs[lvl], algo=A), attn[0], attn[1], nh, scale,
+                                     split=self.precision == "fp32_tc" and A == ops.ALGO_AUTO)
             out = blk["cout"](a, residual=out, algo=A)
             t2 = ops.layernorm(out, *blk["sn"])
             qk = blk["sqk"](ops.add(t2, qpos), algo=A)

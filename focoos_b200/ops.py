@@ -801,7 +801,7 @@ except Exception:  # pragma: no cover - e.g. double import under a different mod
 # MaskFormer-family operators
 # ------------------------------------------------------------------------------------------------
 EXPORTED_SYMBOLS = EXPORTED_SYMBOLS + (
-    "fb200_upsample_nearest_add", "fb200_attn_mask_build", "fb200_attention_masked", "fb200_softmax_drop_last",
+    "fb200_upsample_nearest_add", "fb200_attn_mask_build", "fb200_attention_masked", "fb200_attention_masked_split", "fb200_softmax_drop_last",
     "fb200_mask_sigmoid_upsample", "fb200_mask_sigmoid_upsample_argmax", "fb200_mask_sigmoid_upsample_stats", "fb200_mask_sigmoid_upsample_select", "fb200_mask_stats", "fb200_mask_resize_bbox",
 )
 
@@ -823,6 +823,13 @@ def _cb_attention_masked(self, q, k, v, mask, allowed, out, heads, scale):
     B, Lq, C = q.shape
     self._call("fb200_attention_masked", _p(q), _pitch(q), _p(k), _pitch(k), _p(v), _pitch(v), _p(mask), mask.shape[2], _p(allowed), _p(out), _pitch(out),
                _dt(q), B, Lq, k.shape[1], heads, C // heads, ctypes.c_float(scale), _stream())
+
+
+def _cb_attention_masked_split(self, q, k, v, mask, allowed, out, heads, scale):
+    self._cuda(q, k, v, mask, allowed, out)
+    B, Lq, C = q.shape
+    self._call("fb200_attention_masked_split", _p(q), _pitch(q), _p(k), _pitch(k), _p(v), _pitch(v), _p(mask), mask.shape[2], _p(allowed), _p(out), _pitch(out),
+               B, Lq, k.shape[1], heads, C // heads, ctypes.c_float(scale), _stream())
 
 
 def _cb_softmax_drop_last(self, x, out):
@@ -868,7 +875,7 @@ def _cb_mask_resize_bbox(self, masks, bq, thr, out_masks, out_bbox):
 
 
 for _n, _f in (("mask_sigmoid_upsample_stats", _cb_mask_sigmoid_upsample_stats), ("mask_sigmoid_upsample_select", _cb_mask_sigmoid_upsample_select),
-               ("mask_sigmoid_upsample_argmax", _cb_mask_sigmoid_upsample_argmax), ("upsample_nearest_add", _cb_upsample_nearest_add), ("attn_mask_build", _cb_attn_mask_build), ("attention_masked", _cb_attention_masked),
+               ("mask_sigmoid_upsample_argmax", _cb_mask_sigmoid_upsample_argmax), ("upsample_nearest_add", _cb_upsample_nearest_add), ("attn_mask_build", _cb_attn_mask_build), ("attention_masked", _cb_attention_masked), ("attention_masked_split", _cb_attention_masked_split),
                ("softmax_drop_last", _cb_softmax_drop_last), ("mask_sigmoid_upsample", _cb_mask_sigmoid_upsample), ("mask_stats", _cb_mask_stats),
                ("mask_resize_bbox", _cb_mask_resize_bbox)):
     setattr(CudaBackend, _n, _f)
@@ -892,11 +899,15 @@ def attn_mask_build(mask_logits_nhwc, num_queries: int):
     return mask, allowed
 
 
-def attention_masked(q, k, v, mask, allowed, heads: int, scale: float):
-    """masked cross-attention: q [B,Lq,C], k/v [B,Lk,C]; mask/allowed from attn_mask_build (shared by all heads)."""
+def attention_masked(q, k, v, mask, allowed, heads: int, scale: float, split: bool = False):
+    """masked cross-attention: q [B,Lq,C], k/v [B,Lk,C]; mask/allowed from attn_mask_build (shared by all heads).
+    split (fp32 tensors, precision "fp32_tc"): fp32-accurate tensor-core products instead of the CUDA-core fp32 kernel."""
     B, Lq, C = q.shape
     out = torch.empty((B, Lq, C), dtype=q.dtype, device=q.device)
-    _be().attention_masked(q, k, v, mask, allowed, out, heads, scale)
+    if split and q.dtype == torch.float32:
+        _be().attention_masked_split(q, k, v, mask, allowed, out, heads, scale)
+    else:
+        _be().attention_masked(q, k, v, mask, allowed, out, heads, scale)
     return out
 
 

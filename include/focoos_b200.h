@@ -227,6 +227,11 @@ int fb200_attention_masked(const void* q, int q_pitch, const void* k, int k_pitc
                            const int* allowed, void* out, int out_pitch, int dtype, int B, int Lq, int Lk, int heads, int head_dim, float scale,
                            void* stream);
 
+/* The same masked attention on fp32 tensors with fp32-accurate tensor-core products (precision "fp32_tc"): Q, K, V and the softmax numerators are split into fp16 hi / lo
+ * halves on the fly, S = Qh Kh^T + Qh Kl^T + Ql Kh^T and O += Ph Vh + Ph Vl + Pl Vh with fp32 accumulation (error ~2^-21), keys streamed 256 at a time. */
+int fb200_attention_masked_split(const float* q, int q_pitch, const float* k, int k_pitch, const float* v, int v_pitch, const uint8_t* mask, int LkP, const int* allowed,
+                                 float* out, int out_pitch, int B, int Lq, int Lk, int heads, int head_dim, float scale, void* stream);
+
 /* out[r, 0..N-2] = softmax(x[r, 0..N-1])[..., :-1]  (drop the no-object class; fai_mf/modelling.py:618). fp32. */
 int fb200_softmax_drop_last(const float* x, int64_t rows, int N, int pitch, float* out, void* stream);
 

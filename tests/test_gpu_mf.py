@@ -63,6 +63,28 @@ def test_mask_build_and_masked_attention(dtype, hw):
     close(out, ref, 3e-3 if dtype == torch.float16 else 1e-4, f"masked attention {hw}")
 
 
+@pytest.mark.parametrize("hw,Q", [((10, 13), 100), ((25, 25), 100), ((50, 50), 100), ((33, 41), 100), ((100, 100), 100), ((20, 26), 37)])
+def test_masked_attention_split_precision(hw, Q):
+    """fb200_attention_masked_split (fp32 tensors, three fp16 tensor-core products, keys streamed 256 at a time) vs the fp64 reference: fully allowed, fully masked
+    (-> attends everywhere) and partially masked rows, key counts that are not multiples of the 64-key MMA block or the 256-key chunk."""
+    B, heads = 2, 8
+    Qp = (Q + 7) // 8 * 8
+    h, w = hw
+    Lk = h * w
+    x = rnd((B, h, w, Qp), torch.float32, 3)
+    x[0, :, :, 5] = 1.0    # everything allowed
+    x[1, :, :, 7] = -1.0   # everything masked -> must attend everywhere
+    x[1, : h // 2, :, 9] = -1.0   # the first half of the keys masked: whole leading chunks without a live key
+    m, a = ops.attn_mask_build(x.to(DEV), Q)
+    q, k, v = rnd((B, Q, 256), torch.float32, 4), rnd((B, Lk, 256), torch.float32, 5), rnd((B, Lk, 256), torch.float32, 6)
+    ref = torch.empty((B, Q, 256), dtype=torch.float64)
+    REF.attention_masked(q.double(), k.double(), v.double(), m.cpu(), a.cpu(), ref, heads, 1 / math.sqrt(32))
+    out = ops.attention_masked(q.to(DEV), k.to(DEV), v.to(DEV), m, a, heads, 1 / math.sqrt(32), split=True)
+    simt = ops.attention_masked(q.to(DEV), k.to(DEV), v.to(DEV), m, a, heads, 1 / math.sqrt(32))
+    close(simt, ref.float(), 1e-5, f"masked attention (CUDA-core fp32) {hw}")
+    close(out, ref.float(), 1e-5, f"masked attention (split tensor-core) {hw}")
+
+
 def test_softmax_drop_last():
     x = rnd((3, 100, 81), torch.float32, 7, 3.0)
     ref = torch.empty((3, 100, 80))
