@@ -245,14 +245,16 @@ class BisenetEngine(MFEngine):
         B, C = vec.shape
         return conv(vec.reshape(B, 1, 1, C), algo=ops.ALGO_SIMT).reshape(B, -1)
 
-    def _cat_bottleneck(self, x, blk):
+    def _cat_bottleneck(self, x, blk, first_in_pair=False):
         A, dt = self.algo, self.dt
         c = blk["convs"]
         half = c[0].w.shape[0]
         Cout = half * 2
         B, H, W, _ = x.shape
+        if first_in_pair and blk["stride"] != 2:  # a stride-1 block the pair path does not take: back to fp32 first
+            x, first_in_pair = x.float(), False
         if blk["stride"] == 2:
-            out1 = c[0](x, algo=A)
+            out1 = self._pc(c[0], x, out_pair=False) if first_in_pair else c[0](x, algo=A)
             buf = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, Cout), dtype=dt, device=x.device)
             ops.avgpool3x3s2(out1, out=buf[..., :half])
             src = ops.dwconv3x3s2(out1, *blk["avd"])
@@ -267,6 +269,33 @@ class BisenetEngine(MFEngine):
             src = buf[..., o:o + w]
             o += w
         return buf
+
+    def _cat_bottleneck_pair(self, x, blk):
+        """stride-1 CatBottleneck in the pair format (fp32_tc): the four convs read and write fp16 [hi | lo] planes - each one's output is a channel slice of the block's
+        concat buffer and the next one's input - so no split pass runs inside the block.  x: Pair or fp32 tensor (split once) -> Pair"""
+        c = blk["convs"]
+        half = c[0].w.shape[0]
+        B, H, W, _ = x.shape
+        buf = ops.Pair.empty((B, H, W, 2 * half), x.device)
+        src = self._pc(c[0], x, out=buf.slice(0, half))
+        o = half
+        for i in (1, 2, 3):
+            w = c[i].w.shape[0]
+            src = self._pc(c[i], src, out=buf.slice(o, o + w))
+            o += w
+        return buf
+
+    def _pair_block_ok(self, blk, H, W) -> bool:
+        """conv2d_pair takes the block: every conv has its weight triple; a 32-channel 3x3 input needs the halo mode (rows of at least 64 pixels, Cout <= 64)"""
+        if blk["stride"] != 1 or not self.pair_capable():
+            return False
+        for cv in blk["convs"]:
+            cin, cout, k = cv.w.shape[3], cv.w.shape[0], cv.w.shape[1]
+            if cv.w3 is None or cout % 8:
+                return False
+            if cin % 64 and not (cin == 32 and k == 3 and W >= 64 and cout <= 64):
+                return False
+        return True
 
     @torch.no_grad()
     def forward(self, images: torch.Tensor, taps: Optional[dict] = None):
@@ -283,11 +312,20 @@ class BisenetEngine(MFEngine):
         x = ops.stem_conv(images.contiguous(), self.stem_w, self.stem_s, self.stem_b, cfg.pixel_mean, cfg.pixel_std, ops.ACT_RELU, dt)
         x = self.stem2(x, algo=A)  # res2
         feats = []
+        P = ops.Pair
+        as_f32 = lambda t: t.float() if isinstance(t, P) else t  # noqa: E731  (a torch op: only ever applied to the small 1/32-resolution map below)
         for stage in self.blocks:
             for blk in stage:
-                x = self._cat_bottleneck(x, blk)
+                if self._pair_block_ok(blk, x.shape[1], x.shape[2]):
+                    x = self._cat_bottleneck_pair(x, blk)
+                elif isinstance(x, P):  # a stride-2 block after pair-native ones: its first conv reads the pair and writes fp32, the rest runs as before
+                    x = self._cat_bottleneck(x, blk, first_in_pair=True)
+                else:
+                    x = self._cat_bottleneck(x, blk)
             feats.append(x)
         res3, res4, res5 = feats
+        res5 = as_f32(res5)  # global average pool + ARM gates work on fp32 (33 M elements at bs=64 1024x512)
+        pin = lambda conv, f, **kw: (self._pc(conv, f, out_pair=False, **kw) if isinstance(f, P) else conv(f, algo=A, **kw))  # noqa: E731
         # context path
         avg = self._gate(self.conv_avg, ops.global_avgpool(res5))
         a = self.arm["arm32"]
@@ -295,16 +333,16 @@ class BisenetEngine(MFEngine):
         f32 = ops.channel_scale(f, self._gate(a["att"], ops.global_avgpool(f)), addvec=avg)
         up = self.head32(ops.resize_bilinear(f32, (res4.shape[1], res4.shape[2])), algo=A)
         a = self.arm["arm16"]
-        f = a["conv"](a["proj"](res4, algo=A), algo=A)
+        f = a["conv"](pin(a["proj"], res4), algo=A)
         f16 = ops.channel_scale(f, self._gate(a["att"], ops.global_avgpool(f)), addt=up)
         f8 = self.head16(ops.resize_bilinear(f16, (res3.shape[1], res3.shape[2])), algo=A)
         # feature fusion
-        feat = self.ffm_blk(self.ffm_p1(res3, residual=self.ffm_p2(f8, algo=A), algo=A), algo=A)
+        feat = self.ffm_blk(pin(self.ffm_p1, res3, residual=self.ffm_p2(f8, algo=A)), algo=A)
         att = self._gate(self.ffm_c2, self._gate(self.ffm_c1, ops.global_avgpool(feat)))
         fuse = ops.channel_scale(feat, att, self_add=True)
         mask_features = self.conv_out(fuse, algo=A)
         if taps is not None:
-            taps.update(res3=res3, res4=res4, res5=res5, cp32=f32, cp16=f16, cp8=f8, mask_features=mask_features)
+            taps.update(res3=as_f32(res3), res4=as_f32(res4), res5=res5, cp32=f32, cp16=f16, cp8=f8, mask_features=mask_features)
         return self._run_decoder([f32, f16], mask_features, B, H, W, taps)
 
 

@@ -66,3 +66,23 @@ def test_bisenet_fused_graph_matches_golden(ref_backend):
     for a_, b_ in zip(dets, dets2):
         assert [(d.cls_id, d.bbox, d.mask, d.conf) for d in a_.detections] == [(d.cls_id, d.bbox, d.mask, d.conf) for d in b_.detections]
     assert torch.equal(lazy_out.masks.materialize(), out.masks)
+
+
+def test_bisenet_pair_native_blocks_host_logic(ref_backend):
+    """precision="fp32_tc": the stride-1 CatBottlenecks run in the pair format (concat buffer = channel slices of one pair buffer), the stride-2 blocks and the
+    context path read the pairs through fp32-output convs - host bookkeeping on the CPU references, same results as the fp32 graph up to the pair rounding."""
+    g = load_golden("bisenetformer_l_ade_b2_256x384")
+    m = BisenetFormer(BisenetFormerConfig(), precision="fp32_tc")
+    m.load_state_dict(seeded_state_dict(manifest_template("bisenetformer_l_ade"), 0), strict=True)
+    eng = m.engine()
+    assert eng.pair_capable()
+    H, W = (int(v) for v in g["sizes"][0])
+    taken = [eng._pair_block_ok(blk, H // (8 << si), W // (8 << si)) for si, stage in enumerate(eng.blocks) for blk in stage]
+    assert sum(taken) >= 6 and not any(t for t, blk in zip(taken, [b for st in eng.blocks for b in st]) if blk["stride"] == 2)
+    imgs = synth_images(4, [tuple(s) for s in g["sizes"].tolist()])
+    x = torch.stack([torch.from_numpy(im).permute(2, 0, 1).float() for im in imgs])
+    taps = {}
+    out = m(x, taps=taps)
+    assert np.abs(taps["cp32"].permute(0, 3, 1, 2)[:, ::16].numpy() - g["cp32_tap"]).max() <= 1e-4 * np.abs(g["cp32_tap"]).max()
+    assert np.abs(out.logits.numpy() - g["logits"]).max() <= 1e-3
+    assert np.abs(out.masks[:, ::10, ::4, ::4].numpy() - g["masks_q10_s4"]).max() <= 1e-3
