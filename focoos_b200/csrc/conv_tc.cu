@@ -460,8 +460,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 tma_load_5d(&tmap_a, &full_bar[stage], dst_a, (tw & 1) * p.x_pitch + c_hi, w0 + (tw >> 1), th & 1, h0 + (th >> 1), img);
                 tma_load_5d(&tmap_a, &full_bar[stage], dst_a + A_HALF, (tw & 1) * p.x_pitch + c_lo, w0 + (tw >> 1), th & 1, h0 + (th >> 1), img);
               }
-              tma_load_2d(&tmap_b, &full_bar[stage], dst_b, k_hi, n0);
-              tma_load_2d(&tmap_b, &full_bar[stage], dst_b + B_HALF, k_lo, n0);
+              if (p.w_batched) {  // per-image weights (the mask product of the MaskFormer-family heads): third coordinate = image
+                tma_load_3d(&tmap_b, &full_bar[stage], dst_b, k_hi, n0, img);
+                tma_load_3d(&tmap_b, &full_bar[stage], dst_b + B_HALF, k_lo, n0, img);
+              } else {
+                tma_load_2d(&tmap_b, &full_bar[stage], dst_b, k_hi, n0);
+                tma_load_2d(&tmap_b, &full_bar[stage], dst_b + B_HALF, k_lo, n0);
+              }
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -1230,7 +1235,8 @@ int conv2d_tc(const ConvParams& p, cudaStream_t st) {
   static int fs_env = -1;  // FB200_TC_FS=0 disables
   if (fs_env < 0) { const char* e = getenv("FB200_TC_FS"); fs_env = e ? atoi(e) : 1; }
   const bool out_pair = p.out_dtype == FB200_F16PAIR;
-  if (fs_env && p.split3 && BK == 64 && (p.out_dtype == FB200_F32 || out_pair) && !kp.w_batched) {
+  // (per-image weights: the single-CTA fused-split configurations only - the CTA-pair producer has no 3-D weight loads)
+  if (fs_env && p.split3 && BK == 64 && (p.out_dtype == FB200_F32 || out_pair) && (!kp.w_batched || (p.Cout <= 128 && !out_pair))) {
     // deep K loops want the 3-stage ring (and have a long main loop to hide a single staging buffer behind); layers with a residual (fetched by TMA into the
     // SECOND staging buffer) or a short K loop are bound by the epilogue / HBM: two stages, double-buffered staging
     const bool deep = !p.res && !out_pair && p.KH * p.KW * (Clog / 64) > 4;  // (pair output needs both staging buffers: one per plane pair in flight)
