@@ -12,8 +12,41 @@
 namespace fb200 {
 namespace {
 
-constexpr int HD = 32, HDP = 33;
+constexpr int HD = 32;
+// HDP (template parameter of attention_bwd_kernel) = 36: row pitch a multiple of 4 floats so the inner loops read the (broadcast) rows as float4 - one shared-memory load per four FMAs
+// (with the 33-float pitch every FMA needed its own LDS and the kernel ran at the shared-memory pipe's rate: 545 us per call)
 
+// 33 = the conflict-free scalar pitch, kept for sequences whose four planes do not fit shared memory at 36 (the 400-token AIFI layer at 640x640)
+template <bool VEC>
+__device__ __forceinline__ float dot32(const float (&a)[HD], const float* __restrict__ row) {
+  float s = 0.f;
+  if constexpr (!VEC) {
+#pragma unroll
+    for (int d = 0; d < HD; ++d) s = fmaf(a[d], row[d], s);
+    return s;
+  }
+#pragma unroll
+  for (int d = 0; d < HD; d += 4) {
+    const float4 r = *reinterpret_cast<const float4*>(row + d);
+    s = fmaf(a[d], r.x, s); s = fmaf(a[d + 1], r.y, s); s = fmaf(a[d + 2], r.z, s); s = fmaf(a[d + 3], r.w, s);
+  }
+  return s;
+}
+template <bool VEC>
+__device__ __forceinline__ void axpy32(float (&acc)[HD], float a, const float* __restrict__ row) {
+  if constexpr (!VEC) {
+#pragma unroll
+    for (int d = 0; d < HD; ++d) acc[d] = fmaf(a, row[d], acc[d]);
+    return;
+  }
+#pragma unroll
+  for (int d = 0; d < HD; d += 4) {
+    const float4 r = *reinterpret_cast<const float4*>(row + d);
+    acc[d] = fmaf(a, r.x, acc[d]); acc[d + 1] = fmaf(a, r.y, acc[d + 1]); acc[d + 2] = fmaf(a, r.z, acc[d + 2]); acc[d + 3] = fmaf(a, r.w, acc[d + 3]);
+  }
+}
+
+template <int HDP>
 __global__ void __launch_bounds__(384) attention_bwd_kernel(const float* __restrict__ q, int q_pitch, const float* __restrict__ k, int k_pitch,
                                                             const float* __restrict__ v, int v_pitch, const float* __restrict__ o, int o_pitch,
                                                             const float* __restrict__ dout, int do_pitch, int Lq, int Lk, int heads, float scale,
@@ -51,28 +84,15 @@ __global__ void __launch_bounds__(384) attention_bwd_kernel(const float* __restr
       acc[d] = 0.f;
     }
     float m = -INFINITY;
-    for (int j = 0; j < Lk; ++j) {
-      float s = 0.f;
-#pragma unroll
-      for (int d = 0; d < HD; ++d) s = fmaf(qi[d], sK[j * HDP + d], s);
-      m = fmaxf(m, s * scale);
-    }
+    for (int j = 0; j < Lk; ++j) m = fmaxf(m, dot32<HDP % 4 == 0>(qi, sK + j * HDP) * scale);
     float l = 0.f;
-    for (int j = 0; j < Lk; ++j) {
-      float s = 0.f;
-#pragma unroll
-      for (int d = 0; d < HD; ++d) s = fmaf(qi[d], sK[j * HDP + d], s);
-      l += expf(s * scale - m);
-    }
+    for (int j = 0; j < Lk; ++j) l += expf(dot32<HDP % 4 == 0>(qi, sK + j * HDP) * scale - m);
     const float lse = m + logf(l);
     for (int j = 0; j < Lk; ++j) {
-      float s = 0.f, dp = 0.f;
-#pragma unroll
-      for (int d = 0; d < HD; ++d) { s = fmaf(qi[d], sK[j * HDP + d], s); dp = fmaf(gi[d], sV[j * HDP + d], dp); }
+      const float s = dot32<HDP % 4 == 0>(qi, sK + j * HDP), dp = dot32<HDP % 4 == 0>(gi, sV + j * HDP);
       const float p = expf(s * scale - lse);
       const float ds = p * (dp - D) * scale;
-#pragma unroll
-      for (int d = 0; d < HD; ++d) acc[d] = fmaf(ds, sK[j * HDP + d], acc[d]);
+      axpy32<HDP % 4 == 0>(acc, ds, sK + j * HDP);
     }
     sL[i] = lse;
     sD[i] = D;
@@ -86,13 +106,11 @@ __global__ void __launch_bounds__(384) attention_bwd_kernel(const float* __restr
 #pragma unroll
     for (int d = 0; d < HD; ++d) { kj[d] = sK[j * HDP + d]; vj[d] = sV[j * HDP + d]; ak[d] = 0.f; av[d] = 0.f; }
     for (int i = 0; i < Lq; ++i) {
-      float s = 0.f, dp = 0.f;
-#pragma unroll
-      for (int d = 0; d < HD; ++d) { s = fmaf(sQ[i * HDP + d], kj[d], s); dp = fmaf(sdO[i * HDP + d], vj[d], dp); }
+      const float s = dot32<HDP % 4 == 0>(kj, sQ + i * HDP), dp = dot32<HDP % 4 == 0>(vj, sdO + i * HDP);
       const float p = expf(s * scale - sL[i]);
       const float ds = p * (dp - sD[i]) * scale;
-#pragma unroll
-      for (int d = 0; d < HD; ++d) { av[d] = fmaf(p, sdO[i * HDP + d], av[d]); ak[d] = fmaf(ds, sQ[i * HDP + d], ak[d]); }
+      axpy32<HDP % 4 == 0>(av, p, sdO + i * HDP);
+      axpy32<HDP % 4 == 0>(ak, ds, sQ + i * HDP);
     }
 #pragma unroll
     for (int d = 0; d < HD; ++d) { dk[(kb + j) * dk_pitch + h * HD + d] = ak[d]; dv[(kb + j) * dv_pitch + h * HD + d] = av[d]; }
@@ -177,15 +195,25 @@ extern "C" int fb200_attention_bwd(const float* q, int q_pitch, const float* k, 
                                    float* dk, int dk_pitch, float* dv, int dv_pitch, void* stream) {
   FB_CHECK_ARG(q && k && v && o && dout && dq && dk && dv, "attention_bwd: null pointer");
   FB_CHECK_ARG(head_dim == HD, "attention_bwd: head_dim must be 32");
-  const size_t smem = ((size_t)2 * Lq * HDP + (size_t)2 * Lk * HDP + 2 * Lq) * sizeof(float);
+  auto bytes = [&](int pitch) { return ((size_t)2 * Lq * pitch + (size_t)2 * Lk * pitch + 2 * Lq) * sizeof(float); };
+  const bool vec = bytes(36) <= 227 * 1024;   // float4 rows when the four planes fit at the 36-float pitch, else the 33-float scalar layout
+  const size_t smem = bytes(vec ? 36 : 33);
   FB_CHECK_ARG(smem <= 227 * 1024, "attention_bwd: Lq=%d Lk=%d exceed the shared-memory-resident design (Lq+Lk <= ~850)", Lq, Lk);
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
+  if (!attr) {
+    cudaFuncSetAttribute(attention_bwd_kernel<36>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attention_bwd_kernel<33>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr = true;
+  }
   // one thread per query (phase 1) / key (phase 2): with 256 threads the 300 decoder queries took two rounds, the second with 44 active threads
   int threads = ((Lq > Lk ? Lq : Lk) + 31) / 32 * 32;
   threads = threads < 128 ? 128 : (threads > 384 ? 384 : threads);
-  attention_bwd_kernel<<<B * heads, threads, smem, (cudaStream_t)stream>>>(q, q_pitch, k, k_pitch, v, v_pitch, o, o_pitch, dout, do_pitch, Lq, Lk, heads, scale, dq, dq_pitch,
-                                                                        dk, dk_pitch, dv, dv_pitch);
+  if (vec)
+    attention_bwd_kernel<36><<<B * heads, threads, smem, (cudaStream_t)stream>>>(q, q_pitch, k, k_pitch, v, v_pitch, o, o_pitch, dout, do_pitch, Lq, Lk, heads, scale, dq,
+                                                                                 dq_pitch, dk, dk_pitch, dv, dv_pitch);
+  else
+    attention_bwd_kernel<33><<<B * heads, threads, smem, (cudaStream_t)stream>>>(q, q_pitch, k, k_pitch, v, v_pitch, o, o_pitch, dout, do_pitch, Lq, Lk, heads, scale, dq,
+                                                                                 dq_pitch, dk, dk_pitch, dv, dv_pitch);
   FB_CHECK_LAUNCH("attention_bwd");
   return FB200_OK;
 }
