@@ -114,8 +114,8 @@ int attention_mma_split(const float* q, int q_pitch, const float* k, int k_pitch
                         int heads, float scale, int out_pair, cudaStream_t st);
 int attention_mma(const __half* q, int q_pitch, const __half* k, int k_pitch, const __half* v, int v_pitch, __half* out, int out_pitch, int B,
                   int Lq, int Lk, int heads, float scale, cudaStream_t st);
-int attention_mma_split_stream(const float* q, int q_pitch, const float* k, int k_pitch, const float* v, int v_pitch, const uint8_t* mask, int MP, const int* allowed,
-                               float* out, int out_pitch, int B, int Lq, int Lk, int heads, float scale, cudaStream_t st);
+int attention_mma_split_stream(const float* q, int q_pitch, const void* k, int k_pitch, const void* v, int v_pitch, int kv_pair, int kv_lo_off, const uint8_t* mask, int MP,
+                               const int* allowed, float* out, int out_pitch, int B, int Lq, int Lk, int heads, float scale, cudaStream_t st);
 }  // namespace fb200
 using namespace fb200;
 
@@ -160,15 +160,23 @@ extern "C" int fb200_attention(const void* q, int q_pitch, const void* k, int k_
   return FB200_OK;
 }
 
-extern "C" int fb200_attention_masked_split(const float* q, int q_pitch, const float* k, int k_pitch, const float* v, int v_pitch, const uint8_t* mask, int LkP,
-                                            const int* allowed, float* out, int out_pitch, int B, int Lq, int Lk, int heads, int head_dim, float scale, void* stream) {
+extern "C" int fb200_attention_masked_split(const float* q, int q_pitch, const void* k, int k_pitch, const void* v, int v_pitch, int kv_dtype, int64_t kv_lo_off,
+                                            const uint8_t* mask, int LkP, const int* allowed, float* out, int out_pitch, int B, int Lq, int Lk, int heads, int head_dim,
+                                            float scale, void* stream) {
   FB_CHECK_ARG(q && k && v && out && head_dim == 32, "attention_masked_split: null pointer or head_dim != 32");
   FB_CHECK_ARG((mask == nullptr) == (allowed == nullptr), "attention_masked_split: mask and allowed go together");
-  FB_CHECK_ARG(q_pitch % 4 == 0 && k_pitch % 4 == 0 && v_pitch % 4 == 0 && out_pitch % 2 == 0 && (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) & 15) == 0 &&
-                   ((uintptr_t)out & 7) == 0, "attention_masked_split: pitches / alignment");
+  FB_CHECK_ARG(kv_dtype == FB200_F32 || kv_dtype == FB200_F16PAIR, "attention_masked_split: k / v are fp32 tensors or fp16 [hi|lo] pairs");
   FB_CHECK_ARG(B > 0 && Lq > 0 && Lk > 0 && heads > 0, "attention_masked_split: bad shape");
+  FB_CHECK_ARG(q_pitch % 4 == 0 && out_pitch % 2 == 0 && ((uintptr_t)q & 15) == 0 && ((uintptr_t)out & 7) == 0, "attention_masked_split: q / out pitches / alignment");
+  if (kv_dtype == FB200_F32) {
+    FB_CHECK_ARG(k_pitch % 4 == 0 && v_pitch % 4 == 0 && (((uintptr_t)k | (uintptr_t)v) & 15) == 0, "attention_masked_split: k / v pitches / alignment");
+  } else {  // pair rows: hi plane at the pointer, lo plane kv_lo_off halves further, 16-byte copies
+    FB_CHECK_ARG(k_pitch % 8 == 0 && v_pitch % 8 == 0 && kv_lo_off % 8 == 0 && kv_lo_off >= heads * 32 && k_pitch >= kv_lo_off + heads * 32 && v_pitch >= kv_lo_off + heads * 32 &&
+                     (((uintptr_t)k | (uintptr_t)v) & 15) == 0, "attention_masked_split: pair k / v need 16-byte aligned planes inside the row pitch");
+  }
   FB_CHECK_ARG(mask == nullptr || (LkP % 4 == 0 && LkP >= ((Lk + 1) & ~1) && ((uintptr_t)mask & 3) == 0), "attention_masked_split: mask rows must be 4-byte aligned, pitch %% 4 == 0");
-  return attention_mma_split_stream(q, q_pitch, k, k_pitch, v, v_pitch, mask, LkP, allowed, out, out_pitch, B, Lq, Lk, heads, scale, (cudaStream_t)stream);
+  return attention_mma_split_stream(q, q_pitch, k, k_pitch, v, v_pitch, kv_dtype == FB200_F16PAIR ? 1 : 0, (int)kv_lo_off, mask, LkP, allowed, out, out_pitch, B, Lq, Lk, heads,
+                                    scale, (cudaStream_t)stream);
 }
 
 extern "C" int fb200_attention_split(const float* q, int q_pitch, const float* k, int k_pitch, const float* v, int v_pitch, void* out, int out_dtype, int out_pitch, int B,
@@ -485,16 +493,28 @@ int attention_mma_split(const float* q, int q_pitch, const float* k, int k_pitch
 // (H/8 * W/8) keys; fai_mf/modelling.py:510-513, nn/layers/transformer.py:206-238): K / V are staged (and split into fp16 hi / lo planes) ASK keys at a time, the online
 // softmax carries across the chunks; mask[b,q,key] != 0 removes a key unless allowed[b,q] == 0 (a fully masked row attends everywhere).  Same three-product fragment
 // algebra as above; fp32 in, fp32 out.  Replaces the CUDA-core attention_masked_kernel<float> (two shared-memory loads per FMA; 7.8 of 37.9 ms of the bs=16 800x800 step).
-constexpr int ASK = 256;  // keys per staged chunk
-__global__ void __launch_bounds__(384) attention_mma_split_stream_kernel(const float* __restrict__ q, int q_pitch, const float* __restrict__ k, int k_pitch,
-                                                                         const float* __restrict__ v, int v_pitch, const uint8_t* __restrict__ mask, int MP,
+// KVP: K and V arrive already as fp16 [hi | lo] pairs (written by the epilogue of their projection, conv2d_pair with out_pair) - rows [hi(heads*32) | ... | lo(heads*32)] with
+// the lo plane kv_lo_off halves behind the hi plane.  Staging is then a plain 16-byte cp.async copy, double buffered (chunk c+1 lands while chunk c is multiplied); with fp32
+// K / V the chunk is converted while it is staged (synchronously, single buffer).
+__device__ __forceinline__ void cp_async16_zfill(void* dst, const void* src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  const int sz = valid ? 16 : 0;  // src-size 0: the 16 destination bytes are zero-filled, the source is not read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+template <bool KVP> __host__ __device__ constexpr int ask_keys() { return KVP ? 128 : 256; }  // keys per staged chunk
+template <bool KVP>
+__global__ void __launch_bounds__(384) attention_mma_split_stream_kernel(const float* __restrict__ q, int q_pitch, const void* __restrict__ k_, int k_pitch,
+                                                                         const void* __restrict__ v_, int v_pitch, int kv_lo_off, const uint8_t* __restrict__ mask, int MP,
                                                                          const int* __restrict__ allowed, float* __restrict__ out, int out_pitch, int Lq, int Lk,
                                                                          int heads, float scale_log2) {
   extern __shared__ __align__(16) __half smh[];
+  constexpr int ASK = ask_keys<KVP>();
+  constexpr int NBUF = KVP ? 2 : 1;
   constexpr size_t kv = (size_t)ASK * AM_PITCH;
-  __half* Kh = smh; __half* Kl = Kh + kv; __half* Vh = Kl + kv; __half* Vl = Vh + kv;
+  const float* k = reinterpret_cast<const float*>(k_);
+  const float* v = reinterpret_cast<const float*>(v_);
   const int QB = (int)(blockDim.x >> 5) * 16;  // queries per CTA
-  __half* Qh = Vl + kv; __half* Ql = Qh + QB * AM_PITCH;
+  __half* Qh = smh + NBUF * 4 * kv; __half* Ql = Qh + QB * AM_PITCH;
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int q0 = blockIdx.y * QB;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -523,19 +543,46 @@ __global__ void __launch_bounds__(384) attention_mma_split_stream_kernel(const f
 #pragma unroll
     for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-  for (int c0 = 0; c0 < Lk; c0 += ASK) {
-    __syncthreads();  // the previous chunk has been consumed by every warp
-    for (int i = tid; i < ASK * 8; i += (int)blockDim.x) {  // 8 x float4 per 32-wide row
-      const int r = i >> 3, c = (i & 7) * 4;
-      float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
-      if (c0 + r < Lk) {
-        kk = *reinterpret_cast<const float4*>(k + ((int64_t)b * Lk + c0 + r) * k_pitch + h * 32 + c);
-        vv = *reinterpret_cast<const float4*>(v + ((int64_t)b * Lk + c0 + r) * v_pitch + h * 32 + c);
+  // pair K / V: issue the 16-byte copies of chunk `ci` into buffer ci & 1 (planes Kh, Kl, Vh, Vl; 4 x 16 B per 32-half row and plane)
+  auto issue_pair_chunk = [&](int ci) {
+    if constexpr (KVP) {
+      const __half* kp = reinterpret_cast<const __half*>(k_);
+      const __half* vp = reinterpret_cast<const __half*>(v_);
+      __half* base = smh + (size_t)(ci & 1) * 4 * kv;
+      const int c0 = ci * ASK;
+      for (int i = tid; i < ASK * 16; i += (int)blockDim.x) {
+        const int r = i >> 4, plane = (i >> 2) & 3, c = (i & 3) * 8;   // plane 0 = Kh, 1 = Kl, 2 = Vh, 3 = Vl
+        const bool ok = c0 + r < Lk;
+        const int64_t row = (int64_t)b * Lk + (ok ? c0 + r : 0);
+        const __half* src = (plane < 2 ? kp + row * k_pitch : vp + row * v_pitch) + (plane & 1) * kv_lo_off + h * 32 + c;
+        cp_async16_zfill(base + plane * kv + r * AM_PITCH + c, src, ok);
       }
-      split_store4(Kh + r * AM_PITCH + c, Kl + r * AM_PITCH + c, kk);
-      split_store4(Vh + r * AM_PITCH + c, Vl + r * AM_PITCH + c, vv);
+      asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    __syncthreads();
+  };
+  const int nchunks = (Lk + ASK - 1) / ASK;
+  if constexpr (KVP) issue_pair_chunk(0);
+  for (int ci = 0; ci < nchunks; ++ci) {
+    const int c0 = ci * ASK;
+    __half* Kh = smh + (size_t)(KVP ? (ci & 1) : 0) * 4 * kv; __half* Kl = Kh + kv; __half* Vh = Kl + kv; __half* Vl = Vh + kv;
+    if constexpr (KVP) {
+      if (ci + 1 < nchunks) { issue_pair_chunk(ci + 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+      else asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();  // chunk ci has landed for every thread's copies
+    } else {
+      __syncthreads();  // the previous chunk has been consumed by every warp
+      for (int i = tid; i < ASK * 8; i += (int)blockDim.x) {  // 8 x float4 per 32-wide row
+        const int r = i >> 3, c = (i & 7) * 4;
+        float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+        if (c0 + r < Lk) {
+          kk = *reinterpret_cast<const float4*>(k + ((int64_t)b * Lk + c0 + r) * k_pitch + h * 32 + c);
+          vv = *reinterpret_cast<const float4*>(v + ((int64_t)b * Lk + c0 + r) * v_pitch + h * 32 + c);
+        }
+        split_store4(Kh + r * AM_PITCH + c, Kl + r * AM_PITCH + c, kk);
+        split_store4(Vh + r * AM_PITCH + c, Vl + r * AM_PITCH + c, vv);
+      }
+      __syncthreads();
+    }
     const int kend = min(ASK, (Lk - c0 + 63) & ~63);
     for (int kb = 0; kb < kend; kb += 64) {
       float s[8][4];
@@ -603,6 +650,7 @@ __global__ void __launch_bounds__(384) attention_mma_split_stream_kernel(const f
         }
       }
     }
+    if constexpr (KVP) __syncthreads();  // every warp is done with buffer ci & 1 before chunk ci + 2 is copied into it
   }
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
@@ -615,20 +663,27 @@ __global__ void __launch_bounds__(384) attention_mma_split_stream_kernel(const f
   }
 }
 
-int attention_mma_split_stream(const float* q, int q_pitch, const float* k, int k_pitch, const float* v, int v_pitch, const uint8_t* mask, int MP, const int* allowed,
-                               float* out, int out_pitch, int B, int Lq, int Lk, int heads, float scale, cudaStream_t st) {
+int attention_mma_split_stream(const float* q, int q_pitch, const void* k, int k_pitch, const void* v, int v_pitch, int kv_pair, int kv_lo_off, const uint8_t* mask, int MP,
+                               const int* allowed, float* out, int out_pitch, int B, int Lq, int Lk, int heads, float scale, cudaStream_t st) {
   // two query blocks per (batch, head) for the 100-query decoders: 256 CTAs of 4 warps, two per SM, so one CTA's chunk staging overlaps the other's MMAs
   const int nblk = (int)cdiv(Lq, 64);
   const int NW = (int)cdiv(cdiv(Lq, nblk), 16);
-  const size_t smem = ((size_t)4 * ASK + 2 * 16 * NW) * AM_PITCH * sizeof(__half);
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(attention_mma_split_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attention_mma_split_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attention_mma_split_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     configured = true;
   }
   dim3 grid(B * heads, (unsigned)cdiv(Lq, 16 * NW));
-  attention_mma_split_stream_kernel<<<grid, 32 * NW, smem, st>>>(q, q_pitch, k, k_pitch, v, v_pitch, mask, MP, allowed, out, out_pitch, Lq, Lk, heads,
-                                                                   scale * 1.4426950408889634f);
+  if (kv_pair) {
+    const size_t smem = ((size_t)2 * 4 * ask_keys<true>() + 2 * 16 * NW) * AM_PITCH * sizeof(__half);
+    attention_mma_split_stream_kernel<true><<<grid, 32 * NW, smem, st>>>(q, q_pitch, k, k_pitch, v, v_pitch, kv_lo_off, mask, MP, allowed, out, out_pitch, Lq, Lk, heads,
+                                                                           scale * 1.4426950408889634f);
+  } else {
+    const size_t smem = ((size_t)4 * ask_keys<false>() + 2 * 16 * NW) * AM_PITCH * sizeof(__half);
+    attention_mma_split_stream_kernel<false><<<grid, 32 * NW, smem, st>>>(q, q_pitch, k, k_pitch, v, v_pitch, 0, mask, MP, allowed, out, out_pitch, Lq, Lk, heads,
+                                                                            scale * 1.4426950408889634f);
+  }
   FB_CHECK_LAUNCH("attention_mma_split_stream");
   return FB200_OK;
 }

@@ -368,6 +368,12 @@ class MFEngine(DetrEngine):
             srcs.append(s)
             kpos.append(ops.add(s, self._pos(hh, ww)))
             sizes.append((hh, ww))
+        # fp32_tc: masked cross-attention on the tensor cores (fb200_attention_masked_split); the per-level key / value inputs are split ONCE (they are the same for the
+        # three layers of a level) and the K / V projections run pair -> pair
+        split_attn = self.precision == "fp32_tc" and A == ops.ALGO_AUTO
+        pair_kv = split_attn and self.pair_capable() and all(b_["ck"].w3 is not None and b_["cv"].w3 is not None for b_ in self.dec)
+        if pair_kv:
+            kpos_p, srcs_p = [ops.to_pair(t) for t in kpos], [ops.to_pair(t) for t in srcs]
         Q = cfg.num_queries
         out = self.query_feat.unsqueeze(0).expand(B, Q, d).contiguous()
         qpos = self.query_embed
@@ -378,8 +384,11 @@ class MFEngine(DetrEngine):
             lvl = i % nl
             t2 = ops.layernorm(out, *blk["cn"])
             q = blk["cq"](ops.add(t2, qpos), algo=A)
-            a = ops.attention_masked(q, blk["ck"](kpos[lvl], algo=A), blk["cv"](srcs[lvl], algo=A), attn[0], attn[1], nh, scale,
-                                     split=self.precision == "fp32_tc" and A == ops.ALGO_AUTO)
+            if pair_kv:  # K / V projections write the fp16 [hi | lo] pairs the attention kernel stages with plain 16-byte copies
+                kk, vv = self._plin(blk["ck"], kpos_p[lvl], out_pair=True), self._plin(blk["cv"], srcs_p[lvl], out_pair=True)
+            else:
+                kk, vv = blk["ck"](kpos[lvl], algo=A), blk["cv"](srcs[lvl], algo=A)
+            a = ops.attention_masked(q, kk, vv, attn[0], attn[1], nh, scale, split=split_attn)
             out = blk["cout"](a, residual=out, algo=A)
             t2 = ops.layernorm(out, *blk["sn"])
             qk = blk["sqk"](ops.add(t2, qpos), algo=A)

@@ -826,10 +826,13 @@ def _cb_attention_masked(self, q, k, v, mask, allowed, out, heads, scale):
 
 
 def _cb_attention_masked_split(self, q, k, v, mask, allowed, out, heads, scale):
-    self._cuda(q, k, v, mask, allowed, out)
+    """k / v: fp32 tensors [B,Lk,C] or `Pair`s (hi / lo fp16 planes written by their projection)"""
+    pair = isinstance(k, Pair)
+    kh, vh = (k.hi, v.hi) if pair else (k, v)
+    self._cuda(q, kh, vh, mask, allowed, out)
     B, Lq, C = q.shape
-    self._call("fb200_attention_masked_split", _p(q), _pitch(q), _p(k), _pitch(k), _p(v), _pitch(v), _p(mask), mask.shape[2], _p(allowed), _p(out), _pitch(out),
-               B, Lq, k.shape[1], heads, C // heads, ctypes.c_float(scale), _stream())
+    self._call("fb200_attention_masked_split", _p(q), _pitch(q), _p(kh), _pitch(kh), _p(vh), _pitch(vh), F16PAIR if pair else F32, ctypes.c_int64(k.lo_off if pair else 0),
+               _p(mask), mask.shape[2], _p(allowed), _p(out), _pitch(out), B, Lq, kh.shape[1], heads, C // heads, ctypes.c_float(scale), _stream())
 
 
 def _cb_softmax_drop_last(self, x, out):
@@ -905,6 +908,8 @@ def attention_masked(q, k, v, mask, allowed, heads: int, scale: float, split: bo
     B, Lq, C = q.shape
     out = torch.empty((B, Lq, C), dtype=q.dtype, device=q.device)
     if split and q.dtype == torch.float32:
+        if isinstance(k, Pair):
+            assert isinstance(v, Pair) and k.lo_off == v.lo_off and k.C == C and v.C == C
         _be().attention_masked_split(q, k, v, mask, allowed, out, heads, scale)
     else:
         _be().attention_masked(q, k, v, mask, allowed, out, heads, scale)

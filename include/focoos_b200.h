@@ -227,10 +227,12 @@ int fb200_attention_masked(const void* q, int q_pitch, const void* k, int k_pitc
                            const int* allowed, void* out, int out_pitch, int dtype, int B, int Lq, int Lk, int heads, int head_dim, float scale,
                            void* stream);
 
-/* The same masked attention on fp32 tensors with fp32-accurate tensor-core products (precision "fp32_tc"): Q, K, V and the softmax numerators are split into fp16 hi / lo
- * halves on the fly, S = Qh Kh^T + Qh Kl^T + Ql Kh^T and O += Ph Vh + Ph Vl + Pl Vh with fp32 accumulation (error ~2^-21), keys streamed 256 at a time. */
-int fb200_attention_masked_split(const float* q, int q_pitch, const float* k, int k_pitch, const float* v, int v_pitch, const uint8_t* mask, int LkP, const int* allowed,
-                                 float* out, int out_pitch, int B, int Lq, int Lk, int heads, int head_dim, float scale, void* stream);
+/* The same masked attention with fp32-accurate tensor-core products (precision "fp32_tc"): Q (fp32), K, V and the softmax numerators as fp16 hi / lo halves,
+ * S = Qh Kh^T + Qh Kl^T + Ql Kh^T and O += Ph Vh + Ph Vl + Pl Vh with fp32 accumulation (error ~2^-21), keys streamed in chunks.  kv_dtype FB200_F32: k / v are fp32 tensors,
+ * split while they are staged; FB200_F16PAIR: k / v are the [hi | lo] pairs their projection already wrote (fb200_conv2d_pair with a pair output): hi plane at the pointer, lo
+ * plane kv_lo_off halves further, pitches in halves - staged by 16-byte asynchronous copies, double buffered. */
+int fb200_attention_masked_split(const float* q, int q_pitch, const void* k, int k_pitch, const void* v, int v_pitch, int kv_dtype, int64_t kv_lo_off, const uint8_t* mask,
+                                 int LkP, const int* allowed, float* out, int out_pitch, int B, int Lq, int Lk, int heads, int head_dim, float scale, void* stream);
 
 /* out[r, 0..N-2] = softmax(x[r, 0..N-1])[..., :-1]  (drop the no-object class; fai_mf/modelling.py:618). fp32. */
 int fb200_softmax_drop_last(const float* x, int64_t rows, int N, int pitch, float* out, void* stream);

@@ -296,6 +296,13 @@ def _ref_attention_masked(self, q, k, v, mask, allowed, out, heads, scale):
     out.copy_((torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(B, Lq, C).to(out.dtype))
 
 
+def _ref_attention_masked_split(self, q, k, v, mask, allowed, out, heads, scale):
+    """fb200_attention_masked_split: k / v as fp32 tensors or as Pairs (the fp32 values they encode)"""
+    kf = k.float() if hasattr(k, "hi") else k
+    vf = v.float() if hasattr(v, "hi") else v
+    _ref_attention_masked(self, q, kf, vf, mask, allowed, out, heads, scale)
+
+
 def _ref_softmax_drop_last(self, x, out):
     out.copy_(F.softmax(x.float(), dim=-1)[..., :-1])
 
@@ -321,7 +328,7 @@ def _ref_mask_resize_bbox(self, masks, bq, thr, out_masks, out_bbox):
         out_bbox[i] = torch.tensor([int(cols[0]), int(rows[0]), int(cols[-1]), int(rows[-1])] if len(rows) else [0, 0, 0, 0], dtype=torch.int32)
 
 
-for _n, _f in (("upsample_nearest_add", _ref_upsample_nearest_add), ("attn_mask_build", _ref_attn_mask_build), ("attention_masked", _ref_attention_masked), ("attention_masked_split", _ref_attention_masked),
+for _n, _f in (("upsample_nearest_add", _ref_upsample_nearest_add), ("attn_mask_build", _ref_attn_mask_build), ("attention_masked", _ref_attention_masked), ("attention_masked_split", _ref_attention_masked_split),
                ("softmax_drop_last", _ref_softmax_drop_last), ("mask_sigmoid_upsample", _ref_mask_sigmoid_upsample), ("mask_stats", _ref_mask_stats),
                ("mask_resize_bbox", _ref_mask_resize_bbox)):
     setattr(RefBackend, _n, _f)

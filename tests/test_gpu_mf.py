@@ -83,6 +83,10 @@ def test_masked_attention_split_precision(hw, Q):
     simt = ops.attention_masked(q.to(DEV), k.to(DEV), v.to(DEV), m, a, heads, 1 / math.sqrt(32))
     close(simt, ref.float(), 1e-5, f"masked attention (CUDA-core fp32) {hw}")
     close(out, ref.float(), 1e-5, f"masked attention (split tensor-core) {hw}")
+    # K / V as the fp16 [hi | lo] pairs their projection writes (16-byte asynchronous staging, double buffered)
+    kp, vp = ops.Pair(ops.split_pair(k.to(DEV))), ops.Pair(ops.split_pair(v.to(DEV)))
+    outp = ops.attention_masked(q.to(DEV), kp, vp, m, a, heads, 1 / math.sqrt(32), split=True)
+    close(outp, ref.float(), 1e-5, f"masked attention (split tensor-core, pair K/V) {hw}")
 
 
 @pytest.mark.parametrize("B,h,w,C,Q", [(3, 40, 52, 256, 100), (2, 37, 45, 256, 100), (2, 64, 128, 128, 100), (1, 200, 200, 256, 100)])
