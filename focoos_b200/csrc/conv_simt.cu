@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const void* __restrict__
 // Tiled stem: a CTA computes a 16 x 16 tile of output pixels.  The 33 x 33 x 3 input patch is read ONCE (coalesced rows), normalised ONCE per input pixel and kept in
 // shared memory as even / odd column planes (the stride-2 taps of 16 neighbouring threads then hit 16 consecutive floats: no bank conflicts); the 27 x 32 weights are
 // read as float4 broadcasts.  The per-pixel kernel above re-loaded and re-normalised (with a division) every input byte for each of the up to nine taps that use it.
-template <typename TOut, bool U8_NHWC>
+template <typename TOut, bool U8_NHWC, bool RELU>   // RELU: the activation is known to be ReLU (every model family's stem): no generic activation code in the kernel at all
 __global__ void __launch_bounds__(256) stem_conv_tiled_kernel(const void* __restrict__ img_, int B, int H, int W, const float* __restrict__ w,
                                                               const float* __restrict__ scale, const float* __restrict__ bias, float m0, float m1, float m2,
                                                               float s0, float s1, float s2, int act, TOut* __restrict__ out, int tiles_w, int tiles_h) {
@@ -113,23 +113,57 @@ __global__ void __launch_bounds__(256) stem_conv_tiled_kernel(const void* __rest
   const int ho0 = th * T, wo0 = tw * T;
   const int hi0 = 2 * ho0 - 1, wi0 = 2 * wo0 - 1;
   const float mean[3] = {m0, m1, m2}, stdv[3] = {s0, s1, s2};
+  // the patch: all of a thread's (up to 13) loads are issued before the first one is consumed - as a rolled loop every iteration waited for its own global load
+  // (13 dependent round trips per CTA in front of ~2 us of arithmetic)
+  constexpr int NP = PR * PR * 3, NIT = (NP + 255) / 256;
+  float raw[NIT];
   if (U8_NHWC) {
+    // patch row r = 99 consecutive bytes (33 pixels x 3 channels) of image row hi0 + r: element i = r * 99 + j, walked incrementally (256 = 2 * 99 + 58) with 32-bit
+    // offsets inside the image - the kernel is instruction-bound (ncu: 3340 instructions per warp for 864 FMAs, ALU pipe busier than the FMA pipe)
+    constexpr int RB = PR * 3;
     const uint8_t* ub = reinterpret_cast<const uint8_t*>(img_) + (int64_t)b * H * W * 3;
-    for (int i = tid; i < PR * PR * 3; i += 256) {  // consecutive threads -> consecutive bytes of a patch row
-      const int ci = i % 3, c = (i / 3) % PR, r = i / (3 * PR);
+    // (x - mean) / std takes only 3 x 256 values for uint8 input: one IEEE division per table entry (3 per thread) instead of one per patch element (13 per thread,
+    // ~25 instructions each) - same arithmetic, same bits
+    __shared__ float lut[3][256];
+    lut[0][tid] = ((float)tid - m0) / s0; lut[1][tid] = ((float)tid - m1) / s1; lut[2][tid] = ((float)tid - m2) / s2;
+    int r = tid / RB, j = tid - r * RB;
+    int rr[NIT], jj[NIT];
+#pragma unroll
+    for (int u = 0; u < NIT; ++u) {  // consecutive threads -> consecutive bytes of a patch row
+      rr[u] = r; jj[u] = j;
+      const int c = j / 3;
       const int hi = hi0 + r, wi = wi0 + c;
-      float v = 0.f;  // the conv pads the NORMALISED image with zeros
-      if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = ((float)ub[((int64_t)hi * W + wi) * 3 + ci] - mean[ci]) / stdv[ci];
-      sin_[ci][r][c & 1][c >> 1] = v;
+      raw[u] = -1.f;  // marks "outside": the conv pads the NORMALISED image with zeros
+      if (r < PR && hi >= 0 && hi < H && wi >= 0 && wi < W) raw[u] = (float)ub[(hi * W + wi0) * 3 + j];
+      j += 256 - 2 * RB; r += 2;
+      if (j >= RB) { j -= RB; r += 1; }
+    }
+    __syncthreads();  // the table
+#pragma unroll
+    for (int u = 0; u < NIT; ++u) {
+      if (rr[u] < PR) {
+        const int c = jj[u] / 3, ci = jj[u] - 3 * c;
+        sin_[ci][rr[u]][c & 1][c >> 1] = raw[u] < 0.f ? 0.f : lut[ci][(int)raw[u]];
+      }
     }
   } else {
     const float* ib = reinterpret_cast<const float*>(img_) + (int64_t)b * 3 * H * W;
-    for (int i = tid; i < PR * PR * 3; i += 256) {
+    bool inb[NIT];
+#pragma unroll
+    for (int u = 0; u < NIT; ++u) {
+      const int i = tid + u * 256;
       const int c = i % PR, r = (i / PR) % PR, ci = i / (PR * PR);
       const int hi = hi0 + r, wi = wi0 + c;
-      float v = 0.f;
-      if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = (ib[((int64_t)ci * H + hi) * W + wi] - mean[ci]) / stdv[ci];
-      sin_[ci][r][c & 1][c >> 1] = v;
+      inb[u] = i < NP && hi >= 0 && hi < H && wi >= 0 && wi < W;
+      raw[u] = inb[u] ? ib[((int64_t)ci * H + hi) * W + wi] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < NIT; ++u) {
+      const int i = tid + u * 256;
+      if (i < NP) {
+        const int c = i % PR, r = (i / PR) % PR, ci = i / (PR * PR);
+        sin_[ci][r][c & 1][c >> 1] = inb[u] ? (raw[u] - mean[ci]) / stdv[ci] : 0.f;
+      }
     }
   }
   __syncthreads();
@@ -157,19 +191,30 @@ __global__ void __launch_bounds__(256) stem_conv_tiled_kernel(const void* __rest
   const int ho = ho0 + ty, wo = wo0 + tx;
   if (ho >= Ho || wo >= Wo) return;
   const int64_t pix = ((int64_t)b * Ho + ho) * Wo + wo;
-  if (act & 256) {  // FB200_F16PAIR output: [hi(32) | lo(32)] fp16 per pixel
+  // folded BN + activation with the activation switch OUTSIDE the element loop (a per-element switch on the runtime `act` was a third of the kernel's instructions)
+#pragma unroll
+  for (int co = 0; co < COUT; ++co) acc[co] = acc[co] * sc[co] + bi[co];
+  if constexpr (RELU) {
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc[co] = fmaxf(acc[co], 0.f);
+  } else if ((act & 15) != FB200_ACT_NONE) {
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc[co] = apply_act(acc[co], act);
+  }
+  if (act & 256) {  // FB200_F16PAIR output: [hi(32) | lo(32)] fp16 per pixel, written as 16-byte vectors (8 halves): half the store instructions of 8-byte pieces
     __half* o = reinterpret_cast<__half*>(out) + pix * 2 * COUT;
 #pragma unroll
-    for (int co = 0; co < COUT; co += 4) {
-      float v[4], h[4], l[4];
+    for (int co = 0; co < COUT; co += 8) {
+      __half2 h2[4], l2[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        v[j] = apply_act(acc[co + j] * sc[co + j] + bi[co + j], act);
-        h[j] = __half2float(__float2half_rn(v[j]));
-        l[j] = v[j] - h[j];
+        const float v0 = acc[co + 2 * j], v1 = acc[co + 2 * j + 1];
+        const __half a0 = __float2half_rn(v0), a1 = __float2half_rn(v1);
+        h2[j] = __halves2half2(a0, a1);
+        l2[j] = __halves2half2(__float2half_rn(v0 - __half2float(a0)), __float2half_rn(v1 - __half2float(a1)));
       }
-      store4(o + co, h);
-      store4(o + COUT + co, l);
+      *reinterpret_cast<uint4*>(o + co) = *reinterpret_cast<const uint4*>(h2);
+      *reinterpret_cast<uint4*>(o + COUT + co) = *reinterpret_cast<const uint4*>(l2);
     }
     return;
   }
@@ -178,7 +223,7 @@ __global__ void __launch_bounds__(256) stem_conv_tiled_kernel(const void* __rest
   for (int co = 0; co < COUT; co += 4) {
     float v[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = apply_act(acc[co + j] * sc[co + j] + bi[co + j], act);
+    for (int j = 0; j < 4; ++j) v[j] = acc[co + j];
     store4(o + co, v);
   }
 }
@@ -357,7 +402,8 @@ static int stem_launch(const void* img, bool u8, int B, int H, int W, const floa
   const unsigned grid = tiled ? (unsigned)((int64_t)B * tiles_w * tiles_h) : (unsigned)cdiv(total, 128);
 #define STEM_LAUNCH(T, U8)                                                                                                                                              \
   do {                                                                                                                                                                  \
-    if (tiled) stem_conv_tiled_kernel<T, U8><<<grid, 256, 0, st>>>(img, B, H, W, w, scale, bias, m[0], m[1], m[2], s[0], s[1], s[2], act, (T*)out, tiles_w, tiles_h);   \
+    if (tiled && (act & 15) == FB200_ACT_RELU) stem_conv_tiled_kernel<T, U8, true><<<grid, 256, 0, st>>>(img, B, H, W, w, scale, bias, m[0], m[1], m[2], s[0], s[1], s[2], act, (T*)out, tiles_w, tiles_h);   \
+    else if (tiled) stem_conv_tiled_kernel<T, U8, false><<<grid, 256, 0, st>>>(img, B, H, W, w, scale, bias, m[0], m[1], m[2], s[0], s[1], s[2], act, (T*)out, tiles_w, tiles_h);   \
     else stem_conv_kernel<T, 32, U8><<<grid, 128, 0, st>>>(img, B, H, W, w, scale, bias, m[0], m[1], m[2], s[0], s[1], s[2], act, (T*)out);                              \
   } while (0)
   if (out_dtype == FB200_F32) { if (u8) STEM_LAUNCH(float, true); else STEM_LAUNCH(float, false); }
