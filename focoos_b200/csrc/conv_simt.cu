@@ -228,6 +228,117 @@ __global__ void __launch_bounds__(256) stem_conv_tiled_kernel(const void* __rest
   }
 }
 
+// Two output pixels per thread (rows ty and ty + 8 of the 16 x 16 tile, 128 threads): every float4 weight broadcast feeds 8 FMAs instead of 4 and the per-thread
+// preamble / epilogue instructions are shared by two pixels - the one-pixel kernel above is instruction-bound (2184 SASS instructions per pixel for 864 FMAs).
+// uint8 NHWC input + ReLU only (the deployment path of all three model families); PAIR selects the [hi(32) | lo(32)] fp16 output.
+template <typename TOut, bool PAIR>
+__global__ void __launch_bounds__(128) stem_conv_tiled2_kernel(const uint8_t* __restrict__ img, int B, int H, int W, const float* __restrict__ w,
+                                                               const float* __restrict__ scale, const float* __restrict__ bias, float m0, float m1, float m2, float s0,
+                                                               float s1, float s2, TOut* __restrict__ out, int tiles_w, int tiles_h) {
+  constexpr int COUT = 32, T = 16, PR = 2 * T + 1, HC = T + 1, NT = 128, RB = PR * 3;
+  __shared__ __align__(16) float ws[27 * COUT];
+  __shared__ float sc[COUT], bi[COUT];
+  __shared__ float lut[3][256];
+  __shared__ float sin_[3][PR][2][HC + 3];  // two patch rows = 80 floats = 16 banks apart: the two half-warps (rows ty, ty + 1) do not collide
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 27 * COUT; i += NT) { const int co = i % COUT, t = i / COUT; ws[i] = w[co * 27 + t]; }
+  if (tid < COUT) { sc[tid] = scale ? scale[tid] : 1.f; bi[tid] = bias ? bias[tid] : 0.f; }
+#pragma unroll
+  for (int v = tid; v < 256; v += NT) { lut[0][v] = ((float)v - m0) / s0; lut[1][v] = ((float)v - m1) / s1; lut[2][v] = ((float)v - m2) / s2; }
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  int t = blockIdx.x;
+  const int tw = t % tiles_w; t /= tiles_w;
+  const int th = t % tiles_h; const int b = t / tiles_h;
+  const int ho0 = th * T, wo0 = tw * T;
+  const int hi0 = 2 * ho0 - 1, wi0 = 2 * wo0 - 1;
+  const uint8_t* ub = img + (int64_t)b * H * W * 3;
+  __syncthreads();  // the table
+  {  // patch: element i = r * 99 + j, two batches of 13 loads per thread, each batch issued before it is consumed (128 = 99 + 29)
+    constexpr int NB = 13;
+    int r = tid / RB, j = tid - r * RB;
+#pragma unroll
+    for (int batch = 0; batch < 2; ++batch) {
+      float raw[NB];
+      int rr[NB], jj[NB];
+#pragma unroll
+      for (int u = 0; u < NB; ++u) {
+        rr[u] = r; jj[u] = j;
+        const int c = j / 3, hi = hi0 + r, wi = wi0 + c;
+        raw[u] = -1.f;
+        if (r < PR && hi >= 0 && hi < H && wi >= 0 && wi < W) raw[u] = (float)ub[(hi * W + wi0) * 3 + j];
+        j += NT - RB; r += 1;
+        if (j >= RB) { j -= RB; r += 1; }
+      }
+#pragma unroll
+      for (int u = 0; u < NB; ++u) {
+        if (rr[u] < PR) {
+          const int c = jj[u] / 3, ci = jj[u] - 3 * c;
+          sin_[ci][rr[u]][c & 1][c >> 1] = raw[u] < 0.f ? 0.f : lut[ci][(int)raw[u]];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  const int tx = lane & 15, ty = warp * 2 + (lane >> 4);   // rows ty and ty + 8
+  float acc[2][COUT];
+#pragma unroll
+  for (int i = 0; i < COUT; ++i) { acc[0][i] = 0.f; acc[1][i] = 0.f; }
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        const float v0 = sin_[ci][2 * ty + kh][kw & 1][tx + (kw >> 1)];
+        const float v1 = sin_[ci][2 * (ty + 8) + kh][kw & 1][tx + (kw >> 1)];
+        const float4* wr = reinterpret_cast<const float4*>(&ws[((kh * 3 + kw) * 3 + ci) * COUT]);
+#pragma unroll
+        for (int q = 0; q < COUT / 4; ++q) {
+          const float4 wv = wr[q];
+          acc[0][q * 4 + 0] = fmaf(v0, wv.x, acc[0][q * 4 + 0]); acc[0][q * 4 + 1] = fmaf(v0, wv.y, acc[0][q * 4 + 1]);
+          acc[0][q * 4 + 2] = fmaf(v0, wv.z, acc[0][q * 4 + 2]); acc[0][q * 4 + 3] = fmaf(v0, wv.w, acc[0][q * 4 + 3]);
+          acc[1][q * 4 + 0] = fmaf(v1, wv.x, acc[1][q * 4 + 0]); acc[1][q * 4 + 1] = fmaf(v1, wv.y, acc[1][q * 4 + 1]);
+          acc[1][q * 4 + 2] = fmaf(v1, wv.z, acc[1][q * 4 + 2]); acc[1][q * 4 + 3] = fmaf(v1, wv.w, acc[1][q * 4 + 3]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int px = 0; px < 2; ++px) {
+    const int ho = ho0 + ty + 8 * px, wo = wo0 + tx;
+    if (ho >= Ho || wo >= Wo) continue;
+    const int64_t pix = ((int64_t)b * Ho + ho) * Wo + wo;
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc[px][co] = fmaxf(acc[px][co] * sc[co] + bi[co], 0.f);
+    if constexpr (PAIR) {
+      __half* o = reinterpret_cast<__half*>(out) + pix * 2 * COUT;
+#pragma unroll
+      for (int co = 0; co < COUT; co += 8) {
+        __half2 h2[4], l2[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float v0 = acc[px][co + 2 * j], v1 = acc[px][co + 2 * j + 1];
+          const __half a0 = __float2half_rn(v0), a1 = __float2half_rn(v1);
+          h2[j] = __halves2half2(a0, a1);
+          l2[j] = __halves2half2(__float2half_rn(v0 - __half2float(a0)), __float2half_rn(v1 - __half2float(a1)));
+        }
+        *reinterpret_cast<uint4*>(o + co) = *reinterpret_cast<const uint4*>(h2);
+        *reinterpret_cast<uint4*>(o + COUT + co) = *reinterpret_cast<const uint4*>(l2);
+      }
+    } else {
+      TOut* o = out + pix * COUT;
+#pragma unroll
+      for (int co = 0; co < COUT; co += 4) {
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = acc[px][co + j];
+        store4(o + co, v);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // generic implicit GEMM.  M = B*Ho*Wo, N = Cout, K = KH*KW*Cin (k = (kh*KW+kw)*Cin + c).
 // 64x64x16 tile, 256 threads, 4x4 micro-tile, register-prefetch double buffering.
@@ -397,12 +508,15 @@ static int stem_launch(const void* img, bool u8, int B, int H, int W, const floa
   cudaStream_t st = (cudaStream_t)stream;
   const float* m = mean3; const float* s = std3;  // HOST pointers (3 floats each)
   const int tiles_w = (Wo + 15) / 16, tiles_h = (Ho + 15) / 16;
-  static int tiled = -1;  // FB200_STEM_TILED=0: the per-pixel kernel (A/B)
-  if (tiled < 0) { const char* e = getenv("FB200_STEM_TILED"); tiled = e ? atoi(e) : 1; }
+  static int tiled = -1;  // FB200_STEM_TILED: 0 = the per-pixel kernel, 1 = the tiled one-pixel-per-thread kernel, 2 (default) = two pixels per thread where it applies (A/B)
+  if (tiled < 0) { const char* e = getenv("FB200_STEM_TILED"); tiled = e ? atoi(e) : 2; }
   const unsigned grid = tiled ? (unsigned)((int64_t)B * tiles_w * tiles_h) : (unsigned)cdiv(total, 128);
 #define STEM_LAUNCH(T, U8)                                                                                                                                              \
   do {                                                                                                                                                                  \
-    if (tiled && (act & 15) == FB200_ACT_RELU) stem_conv_tiled_kernel<T, U8, true><<<grid, 256, 0, st>>>(img, B, H, W, w, scale, bias, m[0], m[1], m[2], s[0], s[1], s[2], act, (T*)out, tiles_w, tiles_h);   \
+    if (tiled == 2 && U8 && (act & 15) == FB200_ACT_RELU) {                                                                                                               \
+      if (act & 256) stem_conv_tiled2_kernel<T, true><<<grid, 128, 0, st>>>((const uint8_t*)img, B, H, W, w, scale, bias, m[0], m[1], m[2], s[0], s[1], s[2], (T*)out, tiles_w, tiles_h);   \
+      else stem_conv_tiled2_kernel<T, false><<<grid, 128, 0, st>>>((const uint8_t*)img, B, H, W, w, scale, bias, m[0], m[1], m[2], s[0], s[1], s[2], (T*)out, tiles_w, tiles_h);           \
+    } else if (tiled && (act & 15) == FB200_ACT_RELU) stem_conv_tiled_kernel<T, U8, true><<<grid, 256, 0, st>>>(img, B, H, W, w, scale, bias, m[0], m[1], m[2], s[0], s[1], s[2], act, (T*)out, tiles_w, tiles_h);   \
     else if (tiled) stem_conv_tiled_kernel<T, U8, false><<<grid, 256, 0, st>>>(img, B, H, W, w, scale, bias, m[0], m[1], m[2], s[0], s[1], s[2], act, (T*)out, tiles_w, tiles_h);   \
     else stem_conv_kernel<T, 32, U8><<<grid, 128, 0, st>>>(img, B, H, W, w, scale, bias, m[0], m[1], m[2], s[0], s[1], s[2], act, (T*)out);                              \
   } while (0)
