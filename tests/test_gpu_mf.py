@@ -281,3 +281,23 @@ def test_mf_full_size_batch_invariance_and_oracle():
     if len(ref.detections):
         assert np.abs(np.array([d.conf for d in got.detections]) - np.array([d.conf for d in ref.detections])).max() < 1e-3
         assert np.abs(np.array([d.bbox for d in got.detections]) - np.array([d.bbox for d in ref.detections])).max() <= 3
+
+
+@pytest.mark.parametrize("name,manifest,size", [("fai-mf-l-coco-ins", "fai_mf_l_coco_ins", (320, 416)), ("bisenetformer-l-ade", "bisenetformer_l_ade", (256, 384))])
+def test_focoos_model_fp32_tc_graph_replay_equals_eager(name, manifest, size):
+    """The public path in the parity-green mode: ModelManager.get(..., precision="fp32_tc") -> FocoosModel.__call__ on a pinned uint8 batch.  The first call runs eagerly, the
+    following ones replay the captured CUDA graph (pair-native backbone, split tensor-core mask GEMM and masked attention inside): identical detections every time, and
+    equal to model.forward + processor.postprocess."""
+    from focoos_b200 import ModelManager
+
+    sd = seeded_state_dict(manifest_template(manifest), 0)
+    fm = ModelManager.get(name, state_dict=sd, precision="fp32_tc")
+    fm.model.cuda()
+    imgs = synth_images(9, [size, size])
+    runs = [fm(imgs, threshold=0.5, batched=True) for _ in range(3)]
+    x = torch.stack([torch.from_numpy(im).permute(2, 0, 1).float() for im in imgs]).cuda()
+    ref = fm.processor.postprocess(fm.model(x), imgs, threshold=0.5)
+    key = lambda dets: [[(d.cls_id, tuple(d.bbox), d.mask) for d in r.detections] for r in dets]  # noqa: E731
+    assert key(runs[0]) == key(runs[1]) == key(runs[2]) == key(ref)
+    for a, b in zip(runs[2], ref):
+        assert np.allclose([d.conf for d in a.detections], [d.conf for d in b.detections], atol=1e-6)
