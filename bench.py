@@ -435,10 +435,17 @@ def main():
             keys = ("value", "unit", "n_gpus", "ms_per_step", "steps", "warmup", "scaling", "dtype", "precision", "config", "kernel_launches_per_step", "phases_ms", "peak_mem_GB")
             # the reference's TrainerArgs.amp_enabled defaults to True (ports.py:1029): its iteration runs under torch.autocast(fp16) + GradScaler, so the config-5 number is
             # the "amp" precision (one fp16 tensor-core product, fp32 accumulation / storage); the fp32-accurate (three-product) step is reported next to it
-            t_amp = bench_train.run_leg(batch=16, size=640, steps=4, warmup=2, precision="amp", by_symbol=False)
+            # several ranks: BatchNorm statistics over ALL ranks, like the reference (trainer/trainer.py:333-334 converts every BatchNorm to SyncBatchNorm whenever
+            # world_size > 1); the step with per-rank statistics is reported next to it
+            sync = world > 1
+            t_amp = bench_train.run_leg(batch=16, size=640, steps=4, warmup=2, precision="amp", by_symbol=False, sync_bn=sync)
             train = {k: t_amp[k] for k in keys if k in t_amp}
-            t_acc = bench_train.run_leg(batch=16, size=640, steps=2, warmup=1, precision="fp32_tc", by_symbol=False)
-            train["fp32_accurate"] = {k: t_acc[k] for k in ("value", "ms_per_step", "steps", "warmup", "dtype", "precision", "phases_ms", "peak_mem_GB") if k in t_acc}
+            sub = ("value", "ms_per_step", "steps", "warmup", "dtype", "precision", "phases_ms", "peak_mem_GB")
+            if sync:
+                t_loc = bench_train.run_leg(batch=16, size=640, steps=2, warmup=1, precision="amp", by_symbol=False, sync_bn=False)
+                train["local_batchnorm"] = {k: t_loc[k] for k in sub if k in t_loc}
+            t_acc = bench_train.run_leg(batch=16, size=640, steps=2, warmup=1, precision="fp32_tc", by_symbol=False, sync_bn=sync)
+            train["fp32_accurate"] = {k: t_acc[k] for k in sub if k in t_acc}
         except Exception as e:  # noqa: BLE001
             train = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
 

@@ -29,7 +29,7 @@ from . import ops
 from .ops import CudaBackend, _p, _stream
 
 ops.EXPORTED_SYMBOLS = ops.EXPORTED_SYMBOLS + (
-    "fb200_conv_wgrad_workspace_bytes", "fb200_conv_wgrad", "fb200_conv_wgrad_tc_supported", "fb200_conv_wgrad_tc_workspace_bytes", "fb200_conv_wgrad_tc", "fb200_conv_wgrad_tc_f16", "fb200_dilate2", "fb200_col_workspace_bytes", "fb200_colsum", "fb200_bn_train_fwd", "fb200_bn_train_bwd", "fb200_bn_stats", "fb200_bn_apply", "fb200_bn_bwd_reduce", "fb200_bn_bwd_apply",
+    "fb200_conv_wgrad_workspace_bytes", "fb200_conv_wgrad", "fb200_conv_wgrad_tc_supported", "fb200_conv_wgrad_tc_workspace_bytes", "fb200_conv_wgrad_tc", "fb200_conv_wgrad_tc_f16", "fb200_dilate2", "fb200_col_workspace_bytes", "fb200_colsum", "fb200_bn_train_fwd", "fb200_bn_train_bwd", "fb200_bn_stats", "fb200_bn_sync_combine", "fb200_bn_apply", "fb200_bn_bwd_reduce", "fb200_bn_bwd_apply",
     "fb200_add_act", "fb200_maxpool3x3s2_bwd", "fb200_avgpool2x2_ceil_bwd", "fb200_resize_bilinear_bwd", "fb200_layernorm_bwd", "fb200_attention_bwd", "fb200_msda_bwd")
 
 _f = ctypes.c_float
@@ -111,6 +111,12 @@ def _cb_bn_stats(self, x2d, mean, var):
     self._call("fb200_bn_stats", _p(x2d), x2d.stride(0), ctypes.c_int64(R), C, _p(mean), _p(var), _p(_col_ws(self, C, x2d.device)), _stream())
 
 
+def _cb_bn_sync_combine(self, allst, eps, momentum, rmean, rvar, mean, rstd, inv_total):
+    self._cuda(allst, mean, rstd, inv_total)
+    world, width = allst.shape
+    self._call("fb200_bn_sync_combine", _p(allst), world, (width - 1) // 2, _f(eps), _f(momentum), _p(rmean), _p(rvar), _p(mean), _p(rstd), _p(inv_total), _stream())
+
+
 def _cb_bn_apply(self, x2d, mean, rstd, gamma, beta, res2d, act, y2d):
     self._cuda(x2d, mean, rstd, gamma, beta, y2d)
     R, C = x2d.shape
@@ -179,7 +185,7 @@ def _cb_msda_bwd(self, value, oa, ref, do, shapes, P, heads, dvalue, doa):
 
 
 for _n, _fn in (("conv_wgrad", _cb_conv_wgrad), ("conv_wgrad_tc_supported", _cb_conv_wgrad_tc_supported), ("conv_wgrad_tc", _cb_conv_wgrad_tc), ("conv_wgrad_tc_f16", _cb_conv_wgrad_tc_f16), ("dilate2", _cb_dilate2), ("colsum", _cb_colsum), ("bn_train_fwd", _cb_bn_train_fwd), ("bn_train_bwd", _cb_bn_train_bwd),
-                ("bn_stats", _cb_bn_stats), ("bn_apply", _cb_bn_apply), ("bn_bwd_reduce", _cb_bn_bwd_reduce), ("bn_bwd_apply", _cb_bn_bwd_apply),
+                ("bn_stats", _cb_bn_stats), ("bn_sync_combine", _cb_bn_sync_combine), ("bn_apply", _cb_bn_apply), ("bn_bwd_reduce", _cb_bn_bwd_reduce), ("bn_bwd_apply", _cb_bn_bwd_apply),
                 ("add_act", _cb_add_act), ("maxpool_bwd", _cb_maxpool_bwd), ("avgpool_bwd", _cb_avgpool_bwd), ("resize_bwd", _cb_resize_bwd),
                 ("layernorm_bwd", _cb_layernorm_bwd), ("attention_bwd", _cb_attention_bwd), ("msda_bwd", _cb_msda_bwd)):
     setattr(CudaBackend, _n, _fn)
@@ -345,31 +351,27 @@ class SyncBatchNormTrainFn(torch.autograd.Function):
         be = ops._be()
         stats = torch.empty((2 * C + 1,), dtype=torch.float32, device=x.device)
         be.bn_stats(x2, stats[:C], stats[C:2 * C])
-        stats[2 * C] = float(x2.shape[0])
+        stats[2 * C:].fill_(float(x2.shape[0]))  # a fill kernel: no host -> device copy in the middle of the launch stream
         world = dist.get_world_size(group)
-        allst = torch.empty((world * (2 * C + 1),), dtype=torch.float32, device=x.device)
-        dist.all_gather_into_tensor(allst, stats, group=group)
-        allst = allst.view(world, 2 * C + 1)
-        n = allst[:, 2 * C:2 * C + 1]                                  # [world, 1]
-        total = n.sum()
-        mean = (allst[:, :C] * n).sum(0) / total
-        var = ((allst[:, C:2 * C] + (allst[:, :C] - mean) ** 2) * n).sum(0) / total
-        rstd = torch.rsqrt(var + eps)
-        with torch.no_grad():  # running statistics: unbiased variance over the GLOBAL count
-            running_mean.mul_(1 - momentum).add_(mean, alpha=momentum)
-            running_var.mul_(1 - momentum).add_(var * (total / (total - 1).clamp(min=1)), alpha=momentum)
+        allst = torch.empty((world, 2 * C + 1), dtype=torch.float32, device=x.device)
+        dist.all_gather_into_tensor(allst.view(-1), stats, group=group)
+        mean = torch.empty(C, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(C, dtype=torch.float32, device=x.device)
+        inv_total = torch.empty(1, dtype=torch.float32, device=x.device)
+        # global moments, running statistics (unbiased variance over the GLOBAL count) and 1 / total in one launch; nothing of it is read back by the host
+        be.bn_sync_combine(allst, eps, momentum, running_mean, running_var, mean, rstd, inv_total)
         y = torch.empty_like(x)
         r2 = None if res is None else res.contiguous().reshape(-1, C)
         be.bn_apply(x2, mean, rstd, gamma, beta, r2, act, y.reshape(-1, C))
-        ctx.save_for_backward(x, gamma, beta, mean, rstd, y if (act != ops.ACT_NONE and res is not None) else None)
-        ctx.cfg = (act, res is not None, group, float(total))
+        ctx.save_for_backward(x, gamma, beta, mean, rstd, y if (act != ops.ACT_NONE and res is not None) else None, inv_total)
+        ctx.cfg = (act, res is not None, group)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         import torch.distributed as dist
-        x, gamma, beta, mean, rstd, y = ctx.saved_tensors
-        act, has_res, group, total = ctx.cfg
+        x, gamma, beta, mean, rstd, y, inv_total = ctx.saved_tensors
+        act, has_res, group = ctx.cfg
         C = x.shape[-1]
         dy = dy.contiguous()
         be = ops._be()
@@ -378,9 +380,10 @@ class SyncBatchNormTrainFn(torch.autograd.Function):
         be.bn_bwd_reduce(x.reshape(-1, C), dy.reshape(-1, C), y2, gamma, beta, mean, rstd, act, sums[0], sums[1])
         local = sums.clone()
         dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+        sums.mul_(inv_total)  # the global sums over the global row count, scaled on the device (the kernel's own factor is 1): sum * (1 / total) is the same product it forms
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if has_res else None
-        be.bn_bwd_apply(x.reshape(-1, C), dy.reshape(-1, C), y2, gamma, beta, mean, rstd, sums[0], sums[1], 1.0 / total, act, dx.reshape(-1, C),
+        be.bn_bwd_apply(x.reshape(-1, C), dy.reshape(-1, C), y2, gamma, beta, mean, rstd, sums[0], sums[1], 1.0, act, dx.reshape(-1, C),
                         None if dres is None else dres.reshape(-1, C))
         return dx, local[1], local[0], None, None, dres, None, None, None, None
 

@@ -883,6 +883,43 @@ extern "C" int fb200_bn_stats(const float* x, int x_pitch, int64_t R, int C, flo
   return FB200_OK;
 }
 
+// SyncBatchNorm: combine the per-rank moments gathered by all_gather (row r = [mean_r (C) | biased var_r (C) | row count n_r]) into the global mean / rstd, update the
+// running statistics (unbiased variance over the GLOBAL count, like aten's batch_norm_gather_stats_with_counts) and leave 1 / total on the device for the backward pass -
+// one launch instead of a dozen small torch kernels and two host read-backs per layer
+__global__ void bn_sync_combine_kernel(const float* __restrict__ allst, int world, int C, float eps, float momentum, float* __restrict__ run_mean,
+                                       float* __restrict__ run_var, float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ inv_total) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int pitch = 2 * C + 1;
+  double total = 0.0;
+  for (int r = 0; r < world; ++r) total += (double)allst[(int64_t)r * pitch + 2 * C];
+  if (c == 0) inv_total[0] = (float)(1.0 / total);
+  if (c >= C) return;
+  double m = 0.0;
+  for (int r = 0; r < world; ++r) m += (double)allst[(int64_t)r * pitch + c] * (double)allst[(int64_t)r * pitch + 2 * C];
+  m /= total;
+  double v = 0.0;
+  for (int r = 0; r < world; ++r) {
+    const double d = (double)allst[(int64_t)r * pitch + c] - m;
+    v += ((double)allst[(int64_t)r * pitch + C + c] + d * d) * (double)allst[(int64_t)r * pitch + 2 * C];
+  }
+  v /= total;
+  mean[c] = (float)m;
+  rstd[c] = (float)(1.0 / sqrt(v + (double)eps));
+  if (run_mean) {
+    run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * (float)m;
+    run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)(total > 1.0 ? v * total / (total - 1.0) : v);
+  }
+}
+
+extern "C" int fb200_bn_sync_combine(const float* all_stats, int world, int C, float eps, float momentum, float* running_mean, float* running_var, float* mean,
+                                     float* rstd, float* inv_total, void* stream) {
+  FB_CHECK_ARG(all_stats && mean && rstd && inv_total && world > 0 && C > 0, "bn_sync_combine: bad arguments");
+  FB_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "bn_sync_combine: running_mean and running_var go together");
+  bn_sync_combine_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(all_stats, world, C, eps, momentum, running_mean, running_var, mean, rstd, inv_total);
+  FB_CHECK_LAUNCH("bn_sync_combine");
+  return FB200_OK;
+}
+
 extern "C" int fb200_bn_apply(const float* x, int x_pitch, int64_t R, int C, const float* mean, const float* rstd, const float* gamma, const float* beta,
                               const float* res, int res_pitch, int act, float* y, int y_pitch, void* stream) {
   FB_CHECK_ARG(x && mean && rstd && gamma && beta && y && R > 0 && C % 4 == 0, "bn_apply: bad arguments");

@@ -364,6 +364,11 @@ int fb200_bn_train_bwd(const float* x, int x_pitch, const float* dy, int dy_pitc
  *     fb200_bn_bwd_apply forms dx with the global sums and inv_count = 1 / total rows;
  *   FrozenBatchNorm2d (nn/backbone/resnet.py:226-250, TrainerArgs.freeze_bn): fb200_bn_apply with the RUNNING statistics, fb200_bn_bwd_apply with zero sums. */
 int fb200_bn_stats(const float* x, int x_pitch, int64_t R, int C, float* mean, float* var_biased, void* workspace, void* stream);
+/* SyncBatchNorm, between the all_gather of the per-rank statistics and fb200_bn_apply: all_stats [world][2C+1] = rows [mean (C) | biased variance (C) | row count] ->
+ * global mean / rstd, running statistics updated with the unbiased variance over the global count (aten batch_norm_gather_stats_with_counts), and inv_total[0] = 1 / (sum of
+ * the row counts) left on the device for the backward pass (no host read-back between two layers). */
+int fb200_bn_sync_combine(const float* all_stats, int world, int C, float eps, float momentum, float* running_mean, float* running_var, float* mean, float* rstd,
+                          float* inv_total, void* stream);
 int fb200_bn_apply(const float* x, int x_pitch, int64_t R, int C, const float* mean, const float* rstd, const float* gamma, const float* beta,
                    const float* res, int res_pitch, int act, float* y, int y_pitch, void* stream);
 int fb200_bn_bwd_reduce(const float* x, int x_pitch, const float* dy, int dy_pitch, const float* y, int y_pitch, int64_t R, int C, const float* gamma,

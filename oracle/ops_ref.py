@@ -589,6 +589,22 @@ def _rb_bn_stats(self, x2d, mean, var):
     var.copy_(((x2d.double() - m) ** 2).mean(0).float())
 
 
+def _rb_bn_sync_combine(self, allst, eps, momentum, rmean, rvar, mean, rstd, inv_total):
+    """fb200_bn_sync_combine: aten batch_norm_gather_stats_with_counts on the gathered [world, 2C+1] rows"""
+    C = (allst.shape[1] - 1) // 2
+    a = allst.double()
+    n = a[:, 2 * C:2 * C + 1]
+    total = n.sum()
+    m = (a[:, :C] * n).sum(0) / total
+    v = ((a[:, C:2 * C] + (a[:, :C] - m) ** 2) * n).sum(0) / total
+    mean.copy_(m.float())
+    rstd.copy_((1.0 / torch.sqrt(v + eps)).float())
+    inv_total.copy_((1.0 / total).float().reshape(1))
+    if rmean is not None:
+        rmean.mul_(1 - momentum).add_(m.float(), alpha=momentum)
+        rvar.mul_(1 - momentum).add_((v * total / (total - 1).clamp(min=1)).float(), alpha=momentum)
+
+
 def _rb_bn_apply(self, x2d, mean, rstd, gamma, beta, res2d, act, y2d):
     z = (x2d - mean) * rstd * gamma + beta
     if res2d is not None:
@@ -692,7 +708,7 @@ def _rb_msda_bwd(self, value, oa, ref, do, shapes, P, heads, dvalue, doa):
 
 
 for _n, _f in (("conv_wgrad", _rb_conv_wgrad), ("conv_wgrad_tc_supported", _rb_conv_wgrad_tc_supported), ("conv_wgrad_tc", _rb_conv_wgrad_tc), ("conv_wgrad_tc_f16", _rb_conv_wgrad_tc_f16), ("dilate2", _rb_dilate2), ("colsum", _rb_colsum), ("bn_train_fwd", _rb_bn_train_fwd), ("bn_train_bwd", _rb_bn_train_bwd),
-               ("bn_stats", _rb_bn_stats), ("bn_apply", _rb_bn_apply), ("bn_bwd_reduce", _rb_bn_bwd_reduce), ("bn_bwd_apply", _rb_bn_bwd_apply),
+               ("bn_stats", _rb_bn_stats), ("bn_sync_combine", _rb_bn_sync_combine), ("bn_apply", _rb_bn_apply), ("bn_bwd_reduce", _rb_bn_bwd_reduce), ("bn_bwd_apply", _rb_bn_bwd_apply),
                ("add_act", _rb_add_act), ("maxpool_bwd", _rb_maxpool_bwd), ("avgpool_bwd", _rb_avgpool_bwd), ("resize_bwd", _rb_resize_bwd),
                ("layernorm_bwd", _rb_layernorm_bwd), ("attention_bwd", _rb_attention_bwd), ("msda_bwd", _rb_msda_bwd)):
     setattr(RefBackend, _n, _f)
