@@ -199,6 +199,11 @@ def _split3_weights(w):
     return torch.cat([hi, lo, hi], dim=-1).contiguous()
 
 
+def _to_half_contiguous(t):
+    """fp16, contiguous copy of a (possibly permuted) fp32 view in ONE copy kernel (cast + layout change) - `.contiguous().half()` is two"""
+    return torch.empty(t.shape, dtype=torch.float16, device=t.device).copy_(t)
+
+
 def conv_any(x, w_khwc, bias, stride: int, pad: int, precision: str, act=ops.ACT_NONE, x_pair=None, return_pair=False):
     """x NHWC fp32, w [Cout,KH,KW,Cin] fp32 -> NHWC fp32 through the SIMT fp32 or the split-precision tcgen05 kernel.
     x_pair: the [hi|lo] fp16 pair of x if the caller already has it; return_pair: also return the pair used (None on the SIMT path)."""
@@ -210,12 +215,15 @@ def conv_any(x, w_khwc, bias, stride: int, pad: int, precision: str, act=ops.ACT
           and KH == KW and geom and act in (ops.ACT_NONE, ops.ACT_RELU, ops.ACT_SILU))
     if ok and precision == "amp":  # fp16 operands (x_pair carries the fp16 copy of x when the caller already has it), one product, fp32 out
         x16 = x_pair if x_pair is not None else x.half()
-        y = ops.conv2d(x16, w_khwc.half(), None, bias, stride=stride, pad=pad, act=act, out_dtype=torch.float32, algo=ops.ALGO_TCGEN05)
+        w16 = w_khwc if w_khwc.dtype == torch.float16 else _to_half_contiguous(w_khwc)
+        y = ops.conv2d(x16, w16, None, bias, stride=stride, pad=pad, act=act, out_dtype=torch.float32, algo=ops.ALGO_TCGEN05)
         return (y, x16) if return_pair else y
     if ok:
         xp = x_pair if x_pair is not None else ops.split_pair(x)
         y = ops.conv2d(xp, _split3_weights(w_khwc), None, bias, stride=stride, pad=pad, act=act, out_dtype=torch.float32, algo=ops.ALGO_TCGEN05_SPLIT3)
         return (y, xp) if return_pair else y
+    if w_khwc.dtype != x.dtype:  # an "amp" caller packed the weight in fp16 but the shape does not take the tensor-core path: the CUDA-core kernel wants one dtype
+        w_khwc = w_khwc.to(x.dtype)
     if C % 4:  # the 3-channel image: zero-pad the channel dimension (the SIMT kernel reads 16-byte vectors)
         padc = 4 - C % 4
         x = torch.nn.functional.pad(x, (0, padc))
@@ -261,7 +269,9 @@ class Conv2dFn(torch.autograd.Function):
     def forward(ctx, x, w, bias, stride, pad, precision):
         x = x.contiguous()
         Cout, _, KH, KW = w.shape
-        y, xp = conv_any(x, w.permute(0, 2, 3, 1).contiguous(), bias, stride, pad, precision, return_pair=True)
+        wk = w.permute(0, 2, 3, 1)
+        wk = _to_half_contiguous(wk) if (precision == "amp" and x.shape[-1] % 32 == 0) else wk.contiguous()  # amp: the packed weight straight in fp16 (one kernel)
+        y, xp = conv_any(x, wk, bias, stride, pad, precision, return_pair=True)
         keep_pair = xp is not None and wgrad_on_tensor_cores(x.shape, y.shape, KH, KW, stride, pad, precision)
         ctx.save_for_backward(xp if keep_pair else x, w)
         ctx.cfg = (stride, pad, precision, bias is not None, keep_pair, tuple(x.shape))
@@ -281,7 +291,8 @@ class Conv2dFn(torch.autograd.Function):
             dyp = tc_operand(dy, precision)  # shared by the data-gradient conv and the weight-gradient GEMM
         if ctx.needs_input_grad[0]:
             # data gradient: correlation of (dilated) dy with the spatially flipped, in/out-transposed filter
-            wt = w.flip(2, 3).permute(1, 2, 3, 0).contiguous()  # [Cin,KH,KW,Cout]
+            wsrc = (w if KH == 1 and KW == 1 else w.flip(2, 3)).permute(1, 2, 3, 0)  # [Cin,KH,KW,Cout] (a 1x1 filter has nothing to flip)
+            wt = _to_half_contiguous(wsrc) if (precision == "amp" and Cout % 32 == 0) else wsrc.contiguous()
             g, gp = dy, dyp
             if stride == 2:
                 Hd, Wd = H + 2 * pad - KH + 1, W + 2 * pad - KW + 1
@@ -449,7 +460,9 @@ class LinearFn(torch.autograd.Function):
         x = x.contiguous()
         K, N = x.shape[-1], w.shape[0]
         x4 = x.reshape(1, 1, -1, K)
-        y4, xp = conv_any(x4, w.reshape(N, 1, 1, K).contiguous(), bias, 1, 0, precision, act=act, return_pair=True)
+        w4 = w.reshape(N, 1, 1, K)
+        w4 = _to_half_contiguous(w4) if (precision == "amp" and K % 32 == 0) else w4.contiguous()
+        y4, xp = conv_any(x4, w4, bias, 1, 0, precision, act=act, return_pair=True)
         y = y4.reshape(*x.shape[:-1], N)
         keep_pair = xp is not None and wgrad_on_tensor_cores(x4.shape, y4.shape, 1, 1, 1, 0, precision)
         ctx.save_for_backward(xp if keep_pair else x, w, y if act == ops.ACT_RELU else None)
@@ -471,7 +484,8 @@ class LinearFn(torch.autograd.Function):
         gp = tc_operand(g2, precision) if (keep_pair or (precision in ("fp32_tc", "amp") and N % 32 == 0 and g2.shape[2] >= 64 and ctx.needs_input_grad[0])) else None
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = conv_any(g2, w.t().contiguous().reshape(K, 1, 1, N), None, 1, 0, precision, x_pair=gp).reshape(xshape)
+            wt = _to_half_contiguous(w.t()) if (precision == "amp" and N % 32 == 0) else w.t().contiguous()
+            dx = conv_any(g2, wt.reshape(K, 1, 1, N), None, 1, 0, precision, x_pair=gp).reshape(xshape)
         if ctx.needs_input_grad[1]:
             if keep_pair:
                 dw = weight_grad(None, g2, 1, 1, 1, 0, precision, x_pair=saved, dy_pair=gp).reshape(N, K)
