@@ -160,6 +160,35 @@ __global__ void resize_bilinear_kernel(const T* __restrict__ x, int B, int H, in
   }
 }
 
+// Image resize of the pre-processing step (processor/base_processor.py:284-294: F.interpolate(images, size, mode="bilinear", align_corners=False) on the float image): a
+// whole batch of decoded images - uint8 NHWC [B,H,W,3] or float NCHW [B,3,H,W] - straight to the model's float NCHW input, one launch, no padded intermediate.  Same
+// source-index arithmetic and interpolation order as resize_bilinear_kernel above.
+template <bool U8_NHWC>
+__global__ void image_resize_kernel(const void* __restrict__ img, int B, int H, int W, float* __restrict__ out, int Ho, int Wo, float sh, float sw) {
+  const int64_t total = (int64_t)B * Ho * Wo;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int wo = i % Wo, ho = (i / Wo) % Ho, b = i / ((int64_t)Wo * Ho);
+    const float fh = fmaxf(((float)ho + 0.5f) * sh - 0.5f, 0.f), fw = fmaxf(((float)wo + 0.5f) * sw - 0.5f, 0.f);
+    const int h0 = (int)fh, w0 = (int)fw;
+    const int h1 = h0 + (h0 < H - 1 ? 1 : 0), w1 = w0 + (w0 < W - 1 ? 1 : 0);
+    const float lh1 = fh - (float)h0, lh0 = 1.f - lh1, lw1 = fw - (float)w0, lw0 = 1.f - lw1;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float v00, v01, v10, v11;
+      if (U8_NHWC) {
+        const uint8_t* p = reinterpret_cast<const uint8_t*>(img) + (int64_t)b * H * W * 3 + c;
+        v00 = (float)p[((int64_t)h0 * W + w0) * 3]; v01 = (float)p[((int64_t)h0 * W + w1) * 3];
+        v10 = (float)p[((int64_t)h1 * W + w0) * 3]; v11 = (float)p[((int64_t)h1 * W + w1) * 3];
+      } else {
+        const float* p = reinterpret_cast<const float*>(img) + ((int64_t)b * 3 + c) * H * W;
+        v00 = p[(int64_t)h0 * W + w0]; v01 = p[(int64_t)h0 * W + w1];
+        v10 = p[(int64_t)h1 * W + w0]; v11 = p[(int64_t)h1 * W + w1];
+      }
+      out[(((int64_t)b * 3 + c) * Ho + ho) * Wo + wo] = lh0 * (lw0 * v00 + lw1 * v01) + lh1 * (lw0 * v10 + lw1 * v11);
+    }
+  }
+}
+
 __global__ void resize_bilinear_h8_kernel(const __half* __restrict__ x, int B, int H, int W, int C, int x_pitch, __half* __restrict__ out,
                                           int Ho, int Wo, int out_pitch, float sh, float sw) {
   const int cv = C / 8;
@@ -366,6 +395,16 @@ extern "C" int fb200_resize_bilinear(const void* x, int dtype, int B, int H, int
   }
   FB_DISPATCH_DTYPE(dtype, T, (resize_bilinear_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, B, H, W, C, x_pitch, (T*)out, Ho, Wo, out_pitch, sh, sw)));
   FB_CHECK_LAUNCH("resize_bilinear");
+  return FB200_OK;
+}
+
+extern "C" int fb200_image_resize(const void* images, int u8_nhwc, int B, int H, int W, float* out_nchw, int Ho, int Wo, void* stream) {
+  FB_CHECK_ARG(images && out_nchw && B > 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0, "image_resize: bad arguments");
+  const float sh = (float)H / (float)Ho, sw = (float)W / (float)Wo;
+  const int64_t total = (int64_t)B * Ho * Wo;
+  if (u8_nhwc) image_resize_kernel<true><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(images, B, H, W, out_nchw, Ho, Wo, sh, sw);
+  else image_resize_kernel<false><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(images, B, H, W, out_nchw, Ho, Wo, sh, sw);
+  FB_CHECK_LAUNCH("image_resize");
   return FB200_OK;
 }
 

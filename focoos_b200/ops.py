@@ -64,7 +64,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = (
-    "fb200_last_error", "fb200_version", "fb200_device_supports_tcgen05", "fb200_set_option", "fb200_set_conv_trace", "fb200_stem_conv3x3s2", "fb200_stem_conv3x3s2_u8", "fb200_conv2d", "fb200_conv2d_per_image_weights", "fb200_linear_rowmax",
+    "fb200_last_error", "fb200_version", "fb200_device_supports_tcgen05", "fb200_set_option", "fb200_set_conv_trace", "fb200_stem_conv3x3s2", "fb200_stem_conv3x3s2_u8", "fb200_conv2d", "fb200_conv2d_per_image_weights", "fb200_linear_rowmax", "fb200_image_resize",
     "fb200_split_f32_pair", "fb200_conv2d_pair", "fb200_pair_pool", "fb200_linear_rowmax_pair",
     "fb200_maxpool3x3s2", "fb200_avgpool2x2_ceil", "fb200_resize_bilinear", "fb200_add", "fb200_layernorm",
     "fb200_attention", "fb200_attention_split", "fb200_msda", "fb200_row_select", "fb200_rowmax", "fb200_topk", "fb200_gather_rows",
@@ -188,6 +188,13 @@ class CudaBackend:
         self._call("fb200_conv2d_pair", _p(xh), B, H, W, C, _pitch(xh), ctypes.c_int64(x.lo_off), _p(w3), KH, KW, stride, pad, _p(scale), _p(bias), _p(rh),
                    0 if rh is None else _pitch(rh), ctypes.c_int64(residual.lo_off if (out_pair and residual is not None) else 0), act, _p(oh), F16PAIR if out_pair else F32,
                    _pitch(oh, True), ctypes.c_int64(out.lo_off if out_pair else 0), ctypes.c_int64(_batch_stride(oh)), Cout, _stream())
+
+    def image_resize(self, images, out):
+        self._cuda(images, out)
+        u8 = images.dtype == torch.uint8
+        B = images.shape[0]
+        H, W = (images.shape[1], images.shape[2]) if u8 else (images.shape[2], images.shape[3])
+        self._call("fb200_image_resize", _p(images), 1 if u8 else 0, B, H, W, _p(out), out.shape[2], out.shape[3], _stream())
 
     def pair_pool(self, mode, x, out):
         xh, oh = x.hi, out.hi
@@ -517,6 +524,16 @@ def conv2d_pair(x: Pair, w3, scale=None, bias=None, *, stride=1, pad=0, act=ACT_
     if residual is not None:
         assert isinstance(residual, Pair) == isinstance(out, Pair) and tuple(residual.shape) == tuple(out.shape)
     _be().conv2d_pair(x, w3, scale, bias, stride, pad, act, residual, out)
+    return out
+
+
+def image_resize(images, size: Tuple[int, int]):
+    """a batch of decoded images - uint8 NHWC [B,H,W,3] or float32 NCHW [B,3,H,W] - resized (bilinear, align_corners=False on the float values, like the reference's
+    F.interpolate in processor/base_processor.py:284-294) to float32 NCHW [B,3,size[0],size[1]] in ONE launch."""
+    images = images.contiguous()
+    assert (images.dtype == torch.uint8 and images.dim() == 4 and images.shape[3] == 3) or (images.dtype == torch.float32 and images.dim() == 4 and images.shape[1] == 3)
+    out = torch.empty((images.shape[0], 3, int(size[0]), int(size[1])), dtype=torch.float32, device=images.device)
+    _be().image_resize(images, out)
     return out
 
 

@@ -74,18 +74,12 @@ class DETRProcessor:
         if _is_u8_nhwc_batch(inputs):  # one H2D copy for the whole batch
             x = inputs.to(device, non_blocking=True)
             if target_size is not None and tuple(x.shape[1:3]) != tuple(target_size):
-                x4 = torch.zeros((*x.shape[:3], 4), dtype=dtype, device=x.device)
-                x4[..., :3] = x
-                x = ops.resize_bilinear(x4, target_size)[..., :3]  # float from here on
-            if x.dtype == torch.uint8:
-                return x.contiguous()  # FAIDetr's stem kernel reads uint8 NHWC directly (no float CHW copy)
-            return x.permute(0, 3, 1, 2).to(dtype).contiguous()
+                return ops.image_resize(x, target_size).to(dtype)  # one launch: uint8 NHWC batch -> resized float NCHW (the model's float input)
+            return x.contiguous()  # FAIDetr's stem kernel reads uint8 NHWC directly (no float CHW copy)
         if _is_nchw_batch(inputs):  # one H2D copy, one batched resize
             x = (torch.from_numpy(np.ascontiguousarray(inputs)) if isinstance(inputs, np.ndarray) else inputs).to(device, non_blocking=True).to(dtype)
             if target_size is not None and tuple(x.shape[-2:]) != tuple(target_size):
-                x4 = torch.zeros((x.shape[0], x.shape[2], x.shape[3], 4), dtype=dtype, device=x.device)
-                x4[..., :3] = x.permute(0, 2, 3, 1)
-                x = ops.resize_bilinear(x4, target_size)[..., :3].permute(0, 3, 1, 2)
+                x = ops.image_resize(x.float(), target_size).to(dtype)
             return x.contiguous()
         if not isinstance(inputs, (list, tuple)):
             inputs = [inputs]
@@ -111,6 +105,8 @@ class DETRProcessor:
     def _resize(img_nchw: torch.Tensor, size):
         """bilinear, align_corners=False, via the NHWC resize kernel (channels padded 3 -> 4 for vector access)."""
         _, C, H, W = img_nchw.shape
+        if C == 3 and img_nchw.dtype == torch.float32:
+            return ops.image_resize(img_nchw, size)
         x = torch.zeros((1, H, W, 4), dtype=img_nchw.dtype, device=img_nchw.device)
         x[..., :C] = img_nchw.permute(0, 2, 3, 1)
         y = ops.resize_bilinear(x, size)

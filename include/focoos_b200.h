@@ -126,6 +126,10 @@ int fb200_avgpool2x2_ceil(const void* x, int dtype, int B, int H, int W, int C, 
 int fb200_resize_bilinear(const void* x, int dtype, int B, int H, int W, int C, int x_pitch, void* out, int Ho, int Wo,
                           int out_pitch, void* stream);
 
+/* ---- a13 / f1: the resize of the pre-processing step (processor/base_processor.py:284-294, F.interpolate(..., mode="bilinear", align_corners=False) on the float
+ * image) for a whole batch in one launch: images = uint8 NHWC [B,H,W,3] (u8_nhwc = 1) or float NCHW [B,3,H,W] (0) -> out_nchw float [B,3,Ho,Wo]. */
+int fb200_image_resize(const void* images, int u8_nhwc, int B, int H, int W, float* out_nchw, int Ho, int Wo, void* stream);
+
 /* ---- elementwise: out = a + b (b broadcast over the leading `rows/brows` blocks when brows < rows).
  * with_pos_embed (nn/layers/transformer.py:579-581, modelling.py:918-919). */
 int fb200_add(const void* a, const void* b, void* out, int dtype, int64_t rows, int64_t brows, int C, void* stream);

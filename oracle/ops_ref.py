@@ -85,6 +85,10 @@ class RefBackend:
         y = xp.float().reshape(-1, K) @ w.reshape(w.shape[0], K).t()
         out.copy_((y + (bias if bias is not None else 0.0)).max(-1).values)
 
+    def image_resize(self, images, out):
+        x = images.permute(0, 3, 1, 2).float() if images.dtype == torch.uint8 else images.float()
+        out.copy_(F.interpolate(x, size=tuple(out.shape[2:]), mode="bilinear", align_corners=False))
+
     def pair_pool(self, mode, x, out):
         v = x.float().permute(0, 3, 1, 2)
         if mode == 0:

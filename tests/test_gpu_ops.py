@@ -317,3 +317,19 @@ def test_msda_pair_rows_equal_the_split_fp32_output():
     out = ops.msda(value, oa, ref, shapes, P, heads)
     op = ops.msda(value, oa, ref, shapes, P, heads, out_pair=True)
     assert _pair_eq(op, out)
+
+
+@pytest.mark.parametrize("B,H,W,size", [(3, 480, 640, (640, 640)), (2, 720, 1280, (640, 640)), (1, 333, 500, (800, 800)), (2, 64, 48, (96, 160))])
+def test_image_resize_matches_interpolate(B, H, W, size):
+    """fb200_image_resize (the pre-processing resize of a whole batch in one launch) vs F.interpolate(bilinear, align_corners=False) on the float image - what the
+    reference runs (processor/base_processor.py:284-294) - for uint8 NHWC and float NCHW inputs, up- and down-scaling."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(5)
+    u8 = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8)
+    ref = F.interpolate(u8.permute(0, 3, 1, 2).float(), size=size, mode="bilinear", align_corners=False)
+    got = ops.image_resize(u8.cuda(), size)
+    assert got.shape == ref.shape and got.dtype == torch.float32
+    assert float((got.cpu() - ref).abs().max()) <= 2e-4, float((got.cpu() - ref).abs().max())
+    f32 = u8.permute(0, 3, 1, 2).float().contiguous()
+    got2 = ops.image_resize(f32.cuda(), size)
+    assert torch.equal(got2, got), "uint8 NHWC and float NCHW inputs of the same image must give the same result"
