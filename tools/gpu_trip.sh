@@ -47,6 +47,7 @@ for s in $STAGES; do
     ablib) timeout 900 python tools/ab_lib.py focoos_b200/lib/libfocoos_b200_r01.so $(ls focoos_b200/lib/libfocoos_b200_*.so | grep -v r01) focoos_b200/lib/libfocoos_b200.so > gpurun_out/ab_lib.txt 2>&1 ;;
     ddp2) timeout 1500 python -m pytest tests/test_gpu_train_ddp.py -q -m gpu -s 2>&1 | tail -15 > gpurun_out/t_ddp2.log ;;
     bench2) timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 2 --steps 20 --warmup 3 --no-other-configs > gpurun_out/bench_2gpu.log 2> gpurun_out/bench_2gpu.err ;;
+    bench4) timeout 1800 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29543 bench.py --gpus 4 --steps 20 --warmup 3 --no-other-configs > gpurun_out/bench_4gpu.log 2> gpurun_out/bench_4gpu.err ;;
     bench8) timeout 1800 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus 8 --steps 20 --warmup 3 --no-other-configs > gpurun_out/bench_8gpu.log 2> gpurun_out/bench_8gpu.err ;;
     benchdefault) (time timeout 1500 python bench.py) > gpurun_out/bench_default.log 2> gpurun_out/bench_default.err ;;
     ncu_list32) timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_fp32_tc.csv python tools/profile_step.py fp32_tc > gpurun_out/ncu_list_fp32_tc.log 2>&1 ;;
