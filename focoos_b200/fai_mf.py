@@ -283,9 +283,14 @@ class MFEngine(DetrEngine):
         """PredictionHeads.forward (:69-112) -> (class logits fp32 or None, mask logits NHWC [B,h4,w4,Qp], (mask, allowed) or None)."""
         A, dt = self.algo, self.dt
         B, Q, d = out.shape
-        dn = ops.layernorm(out, *self.head_norm)
-        cls = self.classifier(dn, out_dtype=torch.float32, algo=ops.ALGO_SIMT) if want_class else None
-        me = self.mask_mlp[2](self.mask_mlp[1](self.mask_mlp[0](dn, act=ops.ACT_RELU, algo=A), act=ops.ACT_RELU, algo=A), algo=A)  # [B,Q,256]
+        if getattr(self, "_fused_glue", False):  # fp32_tc: LayerNorm writes the pair operand of the mask MLP, whose hidden layers stay in the pair format
+            dn, dnp, _ = ops.layernorm_ex(out, *self.head_norm, want_f32=want_class)
+            cls = self.classifier(dn, out_dtype=torch.float32, algo=ops.ALGO_SIMT) if want_class else None
+            me = self._plin(self.mask_mlp[2], self._plin(self.mask_mlp[1], self._plin(self.mask_mlp[0], dnp, act=ops.ACT_RELU, out_pair=True), act=ops.ACT_RELU, out_pair=True))
+        else:
+            dn = ops.layernorm(out, *self.head_norm)
+            cls = self.classifier(dn, out_dtype=torch.float32, algo=ops.ALGO_SIMT) if want_class else None
+            me = self.mask_mlp[2](self.mask_mlp[1](self.mask_mlp[0](dn, act=ops.ACT_RELU, algo=A), act=ops.ACT_RELU, algo=A), algo=A)  # [B,Q,256]
         _, h4, w4, C = mask_features.shape
         Qp = (Q + 7) // 8 * 8
         masks = torch.zeros((B, h4, w4, Qp), dtype=dt, device=out.device)
@@ -377,11 +382,32 @@ class MFEngine(DetrEngine):
         Q = cfg.num_queries
         out = self.query_feat.unsqueeze(0).expand(B, Q, d).contiguous()
         qpos = self.query_embed
+        # fused row glue (csrc/head_fused.cu, the kernels of the fai-detr head): every LayerNorm writes the pair operand(s) of the linears behind it - LN(x) and
+        # LN(x) + query_pos in one launch - and the FFN / mask-MLP hidden layers stay in the pair format: no add / split launches between two tensor-core linears
+        lins = [b_[k] for b_ in self.dec for k in ("cq", "cout", "sqk", "sv", "sout", "l1", "l2")] + list(self.mask_mlp)
+        self._fused_glue = bool(pair_kv and self.fused_glue and all(getattr(l_, "w3", None) is not None for l_ in lins))
         _, masks, attn = self._heads(out, mask_features, sizes[0], False)
         L = len(self.dec)
         cls = None
         for i, blk in enumerate(self.dec):
             lvl = i % nl
+            if self._fused_glue:
+                _, _, tq = ops.layernorm_ex(out, *blk["cn"], pos=qpos, want_f32=False, want_pair=False, want_pair_pos=True)
+                q = self._plin(blk["cq"], tq)
+                kk, vv = self._plin(blk["ck"], kpos_p[lvl], out_pair=True), self._plin(blk["cv"], srcs_p[lvl], out_pair=True)
+                a = ops.attention_masked(q, kk, vv, attn[0], attn[1], nh, scale, split=True)
+                out = self._plin(blk["cout"], ops.to_pair(a), residual=out)
+                _, t2p, t2pp = ops.layernorm_ex(out, *blk["sn"], pos=qpos, want_f32=False, want_pair=True, want_pair_pos=True)
+                qk = self._plin(blk["sqk"], t2pp)
+                a = ops.attention(qk[..., :d], qk[..., d:], self._plin(blk["sv"], t2p), nh, scale, split=True, out_pair=True)
+                out = self._plin(blk["sout"], a, residual=out)
+                _, t2p, _ = ops.layernorm_ex(out, *blk["fn"], want_f32=False)
+                out = self._plin(blk["l2"], self._plin(blk["l1"], t2p, act=ops.ACT_RELU, out_pair=True), residual=out)
+                last = i == L - 1
+                cls, masks, attn = self._heads(out, mask_features, None if last else sizes[(i + 1) % nl], last)
+                if taps is not None:
+                    taps[f"dec{i}_out"] = out
+                continue
             t2 = ops.layernorm(out, *blk["cn"])
             q = blk["cq"](ops.add(t2, qpos), algo=A)
             if pair_kv:  # K / V projections write the fp16 [hi | lo] pairs the attention kernel stages with plain 16-byte copies
@@ -404,7 +430,7 @@ class MFEngine(DetrEngine):
             taps.update(pred_logits=cls, pred_masks=masks)  # masks: NHWC [B,h4,w4,Qp] pre-sigmoid logits
         probs = ops.softmax_drop_last(cls)
         lazy = LazyMasks(masks, Q, (H, W))
-        self._mf_pair = None
+        self._mf_pair, self._fused_glue = None, False
         return probs, (lazy if self.lazy_masks else lazy.materialize())
 
 
