@@ -346,13 +346,17 @@ class MFEngine(DetrEngine):
         src = ops.layernorm(src, *self.enc_norm)
         y = self.layer[4](src.reshape(B, h, w, d), algo=A)
         ms = [y]
+        # fp32_tc: the 1/4-resolution layer feeds only the mask_features conv, whose output is only ever read as a tensor-core operand (the per-image mask product):
+        # both stay in the pair format - no fp32 copy of the two largest activations of the pixel decoder, no split pass over them
+        chain = pair and getattr(self.layer[1], "w3", None) is not None and getattr(self.mask_features, "w3", None) is not None
         for idx, f in ((3, res4), (2, res3), (1, res2)):
-            y = self.layer[idx](ops.upsample_nearest_add(y, in_conv(self.adapter[idx], f)), algo=A)
+            u = ops.upsample_nearest_add(y, in_conv(self.adapter[idx], f))
+            y = self._pc(self.layer[idx], u) if (chain and idx == 1) else self.layer[idx](u, algo=A)
             if len(ms) < 3:
                 ms.append(y)
-        mask_features = self.mask_features(y, algo=A)
+        mask_features = self._pc(self.mask_features, y) if chain else self.mask_features(y, algo=A)
         if taps is not None:
-            taps.update(res5=res5.float() if pair else res5, enc_memory=src.reshape(B, h, w, d), mask_features=mask_features, multi_scale=ms)
+            taps.update(res5=res5.float() if pair else res5, enc_memory=src.reshape(B, h, w, d), mask_features=mask_features.float() if chain else mask_features, multi_scale=ms)
         return self._run_decoder(ms, mask_features, B, H, W, taps)
 
     def _run_decoder(self, ms, mask_features, B, H, W, taps=None):
@@ -363,7 +367,9 @@ class MFEngine(DetrEngine):
         scale = 1.0 / math.sqrt(d // nh)
         nl = len(ms)
         self._mf_pair = None
-        if (self.precision == "fp32_tc" and A == ops.ALGO_AUTO and mask_features.dtype == torch.float32 and mask_features.shape[-1] % 64 == 0
+        if isinstance(mask_features, ops.Pair):  # written as a pair by its conv (MFEngine.forward)
+            self._mf_pair = (mask_features, mask_features.buf)
+        elif (self.precision == "fp32_tc" and A == ops.ALGO_AUTO and mask_features.dtype == torch.float32 and mask_features.shape[-1] % 64 == 0
                 and (ops._backend is not None or ops.supports_tcgen05_cached())):
             self._mf_pair = (mask_features, ops.split_pair(mask_features))  # consumed by every _heads call of this forward
         srcs, kpos, sizes = [], [], []
