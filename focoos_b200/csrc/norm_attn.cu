@@ -665,8 +665,10 @@ __global__ void __launch_bounds__(384) attention_mma_split_stream_kernel(const f
 
 int attention_mma_split_stream(const float* q, int q_pitch, const void* k, int k_pitch, const void* v, int v_pitch, int kv_pair, int kv_lo_off, const uint8_t* mask, int MP,
                                const int* allowed, float* out, int out_pitch, int B, int Lq, int Lk, int heads, float scale, cudaStream_t st) {
-  // two query blocks per (batch, head) for the 100-query decoders: 256 CTAs of 4 warps, two per SM, so one CTA's chunk staging overlaps the other's MMAs
-  const int nblk = (int)cdiv(Lq, 64);
+
+  static int qb = -1;  // FB200_MATTN_QB: upper bound of queries per CTA (multiple of 16); tuning knob
+  if (qb < 0) { const char* e = getenv("FB200_MATTN_QB"); qb = e ? atoi(e) : 128; if (qb < 16 || qb > 192) qb = 128; }  // one CTA per (batch, head) for the 100-query decoders: K / V staged once (trip 52: 3.12 ms vs 3.31 at 64, 7.15 at 32)
+  const int nblk = (int)cdiv(Lq, qb);
   const int NW = (int)cdiv(cdiv(Lq, nblk), 16);
   static bool configured = false;
   if (!configured) {

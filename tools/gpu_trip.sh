@@ -23,6 +23,7 @@ for s in $STAGES; do
     ncu_stem) timeout 900 ncu --set full --clock-control none --import-source on -k regex:stem_conv_tiled -c 1 -o gpurun_out/prof_stem python tools/profile_step.py fp32_tc > gpurun_out/ncu_stem.log 2>&1 ;;
     stem2) FB200_STEM_TILED=2 timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_stem2.csv python tools/profile_step.py fp32_tc > gpurun_out/ncu_list_stem2.log 2>&1; FB200_STEM_TILED=2 timeout 600 python -m pytest tests/test_gpu_ops.py -q -m gpu -k stem 2>&1 | tail -3 > gpurun_out/t_stem2.log ;;
     headtrace) timeout 300 python tools/head_trace.py > gpurun_out/head_trace.txt 2>&1 ;;
+    mattnqb) (for qb in 32 48 64 112; do echo "### FB200_MATTN_QB=$qb"; FB200_MATTN_QB=$qb FB200_BENCH_PRECISION=fp32_tc FB200_BENCH_PARITY_MODE=0 timeout 300 python tools/bench_mf.py | grep -E 'images_per_s|attention_masked'; done; true) > gpurun_out/mattn_qb.txt 2>&1 ;;
     wgmicro) python tools/wgrad_micro.py > gpurun_out/wgrad_micro.txt 2>&1 ;;
     wgncu) timeout 900 ncu --set full --clock-control none --import-source on -k regex:wgrad_tc_kernel -s 3 -c 1 -o gpurun_out/prof_wgrad python tools/wgrad_micro.py fpn_rep_3x3_80 > gpurun_out/wgrad_ncu.log 2>&1 ;;
     microres) (python tools/conv_micro.py s0_2c_res s1_2c_res s2_2c_res; FB200_TC_RES_TMA=0 python tools/conv_micro.py s0_2c_res s1_2c_res s2_2c_res; true) > gpurun_out/conv_micro_res.txt 2>&1 ;;
