@@ -123,3 +123,25 @@ def test_box_ap_evaluator_known_answer():
     ev.process([gt], shifted)  # class 0: IoU 0.8 -> hit for thresholds .50-.80 (7 of 10); class 1: miss
     r = ev.evaluate()["bbox"]
     assert r["AP50"] == pytest.approx(50.0) and r["AP"] == pytest.approx(35.0)
+
+
+def test_preprocess_resizes_a_whole_batch_like_interpolate(ref_backend):
+    """DETRProcessor.preprocess with image_size set: a uint8 NHWC batch, a float NCHW batch and a list of differently sized images all come out as the float NCHW
+    tensor F.interpolate(bilinear, align_corners=False) gives per image (processor/base_processor.py:284-294) - one image_resize call per batch / image."""
+    import torch.nn.functional as F
+    from focoos_b200 import DETRConfig, DETRProcessor
+
+    proc = DETRProcessor(DETRConfig(), image_size=64)
+    g = torch.Generator().manual_seed(3)
+    u8 = torch.randint(0, 256, (3, 48, 80, 3), generator=g, dtype=torch.uint8)
+    ref = F.interpolate(u8.permute(0, 3, 1, 2).float(), size=(64, 64), mode="bilinear", align_corners=False)
+    x, _ = proc.preprocess(u8, device=torch.device("cpu"))
+    assert x.dtype == torch.float32 and tuple(x.shape) == (3, 3, 64, 64) and torch.allclose(x, ref, atol=1e-4)
+    x2, _ = proc.preprocess(u8.permute(0, 3, 1, 2).float().contiguous(), device=torch.device("cpu"))
+    assert torch.allclose(x2, ref, atol=1e-4)
+    imgs = [np.asarray(u8[0]), np.asarray(torch.randint(0, 256, (100, 60, 3), generator=g, dtype=torch.uint8))]
+    x3, _ = proc.preprocess(imgs, device=torch.device("cpu"))
+    assert tuple(x3.shape) == (2, 3, 64, 64) and torch.allclose(x3[0], ref[0], atol=1e-4)
+    same = torch.randint(0, 256, (2, 64, 64, 3), generator=g, dtype=torch.uint8)
+    x4, _ = proc.preprocess(same, device=torch.device("cpu"))
+    assert x4.dtype == torch.uint8 and tuple(x4.shape) == (2, 64, 64, 3), "a batch that already has the model size stays uint8 NHWC (the stem kernel reads it directly)"
